@@ -1,0 +1,286 @@
+/*
+ * plume_b200.h -- C ABI of libplume_b200.so: the B200 (sm_100a) data-parallel hot path of
+ * su1phurd/UAV-WRF-LES-PPO-LSTM (vectorised plume rollout + PPO update).
+ *
+ * The reference has no FFI: its boundary is three duck-typed Python surfaces
+ * (environment.py reset/step, model.py actor/critic/LSTM forward, train_ppo*.py
+ * _update_model).  Every entry point below replaces the arithmetic of one of those
+ * reference functions for a whole batch of environments; the citation next to each
+ * declaration names it (paths are relative to the reference root, PPOV2.1 unless noted).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch types.  Unless a parameter is documented as
+ *    HOST, every pointer is a DEVICE pointer on the current CUDA device.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
+ *    launches are asynchronous on that stream; nothing synchronises unless stated.
+ *  - every function returns 0 on success, non-zero on error; plume_last_error() gives
+ *    the message of the last failure on the calling thread.
+ *  - there is no CPU fallback: without a CUDA device the calls fail.
+ */
+#ifndef PLUME_B200_H
+#define PLUME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLUME_B200_ABI_VERSION 1
+
+#define PLUME_OBS_DIM 6          /* environment.py:80-87 */
+#define PLUME_NUM_ACTIONS 5      /* environment.py:23 */
+#define PLUME_INFO_DIM 5         /* environment.py:170-176 */
+#define PLUME_VISIT_STRIDE 104   /* 10x10 visit counters (uint16) padded to 13 x 16 B */
+#define PLUME_MAX_GRID_DIVISIONS 10
+
+/* field_mode */
+#define PLUME_FIELD_PROCEDURAL 0 /* no field in memory: cells are evaluated from the Philox stream */
+#define PLUME_FIELD_F32 1        /* conc/tke materialised as float  [N,G,G] */
+#define PLUME_FIELD_F64 2        /* conc/tke materialised as double [N,G,G] (reference layout, environment.py:62-63) */
+
+/* flags of plume_env_step / plume_rollout */
+#define PLUME_FLAG_AUTO_RESET 1u     /* finished envs are reset inside the call (procedural mode) */
+#define PLUME_FLAG_GREEDY 2u         /* argmax actions (evaluate_with_lstm.py:65) instead of sampling */
+#define PLUME_FLAG_STOP_TERMINATES 4u /* a stop-head decision ends the episode (evaluate_with_lstm.py:77-80) */
+
+/* Constants of one reference version (PPOV x/config.py; environment.py). HOST struct. */
+typedef struct plume_env_config {
+    int32_t grid_size;            /* config.py:6 */
+    int32_t max_steps;            /* config.py:7 (V1.1: 5000) */
+    int32_t grid_divisions;       /* config.py:27 */
+    int32_t field_mode;           /* PLUME_FIELD_* */
+    double conc_peak;             /* config.py:8,13 */
+    double turbulence_intensity;  /* config.py:9 */
+    double sigma;                 /* config.py:12; V2.0/V1.1: grid/16 (PPOV2.0/environment.py:54) */
+    double clip_hi;               /* environment.py:112; V1.1: grid-1e-6 (PPOV1.1/environment.py:105) */
+    double conc_reward_coef;      /* config.py:38 */
+    double tke_penalty_factor;    /* config.py:39 */
+    double boundary_penalty;      /* config.py:40 */
+    double boundary_decay_start;  /* config.py:41 */
+    double initial_radius;        /* config.py:31 */
+    uint64_t seed;                /* Philox key */
+} plume_env_config;
+
+/* Struct-of-arrays state of n_envs environments (DEVICE pointers, HOST struct).
+ * Replaces the attributes of MethaneEnv (environment.py:20-50). */
+typedef struct plume_env_state {
+    int32_t n_envs;
+    int32_t env_id_base;          /* global id of env 0 (rank * n_envs): Philox counters use global ids */
+    float* pos_x;                 /* agent_pos after astype(float32), environment.py:113 */
+    float* pos_y;
+    double* src_x;                /* source_pos, environment.py:44 */
+    double* src_y;
+    int32_t* step_count;          /* environment.py:47,90 */
+    int32_t* episode_idx;         /* number of resets so far (Philox counter, episode index output) */
+    uint16_t* visited;            /* [n_envs][PLUME_VISIT_STRIDE], environment.py:38,136 */
+    double* radius;               /* current_radius latched at reset, environment.py:32; model.py:189 */
+    double* explore_bonus;        /* explore_bonus latched at reset, environment.py:39; model.py:190 */
+    void* conc_field;             /* [n_envs][G][G] float/double or NULL (procedural) */
+    void* tke_field;              /* idem */
+    const double* sin_tab;        /* [G] sin(0.05 x), environment.py:59 */
+    const double* cos_tab;        /* [G] cos(0.07 y) */
+    const double* curriculum;     /* [2] = {current_radius, explore_bonus} that resets latch (model.py:189-190) */
+} plume_env_state;
+
+/* ---- library ------------------------------------------------------------------------- */
+int plume_abi_version(void);
+const char* plume_last_error(void);
+/* HOST outputs: SM count, compute capability. */
+int plume_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- P0 reset: MethaneEnv.reset, environment.py:42-50 -------------------------------- */
+/* Resets the envs listed in env_list (int32[n_list] device, NULL = all n_envs): draws the
+ * source (Philox TAG_SRC) unless u_src (double[n_list][2], the two rand() of :44) is given,
+ * zeroes position/step/visit table, bumps episode_idx, latches the curriculum scalars.
+ * Materialised fields are NOT regenerated here (call plume_generate_fields next). */
+int plume_env_reset(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_list,
+                    int32_t n_list, const double* u_src, void* stream);
+
+/* ---- P1 _generate_plume, environment.py:52-63 ----------------------------------------- */
+/* Writes conc/tke fields of the listed envs (field_mode F32 or F64) from the Philox field
+ * stream of each env's current episode.  Optionally also dumps the raw draws
+ * z_out/u_out (float[n_list][G][G] each, may be NULL) so a CPU oracle can rebuild the
+ * identical field. */
+int plume_generate_fields(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_list,
+                          int32_t n_list, float* z_out, float* u_out, void* stream);
+
+/* Noise draws of individual cells: z_out/u_out float[n] for (env_local[i], x[i], y[i]) at the
+ * env's current episode (what a procedural lookup of that cell uses). */
+int plume_field_noise_at(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_local,
+                         const int32_t* x, const int32_t* y, int32_t n, float* z_out, float* u_out, void* stream);
+
+/* ---- P3 _get_obs, environment.py:71-87 ------------------------------------------------- */
+/* obs float[n_envs][6]. */
+int plume_env_observe(const plume_env_config* cfg, const plume_env_state* st, float* obs, void* stream);
+
+/* ---- P2 MethaneEnv.step, environment.py:89-178 ----------------------------------------- */
+/* One lockstep step of all n_envs.
+ *  actions      int32[n_envs]
+ *  step_noise   double[n_envs][2] = the randn(2) of :108, or NULL to draw from Philox TAG_STEP
+ *  obs          float[n_envs][6]   observation after the step (after the reset if auto-reset fired)
+ *  reward       double[n_envs]     (the reference returns float64)
+ *  done,reached uint8[n_envs]
+ *  info         float[5][n_envs]   concentration_reward, explore_reward, move_penalty, tke_penalty,
+ *                                  boundary_penalty (may be NULL)
+ *  final_obs    float[n_envs][6]   pre-reset observation, written when auto-reset (may be NULL)
+ *  noise_out    double[n_envs][2]  the step noise actually used (may be NULL)
+ */
+int plume_env_step(const plume_env_config* cfg, const plume_env_state* st, const int32_t* actions,
+                   const double* step_noise, uint32_t flags, float* obs, double* reward, uint8_t* done,
+                   uint8_t* reached, float* info, float* final_obs, double* noise_out, void* stream);
+
+/* ---- P4 PPOActorCritic.forward, model.py:38-46 ----------------------------------------- */
+/* Flat parameter layout (floats), each block padded to 4 floats:
+ *   feature.0.weight[256][6] feature.0.bias[256] feature.1.weight[256] feature.1.bias[256]
+ *   feature.3.weight[128][256] feature.3.bias[128] feature.4.weight[128] feature.4.bias[128]
+ *   actor.weight[5][128] actor.bias[5](+3) critic.weight[1][128] critic.bias[1](+3) */
+#define PLUME_MLP_IN 6
+#define PLUME_MLP_H1 256
+#define PLUME_MLP_H2 128
+#define PLUME_OFF_W1 0
+#define PLUME_OFF_B1 1536
+#define PLUME_OFF_G1 1792
+#define PLUME_OFF_BE1 2048
+#define PLUME_OFF_W2 2304
+#define PLUME_OFF_B2 35072
+#define PLUME_OFF_G2 35200
+#define PLUME_OFF_BE2 35328
+#define PLUME_OFF_WA 35456
+#define PLUME_OFF_BA 36096
+#define PLUME_OFF_WC 36104
+#define PLUME_OFF_BC 36232
+#define PLUME_MLP_PARAMS 36236   /* padded size of the flat buffer */
+
+/* probs float[B][5], value float[B]; nan_flag int32[1] is set to 1 if any logit is NaN
+ * (model.py:41-43 raises RuntimeError("NaN in model output")). */
+int plume_policy_forward(const float* params, const float* x, int32_t batch, float* probs, float* value,
+                         int32_t* nan_flag, void* stream);
+
+/* P4s: forward + Categorical sample/log_prob (train_ppo2.0.py:161-162,185).
+ *  uniforms float[B] in [0,1) for the inverse-CDF draw, or NULL: Philox TAG_ACT keyed by the
+ *  env state (then B must equal st->n_envs); forced_actions int32[B] (may be NULL) overrides the
+ *  draw (action-trace replay); flags: PLUME_FLAG_GREEDY. */
+int plume_policy_act(const plume_env_config* cfg, const plume_env_state* st, const float* params,
+                     const float* obs, int32_t batch, const float* uniforms, const int32_t* forced_actions,
+                     uint32_t flags, int32_t* actions, float* logp, float* value, float* probs,
+                     int32_t* nan_flag, void* stream);
+
+/* ---- P4L LSTM stop heads ---------------------------------------------------------------- */
+/* V2.1 PeakAndStopPredictor (evaluate_with_lstm.py:11-27): single-layer LSTM(1->H) from zero
+ * state over windows float[B][T] (already divided by 100), torch parameter layouts:
+ * w_ih[4H][1], w_hh[4H][H], b_ih[4H], b_hh[4H] (gate order i,f,g,o), fc_peak w[H] b[1],
+ * fc_stop w[H] b[1].  Outputs peak[B], stop_prob[B]. H in {32,64,128}. */
+int plume_lstm_stop_head(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                         const float* w_peak, const float* b_peak, const float* w_stop, const float* b_stop,
+                         int32_t hidden, const float* windows, int32_t batch, int32_t steps, float* peak,
+                         float* stop_prob, void* stream);
+
+/* Generic multi-layer LSTM (input size 1) over windows float[B][T] from zero state; writes the
+ * top layer's last hidden state float[B][H] (V2.0 ConcentrationThresholdPredictor,
+ * PPOV2.0/model.py:203-240).  params: per layer l: w_ih (4H x in_l), w_hh (4H x H), b_ih, b_hh
+ * concatenated in that order. */
+int plume_lstm_forward(const float* params, int32_t layers, int32_t hidden, const float* windows,
+                       int32_t batch, int32_t steps, float* h_out, void* stream);
+
+/* P4t trend features, model.py:113-127: conc float[B][W] (raw 0..100), last position float[B][2],
+ * source double[B][2] -> out float[B][4] = {label, trend_score, dist_score, conc_score}. */
+int plume_trend_features(const float* conc, int32_t batch, int32_t window, const float* pos_last,
+                         const double* src, double conc_peak, float* out, void* stream);
+
+/* ---- fused rollout: train_ppo2.0.py:156-192 + evaluate_with_lstm.py:61-82 ---------------- */
+typedef struct plume_lstm_params {        /* V2.1 stop head, DEVICE pointers; hidden = 0 disables the head */
+    int32_t hidden;
+    int32_t window;                       /* evaluate_with_lstm.py:42 */
+    float threshold;                      /* evaluate_with_lstm.py:77 */
+    const float *w_ih, *w_hh, *b_ih, *b_hh, *w_peak, *b_peak, *w_stop, *b_stop;
+} plume_lstm_params;
+
+typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major unless noted */
+    float* obs;            /* [T][N][6]  state fed to the policy at step t */
+    int32_t* actions;
+    float* rewards;        /* float(reward), model.py:152 */
+    float* values;
+    float* log_probs;
+    float* dones;          /* float(done), model.py:155 */
+    uint8_t* reached;      /* trajectory[-1]['reached'], environment.py:167 */
+    float* stop_prob;      /* LSTM stop probability (0 while the window is not full), may be NULL */
+    uint8_t* stop_flag;    /* stop_prob > threshold, may be NULL */
+    float* peak_pred;      /* may be NULL */
+    float* trend;          /* [T][N][4] trend features over the stop window, may be NULL */
+    float* info;           /* [T][5][N] reward components, may be NULL */
+    int32_t* episode_idx;  /* [T][N] episode index the transition belongs to, may be NULL */
+    const int32_t* forced_actions; /* [T][N] action-trace replay, may be NULL */
+    const double* step_noise;      /* [T][N][2] injected randn(2), may be NULL */
+    double* noise_out;             /* [T][N][2] the randn(2) actually used, may be NULL */
+    float* conc_window;    /* [N][window] ring of obs[2] inside the current episode (persistent state) */
+    int32_t* window_fill;  /* [N] samples in the ring (persistent state) */
+    float* last_obs;       /* [N][6] observation each env will act on next (persistent state, in/out) */
+} plume_rollout_buffers;
+
+/* T lockstep iterations of: policy forward + sample, env step, stop head, auto-reset; one
+ * persistent kernel, procedural field mode only. nan_flag as in plume_policy_forward. */
+int plume_rollout(const plume_env_config* cfg, const plume_env_state* st, const float* mlp_params,
+                  const plume_lstm_params* lstm, const plume_rollout_buffers* buf, int32_t horizon,
+                  uint32_t flags, int32_t* nan_flag, void* stream);
+
+/* ---- P5 GAE + normalisation, train_ppo2.0.py:17-39 -------------------------------------- */
+/* Per-env reverse scan over [T][N] (the reference's quirks kept: self-bootstrap at T-1, mask with
+ * dones[t+1]); writes raw advantages and accumulates {sum, sum of squares, count} of them into
+ * stats double[3] (caller zeroes; all-reduce it across ranks for global statistics). */
+int plume_gae_scan(const float* rewards, const float* values, const float* dones, int32_t horizon,
+                   int32_t n_envs, double gamma, double lam, float* advantages, double* stats, void* stream);
+/* adv = (adv-mean)/(std_unbiased+1e-6) (std := 1 if <1e-6 or NaN); returns = adv + values (sic, :39). */
+int plume_gae_normalise(float* advantages, const float* values, int64_t count, const double* stats,
+                        float* returns, void* stream);
+
+/* ---- P6/P7 PPO minibatch update, train_ppo2.0.py:42-87 ---------------------------------- */
+typedef struct plume_ppo_batch {          /* DEVICE pointers over the flat [M] transition set */
+    int64_t total;                        /* M = T*N */
+    const float* obs;                     /* [M][6] */
+    const int32_t* actions;
+    const float* old_log_probs;
+    const float* advantages;
+    const float* returns;
+    const float* old_values;
+} plume_ppo_batch;
+
+/* Forward + loss + backward of one minibatch: samples are perm[i] for i in [mb_start, mb_start+mb_size)
+ * if perm (int64[M] device) is given, else the stateless bijection keyed by (perm_seed, epoch).
+ * Accumulates d(loss)/d(params) into grads float[PLUME_MLP_PARAMS] (caller zeroes) and
+ * {loss, policy_loss, value_loss, entropy} sums into loss_out double[4] scaled by 1/mb_size_global.
+ * mb_size_global is the divisor of the means (= mb_size on one GPU; sum over ranks otherwise). */
+int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int64_t* perm, uint64_t perm_seed,
+                   int32_t epoch, int64_t mb_start, int64_t mb_size, int64_t mb_size_global, float clip_eps,
+                   float entropy_beta, float* grads, double* loss_out, int32_t* nan_flag, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* bytes of workspace plume_ppo_grad needs for a minibatch of mb_size samples */
+int64_t plume_ppo_workspace_bytes(int64_t mb_size);
+
+/* clip_grad_norm_(0.5) + Adam (train_ppo2.0.py:86-87,113): global L2 norm over grads, scale by
+ * max_norm/(norm+1e-6) if norm > max_norm, Adam(lr, b1, b2, eps) bias-corrected with `step`
+ * (1-based).  grad_norm_out float[1] (may be NULL). */
+int plume_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t n,
+                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
+                    float* grad_norm_out, void* stream);
+
+/* The index permutation plume_ppo_grad uses when perm == NULL: out int64[count] = positions
+ * [start, start+count) of the bijection of [0,total) keyed by (seed, epoch). */
+int plume_permutation(int64_t total, uint64_t seed, int32_t epoch, int64_t start, int64_t count, int64_t* out,
+                      void* stream);
+
+/* ---- P8 curriculum, model.py:188-221 ----------------------------------------------------- */
+/* Applies PPOTrainer.update once per finished episode of a [T][N] segment in canonical order
+ * (step-major, then env index), on the device.  state double[8 + window]:
+ * {trainer_radius, trainer_explore_bonus, env_radius, env_explore_bonus, history_len,
+ *  history_successes, episodes_total, successes_total, ring...}; curriculum double[2] receives the
+ * values the next resets latch. */
+int plume_curriculum_update(const float* dones, const uint8_t* reached, int32_t horizon, int32_t n_envs,
+                            double* state, double* curriculum, double initial_radius, double min_radius,
+                            double radius_decay, double success_threshold, int32_t window,
+                            double decay_factor, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLUME_B200_H */

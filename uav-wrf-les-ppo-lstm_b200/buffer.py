@@ -1,0 +1,80 @@
+"""Device-resident rollout buffer: the batched form of ``PPOBuffer`` (PPOV2.1/model.py:132-173).
+
+The reference appends python scalars to six lists and converts them to CPU tensors in
+``get()``.  Here the six arrays live in HBM as ``[T, N]`` struct-of-arrays (step-major, env
+fastest) which is what the rollout kernel writes, what the GAE scan reads along ``T`` and what
+the minibatch gather indexes as a flat ``[T*N]`` set.  ``store/get/clear/len(states)`` keep the
+reference's call pattern (train_ppo2.0.py:182-191)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class PPOBuffer:
+    def __init__(self, horizon: int = 256, num_envs: int = 1, device="cuda", with_info: bool = False,
+                 with_stop: bool = True, with_trend: bool = False, with_episode: bool = True):
+        self.horizon, self.num_envs, self.device = int(horizon), int(num_envs), torch.device(device)
+        T, N, dev = self.horizon, self.num_envs, self.device
+        z = lambda dt, *s: torch.zeros(*s, dtype=dt, device=dev)
+        self.obs = z(torch.float32, T, N, _lib.OBS_DIM)
+        self.actions = z(torch.int32, T, N)
+        self.rewards = z(torch.float32, T, N)
+        self.values = z(torch.float32, T, N)
+        self.log_probs = z(torch.float32, T, N)
+        self.dones = z(torch.float32, T, N)
+        self.reached = z(torch.uint8, T, N)
+        self.stop_prob = z(torch.float32, T, N) if with_stop else None
+        self.stop_flag = z(torch.uint8, T, N) if with_stop else None
+        self.peak_pred = z(torch.float32, T, N) if with_stop else None
+        self.trend = z(torch.float32, T, N, 4) if with_trend else None
+        self.info = z(torch.float32, T, _lib.INFO_DIM, N) if with_info else None
+        self.episode_idx = z(torch.int32, T, N) if with_episode else None
+        self.advantages = z(torch.float32, T, N)
+        self.returns = z(torch.float32, T, N)
+        self.filled = 0          # rows written
+
+    # -- reference API ----------------------------------------------------------------------
+    def clear(self) -> None:
+        self.filled = 0
+
+    def store(self, state, action, reward, value, log_prob, done) -> None:
+        """Appends one lockstep row (each argument ``[N]``-shaped, ``state`` ``[N,6]``)."""
+        t = self.filled
+        if t >= self.horizon:
+            raise IndexError("PPOBuffer is full: call clear() after update_model()")
+        dev = self.device
+        self.obs[t] = torch.as_tensor(state, dtype=torch.float32, device=dev).reshape(self.num_envs, -1)
+        self.actions[t] = torch.as_tensor(action, device=dev).to(torch.int32).reshape(self.num_envs)
+        self.rewards[t] = torch.as_tensor(reward, device=dev).to(torch.float32).reshape(self.num_envs)
+        self.values[t] = torch.as_tensor(value, device=dev).to(torch.float32).reshape(self.num_envs)
+        self.log_probs[t] = torch.as_tensor(log_prob, device=dev).to(torch.float32).reshape(self.num_envs)
+        self.dones[t] = torch.as_tensor(done, device=dev).to(torch.float32).reshape(self.num_envs)
+        self.filled = t + 1
+
+    @property
+    def states(self) -> torch.Tensor:
+        """Flat ``[filled*N, 6]`` view; ``len(buffer.states)`` counts transitions like the
+        reference's list (train_ppo2.0.py:189)."""
+        return self.obs[: self.filled].reshape(-1, _lib.OBS_DIM)
+
+    def get(self):
+        """(states, actions, rewards, values, log_probs, dones) flattened step-major."""
+        t = self.filled
+        return (self.obs[:t].reshape(-1, _lib.OBS_DIM), self.actions[:t].reshape(-1).long(),
+                self.rewards[:t].reshape(-1), self.values[:t].reshape(-1), self.log_probs[:t].reshape(-1),
+                self.dones[:t].reshape(-1))
+
+    def __len__(self) -> int:
+        return self.filled * self.num_envs
+
+    # -- C view -----------------------------------------------------------------------------
+    def c_rollout_buffers(self, conc_window, window_fill, last_obs, forced_actions=None, step_noise=None,
+                          noise_out=None) -> _lib.RolloutBuffers:
+        p = _lib.ptr
+        return _lib.RolloutBuffers(p(self.obs), p(self.actions), p(self.rewards), p(self.values), p(self.log_probs),
+                                   p(self.dones), p(self.reached), p(self.stop_prob), p(self.stop_flag),
+                                   p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
+                                   p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
+                                   p(last_obs))

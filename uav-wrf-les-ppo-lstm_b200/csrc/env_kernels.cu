@@ -1,0 +1,370 @@
+// env_kernels.cu -- batched plume environment: reset (P0), field generation (P1/K1),
+// observation (P3) and the lockstep step (P2/K2).  Reference: PPOV2.1/environment.py.
+//
+// Layout: struct-of-arrays env state (one float/double/int array per attribute, index = env),
+// so a warp stepping 32 consecutive envs issues fully coalesced 128 B / 256 B requests.
+// Materialised fields are [N][G][G] with y fastest (the reference's field[x, y]).
+//
+// Algorithmic bytes (DESIGN.md "K1"/"K2"):
+//   K1 generate : 2 fields x G*G x sizeof(T) written per env-reset (2.0 MB float, 4.0 MB double)
+//   K2 step     : per env-step read pos 8 + src 16 + step 4 + episode 4 + radius 8 + bonus 8 +
+//                 action 4 + visit 2 = 54 B, write pos 8 + step 4 + visit 2 + obs 24 + reward 8 +
+//                 done 1 + reached 1 = 48 B  => 102 B (+20 B info, +16 B injected noise,
+//                 +4 field gathers x sizeof(T) in the materialised modes)
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace plume {
+
+std::string& last_error_ref() {
+    static thread_local std::string err;
+    return err;
+}
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return 1;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return cached;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: field generation
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+    static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    }
+};
+template <>
+struct Vec4<double> {
+    static __device__ __forceinline__ void store(double* p, double a, double b, double c, double d) {
+        reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+        reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+    }
+};
+
+// float instantiation: single-precision evaluation of env:53-63 (the float field is an
+// approximation of the float64 reference field by construction)
+__device__ __forceinline__ void cell_f32(const Cfg& c, float sx, float sy, int x, int y, float z, float u, float sinx,
+                                         float cosy, float& conc, float& tke) {
+    const float ddx = (float)x - sx, ddy = (float)y - sy;
+    const float d2 = ddx * ddx + ddy * ddy;
+    const float base = (float)c.conc_peak * expf(-d2 / (float)c.two_sigma_sq);
+    tke = (float)c.ti * ((fabsf(z) + 0.3f * sinx * cosy) + 0.2f * u);
+    conc = fminf(fmaxf(base + tke, 0.0f), (float)c.conc_peak);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) generate_fields_kernel(Cfg c, plume_env_state st, const int32_t* env_list,
+                                                              int blocks_per_env, float* z_out, float* u_out) {
+    const int li = blockIdx.x / blocks_per_env;
+    const int quad = (blockIdx.x - li * blocks_per_env) * blockDim.x + threadIdx.x;
+    const int cells = c.G * c.G;
+    if (quad * 4 >= cells) return;
+    const int env = env_list ? env_list[li] : li;
+    const uint32_t gid = (uint32_t)(st.env_id_base + env);
+    const uint32_t episode = (uint32_t)st.episode_idx[env];
+    const double sx = st.src_x[env], sy = st.src_y[env];
+    const int cell0 = quad * 4;
+    const int x = cell0 / c.G, y = cell0 - x * c.G;    // G % 4 == 0: the 4 cells share the row
+
+    const U4 ra = philox4x32_10((uint32_t)(cell0 >> 1), episode, gid, kTagField, c.k0, c.k1);
+    const U4 rb = philox4x32_10((uint32_t)(cell0 >> 1) + 1u, episode, gid, kTagField, c.k0, c.k1);
+    float z[4], u[4];
+    box_muller(ra.x, ra.y, z[0], z[1]);
+    box_muller(rb.x, rb.y, z[2], z[3]);
+    u[0] = uniform24(ra.z);
+    u[1] = uniform24(ra.w);
+    u[2] = uniform24(rb.z);
+    u[3] = uniform24(rb.w);
+
+    T conc[4], tke[4];
+    const double sinx = st.sin_tab[x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if constexpr (sizeof(T) == 8) {
+            double cc, tt;
+            plume_cell(c, sx, sy, x, y + k, (double)z[k], (double)u[k], sinx, st.cos_tab[y + k], cc, tt);
+            conc[k] = cc;
+            tke[k] = tt;
+        } else {
+            float cc, tt;
+            cell_f32(c, (float)sx, (float)sy, x, y + k, z[k], u[k], (float)sinx, (float)st.cos_tab[y + k], cc, tt);
+            conc[k] = cc;
+            tke[k] = tt;
+        }
+    }
+    const size_t off = (size_t)env * cells + cell0;
+    Vec4<T>::store(reinterpret_cast<T*>(st.conc_field) + off, conc[0], conc[1], conc[2], conc[3]);
+    Vec4<T>::store(reinterpret_cast<T*>(st.tke_field) + off, tke[0], tke[1], tke[2], tke[3]);
+    if (z_out) {
+        const size_t o2 = (size_t)li * cells + cell0;
+        *reinterpret_cast<float4*>(z_out + o2) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4*>(u_out + o2) = make_float4(u[0], u[1], u[2], u[3]);
+    }
+}
+
+// dump-only variant (no field pointers needed): the draws of the listed envs
+__global__ void __launch_bounds__(256) dump_noise_kernel(Cfg c, plume_env_state st, const int32_t* env_list,
+                                                         int blocks_per_env, float* z_out, float* u_out) {
+    const int li = blockIdx.x / blocks_per_env;
+    const int quad = (blockIdx.x - li * blocks_per_env) * blockDim.x + threadIdx.x;
+    const int cells = c.G * c.G;
+    if (quad * 4 >= cells) return;
+    const int env = env_list ? env_list[li] : li;
+    const uint32_t gid = (uint32_t)(st.env_id_base + env);
+    const uint32_t episode = (uint32_t)st.episode_idx[env];
+    const int cell0 = quad * 4;
+    const U4 ra = philox4x32_10((uint32_t)(cell0 >> 1), episode, gid, kTagField, c.k0, c.k1);
+    const U4 rb = philox4x32_10((uint32_t)(cell0 >> 1) + 1u, episode, gid, kTagField, c.k0, c.k1);
+    float z[4];
+    box_muller(ra.x, ra.y, z[0], z[1]);
+    box_muller(rb.x, rb.y, z[2], z[3]);
+    const size_t o2 = (size_t)li * cells + cell0;
+    *reinterpret_cast<float4*>(z_out + o2) = make_float4(z[0], z[1], z[2], z[3]);
+    *reinterpret_cast<float4*>(u_out + o2) =
+        make_float4(uniform24(ra.z), uniform24(ra.w), uniform24(rb.z), uniform24(rb.w));
+}
+
+__global__ void noise_at_kernel(Cfg c, plume_env_state st, const int32_t* env_local, const int32_t* x,
+                                const int32_t* y, int n, float* z_out, float* u_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int env = env_local[i];
+    float z, u;
+    field_noise(c, (uint32_t)(st.env_id_base + env), (uint32_t)st.episode_idx[env], x[i], y[i], z, u);
+    z_out[i] = z;
+    u_out[i] = u;
+}
+
+// ---------------------------------------------------------------------------------------
+// P0 reset
+// ---------------------------------------------------------------------------------------
+__global__ void reset_kernel(Cfg c, plume_env_state st, const int32_t* env_list, int n_list, const double* u_src) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_list) return;
+    const int env = env_list ? env_list[li] : li;
+    EnvRegs e = load_env(st, env);
+    env_reset(c, (uint32_t)(st.env_id_base + env), e, st.visited + (size_t)env * PLUME_VISIT_STRIDE,
+              u_src ? u_src + 2 * (size_t)li : nullptr, st.curriculum[0], st.curriculum[1]);
+    store_env(st, env, e);
+}
+
+// ---------------------------------------------------------------------------------------
+// P3 observe
+// ---------------------------------------------------------------------------------------
+template <typename Field>
+__global__ void observe_kernel(Cfg c, plume_env_state st, Field f, float* obs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n_envs) return;
+    const EnvRegs e = load_env(st, i);
+    float o[6];
+    observe(c, f, i, (uint32_t)(st.env_id_base + i), e, st.visited + (size_t)i * PLUME_VISIT_STRIDE, o);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) obs[(size_t)i * 6 + k] = o[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: lockstep step, one thread per env
+// ---------------------------------------------------------------------------------------
+template <typename Field>
+__global__ void __launch_bounds__(128) step_kernel(Cfg c, plume_env_state st, Field f, const int32_t* actions,
+                                                   const double* step_noise_in, uint32_t flags, float* obs,
+                                                   double* reward, uint8_t* done, uint8_t* reached, float* info,
+                                                   float* final_obs, double* noise_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n_envs) return;
+    const uint32_t gid = (uint32_t)(st.env_id_base + i);
+    EnvRegs e = load_env(st, i);
+    uint16_t* vis = st.visited + (size_t)i * PLUME_VISIT_STRIDE;
+
+    double z0, z1;
+    if (step_noise_in) {
+        const double2 z = reinterpret_cast<const double2*>(step_noise_in)[i];
+        z0 = z.x;
+        z1 = z.y;
+    } else {
+        step_noise(c, gid, e, z0, z1);
+    }
+    if (noise_out) reinterpret_cast<double2*>(noise_out)[i] = make_double2(z0, z1);
+
+    int px, py;
+    cell32_of(c, e, px, py);
+    double pconc, ptke;
+    f.eval(c, i, gid, e.episode, e.sx, e.sy, px, py, pconc, ptke);
+
+    StepResult r;
+    env_step(c, f, i, gid, e, vis, actions[i], z0, z1, pconc, ptke, r);
+
+    reward[i] = r.reward;
+    done[i] = r.done ? 1 : 0;
+    reached[i] = r.reached ? 1 : 0;
+    if (info) {
+        const int n = st.n_envs;
+        info[0 * (size_t)n + i] = r.conc_reward;
+        info[1 * (size_t)n + i] = r.explore_reward;
+        info[2 * (size_t)n + i] = (float)r.move_penalty;
+        info[3 * (size_t)n + i] = r.tke_penalty;
+        info[4 * (size_t)n + i] = (float)r.boundary_penalty;
+    }
+    if ((flags & PLUME_FLAG_AUTO_RESET) && r.done) {
+        if (final_obs) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) final_obs[(size_t)i * 6 + k] = r.obs[k];
+        }
+        env_reset(c, gid, e, vis, nullptr, st.curriculum[0], st.curriculum[1]);
+        observe(c, f, i, gid, e, vis, r.obs);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) obs[(size_t)i * 6 + k] = r.obs[k];
+    store_env(st, i, e);
+}
+
+}  // namespace plume
+
+using namespace plume;
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+static int check_cfg(const plume_env_config* cfg, const plume_env_state* st) {
+    if (!cfg || !st) return fail("null config/state");
+    if (cfg->grid_size <= 0 || cfg->grid_size % 4 != 0) return fail("grid_size must be a positive multiple of 4");
+    if (cfg->grid_divisions <= 0 || cfg->grid_divisions > PLUME_MAX_GRID_DIVISIONS)
+        return fail("grid_divisions must be in [1,%d]", PLUME_MAX_GRID_DIVISIONS);
+    if (cfg->max_steps <= 0 || cfg->max_steps > 65535) return fail("max_steps must be in [1,65535] (uint16 visit counters)");
+    if (st->n_envs < 0) return fail("negative n_envs");
+    if (cfg->field_mode != PLUME_FIELD_PROCEDURAL && (!st->conc_field || !st->tke_field))
+        return fail("materialised field mode needs conc_field/tke_field");
+    if (!st->sin_tab || !st->cos_tab || !st->curriculum) return fail("sin_tab/cos_tab/curriculum missing");
+    return 0;
+}
+
+extern "C" int plume_abi_version(void) { return PLUME_B200_ABI_VERSION; }
+
+extern "C" const char* plume_last_error(void) { return last_error_ref().c_str(); }
+
+extern "C" int plume_device_info(int32_t* sms, int32_t* major, int32_t* minor) {
+    int dev = 0;
+    PLUME_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    PLUME_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    return 0;
+}
+
+extern "C" int plume_env_reset(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_list,
+                               int32_t n_list, const double* u_src, void* stream) {
+    if (check_cfg(cfg, st)) return 1;
+    if (!env_list) n_list = st->n_envs;
+    if (n_list <= 0) return 0;
+    const Cfg c = make_cfg(*cfg);
+    reset_kernel<<<(n_list + 127) / 128, 128, 0, as_stream(stream)>>>(c, *st, env_list, n_list, u_src);
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plume_generate_fields(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_list,
+                                     int32_t n_list, float* z_out, float* u_out, void* stream) {
+    if (!cfg || !st) return fail("null config/state");
+    if (cfg->grid_size <= 0 || cfg->grid_size % 4 != 0) return fail("grid_size must be a positive multiple of 4");
+    if (!env_list) n_list = st->n_envs;
+    if (n_list <= 0) return 0;
+    PLUME_CHECK_ARG((z_out == nullptr) == (u_out == nullptr), "z_out and u_out must be given together");
+    const Cfg c = make_cfg(*cfg);
+    const int quads = c.G * c.G / 4;
+    const int bpe = (quads + 255) / 256;
+    const long long blocks = (long long)bpe * n_list;
+    PLUME_CHECK_ARG(blocks < 2147483647LL, "too many envs for one launch");
+    cudaStream_t s = as_stream(stream);
+    if (cfg->field_mode == PLUME_FIELD_F32) {
+        PLUME_CHECK_ARG(st->conc_field && st->tke_field, "field pointers missing");
+        generate_fields_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(c, *st, env_list, bpe, z_out, u_out);
+    } else if (cfg->field_mode == PLUME_FIELD_F64) {
+        PLUME_CHECK_ARG(st->conc_field && st->tke_field, "field pointers missing");
+        generate_fields_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(c, *st, env_list, bpe, z_out, u_out);
+    } else {
+        PLUME_CHECK_ARG(z_out != nullptr, "procedural mode: only the noise dump is available");
+        dump_noise_kernel<<<(unsigned)blocks, 256, 0, s>>>(c, *st, env_list, bpe, z_out, u_out);
+    }
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plume_field_noise_at(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_local,
+                                    const int32_t* x, const int32_t* y, int32_t n, float* z_out, float* u_out,
+                                    void* stream) {
+    if (!cfg || !st) return fail("null config/state");
+    if (n <= 0) return 0;
+    const Cfg c = make_cfg(*cfg);
+    noise_at_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(c, *st, env_local, x, y, n, z_out, u_out);
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plume_env_observe(const plume_env_config* cfg, const plume_env_state* st, float* obs, void* stream) {
+    if (check_cfg(cfg, st)) return 1;
+    if (st->n_envs == 0) return 0;
+    const Cfg c = make_cfg(*cfg);
+    const int blocks = (st->n_envs + 127) / 128;
+    cudaStream_t s = as_stream(stream);
+    if (cfg->field_mode == PLUME_FIELD_PROCEDURAL) {
+        observe_kernel<<<blocks, 128, 0, s>>>(c, *st, ProceduralField{st->sin_tab, st->cos_tab}, obs);
+    } else if (cfg->field_mode == PLUME_FIELD_F32) {
+        observe_kernel<<<blocks, 128, 0, s>>>(
+            c, *st, MaterialisedField<float>{(const float*)st->conc_field, (const float*)st->tke_field}, obs);
+    } else {
+        observe_kernel<<<blocks, 128, 0, s>>>(
+            c, *st, MaterialisedField<double>{(const double*)st->conc_field, (const double*)st->tke_field}, obs);
+    }
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plume_env_step(const plume_env_config* cfg, const plume_env_state* st, const int32_t* actions,
+                              const double* step_noise_in, uint32_t flags, float* obs, double* reward, uint8_t* done,
+                              uint8_t* reached, float* info, float* final_obs, double* noise_out, void* stream) {
+    if (check_cfg(cfg, st)) return 1;
+    PLUME_CHECK_ARG(actions && obs && reward && done && reached, "null output/input pointer");
+    if (st->n_envs == 0) return 0;
+    if ((flags & PLUME_FLAG_AUTO_RESET) && cfg->field_mode != PLUME_FIELD_PROCEDURAL)
+        return fail("auto-reset inside the step needs the procedural field mode "
+                    "(materialised fields are regenerated by plume_generate_fields)");
+    const Cfg c = make_cfg(*cfg);
+    const int blocks = (st->n_envs + 127) / 128;
+    cudaStream_t s = as_stream(stream);
+    if (cfg->field_mode == PLUME_FIELD_PROCEDURAL) {
+        step_kernel<<<blocks, 128, 0, s>>>(c, *st, ProceduralField{st->sin_tab, st->cos_tab}, actions, step_noise_in,
+                                           flags, obs, reward, done, reached, info, final_obs, noise_out);
+    } else if (cfg->field_mode == PLUME_FIELD_F32) {
+        step_kernel<<<blocks, 128, 0, s>>>(
+            c, *st, MaterialisedField<float>{(const float*)st->conc_field, (const float*)st->tke_field}, actions,
+            step_noise_in, flags, obs, reward, done, reached, info, final_obs, noise_out);
+    } else {
+        step_kernel<<<blocks, 128, 0, s>>>(
+            c, *st, MaterialisedField<double>{(const double*)st->conc_field, (const double*)st->tke_field}, actions,
+            step_noise_in, flags, obs, reward, done, reached, info, final_obs, noise_out);
+    }
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,218 @@
+// lstm_kernels.cu -- K4: LSTM stop heads (P4L) and trend features (P4t) as standalone batch
+// kernels.  V2.1 PeakAndStopPredictor: PPOV2.1/evaluate_with_lstm.py:11-27; V2.0
+// ConcentrationThresholdPredictor LSTM stack: PPOV2.0/model.py:203-240; trend label:
+// PPOV2.1/model.py:113-127.
+#include "lstm_tile.cuh"
+
+namespace plume {
+
+// ---- V2.1 head, weights in shared memory, 32 windows per tile ------------------------------
+template <int H>
+__global__ void __launch_bounds__(256, 1)
+lstm_stop_head_kernel(LstmWeights w, const float* __restrict__ windows, int batch, int steps,
+                      float* __restrict__ peak, float* __restrict__ stop_prob) {
+    extern __shared__ __align__(16) float sm[];
+    lstm_load_weights<H>(sm, w);
+    const int tid = threadIdx.x;
+    const int tiles = (batch + 31) / 32;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int base = tile * 32;
+        __syncthreads();
+        for (int i = tid; i < steps * 32; i += 256) {     // xs[t][s] <- windows[base+s][t]
+            const int s = i / steps, t = i - s * steps;
+            sm[LstmSmem<H>::xs + t * 32 + s] = (base + s < batch) ? windows[(size_t)(base + s) * steps + t] : 0.0f;
+        }
+        __syncthreads();
+        lstm_window_tile<H>(sm, steps);
+        const float v = lstm_heads<H>(sm, steps);
+        if (tid < 64) {
+            const int s = tid & 31;
+            if (base + s < batch) {
+                if (tid < 32) peak[base + s] = v;
+                else stop_prob[base + s] = v;
+            }
+        }
+    }
+}
+
+// ---- generic multi-layer LSTM (any H <= 256), weights streamed from L2 ----------------------
+// One CTA = 8 sequences, one thread per hidden unit.  seq [T][8][H] in shared memory is
+// rewritten in place layer by layer.
+constexpr int kGenTS = 8;
+
+__global__ void lstm_generic_kernel(const float* __restrict__ params, int layers, int H,
+                                    const float* __restrict__ windows, int batch, int steps,
+                                    float* __restrict__ h_out) {
+    extern __shared__ __align__(16) float sm[];
+    float* seq = sm;                              // [steps][8][H]
+    float* xin = sm + (size_t)steps * kGenTS * H; // [steps][8] layer-0 scalar inputs
+    const int j = threadIdx.x;
+    const int base = blockIdx.x * kGenTS;
+    for (int i = j; i < steps * kGenTS; i += blockDim.x) {
+        const int s = i / steps, t = i - s * steps;
+        xin[t * kGenTS + s] = (base + s < batch) ? windows[(size_t)(base + s) * steps + t] : 0.0f;
+    }
+    __syncthreads();
+    const float* p = params;
+    for (int l = 0; l < layers; ++l) {
+        const int in = (l == 0) ? 1 : H;
+        const float* w_ih = p;
+        const float* w_hh = w_ih + (size_t)4 * H * in;
+        const float* b_ih = w_hh + (size_t)4 * H * H;
+        const float* b_hh = b_ih + 4 * H;
+        p = b_hh + 4 * H;
+        float c[kGenTS];
+#pragma unroll
+        for (int s = 0; s < kGenTS; ++s) c[s] = 0.0f;
+        for (int t = 0; t < steps; ++t) {
+            float acc[kGenTS][4];
+            if (j < H) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float b = b_ih[g * H + j] + b_hh[g * H + j];
+#pragma unroll
+                    for (int s = 0; s < kGenTS; ++s) acc[s][g] = b;
+                }
+                if (l == 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float wv = w_ih[g * H + j];
+#pragma unroll
+                        for (int s = 0; s < kGenTS; ++s) acc[s][g] = fmaf(xin[t * kGenTS + s], wv, acc[s][g]);
+                    }
+                } else {
+                    const float* xt = seq + (size_t)t * kGenTS * H;
+                    for (int k = 0; k < H; ++k) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float wv = w_ih[(size_t)(g * H + j) * H + k];
+#pragma unroll
+                            for (int s = 0; s < kGenTS; ++s) acc[s][g] = fmaf(xt[s * H + k], wv, acc[s][g]);
+                        }
+                    }
+                }
+                if (t > 0) {
+                    const float* hp = seq + (size_t)(t - 1) * kGenTS * H;
+                    for (int k = 0; k < H; ++k) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float wv = w_hh[(size_t)(g * H + j) * H + k];
+#pragma unroll
+                            for (int s = 0; s < kGenTS; ++s) acc[s][g] = fmaf(hp[s * H + k], wv, acc[s][g]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();      // everyone has read seq[t] (layer input) before it is overwritten
+            if (j < H) {
+#pragma unroll
+                for (int s = 0; s < kGenTS; ++s) {
+                    const float ig = sigmoidf_acc(acc[s][0]), fg = sigmoidf_acc(acc[s][1]);
+                    const float gg = tanhf(acc[s][2]), og = sigmoidf_acc(acc[s][3]);
+                    c[s] = fmaf(fg, c[s], ig * gg);
+                    seq[((size_t)t * kGenTS + s) * H + j] = og * tanhf(c[s]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (j < H) {
+        for (int s = 0; s < kGenTS; ++s)
+            if (base + s < batch) h_out[(size_t)(base + s) * H + j] = seq[((size_t)(steps - 1) * kGenTS + s) * H + j];
+    }
+}
+
+__global__ void linear_heads_kernel(const float* __restrict__ h, int batch, int H, const float* __restrict__ w_peak,
+                                    const float* __restrict__ b_peak, const float* __restrict__ w_stop,
+                                    const float* __restrict__ b_stop, float* peak, float* stop_prob) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    float a = 0.0f, b = 0.0f;
+    for (int k = 0; k < H; ++k) {
+        const float v = h[(size_t)i * H + k];
+        a = fmaf(v, w_peak[k], a);
+        b = fmaf(v, w_stop[k], b);
+    }
+    peak[i] = a + b_peak[0];
+    stop_prob[i] = sigmoidf_acc(b + b_stop[0]);
+}
+
+// ---- P4t trend features (device function in lstm_tile.cuh) ----
+__global__ void trend_kernel(const float* __restrict__ conc, int batch, int W, const float* __restrict__ pos,
+                             const double* __restrict__ src, double conc_peak, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    trend_features(conc + (size_t)i * W, W, (double)pos[2 * i], (double)pos[2 * i + 1], src[2 * i], src[2 * i + 1],
+                   conc_peak, out + 4 * (size_t)i);
+}
+
+template <int H>
+static int launch_stop_head(const LstmWeights& w, const float* windows, int batch, int steps, float* peak,
+                            float* stop_prob, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = LstmSmem<H>::total * (int)sizeof(float);
+    if (!configured) {
+        if (cudaFuncSetAttribute(lstm_stop_head_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+            return fail("lstm kernel: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    const int tiles = (batch + 31) / 32;
+    int grid = 2 * sm_count();
+    if (grid <= 0) return fail("no CUDA device");
+    if (tiles < grid) grid = tiles;
+    lstm_stop_head_kernel<H><<<grid, 256, smem, s>>>(w, windows, batch, steps, peak, stop_prob);
+    if (cudaGetLastError() != cudaSuccess) return fail("lstm kernel launch failed");
+    return 0;
+}
+
+static int launch_generic(const float* params, int layers, int H, const float* windows, int batch, int steps,
+                          float* h_out, cudaStream_t s) {
+    const size_t smem = ((size_t)steps * kGenTS * H + (size_t)steps * kGenTS) * sizeof(float);
+    if (smem > 227 * 1024) return fail("lstm: window %d x hidden %d does not fit in shared memory", steps, H);
+    if (cudaFuncSetAttribute(lstm_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return fail("lstm generic kernel: cannot reserve %zu B of shared memory", smem);
+    const int threads = ((H + 31) / 32) * 32;
+    lstm_generic_kernel<<<(batch + kGenTS - 1) / kGenTS, threads, smem, s>>>(params, layers, H, windows, batch, steps,
+                                                                             h_out);
+    if (cudaGetLastError() != cudaSuccess) return fail("lstm generic kernel launch failed");
+    return 0;
+}
+
+}  // namespace plume
+
+using namespace plume;
+
+extern "C" int plume_lstm_stop_head(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                    const float* w_peak, const float* b_peak, const float* w_stop, const float* b_stop,
+                                    int32_t hidden, const float* windows, int32_t batch, int32_t steps, float* peak,
+                                    float* stop_prob, void* stream) {
+    PLUME_CHECK_ARG(w_ih && w_hh && b_ih && b_hh && w_peak && b_peak && w_stop && b_stop && windows && peak && stop_prob,
+                    "null pointer");
+    PLUME_CHECK_ARG(steps >= 1 && steps <= kLstmMaxSteps, "window length must be in [1,32]");
+    if (batch <= 0) return 0;
+    const LstmWeights w{w_ih, w_hh, b_ih, b_hh, w_peak, b_peak, w_stop, b_stop};
+    if (hidden == 32) return launch_stop_head<32>(w, windows, batch, steps, peak, stop_prob, as_stream(stream));
+    if (hidden == 64) return launch_stop_head<64>(w, windows, batch, steps, peak, stop_prob, as_stream(stream));
+    return fail("plume_lstm_stop_head: hidden must be 32 or 64 (use plume_lstm_forward for other sizes)");
+}
+
+extern "C" int plume_lstm_forward(const float* params, int32_t layers, int32_t hidden, const float* windows,
+                                  int32_t batch, int32_t steps, float* h_out, void* stream) {
+    PLUME_CHECK_ARG(params && windows && h_out, "null pointer");
+    PLUME_CHECK_ARG(layers >= 1 && layers <= 8, "layers must be in [1,8]");
+    PLUME_CHECK_ARG(hidden >= 1 && hidden <= 256, "hidden must be in [1,256]");
+    PLUME_CHECK_ARG(steps >= 1, "empty window");
+    if (batch <= 0) return 0;
+    return launch_generic(params, layers, hidden, windows, batch, steps, h_out, as_stream(stream));
+}
+
+extern "C" int plume_trend_features(const float* conc, int32_t batch, int32_t window, const float* pos_last,
+                                    const double* src, double conc_peak, float* out, void* stream) {
+    PLUME_CHECK_ARG(conc && pos_last && src && out, "null pointer");
+    PLUME_CHECK_ARG(window >= 2, "window must hold at least 2 samples");
+    if (batch <= 0) return 0;
+    trend_kernel<<<(batch + 127) / 128, 128, 0, as_stream(stream)>>>(conc, batch, window, pos_last, src, conc_peak, out);
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}

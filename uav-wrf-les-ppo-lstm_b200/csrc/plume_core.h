@@ -1,0 +1,384 @@
+// plume_core.h -- per-environment arithmetic shared by every kernel of libplume_b200.
+//
+// Everything here is a __host__ __device__ inline function so that the exact device logic
+// can also be compiled with g++ into the host-side logic tests (tests/host_sim); the
+// product only ever runs the device instantiation.
+//
+// Reference: /root/reference/PPOV2.1/environment.py (cited as env:LINE below).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/plume_b200.h"
+
+#if defined(__CUDACC__)
+#define PLUME_HD __host__ __device__ __forceinline__
+#else
+#define PLUME_HD inline
+#endif
+
+namespace plume {
+
+// ---------------------------------------------------------------------------------------
+// IEEE double arithmetic that the compiler may not contract into FMAs: the position
+// update, the cell truncation and the reached test must be bit-identical to numpy's
+// float64 scalar arithmetic (env:107-117,155-156).
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+PLUME_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+PLUME_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+PLUME_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+PLUME_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+PLUME_HD double dsqrt(double a) { return __dsqrt_rn(a); }
+PLUME_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+PLUME_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+PLUME_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+PLUME_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+#else
+// host build: compiled with -ffp-contract=off
+PLUME_HD double dadd(double a, double b) { return a + b; }
+PLUME_HD double dsub(double a, double b) { return a - b; }
+PLUME_HD double dmul(double a, double b) { return a * b; }
+PLUME_HD double ddiv(double a, double b) { return a / b; }
+PLUME_HD double dsqrt(double a) { return sqrt(a); }
+PLUME_HD float fadd(float a, float b) { return a + b; }
+PLUME_HD float fsub(float a, float b) { return a - b; }
+PLUME_HD float fmul(float a, float b) { return a * b; }
+PLUME_HD float fdiv(float a, float b) { return a / b; }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+constexpr uint32_t kTagSrc = 1, kTagField = 2, kTagStep = 3, kTagAct = 4;
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+PLUME_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+PLUME_HD float uniform24(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }           // [0,1)
+PLUME_HD float uniform24_open0(uint32_t r) { return ((float)(r >> 8) + 1.0f) * 5.9604644775390625e-08f; }  // (0,1]
+PLUME_HD double uniform53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
+}
+
+// Box-Muller in float32; the same function generates the materialised field and the
+// procedural lookups, so both see identical draws.
+PLUME_HD void box_muller(uint32_t r0, uint32_t r1, float& z0, float& z1) {
+    const float u1 = uniform24_open0(r0);
+    const float u2 = uniform24(r1);
+#if defined(__CUDA_ARCH__)
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+#else
+    const float rad = sqrtf(-2.0f * logf(u1));
+    const float s = sinf(6.283185307179586f * u2), c = cosf(6.283185307179586f * u2);
+#endif
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+// ---------------------------------------------------------------------------------------
+// device-side view of the configuration
+// ---------------------------------------------------------------------------------------
+struct Cfg {
+    int32_t G, max_steps, divisions, cell_size, field_mode;
+    double conc_peak, ti, two_sigma_sq, clip_hi, move_step;
+    double conc_coef, tke_factor, bnd_penalty, bnd_start, initial_radius;
+    uint32_t k0, k1;
+};
+
+inline Cfg make_cfg(const plume_env_config& c) {
+    Cfg o;
+    o.G = c.grid_size;
+    o.max_steps = c.max_steps;
+    o.divisions = c.grid_divisions;
+    o.cell_size = c.grid_size / c.grid_divisions;          // env:37
+    o.field_mode = c.field_mode;
+    o.conc_peak = c.conc_peak;
+    o.ti = c.turbulence_intensity;
+    o.two_sigma_sq = 2 * (c.sigma * c.sigma);              // env:56  2*(GAUSSIAN_RADIUS)**2
+    o.clip_hi = c.clip_hi;
+    o.move_step = c.grid_size * 0.05;                      // env:98
+    o.conc_coef = c.conc_reward_coef;
+    o.tke_factor = c.tke_penalty_factor;
+    o.bnd_penalty = c.boundary_penalty;
+    o.bnd_start = c.boundary_decay_start;
+    o.initial_radius = c.initial_radius;
+    o.k0 = (uint32_t)(c.seed & 0xFFFFFFFFu);
+    o.k1 = (uint32_t)(c.seed >> 32);
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// P1: one cell of the plume, env:53-63.  `z`,`u` are the cell's randn/rand draws.
+// ---------------------------------------------------------------------------------------
+PLUME_HD void plume_cell(const Cfg& c, double sx, double sy, int x, int y, double z, double u, double sinx,
+                         double cosy, double& conc, double& tke) {
+    const double ddx = dsub((double)x, sx), ddy = dsub((double)y, sy);
+    const double dist = dsqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));          // env:54
+    const double base = dmul(c.conc_peak, exp(ddiv(-dmul(dist, dist), c.two_sigma_sq)));   // env:56
+    const double wave = dmul(dmul(0.3, sinx), cosy);                          // env:59
+    tke = dmul(c.ti, dadd(dadd(fabs(z), wave), dmul(0.2, u)));                // env:57-61,63
+    const double v = dadd(base, tke);
+    conc = v < 0.0 ? 0.0 : (v > c.conc_peak ? c.conc_peak : v);               // env:62
+}
+
+// the two draws of cell (x,y) of (env, episode) from the Philox field stream
+PLUME_HD void field_noise(const Cfg& c, uint32_t env_gid, uint32_t episode, int x, int y, float& z, float& u) {
+    const uint32_t cell = (uint32_t)x * (uint32_t)c.G + (uint32_t)y;
+    const U4 r = philox4x32_10(cell >> 1, episode, env_gid, kTagField, c.k0, c.k1);
+    float z0, z1;
+    box_muller(r.x, r.y, z0, z1);
+    const bool odd = cell & 1u;
+    z = odd ? z1 : z0;
+    u = uniform24(odd ? r.w : r.z);
+}
+
+// Field access policies -------------------------------------------------------------------
+struct ProceduralField {
+    const double* sin_tab;
+    const double* cos_tab;
+    PLUME_HD void eval(const Cfg& c, int env_local, uint32_t env_gid, uint32_t episode, double sx, double sy, int x,
+                       int y, double& conc, double& tke) const {
+        (void)env_local;
+        float z, u;
+        field_noise(c, env_gid, episode, x, y, z, u);
+        plume_cell(c, sx, sy, x, y, (double)z, (double)u, sin_tab[x], cos_tab[y], conc, tke);
+    }
+};
+
+template <typename T>
+struct MaterialisedField {
+    const T* conc_field;
+    const T* tke_field;
+    PLUME_HD void eval(const Cfg& c, int env_local, uint32_t, uint32_t, double, double, int x, int y, double& conc,
+                       double& tke) const {
+        const size_t off = ((size_t)env_local * c.G + x) * c.G + y;      // field[x, y], x = first axis
+        conc = (double)conc_field[off];
+        tke = (double)tke_field[off];
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// per-env registers
+// ---------------------------------------------------------------------------------------
+struct EnvRegs {
+    float px, py;        // agent_pos (float32)
+    double sx, sy;       // source_pos
+    int32_t step;        // step_count
+    uint32_t episode;    // episode_idx
+    double radius;       // current_radius (latched)
+    double ebonus;       // explore_bonus (latched)
+};
+
+struct StepResult {
+    float obs[6];
+    double reward;
+    bool done, reached;
+    float conc_reward, explore_reward, tke_penalty;
+    double move_penalty, boundary_penalty;
+    double cur_conc;       // conc at the float64 cell / peak (env:118)
+    double cell_conc, cell_tke;   // field at the float32 cell after the move (what obs[2], obs[3] hold)
+};
+
+PLUME_HD int clip_cell(int v, int G) { return v < 0 ? 0 : (v > G - 1 ? G - 1 : v); }
+
+// vc**0.75 + 1 (env:140): vc^3 is exact in double, two correctly rounded sqrt's.
+PLUME_HD double visit_denominator(int vc) {
+    const double v = (double)vc;
+    return dadd(dsqrt(dsqrt(dmul(dmul(v, v), v))), 1.0);
+}
+
+// P3 _get_obs, env:71-87, given the field values at the float32 cell.
+PLUME_HD void make_obs(const Cfg& c, const EnvRegs& e, double cell_conc, double cell_tke, int visit_here,
+                       float* obs) {
+    const float g = (float)c.G;
+    obs[0] = fdiv(e.px, g);                                                   // env:81
+    obs[1] = fdiv(e.py, g);
+    obs[2] = (float)ddiv(cell_conc, c.conc_peak);                             // env:83
+    obs[3] = (float)ddiv(cell_tke, dmul(c.ti, 3.0));                          // env:84
+    obs[4] = (float)ddiv((double)e.step, (double)c.max_steps);                // env:85
+    const double lvl = ddiv((double)visit_here, 5.0);                         // env:78
+    obs[5] = (float)(lvl < 1.0 ? lvl : 1.0);
+}
+
+PLUME_HD void cell32_of(const Cfg& c, const EnvRegs& e, int& x, int& y) {
+    x = clip_cell((int)e.px, c.G);                                            // env:72-73
+    y = clip_cell((int)e.py, c.G);
+}
+
+template <typename Field>
+PLUME_HD void observe(const Cfg& c, const Field& f, int env_local, uint32_t env_gid, const EnvRegs& e,
+                      const uint16_t* visited, float* obs) {
+    int x, y;
+    cell32_of(c, e, x, y);
+    double conc, tke;
+    f.eval(c, env_local, env_gid, e.episode, e.sx, e.sy, x, y, conc, tke);
+    const int vis = visited[(x / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (y / c.cell_size)];
+    make_obs(c, e, conc, tke, vis, obs);
+}
+
+// P2 MethaneEnv.step, env:89-178.  `visited` points at this env's PLUME_VISIT_STRIDE counters.
+// prev_conc/prev_tke: field at the float32 cell before the move (env:93-95,105-108).
+template <typename Field>
+PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env_gid, EnvRegs& e, uint16_t* visited,
+                       int action, double z0, double z1, double prev_cell_conc, double prev_cell_tke,
+                       StepResult& out) {
+    e.step += 1;                                                              // env:90
+    const double prev_conc = ddiv(prev_cell_conc, c.conc_peak);               // env:95
+    // env:98-102
+    const double ms = c.move_step;
+    double dx = 0.0, dy = 0.0;
+    if (action == 1) dy = ms;
+    else if (action == 2) dy = -ms;
+    else if (action == 3) dx = ms;
+    else if (action == 4) dx = -ms;
+    const double dnorm = (action == 0) ? 0.0 : ms;                            // ||(dx,dy)||, exact
+    const double move_mag = ddiv(dnorm, ms);
+    const double move_penalty = dmul(-0.15, dsub(1.0, move_mag));
+    // env:105-108   move_step*0.2*(randn(2)*tke/(TI*3))
+    const double nine = dmul(c.ti, 3.0);
+    const double gain = dmul(ms, 0.2);
+    const double tx = dmul(gain, ddiv(dmul(z0, prev_cell_tke), nine));
+    const double ty = dmul(gain, ddiv(dmul(z1, prev_cell_tke), nine));
+    // env:111-113
+    double nx = dadd(dadd((double)e.px, dx), tx);
+    double ny = dadd(dadd((double)e.py, dy), ty);
+    nx = nx < 0.0 ? 0.0 : (nx > c.clip_hi ? c.clip_hi : nx);
+    ny = ny < 0.0 ? 0.0 : (ny > c.clip_hi ? c.clip_hi : ny);
+    e.px = (float)nx;
+    e.py = (float)ny;
+    // env:116-119
+    const int cx = clip_cell((int)nx, c.G), cy = clip_cell((int)ny, c.G);
+    int ox, oy;
+    cell32_of(c, e, ox, oy);
+    double conc64, tke64;
+    f.eval(c, env_local, env_gid, e.episode, e.sx, e.sy, cx, cy, conc64, tke64);
+    double conc32 = conc64, tke32 = tke64;
+    if (ox != cx || oy != cy)   // float32 rounding of the position crossed a cell edge (rare)
+        f.eval(c, env_local, env_gid, e.episode, e.sx, e.sy, ox, oy, conc32, tke32);
+    const double cur_conc = ddiv(conc64, c.conc_peak);
+    const double grad = ddiv(dsub(cur_conc, prev_conc), dadd(dnorm, 1e-6));
+    // env:121-131
+    const double G = (double)c.G;
+    const double b0 = ddiv(nx, G), b1 = ddiv(dsub(G, nx), G), b2 = ddiv(ny, G), b3 = ddiv(dsub(G, ny), G);
+    const double bd = fmin(fmin(b0, b1), fmin(b2, b3));
+    double bpen = 0.0;
+    if (bd < c.bnd_start && grad < -0.01) {
+        const double gap = dsub(c.bnd_start, bd);
+        bpen = dmul(-c.bnd_penalty, dmul(gap, gap));
+    }
+    // env:134-137  (floor division of the float64 position)
+    const int gx = (int)floor(ddiv(nx, (double)c.cell_size)), gy = (int)floor(ddiv(ny, (double)c.cell_size));
+    const int slot = gx * PLUME_MAX_GRID_DIVISIONS + gy;
+    const int vc = (int)visited[slot] + 1;
+    visited[slot] = (uint16_t)vc;
+    // env:140-143
+    const int vis32 = visited[(ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size)];
+    make_obs(c, e, conc32, tke32, vis32, out.obs);
+    const float explore = fdiv(fmul((float)e.ebonus, fsub(1.0f, out.obs[5])), (float)visit_denominator(vc));
+    // env:146-152 (numpy>=2 promotion: float32 terms, float64 from move_penalty on)
+    const float conc_reward = fmul((float)c.conc_coef, out.obs[2]);
+    const float tke_term = fmul((float)c.tke_factor, out.obs[3]);
+    double total = dadd((double)fadd(conc_reward, explore), move_penalty);
+    total = dsub(total, (double)tke_term);
+    total = dadd(total, bpen);
+    // env:155-158
+    const double ex = dsub((double)e.px, e.sx), ey = dsub((double)e.py, e.sy);
+    const double distance = dsqrt(dadd(dmul(ex, ex), dmul(ey, ey)));
+    const bool reached = distance <= e.radius;
+    if (reached) total = dadd(total, fmin(500.0, dmul(150.0, ddiv(c.initial_radius, e.radius))));
+    out.reward = total;
+    out.reached = reached;
+    out.done = (e.step >= c.max_steps) || reached;                            // env:161
+    out.conc_reward = conc_reward;
+    out.explore_reward = explore;
+    out.tke_penalty = -tke_term;
+    out.move_penalty = move_penalty;
+    out.boundary_penalty = bpen;
+    out.cur_conc = cur_conc;
+    out.cell_conc = conc32;
+    out.cell_tke = tke32;
+}
+
+// P0 reset, env:42-50: source draw, zero position/step, clear visit table, latch curriculum.
+PLUME_HD void env_reset(const Cfg& c, uint32_t env_gid, EnvRegs& e, uint16_t* visited, const double* u_src,
+                        double radius, double ebonus) {
+    e.episode += 1;
+    double ux, uy;
+    if (u_src) {
+        ux = u_src[0];
+        uy = u_src[1];
+    } else {
+        const U4 r = philox4x32_10(0u, e.episode, env_gid, kTagSrc, c.k0, c.k1);
+        ux = uniform53(r.x, r.y);
+        uy = uniform53(r.z, r.w);
+    }
+    const double span = (double)(c.G - 100);                                  // env:43-44
+    e.sx = dadd(dmul(ux, span), 50.0);
+    e.sy = dadd(dmul(uy, span), 50.0);
+    e.px = 0.0f;                                                              // env:46
+    e.py = 0.0f;
+    e.step = 0;                                                               // env:47
+    e.radius = radius;
+    e.ebonus = ebonus;
+    for (int i = 0; i < PLUME_VISIT_STRIDE; ++i) visited[i] = 0;              // env:49
+}
+
+PLUME_HD void step_noise(const Cfg& c, uint32_t env_gid, const EnvRegs& e, double& z0, double& z1) {
+    const U4 r = philox4x32_10((uint32_t)e.step, e.episode, env_gid, kTagStep, c.k0, c.k1);
+    float a, b;
+    box_muller(r.x, r.y, a, b);
+    z0 = (double)a;
+    z1 = (double)b;
+}
+
+PLUME_HD float action_uniform(const Cfg& c, uint32_t env_gid, const EnvRegs& e) {
+    const U4 r = philox4x32_10((uint32_t)e.step, e.episode, env_gid, kTagAct, c.k0, c.k1);
+    return uniform24(r.x);
+}
+
+// ---------------------------------------------------------------------------------------
+// stateless permutation of [0,n): 4-round Feistel over the enclosing power of 4, cycle-walked.
+// Replaces torch.randperm (train_ppo2.0.py:43) without materialising the permutation.
+// ---------------------------------------------------------------------------------------
+PLUME_HD uint64_t feistel_permute(uint64_t idx, uint64_t n, uint64_t seed, uint32_t epoch) {
+    int half_bits = 1;
+    while ((1ull << (2 * half_bits)) < n) ++half_bits;
+    const uint64_t half_mask = (1ull << half_bits) - 1;
+    uint64_t v = idx;
+    do {
+        uint32_t l = (uint32_t)(v >> half_bits), r = (uint32_t)(v & half_mask);
+#pragma unroll
+        for (uint32_t round = 0; round < 4; ++round) {
+            const U4 h = philox4x32_10(r, round, epoch, 0x5045524Du, (uint32_t)seed, (uint32_t)(seed >> 32));
+            const uint32_t nl = r;
+            r = (l ^ h.x) & (uint32_t)half_mask;
+            l = nl;
+        }
+        v = ((uint64_t)l << half_bits) | r;
+    } while (v >= n);
+    return v;
+}
+
+}  // namespace plume

@@ -1,0 +1,262 @@
+// rollout_kernel.cu -- the fused persistent rollout: for a tile of 32 environments one CTA runs
+// T lockstep iterations of
+//     policy forward + Categorical sample   (train_ppo2.0.py:158-162,185; model.py:38-46)
+//     MethaneEnv.step                        (environment.py:89-178)
+//     LSTM stop head over the sliding window (evaluate_with_lstm.py:67-80), trend features
+//     auto-reset of finished episodes        (environment.py:42-50)
+// without returning to the host: MLP (145 KB) and LSTM (17 KB) weights stay in shared memory,
+// the per-env state stays in the registers of the tile's first warp, and only the [T][N]
+// rollout buffers are written to HBM.  Procedural field mode only (cells are evaluated from
+// the Philox stream, so a reset costs O(1)).
+//
+// Algorithmic bytes per env-step (DESIGN.md "rollout"): obs 24 + action 4 + reward 4 + value 4 +
+// logp 4 + done 4 + reached 1 = 45 B written (+ stop 9, info 20, episode 4 when requested),
+// visit-table RMW 4 B; nothing else touches HBM.
+#include "lstm_tile.cuh"
+#include "mlp_tile.cuh"
+
+namespace plume {
+
+struct RolloutArgs {
+    Cfg c;
+    plume_env_state st;
+    const float* mlp;
+    plume_lstm_params lstm;
+    plume_rollout_buffers buf;
+    int horizon;
+    uint32_t flags;
+    int32_t* nan_flag;
+};
+
+template <int H>
+struct RolloutSmem {
+    static constexpr int lstm = MlpSmem::total;
+    static constexpr int misc = lstm + (H > 0 ? LstmSmem<(H > 0 ? H : 32)>::total : kLstmMaxSteps * 32);
+    static constexpr int total = misc + 96;     // [32] stop prob, [32] peak, [32] scratch
+};
+
+template <int H>
+__global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int HH = H > 0 ? H : 32;
+    float* lsm = sm + RolloutSmem<H>::lstm;
+    // the window doubles as the LSTM input xs[t][s]; without a head it is the only part allocated
+    float* win = H > 0 ? lsm + LstmSmem<HH>::xs : lsm;
+    float* s_stop = sm + RolloutSmem<H>::misc;
+    float* s_peak = s_stop + 32;
+
+    const Cfg& c = a.c;
+    const int tid = threadIdx.x;
+    const int N = a.st.n_envs;
+    const int W = a.lstm.window;
+    mlp_load_weights(sm, a.mlp);
+    if (H > 0) {
+        const LstmWeights lw{a.lstm.w_ih, a.lstm.w_hh, a.lstm.b_ih, a.lstm.b_hh,
+                             a.lstm.w_peak, a.lstm.b_peak, a.lstm.w_stop, a.lstm.b_stop};
+        lstm_load_weights<HH>(lsm, lw);
+    }
+    const ProceduralField field{a.st.sin_tab, a.st.cos_tab};
+    const double cur_radius = a.st.curriculum[0], cur_bonus = a.st.curriculum[1];
+    const bool greedy = (a.flags & PLUME_FLAG_GREEDY) != 0;
+    const bool stop_terminates = (a.flags & PLUME_FLAG_STOP_TERMINATES) != 0;
+
+    const int tiles = (N + kTileM - 1) / kTileM;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int env = tile * kTileM + tid;          // meaningful for tid < 32
+        const bool owner = tid < kTileM && env < N;
+        const uint32_t gid = (uint32_t)(a.st.env_id_base + env);
+        EnvRegs e{};
+        uint16_t* vis = nullptr;
+        double cell_conc = 0.0, cell_tke = 0.0;      // field at the float32 cell of the current position
+        int fill = 0;
+        __syncthreads();
+        if (tid < kTileM) {
+            float o[6] = {0, 0, 0, 0, 0, 0};
+            if (owner) {
+                e = load_env(a.st, env);
+                vis = a.st.visited + (size_t)env * PLUME_VISIT_STRIDE;
+                int x, y;
+                cell32_of(c, e, x, y);
+                field.eval(c, env, gid, e.episode, e.sx, e.sy, x, y, cell_conc, cell_tke);
+                make_obs(c, e, cell_conc, cell_tke,
+                         vis[(x / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (y / c.cell_size)], o);
+                fill = a.buf.window_fill ? a.buf.window_fill[env] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sm[MlpSmem::x + tid * 8 + k] = o[k];
+            sm[MlpSmem::x + tid * 8 + 6] = 0.0f;
+            sm[MlpSmem::x + tid * 8 + 7] = 0.0f;
+            for (int k = 0; k < W; ++k)
+                win[k * 32 + tid] = (owner && a.buf.conc_window) ? a.buf.conc_window[(size_t)env * W + k] : 0.0f;
+        }
+
+        for (int t = 0; t < a.horizon; ++t) {
+            const size_t row = (size_t)t * N;
+            // the observation the policy acts on, coalesced [32][6] -> buf.obs[t][tile*32 ..][6]
+            __syncthreads();
+            if (tid < 6 * kTileM) {
+                const int s = tid / 6, k = tid - s * 6;
+                if (tile * kTileM + s < N) a.buf.obs[(row + (size_t)tile * kTileM) * 6 + tid] = sm[MlpSmem::x + s * 8 + k];
+            }
+            mlp_forward_tile<false>(sm);
+            // ---- part A: sample, step, push the window ------------------------------------------------
+            StepResult r{};
+            int action = 0;
+            float logp = 0.0f, value = 0.0f;
+            uint32_t ep_of_transition = e.episode;
+            if (owner) {
+                const float* o = sm + MlpSmem::out + tid * 8;
+                bool bad = false;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) bad |= isnan(o[k]);
+                if (bad) atomicExch(a.nan_flag, 1);
+                float p[5];
+                softmax5(o, p);
+                value = o[5];
+                const int forced = a.buf.forced_actions ? a.buf.forced_actions[row + env] : -1;
+                const float u = (forced < 0 && !greedy) ? action_uniform(c, gid, e) : 0.0f;
+                action = categorical_pick(p, u, greedy, forced, logp);
+                double z0, z1;
+                if (a.buf.step_noise) {
+                    const double2 z = reinterpret_cast<const double2*>(a.buf.step_noise)[row + env];
+                    z0 = z.x;
+                    z1 = z.y;
+                } else {
+                    step_noise(c, gid, e, z0, z1);
+                }
+                if (a.buf.noise_out) reinterpret_cast<double2*>(a.buf.noise_out)[row + env] = make_double2(z0, z1);
+                env_step(c, field, env, gid, e, vis, action, z0, z1, cell_conc, cell_tke, r);
+                cell_conc = r.cell_conc;
+                cell_tke = r.cell_tke;
+                // sliding window of obs[2] (= conc_field[int(x),int(y)]/100 as float32, evaluate_with_lstm.py:67-74)
+                for (int k = 0; k + 1 < W; ++k) win[k * 32 + tid] = win[(k + 1) * 32 + tid];
+                win[(W - 1) * 32 + tid] = r.obs[2];
+                fill = fill < W ? fill + 1 : W;
+            }
+            // ---- LSTM stop head over the window, all threads ------------------------------------------------
+            if (H > 0) {
+                __syncthreads();
+                lstm_window_tile<HH>(lsm, W);
+                const float hv = lstm_heads<HH>(lsm, W);
+                if (tid < 32) s_peak[tid] = hv;
+                else if (tid < 64) s_stop[tid - 32] = hv;
+                __syncthreads();
+            }
+            // ---- part B: stop decision, outputs, auto-reset --------------------------------------------------
+            if (owner) {
+                float stop_p = 0.0f, peak = 0.0f;
+                bool stop = false;
+                if (H > 0 && fill >= W) {                                    // evaluate_with_lstm.py:73
+                    stop_p = s_stop[tid];
+                    peak = s_peak[tid];
+                    stop = stop_p > a.lstm.threshold;                        // :77
+                }
+                const bool done = r.done || (stop_terminates && stop);
+                const size_t i = row + env;
+                a.buf.actions[i] = action;
+                a.buf.rewards[i] = (float)r.reward;
+                a.buf.values[i] = value;
+                a.buf.log_probs[i] = logp;
+                a.buf.dones[i] = done ? 1.0f : 0.0f;
+                a.buf.reached[i] = r.reached ? 1 : 0;
+                if (a.buf.stop_prob) a.buf.stop_prob[i] = stop_p;
+                if (a.buf.stop_flag) a.buf.stop_flag[i] = stop ? 1 : 0;
+                if (a.buf.peak_pred) a.buf.peak_pred[i] = peak;
+                if (a.buf.episode_idx) a.buf.episode_idx[i] = (int32_t)ep_of_transition;
+                if (a.buf.info) {
+                    float* inf = a.buf.info + (size_t)t * 5 * N + env;
+                    inf[0] = r.conc_reward;
+                    inf[(size_t)N] = r.explore_reward;
+                    inf[2 * (size_t)N] = (float)r.move_penalty;
+                    inf[3 * (size_t)N] = r.tke_penalty;
+                    inf[4 * (size_t)N] = (float)r.boundary_penalty;
+                }
+                if (a.buf.trend) {
+                    float tr[4] = {0, 0, 0, 0};
+                    if (fill >= W && W >= 4) {
+                        trend_from_last4(100.0 * (double)win[(W - 4) * 32 + tid], 100.0 * (double)win[(W - 3) * 32 + tid],
+                                         100.0 * (double)win[(W - 2) * 32 + tid], 100.0 * (double)win[(W - 1) * 32 + tid],
+                                         (double)e.px, (double)e.py, e.sx, e.sy, c.conc_peak, tr);
+                    }
+                    *reinterpret_cast<float4*>(a.buf.trend + i * 4) = make_float4(tr[0], tr[1], tr[2], tr[3]);
+                }
+                if (done) {
+                    env_reset(c, gid, e, vis, nullptr, cur_radius, cur_bonus);
+                    fill = 0;
+                    field.eval(c, env, gid, e.episode, e.sx, e.sy, 0, 0, cell_conc, cell_tke);
+                    make_obs(c, e, cell_conc, cell_tke, 0, r.obs);
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sm[MlpSmem::x + tid * 8 + k] = r.obs[k];
+            }
+        }
+        // ---- persist the tile's state ----------------------------------------------------------------------
+        if (owner) {
+            store_env(a.st, env, e);
+            if (a.buf.window_fill) a.buf.window_fill[env] = fill;
+            if (a.buf.conc_window)
+                for (int k = 0; k < W; ++k) a.buf.conc_window[(size_t)env * W + k] = win[k * 32 + tid];
+            if (a.buf.last_obs) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a.buf.last_obs[(size_t)env * 6 + k] = sm[MlpSmem::x + tid * 8 + k];
+            }
+        }
+    }
+}
+
+template <int H>
+static int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = RolloutSmem<H>::total * (int)sizeof(float);
+    if (!configured) {
+        if (cudaFuncSetAttribute(rollout_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return fail("rollout kernel: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    const int tiles = (a.st.n_envs + kTileM - 1) / kTileM;
+    int grid = sm_count();
+    if (grid <= 0) return fail("no CUDA device");
+    if (tiles < grid) grid = tiles;
+    rollout_kernel<H><<<grid, kMlpThreads, smem, s>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return fail("rollout kernel launch failed");
+    return 0;
+}
+
+}  // namespace plume
+
+using namespace plume;
+
+extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state* st, const float* mlp_params,
+                             const plume_lstm_params* lstm, const plume_rollout_buffers* buf, int32_t horizon,
+                             uint32_t flags, int32_t* nan_flag, void* stream) {
+    PLUME_CHECK_ARG(cfg && st && mlp_params && buf && nan_flag, "null pointer");
+    PLUME_CHECK_ARG(cfg->field_mode == PLUME_FIELD_PROCEDURAL,
+                    "the fused rollout needs the procedural field mode (no CPU or materialised fallback)");
+    PLUME_CHECK_ARG(cfg->grid_size > 0 && cfg->grid_size % 2 == 0, "grid_size must be even");
+    PLUME_CHECK_ARG(cfg->grid_divisions > 0 && cfg->grid_divisions <= PLUME_MAX_GRID_DIVISIONS, "grid_divisions");
+    PLUME_CHECK_ARG(cfg->max_steps > 0 && cfg->max_steps <= 65535, "max_steps must fit uint16 visit counters");
+    PLUME_CHECK_ARG(st->sin_tab && st->cos_tab && st->curriculum, "sin_tab/cos_tab/curriculum missing");
+    PLUME_CHECK_ARG(buf->obs && buf->actions && buf->rewards && buf->values && buf->log_probs && buf->dones &&
+                        buf->reached, "null rollout buffer");
+    if (horizon <= 0 || st->n_envs <= 0) return 0;
+    RolloutArgs a;
+    a.c = make_cfg(*cfg);
+    a.st = *st;
+    a.mlp = mlp_params;
+    a.buf = *buf;
+    a.horizon = horizon;
+    a.flags = flags;
+    a.nan_flag = nan_flag;
+    if (lstm && lstm->hidden > 0) {
+        a.lstm = *lstm;
+        PLUME_CHECK_ARG(lstm->window >= 1 && lstm->window <= kLstmMaxSteps, "stop-head window must be in [1,32]");
+        PLUME_CHECK_ARG(lstm->w_ih && lstm->w_hh && lstm->b_ih && lstm->b_hh && lstm->w_peak && lstm->b_peak &&
+                            lstm->w_stop && lstm->b_stop, "null LSTM parameter");
+        if (lstm->hidden == 32) return launch_rollout<32>(a, as_stream(stream));
+        return fail("plume_rollout: fused stop head supports hidden=32 (got %d); use plume_lstm_stop_head "
+                    "for other sizes", lstm->hidden);
+    }
+    a.lstm = plume_lstm_params{};
+    a.lstm.window = (lstm && lstm->window > 0 && lstm->window <= kLstmMaxSteps) ? lstm->window : 20;
+    return launch_rollout<0>(a, as_stream(stream));
+}

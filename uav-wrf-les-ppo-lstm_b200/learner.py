@@ -1,0 +1,208 @@
+"""The learner: ``update_model`` (= ``_update_model``, PPOV2.1/train_ppo2.0.py:14-87), the fused
+clip+Adam optimiser (train_ppo2.0.py:86-87,113) and the curriculum ``PPOTrainer``
+(model.py:178-221).  GAE, the loss/gradient, the optimiser step and the batched curriculum run
+in csrc/learner_kernels.cu and csrc/ppo_kernels.cu; the only collective is one all-reduce of
+the flat gradient per minibatch (plus three doubles for global advantage statistics)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import PlumeConfig, config_for
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class FusedAdam:
+    """``torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8)`` + ``clip_grad_norm_`` in one kernel
+    over the model's flat parameter/gradient buffers."""
+
+    def __init__(self, model_or_params, lr: float = 3e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: float = 0.5):
+        model = model_or_params
+        if not hasattr(model, "flat"):
+            raise TypeError("FusedAdam takes the PPOActorCritic module (its parameters share one flat buffer)")
+        self.model = model
+        self.lr, self.betas, self.eps, self.max_grad_norm = float(lr), tuple(betas), float(eps), float(max_grad_norm)
+        self.exp_avg = torch.zeros_like(model.flat)
+        self.exp_avg_sq = torch.zeros_like(model.flat)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=model.flat.device)
+        self.step_count = 0
+        self.launches = 0
+
+    def zero_grad(self) -> None:
+        self.model.flat_grad.zero_()
+
+    def step(self) -> None:
+        m = self.model
+        self.step_count += 1
+        lib = _lib.load()
+        with torch.cuda.device(m.flat.device):
+            rc = lib.plume_clip_adam(m.flat.data_ptr(), m.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                     self.exp_avg_sq.data_ptr(), _lib.MLP_PARAMS, self.max_grad_norm, self.lr,
+                                     self.betas[0], self.betas[1], self.eps, self.step_count,
+                                     self.grad_norm.data_ptr(), _stream(m.flat.device))
+        _lib.check(rc, "plume_clip_adam")
+        self.launches += 1
+
+    def state_dict(self) -> dict:
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_count,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step"])
+
+
+class UpdateWorkspace:
+    """Scratch memory of the update, allocated once and reused."""
+
+    def __init__(self, device, max_minibatch: int):
+        lib = _lib.load()
+        self.max_minibatch = int(max_minibatch)
+        self.bytes = int(lib.plume_ppo_workspace_bytes(self.max_minibatch))
+        self.ws = torch.empty(self.bytes, dtype=torch.uint8, device=device)
+        self.stats = torch.zeros(3, dtype=torch.float64, device=device)
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_group=None) -> None:
+    """P5: GAE reverse scan per env column + global normalisation; fills ``buffer.advantages``
+    and ``buffer.returns`` (train_ppo2.0.py:17-39)."""
+    lib = _lib.load()
+    T, N, dev = buffer.filled, buffer.num_envs, buffer.device
+    ws.stats.zero_()
+    with torch.cuda.device(dev):
+        _lib.check(lib.plume_gae_scan(buffer.rewards.data_ptr(), buffer.values.data_ptr(), buffer.dones.data_ptr(), T,
+                                      N, cfg.gamma, cfg.lam, buffer.advantages.data_ptr(), ws.stats.data_ptr(),
+                                      _stream(dev)), "plume_gae_scan")
+        if process_group is not None:
+            torch.distributed.all_reduce(ws.stats, group=process_group)
+        _lib.check(lib.plume_gae_normalise(buffer.advantages.data_ptr(), buffer.values.data_ptr(), T * N,
+                                           ws.stats.data_ptr(), buffer.returns.data_ptr(), _stream(dev)),
+                   "plume_gae_normalise")
+
+
+def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms=None,
+                 minibatch_size: int | None = None, workspace: UpdateWorkspace | None = None,
+                 process_group=None, perm_seed: int = 0, check_nan: bool = True, record=None):
+    """Drop-in for ``_update_model(buffer, model, optimizer)`` (train_ppo2.0.py:14-87).
+
+    ``perms``: optional list of ``cfg.epochs`` int64 index permutations of the flat ``[T*N]``
+    transition set (what ``torch.randperm`` gives the reference, :43); by default the kernels use
+    a stateless Feistel bijection keyed by ``(perm_seed, epoch)``.  ``minibatch_size`` defaults
+    to ``cfg.batch_size`` (256).  With ``process_group`` the advantage statistics and the
+    gradient are all-reduced (each rank holds its own envs).  Returns a ``[steps, 4]`` float64
+    device tensor of (loss, policy loss, value loss, entropy) per optimiser step."""
+    cfg = cfg or config_for("2.1")
+    lib = _lib.load()
+    dev = buffer.device
+    T, N = buffer.filled, buffer.num_envs
+    M = T * N
+    if M == 0:
+        return None
+    mb = int(minibatch_size or cfg.batch_size)
+    if workspace is None or workspace.max_minibatch < min(mb, M):
+        workspace = UpdateWorkspace(dev, min(mb, M))
+    world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    compute_advantages(buffer, cfg, workspace, process_group)
+    batch = _lib.PpoBatch(M, buffer.obs.data_ptr(), buffer.actions.data_ptr(), buffer.log_probs.data_ptr(),
+                          buffer.advantages.data_ptr(), buffer.returns.data_ptr(), buffer.values.data_ptr())
+    n_mb = (M + mb - 1) // mb
+    losses = torch.zeros(cfg.epochs * n_mb, 4, dtype=torch.float64, device=dev)
+    step = 0
+    with torch.cuda.device(dev):
+        for epoch in range(cfg.epochs):
+            perm = None
+            if perms is not None:
+                perm = torch.as_tensor(perms[epoch], dtype=torch.int64, device=dev).contiguous()
+            for start in range(0, M, mb):
+                size = min(mb, M - start)
+                optimizer.zero_grad()
+                rc = lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), _lib.ptr(perm), perm_seed, epoch, start,
+                                        size, size * world, cfg.clip_epsilon, cfg.entropy_beta,
+                                        model.flat_grad.data_ptr(), losses[step].data_ptr(),
+                                        workspace.nan_flag.data_ptr(), workspace.ws.data_ptr(), workspace.bytes,
+                                        _stream(dev))
+                _lib.check(rc, "plume_ppo_grad")
+                if process_group is not None:
+                    torch.distributed.all_reduce(model.flat_grad, group=process_group)
+                optimizer.step()
+                if record is not None:
+                    record.append(optimizer.grad_norm.clone())
+                step += 1
+    if check_nan and int(workspace.nan_flag.item()) != 0:            # train_ppo2.0.py:57-61
+        workspace.nan_flag.zero_()
+        raise RuntimeError("NaN in probs")
+    return losses
+
+
+class PPOTrainer:
+    """Curriculum (model.py:178-221).  ``update(success)`` is the reference's per-episode host
+    logic (exact for the single-env driver); ``update_from_rollout(buffer)`` applies the same rule
+    on the device to every finished episode of a ``[T,N]`` segment in canonical order
+    (step-major, then env index) without a host round trip."""
+
+    def __init__(self, env, model=None, optimizer=None, cfg: PlumeConfig | None = None):
+        self.env, self.model, self.optimizer = env, model, optimizer
+        self.cfg = cfg or getattr(env, "cfg", None) or config_for("2.1")
+        self.success_history: list = []
+        self.current_radius = self.cfg.initial_radius
+        self.explore_bonus = self.cfg.explore_bonus
+        self._dev_state = None
+
+    def update(self, success) -> None:
+        c = self.cfg
+        self.env.current_radius = self.current_radius
+        self.env.explore_bonus = self.explore_bonus
+        self.success_history.append(bool(success))
+        if len(self.success_history) > c.window_size:
+            self.success_history.pop(0)
+        full = len(self.success_history) >= c.window_size
+        if full:
+            rate = float(np.mean(self.success_history[-c.window_size:]))
+            self.explore_bonus *= c.decay_factor ** (1 + rate)
+        self.explore_bonus = max(self.explore_bonus, 0.1)
+        if full:
+            rate = float(np.mean(self.success_history[-c.window_size:]))
+            if rate > c.success_threshold:
+                self.current_radius = max(c.min_radius,
+                                          self.current_radius * c.radius_decay ** (2 + 3 * (rate - c.success_threshold)))
+            elif rate < 0.25:
+                self.current_radius = min(c.initial_radius, self.current_radius * 1.1)
+            env_r = self.env.current_radius
+            if abs(self.current_radius - env_r) > 5:
+                self.current_radius = env_r + 5 * float(np.sign(self.current_radius - env_r))
+            self.success_history = []
+
+    # -- batched, on device ----------------------------------------------------------------
+    def device_state(self) -> torch.Tensor:
+        if self._dev_state is None:
+            s = torch.zeros(8, dtype=torch.float64, device=self.env.device)
+            s[0], s[1], s[2], s[3] = self.current_radius, self.explore_bonus, self.current_radius, self.explore_bonus
+            self._dev_state = s
+        return self._dev_state
+
+    def update_from_rollout(self, buffer) -> None:
+        lib = _lib.load()
+        c, st = self.cfg, self.device_state()
+        with torch.cuda.device(self.env.device):
+            rc = lib.plume_curriculum_update(buffer.dones.data_ptr(), buffer.reached.data_ptr(), buffer.filled,
+                                             buffer.num_envs, st.data_ptr(), self.env.curriculum.data_ptr(),
+                                             c.initial_radius, c.min_radius, c.radius_decay, c.success_threshold,
+                                             c.window_size, c.decay_factor, _stream(self.env.device))
+        _lib.check(rc, "plume_curriculum_update")
+
+    def sync_from_device(self) -> dict:
+        s = self.device_state().cpu()
+        if s[4] < 0:
+            raise RuntimeError("curriculum kernel overflow: too many finished episodes in one segment")
+        self.current_radius, self.explore_bonus = float(s[0]), float(s[1])
+        return {"radius": float(s[0]), "explore_bonus": float(s[1]), "window_len": int(s[4]),
+                "window_successes": int(s[5]), "episodes": int(s[6]), "successes": int(s[7])}

@@ -1,0 +1,69 @@
+"""Fused rollout driver: T lockstep iterations of policy + env step + LSTM stop head in ONE
+persistent kernel launch (csrc/rollout_kernel.cu), replacing the reference's python
+``while not done`` loop (PPOV2.1/train_ppo2.0.py:156-192, evaluate_with_lstm.py:61-82)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .buffer import PPOBuffer
+from .config import FIELD_PROCEDURAL
+
+
+class RolloutEngine:
+    def __init__(self, env, model, stop_head=None, horizon: int = 256, with_info: bool = False,
+                 with_trend: bool = False):
+        if env.field_mode != FIELD_PROCEDURAL:
+            raise ValueError("the fused rollout needs field_mode='procedural'")
+        self.env, self.model, self.stop_head = env, model, stop_head
+        self.lib = _lib.load()
+        self.horizon = int(horizon)
+        dev, N = env.device, env.num_envs
+        self.window = env.cfg.lstm_window
+        self.buffer = PPOBuffer(horizon, N, dev, with_info=with_info, with_stop=stop_head is not None,
+                                with_trend=with_trend)
+        self.conc_window = torch.zeros(N, self.window, dtype=torch.float32, device=dev)
+        self.window_fill = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.last_obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.launches = 0
+
+    def reset_windows(self) -> None:
+        self.window_fill.zero_()
+
+    @torch.no_grad()
+    def collect(self, greedy: bool = False, stop_terminates: bool = False, forced_actions=None,
+                step_noise=None, noise_out=None, horizon: int | None = None) -> PPOBuffer:
+        """Runs ``horizon`` lockstep iterations and returns the filled buffer (asynchronous)."""
+        env, T = self.env, int(horizon or self.horizon)
+        assert T <= self.horizon
+        flags = _lib.FLAG_AUTO_RESET
+        flags |= _lib.FLAG_GREEDY if greedy else 0
+        flags |= _lib.FLAG_STOP_TERMINATES if stop_terminates else 0
+        if forced_actions is not None:
+            forced_actions = forced_actions.to(device=env.device, dtype=torch.int32).contiguous()
+        if step_noise is not None:
+            step_noise = step_noise.to(device=env.device, dtype=torch.float64).contiguous()
+        bufs = self.buffer.c_rollout_buffers(self.conc_window, self.window_fill, self.last_obs, forced_actions,
+                                             step_noise, noise_out)
+        if self.stop_head is not None:
+            lp = self.stop_head.c_params(self.window, env.cfg.lstm_stop_threshold)
+        else:
+            lp = _lib.LstmParams()
+            lp.window = self.window
+        with torch.cuda.device(env.device):
+            rc = self.lib.plume_rollout(C.byref(env.c_config), C.byref(env.c_state), self.model.flat.data_ptr(),
+                                        C.byref(lp), C.byref(bufs), T, flags, self.nan_flag.data_ptr(),
+                                        torch.cuda.current_stream(env.device).cuda_stream)
+        _lib.check(rc, "plume_rollout")
+        self.launches += 1
+        self.buffer.filled = T
+        return self.buffer
+
+    def check_nan(self) -> None:
+        """model.py:41-43: raise if any logit was NaN during the last rollout(s)."""
+        if int(self.nan_flag.item()) != 0:
+            self.nan_flag.zero_()
+            raise RuntimeError("NaN in model output")

@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- PPO env-steps/s of the plume hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU loop (oracle port)
+
+A *step* is one PPO iteration at the BASELINE.json configuration "PPOV2.1, 4096 envs/GPU with
+LSTM policy": a fused rollout of 256 lockstep env steps over 4096 envs (MLP policy + Categorical
+sample + env step + LSTM(1->32) stop head over the 20-sample window + trend features, auto-reset),
+the curriculum, GAE and 5 epochs x 4 minibatches of the clipped-surrogate update with Adam (and,
+for N > 1, one NCCL all-reduce of the flat gradient per minibatch).  ``value`` = env-steps/s of the
+whole job with everything resident in HBM; ``e2e`` = the same through the host-buffer API (model
+parameters uploaded from / downloaded to pinned host memory every iteration).
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ppo_env_steps_per_sec"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 4096
+HORIZON = 256
+WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(1->32) stop head, window 20, "
+            "trend features) x 256 steps + curriculum + GAE + 5 epochs x 4 minibatches PPO update")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.samples:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference loop)
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n_steps = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import plume_oracle as po
+    from oracle import ppo_oracle as pp
+    cfg = po.config_for("2.1")
+    env = po.OracleScalarEnv(cfg, np.random.default_rng(seed))
+    torch.manual_seed(seed)
+    model = pp.OracleActorCritic()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.learning_rate)
+    cur = pp.OracleCurriculum(env, cfg)
+    t0 = time.perf_counter()
+    steps, updates, episodes = pp.cpu_train_loop(env, model, opt, cfg, n_steps, curriculum=cur, seed=seed)
+    return steps, time.perf_counter() - t0
+
+
+def cpu_baseline_single(n_steps: int = 12000) -> dict:
+    steps, dt = _cpu_worker((0, n_steps))
+    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{steps} env-steps of the reference loop (batch-1 policy forward + env.step + "
+                      f"_update_model every 256 transitions), oracle port, 1 thread, {dt:.1f} s"}
+
+
+def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's CPU loop (oracle port; the reference is pure Python and
+    cannot travel to the GPU box) on all host cores, one independent single-env process per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_proc = 2048           # env-steps per process per bench step (8 updates)
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(1000 * it + i, per_proc) for i in range(cores)])
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append((sum(r[0] for r in res), dt))
+    total_steps = sum(t[0] for t in times)
+    total_time = sum(t[1] for t in times)
+    value = total_steps / total_time
+    sample = (f"{cores} processes x {per_proc} env-steps per step of the reference loop (policy + env.step + "
+              f"_update_model every 256), oracle port")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_time / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference_arm": "CPU, all host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# the CUDA arm
+# ----------------------------------------------------------------------------------------------
+def timed(fn, stream_sync):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    stream_sync()
+    return e0.elapsed_time(e1)
+
+
+def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
+    """Auxiliary HBM rooflines of the plume kernels, outside the timed region: K1 field generation
+    (float fields, 2 x 500 x 500 x 4 B written per env) and K2 lockstep step."""
+    import ctypes as C
+    out = {}
+    sync = torch.cuda.synchronize
+    # K1: 1024 envs x 2 MB = 2.1 GB written (>> L2)
+    n1 = 1024
+    env = pb.VecMethaneEnv(n1, device=dev, field_mode="f32", seed=1)
+    lib = pb._lib.load()
+
+    def gen():
+        pb._lib.check(lib.plume_generate_fields(C.byref(env.c_config), C.byref(env.c_state), None, n1, None, None,
+                                                torch.cuda.current_stream().cuda_stream), "generate")
+    for _ in range(3):
+        gen()
+    sync()
+    ms = min(timed(gen, sync) for _ in range(5))
+    bytes_k1 = n1 * 2 * 500 * 500 * 4
+    out["plume_generate_f32"] = {"bound": "hbm", "achieved": bytes_k1 / ms / 1e6, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": bytes_k1 / ms / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                                 "ms": ms, "envs": n1, "algorithmic_bytes": bytes_k1, "peak_source": peaks["source"]}
+    del env
+    torch.cuda.empty_cache()
+    # K2: procedural, 102 B per env-step (csrc/env_kernels.cu header) + 20 B info
+    for n2 in (4096, 1 << 20):
+        env = pb.VecMethaneEnv(n2, device=dev, field_mode="procedural", auto_reset=True, seed=2)
+        acts = torch.randint(0, 5, (n2,), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            env.step(acts)
+        sync()
+        ms = min(timed(lambda: env.step(acts), sync) for _ in range(10))
+        b = n2 * 122
+        out[f"plume_step_{n2}"] = {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": b / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "envs": n2,
+                                   "algorithmic_bytes": b, "env_steps_per_s": n2 / ms * 1e3,
+                                   "peak_source": peaks["source"]}
+        del env
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_cuda_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import uav_wrf_les_ppo_lstm_b200 as pb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    peaks = measured_peaks()
+    N, T = args.envs, args.horizon
+    trainer = pb.PlumeTrainer(num_envs=N, horizon=T, version="2.1", device=dev, seed=0, rank=rank, world_size=world,
+                              process_group=pg, minibatch_size=(N * T) // 4)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    sync = lambda: torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up --------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 1)):
+        trainer.train_iteration()
+    trainer.engine.check_nan()
+    barrier()
+
+    # ---- timed region: K iterations, device time per iteration, L2 flushed in between -----------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_roll = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        ev_roll[k][0].record()
+        buf = trainer.engine.collect()
+        ev_roll[k][1].record()
+        trainer.curriculum.update_from_rollout(buf)
+        trainer.last_losses = pb.update_model(buf, trainer.model, trainer.optimizer, cfg=trainer.cfg,
+                                              minibatch_size=trainer.minibatch_size, workspace=trainer.workspace,
+                                              process_group=pg, perm_seed=trainer.iteration, check_nan=False)
+        trainer.iteration += 1
+        ev[k][1].record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_roll = [a.elapsed_time(b) for a, b in ev_roll]
+    total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    roll_ms = torch.tensor([sum(ms_roll)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(roll_ms, op=dist.ReduceOp.MAX)
+    total_ms, roll_ms = float(total_ms.item()), float(roll_ms.item())
+    trainer.engine.check_nan()
+    if int(trainer.workspace.nan_flag.item()) != 0:
+        raise RuntimeError("NaN in probs")
+    env_steps_global = N * T * world * args.steps
+    value = env_steps_global / (total_ms / 1e3)
+    rollout_value = env_steps_global / (roll_ms / 1e3)
+
+    # ---- per-kernel timing of one update (same stream, CUDA events) ---------------------------------
+    import ctypes as C
+    lib = pb._lib.load()
+    buf = trainer.engine.buffer
+    cfg, ws, model = trainer.cfg, trainer.workspace, trainer.model
+    M, mb = N * T, trainer.minibatch_size
+    batch = pb._lib.PpoBatch(M, buf.obs.data_ptr(), buf.actions.data_ptr(), buf.log_probs.data_ptr(),
+                             buf.advantages.data_ptr(), buf.returns.data_ptr(), buf.values.data_ptr())
+    loss = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def grad_call():
+        pb._lib.check(lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), None, 1, 0, 0, min(mb, M), min(mb, M),
+                                         cfg.clip_epsilon, cfg.entropy_beta, model.flat_grad.data_ptr(),
+                                         loss.data_ptr(), ws.nan_flag.data_ptr(), ws.ws.data_ptr(), ws.bytes,
+                                         torch.cuda.current_stream().cuda_stream), "ppo_grad")
+    grad_ms = min(timed(grad_call, sync) for _ in range(3))
+    gae_ms = min(timed(lambda: pb.compute_advantages(buf, cfg, ws, None), sync) for _ in range(3))
+    n_opt = cfg.epochs * ((M + mb - 1) // mb)
+    flops_grad = 3 * 70144 * min(mb, M)
+    flops_roll = N * T * (70144 + 20 * 2 * 4 * 32 * 33)
+    kernels = {
+        "ppo_grad(fwd_bwd+wgrad2)": {"ms": grad_ms, "launches_per_step": 2 * n_opt, "tflops": flops_grad / grad_ms / 1e9,
+                                      "share_of_step": grad_ms * n_opt / (total_ms / args.steps)},
+        "rollout": {"ms": roll_ms / args.steps, "launches_per_step": 1,
+                    "tflops": flops_roll / (roll_ms / args.steps) / 1e9,
+                    "share_of_step": roll_ms / total_ms,
+                    "us_per_lockstep_iteration": 1e3 * roll_ms / args.steps / T},
+        "gae(scan+normalise)": {"ms": gae_ms, "launches_per_step": 2, "gbs": 32 * M / gae_ms / 1e6,
+                                "hbm_frac": 32 * M / gae_ms / 1e6 / peaks["hbm_gbs"],
+                                "share_of_step": gae_ms / (total_ms / args.steps)},
+    }
+    dom = max(("ppo_grad(fwd_bwd+wgrad2)", "rollout"), key=lambda k: kernels[k]["share_of_step"])
+    peak_tf = peaks["bf16_tflops_sustained"]
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peak_tf, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16 dense (sustained)",
+                "note": "fp32 CUDA-core FMA kernel (fp32 parity requirement); fraction is against the tensor-core "
+                        "peak the GEMM-shaped work could reach; fp32 CUDA-core peak ~74 TFLOP/s",
+                "fp32_core_frac": kernels[dom]["tflops"] / 74.4}
+
+    # ---- end to end through the host-buffer API -------------------------------------------------------
+    hb = trainer.make_host_buffers()
+    hb["params_in"].copy_(trainer.model.flat.cpu())
+    if trainer.head is not None:
+        hb["lstm_in"].copy_(torch.cat([p.detach().reshape(-1) for p in trainer.head.parameters()]).cpu())
+    hb["curriculum_in"].copy_(trainer.env.curriculum.cpu())
+    trainer.train_iteration_host(hb)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        trainer.train_iteration_host(hb)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    h2d, d2h = trainer.host_bytes_per_iteration(hb)
+    e2e = {"value": N * T * world * e2e_steps / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "api": "PlumeTrainer.train_iteration_host (pinned host parameter/metric buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    plume = plume_kernel_rooflines(pb, torch, peaks, dev) if not args.skip_aux else {}
+    cpu = cpu_baseline_single(args.cpu_steps) if (world == 1 and not args.skip_cpu) else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": N, "horizon": T, "version": "2.1",
+                       "minibatch": trainer.minibatch_size, "epochs": cfg.epochs, "field_mode": "procedural",
+                       "lstm_hidden": 32, "lstm_window": cfg.lstm_window, "parallelism": f"env-shard x{world}",
+                       "l2_flush": "256 MB write between timed steps"},
+            "rollout_env_steps_per_sec": rollout_value,
+            "roofline": roofline, "kernels": kernels, "plume_kernels": plume, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": trainer.launches_per_iteration * args.steps}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--horizon", type=int, default=HORIZON)
+    ap.add_argument("--cpu-steps", type=int, default=12000)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-aux", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

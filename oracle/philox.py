@@ -18,8 +18,9 @@ tag        counter = (c0, c1, c2, c3)
 TAG_SRC=1  (0, episode, env, 1): words 0,1 -> u_x (53-bit double), words 2,3 -> u_y
 TAG_FIELD=2 (cell>>1, episode, env, 2): Box-Muller(words 0,1) -> (z_even, z_odd) cells,
            words 2,3 -> (u_even, u_odd); cell = x*G + y
-TAG_STEP=3 (step, episode, env, 3): Box-Muller(words 0,1) -> the two randn of one step
-TAG_ACT=4  (step, episode, env, 4): word 0 -> uniform for the inverse-CDF action draw
+TAG_STEP=3 (step, episode, env, 3): Box-Muller(words 0,1) -> the two randn of one step;
+           step = step_count BEFORE the step (0 for the first step of an episode)
+TAG_ACT=4  (step, episode, env, 4): word 0 -> uniform for the inverse-CDF action draw (same step index)
 =========  =====================================================================
 """
 from __future__ import annotations

@@ -1,0 +1,248 @@
+"""GPU parity of GAE (P5/K5), the PPO minibatch gradient (P6/K6), clip+Adam (P7/K7), the
+minibatch permutation and the curriculum (P8/K8) against the torch-CPU oracle and the
+reference's golden update trace."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import plume_oracle as po
+from oracle import ppo_oracle as pp
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def pb():
+    import uav_wrf_les_ppo_lstm_b200 as m
+    return m
+
+
+def _fill_buffer(m, T, N, seed, done_p=0.03):
+    rng = np.random.default_rng(seed)
+    buf = m.PPOBuffer(T, N, "cuda")
+    buf.obs.copy_(torch.from_numpy(rng.random((T, N, 6)).astype(np.float32)))
+    buf.actions.copy_(torch.from_numpy(rng.integers(0, 5, (T, N)).astype(np.int32)))
+    buf.rewards.copy_(torch.from_numpy(rng.normal(size=(T, N)).astype(np.float32)))
+    buf.values.copy_(torch.from_numpy(rng.normal(size=(T, N)).astype(np.float32)))
+    buf.log_probs.copy_(torch.from_numpy((-1.6 + 0.1 * rng.normal(size=(T, N))).astype(np.float32)))
+    buf.dones.copy_(torch.from_numpy((rng.random((T, N)) < done_p).astype(np.float32)))
+    buf.filled = T
+    return buf
+
+
+@pytest.mark.parametrize("T,N", [(256, 1), (64, 40), (7, 1000), (1, 5)])
+def test_gae_scan_bit_exact_and_normalise(T, N):
+    m = pb()
+    cfg = m.config_for("2.1")
+    buf = _fill_buffer(m, T, N, T * 1000 + N)
+    ws = m.UpdateWorkspace("cuda", 256)
+    lib = m._lib.load()
+    ws.stats.zero_()
+    rc = lib.plume_gae_scan(buf.rewards.data_ptr(), buf.values.data_ptr(), buf.dones.data_ptr(), T, N, cfg.gamma,
+                            cfg.lam, buf.advantages.data_ptr(), ws.stats.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    raw = pp.gae_quirk(buf.rewards.cpu(), buf.values.cpu(), buf.dones.cpu(), cfg.gamma, cfg.lam)
+    assert torch.equal(buf.advantages.cpu(), raw)                    # bit-exact reverse scan
+    st = ws.stats.cpu().numpy()
+    assert st[2] == T * N and np.isclose(st[0], raw.double().sum().item(), rtol=1e-12)
+    if T * N > 1:
+        m.compute_advantages(buf, cfg, ws)
+        a_ref, r_ref = pp.normalise_advantages(raw, buf.values.cpu())
+        assert torch.allclose(buf.advantages.cpu(), a_ref, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(buf.returns.cpu(), r_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_gae_degenerate_std():
+    """adv_std < 1e-6 -> divide by 1 (train_ppo2.0.py:36-37)."""
+    m = pb()
+    cfg = m.config_for("2.1")
+    buf = m.PPOBuffer(4, 3, "cuda")
+    buf.filled = 4
+    ws = m.UpdateWorkspace("cuda", 256)
+    m.compute_advantages(buf, cfg, ws)
+    assert torch.all(buf.advantages == 0) and torch.all(buf.returns == 0)
+
+
+def _oracle_grads(ora, cfg, S, A, LP, ADV, RET, V):
+    ora.zero_grad()
+    total, pl, vl, ent = pp.ppo_loss(ora, S, A, LP, ADV, RET, V, cfg)
+    total.backward()
+    return total.item(), pl.item(), vl.item(), ent.item()
+
+
+@pytest.mark.parametrize("M,mb_start,mb_size", [(256, 0, 256), (1000, 100, 333), (64, 0, 1), (4096, 1024, 2048)])
+def test_ppo_gradient_vs_autograd(M, mb_start, mb_size):
+    m = pb()
+    cfg = po.config_for("2.1")
+    torch.manual_seed(M)
+    ora = pp.OracleActorCritic()
+    with torch.no_grad():
+        for p in ora.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+        ora.actor.weight.mul_(30.0)
+    model = m.PPOActorCritic(device="cuda")
+    model.load_state_dict(ora.state_dict())
+    rng = np.random.default_rng(M)
+    S = torch.from_numpy(rng.random((M, 6)).astype(np.float32))
+    A = torch.from_numpy(rng.integers(0, 5, M))
+    with torch.no_grad():
+        P, V0 = ora(S)
+    LP = pp.categorical_log_prob(P, A) + torch.from_numpy((0.25 * rng.normal(size=M)).astype(np.float32))
+    ADV = torch.from_numpy(rng.normal(size=M).astype(np.float32))
+    V = V0.squeeze(-1) + torch.from_numpy((0.3 * rng.normal(size=M)).astype(np.float32))
+    RET = V + torch.from_numpy(rng.normal(size=M).astype(np.float32))
+    perm = torch.randperm(M)
+    idx = perm[mb_start:mb_start + mb_size]
+    want = _oracle_grads(ora, cfg, S[idx], A[idx], LP[idx], ADV[idx], RET[idx], V[idx])
+
+    lib = m._lib.load()
+    dev = "cuda"
+    t = lambda x, dt: x.to(dt).to(dev).contiguous()
+    obs, act, lp, adv, ret, val = t(S, torch.float32), t(A, torch.int32), t(LP, torch.float32), t(ADV, torch.float32), \
+        t(RET, torch.float32), t(V, torch.float32)
+    batch = m._lib.PpoBatch(M, obs.data_ptr(), act.data_ptr(), lp.data_ptr(), adv.data_ptr(), ret.data_ptr(),
+                            val.data_ptr())
+    ws = m.UpdateWorkspace(dev, mb_size)
+    loss = torch.zeros(4, dtype=torch.float64, device=dev)
+    model.flat_grad.zero_()
+    permd = perm.to(dev)
+    rc = lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), permd.data_ptr(), 0, 0, mb_start, mb_size, mb_size,
+                            cfg.clip_epsilon, cfg.entropy_beta, model.flat_grad.data_ptr(), loss.data_ptr(),
+                            ws.nan_flag.data_ptr(), ws.ws.data_ptr(), ws.bytes, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.plume_last_error()
+    got = loss.cpu().numpy()
+    assert np.allclose(got, np.array(want), rtol=1e-5, atol=1e-7), (got, want)
+    named = dict(ora.named_parameters())
+    gnorm = torch.sqrt(sum((p.grad ** 2).sum() for p in named.values())).item()
+    for name, (off, shape) in m._lib.MLP_OFFSETS.items():
+        n = int(np.prod(shape))
+        g_gpu = model.flat_grad[off:off + n].view(shape).cpu()
+        g_ref = named[name].grad
+        err = (g_gpu - g_ref).abs().max().item()
+        assert err <= 1e-5 * max(g_ref.abs().max().item(), 1e-3 * gnorm) + 1e-8, (name, err, g_ref.abs().max().item())
+    assert int(ws.nan_flag.item()) == 0
+
+
+def test_update_model_reproduces_reference_update():
+    """Full _update_model on the reference's golden trace (same permutations): parameters after
+    5 epochs agree with what the reference produced."""
+    g = load_golden("update_s5.npz")
+    m = pb()
+    cfg = m.config_for("2.1")
+    model = m.PPOActorCritic(device="cuda")
+    init = {k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init.")}
+    model.load_state_dict(init)
+    opt = m.FusedAdam(model, lr=cfg.learning_rate)
+    M = len(g["actions"])
+    buf = m.PPOBuffer(M, 1, "cuda")
+    for i in range(M):   # the reference's store() call pattern, one transition at a time
+        buf.store(g["states"][i][None], [g["actions"][i]], [g["rewards"][i]], [g["values"][i]], [g["log_probs"][i]],
+                  [g["dones"][i]])
+    assert len(buf.states) == M
+    losses = m.update_model(buf, model, opt, cfg=cfg, perms=list(g["perms"]))
+    assert losses.shape == (cfg.epochs, 4)
+    sd = model.state_dict()
+    num = den = 0.0
+    for k, v in sd.items():
+        final = torch.from_numpy(g["final." + k])
+        # Adam's first steps move each weight by ~lr*g/(|g|+1e-8): entries whose gradient is ~1e-8 amplify
+        # fp32 summation-order noise, so the bound is 2% of the total movement (5 steps x lr = 1.5e-4)
+        diff = (v.cpu() - final).abs()
+        assert diff.max().item() <= 3e-6, (k, diff.max().item(), (diff > 3e-7).float().mean().item())
+        assert (diff > 3e-7).float().mean().item() < 0.02, (k, (diff > 3e-7).float().mean().item())
+        d_ref = (final - init[k]).flatten().double()
+        d_gpu = (v.cpu() - init[k]).flatten().double()
+        num += float((d_ref * d_gpu).sum())
+        den += float(d_ref.norm() ** 2)
+    assert num / den > 0.999          # the update itself (not just the parameters) agrees
+    # oracle losses on the same data
+    ora = pp.OracleActorCritic()
+    ora.load_state_dict(init)
+    rec = []
+    pp.ppo_update(ora, torch.optim.Adam(ora.parameters(), lr=cfg.learning_rate), torch.from_numpy(g["states"]),
+                  torch.from_numpy(g["actions"]), torch.from_numpy(g["rewards"]), torch.from_numpy(g["values"]),
+                  torch.from_numpy(g["log_probs"]), torch.from_numpy(g["dones"]), po.config_for("2.1"),
+                  perms=list(g["perms"]), record=rec)
+    want = np.array([[r["loss"], r["policy_loss"], r["value_loss"], r["entropy"]] for r in rec])
+    assert np.allclose(losses.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+
+
+def test_clip_adam_vs_torch():
+    m = pb()
+    torch.manual_seed(0)
+    model = m.PPOActorCritic(device="cuda")
+    ora = pp.OracleActorCritic()
+    ora.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    opt = m.FusedAdam(model, lr=3e-4)
+    topt = torch.optim.Adam(ora.parameters(), lr=3e-4)
+    named = dict(ora.named_parameters())
+    for step in range(6):
+        scale = [5.0, 0.01, 1.0, 3.0, 1e-4, 0.5][step]      # above and below the 0.5 clip norm
+        gflat = torch.zeros(m._lib.MLP_PARAMS)
+        for name, (off, shape) in m._lib.MLP_OFFSETS.items():
+            n = int(np.prod(shape))
+            gr = torch.randn(shape) * scale / 100
+            named[name].grad = gr.clone()
+            gflat[off:off + n] = gr.flatten()
+        model.flat_grad.copy_(gflat)
+        norm = torch.nn.utils.clip_grad_norm_(ora.parameters(), 0.5)
+        topt.step()
+        opt.step()
+        assert np.isclose(opt.grad_norm.item(), norm.item(), rtol=1e-5)
+        for k, v in model.state_dict().items():
+            assert torch.allclose(v.cpu(), named[k].detach(), rtol=1e-5, atol=1e-7), (step, k)
+
+
+@pytest.mark.parametrize("total", [1, 255, 4096, 100000])
+def test_permutation_kernel(total):
+    m = pb()
+    lib = m._lib.load()
+    out = torch.zeros(total, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.plume_permutation(total, 77, 1, 0, total, out.data_ptr(), s) == 0
+    got = out.cpu().numpy()
+    assert np.array_equal(np.sort(got), np.arange(total))
+    part = torch.zeros(max(total // 2, 1), dtype=torch.int64, device="cuda")
+    assert lib.plume_permutation(total, 77, 1, total // 4, part.numel(), part.data_ptr(), s) == 0 or total < 4
+    if total >= 4:
+        assert np.array_equal(part.cpu().numpy(), got[total // 4: total // 4 + part.numel()])
+    assert lib.plume_permutation(total, 77, 1, 1, total, out.data_ptr(), s) != 0      # range check
+
+
+def test_curriculum_kernel_vs_oracle():
+    m = pb()
+    cfg = po.config_for("2.1")
+    rng = np.random.default_rng(0)
+
+    class E:
+        current_radius = 50.0
+        explore_bonus = 0.6
+    ora_env = E()
+    ora = pp.OracleCurriculum(ora_env, cfg)
+    env = m.VecMethaneEnv(64, field_mode="procedural")
+    tr = m.PPOTrainer(env)
+    T, N = 128, 64
+    for seg in range(6):
+        buf = m.PPOBuffer(T, N, "cuda")
+        p_done = 0.06
+        dones = rng.random((T, N)) < p_done
+        reached = dones & (rng.random((T, N)) < [0.1, 0.5, 0.9, 0.95, 0.7, 0.2][seg])
+        buf.dones.copy_(torch.from_numpy(dones.astype(np.float32)))
+        buf.reached.copy_(torch.from_numpy(reached.astype(np.uint8)))
+        buf.filled = T
+        tr.update_from_rollout(buf)
+        for t in range(T):
+            for n in range(N):
+                if dones[t, n]:
+                    ora.update(bool(reached[t, n]))
+        st = tr.sync_from_device()
+        assert np.isclose(st["radius"], ora.current_radius, rtol=1e-12), seg
+        assert np.isclose(st["explore_bonus"], ora.explore_bonus, rtol=1e-12), seg
+        assert st["window_len"] == len(ora.success_history)
+        assert st["window_successes"] == int(np.sum(ora.success_history))
+        assert np.isclose(env.current_radius, ora.current_radius, rtol=1e-12)
+    assert ora.current_radius < 50.0

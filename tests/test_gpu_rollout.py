@@ -1,0 +1,223 @@
+"""GPU parity of the fused persistent rollout kernel: the transitions it produced (with its own
+Philox draws and sampled actions) are replayed through the oracle; the fused kernel must also
+agree bit-for-bit with the discrete step/act kernels it is built from."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import plume_oracle as po
+from oracle import ppo_oracle as pp
+
+pytestmark = pytest.mark.gpu
+
+
+def pb():
+    import uav_wrf_les_ppo_lstm_b200 as m
+    return m
+
+
+def _setup(N, T, seed, with_head=True, radius=None, actor_gain=40.0):
+    m = pb()
+    torch.manual_seed(seed)
+    env = m.VecMethaneEnv(N, version="2.1", seed=seed, field_mode="procedural", auto_reset=True)
+    if radius is not None:
+        env.curriculum[0] = radius
+        env.reset()
+    model = m.PPOActorCritic(device="cuda")
+    with torch.no_grad():
+        model.actor.weight.mul_(actor_gain)
+    head = None
+    if with_head:
+        head = m.PeakAndStopPredictor(device="cuda")
+        with torch.no_grad():
+            head.fc_stop[0].bias.fill_(1.386)       # sigmoid(1.386) = 0.8: flags straddle the threshold
+            head.fc_stop[0].weight.mul_(40.0)
+            head.lstm.weight_ih_l0.mul_(6.0)
+    eng = m.RolloutEngine(env, model, head, horizon=T, with_info=True, with_trend=True)
+    return m, env, model, head, eng
+
+
+def test_rollout_replay_through_oracle():
+    N, T = 96, 80
+    m, env, model, head, eng = _setup(N, T, seed=11, radius=30.0)
+    cfg = po.config_for("2.1")
+    src0 = env.source_pos.cpu().numpy().copy()
+    ep0 = env.episode_idx.cpu().numpy().copy()
+    noise = torch.zeros(T, N, 2, dtype=torch.float64, device="cuda")
+    buf = eng.collect(noise_out=noise)
+    eng.check_nan()
+    obs = buf.obs.cpu().numpy()
+    acts = buf.actions.cpu().numpy()
+    rew = buf.rewards.cpu().numpy()
+    dones = buf.dones.cpu().numpy() != 0
+    reached = buf.reached.cpu().numpy() != 0
+    epi = buf.episode_idx.cpu().numpy()
+    info = buf.info.cpu().numpy()
+    zs = noise.cpu().numpy()
+
+    # (1) env transitions of every env's first episode == oracle on the same actions/noise
+    frozen = m.VecMethaneEnv(N, version="2.1", seed=11, field_mode="procedural")
+    frozen.curriculum[0] = 30.0
+    frozen.reset()                                  # same episode index (2) as the rollout env at start
+    assert np.array_equal(frozen.episode_idx.cpu().numpy(), ep0)
+
+    def noise_cb(idx, x, y):
+        z, u = frozen.field_noise_at(np.asarray(idx, dtype=np.int32), np.asarray(x, dtype=np.int32),
+                                     np.asarray(y, dtype=np.int32))
+        return z.cpu().numpy(), u.cpu().numpy()
+
+    ora = po.OracleVecEnv(cfg, N, fields=po.CellNoiseFields(cfg, N, noise_cb))
+    for i in range(N):
+        ora.set_source(i, src0[i])
+    ora.current_radius[:] = 30.0
+    alive = np.ones(N, dtype=bool)
+    assert np.allclose(ora.observe(), obs[0], rtol=2e-7, atol=1e-9)
+    for t in range(T):
+        o, r, d, inf = ora.step(acts[t], zs[t])
+        assert np.array_equal(d[alive], dones[t][alive]), t
+        assert np.array_equal(inf["reached"][alive], reached[t][alive])
+        assert np.allclose(r[alive], rew[t][alive], rtol=1e-5, atol=1e-6)
+        assert np.allclose(np.asarray(inf["explore_reward"], dtype=np.float32)[alive], info[t, 1][alive], rtol=1e-6)
+        assert np.all(epi[t][alive] == ep0[alive])
+        if t + 1 < T:
+            cont = alive & ~d
+            assert np.array_equal(o[cont][:, [0, 1, 4, 5]], obs[t + 1][cont][:, [0, 1, 4, 5]]), t
+            assert np.allclose(o[cont], obs[t + 1][cont], rtol=2e-7, atol=1e-9)
+            fresh = alive & d                       # auto-reset: next obs is a reset observation
+            assert np.all(obs[t + 1][fresh][:, [0, 1, 4, 5]] == 0)
+            assert np.all(epi[t + 1][fresh] == ep0[fresh] + 1)
+        alive &= ~d
+    assert (~alive).sum() > 5                       # several envs reached the source
+
+    # (2) policy outputs on the recorded observations == oracle MLP
+    ora_m = pp.OracleActorCritic()
+    ora_m.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    with torch.no_grad():
+        p, v = ora_m(torch.from_numpy(obs.reshape(-1, 6)))
+    lp = pp.categorical_log_prob(p, torch.from_numpy(acts.reshape(-1)).long())
+    assert torch.allclose(buf.values.cpu().reshape(-1), v.squeeze(-1), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(buf.log_probs.cpu().reshape(-1), lp, rtol=1e-5, atol=2e-6)
+    assert len(set(acts.reshape(-1).tolist())) == 5
+
+    # (3) stop head == oracle LSTM on the per-episode sliding window of obs[2] after each step
+    ora_l = pp.OraclePeakAndStop()
+    ora_l.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
+    sp = buf.stop_prob.cpu().numpy()
+    sf = buf.stop_flag.cpu().numpy() != 0
+    last = eng.last_obs.cpu().numpy()
+    hist = [[] for _ in range(N)]
+    wins, where = [], []
+    for t in range(T):
+        nxt = obs[t + 1] if t + 1 < T else last
+        for i in range(N):
+            if dones[t, i]:
+                # the post-step observation of a finished episode is not in obs[t+1]; use the info term
+                hist[i].append(info[t, 0, i] / 2.0)
+            else:
+                hist[i].append(nxt[i, 2])
+            if len(hist[i]) >= 20:
+                wins.append(hist[i][-20:])
+                where.append((t, i))
+            else:
+                assert sp[t, i] == 0 and not sf[t, i]
+            if dones[t, i]:
+                hist[i] = []
+    assert len(wins) > 1000
+    with torch.no_grad():
+        _, s_ref = ora_l(torch.tensor(np.array(wins, dtype=np.float32)).unsqueeze(-1))
+    got = np.array([sp[t, i] for t, i in where])
+    assert np.allclose(got, s_ref.numpy(), rtol=1e-5, atol=2e-6)
+    gotf = np.array([sf[t, i] for t, i in where])
+    clear = np.abs(s_ref.numpy() - 0.8) > 1e-5
+    assert np.array_equal(gotf[clear], (s_ref.numpy() > 0.8)[clear])
+    assert 0 < gotf.sum() < len(gotf)
+
+    # (4) trend features over the same window
+    tr = buf.trend.cpu().numpy()
+    t_i = where[len(where) // 2]
+    k = where.index(t_i)
+    w = np.array(wins[k], dtype=np.float64) * 100.0
+    t, i = t_i
+    if not dones[t, i]:
+        pos_next = (obs[t + 1][i, :2] if t + 1 < T else last[i, :2]).astype(np.float64) * 500.0
+        lab = pp.trend_label(w, pos_next, src0[i] if epi[t, i] == ep0[i] else frozen.source_pos.cpu().numpy()[i])
+        if epi[t, i] == ep0[i]:
+            assert np.isclose(tr[t, i, 0], lab[0], rtol=1e-4, atol=1e-5)
+
+
+def test_fused_rollout_equals_discrete_kernels():
+    """Same seed, same Philox counters: the persistent kernel and the step-by-step kernels (policy
+    act -> env step with auto-reset) produce identical transitions."""
+    N, T = 200, 60
+    m, env_f, model, head, eng = _setup(N, T, seed=3, with_head=False, radius=40.0)
+    buf = eng.collect()
+    env_d = m.VecMethaneEnv(N, version="2.1", seed=3, field_mode="procedural", auto_reset=True)
+    env_d.curriculum[0] = 40.0
+    obs = env_d.reset().clone()
+    for t in range(T):
+        assert torch.equal(buf.obs[t], obs), t
+        a, lp, v, _ = model.act(obs, env=env_d)
+        o, r, d, info = env_d.step(a)
+        assert torch.equal(buf.actions[t], a), t
+        assert torch.equal(buf.log_probs[t], lp) and torch.equal(buf.values[t], v)
+        assert torch.equal(buf.rewards[t], r.float())
+        assert torch.equal(buf.dones[t] != 0, d)
+        obs = o.clone()
+    assert torch.equal(eng.last_obs, obs)
+    assert torch.equal(env_f.episode_idx, env_d.episode_idx)
+    assert torch.equal(env_f.visited_t, env_d.visited_t)
+    assert torch.equal(env_f.pos_x, env_d.pos_x) and torch.equal(env_f.step_count_t, env_d.step_count_t)
+
+
+def test_rollout_segments_are_continuous():
+    """Two collect() calls of T/2 == one of T (state, windows and counters persist)."""
+    N, T = 64, 64
+    m, env_a, model, head, eng_a = _setup(N, T, seed=9, radius=30.0)
+    full = eng_a.collect()
+    ra, sa = full.rewards.clone(), full.stop_prob.clone()
+    m2, env_b, model_b, head_b, eng_b = _setup(N, T, seed=9, radius=30.0)
+    first = eng_b.collect(horizon=T // 2)
+    r1, s1 = first.rewards[: T // 2].clone(), first.stop_prob[: T // 2].clone()
+    second = eng_b.collect(horizon=T // 2)
+    assert torch.equal(ra[: T // 2], r1) and torch.equal(ra[T // 2:], second.rewards[: T // 2])
+    assert torch.equal(sa[: T // 2], s1) and torch.equal(sa[T // 2:], second.stop_prob[: T // 2])
+
+
+def test_forced_actions_noise_and_stop_termination():
+    N, T = 64, 50
+    m, env, model, head, eng = _setup(N, T, seed=21, radius=10.0)
+    forced = torch.randint(0, 5, (T, N), dtype=torch.int32)
+    noise = torch.randn(T, N, 2, dtype=torch.float64)
+    used = torch.zeros(T, N, 2, dtype=torch.float64, device="cuda")
+    buf = eng.collect(forced_actions=forced, step_noise=noise, noise_out=used, stop_terminates=True)
+    assert torch.equal(buf.actions.cpu(), forced) and torch.equal(used.cpu(), noise)
+    stop = buf.stop_flag.cpu() != 0
+    done = buf.dones.cpu() != 0
+    assert stop.any() and torch.all(done[stop])           # a stop decision ends the episode
+    # greedy rollouts are deterministic given the state
+    m2, env2, model2, head2, eng2 = _setup(N, T, seed=21, radius=10.0)
+    g = eng2.collect(greedy=True)
+    with torch.no_grad():
+        p, _ = model2(g.obs.reshape(-1, 6))
+    assert torch.equal(g.actions.reshape(-1).long(), p.argmax(-1))
+
+
+def test_full_size_invariants():
+    """BASELINE size (4096 envs): size-independent properties of the rollout."""
+    N, T = 4096, 64
+    m, env, model, head, eng = _setup(N, T, seed=2, radius=50.0, actor_gain=1.0)
+    ep0 = env.episode_idx.clone()
+    buf = eng.collect()
+    eng.check_nan()
+    done = buf.dones != 0
+    epi = buf.episode_idx
+    assert torch.equal(env.episode_idx - ep0, done.sum(0).int())              # one reset per done
+    assert torch.equal(epi[1:] - epi[:-1], done[:-1].int())                    # episode index steps at dones
+    step_obs = buf.obs[:, :, 4] * 1000
+    nxt = torch.where(done[:-1], torch.zeros_like(step_obs[1:]), step_obs[:-1] + 1)
+    assert torch.allclose(step_obs[1:], nxt, atol=1e-3)                        # step counter in the observation
+    assert torch.all(buf.reached[done] == 1)                                  # nothing times out in 64 steps
+    assert torch.isfinite(buf.rewards).all() and torch.isfinite(buf.values).all()
+    assert torch.all((buf.actions >= 0) & (buf.actions < 5))
+    assert torch.all(buf.obs[:, :, 0] >= 0) and torch.all(buf.obs[:, :, 0] <= 1)
+    assert float(buf.log_probs.max()) <= 0

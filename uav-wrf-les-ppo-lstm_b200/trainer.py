@@ -1,0 +1,102 @@
+"""``PlumeTrainer``: the batched equivalent of ``train_ppo()`` (PPOV2.1/train_ppo2.0.py:109-267)
+for one GPU (one process per GPU; ranks hold disjoint env shards and all-reduce the gradient).
+
+One ``train_iteration()`` = one fused rollout segment of ``horizon`` lockstep steps over all envs
+(policy + env + LSTM stop head, one kernel), the on-device curriculum, GAE and
+``epochs x minibatches`` optimiser steps.  Nothing returns to the host inside an iteration."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .config import PlumeConfig, config_for
+from .env import VecMethaneEnv
+from .learner import FusedAdam, PPOTrainer, UpdateWorkspace, update_model
+from .model import PeakAndStopPredictor, PPOActorCritic
+from .rollout import RolloutEngine
+
+
+class PlumeTrainer:
+    def __init__(self, num_envs: int = 4096, horizon: int = 256, version: str = "2.1", device="cuda",
+                 seed: int = 0, minibatch_size: int | None = None, stop_head: bool = True,
+                 rank: int = 0, world_size: int = 1, process_group=None, with_info: bool = False,
+                 with_trend: bool = True, cfg: PlumeConfig | None = None):
+        self.cfg = cfg or config_for(version)
+        self.device = torch.device(device)
+        self.rank, self.world_size, self.process_group = rank, world_size, process_group
+        self.num_envs, self.horizon = int(num_envs), int(horizon)
+        torch.manual_seed(seed)                       # identical initial weights on every rank
+        self.env = VecMethaneEnv(num_envs, device=self.device, version=version, seed=seed,
+                                 field_mode="procedural", auto_reset=True, env_id_base=rank * num_envs,
+                                 config=self.cfg)
+        self.model = PPOActorCritic(device=self.device)
+        self.head = PeakAndStopPredictor(device=self.device) if stop_head else None
+        self.engine = RolloutEngine(self.env, self.model, self.head, horizon=horizon, with_info=with_info,
+                                    with_trend=with_trend and stop_head)
+        self.optimizer = FusedAdam(self.model, lr=self.cfg.learning_rate, max_grad_norm=self.cfg.max_grad_norm)
+        self.curriculum = PPOTrainer(self.env, self.model, self.optimizer, cfg=self.cfg)
+        self.minibatch_size = int(minibatch_size or (num_envs * horizon) // 4)
+        self.workspace = UpdateWorkspace(self.device, min(self.minibatch_size, num_envs * horizon))
+        self.iteration = 0
+        self.last_losses = None
+        n_mb = (num_envs * horizon + self.minibatch_size - 1) // self.minibatch_size
+        # my kernels per iteration: rollout, curriculum, gae scan + normalise, (fwd_bwd, wgrad2, clip_adam) per step
+        self.launches_per_iteration = 4 + 3 * self.cfg.epochs * n_mb
+
+    def train_iteration(self, check_nan: bool = False):
+        buf = self.engine.collect()
+        self.curriculum.update_from_rollout(buf)
+        self.last_losses = update_model(buf, self.model, self.optimizer, cfg=self.cfg,
+                                        minibatch_size=self.minibatch_size, workspace=self.workspace,
+                                        process_group=self.process_group, perm_seed=self.iteration,
+                                        check_nan=check_nan)
+        self.iteration += 1
+        return self.last_losses
+
+    def rollout_only(self):
+        return self.engine.collect()
+
+    # -- host-resident model: the end-to-end path with host buffers -------------------------------
+    def make_host_buffers(self):
+        """Pinned host buffers of the public host API: parameters in/out, metrics out."""
+        n_steps = self.cfg.epochs * ((self.num_envs * self.horizon + self.minibatch_size - 1) // self.minibatch_size)
+        lstm_n = sum(p.numel() for p in self.head.parameters()) if self.head is not None else 0
+        return {
+            "params_in": torch.empty(_lib.MLP_PARAMS, dtype=torch.float32).pin_memory(),
+            "lstm_in": torch.empty(max(lstm_n, 1), dtype=torch.float32).pin_memory(),
+            "curriculum_in": torch.empty(2, dtype=torch.float64).pin_memory(),
+            "params_out": torch.empty(_lib.MLP_PARAMS, dtype=torch.float32).pin_memory(),
+            "losses_out": torch.empty(n_steps, 4, dtype=torch.float64).pin_memory(),
+            "curriculum_out": torch.empty(8, dtype=torch.float64).pin_memory(),
+            "episodes_out": torch.empty(2, dtype=torch.float32).pin_memory(),
+        }
+
+    def train_iteration_host(self, hb: dict) -> None:
+        """One iteration for a caller that keeps the model on the host: uploads the parameters
+        (and the curriculum scalars) from pinned memory, runs the iteration, downloads the updated
+        parameters, the per-step losses, the curriculum state and the episode/success counts."""
+        self.model.flat.copy_(hb["params_in"], non_blocking=True)
+        if self.head is not None:
+            off = 0
+            for p in self.head.parameters():
+                n = p.numel()
+                p.data.copy_(hb["lstm_in"][off:off + n].view_as(p), non_blocking=True)
+                off += n
+        self.env.curriculum.copy_(hb["curriculum_in"], non_blocking=True)
+        losses = self.train_iteration()
+        hb["params_out"].copy_(self.model.flat, non_blocking=True)
+        hb["losses_out"].copy_(losses, non_blocking=True)
+        hb["curriculum_out"].copy_(self.curriculum.device_state(), non_blocking=True)
+        buf = self.engine.buffer
+        hb["episodes_out"].copy_(torch.stack([buf.dones[: buf.filled].sum(), buf.reached[: buf.filled].float().sum()]),
+                                 non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        hb["params_in"].copy_(hb["params_out"])
+        hb["curriculum_in"][0] = hb["curriculum_out"][0]
+        hb["curriculum_in"][1] = hb["curriculum_out"][1]
+
+    def host_bytes_per_iteration(self, hb: dict):
+        h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("params_in", "lstm_in", "curriculum_in"))
+        d2h = sum(hb[k].numel() * hb[k].element_size() for k in ("params_out", "losses_out", "curriculum_out",
+                                                                "episodes_out"))
+        return h2d, d2h

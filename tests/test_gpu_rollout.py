@@ -189,16 +189,24 @@ def test_forced_actions_noise_and_stop_termination():
     forced = torch.randint(0, 5, (T, N), dtype=torch.int32)
     noise = torch.randn(T, N, 2, dtype=torch.float64)
     used = torch.zeros(T, N, 2, dtype=torch.float64, device="cuda")
-    buf = eng.collect(forced_actions=forced, step_noise=noise, noise_out=used, stop_terminates=True)
-    assert torch.equal(buf.actions.cpu(), forced) and torch.equal(used.cpu(), noise)
+    probe = eng.collect(forced_actions=forced, step_noise=noise, noise_out=used)
+    assert torch.equal(probe.actions.cpu(), forced) and torch.equal(used.cpu(), noise)
+    sp = probe.stop_prob.cpu()
+    med = float(sp[sp > 0].median())
+    # shift the stop-head bias so that the median stop probability sits on the 0.8 threshold
+    shift = float(np.log(0.8 / 0.2) - np.log(med / (1 - med)))
+    m, env, model, head, eng = _setup(N, T, seed=21, radius=10.0)
+    with torch.no_grad():
+        head.fc_stop[0].bias.add_(shift)
+    buf = eng.collect(forced_actions=forced, step_noise=noise, stop_terminates=True)
     stop = buf.stop_flag.cpu() != 0
     done = buf.dones.cpu() != 0
-    assert stop.any() and torch.all(done[stop])           # a stop decision ends the episode
+    assert stop.any() and not stop.all() and torch.all(done[stop])      # a stop decision ends the episode
+    assert (done & ~stop & ~(buf.reached.cpu() != 0)).sum() == 0        # nothing else ends one here
     # greedy rollouts are deterministic given the state
     m2, env2, model2, head2, eng2 = _setup(N, T, seed=21, radius=10.0)
     g = eng2.collect(greedy=True)
-    with torch.no_grad():
-        p, _ = model2(g.obs.reshape(-1, 6))
+    p, _ = model2(g.obs.reshape(-1, 6))
     assert torch.equal(g.actions.reshape(-1).long(), p.argmax(-1))
 
 

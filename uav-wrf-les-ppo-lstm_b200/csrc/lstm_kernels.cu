@@ -108,9 +108,9 @@ __global__ void lstm_generic_kernel(const float* __restrict__ params, int layers
 #pragma unroll
                 for (int s = 0; s < kGenTS; ++s) {
                     const float ig = sigmoidf_acc(acc[s][0]), fg = sigmoidf_acc(acc[s][1]);
-                    const float gg = tanhf(acc[s][2]), og = sigmoidf_acc(acc[s][3]);
+                    const float gg = tanhf_acc(acc[s][2]), og = sigmoidf_acc(acc[s][3]);
                     c[s] = fmaf(fg, c[s], ig * gg);
-                    seq[((size_t)t * kGenTS + s) * H + j] = og * tanhf(c[s]);
+                    seq[((size_t)t * kGenTS + s) * H + j] = og * tanhf_acc(c[s]);
                 }
             }
             __syncthreads();

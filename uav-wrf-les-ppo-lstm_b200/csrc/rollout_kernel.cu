@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 fill = fill < W ? fill + 1 : W;
             }
             // ---- LSTM stop head over the window, all threads ------------------------------------------------
-            if (H > 0) {
-                __syncthreads();
+            // (skipped while no env of the tile has a full window: the first W-1 steps after a cold start)
+            if (H > 0 && __syncthreads_or(owner && fill >= W)) {
                 lstm_window_tile<HH>(lsm, W);
                 const float hv = lstm_heads<HH>(lsm, W);
                 if (tid < 32) s_peak[tid] = hv;

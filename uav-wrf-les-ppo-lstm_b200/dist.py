@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: one process per GPU, envs sharded by rank, no rollout traffic.
+
+The only exchange steps of the path are (1) three doubles per update -- {sum, sum of squares,
+count} of the raw advantages, so that every rank normalises with the *global* statistics
+(train_ppo2.0.py:34-38 over the whole batch) -- and (2) one all-reduce (sum) of the flat gradient
+per minibatch; each rank divides its loss by the global minibatch size, so the sum is the
+gradient of the global mean loss (train_ppo2.0.py:70-87).  NCCL on the GPUs, gloo in CPU tests."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None, device: torch.device | None = None):
+    """Initialises torch.distributed from RANK/WORLD_SIZE/MASTER_* (torchrun).  Returns
+    (rank, world_size, process_group or None)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world <= 1:
+        return 0, 1, None
+    if not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kwargs = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kwargs)
+    return rank, world, dist.group.WORLD
+
+
+def env_shard(rank: int, envs_per_rank: int):
+    """Global env ids owned by ``rank``: [rank*n, (rank+1)*n).  Philox counters use the global id,
+    so a run does not depend on how many ranks the envs are spread over."""
+    base = rank * envs_per_rank
+    return base, range(base, base + envs_per_rank)
+
+
+def allreduce_stats(stats: torch.Tensor, process_group=None) -> torch.Tensor:
+    """Sum-reduces the {sum, sumsq, count} advantage statistics in place."""
+    if process_group is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=process_group)
+    return stats
+
+
+def allreduce_gradient(flat_grad: torch.Tensor, process_group=None) -> torch.Tensor:
+    """Sum-reduces the flat gradient in place (one collective per minibatch, 145 KB)."""
+    if process_group is not None:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=process_group)
+    return flat_grad
+
+
+def global_minibatch(local_minibatch: int, process_group=None) -> int:
+    return local_minibatch * (dist.get_world_size(process_group) if process_group is not None else 1)
+
+
+def normalisation_from_stats(stats: torch.Tensor):
+    """(mean, denominator) exactly as csrc/learner_kernels.cu::gae_normalise_kernel derives them
+    from {sum, sumsq, count}: unbiased std, replaced by 1 if < 1e-6 or NaN, + 1e-6."""
+    s1, s2, n = (float(x) for x in stats.tolist())
+    mean = s1 / n
+    var = max((s2 - n * mean * mean) / (n - 1.0), 0.0) if n > 1 else float("nan")
+    sd = var ** 0.5
+    if not (sd >= 1e-6):
+        sd = 1.0
+    return mean, sd + 1e-6

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import dist as pdist
 from .config import PlumeConfig, config_for
 
 
@@ -82,8 +83,7 @@ def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_gr
         _lib.check(lib.plume_gae_scan(buffer.rewards.data_ptr(), buffer.values.data_ptr(), buffer.dones.data_ptr(), T,
                                       N, cfg.gamma, cfg.lam, buffer.advantages.data_ptr(), ws.stats.data_ptr(),
                                       _stream(dev)), "plume_gae_scan")
-        if process_group is not None:
-            torch.distributed.all_reduce(ws.stats, group=process_group)
+        pdist.allreduce_stats(ws.stats, process_group)
         _lib.check(lib.plume_gae_normalise(buffer.advantages.data_ptr(), buffer.values.data_ptr(), T * N,
                                            ws.stats.data_ptr(), buffer.returns.data_ptr(), _stream(dev)),
                    "plume_gae_normalise")
@@ -110,7 +110,6 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
     mb = int(minibatch_size or cfg.batch_size)
     if workspace is None or workspace.max_minibatch < min(mb, M):
         workspace = UpdateWorkspace(dev, min(mb, M))
-    world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     compute_advantages(buffer, cfg, workspace, process_group)
     batch = _lib.PpoBatch(M, buffer.obs.data_ptr(), buffer.actions.data_ptr(), buffer.log_probs.data_ptr(),
                           buffer.advantages.data_ptr(), buffer.returns.data_ptr(), buffer.values.data_ptr())
@@ -126,13 +125,12 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
                 size = min(mb, M - start)
                 optimizer.zero_grad()
                 rc = lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), _lib.ptr(perm), perm_seed, epoch, start,
-                                        size, size * world, cfg.clip_epsilon, cfg.entropy_beta,
+                                        size, pdist.global_minibatch(size, process_group), cfg.clip_epsilon, cfg.entropy_beta,
                                         model.flat_grad.data_ptr(), losses[step].data_ptr(),
                                         workspace.nan_flag.data_ptr(), workspace.ws.data_ptr(), workspace.bytes,
                                         _stream(dev))
                 _lib.check(rc, "plume_ppo_grad")
-                if process_group is not None:
-                    torch.distributed.all_reduce(model.flat_grad, group=process_group)
+                pdist.allreduce_gradient(model.flat_grad, process_group)
                 optimizer.step()
                 if record is not None:
                     record.append(optimizer.grad_norm.clone())

@@ -269,6 +269,12 @@ int plume_clip_adam(float* params, const float* grads, float* exp_avg, float* ex
 int plume_permutation(int64_t total, uint64_t seed, int32_t epoch, int64_t start, int64_t count, int64_t* out,
                       void* stream);
 
+/* ---- tensor-core GEMM building block ----------------------------------------------------- */
+/* C[M][N] = A[M][K] . B[N][K]^T, fp32 in/out, 3xTF32 on tcgen05 (fp32-grade accuracy); N in {128,256},
+ * K a multiple of 32.  The GEMM-shaped parts of the PPO update (model.py:23 feature.3, forward and
+ * backward, train_ppo2.0.py:54,85) run on this path; exported so it can be tested on its own. */
+int plume_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* ---- P8 curriculum, model.py:188-221 ----------------------------------------------------- */
 /* Applies PPOTrainer.update once per finished episode of a [T][N] segment in canonical order
  * (step-major, then env index), on the device.  state double[8 + window]:

@@ -1,0 +1,36 @@
+"""tcgen05 3xTF32 GEMM building block (csrc/tc_gemm.cuh) against float64 matmul."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def pb():
+    import uav_wrf_les_ppo_lstm_b200 as m
+    return m
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (1000, 128, 256), (384, 256, 128), (4096, 256, 128),
+                                   (65536, 128, 256)])
+def test_tc_gemm_3xtf32(M, N, K):
+    m = pb()
+    lib = m._lib.load()
+    rng = np.random.default_rng(M + N + K)
+    A = (rng.standard_normal((M, K)) * np.exp(rng.uniform(-3, 3, (M, 1)))).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.plume_tc_gemm(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.plume_last_error()
+    torch.cuda.synchronize()
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    got = c.cpu().numpy().astype(np.float64)
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T       # condition-aware bound
+    err = np.abs(got - want) / scale
+    assert np.isfinite(got).all()
+    assert err.max() < 2e-6, err.max()
+    # fp32 matmul of the same data is not meaningfully better
+    ref32 = (torch.from_numpy(A) @ torch.from_numpy(B).T).numpy().astype(np.float64)
+    err32 = np.abs(ref32 - want) / scale
+    assert err.max() < 20 * max(err32.max(), 1e-8)

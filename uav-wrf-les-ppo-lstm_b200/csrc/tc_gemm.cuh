@@ -1,0 +1,163 @@
+// tc_gemm.cuh -- sm_100a tensor-core building blocks: tcgen05.mma (kind::tf32) with operands in
+// shared memory and fp32 accumulators in TMEM, used with the 3xTF32 split so that the GEMM-shaped
+// parts of the PPO update keep fp32-grade accuracy (parity bar: fp32 rel 1e-5):
+//
+//      a = a_hi + a_lo,  a_hi = a with the 13 low mantissa bits cleared (exactly a TF32 value)
+//      A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi          (3 MMAs per K-step, error ~2^-21 relative)
+//
+// Operand tiles are written to shared memory by the CTA's own threads (they have to be split
+// anyway) in the canonical K-major no-swizzle ("interleaved") UMMA layout: 8-row x 16-byte core
+// matrices, stored [row/8][k/4][row%8][k%4]; LBO = 128 B (next core matrix along K), SBO =
+// (KC/4)*128 B (next 8 rows).  For a [ROWS][32] fp32 chunk the 16-byte slot index is simply
+// f = (row/8)*64 + (k/4)*8 + row%8, so consecutive threads store consecutive slots (conflict free)
+// while reading 64 contiguous bytes per row from global memory.
+//
+// Descriptor formats follow the PTX ISA / CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor,
+// InstrDescriptor); the guide is /opt/skills/guides/blackwell_cuda_programming.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plume {
+namespace tc {
+
+constexpr int kChunkK = 32;                      // fp32 elements per K chunk (128 B per row)
+constexpr uint32_t kLBO = 128;                   // bytes between K-adjacent core matrices
+constexpr uint32_t kSBO = (kChunkK / 4) * 128;   // bytes between 8-row groups (1024)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// ---- proxy / tcgen05 fences -----------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM ------------------------------------------------------------------------------------
+// one full warp allocates `cols` (power of two >= 32) columns; the base address lands in *slot
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread i of the warp = lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors -----------------------------------------------------------------------------
+// shared-memory matrix descriptor: K-major, no swizzle, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, one K-step of 8 tf32; issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread -> one arrive on `bar` when they have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- operand staging -----------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;        // exact
+}
+
+// Cooperative load of a [ROWS][32] fp32 chunk (row-major, leading dimension ld floats, rows
+// beyond `valid_rows` read as zero) into the hi/lo operand buffers.  kThreads threads.
+template <int ROWS, int kThreads>
+__device__ __forceinline__ void load_split_chunk(float* __restrict__ s_hi, float* __restrict__ s_lo,
+                                                 const float* __restrict__ src, size_t ld, int valid_rows, int tid) {
+    constexpr int kSlots = ROWS * 8;
+#pragma unroll
+    for (int f = tid; f < kSlots; f += kThreads) {
+        const int row = (f >> 6) * 8 + (f & 7), k4 = (f & 63) >> 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < valid_rows) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + k4 * 4));
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x);
+        split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z);
+        split_tf32(v.w, h.w, l.w);
+        reinterpret_cast<float4*>(s_hi)[f] = h;
+        reinterpret_cast<float4*>(s_lo)[f] = l;
+    }
+}
+
+// element (row, k) of a chunk buffer (for producers that write operands from registers)
+__device__ __forceinline__ int chunk_offset(int row, int k) {
+    return ((row >> 3) * 64 + (k >> 2) * 8 + (row & 7)) * 4 + (k & 3);
+}
+
+// The 12 MMAs of one 32-wide K chunk: M=128 rows of A, N rows of B; issued by one thread.
+__device__ __forceinline__ void mma_chunk_3xtf32(uint32_t tmem_d, const float* a_hi, const float* a_lo,
+                                                 const float* b_hi, const float* b_lo, uint32_t idesc,
+                                                 bool first_chunk) {
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+    for (int j = 0; j < kChunkK / 8; ++j) {
+        const uint32_t off = j * 2 * kLBO;       // 8 tf32 = two 16-byte core-matrix columns
+        const uint64_t dah = make_smem_desc(ah + off, kLBO, kSBO), dal = make_smem_desc(al + off, kLBO, kSBO);
+        const uint64_t dbh = make_smem_desc(bh + off, kLBO, kSBO), dbl = make_smem_desc(bl + off, kLBO, kSBO);
+        mma_tf32(tmem_d, dal, dbh, idesc, (first_chunk && j == 0) ? 0u : 1u);   // small terms first
+        mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+    }
+}
+
+}  // namespace tc
+}  // namespace plume

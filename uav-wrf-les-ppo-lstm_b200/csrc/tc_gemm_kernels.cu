@@ -1,0 +1,101 @@
+// tc_gemm_kernels.cu -- C[M][N] = A[M][K] . B[N][K]^T in fp32-grade 3xTF32 on the sm_100a tensor
+// cores (tcgen05.mma kind::tf32, accumulators in TMEM).  The stand-alone GEMM is the unit test of
+// the building blocks in tc_gemm.cuh that the PPO update kernels use.
+//
+// One CTA (128 threads) per 128-row tile; K streamed in 32-wide chunks through a 2-stage shared-
+// memory ring: all threads load + split a chunk while the previous chunk's MMAs run asynchronously;
+// thread 0 issues the MMAs and commits them to the stage's mbarrier.
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace plume {
+
+template <int BN>
+__global__ void __launch_bounds__(128, 1) tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                         float* __restrict__ C, int M, int K) {
+    extern __shared__ __align__(1024) float sm[];
+    constexpr int kA = 128 * tc::kChunkK, kB = BN * tc::kChunkK;
+    float* a_hi = sm;                  // [2][kA]
+    float* a_lo = a_hi + 2 * kA;
+    float* b_hi = a_lo + 2 * kA;       // [2][kB]
+    float* b_lo = b_hi + 2 * kB;
+    __shared__ uint64_t mma_done[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * 128;
+    if (tid == 0) {
+        tc::mbar_init(&mma_done[0], 1);
+        tc::mbar_init(&mma_done[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc<BN>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = tc::make_idesc_tf32(128, BN);
+
+    const int chunks = K / tc::kChunkK;
+    for (int kc = 0; kc < chunks; ++kc) {
+        const int s = kc & 1;
+        if (kc >= 2) tc::mbar_wait(&mma_done[s], (uint32_t)(((kc >> 1) - 1) & 1));   // stage s is free again
+        tc::load_split_chunk<128, 128>(a_hi + s * kA, a_lo + s * kA, A + (size_t)m0 * K + kc * tc::kChunkK, K, M - m0, tid);
+        tc::load_split_chunk<BN, 128>(b_hi + s * kB, b_lo + s * kB, B + kc * tc::kChunkK, K, BN, tid);
+        tc::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            tc::mma_chunk_3xtf32(tmem_d, a_hi + s * kA, a_lo + s * kA, b_hi + s * kB, b_lo + s * kB, idesc, kc == 0);
+            tc::mma_commit(&mma_done[s]);
+        }
+    }
+    // all MMAs complete in order: wait for the last chunk's commit
+    {
+        const int last = chunks - 1;
+        tc::mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
+    }
+    tc::tc_fence_after();
+    // epilogue: warp w owns TMEM lanes 32w..32w+31 = rows m0+32w+lane
+    const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        tc::tmem_ld_wait();
+        if (row < M) {
+            float4* dst = reinterpret_cast<float4*>(C + (size_t)row * BN + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<BN>(tmem_d);
+}
+
+template <int BN>
+static int launch_tc_gemm(const float* A, const float* B, float* C, int M, int K, cudaStream_t s) {
+    const int smem = (2 * 2 * 128 * tc::kChunkK + 2 * 2 * BN * tc::kChunkK) * (int)sizeof(float) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return fail("tc_gemm: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    tc_gemm_kernel<BN><<<(M + 127) / 128, 128, smem, s>>>(A, B, C, M, K);
+    if (cudaGetLastError() != cudaSuccess) return fail("tc_gemm launch failed");
+    return 0;
+}
+
+}  // namespace plume
+
+using namespace plume;
+
+extern "C" int plume_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream) {
+    PLUME_CHECK_ARG(A && B && C, "null pointer");
+    PLUME_CHECK_ARG(M > 0 && K > 0 && K % tc::kChunkK == 0, "K must be a positive multiple of 32");
+    if (N == 128) return launch_tc_gemm<128>(A, B, C, M, K, as_stream(stream));
+    if (N == 256) return launch_tc_gemm<256>(A, B, C, M, K, as_stream(stream));
+    return fail("plume_tc_gemm: N must be 128 or 256");
+}

@@ -14,7 +14,7 @@
 // Algorithmic bytes per sample (DESIGN.md "K6"): gather obs 24 + action 4 + old logp 4 + adv 4 +
 // ret 4 + old value 4 = 44 B read; workspace dz2 512 + x 32 + stats 8 = 552 B written by A and
 // read by B.  FLOP per sample: forward 70 144, backward ~140 288.
-#include "mlp_tile.cuh"
+#include "ppo_loss.cuh"
 
 namespace plume {
 
@@ -35,21 +35,6 @@ struct PpoArgs {
     float* ws_x;              // [mb_size][8]
     float* ws_stat;           // [mb_size][2]  LN1 mean, rstd
 };
-
-// warp "transpose-reduce": v[32] per lane -> returns sum over lanes of v[lane index]
-__device__ __forceinline__ float warp_reduce_by_index(float (&v)[32], int lane) {
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-        const bool up = (lane & step) != 0;
-#pragma unroll
-        for (int i = 0; i < step; ++i) {
-            const float send = up ? v[i] : v[i + step];
-            const float keep = up ? v[i + step] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-        }
-    }
-    return v[0];
-}
 
 __global__ void __launch_bounds__(kMlpThreads, 1) ppo_fwd_bwd_kernel(const float* __restrict__ params, PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -110,71 +95,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) ppo_fwd_bwd_kernel(const float
         if (tid < kTileM) {
             float dout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (tid < n_valid) {
-                const float* o = sm + MlpSmem::out + tid * 8;
-                bool bad = false;
+                const SampleLoss L = ppo_sample_loss(sm + MlpSmem::out + tid * 8, s_act[tid], s_adv[tid], s_ret[tid],
+                                                     s_vold[tid], s_lpold[tid], a.clip_eps, a.entropy_beta,
+                                                     a.inv_global);
+                if (L.nan) atomicExch(a.nan_flag, 1);                            // :57-61
 #pragma unroll
-                for (int k = 0; k < 5; ++k) bad |= isnan(o[k]);
-                if (bad) atomicExch(a.nan_flag, 1);                              // :57-61
-                float p[5];
-                softmax5(o, p);
-                const int act = s_act[tid];
-                float S = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) S += p[k];
-                float pa = p[0];
-#pragma unroll
-                for (int k = 1; k < 5; ++k)
-                    if (act == k) pa = p[k];
-                const float q = pa / S;
-                const float eps = 1.1920928955078125e-07f;
-                const bool q_inside = (q >= eps) && (q <= 1.0f - eps);
-                const float lp = logf(fminf(fmaxf(q, eps), 1.0f - eps));          // :63-64
-                const float adv = s_adv[tid];
-                const float ratio = expf(lp - s_lpold[tid]);                     // :67
-                const float lo = 1.0f - a.clip_eps, hi = 1.0f + a.clip_eps;
-                const float s1 = ratio * adv;
-                const float s2 = fminf(fmaxf(ratio, lo), hi) * adv;               // :68-69
-                const bool inside = (ratio >= lo) && (ratio <= hi);
-                float dratio;                                                     // d(-min(s1,s2))/d ratio
-                if (inside) dratio = -adv;
-                else if (s1 < s2) dratio = -adv;
-                else if (s1 > s2) dratio = 0.0f;
-                else dratio = -0.5f * adv;
-                const float dlp = q_inside ? dratio * ratio : 0.0f;
-                const float pol = -fminf(s1, s2);                                 // :70
-                // value loss :73-77
-                const float v = o[5], ret = s_ret[tid], vold = s_vold[tid];
-                const float dvv = v - vold;
-                const bool v_inside = (dvv >= -a.clip_eps) && (dvv <= a.clip_eps);
-                const float vclip = vold + fminf(fmaxf(dvv, -a.clip_eps), a.clip_eps);
-                const float e1 = (v - ret) * (v - ret), e2 = (vclip - ret) * (vclip - ret);
-                float dv;
-                if (e1 > e2) dv = (v - ret);
-                else if (e2 > e1) dv = v_inside ? (vclip - ret) : 0.0f;
-                else dv = 0.5f * (v - ret) + (v_inside ? 0.5f * (vclip - ret) : 0.0f);
-                const float val = 0.5f * fmaxf(e1, e2);
-                // entropy :80
-                float ent = 0.0f, gbar = 0.0f, gk[5];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float lg = logf(p[k] + 1e-8f);
-                    ent -= p[k] * lg;
-                    gk[k] = lg + p[k] / (p[k] + 1e-8f);     // d/dp_k sum p log(p+1e-8)
-                    gbar += gk[k] * p[k];
-                }
-                // d total / d logits_j, total = pol + val - beta*ent (:82), all means over the batch
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float onehot = (act == k) ? 1.0f : 0.0f;
-                    const float d_pol = dlp * ((onehot - p[k]) - p[k] * (1.0f - S) / S);
-                    const float d_ent = a.entropy_beta * p[k] * (gk[k] - gbar);
-                    dout[k] = (d_pol + d_ent) * a.inv_global;
-                }
-                dout[5] = dv * a.inv_global;
-                l_pol += (double)pol;
-                l_val += (double)val;
-                l_ent += (double)ent;
-                l_tot += (double)pol + (double)val - (double)a.entropy_beta * (double)ent;
+                for (int k = 0; k < 6; ++k) dout[k] = L.dout[k];
+                l_pol += (double)L.pol;
+                l_val += (double)L.val;
+                l_ent += (double)L.ent;
+                l_tot += (double)L.pol + (double)L.val - (double)a.entropy_beta * (double)L.ent;
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) sm[MlpSmem::out + tid * 8 + k] = dout[k];

@@ -1,0 +1,95 @@
+// ppo_loss.cuh -- per-sample PPO loss and its gradient w.r.t. the 5 logits and the value
+// (train_ppo2.0.py:63-82), shared by the CUDA-core and the tensor-core update kernels.
+#pragma once
+#include "mlp_tile.cuh"
+
+namespace plume {
+
+struct SampleLoss {
+    float dout[6];      // d total / d logits[0..4], d total / d value, already divided by the global batch
+    float pol, val, ent;
+    bool nan;
+};
+
+// o[0..4] logits, o[5] value.
+__device__ __forceinline__ SampleLoss ppo_sample_loss(const float* o, int act, float adv, float ret, float vold,
+                                                      float lpold, float clip_eps, float entropy_beta,
+                                                      float inv_global) {
+    SampleLoss r;
+    r.nan = false;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r.nan |= isnan(o[k]);                    // :57-61
+    float p[5];
+    softmax5(o, p);
+    float S = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) S += p[k];
+    float pa = p[0];
+#pragma unroll
+    for (int k = 1; k < 5; ++k)
+        if (act == k) pa = p[k];
+    const float q = pa / S;
+    const float eps = 1.1920928955078125e-07f;
+    const bool q_inside = (q >= eps) && (q <= 1.0f - eps);
+    const float lp = logf(fminf(fmaxf(q, eps), 1.0f - eps));          // :63-64
+    const float ratio = expf(lp - lpold);                             // :67
+    const float lo = 1.0f - clip_eps, hi = 1.0f + clip_eps;
+    const float s1 = ratio * adv;
+    const float s2 = fminf(fmaxf(ratio, lo), hi) * adv;               // :68-69
+    const bool inside = (ratio >= lo) && (ratio <= hi);
+    float dratio;                                                     // d(-min(s1,s2))/d ratio
+    if (inside) dratio = -adv;
+    else if (s1 < s2) dratio = -adv;
+    else if (s1 > s2) dratio = 0.0f;
+    else dratio = -0.5f * adv;
+    const float dlp = q_inside ? dratio * ratio : 0.0f;
+    r.pol = -fminf(s1, s2);                                           // :70
+    // value loss :73-77
+    const float v = o[5];
+    const float dvv = v - vold;
+    const bool v_inside = (dvv >= -clip_eps) && (dvv <= clip_eps);
+    const float vclip = vold + fminf(fmaxf(dvv, -clip_eps), clip_eps);
+    const float e1 = (v - ret) * (v - ret), e2 = (vclip - ret) * (vclip - ret);
+    float dv;
+    if (e1 > e2) dv = (v - ret);
+    else if (e2 > e1) dv = v_inside ? (vclip - ret) : 0.0f;
+    else dv = 0.5f * (v - ret) + (v_inside ? 0.5f * (vclip - ret) : 0.0f);
+    r.val = 0.5f * fmaxf(e1, e2);
+    // entropy :80
+    float ent = 0.0f, gbar = 0.0f, gk[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float lg = logf(p[k] + 1e-8f);
+        ent -= p[k] * lg;
+        gk[k] = lg + p[k] / (p[k] + 1e-8f);     // d/dp_k sum p log(p+1e-8)
+        gbar += gk[k] * p[k];
+    }
+    r.ent = ent;
+    // d total / d logits_j, total = pol + val - beta*ent (:82), all means over the batch
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float onehot = (act == k) ? 1.0f : 0.0f;
+        const float d_pol = dlp * ((onehot - p[k]) - p[k] * (1.0f - S) / S);
+        const float d_ent = entropy_beta * p[k] * (gk[k] - gbar);
+        r.dout[k] = (d_pol + d_ent) * inv_global;
+    }
+    r.dout[5] = dv * inv_global;
+    return r;
+}
+
+// warp "transpose-reduce": v[32] per lane -> returns sum over lanes of v[lane index]
+__device__ __forceinline__ float warp_reduce_by_index(float (&v)[32], int lane) {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const float send = up ? v[i] : v[i + step];
+            const float keep = up ? v[i + step] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return v[0];
+}
+
+}  // namespace plume

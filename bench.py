@@ -306,16 +306,32 @@ def run_cuda_arm(args) -> None:
                                          torch.cuda.current_stream().cuda_stream), "ppo_grad")
     grad_ms = min(timed(grad_call, sync) for _ in range(3))
     gae_ms = min(timed(lambda: pb.compute_advantages(buf, cfg, ws, None), sync) for _ in range(3))
+    eng = trainer.engine
+    seg_ms = None
+    if trainer.head is not None:
+        lp = trainer.head.c_params(eng.window, cfg.lstm_stop_threshold)
+
+        def seg_call():
+            pb._lib.check(lib.plume_stop_head_segment(C.byref(lp), buf.conc_sample.data_ptr(), buf.fill_t.data_ptr(),
+                                                      pb._lib.ptr(buf.src_dist), T, N, eng.conc_window.data_ptr(),
+                                                      eng._window_next.data_ptr(), cfg.conc_peak,
+                                                      buf.stop_prob.data_ptr(), buf.stop_flag.data_ptr(),
+                                                      buf.peak_pred.data_ptr(), pb._lib.ptr(buf.trend),
+                                                      torch.cuda.current_stream().cuda_stream), "stop_head_segment")
+        seg_ms = min(timed(seg_call, sync) for _ in range(3))
     n_opt = cfg.epochs * ((M + mb - 1) // mb)
     flops_grad = 3 * 70144 * min(mb, M)
     flops_roll = N * T * (70144 + 20 * 2 * 4 * 32 * 33)
     kernels = {
         "ppo_grad(fwd_bwd+wgrad2)": {"ms": grad_ms, "launches_per_step": 2 * n_opt, "tflops": flops_grad / grad_ms / 1e9,
                                       "share_of_step": grad_ms * n_opt / (total_ms / args.steps)},
-        "rollout": {"ms": roll_ms / args.steps, "launches_per_step": 1,
+        "rollout": {"ms": roll_ms / args.steps, "launches_per_step": 2 if seg_ms else 1,
                     "tflops": flops_roll / (roll_ms / args.steps) / 1e9,
                     "share_of_step": roll_ms / total_ms,
-                    "us_per_lockstep_iteration": 1e3 * roll_ms / args.steps / T},
+                    "us_per_lockstep_iteration": 1e3 * roll_ms / args.steps / T,
+                    "stop_head_segment_ms": seg_ms,
+                    "stop_head_segment_tflops": (N * T * 20 * 2 * 4 * 32 * 33 / seg_ms / 1e9) if seg_ms else None,
+                    "lockstep_loop_ms": (roll_ms / args.steps - seg_ms) if seg_ms else roll_ms / args.steps},
         "gae(scan+normalise)": {"ms": gae_ms, "launches_per_step": 2, "gbs": 32 * M / gae_ms / 1e6,
                                 "hbm_frac": 32 * M / gae_ms / 1e6 / peaks["hbm_gbs"],
                                 "share_of_step": gae_ms / (total_ms / args.steps)},

@@ -43,6 +43,10 @@ extern "C" {
 #define PLUME_FLAG_AUTO_RESET 1u     /* finished envs are reset inside the call (procedural mode) */
 #define PLUME_FLAG_GREEDY 2u         /* argmax actions (evaluate_with_lstm.py:65) instead of sampling */
 #define PLUME_FLAG_STOP_TERMINATES 4u /* a stop-head decision ends the episode (evaluate_with_lstm.py:77-80) */
+#define PLUME_FLAG_DEFER_STOP_HEAD 8u /* plume_rollout only records the stop-head inputs (conc_sample, fill_t,
+                                       * src_dist); plume_stop_head_segment evaluates the head and the trend
+                                       * features for the whole [T][N] segment afterwards.  Identical results;
+                                       * not combinable with PLUME_FLAG_STOP_TERMINATES. */
 
 /* Constants of one reference version (PPOV x/config.py; environment.py). HOST struct. */
 typedef struct plume_env_config {
@@ -216,6 +220,11 @@ typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major u
     float* conc_window;    /* [N][window] ring of obs[2] inside the current episode (persistent state) */
     int32_t* window_fill;  /* [N] samples in the ring (persistent state) */
     float* last_obs;       /* [N][6] observation each env will act on next (persistent state, in/out) */
+    /* inputs of the deferred stop head (PLUME_FLAG_DEFER_STOP_HEAD), [T][N]: */
+    float* conc_sample;    /* the value pushed into the window at step t: obs[2] after the step, before a reset
+                            * (evaluate_with_lstm.py:67-70) */
+    uint8_t* fill_t;       /* samples of the current episode in the window after the push (saturates at window) */
+    double* src_dist;      /* ||agent_pos - source_pos|| after the step (environment.py:155), for the trend label */
 } plume_rollout_buffers;
 
 /* T lockstep iterations of: policy forward + sample, env step, stop head, auto-reset; one
@@ -223,6 +232,19 @@ typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major u
 int plume_rollout(const plume_env_config* cfg, const plume_env_state* st, const float* mlp_params,
                   const plume_lstm_params* lstm, const plume_rollout_buffers* buf, int32_t horizon,
                   uint32_t flags, int32_t* nan_flag, void* stream);
+
+/* Deferred stop head + trend features of a whole segment (PPOV2.1/evaluate_with_lstm.py:73-80 and
+ * model.py:113-127 for every (t, env) of the [T][N] rollout): the window of (t, env) is
+ * conc_sample[t-W+1..t][env], continued into window_in [N][W] (the ring carried over from the previous
+ * segment) for t < W-1; it is evaluated when fill_t[t][env] >= W, else the outputs are 0.  Writes
+ * stop_prob/stop_flag/peak_pred [T][N], trend [T][N][4] (each may be NULL) and the ring for the next
+ * segment into window_out [N][W] (must not alias window_in).  Because the stop decision does not feed
+ * back into the rollout unless PLUME_FLAG_STOP_TERMINATES is set, taking the head out of the lockstep
+ * loop changes no result; it turns 20 latency-bound cell steps per env-step into a throughput kernel. */
+int plume_stop_head_segment(const plume_lstm_params* lstm, const float* conc_sample, const uint8_t* fill_t,
+                            const double* src_dist, int32_t horizon, int32_t n_envs, const float* window_in,
+                            float* window_out, double conc_peak, float* stop_prob, uint8_t* stop_flag,
+                            float* peak_pred, float* trend, void* stream);
 
 /* ---- P5 GAE + normalisation, train_ppo2.0.py:17-39 -------------------------------------- */
 /* Per-env reverse scan over [T][N] (the reference's quirks kept: self-bootstrap at T-1, mask with

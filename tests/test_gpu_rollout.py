@@ -229,3 +229,39 @@ def test_full_size_invariants():
     assert torch.all((buf.actions >= 0) & (buf.actions < 5))
     assert torch.all(buf.obs[:, :, 0] >= 0) and torch.all(buf.obs[:, :, 0] <= 1)
     assert float(buf.log_probs.max()) <= 0
+
+
+@pytest.mark.parametrize("splits", [(64,), (7, 13, 44), (32, 32)])
+def test_deferred_stop_head_equals_in_loop_head(splits):
+    """plume_stop_head_segment (the head taken out of the lockstep loop) reproduces the in-loop head
+    bit for bit: stop probability, flag, peak, trend features, and the window ring carried from one
+    segment to the next (also for segments shorter than the window)."""
+    N, T = 80, 64
+    m, env_a, model_a, head_a, eng_a = _setup(N, T, seed=17, radius=25.0)
+    m, env_b, model_b, head_b, eng_b = _setup(N, T, seed=17, radius=25.0)
+    ref = eng_a.collect(defer_stop_head=False)
+    sp, sf, pk, tr = ref.stop_prob.clone(), ref.stop_flag.clone(), ref.peak_pred.clone(), ref.trend.clone()
+    assert (sp > 0).any() and sf.any() and not sf.all()
+    t0 = 0
+    for h in splits:
+        seg = eng_b.collect(horizon=h)                    # default: deferred
+        assert torch.equal(seg.rewards[:h], ref.rewards[t0:t0 + h])
+        assert torch.equal(seg.stop_prob[:h], sp[t0:t0 + h])
+        assert torch.equal(seg.stop_flag[:h], sf[t0:t0 + h])
+        assert torch.equal(seg.peak_pred[:h], pk[t0:t0 + h])
+        assert torch.equal(seg.trend[:h], tr[t0:t0 + h])
+        t0 += h
+    assert torch.equal(eng_a.window_fill, eng_b.window_fill)
+    full = eng_a.window_fill >= eng_a.window
+    assert full.any() and torch.equal(eng_a.conc_window[full], eng_b.conc_window[full])
+    # mixing the modes keeps the carried state consistent
+    nxt_a = eng_a.collect(horizon=8, defer_stop_head=False).stop_prob[:8].clone()
+    nxt_b = eng_b.collect(horizon=8, defer_stop_head=False).stop_prob[:8].clone()
+    assert torch.equal(nxt_a, nxt_b)
+
+
+def test_deferred_stop_head_rejects_terminating_stop():
+    N, T = 32, 8
+    m, env, model, head, eng = _setup(N, T, seed=1)
+    with pytest.raises(ValueError):
+        eng.collect(stop_terminates=True, defer_stop_head=True)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplume_b200.so")
 
 OBS_DIM, NUM_ACTIONS, INFO_DIM, VISIT_STRIDE = 6, 5, 5, 104
-FLAG_AUTO_RESET, FLAG_GREEDY, FLAG_STOP_TERMINATES = 1, 2, 4
+FLAG_AUTO_RESET, FLAG_GREEDY, FLAG_STOP_TERMINATES, FLAG_DEFER_STOP_HEAD = 1, 2, 4, 8
 
 # flat MLP parameter layout (include/plume_b200.h)
 MLP_OFFSETS = {
@@ -53,7 +53,7 @@ class RolloutBuffers(C.Structure):
     _fields_ = [(n, _vp) for n in ("obs", "actions", "rewards", "values", "log_probs", "dones", "reached",
                                    "stop_prob", "stop_flag", "peak_pred", "trend", "info", "episode_idx",
                                    "forced_actions", "step_noise", "noise_out", "conc_window", "window_fill",
-                                   "last_obs")]
+                                   "last_obs", "conc_sample", "fill_t", "src_dist")]
 
 
 class PpoBatch(C.Structure):
@@ -83,6 +83,8 @@ _SIGNATURES = {
     "plume_policy_act": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _vp, C.c_int32, _vp, _vp, C.c_uint32, _vp,
                                    _vp, _vp, _vp, _vp, _vp]),
     "plume_lstm_stop_head": (C.c_int, [_vp] * 8 + [C.c_int32, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "plume_stop_head_segment": (C.c_int, [_P(LstmParams), _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double,
+                                          _vp, _vp, _vp, _vp, _vp]),
     "plume_lstm_forward": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp, _vp]),
     "plume_trend_features": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, _vp, _vp]),
     "plume_rollout": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _P(LstmParams), _P(RolloutBuffers), C.c_int32,

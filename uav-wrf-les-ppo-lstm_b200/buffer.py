@@ -31,6 +31,10 @@ class PPOBuffer:
         self.trend = z(torch.float32, T, N, 4) if with_trend else None
         self.info = z(torch.float32, T, _lib.INFO_DIM, N) if with_info else None
         self.episode_idx = z(torch.int32, T, N) if with_episode else None
+        # inputs of the deferred stop head (csrc/lstm_kernels.cu::stop_head_segment_kernel)
+        self.conc_sample = z(torch.float32, T, N) if with_stop else None
+        self.fill_t = z(torch.uint8, T, N) if with_stop else None
+        self.src_dist = z(torch.float64, T, N) if (with_stop and with_trend) else None
         self.advantages = z(torch.float32, T, N)
         self.returns = z(torch.float32, T, N)
         self.filled = 0          # rows written
@@ -77,4 +81,4 @@ class PPOBuffer:
                                    p(self.dones), p(self.reached), p(self.stop_prob), p(self.stop_flag),
                                    p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
                                    p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
-                                   p(last_obs))
+                                   p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist))

@@ -146,6 +146,94 @@ __global__ void trend_kernel(const float* __restrict__ conc, int batch, int W, c
                    conc_peak, out + 4 * (size_t)i);
 }
 
+
+// ---- deferred stop head over a whole rollout segment -------------------------------------------------
+// One tile = 32 consecutive envs at one step t; the window of (t, env) is read straight out of the
+// [T][N] conc_sample rows t-W+1..t (coalesced 128 B rows), continued into the carried ring for t < W-1.
+// Algorithmic bytes per (t, env): reads 4 (sample; the other W-1 window rows hit L1/L2) + 1 (fill) +
+// 8 (dist); writes 4 + 1 + 4 + 16 = 25.  2*4H*(1+H)*W FLOP (H=32, W=20: 168 960).
+struct SegmentArgs {
+    const float* conc_sample;
+    const uint8_t* fill_t;
+    const double* src_dist;
+    int horizon, n_envs, W;
+    const float* window_in;
+    float* window_out;
+    double conc_peak;
+    float threshold;
+    float *stop_prob, *peak_pred, *trend;
+    uint8_t* stop_flag;
+};
+
+template <int H>
+__global__ void __launch_bounds__(256, 3) stop_head_segment_kernel(LstmWeights w, SegmentArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float s_out[64];
+    lstm_load_weights<H>(sm, w);
+    const int tid = threadIdx.x;
+    const int N = a.n_envs, W = a.W;
+    const int env_tiles = (N + 31) / 32;
+    const long long tiles = (long long)env_tiles * a.horizon;
+    float* xs = sm + LstmSmem<H>::xs;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int t = (int)(tile / env_tiles), env0 = (int)(tile - (long long)t * env_tiles) * 32;
+        __syncthreads();
+        for (int i = tid; i < W * 32; i += 256) {              // xs[k][s], k = 0 oldest
+            const int k = i >> 5, s = i & 31, env = env0 + s;
+            const int tt = t - (W - 1) + k;
+            float v = 0.0f;
+            if (env < N) v = tt >= 0 ? a.conc_sample[(size_t)tt * N + env] : a.window_in[(size_t)env * W + (W + tt)];
+            xs[k * 32 + s] = v;
+        }
+        int fill = 0;
+        if (tid < 32 && env0 + tid < N) fill = a.fill_t[(size_t)t * N + env0 + tid];
+        const bool full = fill >= W;
+        const bool any = __syncthreads_or(full);               // also publishes xs
+        if (any) {
+            lstm_window_tile<H>(sm, W);
+            const float hv = lstm_heads<H>(sm, W);
+            if (tid < 64) s_out[tid] = hv;                     // [0,32) peak, [32,64) stop probability
+            __syncthreads();
+        }
+        if (tid < 32 && env0 + tid < N) {
+            const size_t i = (size_t)t * N + env0 + tid;
+            const float peak = full ? s_out[tid] : 0.0f, stop_p = full ? s_out[32 + tid] : 0.0f;
+            if (a.stop_prob) a.stop_prob[i] = stop_p;
+            if (a.stop_flag) a.stop_flag[i] = (full && stop_p > a.threshold) ? 1 : 0;   // evaluate_with_lstm.py:77
+            if (a.peak_pred) a.peak_pred[i] = peak;
+            if (a.trend) {
+                float tr[4] = {0, 0, 0, 0};
+                if (full && W >= 4)
+                    trend_from_last4(100.0 * (double)xs[(W - 4) * 32 + tid], 100.0 * (double)xs[(W - 3) * 32 + tid],
+                                     100.0 * (double)xs[(W - 2) * 32 + tid], 100.0 * (double)xs[(W - 1) * 32 + tid],
+                                     a.src_dist[i], a.conc_peak, tr);
+                *reinterpret_cast<float4*>(a.trend + i * 4) = make_float4(tr[0], tr[1], tr[2], tr[3]);
+            }
+            if (t == a.horizon - 1 && a.window_out)            // the ring the next segment continues from
+                for (int k = 0; k < W; ++k) a.window_out[(size_t)(env0 + tid) * W + k] = xs[k * 32 + tid];
+        }
+    }
+}
+
+template <int H>
+static int launch_segment(const LstmWeights& w, const SegmentArgs& a, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = LstmSmem<H>::total * (int)sizeof(float);
+    if (!configured) {
+        if (cudaFuncSetAttribute(stop_head_segment_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+            return fail("stop-head segment kernel: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    const long long tiles = (long long)((a.n_envs + 31) / 32) * a.horizon;
+    long long grid = 3LL * sm_count();
+    if (grid <= 0) return fail("no CUDA device");
+    if (tiles < grid) grid = tiles;
+    stop_head_segment_kernel<H><<<(int)grid, 256, smem, s>>>(w, a);
+    if (cudaGetLastError() != cudaSuccess) return fail("stop-head segment kernel launch failed");
+    return 0;
+}
+
 template <int H>
 static int launch_stop_head(const LstmWeights& w, const float* windows, int batch, int steps, float* peak,
                             float* stop_prob, cudaStream_t s) {
@@ -195,6 +283,39 @@ extern "C" int plume_lstm_stop_head(const float* w_ih, const float* w_hh, const 
     if (hidden == 32) return launch_stop_head<32>(w, windows, batch, steps, peak, stop_prob, as_stream(stream));
     if (hidden == 64) return launch_stop_head<64>(w, windows, batch, steps, peak, stop_prob, as_stream(stream));
     return fail("plume_lstm_stop_head: hidden must be 32 or 64 (use plume_lstm_forward for other sizes)");
+}
+
+extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const float* conc_sample, const uint8_t* fill_t,
+                                       const double* src_dist, int32_t horizon, int32_t n_envs,
+                                       const float* window_in, float* window_out, double conc_peak, float* stop_prob,
+                                       uint8_t* stop_flag, float* peak_pred, float* trend, void* stream) {
+    PLUME_CHECK_ARG(lstm && conc_sample && fill_t && window_in, "null pointer");
+    PLUME_CHECK_ARG(lstm->w_ih && lstm->w_hh && lstm->b_ih && lstm->b_hh && lstm->w_peak && lstm->b_peak &&
+                        lstm->w_stop && lstm->b_stop, "null LSTM parameter");
+    PLUME_CHECK_ARG(lstm->window >= 1 && lstm->window <= kLstmMaxSteps, "stop-head window must be in [1,32]");
+    PLUME_CHECK_ARG(!trend || src_dist, "trend features need src_dist");
+    PLUME_CHECK_ARG(window_out != window_in, "window_out must not alias window_in");
+    if (horizon <= 0 || n_envs <= 0) return 0;
+    const LstmWeights w{lstm->w_ih, lstm->w_hh, lstm->b_ih, lstm->b_hh, lstm->w_peak, lstm->b_peak, lstm->w_stop,
+                        lstm->b_stop};
+    SegmentArgs a;
+    a.conc_sample = conc_sample;
+    a.fill_t = fill_t;
+    a.src_dist = src_dist;
+    a.horizon = horizon;
+    a.n_envs = n_envs;
+    a.W = lstm->window;
+    a.window_in = window_in;
+    a.window_out = window_out;
+    a.conc_peak = conc_peak;
+    a.threshold = lstm->threshold;
+    a.stop_prob = stop_prob;
+    a.peak_pred = peak_pred;
+    a.trend = trend;
+    a.stop_flag = stop_flag;
+    if (lstm->hidden == 32) return launch_segment<32>(w, a, as_stream(stream));
+    if (lstm->hidden == 64) return launch_segment<64>(w, a, as_stream(stream));
+    return fail("plume_stop_head_segment: hidden must be 32 or 64");
 }
 
 extern "C" int plume_lstm_forward(const float* params, int32_t layers, int32_t hidden, const float* windows,

@@ -145,12 +145,10 @@ __device__ __forceinline__ float lstm_heads(const float* sm, int steps) {
 }
 
 // ---- P4t trend features (calculate_dynamic_label, PPOV2.1/model.py:113-127) ------------------------
-// m = mean of the last three np.gradient values of the window
-__device__ __forceinline__ void trend_finish(double m, double c_last, double px, double py, double sx, double sy,
-                                             double conc_peak, float* out) {
+// m = mean of the last three np.gradient values of the window; dist = ||pos[-1] - src||
+__device__ __forceinline__ void trend_finish(double m, double c_last, double dist, double conc_peak, float* out) {
     const double trend = tanh(m / 5.0);
-    const double ddx = px - sx, ddy = py - sy;
-    const double dist_score = exp(-sqrt(ddx * ddx + ddy * ddy) / 50.0);
+    const double dist_score = exp(-dist / 50.0);
     double cs = c_last / conc_peak;
     cs = cs < 0.0 ? 0.0 : (cs > 1.0 ? 1.0 : cs);
     double label = 0.4 * dist_score + 0.3 * (trend + 1.0) / 2.0 + 0.3 * cs;
@@ -161,18 +159,25 @@ __device__ __forceinline__ void trend_finish(double m, double c_last, double px,
     out[3] = (float)cs;
 }
 
+// np.linalg.norm(pos - src) in float64, not contracted (same arithmetic as env:155)
+__device__ __forceinline__ double source_distance(double px, double py, double sx, double sy) {
+    const double ddx = dsub(px, sx), ddy = dsub(py, sy);
+    return dsqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));
+}
+
 // window of >= 4 samples: only the last four matter (central differences inside, one-sided at the end)
-__device__ __forceinline__ void trend_from_last4(double c4, double c3, double c2, double c1, double px, double py,
-                                                 double sx, double sy, double conc_peak, float* out) {
+__device__ __forceinline__ void trend_from_last4(double c4, double c3, double c2, double c1, double dist,
+                                                 double conc_peak, float* out) {
     const double g0 = (c2 - c4) / 2.0, g1 = (c1 - c3) / 2.0, g2 = c1 - c2;
-    trend_finish(((g0 + g1) + g2) / 3.0, c1, px, py, sx, sy, conc_peak, out);
+    trend_finish(((g0 + g1) + g2) / 3.0, c1, dist, conc_peak, out);
 }
 
 __device__ __forceinline__ void trend_features(const float* conc, int W, double px, double py, double sx, double sy,
                                                double conc_peak, float* out) {
+    const double dist = source_distance(px, py, sx, sy);
     if (W >= 4) {
-        trend_from_last4((double)conc[W - 4], (double)conc[W - 3], (double)conc[W - 2], (double)conc[W - 1], px, py,
-                         sx, sy, conc_peak, out);
+        trend_from_last4((double)conc[W - 4], (double)conc[W - 3], (double)conc[W - 2], (double)conc[W - 1], dist,
+                         conc_peak, out);
         return;
     }
     // W in {2,3}: np.gradient is one-sided at both ends
@@ -184,7 +189,7 @@ __device__ __forceinline__ void trend_features(const float* conc, int W, double 
                      g2 = (double)conc[2] - (double)conc[1];
         m = ((g0 + g1) + g2) / 3.0;
     }
-    trend_finish(m, (double)conc[W - 1], px, py, sx, sy, conc_peak, out);
+    trend_finish(m, (double)conc[W - 1], dist, conc_peak, out);
 }
 
 }  // namespace plume

@@ -199,6 +199,7 @@ struct StepResult {
     double move_penalty, boundary_penalty;
     double cur_conc;       // conc at the float64 cell / peak (env:118)
     double cell_conc, cell_tke;   // field at the float32 cell after the move (what obs[2], obs[3] hold)
+    double distance;       // ||agent_pos - source_pos|| after the move (env:155)
 };
 
 PLUME_HD int clip_cell(int v, int G) { return v < 0 ? 0 : (v > G - 1 ? G - 1 : v); }
@@ -319,6 +320,7 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     out.cur_conc = cur_conc;
     out.cell_conc = conc32;
     out.cell_tke = tke32;
+    out.distance = distance;
 }
 
 // P0 reset, env:42-50: source draw, zero position/step, clear visit table, latch curriculum.

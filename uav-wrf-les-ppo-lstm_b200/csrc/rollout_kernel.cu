@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     const double cur_radius = a.st.curriculum[0], cur_bonus = a.st.curriculum[1];
     const bool greedy = (a.flags & PLUME_FLAG_GREEDY) != 0;
     const bool stop_terminates = (a.flags & PLUME_FLAG_STOP_TERMINATES) != 0;
+    // deferred stop head: only record the window inputs; plume_stop_head_segment does the rest
+    const bool defer = (a.flags & PLUME_FLAG_DEFER_STOP_HEAD) != 0;
 
     const int tiles = (N + kTileM - 1) / kTileM;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -86,8 +88,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
             for (int k = 0; k < 6; ++k) sm[MlpSmem::x + tid * 8 + k] = o[k];
             sm[MlpSmem::x + tid * 8 + 6] = 0.0f;
             sm[MlpSmem::x + tid * 8 + 7] = 0.0f;
-            for (int k = 0; k < W; ++k)
-                win[k * 32 + tid] = (owner && a.buf.conc_window) ? a.buf.conc_window[(size_t)env * W + k] : 0.0f;
+            if (!defer)
+                for (int k = 0; k < W; ++k)
+                    win[k * 32 + tid] = (owner && a.buf.conc_window) ? a.buf.conc_window[(size_t)env * W + k] : 0.0f;
         }
 
         for (int t = 0; t < a.horizon; ++t) {
@@ -129,9 +132,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 cell_conc = r.cell_conc;
                 cell_tke = r.cell_tke;
                 // sliding window of obs[2] (= conc_field[int(x),int(y)]/100 as float32, evaluate_with_lstm.py:67-74)
-                for (int k = 0; k + 1 < W; ++k) win[k * 32 + tid] = win[(k + 1) * 32 + tid];
-                win[(W - 1) * 32 + tid] = r.obs[2];
                 fill = fill < W ? fill + 1 : W;
+                if (defer) {
+                    a.buf.conc_sample[row + env] = r.obs[2];
+                    a.buf.fill_t[row + env] = (uint8_t)fill;
+                    if (a.buf.src_dist) a.buf.src_dist[row + env] = r.distance;
+                } else {
+                    for (int k = 0; k + 1 < W; ++k) win[k * 32 + tid] = win[(k + 1) * 32 + tid];
+                    win[(W - 1) * 32 + tid] = r.obs[2];
+                }
             }
             // ---- LSTM stop head over the window, all threads ------------------------------------------------
             // (skipped while no env of the tile has a full window: the first W-1 steps after a cold start)
@@ -159,9 +168,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 a.buf.log_probs[i] = logp;
                 a.buf.dones[i] = done ? 1.0f : 0.0f;
                 a.buf.reached[i] = r.reached ? 1 : 0;
-                if (a.buf.stop_prob) a.buf.stop_prob[i] = stop_p;
-                if (a.buf.stop_flag) a.buf.stop_flag[i] = stop ? 1 : 0;
-                if (a.buf.peak_pred) a.buf.peak_pred[i] = peak;
+                if (!defer) {
+                    if (a.buf.stop_prob) a.buf.stop_prob[i] = stop_p;
+                    if (a.buf.stop_flag) a.buf.stop_flag[i] = stop ? 1 : 0;
+                    if (a.buf.peak_pred) a.buf.peak_pred[i] = peak;
+                }
                 if (a.buf.episode_idx) a.buf.episode_idx[i] = (int32_t)ep_of_transition;
                 if (a.buf.info) {
                     float* inf = a.buf.info + (size_t)t * 5 * N + env;
@@ -171,12 +182,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                     inf[3 * (size_t)N] = r.tke_penalty;
                     inf[4 * (size_t)N] = (float)r.boundary_penalty;
                 }
-                if (a.buf.trend) {
+                if (a.buf.trend && !defer) {
                     float tr[4] = {0, 0, 0, 0};
                     if (fill >= W && W >= 4) {
                         trend_from_last4(100.0 * (double)win[(W - 4) * 32 + tid], 100.0 * (double)win[(W - 3) * 32 + tid],
                                          100.0 * (double)win[(W - 2) * 32 + tid], 100.0 * (double)win[(W - 1) * 32 + tid],
-                                         (double)e.px, (double)e.py, e.sx, e.sy, c.conc_peak, tr);
+                                         r.distance, c.conc_peak, tr);
                     }
                     *reinterpret_cast<float4*>(a.buf.trend + i * 4) = make_float4(tr[0], tr[1], tr[2], tr[3]);
                 }
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
         if (owner) {
             store_env(a.st, env, e);
             if (a.buf.window_fill) a.buf.window_fill[env] = fill;
-            if (a.buf.conc_window)
+            if (a.buf.conc_window && !defer)
                 for (int k = 0; k < W; ++k) a.buf.conc_window[(size_t)env * W + k] = win[k * 32 + tid];
             if (a.buf.last_obs) {
 #pragma unroll
@@ -238,6 +249,12 @@ extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state*
     PLUME_CHECK_ARG(st->sin_tab && st->cos_tab && st->curriculum, "sin_tab/cos_tab/curriculum missing");
     PLUME_CHECK_ARG(buf->obs && buf->actions && buf->rewards && buf->values && buf->log_probs && buf->dones &&
                         buf->reached, "null rollout buffer");
+    if (flags & PLUME_FLAG_DEFER_STOP_HEAD) {
+        PLUME_CHECK_ARG(!(flags & PLUME_FLAG_STOP_TERMINATES),
+                        "a stop decision that ends the episode cannot be deferred out of the rollout loop");
+        PLUME_CHECK_ARG(buf->conc_sample && buf->fill_t && buf->window_fill,
+                        "the deferred stop head needs conc_sample, fill_t and window_fill");
+    }
     if (horizon <= 0 || st->n_envs <= 0) return 0;
     RolloutArgs a;
     a.c = make_cfg(*cfg);
@@ -247,7 +264,7 @@ extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state*
     a.horizon = horizon;
     a.flags = flags;
     a.nan_flag = nan_flag;
-    if (lstm && lstm->hidden > 0) {
+    if (lstm && lstm->hidden > 0 && !(flags & PLUME_FLAG_DEFER_STOP_HEAD)) {
         a.lstm = *lstm;
         PLUME_CHECK_ARG(lstm->window >= 1 && lstm->window <= kLstmMaxSteps, "stop-head window must be in [1,32]");
         PLUME_CHECK_ARG(lstm->w_ih && lstm->w_hh && lstm->b_ih && lstm->b_hh && lstm->w_peak && lstm->b_peak &&

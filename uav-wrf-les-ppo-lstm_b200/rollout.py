@@ -1,6 +1,11 @@
-"""Fused rollout driver: T lockstep iterations of policy + env step + LSTM stop head in ONE
+"""Fused rollout driver: T lockstep iterations of policy + env step (+ LSTM stop head) in ONE
 persistent kernel launch (csrc/rollout_kernel.cu), replacing the reference's python
-``while not done`` loop (PPOV2.1/train_ppo2.0.py:156-192, evaluate_with_lstm.py:61-82)."""
+``while not done`` loop (PPOV2.1/train_ppo2.0.py:156-192, evaluate_with_lstm.py:61-82).
+
+Where the stop decision does not end the episode (training rollouts: the reference only lets the
+stop head terminate in evaluate_with_lstm.py:77-80) the head does not feed back into the loop, so
+it is evaluated for the whole ``[T, N]`` segment by one throughput kernel afterwards
+(``plume_stop_head_segment``) -- same windows, same arithmetic, identical results."""
 from __future__ import annotations
 
 import ctypes as C
@@ -25,6 +30,7 @@ class RolloutEngine:
         self.buffer = PPOBuffer(horizon, N, dev, with_info=with_info, with_stop=stop_head is not None,
                                 with_trend=with_trend)
         self.conc_window = torch.zeros(N, self.window, dtype=torch.float32, device=dev)
+        self._window_next = torch.zeros_like(self.conc_window)      # ring written by the deferred head
         self.window_fill = torch.zeros(N, dtype=torch.int32, device=dev)
         self.last_obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -35,11 +41,18 @@ class RolloutEngine:
 
     @torch.no_grad()
     def collect(self, greedy: bool = False, stop_terminates: bool = False, forced_actions=None,
-                step_noise=None, noise_out=None, horizon: int | None = None) -> PPOBuffer:
-        """Runs ``horizon`` lockstep iterations and returns the filled buffer (asynchronous)."""
+                step_noise=None, noise_out=None, horizon: int | None = None,
+                defer_stop_head: bool | None = None) -> PPOBuffer:
+        """Runs ``horizon`` lockstep iterations and returns the filled buffer (asynchronous).
+        ``defer_stop_head`` (default: whenever the stop decision does not terminate episodes)
+        evaluates the LSTM head and the trend features after the loop in one batched kernel."""
         env, T = self.env, int(horizon or self.horizon)
         assert T <= self.horizon
+        defer = (self.stop_head is not None and not stop_terminates) if defer_stop_head is None else bool(defer_stop_head)
+        if defer and (self.stop_head is None or stop_terminates):
+            raise ValueError("defer_stop_head needs a stop head whose decision does not end the episode")
         flags = _lib.FLAG_AUTO_RESET
+        flags |= _lib.FLAG_DEFER_STOP_HEAD if defer else 0
         flags |= _lib.FLAG_GREEDY if greedy else 0
         flags |= _lib.FLAG_STOP_TERMINATES if stop_terminates else 0
         if forced_actions is not None:
@@ -57,8 +70,20 @@ class RolloutEngine:
             rc = self.lib.plume_rollout(C.byref(env.c_config), C.byref(env.c_state), self.model.flat.data_ptr(),
                                         C.byref(lp), C.byref(bufs), T, flags, self.nan_flag.data_ptr(),
                                         torch.cuda.current_stream(env.device).cuda_stream)
-        _lib.check(rc, "plume_rollout")
-        self.launches += 1
+            _lib.check(rc, "plume_rollout")
+            self.launches += 1
+            if defer:
+                b = self.buffer
+                rc = self.lib.plume_stop_head_segment(C.byref(lp), b.conc_sample.data_ptr(), b.fill_t.data_ptr(),
+                                                      _lib.ptr(b.src_dist), T, env.num_envs,
+                                                      self.conc_window.data_ptr(), self._window_next.data_ptr(),
+                                                      env.cfg.conc_peak, b.stop_prob.data_ptr(),
+                                                      b.stop_flag.data_ptr(), b.peak_pred.data_ptr(),
+                                                      _lib.ptr(b.trend),
+                                                      torch.cuda.current_stream(env.device).cuda_stream)
+                _lib.check(rc, "plume_stop_head_segment")
+                self.conc_window, self._window_next = self._window_next, self.conc_window
+                self.launches += 1
         self.buffer.filled = T
         return self.buffer
 

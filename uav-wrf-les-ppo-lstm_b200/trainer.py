@@ -40,8 +40,9 @@ class PlumeTrainer:
         self.iteration = 0
         self.last_losses = None
         n_mb = (num_envs * horizon + self.minibatch_size - 1) // self.minibatch_size
-        # my kernels per iteration: rollout, curriculum, gae scan + normalise, (fwd_bwd, wgrad2, clip_adam) per step
-        self.launches_per_iteration = 4 + 3 * self.cfg.epochs * n_mb
+        # my kernels per iteration: rollout (+ deferred stop head), curriculum, gae scan + normalise,
+        # (fwd_bwd, wgrad2, clip_adam) per step
+        self.launches_per_iteration = 4 + (1 if stop_head else 0) + 3 * self.cfg.epochs * n_mb
 
     def train_iteration(self, check_nan: bool = False):
         buf = self.engine.collect()

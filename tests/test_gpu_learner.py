@@ -73,8 +73,13 @@ def _oracle_grads(ora, cfg, S, A, LP, ADV, RET, V):
     return total.item(), pl.item(), vl.item(), ent.item()
 
 
-@pytest.mark.parametrize("M,mb_start,mb_size", [(256, 0, 256), (1000, 100, 333), (64, 0, 1), (4096, 1024, 2048)])
-def test_ppo_gradient_vs_autograd(M, mb_start, mb_size):
+@pytest.mark.parametrize("path", ["cuda", "tc"])
+@pytest.mark.parametrize("M,mb_start,mb_size", [(256, 0, 256), (1000, 100, 333), (64, 0, 1), (4096, 1024, 2048),
+                                                (60000, 5000, 50001)])
+def test_ppo_gradient_vs_autograd(M, mb_start, mb_size, path, monkeypatch):
+    """Both kernel families (CUDA-core 32-sample tiles, tcgen05 3xTF32 128-sample tiles) against autograd;
+    the largest case gives every CTA several tiles (TMEM accumulation across tiles, ragged last tile)."""
+    monkeypatch.setenv("PLUME_PPO_PATH", path)
     m = pb()
     cfg = po.config_for("2.1")
     torch.manual_seed(M)
@@ -145,15 +150,30 @@ def test_update_model_reproduces_reference_update():
     assert len(buf.states) == M
     losses = m.update_model(buf, model, opt, cfg=cfg, perms=list(g["perms"]))
     assert losses.shape == (cfg.epochs, 4)
+    # The yardstick is the same update carried out in float64 ("exact"): Adam's first steps move a
+    # weight by ~lr*g/(|g|+1e-8), which amplifies fp32 summation-order noise wherever gradients nearly
+    # cancel, so the reference's own float32 result is only an approximation of it too.  The kernels
+    # must be as close to the exact update as the reference's float32 run is.
+    exact = pp.OracleActorCritic().double()
+    exact.load_state_dict({k: v.double() for k, v in init.items()})
+    adv32 = pp.gae_quirk(torch.from_numpy(g["rewards"]), torch.from_numpy(g["values"]), torch.from_numpy(g["dones"]),
+                         cfg.gamma, cfg.lam)
+    adv32, ret32 = pp.normalise_advantages(adv32, torch.from_numpy(g["values"]))
+    pp.ppo_update(exact, torch.optim.Adam(exact.parameters(), lr=cfg.learning_rate),
+                  torch.from_numpy(g["states"]).double(), torch.from_numpy(g["actions"]), None,
+                  torch.from_numpy(g["values"]).double(), torch.from_numpy(g["log_probs"]).double(), None,
+                  po.config_for("2.1"), perms=list(g["perms"]), adv_ret=(adv32.double(), ret32.double()))
+    exact_sd = exact.state_dict()
     sd = model.state_dict()
     num = den = 0.0
     for k, v in sd.items():
         final = torch.from_numpy(g["final." + k])
-        # Adam's first steps move each weight by ~lr*g/(|g|+1e-8): entries whose gradient is ~1e-8 amplify
-        # fp32 summation-order noise, so the bound is 2% of the total movement (5 steps x lr = 1.5e-4)
-        diff = (v.cpu() - final).abs()
-        assert diff.max().item() <= 5 * cfg.learning_rate, (k, diff.max().item())
-        assert (diff > 3e-7).float().mean().item() < 0.05, (k, (diff > 3e-7).float().mean().item())
+        ex = exact_sd[k].reshape(final.shape)
+        err_gpu = (v.cpu().double() - ex).abs()
+        err_ref = (final.double() - ex).abs()
+        assert (v.cpu() - final).abs().max().item() <= 5 * cfg.learning_rate, k
+        assert err_gpu.mean().item() <= 4.0 * err_ref.mean().item() + 5e-9, (k, err_gpu.mean().item(),
+                                                                               err_ref.mean().item())
         d_ref = (final - init[k]).flatten().double()
         d_gpu = (v.cpu() - init[k]).flatten().double()
         num += float((d_ref * d_gpu).sum())

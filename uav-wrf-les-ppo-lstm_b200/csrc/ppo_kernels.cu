@@ -14,27 +14,13 @@
 // Algorithmic bytes per sample (DESIGN.md "K6"): gather obs 24 + action 4 + old logp 4 + adv 4 +
 // ret 4 + old value 4 = 44 B read; workspace dz2 512 + x 32 + stats 8 = 552 B written by A and
 // read by B.  FLOP per sample: forward 70 144, backward ~140 288.
+#include <cstdlib>
+
 #include "ppo_loss.cuh"
 
 namespace plume {
 
 constexpr int kWsFloatsPerSample = 128 + 8 + 2;
-
-struct PpoArgs {
-    plume_ppo_batch batch;
-    const long long* perm;
-    unsigned long long perm_seed;
-    int epoch;
-    long long mb_start, mb_size;
-    float inv_global;         // 1 / mb_size_global
-    float clip_eps, entropy_beta;
-    float* grads;
-    double* loss_out;
-    int32_t* nan_flag;
-    float* ws_dz2;            // [mb_size][128]
-    float* ws_x;              // [mb_size][8]
-    float* ws_stat;           // [mb_size][2]  LN1 mean, rstd
-};
 
 __global__ void __launch_bounds__(kMlpThreads, 1) ppo_fwd_bwd_kernel(const float* __restrict__ params, PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -410,9 +396,22 @@ __global__ void __launch_bounds__(256, 1) ppo_wgrad2_kernel(const float* __restr
 
 using namespace plume;
 
+// Which kernel family computes a minibatch: the tensor-core path (ppo_tc_kernels.cu, 128-sample tiles) from
+// kTcMinBatch samples on, the CUDA-core path (32-sample tiles, more CTAs for tiny batches such as the
+// reference's 256) below.  PLUME_PPO_PATH=tc|cuda forces one of them (tests compare the two).
+constexpr int64_t kTcMinBatch = 1024;
+static bool use_tc_path(int64_t mb_size) {
+    const char* e = getenv("PLUME_PPO_PATH");
+    if (e && e[0] == 't') return true;
+    if (e && e[0] == 'c') return false;
+    return mb_size >= kTcMinBatch;
+}
+
 extern "C" int64_t plume_ppo_workspace_bytes(int64_t mb_size) {
     const int64_t padded = ((mb_size + kTileM - 1) / kTileM) * kTileM;
-    return padded * kWsFloatsPerSample * (int64_t)sizeof(float) + 256;
+    const int64_t cuda_path = padded * kWsFloatsPerSample * (int64_t)sizeof(float) + 256;
+    const int64_t tc_path = ppo_tc_workspace_bytes();
+    return cuda_path > tc_path ? cuda_path : tc_path;
 }
 
 extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int64_t* perm,
@@ -449,6 +448,8 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
     a.grads = grads;
     a.loss_out = loss_out;
     a.nan_flag = nan_flag;
+    a.ws_dz2 = a.ws_x = a.ws_stat = nullptr;
+    if (use_tc_path(mb_size)) return launch_ppo_tc(params, a, workspace, as_stream(stream));
     const int64_t padded = ((mb_size + kTileM - 1) / kTileM) * kTileM;
     uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
     a.ws_dz2 = reinterpret_cast<float*>(wsp);

@@ -5,6 +5,27 @@
 
 namespace plume {
 
+// arguments of one minibatch gradient (both the CUDA-core and the tensor-core kernels)
+struct PpoArgs {
+    plume_ppo_batch batch;
+    const long long* perm;
+    unsigned long long perm_seed;
+    int epoch;
+    long long mb_start, mb_size;
+    float inv_global;         // 1 / mb_size_global
+    float clip_eps, entropy_beta;
+    float* grads;
+    double* loss_out;
+    int32_t* nan_flag;
+    float* ws_dz2;            // [mb_size][128]
+    float* ws_x;              // [mb_size][8]
+    float* ws_stat;           // [mb_size][2]  LN1 mean, rstd
+};
+
+// tensor-core path (ppo_tc_kernels.cu)
+int64_t ppo_tc_workspace_bytes();
+int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s);
+
 struct SampleLoss {
     float dout[6];      // d total / d logits[0..4], d total / d value, already divided by the global batch
     float pol, val, ent;

@@ -1,0 +1,749 @@
+// ppo_tc_kernels.cu -- K6 on the sm_100a tensor cores: the PPO minibatch gradient
+// (train_ppo2.0.py:42-85) with the three GEMM-shaped parts of the actor-critic's 256->128 layer
+// (model.py:23) on tcgen05.mma (kind::tf32, 3xTF32 split = fp32-grade accuracy, accumulators in
+// TMEM) and everything else (6->256 layer, both LayerNorms, heads, loss, all the reductions) on the
+// CUDA cores of the same persistent CTA.  One CTA per SM, 128-sample tiles, 256 threads.
+//
+//   G1  z2[s][o]   = sum_i  h1[s][i] W2[o][i]        A = h1 (produced chunk by chunk from the 6 inputs),
+//                                                     B = W2, pre-split, streamed from L2 with cp.async
+//   G2  dh1[s][i]  = sum_o  dz2[s][o] W2[o][i]       A = dz2 (from shared memory), B = W2^T pre-split
+//   G3  dW2[o][i] += sum_s  dz2[s][o] h1[s][i]       A = dz2^T, B = h1^T (recomputed, K-major along s);
+//                                                     accumulates in TMEM across ALL tiles of the CTA
+//
+// TMEM map (512 columns): [0,128) G1 result, then G2 result for inputs 0..127; [128,256) G2 result for
+// inputs 128..255; [256,512) the persistent dW2 accumulator (row = output o, column = input i).
+//
+// Layer 1 never materialises dz1: with dy1 = relu'(y1) o dh1 and the per-sample LayerNorm scalars
+// m1 = mean_i(g1 dy1), m2 = mean_i(g1 dy1 xhat1), every layer-1 gradient is a linear function of
+//   P[i][c] = sum_s dy1[s][i] * {rstd x_0..x_5, rstd, 1}[s][c]     (column sums, accumulated per thread)
+// and of 35 per-sample scalar sums (S0, S[6], R[7], Q[6][6] symmetric); see the epilogue at the end
+// of the kernel.  z1 - mean(z1) is evaluated directly from centred weights (W1 - column mean), so
+// no mean pass is needed.  The algebra was checked against autograd in float64 and its float32
+// error matches autograd's own (profiles/r1_notes.md).
+//
+// Algorithmic bytes per sample: 44 B gathered (obs 24, action 4, old logp 4, adv 4, ret 4, old value 4);
+// nothing else leaves the SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 for the split),
+// ~14 000 on the CUDA cores.
+#include "ppo_loss.cuh"
+#include "tc_gemm.cuh"
+
+namespace plume {
+
+constexpr int kTcTile = 128;
+constexpr int kTcThreads = 256;
+constexpr int kXhStride = 132;             // [128][132]: conflict-free float4 rows and columns
+constexpr int kStageStride = 129;          // [128][129]: transposed dy1 staging
+constexpr int kChunkFloats = 128 * tc::kChunkK;
+
+struct TcSmem {
+    static constexpr int ring = 0;                                   // [2 stages][A_hi, A_lo, B_hi, B_lo][4096]
+    static constexpr int xh = ring + 2 * 4 * kChunkFloats;           // [128][132] xhat2 -> dz2 -> dy1 staging
+    static constexpr int W1c = xh + kTcTile * kXhStride;             // [6][256] centred feature.0.weight, k-major
+    static constexpr int P1 = W1c + 6 * 256;                         // [3][256] centred bias, LN1 gamma, beta
+    static constexpr int P2 = P1 + 3 * 256;                          // [3][128] feature.3.bias, LN2 gamma, beta
+    static constexpr int Wh = P2 + 3 * 128;                          // [128][8] heads
+    static constexpr int bh = Wh + 128 * 8;                          // [8]
+    static constexpr int x = bh + 8;                                 // [128][8] x0..x5, rstd1, 0
+    static constexpr int dout = x + kTcTile * 8;                     // [128][8] d loss / d (logits, value)
+    static constexpr int sc = dout + kTcTile * 8;                    // [128][4] rstd2, m1, m2, 0
+    static constexpr int exch = sc + kTcTile * 4;                    // [2][128][8] column-half exchange
+    static constexpr int total = exch + 2 * kTcTile * 8;
+};
+static_assert(TcSmem::total * 4 + 64 <= 227 * 1024, "ppo_tc_kernel: shared memory plan exceeds 227 KB");
+static_assert(kTcTile * kStageStride <= kTcTile * kXhStride, "dy1 staging must fit in the xhat region");
+
+// layout of the pre-split weight workspace (floats)
+constexpr int kW2SplitG1Hi = 0;                       // [8 chunks][128 out][32 in]   (K = in)
+constexpr int kW2SplitG1Lo = 32768;
+constexpr int kW2SplitG2Hi = 65536;                   // [2 halves][4 chunks][128 in][32 out] (K = out)
+constexpr int kW2SplitG2Lo = 98304;
+constexpr int kW2SplitFloats = 131072;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
+    tc::split_tf32(v.x, h.x, l.x);
+    tc::split_tf32(v.y, h.y, l.y);
+    tc::split_tf32(v.z, h.z, l.z);
+    tc::split_tf32(v.w, h.w, l.w);
+}
+
+// ---- W2 -> hi/lo operand chunks in the canonical K-major layout (once per minibatch) ---------------
+__global__ void ppo_tc_prep_kernel(const float* __restrict__ params, float* __restrict__ w2s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // element of W2[o][in]
+    if (i >= 128 * 256) return;
+    const int o = i >> 8, in = i & 255;
+    float hi, lo;
+    tc::split_tf32(params[PLUME_OFF_W2 + i], hi, lo);
+    const int g1 = (in >> 5) * kChunkFloats + tc::chunk_offset(o, in & 31);
+    w2s[kW2SplitG1Hi + g1] = hi;
+    w2s[kW2SplitG1Lo + g1] = lo;
+    const int g2 = ((in >> 7) * 4 + (o >> 5)) * kChunkFloats + tc::chunk_offset(in & 127, o & 31);
+    w2s[kW2SplitG2Hi + g2] = hi;
+    w2s[kW2SplitG2Lo + g2] = lo;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s) {
+    extern __shared__ __align__(128) float sm[];     // no-swizzle operand layouts need 16 B alignment only
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wq = warp & 3, ch = warp >> 2;          // TMEM lane quarter / column half of this warp
+    const int srow = wq * 32 + lane;                  // TMEM lane = tile row owned in the epilogues
+    const int r128 = tid & 127, uh = tid >> 7;        // (row, half) mapping of the producer phases
+
+    // ---- one-time setup ----------------------------------------------------------------------------
+    if (tid == 0) {
+        tc::mbar_init(&bar[0], 1);
+        tc::mbar_init(&bar[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    if (tid < 7) {          // column means of feature.0.weight (k < 6) and the mean of feature.0.bias
+        float m = 0.0f;
+        for (int o = 0; o < 256; ++o) m += (tid < 6) ? params[PLUME_OFF_W1 + o * 6 + tid] : params[PLUME_OFF_B1 + o];
+        sm[TcSmem::exch + tid] = m * (1.0f / 256.0f);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    for (int i = tid; i < 6 * 256; i += kTcThreads) {
+        const int o = i / 6, k = i - o * 6;
+        sm[TcSmem::W1c + k * 256 + o] = params[PLUME_OFF_W1 + i] - sm[TcSmem::exch + k];
+    }
+    for (int i = tid; i < 256; i += kTcThreads) {
+        sm[TcSmem::P1 + i] = params[PLUME_OFF_B1 + i] - sm[TcSmem::exch + 6];
+        sm[TcSmem::P1 + 256 + i] = params[PLUME_OFF_G1 + i];
+        sm[TcSmem::P1 + 512 + i] = params[PLUME_OFF_BE1 + i];
+    }
+    for (int i = tid; i < 128; i += kTcThreads) {
+        sm[TcSmem::P2 + i] = params[PLUME_OFF_B2 + i];
+        sm[TcSmem::P2 + 128 + i] = params[PLUME_OFF_G2 + i];
+        sm[TcSmem::P2 + 256 + i] = params[PLUME_OFF_BE2 + i];
+    }
+    for (int i = tid; i < 128 * 8; i += kTcThreads) {
+        const int k = i >> 3, o = i & 7;
+        float w = 0.0f;
+        if (o < 5) w = params[PLUME_OFF_WA + o * 128 + k];
+        else if (o == 5) w = params[PLUME_OFF_WC + k];
+        sm[TcSmem::Wh + i] = w;
+    }
+    if (tid < 8) sm[TcSmem::bh + tid] = tid < 5 ? params[PLUME_OFF_BA + tid] : (tid == 5 ? params[PLUME_OFF_BC] : 0.0f);
+    __syncthreads();
+
+    const uint32_t idesc = tc::make_idesc_tf32(128, 128);
+    float* const xh = sm + TcSmem::xh;
+    const float* const W1c = sm + TcSmem::W1c;
+    const float* const P1 = sm + TcSmem::P1;
+    const float* const P2 = sm + TcSmem::P2;
+    const float* const Wh = sm + TcSmem::Wh;
+    float* const xt = sm + TcSmem::x;
+    float* const exch = sm + TcSmem::exch;
+
+    uint32_t step = 0;        // ring steps issued so far (uniform across the CTA)
+    // stage buffers of ring step st: which = 0 A_hi, 1 A_lo, 2 B_hi, 3 B_lo
+    auto stage_buf = [&](uint32_t st, int which) -> float* {
+        return sm + TcSmem::ring + ((st & 1u) * 4 + which) * kChunkFloats;
+    };
+    // wait until the MMAs that last read this step's stage have completed
+    auto acquire = [&](uint32_t st) {
+        const uint32_t use = st >> 1;
+        if (use >= 1) tc::mbar_wait(&bar[st & 1u], (use - 1) & 1u);
+    };
+    // B operand chunk (hi + lo, 16 KB each) from the pre-split weights: 8 x 16 B per thread
+    auto load_b = [&](uint32_t st, const float* hi, const float* lo) {
+        float4* bh4 = reinterpret_cast<float4*>(stage_buf(st, 2));
+        float4* bl4 = reinterpret_cast<float4*>(stage_buf(st, 3));
+        const float4* gh = reinterpret_cast<const float4*>(hi);
+        const float4* gl = reinterpret_cast<const float4*>(lo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            cp_async16(bh4 + tid + q * kTcThreads, gh + tid + q * kTcThreads);
+            cp_async16(bl4 + tid + q * kTcThreads, gl + tid + q * kTcThreads);
+        }
+    };
+    // operands of step st are complete in shared memory: make them visible to the tensor core, issue
+    auto publish_and_issue = [&](uint32_t st, uint32_t col, bool first) {
+        cp_async_wait_all();
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            tc::mma_chunk_3xtf32(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
+                                 idesc, first);
+            tc::mma_commit(&bar[st & 1u]);
+        }
+    };
+    // every MMA issued so far has completed
+    auto wait_all_mma = [&]() {
+        const uint32_t last = step - 1;
+        tc::mbar_wait(&bar[last & 1u], (last >> 1) & 1u);
+        tc::tc_fence_after();
+    };
+
+    // ---- persistent accumulators ---------------------------------------------------------------------
+    float g_b2 = 0.0f, g_g2 = 0.0f, g_be2 = 0.0f, g_wh[6] = {0, 0, 0, 0, 0, 0};   // (o = r128, half uh)
+    float g_bh[6] = {0, 0, 0, 0, 0, 0};                                          // sample threads (tid < 128)
+    float Pacc[2][8];                                                             // (input r128 + 128 h, half uh)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Pacc[h][c] = 0.0f;
+    float sS0 = 0.0f, sS[6] = {0, 0, 0, 0, 0, 0}, sR[7] = {0, 0, 0, 0, 0, 0, 0}, sQ[21];   // sample threads
+#pragma unroll
+    for (int i = 0; i < 21; ++i) sQ[i] = 0.0f;
+    double l_tot = 0.0, l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
+
+    const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const bool first_tile = (tile == (long long)blockIdx.x);
+        const long long base = tile * kTcTile;
+        const int n_valid = (int)((a.mb_size - base) < kTcTile ? (a.mb_size - base) : kTcTile);
+
+        // ---- Ph0: gather (sample thread tid < 128 keeps the scalars of its sample in registers) --------
+        float r_adv = 0.0f, r_ret = 0.0f, r_vold = 0.0f, r_lpold = 0.0f;
+        int r_act = 0;
+        if (tid < kTcTile) {
+            float xv[6] = {0, 0, 0, 0, 0, 0};
+            if (tid < n_valid) {
+                const long long pos = a.mb_start + base + tid;
+                const long long idx = a.perm ? a.perm[pos]
+                                             : (long long)feistel_permute((uint64_t)pos, (uint64_t)a.batch.total,
+                                                                          a.perm_seed, (uint32_t)a.epoch);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) xv[k] = a.batch.obs[idx * 6 + k];
+                r_adv = a.batch.advantages[idx];
+                r_ret = a.batch.returns[idx];
+                r_vold = a.batch.old_values[idx];
+                r_lpold = a.batch.old_log_probs[idx];
+                r_act = a.batch.actions[idx];
+            }
+            *reinterpret_cast<float4*>(xt + tid * 8) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(xv[4], xv[5], 0.0f, 0.0f);
+        }
+        __syncthreads();
+
+        // ---- Ph1: LayerNorm-1 statistics: thread = (sample r128, 128 of the 256 outputs) ----------------
+        float xr[6];
+        {
+            const float4 x0 = *reinterpret_cast<const float4*>(xt + r128 * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(xt + r128 * 8 + 4);
+            xr[0] = x0.x; xr[1] = x0.y; xr[2] = x0.z; xr[3] = x0.w; xr[4] = x1.x; xr[5] = x1.y;
+            float sq = 0.0f;
+#pragma unroll 4
+            for (int u = 0; u < 32; ++u) {
+                const int in0 = uh * 128 + 4 * u;
+                float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
+                    z.x = fmaf(xr[k], w.x, z.x);
+                    z.y = fmaf(xr[k], w.y, z.y);
+                    z.z = fmaf(xr[k], w.z, z.z);
+                    z.w = fmaf(xr[k], w.w, z.w);
+                }
+                sq = fmaf(z.x, z.x, sq);
+                sq = fmaf(z.y, z.y, sq);
+                sq = fmaf(z.z, z.z, sq);
+                sq = fmaf(z.w, z.w, sq);
+            }
+            exch[(uh * kTcTile + r128) * 8] = sq;
+        }
+        __syncthreads();
+        if (tid < kTcTile) {
+            const float var = (exch[tid * 8] + exch[(kTcTile + tid) * 8]) * (1.0f / 256.0f);
+            xt[tid * 8 + 6] = 1.0f / sqrtf(var + kLnEps);
+        }
+        __syncthreads();
+        const float rstd1 = xt[r128 * 8 + 6];
+
+        // ---- Ph2: G1 forward, K = 256 inputs in 8 chunks; thread = (sample r128, 4 of the 8 units) ----
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t st = step;
+            acquire(st);
+            load_b(st, w2s + kW2SplitG1Hi + c * kChunkFloats, w2s + kW2SplitG1Lo + c * kChunkFloats);
+            float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
+            float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const int u = 4 * uh + uu, in0 = 32 * c + 4 * u;
+                float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
+                    z.x = fmaf(xr[k], w.x, z.x);
+                    z.y = fmaf(xr[k], w.y, z.y);
+                    z.z = fmaf(xr[k], w.z, z.z);
+                    z.w = fmaf(xr[k], w.w, z.w);
+                }
+                const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
+                const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
+                float4 h;
+                h.x = fmaxf(fmaf(z.x * rstd1, g.x, be.x), 0.0f);
+                h.y = fmaxf(fmaf(z.y * rstd1, g.y, be.y), 0.0f);
+                h.z = fmaxf(fmaf(z.z * rstd1, g.z, be.z), 0.0f);
+                h.w = fmaxf(fmaf(z.w * rstd1, g.w, be.w), 0.0f);
+                float4 hi, lo;
+                split4(h, hi, lo);
+                const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
+                ah[f] = hi;
+                al[f] = lo;
+            }
+            publish_and_issue(st, 0u, c == 0);
+            ++step;
+        }
+        wait_all_mma();
+
+        // ---- Ph3: LN2, heads, loss, LN2-backward means: thread = (sample srow, 64 of the 128 outputs) ----
+        float v[64];
+        {
+            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * ch);
+            tc::tmem_ld32(taddr, v);
+            tc::tmem_ld32(taddr + 32u, v + 32);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                v[j] += P2[64 * ch + j];
+                sum += v[j];
+            }
+            float* mine = exch + (ch * kTcTile + srow) * 8;
+            const float* other = exch + ((ch ^ 1) * kTcTile + srow) * 8;
+            mine[6] = sum;
+            __syncthreads();
+            const float mean = (sum + other[6]) * (1.0f / 128.0f);
+            float sq = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float d = v[j] - mean;
+                sq = fmaf(d, d, sq);
+            }
+            mine[7] = sq;
+            __syncthreads();
+            const float rstd2 = 1.0f / sqrtf((sq + other[7]) * (1.0f / 128.0f) + kLnEps);
+            float head[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int o = 64 * ch + j;
+                const float x_hat = (v[j] - mean) * rstd2;
+                v[j] = x_hat;
+                const float h2 = fmaxf(fmaf(x_hat, P2[128 + o], P2[256 + o]), 0.0f);
+                const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);
+                head[0] = fmaf(h2, w0.x, head[0]);
+                head[1] = fmaf(h2, w0.y, head[1]);
+                head[2] = fmaf(h2, w0.z, head[2]);
+                head[3] = fmaf(h2, w0.w, head[3]);
+                head[4] = fmaf(h2, w1.x, head[4]);
+                head[5] = fmaf(h2, w1.y, head[5]);
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                *reinterpret_cast<float4*>(xh + srow * kXhStride + 64 * ch + 4 * q) =
+                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) mine[k] = head[k];
+            __syncthreads();
+            if (ch == 0) {          // srow == tid: the thread that gathered this sample
+                float dl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (srow < n_valid) {
+                    float o6[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) o6[k] = head[k] + other[k] + sm[TcSmem::bh + k];
+                    const SampleLoss L = ppo_sample_loss(o6, r_act, r_adv, r_ret, r_vold, r_lpold, a.clip_eps,
+                                                         a.entropy_beta, a.inv_global);
+                    if (L.nan) atomicExch(a.nan_flag, 1);                           // train_ppo2.0.py:57-61
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        dl[k] = L.dout[k];
+                        g_bh[k] += L.dout[k];
+                    }
+                    l_pol += (double)L.pol;
+                    l_val += (double)L.val;
+                    l_ent += (double)L.ent;
+                    l_tot += (double)L.pol + (double)L.val - (double)a.entropy_beta * (double)L.ent;
+                }
+                *reinterpret_cast<float4*>(sm + TcSmem::dout + srow * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+                *reinterpret_cast<float4*>(sm + TcSmem::dout + srow * 8 + 4) = make_float4(dl[4], dl[5], 0.0f, 0.0f);
+            }
+            __syncthreads();
+            const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8 + 4);
+            float m1p = 0.0f, m2p = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int o = 64 * ch + j;
+                const float g2 = P2[128 + o];
+                const float y = fmaf(v[j], g2, P2[256 + o]);
+                const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);
+                float dh = d0.x * w0.x;
+                dh = fmaf(d0.y, w0.y, dh);
+                dh = fmaf(d0.z, w0.z, dh);
+                dh = fmaf(d0.w, w0.w, dh);
+                dh = fmaf(d1.x, w1.x, dh);
+                dh = fmaf(d1.y, w1.y, dh);
+                const float dxh = (y > 0.0f) ? dh * g2 : 0.0f;
+                m1p += dxh;
+                m2p = fmaf(dxh, v[j], m2p);
+            }
+            mine[6] = m1p;
+            mine[7] = m2p;
+            __syncthreads();
+            if (ch == 0)
+                *reinterpret_cast<float4*>(sm + TcSmem::sc + srow * 4) =
+                    make_float4(rstd2, (m1p + other[6]) * (1.0f / 128.0f), (m2p + other[7]) * (1.0f / 128.0f), 0.0f);
+            __syncthreads();
+        }
+
+        // ---- Ph4: heads + LN2 backward per column: thread = (output r128, 64 of the 128 samples) ---------
+        {
+            const int o = r128;
+            const float g2 = P2[128 + o], be2 = P2[256 + o];
+            float wrow[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) wrow[j] = Wh[o * 8 + j];
+#pragma unroll 4
+            for (int q = 0; q < 64; ++q) {
+                const int s = 64 * uh + q;
+                const float x_hat = xh[s * kXhStride + o];
+                const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8);
+                const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8 + 4);
+                const float4 sc = *reinterpret_cast<const float4*>(sm + TcSmem::sc + s * 4);
+                const float d[6] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y};
+                const float y = fmaf(x_hat, g2, be2);
+                const float h2v = fmaxf(y, 0.0f);
+                float dh = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    dh = fmaf(d[j], wrow[j], dh);
+                    g_wh[j] = fmaf(d[j], h2v, g_wh[j]);
+                }
+                const float dy = (y > 0.0f) ? dh : 0.0f;
+                g_g2 = fmaf(dy, x_hat, g_g2);
+                g_be2 += dy;
+                const float dz = sc.x * (dy * g2 - sc.y - x_hat * sc.z);
+                g_b2 += dz;
+                xh[s * kXhStride + o] = dz;                       // dz2 replaces xhat2
+            }
+        }
+        __syncthreads();
+
+        // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 4 chunks ------------
+        for (int hN = 0; hN < 2; ++hN) {
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t st = step;
+                acquire(st);
+                load_b(st, w2s + kW2SplitG2Hi + (hN * 4 + c) * kChunkFloats,
+                       w2s + kW2SplitG2Lo + (hN * 4 + c) * kChunkFloats);
+                float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
+                float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int u = 4 * uh + uu;
+                    const float4 d = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 32 * c + 4 * u);
+                    float4 hi, lo;
+                    split4(d, hi, lo);
+                    const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
+                    ah[f] = hi;
+                    al[f] = lo;
+                }
+                publish_and_issue(st, (uint32_t)(128 * hN), c == 0);
+                ++step;
+            }
+        }
+
+        // ---- Ph7: G3 dW2 += dz2^T . h1, K = 128 samples in 4 chunks x two halves of the inputs -----------
+        for (int c = 0; c < 4; ++c) {
+            for (int hN = 0; hN < 2; ++hN) {
+                const uint32_t st = step;
+                acquire(st);
+                float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
+                float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
+                float4* bh4 = reinterpret_cast<float4*>(stage_buf(st, 2));
+                float4* bl4 = reinterpret_cast<float4*>(stage_buf(st, 3));
+                const int in = 128 * hN + r128;
+                float w[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];
+                const float b1c = P1[in], g1 = P1[256 + in], be1 = P1[512 + in];
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int u = 4 * uh + uu, s0 = 32 * c + 4 * u;
+                    const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
+                    // A: dz2^T, row = output r128, 4 consecutive samples
+                    float4 d;
+                    d.x = xh[(s0 + 0) * kXhStride + r128];
+                    d.y = xh[(s0 + 1) * kXhStride + r128];
+                    d.z = xh[(s0 + 2) * kXhStride + r128];
+                    d.w = xh[(s0 + 3) * kXhStride + r128];
+                    float4 hi, lo;
+                    split4(d, hi, lo);
+                    ah[f] = hi;
+                    al[f] = lo;
+                    // B: h1^T, row = input `in`, the same 4 samples (recomputed from the 6 inputs)
+                    float hv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 x0 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8);
+                        const float4 x1 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8 + 4);
+                        float z = b1c;
+                        z = fmaf(x0.x, w[0], z);
+                        z = fmaf(x0.y, w[1], z);
+                        z = fmaf(x0.z, w[2], z);
+                        z = fmaf(x0.w, w[3], z);
+                        z = fmaf(x1.x, w[4], z);
+                        z = fmaf(x1.y, w[5], z);
+                        hv[i] = fmaxf(fmaf(z * x1.z, g1, be1), 0.0f);
+                    }
+                    split4(make_float4(hv[0], hv[1], hv[2], hv[3]), hi, lo);
+                    bh4[f] = hi;
+                    bl4[f] = lo;
+                }
+                publish_and_issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0);
+                ++step;
+            }
+        }
+        // (the acquires above waited for every G2 MMA; the xhat region is free after the last publish)
+
+        // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
+        {
+            tc::tc_fence_after();
+            float m1p = 0.0f, m2p = 0.0f;
+#pragma unroll
+            for (int hN = 0; hN < 2; ++hN) {          // unrolled: Pacc[hN] must stay in registers
+                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 * hN + 64 * ch);
+                tc::tmem_ld32(taddr, v);
+                tc::tmem_ld32(taddr + 32u, v + 32);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                // this thread's sample: inputs + rstd1
+                const float4 x0 = *reinterpret_cast<const float4*>(xt + srow * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
+                const float xs[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+#pragma unroll
+                for (int j4 = 0; j4 < 16; ++j4) {
+                    const int in0 = 128 * hN + 64 * ch + 4 * j4;
+                    float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
+                        z.x = fmaf(xs[k], w.x, z.x);
+                        z.y = fmaf(xs[k], w.y, z.y);
+                        z.z = fmaf(xs[k], w.z, z.z);
+                        z.w = fmaf(xs[k], w.w, z.w);
+                    }
+                    const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
+                    const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
+                    const float zz[4] = {z.x, z.y, z.z, z.w}, gg[4] = {g.x, g.y, g.z, g.w},
+                                bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float x_hat = zz[jj] * x1.z;
+                        const float y = fmaf(x_hat, gg[jj], bb[jj]);
+                        const float dy = (y > 0.0f) ? v[4 * j4 + jj] : 0.0f;
+                        const float t = dy * gg[jj];
+                        m1p += t;
+                        m2p = fmaf(t, x_hat, m2p);
+                        xh[(64 * ch + 4 * j4 + jj) * kStageStride + srow] = dy;     // staging [input][sample]
+                    }
+                }
+                __syncthreads();
+                // column sums: thread = (input r128 of this half, 64 of the 128 samples)
+#pragma unroll 4
+                for (int q = 0; q < 64; ++q) {
+                    const int s = 64 * uh + q;
+                    const float dy = xh[r128 * kStageStride + s];
+                    const float4 y0 = *reinterpret_cast<const float4*>(xt + s * 8);
+                    const float4 y1 = *reinterpret_cast<const float4*>(xt + s * 8 + 4);
+                    const float dr = dy * y1.z;
+                    Pacc[hN][0] = fmaf(dr, y0.x, Pacc[hN][0]);
+                    Pacc[hN][1] = fmaf(dr, y0.y, Pacc[hN][1]);
+                    Pacc[hN][2] = fmaf(dr, y0.z, Pacc[hN][2]);
+                    Pacc[hN][3] = fmaf(dr, y0.w, Pacc[hN][3]);
+                    Pacc[hN][4] = fmaf(dr, y1.x, Pacc[hN][4]);
+                    Pacc[hN][5] = fmaf(dr, y1.y, Pacc[hN][5]);
+                    Pacc[hN][6] += dr;
+                    Pacc[hN][7] += dy;
+                }
+                __syncthreads();
+            }
+            float* mine = exch + (ch * kTcTile + srow) * 8;
+            const float* other = exch + ((ch ^ 1) * kTcTile + srow) * 8;
+            mine[6] = m1p;
+            mine[7] = m2p;
+            __syncthreads();
+            if (ch == 0) {          // per-sample scalar sums of the layer-1 backward
+                const float m1 = (m1p + other[6]) * (1.0f / 256.0f), m2 = (m2p + other[7]) * (1.0f / 256.0f);
+                const float4 x0 = *reinterpret_cast<const float4*>(xt + srow * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
+                const float xs[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+                const float rs = x1.z;
+                const float a1 = rs * m1, a2 = rs * rs * m2;
+                sS0 += a1;
+                sR[6] += a2;
+                int qi = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    sS[k] = fmaf(a1, xs[k], sS[k]);
+                    const float ax = a2 * xs[k];
+                    sR[k] += ax;
+#pragma unroll
+                    for (int k2 = k; k2 < 6; ++k2) {
+                        sQ[qi] = fmaf(ax, xs[k2], sQ[qi]);
+                        ++qi;
+                    }
+                }
+            }
+            __syncthreads();       // exch / x tile / staging are rewritten by the next tile
+        }
+    }
+
+    // ---- flush ------------------------------------------------------------------------------------------
+    float* g = a.grads;
+    if (step > 0) {
+        wait_all_mma();
+        // dW2 accumulator: TMEM lane = output srow, this warp's column half = inputs [128 ch, 128 ch + 128)
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float vv[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(256 + 128 * ch + 32 * q), vv);
+            tc::tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(g + PLUME_OFF_W2 + srow * 256 + 128 * ch + 32 * q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                atomicAdd(dst + i, make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]));
+        }
+        tc::tc_fence_before();
+    }
+    {
+        const int o = r128;
+        atomicAdd(g + PLUME_OFF_B2 + o, g_b2);
+        atomicAdd(g + PLUME_OFF_G2 + o, g_g2);
+        atomicAdd(g + PLUME_OFF_BE2 + o, g_be2);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) atomicAdd(g + PLUME_OFF_WA + j * 128 + o, g_wh[j]);
+        atomicAdd(g + PLUME_OFF_WC + o, g_wh[5]);
+    }
+    // layer 1: combine the two sample halves of P and the CTA's per-sample scalar sums
+    __syncthreads();
+    float* pbuf = xh;                      // [2 uh][256 inputs][8]
+    float* sbuf = xh + 2 * 256 * 8;        // [4 warps][48]
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pbuf[(uh * 256 + 128 * h + r128) * 8 + c] = Pacc[h][c];
+    if (tid < kTcTile) {
+        float red[41];
+        red[0] = sS0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) red[1 + k] = sS[k];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) red[7 + k] = sR[k];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) red[14 + k] = sQ[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) red[35 + k] = g_bh[k];
+#pragma unroll
+        for (int k = 0; k < 41; ++k) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 41; ++k) sbuf[warp * 48 + k] = red[k];
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            l_tot += __shfl_xor_sync(0xffffffffu, l_tot, off);
+            l_pol += __shfl_xor_sync(0xffffffffu, l_pol, off);
+            l_val += __shfl_xor_sync(0xffffffffu, l_val, off);
+            l_ent += __shfl_xor_sync(0xffffffffu, l_ent, off);
+        }
+        if (lane == 0) {
+            const double inv = (double)a.inv_global;
+            atomicAdd(a.loss_out + 0, l_tot * inv);
+            atomicAdd(a.loss_out + 1, l_pol * inv);
+            atomicAdd(a.loss_out + 2, l_val * inv);
+            atomicAdd(a.loss_out + 3, l_ent * inv);
+        }
+    }
+    __syncthreads();
+    {
+        float S[41];
+#pragma unroll
+        for (int k = 0; k < 41; ++k) S[k] = sbuf[k] + sbuf[48 + k] + sbuf[96 + k] + sbuf[144 + k];
+        if (tid < 5) atomicAdd(g + PLUME_OFF_BA + tid, S[35 + tid]);
+        if (tid == 5) atomicAdd(g + PLUME_OFF_BC, S[40]);
+        const int in = tid;                  // 256 threads = 256 layer-1 outputs
+        float P[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) P[c] = pbuf[in * 8 + c] + pbuf[(256 + in) * 8 + c];
+        float w[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];
+        const float b1c = P1[in], g1 = P1[256 + in];
+        // Q[k][k2] (symmetric) from the packed upper triangle
+        float Q[6][6];
+        {
+            int qi = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+#pragma unroll
+                for (int k2 = k; k2 < 6; ++k2) {
+                    Q[k][k2] = S[14 + qi];
+                    Q[k2][k] = S[14 + qi];
+                    ++qi;
+                }
+        }
+        float gg1 = b1c * P[6], wr = b1c * S[13];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            gg1 = fmaf(w[k], P[k], gg1);
+            wr = fmaf(w[k], S[7 + k], wr);
+        }
+        atomicAdd(g + PLUME_OFF_BE1 + in, P[7]);
+        atomicAdd(g + PLUME_OFF_G1 + in, gg1);
+        atomicAdd(g + PLUME_OFF_B1 + in, g1 * P[6] - S[0] - wr);
+#pragma unroll
+        for (int k2 = 0; k2 < 6; ++k2) {
+            float wq2 = b1c * S[7 + k2];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wq2 = fmaf(w[k], Q[k2][k], wq2);
+            atomicAdd(g + PLUME_OFF_W1 + in * 6 + k2, g1 * P[k2] - S[1 + k2] - wq2);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// ---- launch ---------------------------------------------------------------------------------------------
+int64_t ppo_tc_workspace_bytes() { return (int64_t)kW2SplitFloats * (int64_t)sizeof(float) + 256; }
+
+int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = TcSmem::total * (int)sizeof(float);
+    if (!configured) {
+        if (cudaFuncSetAttribute(ppo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return fail("ppo_tc_kernel: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    float* w2s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    ppo_tc_prep_kernel<<<128, 256, 0, s>>>(params, w2s);
+    if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_prep_kernel launch failed");
+    const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
+    int grid = sm_count();
+    if (grid <= 0) return fail("no CUDA device");
+    if (tiles < grid) grid = (int)tiles;
+    ppo_tc_kernel<<<grid, kTcThreads, smem, s>>>(params, a, w2s);
+    if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_kernel launch failed");
+    return 0;
+}
+
+}  // namespace plume

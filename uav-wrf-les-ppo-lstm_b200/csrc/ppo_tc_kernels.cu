@@ -169,14 +169,19 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
     };
     // operands of step st are complete in shared memory: make them visible to the tensor core, issue
-    auto publish_and_issue = [&](uint32_t st, uint32_t col, bool first) {
+    // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
+    auto publish_and_issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {
         cp_async_wait_all();
         tc::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
-            tc::mma_chunk_3xtf32(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
-                                 idesc, first);
+            if (col_small != col)
+                tc::mma_chunk_3xtf32_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),
+                                           stage_buf(st, 2), stage_buf(st, 3), idesc, first);
+            else
+                tc::mma_chunk_3xtf32(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2),
+                                     stage_buf(st, 3), idesc, first);
             tc::mma_commit(&bar[st & 1u]);
         }
     };
@@ -295,7 +300,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 ah[f] = hi;
                 al[f] = lo;
             }
-            publish_and_issue(st, 0u, c == 0);
+            publish_and_issue(st, 0u, c == 0, 128u);     // columns [128,256) are free until G2 starts
             ++step;
         }
         wait_all_mma();
@@ -307,6 +312,14 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::tmem_ld32(taddr, v);
             tc::tmem_ld32(taddr + 32u, v + 32);
             tc::tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {               // + the small cross terms (separate accumulator)
+                float sm_terms[32];
+                tc::tmem_ld32(taddr + 128u + 32u * q, sm_terms);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[32 * q + j] += sm_terms[j];
+            }
             tc::tc_fence_before();
             float sum = 0.0f;
 #pragma unroll
@@ -455,7 +468,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     ah[f] = hi;
                     al[f] = lo;
                 }
-                publish_and_issue(st, (uint32_t)(128 * hN), c == 0);
+                publish_and_issue(st, (uint32_t)(128 * hN), c == 0, (uint32_t)(128 * hN));
                 ++step;
             }
         }
@@ -507,7 +520,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     bh4[f] = hi;
                     bl4[f] = lo;
                 }
-                publish_and_issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0);
+                publish_and_issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0, (uint32_t)(256 + 128 * hN));
                 ++step;
             }
         }

@@ -2,7 +2,7 @@
 // shared memory and fp32 accumulators in TMEM, used with the 3xTF32 split so that the GEMM-shaped
 // parts of the PPO update keep fp32-grade accuracy (parity bar: fp32 rel 1e-5):
 //
-//      a = a_hi + a_lo,  a_hi = a with the 13 low mantissa bits cleared (exactly a TF32 value)
+//      a = a_hi + a_lo,  a_hi = a rounded to nearest TF32, a_lo = the remainder rounded to nearest TF32
 //      A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi          (3 MMAs per K-step, error ~2^-21 relative)
 //
 // Operand tiles are written to shared memory by the CTA's own threads (they have to be split
@@ -112,9 +112,17 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- operand staging -----------------------------------------------------------------------
+// round-to-nearest TF32 (10 explicit mantissa bits); the result is an fp32 value whose low 13 bits are 0
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// hi = RN_tf32(x), lo = RN_tf32(x - hi): |x - hi - lo| <= 2^-23 |x| (the tensor core would otherwise
+// TRUNCATE both operands to TF32, which costs two more bits)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;        // exact
+    hi = round_tf32(x);
+    lo = round_tf32(x - hi);
 }
 
 // Cooperative load of a [ROWS][32] fp32 chunk (row-major, leading dimension ld floats, rows
@@ -156,6 +164,25 @@ __device__ __forceinline__ void mma_chunk_3xtf32(uint32_t tmem_d, const float* a
         mma_tf32(tmem_d, dal, dbh, idesc, (first_chunk && j == 0) ? 0u : 1u);   // small terms first
         mma_tf32(tmem_d, dah, dbl, idesc, 1u);
         mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+    }
+}
+
+// Same 12 MMAs, but the two small cross terms go to their own accumulator `tmem_small`.  The tensor core
+// truncates when it adds into an accumulator; keeping the 2^-11-times smaller terms out of the main chain
+// leaves one truncation per K-step on `tmem_big` instead of three (the caller adds the two at the end).
+__device__ __forceinline__ void mma_chunk_3xtf32_split(uint32_t tmem_big, uint32_t tmem_small, const float* a_hi,
+                                                       const float* a_lo, const float* b_hi, const float* b_lo,
+                                                       uint32_t idesc, bool first_chunk) {
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+    for (int j = 0; j < kChunkK / 8; ++j) {
+        const uint32_t off = j * 2 * kLBO;
+        const uint64_t dah = make_smem_desc(ah + off, kLBO, kSBO), dal = make_smem_desc(al + off, kLBO, kSBO);
+        const uint64_t dbh = make_smem_desc(bh + off, kLBO, kSBO), dbl = make_smem_desc(bl + off, kLBO, kSBO);
+        const uint32_t acc = (first_chunk && j == 0) ? 0u : 1u;
+        mma_tf32(tmem_small, dal, dbh, idesc, acc);
+        mma_tf32(tmem_small, dah, dbl, idesc, 1u);
+        mma_tf32(tmem_big, dah, dbh, idesc, acc);
     }
 }
 

@@ -83,23 +83,32 @@ __global__ void __launch_bounds__(256) gae_normalise_kernel(float* __restrict__ 
     }
 }
 
-// ---- K7: one CTA, global-norm clip + Adam over the flat parameter buffer ----------------------
+// ---- K7: global-norm clip + Adam over the flat parameter buffer ------------------------------------
+// Every CTA recomputes the global gradient norm from L2 (145 KB, same summation order in every CTA, so
+// the value is bitwise identical and no grid-wide synchronisation is needed) and then updates its own
+// 1024-element slice.
 __global__ void __launch_bounds__(1024) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v, int n,
                                                          float max_norm, float lr, float b1, float b2, float eps,
                                                          float bc1, float bc2_sqrt, float* grad_norm_out) {
     __shared__ double scratch[32];
     double ss = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double x = (double)g[i];
-        ss += x * x;
+    const int n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 x = __ldg(g4 + i);
+        ss += (double)x.x * (double)x.x + (double)x.y * (double)x.y + (double)x.z * (double)x.z +
+              (double)x.w * (double)x.w;
     }
+    for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) ss += (double)g[i] * (double)g[i];
     const float norm = (float)sqrt(block_sum(ss, scratch));
-    if (threadIdx.x == 0 && grad_norm_out) *grad_norm_out = norm;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && grad_norm_out) *grad_norm_out = norm;
     float coef = max_norm / (norm + 1e-6f);       // torch.nn.utils.clip_grad_norm_
     coef = coef > 1.0f ? 1.0f : coef;
     const float step_size = lr / bc1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
         const float gi = g[i] * coef;
         const float mi = m[i] + (gi - m[i]) * (1.0f - b1);            // exp_avg.lerp_(grad, 1-beta1)
         const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;           // mul_(beta2).addcmul_(g, g, 1-beta2)
@@ -125,38 +134,37 @@ __global__ void __launch_bounds__(1024) curriculum_kernel(const float* __restric
                                                           double* state, double* curriculum, double initial_radius,
                                                           double min_radius, double radius_decay, double thr,
                                                           int window, double decay_factor) {
-    __shared__ int ep_cnt[1024];
+    // One CTA (the episode order is a serial dependency), 32 warps; warp w owns the contiguous range
+    // [w*chunk, (w+1)*chunk) and walks it 32 flags at a time with coalesced loads + ballots.
+    __shared__ int ep_cnt[32];
     __shared__ int blk_succ[kCurMaxBlocks];
     __shared__ int overflow_any;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) overflow_any = 0;
-    const long long chunk = (total + blockDim.x - 1) / blockDim.x;
-    const long long lo = chunk * tid, hi = (lo + chunk < total) ? lo + chunk : total;
+    const long long chunk = (((total + 31) / 32) + 31) / 32 * 32;     // multiple of 32 flags per warp
+    const long long lo = chunk * warp, hi = (lo + chunk < total) ? lo + chunk : total;
     int eps = 0;
-    for (long long i = lo; i < hi; ++i) eps += dones[i] != 0.0f;
-    ep_cnt[tid] = eps;
+#pragma unroll 4
+    for (long long i = lo; i < hi; i += 32) {
+        const bool d = (i + lane < hi) && dones[i + lane] != 0.0f;
+        eps += __popc(__ballot_sync(0xffffffffu, d));
+    }
+    if (lane == 0) ep_cnt[warp] = eps;
     for (int i = tid; i < kCurMaxBlocks; i += blockDim.x) blk_succ[i] = 0;
     __syncthreads();
-    // exclusive scan (Hillis-Steele would need double buffering; 1024 entries: thread 0 does it)
-    if (tid == 0) {
-        int run = 0;
-        for (int i = 0; i < (int)blockDim.x; ++i) {
-            const int c = ep_cnt[i];
-            ep_cnt[i] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
     const long long hist_len = (long long)state[4];
-    long long ord = hist_len + ep_cnt[tid];
+    long long ord = hist_len;                                          // ordinal of this warp's first episode
+    for (int w = 0; w < warp; ++w) ord += ep_cnt[w];
     bool overflow = false;
-    for (long long i = lo; i < hi; ++i) {
-        if (dones[i] != 0.0f) {
-            const long long b = ord / window;
+    for (long long i = lo; i < hi; i += 32) {
+        const bool d = (i + lane < hi) && dones[i + lane] != 0.0f;
+        const unsigned mask = __ballot_sync(0xffffffffu, d);
+        if (d) {
+            const long long b = (ord + __popc(mask & ((1u << lane) - 1u))) / window;
             if (b >= kCurMaxBlocks) overflow = true;
-            else if (reached[i]) atomicAdd(&blk_succ[(int)b], 1);
-            ++ord;
+            else if (reached[i + lane]) atomicAdd(&blk_succ[(int)b], 1);
         }
+        ord += __popc(mask);
     }
     if (overflow) atomicOr(&overflow_any, 1);
     __syncthreads();
@@ -242,7 +250,8 @@ extern "C" int plume_clip_adam(float* params, const float* grads, float* exp_avg
     if (n <= 0) return 0;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    clip_adam_kernel<<<1, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, max_norm, lr, beta1,
+    PLUME_CHECK_ARG((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grads must be 16-byte aligned");
+    clip_adam_kernel<<<(n + 1023) / 1024, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, max_norm, lr, beta1,
                                                         beta2, eps, (float)bc1, (float)sqrt(bc2), grad_norm_out);
     PLUME_LAUNCH_CHECK();
     return 0;

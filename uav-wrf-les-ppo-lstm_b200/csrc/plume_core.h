@@ -86,7 +86,10 @@ PLUME_HD void box_muller(uint32_t r0, uint32_t r1, float& z0, float& z1) {
     const float u1 = uniform24_open0(r0);
     const float u2 = uniform24(r1);
 #if defined(__CUDA_ARCH__)
-    const float rad = sqrtf(-2.0f * __logf(u1));
+    // sqrt.approx (MUFU.SQRT, <= 1 ulp) instead of the IEEE sqrtf sequence: K1 is bound by instruction
+    // issue; every consumer of the field stream goes through this function, so they all see the same draws
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
 #else

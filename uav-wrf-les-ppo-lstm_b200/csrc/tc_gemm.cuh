@@ -112,17 +112,15 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- operand staging -----------------------------------------------------------------------
-// round-to-nearest TF32 (10 explicit mantissa bits); the result is an fp32 value whose low 13 bits are 0
-__device__ __forceinline__ float round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-// hi = RN_tf32(x), lo = RN_tf32(x - hi): |x - hi - lo| <= 2^-23 |x| (the tensor core would otherwise
-// TRUNCATE both operands to TF32, which costs two more bits)
+// hi = RN_tf32(x) (ties away from zero, like cvt.rna.tf32.f32, which ptxas expands into 4 instructions
+// per value because of its Inf/NaN handling -- ncu r1b: 13 % of the update kernel's instructions).  Done
+// on the bit pattern: +0x1000 rounds the magnitude, the mask clears the 13 low bits.  lo = x - hi is
+// exact; the tensor core ignores the 13 low bits of an operand (it truncates), so adding 0x1000 to lo's
+// bit pattern is all that is needed to make that truncation a round-to-nearest.
+// |x - hi - lo_as_seen_by_the_tensor_core| <= 2^-23 |x|.  (Inf/NaN inputs stay non-finite.)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = round_tf32(x);
-    lo = round_tf32(x - hi);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
 }
 
 // Cooperative load of a [ROWS][32] fp32 chunk (row-major, leading dimension ld floats, rows

@@ -2,6 +2,8 @@
 // kernels.  V2.1 PeakAndStopPredictor: PPOV2.1/evaluate_with_lstm.py:11-27; V2.0
 // ConcentrationThresholdPredictor LSTM stack: PPOV2.0/model.py:203-240; trend label:
 // PPOV2.1/model.py:113-127.
+#include <cstdlib>
+
 #include "lstm_tile.cuh"
 
 namespace plume {
@@ -296,6 +298,29 @@ extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const floa
     PLUME_CHECK_ARG(!trend || src_dist, "trend features need src_dist");
     PLUME_CHECK_ARG(window_out != window_in, "window_out must not alias window_in");
     if (horizon <= 0 || n_envs <= 0) return 0;
+    // hidden = 32: gate GEMM on the tensor cores (lstm_tc_kernels.cu); PLUME_LSTM_PATH=cuda forces the
+    // CUDA-core kernel, whose arithmetic is bit-identical to the in-loop head of plume_rollout
+    const char* path = getenv("PLUME_LSTM_PATH");
+    if (lstm->hidden == 32 && !(path && path[0] == 'c')) {
+        LtArgs t;
+        t.conc_sample = conc_sample;
+        t.fill_t = fill_t;
+        t.src_dist = src_dist;
+        t.horizon = horizon;
+        t.n_envs = n_envs;
+        t.W = lstm->window;
+        t.window_in = window_in;
+        t.window_out = window_out;
+        t.conc_peak = conc_peak;
+        t.threshold = lstm->threshold;
+        t.stop_prob = stop_prob;
+        t.peak_pred = peak_pred;
+        t.trend = trend;
+        t.stop_flag = stop_flag;
+        t.w_ih = lstm->w_ih; t.w_hh = lstm->w_hh; t.b_ih = lstm->b_ih; t.b_hh = lstm->b_hh;
+        t.w_peak = lstm->w_peak; t.b_peak = lstm->b_peak; t.w_stop = lstm->w_stop; t.b_stop = lstm->b_stop;
+        return launch_stop_head_segment_tc(t, as_stream(stream));
+    }
     const LstmWeights w{lstm->w_ih, lstm->w_hh, lstm->b_ih, lstm->b_hh, lstm->w_peak, lstm->b_peak, lstm->w_stop,
                         lstm->b_stop};
     SegmentArgs a;

@@ -144,6 +144,22 @@ __device__ __forceinline__ float lstm_heads(const float* sm, int steps) {
     return which ? sigmoidf_acc(a) : a;
 }
 
+// ---- tensor-core deferred stop head (lstm_tc_kernels.cu) ---------------------------------------------
+struct LtArgs {
+    const float* conc_sample;
+    const uint8_t* fill_t;
+    const double* src_dist;
+    int horizon, n_envs, W;
+    const float* window_in;
+    float* window_out;
+    double conc_peak;
+    float threshold;
+    float *stop_prob, *peak_pred, *trend;
+    uint8_t* stop_flag;
+    const float *w_ih, *w_hh, *b_ih, *b_hh, *w_peak, *b_peak, *w_stop, *b_stop;
+};
+int launch_stop_head_segment_tc(const LtArgs& a, cudaStream_t s);
+
 // ---- P4t trend features (calculate_dynamic_label, PPOV2.1/model.py:113-127) ------------------------
 // m = mean of the last three np.gradient values of the window; dist = ||pos[-1] - src||
 __device__ __forceinline__ void trend_finish(double m, double c_last, double dist, double conc_peak, float* out) {

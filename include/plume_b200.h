@@ -39,6 +39,15 @@ extern "C" {
 #define PLUME_FIELD_F32 1        /* conc/tke materialised as float  [N,G,G] */
 #define PLUME_FIELD_F64 2        /* conc/tke materialised as double [N,G,G] (reference layout, environment.py:62-63) */
 
+/* plume_model */
+#define PLUME_MODEL_ISOTROPIC 0  /* the reference CODE: isotropic Gaussian + noise, five-term reward
+                                  * (environment.py:52-63,146-158) -- the parity target */
+#define PLUME_MODEL_DISPERSION 1 /* the reference README (README.md:48-53,95-100; no code behind it): Gaussian
+                                  * dispersion sigma_y = 0.3 x^0.71 in the wind-rotated frame, observation
+                                  * [x, y, CH4, wind_x, step, wind_y], reward R = dCH4 - 0.2 |dtheta|
+                                  * (+ the code's arrival bonus).  Oracle = oracle/plume_oracle.py, not pinned
+                                  * by the reference. */
+
 /* flags of plume_env_step / plume_rollout */
 #define PLUME_FLAG_AUTO_RESET 1u     /* finished envs are reset inside the call (procedural mode) */
 #define PLUME_FLAG_GREEDY 2u         /* argmax actions (evaluate_with_lstm.py:65) instead of sampling */
@@ -64,6 +73,8 @@ typedef struct plume_env_config {
     double boundary_decay_start;  /* config.py:41 */
     double initial_radius;        /* config.py:31 */
     uint64_t seed;                /* Philox key */
+    int32_t plume_model;          /* PLUME_MODEL_* */
+    int32_t reserved0;
 } plume_env_config;
 
 /* Struct-of-arrays state of n_envs environments (DEVICE pointers, HOST struct).
@@ -85,6 +96,7 @@ typedef struct plume_env_state {
     const double* sin_tab;        /* [G] sin(0.05 x), environment.py:59 */
     const double* cos_tab;        /* [G] cos(0.07 y) */
     const double* curriculum;     /* [2] = {current_radius, explore_bonus} that resets latch (model.py:189-190) */
+    int8_t* last_move;            /* last non-zero action (heading) per env, PLUME_MODEL_DISPERSION only; may be NULL */
 } plume_env_state;
 
 /* ---- library ------------------------------------------------------------------------- */

@@ -21,6 +21,8 @@ TAG_FIELD=2 (cell>>1, episode, env, 2): Box-Muller(words 0,1) -> (z_even, z_odd)
 TAG_STEP=3 (step, episode, env, 3): Box-Muller(words 0,1) -> the two randn of one step;
            step = step_count BEFORE the step (0 for the first step of an episode)
 TAG_ACT=4  (step, episode, env, 4): word 0 -> uniform for the inverse-CDF action draw (same step index)
+TAG_WIND=5 (0, episode, env, 5): words 0,1 -> wind direction phi = 2 pi u53, words 2,3 -> speed 1 + 4 u53
+           (README dispersion plume only)
 =========  =====================================================================
 """
 from __future__ import annotations
@@ -33,7 +35,7 @@ W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 
-TAG_SRC, TAG_FIELD, TAG_STEP, TAG_ACT = 1, 2, 3, 4
+TAG_SRC, TAG_FIELD, TAG_STEP, TAG_ACT, TAG_WIND = 1, 2, 3, 4, 5
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -113,3 +115,11 @@ def action_uniform(seed: int, env, episode, step):
     k0, k1 = seed_key(seed)
     r = philox4x32_10(step, episode, env, TAG_ACT, k0, k1)
     return uniform24(r[0])
+
+
+def wind(seed: int, env, episode):
+    """(cos phi, sin phi, speed) of the README dispersion plume for (env, episode)."""
+    k0, k1 = seed_key(seed)
+    r = philox4x32_10(0, episode, env, TAG_WIND, k0, k1)
+    phi = 6.283185307179586 * uniform53(r[0], r[1])
+    return np.cos(phi), np.sin(phi), 1.0 + 4.0 * uniform53(r[2], r[3])

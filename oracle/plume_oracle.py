@@ -61,6 +61,9 @@ class PlumeConfig:
     learning_rate: float = 3e-5
     batch_size: int = 256
     epochs: int = 5
+    # "isotropic" = the reference code (pinned); "dispersion" = the README's plume/state/reward
+    # (README.md:48-53,95-100: no reference code exists for it => this restatement is UNPINNED)
+    plume_model: str = "isotropic"
 
     @property
     def cell_size(self) -> int:     # environment.py:37
@@ -116,14 +119,33 @@ def plume_fields(cfg: PlumeConfig, src, z_field, u_field):
     return conc, turbulence
 
 
-def plume_cells(cfg: PlumeConfig, src_x, src_y, x, y, z, u):
+WIND_MAX_SPEED = 5.0
+DISPERSION_REF = 10.0
+
+
+def dispersion_base(cfg: PlumeConfig, ddx, ddy, wind_c, wind_s):
+    """README plume (README.md:50,97; parity unpinned): Gaussian dispersion with sigma_y = 0.3 x^0.71 in the
+    wind-rotated frame, amplitude peak * min(1, sigma_y(10) / sigma_y(x)), zero upwind of the source."""
+    xd = ddx * wind_c + ddy * wind_s
+    yc = ddy * wind_c - ddx * wind_s
+    down = xd > 0.0
+    sig = 0.3 * np.power(np.where(down, xd, 1.0), 0.71)
+    sig0 = 0.3 * DISPERSION_REF ** 0.71
+    amp = np.where(sig0 < sig, sig0 / sig, 1.0)
+    return np.where(down, cfg.conc_peak * amp * np.exp(-(yc * yc) / (2.0 * sig * sig)), 0.0)
+
+
+def plume_cells(cfg: PlumeConfig, src_x, src_y, x, y, z, u, wind=None):
     """Same arithmetic as :func:`plume_fields` for individual cells (vectorised over the
     leading dimension): returns (conc, tke) float64 at integer cells (x, y) given the
-    cell's two noise draws."""
+    cell's two noise draws.  ``wind`` = (cos, sin) arrays selects the README dispersion base."""
     x = np.asarray(x, dtype=np.int64)
     y = np.asarray(y, dtype=np.int64)
-    dist = np.sqrt((x - src_x) ** 2 + (y - src_y) ** 2)
-    base = cfg.conc_peak * np.exp(-dist ** 2 / (2 * (cfg.sigma) ** 2))
+    if wind is not None:
+        base = dispersion_base(cfg, x - src_x, y - src_y, wind[0], wind[1])
+    else:
+        dist = np.sqrt((x - src_x) ** 2 + (y - src_y) ** 2)
+        base = cfg.conc_peak * np.exp(-dist ** 2 / (2 * (cfg.sigma) ** 2))
     turbulence = cfg.turbulence_intensity * (
         np.abs(np.asarray(z, dtype=np.float64)) + 0.3 * np.sin(0.05 * x) * np.cos(0.07 * y)
         + 0.2 * np.asarray(u, dtype=np.float64))
@@ -155,13 +177,15 @@ class CellNoiseFields:
         self.cfg = cfg
         self.noise = noise
         self.src = np.zeros((n, 2), dtype=np.float64)
+        self.wind = None          # [n, 3] (cos, sin, speed) in the README dispersion model
 
     def regenerate(self, i: int, src, z_field=None, u_field=None):
         self.src[i] = src
 
     def at(self, idx, x, y):
         z, u = self.noise(idx, x, y)
-        return plume_cells(self.cfg, self.src[idx, 0], self.src[idx, 1], x, y, z, u)
+        wind = None if self.wind is None else (self.wind[idx, 0], self.wind[idx, 1])
+        return plume_cells(self.cfg, self.src[idx, 0], self.src[idx, 1], x, y, z, u, wind)
 
 
 # --------------------------------------------------------------------------------------
@@ -188,6 +212,8 @@ class OracleVecEnv:
         self.explore_bonus_strong = False
         self.episode_idx = np.zeros(n, dtype=np.int64)
         self.last_reached = np.zeros(n, dtype=bool)
+        self.wind = np.zeros((n, 3), dtype=np.float64)           # README model: (cos, sin, speed) per env
+        self.last_move = np.zeros(n, dtype=np.int64)             # README model: last non-zero action
         self._pow = visit_denominator_table(cfg.max_steps)
         self._all = np.arange(n)
 
@@ -210,6 +236,15 @@ class OracleVecEnv:
         self.pos32[i] = 0.0
         self.step_count[i] = 0
         self.visited[i] = 0
+        self.last_move[i] = 0
+
+    def set_wind(self, i: int, wind):
+        """README model: (cos, sin, speed) of env ``i`` for its current episode."""
+        self.wind[i] = wind
+        if hasattr(self.fields, "wind"):
+            if self.fields.wind is None:
+                self.fields.wind = np.zeros((self.n, 3), dtype=np.float64)
+            self.fields.wind[i] = wind
 
     # -- _get_obs, :71-87 --------------------------------------------------------------
     def _cells32(self):
@@ -233,6 +268,9 @@ class OracleVecEnv:
         obs[:, 3] = tke / (cfg.turbulence_intensity * 3)
         obs[:, 4] = self.step_count / cfg.max_steps
         obs[:, 5] = explore_level
+        if cfg.plume_model == "dispersion":      # README state: [CH4], wind vector, UAV position
+            obs[:, 3] = self.wind[:, 0] * self.wind[:, 2] / WIND_MAX_SPEED
+            obs[:, 5] = self.wind[:, 1] * self.wind[:, 2] / WIND_MAX_SPEED
         return obs
 
     # -- step, :89-178 -----------------------------------------------------------------
@@ -293,6 +331,20 @@ class OracleVecEnv:
         total = total.astype(np.float64) + move_penalty                              # f64 from here on
         total = total - tke_term.astype(np.float64)
         total = total + boundary_penalty                                             # :146-152
+        if cfg.plume_model == "dispersion":
+            # README reward R = d[CH4] - 0.2 |d theta| (README.md:52,99); theta = heading of the move
+            prev_move = self.last_move
+            turned = (a != 0) & (prev_move != 0) & (a != prev_move)
+            same_axis = (a <= 2) == (prev_move <= 2)
+            dtheta = np.where(turned, np.where(same_axis, np.pi, np.pi / 2), 0.0)
+            self.last_move = np.where(a != 0, a, prev_move)
+            dconc = current_conc - prev_conc
+            total = dconc - 0.2 * dtheta
+            conc_reward = dconc.astype(np.float32)
+            explore_reward = np.zeros(self.n, dtype=np.float32)
+            tke_term = np.zeros(self.n, dtype=np.float32)
+            move_penalty = -(0.2 * dtheta)
+            boundary_penalty = np.zeros(self.n)
 
         dx = self.pos32[:, 0].astype(np.float64) - self.src[:, 0]
         dy = self.pos32[:, 1].astype(np.float64) - self.src[:, 1]

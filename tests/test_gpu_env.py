@@ -198,3 +198,61 @@ def test_errors_are_loud():
     rc = lib.plume_env_step(C.byref(env.c_config), C.byref(env.c_state), None, None, 0, None, None, None, None,
                             None, None, None, None)
     assert rc != 0 and b"null" in lib.plume_last_error()
+
+
+def test_readme_dispersion_model_vs_oracle():
+    """P1' (README.md:48-53,95-100): Gaussian dispersion sigma_y = 0.3 x^0.71 in the wind-rotated frame,
+    observation [x, y, CH4, wind_x, step, wind_y], reward dCH4 - 0.2 |dtheta| (+ arrival bonus).  There is no
+    reference code behind the README: the oracle is our own CPU restatement (parity UNPINNED); device
+    pow/exp/cos differ from numpy's in the last bits, so values are compared to 1e-9 and flags exactly."""
+    from dataclasses import replace
+    from oracle import philox as ph
+    cfg = replace(po.config_for("2.1"), plume_model="dispersion")
+    n, T, seed = 16, 300, 8
+    env = pb().VecMethaneEnv(n, version="2.1", seed=seed, field_mode="procedural", plume_model="dispersion")
+    z, u = env.field_noise()
+    ora = po.OracleVecEnv(cfg, n, fields=po.CellNoiseFields(
+        cfg, n, lambda idx, x, y: (z.cpu().numpy()[idx, x, y], u.cpu().numpy()[idx, x, y])))
+    src = env.source_pos.cpu().numpy()
+    ep = env.episode_idx.cpu().numpy()
+    for i in range(n):
+        ora.set_source(i, src[i])
+        ora.set_wind(i, ph.wind(seed, i, int(ep[i])))
+    assert len({round(float(w), 6) for w in ora.wind[:, 0]}) > 8        # every env has its own wind
+    env.current_radius = 25.0
+    ora.current_radius[:] = 25.0
+    rng = np.random.default_rng(4)
+    noise = torch.zeros(n, 2, dtype=torch.float64, device=env.device)
+    o0 = env.observe().cpu().numpy()
+    assert np.allclose(o0, ora.observe(), rtol=1e-6, atol=1e-7)
+    assert np.allclose(o0[:, 3] ** 2 + o0[:, 5] ** 2, (ora.wind[:, 2] / 5.0) ** 2, rtol=1e-5)
+    done_seen = np.zeros(n, dtype=bool)
+    turn_pen = 0
+    for t in range(T):
+        d_src = ora.src - ora.pos32
+        greedy = np.where(np.abs(d_src[:, 0]) > np.abs(d_src[:, 1]), np.where(d_src[:, 0] > 0, 3, 4),
+                          np.where(d_src[:, 1] > 0, 1, 2))
+        a = np.where(rng.random(n) < 0.5, rng.integers(0, 5, n), greedy).astype(np.int32)
+        go, gr, gd, ginfo = env.step(torch.from_numpy(a), noise_out=noise)
+        o, r, d, info = ora.step(a, noise.cpu().numpy())
+        live = ~done_seen
+        assert np.array_equal(gd.cpu().numpy()[live], d[live]), t
+        assert np.array_equal(ginfo["reached"].cpu().numpy()[live], info["reached"][live])
+        assert np.allclose(go.cpu().numpy()[live], o[live], rtol=1e-6, atol=1e-7)
+        assert np.allclose(gr.cpu().numpy()[live], r[live], rtol=1e-9, atol=1e-9), t
+        assert np.allclose(ginfo["move_penalty"].cpu().numpy()[live], info["move_penalty"][live], atol=1e-6)
+        turn_pen += int((info["move_penalty"][live] < 0).sum())
+        done_seen |= d
+    assert done_seen.any() and turn_pen > 0
+    # materialised float64 fields of the same model agree with the procedural lookups
+    env2 = pb().VecMethaneEnv(2, version="2.1", seed=seed, field_mode="f64", plume_model="dispersion")
+    z2, u2 = env2.field_noise()
+    src2 = env2.source_pos.cpu().numpy()
+    conc = env2.conc_field_t.cpu().numpy()
+    for i in range(2):
+        wc, ws, _ = ph.wind(seed, i, 1)
+        xs, ys = np.mgrid[:500, :500]
+        ref, _ = po.plume_cells(cfg, src2[i, 0], src2[i, 1], xs, ys, z2[i].cpu().numpy(), u2[i].cpu().numpy(),
+                                (wc, ws))
+        assert np.allclose(conc[i], ref, rtol=1e-9, atol=1e-9)
+        assert (ref > 50).sum() > 50 and (ref > 50).sum() < 20000      # a narrow plume, not a disc

@@ -16,10 +16,11 @@ def pb():
     return m
 
 
-def _setup(N, T, seed, with_head=True, radius=None, actor_gain=40.0):
+def _setup(N, T, seed, with_head=True, radius=None, actor_gain=40.0, plume_model="isotropic"):
     m = pb()
     torch.manual_seed(seed)
-    env = m.VecMethaneEnv(N, version="2.1", seed=seed, field_mode="procedural", auto_reset=True)
+    env = m.VecMethaneEnv(N, version="2.1", seed=seed, field_mode="procedural", auto_reset=True,
+                          plume_model=plume_model)
     if radius is not None:
         env.curriculum[0] = radius
         env.reset()
@@ -145,13 +146,15 @@ def test_rollout_replay_through_oracle():
             assert np.isclose(tr[t, i, 0], lab[0], rtol=1e-4, atol=1e-5)
 
 
-def test_fused_rollout_equals_discrete_kernels():
+@pytest.mark.parametrize("plume_model", ["isotropic", "dispersion"])
+def test_fused_rollout_equals_discrete_kernels(plume_model):
     """Same seed, same Philox counters: the persistent kernel and the step-by-step kernels (policy
-    act -> env step with auto-reset) produce identical transitions."""
+    act -> env step with auto-reset) produce identical transitions (code model and README model)."""
     N, T = 200, 60
-    m, env_f, model, head, eng = _setup(N, T, seed=3, with_head=False, radius=40.0)
+    m, env_f, model, head, eng = _setup(N, T, seed=3, with_head=False, radius=40.0, plume_model=plume_model)
     buf = eng.collect()
-    env_d = m.VecMethaneEnv(N, version="2.1", seed=3, field_mode="procedural", auto_reset=True)
+    env_d = m.VecMethaneEnv(N, version="2.1", seed=3, field_mode="procedural", auto_reset=True,
+                            plume_model=plume_model)
     env_d.curriculum[0] = 40.0
     obs = env_d.reset().clone()
     for t in range(T):

@@ -33,14 +33,15 @@ class EnvConfig(C.Structure):
                 ("field_mode", C.c_int32), ("conc_peak", C.c_double), ("turbulence_intensity", C.c_double),
                 ("sigma", C.c_double), ("clip_hi", C.c_double), ("conc_reward_coef", C.c_double),
                 ("tke_penalty_factor", C.c_double), ("boundary_penalty", C.c_double),
-                ("boundary_decay_start", C.c_double), ("initial_radius", C.c_double), ("seed", C.c_uint64)]
+                ("boundary_decay_start", C.c_double), ("initial_radius", C.c_double), ("seed", C.c_uint64),
+                ("plume_model", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class EnvState(C.Structure):
     _fields_ = [("n_envs", C.c_int32), ("env_id_base", C.c_int32), ("pos_x", _vp), ("pos_y", _vp),
                 ("src_x", _vp), ("src_y", _vp), ("step_count", _vp), ("episode_idx", _vp), ("visited", _vp),
                 ("radius", _vp), ("explore_bonus", _vp), ("conc_field", _vp), ("tke_field", _vp),
-                ("sin_tab", _vp), ("cos_tab", _vp), ("curriculum", _vp)]
+                ("sin_tab", _vp), ("cos_tab", _vp), ("curriculum", _vp), ("last_move", _vp)]
 
 
 class LstmParams(C.Structure):
@@ -61,11 +62,16 @@ class PpoBatch(C.Structure):
                 ("advantages", _vp), ("returns", _vp), ("old_values", _vp)]
 
 
-def make_env_config(cfg, field_mode: int, seed: int) -> EnvConfig:
+MODEL_ISOTROPIC, MODEL_DISPERSION = 0, 1
+PLUME_MODELS = {"isotropic": MODEL_ISOTROPIC, "code": MODEL_ISOTROPIC, "dispersion": MODEL_DISPERSION,
+                "readme": MODEL_DISPERSION}
+
+
+def make_env_config(cfg, field_mode: int, seed: int, plume_model: int = 0) -> EnvConfig:
     return EnvConfig(cfg.grid_size, cfg.max_steps, cfg.grid_divisions, field_mode, cfg.conc_peak,
                      cfg.turbulence_intensity, cfg.sigma, cfg.clip_hi, cfg.conc_reward_coef,
                      cfg.tke_penalty_factor, cfg.boundary_penalty, cfg.boundary_decay_start,
-                     cfg.initial_radius, seed & 0xFFFFFFFFFFFFFFFF)
+                     cfg.initial_radius, seed & 0xFFFFFFFFFFFFFFFF, plume_model, 0)
 
 
 _P = C.POINTER

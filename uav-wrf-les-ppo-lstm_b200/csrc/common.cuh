@@ -42,6 +42,7 @@ __device__ __forceinline__ EnvRegs load_env(const plume_env_state& st, int i) {
     e.episode = (uint32_t)st.episode_idx[i];
     e.radius = st.radius[i];
     e.ebonus = st.explore_bonus[i];
+    e.last_move = st.last_move ? (int32_t)st.last_move[i] : 0;
     return e;
 }
 
@@ -54,6 +55,7 @@ __device__ __forceinline__ void store_env(const plume_env_state& st, int i, cons
     st.episode_idx[i] = (int32_t)e.episode;
     st.radius[i] = e.radius;
     st.explore_bonus[i] = e.ebonus;
+    if (st.last_move) st.last_move[i] = (int8_t)e.last_move;
 }
 
 }  // namespace plume

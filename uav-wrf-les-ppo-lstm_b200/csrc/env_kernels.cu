@@ -104,13 +104,17 @@ __global__ void __launch_bounds__(256) generate_fields_kernel(Cfg c, plume_env_s
 
     T conc[4], tke[4];
     const double sinx = st.sin_tab[x];
+    const bool dispersion = c.plume_model == PLUME_MODEL_DISPERSION;
+    Wind wind{1.0, 0.0, 1.0};
+    if (dispersion) wind = wind_of(c, gid, episode);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if constexpr (sizeof(T) == 8) {
+        if (sizeof(T) == 8 || dispersion) {
             double cc, tt;
-            plume_cell(c, sx, sy, x, y + k, (double)z[k], (double)u[k], sinx, st.cos_tab[y + k], cc, tt);
-            conc[k] = cc;
-            tke[k] = tt;
+            plume_cell(c, sx, sy, x, y + k, (double)z[k], (double)u[k], sinx, st.cos_tab[y + k], cc, tt,
+                       dispersion ? &wind : nullptr);
+            conc[k] = (T)cc;
+            tke[k] = (T)tt;
         } else {
             float cc, tt;
             cell_f32(c, (float)sx, (float)sy, x, y + k, z[k], u[k], (float)sinx, (float)st.cos_tab[y + k], cc, tt);
@@ -353,7 +357,8 @@ extern "C" int plume_generate_fields(const plume_env_config* cfg, const plume_en
     cudaStream_t s = as_stream(stream);
     if (cfg->field_mode == PLUME_FIELD_F32) {
         PLUME_CHECK_ARG(st->conc_field && st->tke_field, "field pointers missing");
-        if (!z_out && !u_out && c.G % 4 == 0 && c.G <= 512 && n_list <= 65535) {
+        if (!z_out && !u_out && c.G % 4 == 0 && c.G <= 512 && n_list <= 65535 &&
+            c.plume_model == PLUME_MODEL_ISOTROPIC) {
             FieldF32Cfg fc;
             fc.peak = (float)c.conc_peak;
             fc.ti = (float)c.ti;

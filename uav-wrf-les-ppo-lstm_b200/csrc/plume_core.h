@@ -52,7 +52,7 @@ PLUME_HD float fdiv(float a, float b) { return a / b; }
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
-constexpr uint32_t kTagSrc = 1, kTagField = 2, kTagStep = 3, kTagAct = 4;
+constexpr uint32_t kTagSrc = 1, kTagField = 2, kTagStep = 3, kTagAct = 4, kTagWind = 5;
 
 struct U4 {
     uint32_t x, y, z, w;
@@ -104,7 +104,7 @@ PLUME_HD void box_muller(uint32_t r0, uint32_t r1, float& z0, float& z1) {
 // device-side view of the configuration
 // ---------------------------------------------------------------------------------------
 struct Cfg {
-    int32_t G, max_steps, divisions, cell_size, field_mode;
+    int32_t G, max_steps, divisions, cell_size, field_mode, plume_model;
     double conc_peak, ti, two_sigma_sq, clip_hi, move_step;
     double conc_coef, tke_factor, bnd_penalty, bnd_start, initial_radius;
     uint32_t k0, k1;
@@ -117,6 +117,7 @@ inline Cfg make_cfg(const plume_env_config& c) {
     o.divisions = c.grid_divisions;
     o.cell_size = c.grid_size / c.grid_divisions;          // env:37
     o.field_mode = c.field_mode;
+    o.plume_model = c.plume_model;
     o.conc_peak = c.conc_peak;
     o.ti = c.turbulence_intensity;
     o.two_sigma_sq = 2 * (c.sigma * c.sigma);              // env:56  2*(GAUSSIAN_RADIUS)**2
@@ -135,11 +136,42 @@ inline Cfg make_cfg(const plume_env_config& c) {
 // ---------------------------------------------------------------------------------------
 // P1: one cell of the plume, env:53-63.  `z`,`u` are the cell's randn/rand draws.
 // ---------------------------------------------------------------------------------------
+// README plume (README.md:50,97): wind of (env, episode) -- direction uniform on the circle, speed in [1,5) m/s
+struct Wind {
+    double c, s, speed;
+};
+constexpr double kWindMaxSpeed = 5.0;
+constexpr double kDispersionRef = 10.0;     // centre line saturates at the peak within 10 px of the source
+
+PLUME_HD Wind wind_of(const Cfg& c, uint32_t env_gid, uint32_t episode) {
+    const U4 r = philox4x32_10(0u, episode, env_gid, kTagWind, c.k0, c.k1);
+    const double phi = 6.283185307179586 * (((double)(r.x >> 5) * 67108864.0 + (double)(r.y >> 6)) / 9007199254740992.0);
+    const double u = ((double)(r.z >> 5) * 67108864.0 + (double)(r.w >> 6)) / 9007199254740992.0;
+    return Wind{cos(phi), sin(phi), 1.0 + (kWindMaxSpeed - 1.0) * u};
+}
+
+// Gaussian dispersion in the wind-rotated frame: sigma_y = 0.3 xd^0.71 (README.md:50), amplitude
+// peak * min(1, sigma_y(10) / sigma_y(xd)), zero upwind of the source.
+PLUME_HD double dispersion_base(const Cfg& c, double ddx, double ddy, const Wind& w) {
+    const double xd = ddx * w.c + ddy * w.s;          // downwind distance
+    if (!(xd > 0.0)) return 0.0;
+    const double yc = ddy * w.c - ddx * w.s;          // crosswind offset
+    const double sig = 0.3 * pow(xd, 0.71);
+    const double sig0 = 0.3 * pow(kDispersionRef, 0.71);
+    const double amp = sig0 < sig ? sig0 / sig : 1.0;
+    return c.conc_peak * amp * exp(-(yc * yc) / (2.0 * sig * sig));
+}
+
 PLUME_HD void plume_cell(const Cfg& c, double sx, double sy, int x, int y, double z, double u, double sinx,
-                         double cosy, double& conc, double& tke) {
+                         double cosy, double& conc, double& tke, const Wind* wind = nullptr) {
     const double ddx = dsub((double)x, sx), ddy = dsub((double)y, sy);
-    const double dist = dsqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));          // env:54
-    const double base = dmul(c.conc_peak, exp(ddiv(-dmul(dist, dist), c.two_sigma_sq)));   // env:56
+    double base;
+    if (wind) {
+        base = dispersion_base(c, ddx, ddy, *wind);
+    } else {
+        const double dist = dsqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));      // env:54
+        base = dmul(c.conc_peak, exp(ddiv(-dmul(dist, dist), c.two_sigma_sq)));   // env:56
+    }
     const double wave = dmul(dmul(0.3, sinx), cosy);                          // env:59
     tke = dmul(c.ti, dadd(dadd(fabs(z), wave), dmul(0.2, u)));                // env:57-61,63
     const double v = dadd(base, tke);
@@ -166,7 +198,12 @@ struct ProceduralField {
         (void)env_local;
         float z, u;
         field_noise(c, env_gid, episode, x, y, z, u);
-        plume_cell(c, sx, sy, x, y, (double)z, (double)u, sin_tab[x], cos_tab[y], conc, tke);
+        if (c.plume_model == PLUME_MODEL_DISPERSION) {
+            const Wind w = wind_of(c, env_gid, episode);
+            plume_cell(c, sx, sy, x, y, (double)z, (double)u, sin_tab[x], cos_tab[y], conc, tke, &w);
+        } else {
+            plume_cell(c, sx, sy, x, y, (double)z, (double)u, sin_tab[x], cos_tab[y], conc, tke);
+        }
     }
 };
 
@@ -192,6 +229,7 @@ struct EnvRegs {
     uint32_t episode;    // episode_idx
     double radius;       // current_radius (latched)
     double ebonus;       // explore_bonus (latched)
+    int32_t last_move;   // last non-zero action (README reward: heading change), 0 = none yet
 };
 
 struct StepResult {
@@ -215,7 +253,7 @@ PLUME_HD double visit_denominator(int vc) {
 
 // P3 _get_obs, env:71-87, given the field values at the float32 cell.
 PLUME_HD void make_obs(const Cfg& c, const EnvRegs& e, double cell_conc, double cell_tke, int visit_here,
-                       float* obs) {
+                       float* obs, uint32_t env_gid = 0) {
     const float g = (float)c.G;
     obs[0] = fdiv(e.px, g);                                                   // env:81
     obs[1] = fdiv(e.py, g);
@@ -224,6 +262,11 @@ PLUME_HD void make_obs(const Cfg& c, const EnvRegs& e, double cell_conc, double 
     obs[4] = (float)ddiv((double)e.step, (double)c.max_steps);                // env:85
     const double lvl = ddiv((double)visit_here, 5.0);                         // env:78
     obs[5] = (float)(lvl < 1.0 ? lvl : 1.0);
+    if (c.plume_model == PLUME_MODEL_DISPERSION) {      // README state: [CH4], wind vector, UAV position
+        const Wind w = wind_of(c, env_gid, e.episode);
+        obs[3] = (float)(w.c * w.speed / kWindMaxSpeed);
+        obs[5] = (float)(w.s * w.speed / kWindMaxSpeed);
+    }
 }
 
 PLUME_HD void cell32_of(const Cfg& c, const EnvRegs& e, int& x, int& y) {
@@ -239,7 +282,7 @@ PLUME_HD void observe(const Cfg& c, const Field& f, int env_local, uint32_t env_
     double conc, tke;
     f.eval(c, env_local, env_gid, e.episode, e.sx, e.sy, x, y, conc, tke);
     const int vis = visited[(x / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (y / c.cell_size)];
-    make_obs(c, e, conc, tke, vis, obs);
+    make_obs(c, e, conc, tke, vis, obs, env_gid);
 }
 
 // P2 MethaneEnv.step, env:89-178.  `visited` points at this env's PLUME_VISIT_STRIDE counters.
@@ -299,7 +342,7 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     visited[slot] = (uint16_t)vc;
     // env:140-143
     const int vis32 = visited[(ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size)];
-    make_obs(c, e, conc32, tke32, vis32, out.obs);
+    make_obs(c, e, conc32, tke32, vis32, out.obs, env_gid);
     const float explore = fdiv(fmul((float)e.ebonus, fsub(1.0f, out.obs[5])), (float)visit_denominator(vc));
     // env:146-152 (numpy>=2 promotion: float32 terms, float64 from move_penalty on)
     const float conc_reward = fmul((float)c.conc_coef, out.obs[2]);
@@ -307,6 +350,23 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     double total = dadd((double)fadd(conc_reward, explore), move_penalty);
     total = dsub(total, (double)tke_term);
     total = dadd(total, bpen);
+    float info_conc = conc_reward, info_explore = explore, info_tke = -tke_term;
+    double info_move = move_penalty, info_bnd = bpen;
+    if (c.plume_model == PLUME_MODEL_DISPERSION) {
+        // README reward R = d[CH4] - 0.2 |d theta| (README.md:52,99): concentrations normalised by the peak,
+        // theta = heading of the move (axis aligned: the change is 0, pi/2 or pi); staying keeps the heading
+        const double dconc = dsub(cur_conc, prev_conc);
+        double dtheta = 0.0;
+        if (action != 0 && e.last_move != 0 && action != e.last_move)
+            dtheta = ((action <= 2) == (e.last_move <= 2)) ? 3.141592653589793 : 1.5707963267948966;
+        if (action != 0) e.last_move = action;
+        total = dsub(dconc, dmul(0.2, dtheta));
+        info_conc = (float)dconc;
+        info_explore = 0.0f;
+        info_tke = 0.0f;
+        info_move = -dmul(0.2, dtheta);
+        info_bnd = 0.0;
+    }
     // env:155-158
     const double ex = dsub((double)e.px, e.sx), ey = dsub((double)e.py, e.sy);
     const double distance = dsqrt(dadd(dmul(ex, ex), dmul(ey, ey)));
@@ -315,11 +375,11 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     out.reward = total;
     out.reached = reached;
     out.done = (e.step >= c.max_steps) || reached;                            // env:161
-    out.conc_reward = conc_reward;
-    out.explore_reward = explore;
-    out.tke_penalty = -tke_term;
-    out.move_penalty = move_penalty;
-    out.boundary_penalty = bpen;
+    out.conc_reward = info_conc;
+    out.explore_reward = info_explore;
+    out.tke_penalty = info_tke;
+    out.move_penalty = info_move;
+    out.boundary_penalty = info_bnd;
     out.cur_conc = cur_conc;
     out.cell_conc = conc32;
     out.cell_tke = tke32;
@@ -345,6 +405,7 @@ PLUME_HD void env_reset(const Cfg& c, uint32_t env_gid, EnvRegs& e, uint16_t* vi
     e.px = 0.0f;                                                              // env:46
     e.py = 0.0f;
     e.step = 0;                                                               // env:47
+    e.last_move = 0;
     e.radius = radius;
     e.ebonus = ebonus;
     for (int i = 0; i < PLUME_VISIT_STRIDE; ++i) visited[i] = 0;              // env:49

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 cell32_of(c, e, x, y);
                 field.eval(c, env, gid, e.episode, e.sx, e.sy, x, y, cell_conc, cell_tke);
                 make_obs(c, e, cell_conc, cell_tke,
-                         vis[(x / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (y / c.cell_size)], o);
+                         vis[(x / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (y / c.cell_size)], o, gid);
                 fill = a.buf.window_fill ? a.buf.window_fill[env] : 0;
             }
 #pragma unroll
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                     env_reset(c, gid, e, vis, nullptr, cur_radius, cur_bonus);
                     fill = 0;
                     field.eval(c, env, gid, e.episode, e.sx, e.sy, 0, 0, cell_conc, cell_tke);
-                    make_obs(c, e, cell_conc, cell_tke, 0, r.obs);
+                    make_obs(c, e, cell_conc, cell_tke, 0, r.obs, gid);
                 }
 #pragma unroll
                 for (int k = 0; k < 6; ++k) sm[MlpSmem::x + tid * 8 + k] = r.obs[k];

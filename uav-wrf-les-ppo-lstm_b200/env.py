@@ -38,7 +38,7 @@ class VecMethaneEnv:
 
     def __init__(self, num_envs: int = 1, device="cuda", version: str = "2.1", seed: int = 0,
                  field_mode: str = "procedural", auto_reset: bool = False, env_id_base: int = 0,
-                 config: PlumeConfig | None = None):
+                 config: PlumeConfig | None = None, plume_model: str = "isotropic"):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.cfg = config if config is not None else config_for(version)
@@ -49,6 +49,8 @@ class VecMethaneEnv:
             raise ValueError("auto_reset needs field_mode='procedural' (materialised fields are regenerated "
                              "by reset(), which launches the field kernel)")
         self.seed = int(seed)
+        # "isotropic" = the reference code (parity target); "dispersion" = the README's plume/state/reward
+        self.plume_model = _lib.PLUME_MODELS[plume_model] if isinstance(plume_model, str) else int(plume_model)
         self.grid_size = self.cfg.grid_size                                   # environment.py:23
         self.action_space = SimpleNamespace(n=_lib.NUM_ACTIONS)                # environment.py:24
         self.observation_space = SimpleNamespace(shape=(_lib.OBS_DIM,), dtype=np.float32)
@@ -63,6 +65,7 @@ class VecMethaneEnv:
             self.step_count_t = z(torch.int32, N)
             self.episode_idx = z(torch.int32, N)
             self.visited_t = z(torch.int16, N, _lib.VISIT_STRIDE)
+            self.last_move_t = z(torch.int8, N)
             self.radius_t = torch.full((N,), self.cfg.initial_radius, dtype=torch.float64, device=dev)
             self.explore_bonus_t = torch.full((N,), self.cfg.explore_bonus, dtype=torch.float64, device=dev)
             # the two curriculum scalars resets latch (model.py:189-190)
@@ -82,13 +85,13 @@ class VecMethaneEnv:
             self.done = z(torch.uint8, N)
             self.reached = z(torch.uint8, N)
             self.info_t = z(torch.float32, _lib.INFO_DIM, N)
-        self._ccfg = _lib.make_env_config(self.cfg, self.field_mode, self.seed)
+        self._ccfg = _lib.make_env_config(self.cfg, self.field_mode, self.seed, self.plume_model)
         self._cstate = _lib.EnvState(
             N, int(env_id_base), self.pos_x.data_ptr(), self.pos_y.data_ptr(), self.src_x.data_ptr(),
             self.src_y.data_ptr(), self.step_count_t.data_ptr(), self.episode_idx.data_ptr(),
             self.visited_t.data_ptr(), self.radius_t.data_ptr(), self.explore_bonus_t.data_ptr(),
             _lib.ptr(self.conc_field_t), _lib.ptr(self.tke_field_t), self.sin_tab.data_ptr(),
-            self.cos_tab.data_ptr(), self.curriculum.data_ptr())
+            self.cos_tab.data_ptr(), self.curriculum.data_ptr(), self.last_move_t.data_ptr())
         self.launches = 0
         self.reset()                                                           # environment.py:40
 

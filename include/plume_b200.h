@@ -126,6 +126,12 @@ int plume_generate_fields(const plume_env_config* cfg, const plume_env_state* st
 int plume_field_noise_at(const plume_env_config* cfg, const plume_env_state* st, const int32_t* env_local,
                          const int32_t* x, const int32_t* y, int32_t n, float* z_out, float* u_out, void* stream);
 
+/* conc_field[x[i], y[i]] and tke_field[x[i], y[i]] of env i (int32 x/y [n_envs], clipped to the grid) as double
+ * [n_envs]; either output may be NULL.  Works in every field mode (the accessor behind env.conc_field[...] in
+ * evaluate_with_lstm.py:67-68). */
+int plume_field_at(const plume_env_config* cfg, const plume_env_state* st, const int32_t* x, const int32_t* y,
+                   double* conc, double* tke, void* stream);
+
 /* ---- P3 _get_obs, environment.py:71-87 ------------------------------------------------- */
 /* obs float[n_envs][6]. */
 int plume_env_observe(const plume_env_config* cfg, const plume_env_state* st, float* obs, void* stream);
@@ -198,6 +204,13 @@ int plume_lstm_stop_head(const float* w_ih, const float* w_hh, const float* b_ih
  * concatenated in that order. */
 int plume_lstm_forward(const float* params, int32_t layers, int32_t hidden, const float* windows,
                        int32_t batch, int32_t steps, float* h_out, void* stream);
+
+/* FC head of the V2.0 ConcentrationThresholdPredictor (PPOV2.0/model.py:213-220, eval mode): h float[B][H] (the
+ * last hidden state from plume_lstm_forward) -> Linear(H,64) -> LayerNorm(64) -> ReLU -> Linear(64,1) -> out[B].
+ * w1 [64][H], b1 [64], ln_weight/ln_bias [64], w2 [64], b2 [1] (torch layouts). */
+int plume_threshold_head(const float* h, int32_t batch, int32_t hidden, const float* w1, const float* b1,
+                         const float* ln_weight, const float* ln_bias, const float* w2, const float* b2, float* out,
+                         void* stream);
 
 /* P4t trend features, model.py:113-127: conc float[B][W] (raw 0..100), last position float[B][2],
  * source double[B][2] -> out float[B][4] = {label, trend_score, dist_score, conc_score}. */

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "plume_env_reset": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, C.c_int32, _vp, _vp]),
     "plume_generate_fields": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, C.c_int32, _vp, _vp, _vp]),
     "plume_field_noise_at": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp]),
+    "plume_field_at": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _vp, _vp, _vp, _vp]),
     "plume_env_observe": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _vp]),
     "plume_env_step": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp]),
@@ -92,6 +93,7 @@ _SIGNATURES = {
     "plume_stop_head_segment": (C.c_int, [_P(LstmParams), _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double,
                                           _vp, _vp, _vp, _vp, _vp]),
     "plume_lstm_forward": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp, _vp]),
+    "plume_threshold_head": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plume_trend_features": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, _vp, _vp]),
     "plume_rollout": (C.c_int, [_P(EnvConfig), _P(EnvState), _vp, _P(LstmParams), _P(RolloutBuffers), C.c_int32,
                                 C.c_uint32, _vp, _vp]),

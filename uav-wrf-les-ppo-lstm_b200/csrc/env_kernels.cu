@@ -202,6 +202,20 @@ __global__ void __launch_bounds__(256) dump_noise_kernel(Cfg c, plume_env_state 
         make_float4(uniform24(ra.z), uniform24(ra.w), uniform24(rb.z), uniform24(rb.w));
 }
 
+// conc_field[x, y] / tke_field[x, y] of every env at one cell per env (the accessor the evaluators use,
+// evaluate_with_lstm.py:67-68), for any field mode
+template <typename Field>
+__global__ void field_at_kernel(Cfg c, plume_env_state st, Field f, const int32_t* x, const int32_t* y, double* conc,
+                                double* tke) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n_envs) return;
+    const int cx = clip_cell(x[i], c.G), cy = clip_cell(y[i], c.G);
+    double cc, tt;
+    f.eval(c, i, (uint32_t)(st.env_id_base + i), (uint32_t)st.episode_idx[i], st.src_x[i], st.src_y[i], cx, cy, cc, tt);
+    if (conc) conc[i] = cc;
+    if (tke) tke[i] = tt;
+}
+
 __global__ void noise_at_kernel(Cfg c, plume_env_state st, const int32_t* env_local, const int32_t* x,
                                 const int32_t* y, int n, float* z_out, float* u_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +388,27 @@ extern "C" int plume_generate_fields(const plume_env_config* cfg, const plume_en
         PLUME_CHECK_ARG(z_out != nullptr, "procedural mode: only the noise dump is available");
         dump_noise_kernel<<<(unsigned)blocks, 256, 0, s>>>(c, *st, env_list, bpe, z_out, u_out);
     }
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plume_field_at(const plume_env_config* cfg, const plume_env_state* st, const int32_t* x, const int32_t* y,
+                              double* conc, double* tke, void* stream) {
+    if (check_cfg(cfg, st)) return 1;
+    PLUME_CHECK_ARG(x && y && (conc || tke), "null pointer");
+    if (st->n_envs == 0) return 0;
+    const Cfg c = make_cfg(*cfg);
+    const int blocks = (st->n_envs + 127) / 128;
+    cudaStream_t s = as_stream(stream);
+    if (cfg->field_mode == PLUME_FIELD_PROCEDURAL)
+        field_at_kernel<<<blocks, 128, 0, s>>>(c, *st, ProceduralField{st->sin_tab, st->cos_tab}, x, y, conc, tke);
+    else if (cfg->field_mode == PLUME_FIELD_F32)
+        field_at_kernel<<<blocks, 128, 0, s>>>(
+            c, *st, MaterialisedField<float>{(const float*)st->conc_field, (const float*)st->tke_field}, x, y, conc, tke);
+    else
+        field_at_kernel<<<blocks, 128, 0, s>>>(
+            c, *st, MaterialisedField<double>{(const double*)st->conc_field, (const double*)st->tke_field}, x, y, conc,
+            tke);
     PLUME_LAUNCH_CHECK();
     return 0;
 }

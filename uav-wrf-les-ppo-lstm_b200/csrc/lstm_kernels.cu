@@ -139,6 +139,38 @@ __global__ void linear_heads_kernel(const float* __restrict__ h, int batch, int 
     stop_prob[i] = sigmoidf_acc(b + b_stop[0]);
 }
 
+
+// ---- V2.0 threshold predictor head: Linear(H,64) -> LayerNorm(64) -> ReLU -> Linear(64,1) ----------------
+// (PPOV2.0/model.py:213-220; dropout is inactive in eval mode).  One 64-thread CTA per sample.
+__global__ void __launch_bounds__(64) threshold_head_kernel(const float* __restrict__ h, int batch, int H,
+                                                            const float* __restrict__ w1, const float* __restrict__ b1,
+                                                            const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                            const float* __restrict__ w2, const float* __restrict__ b2,
+                                                            float* __restrict__ out) {
+    __shared__ float red[4];
+    const int i = blockIdx.x, o = threadIdx.x, lane = o & 31, warp = o >> 5;
+    if (i >= batch) return;
+    float a = b1[o];
+    for (int k = 0; k < H; ++k) a = fmaf(h[(size_t)i * H + k], w1[o * H + k], a);
+    float s = a;
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    const float mean = (red[0] + red[1]) * (1.0f / 64.0f);
+    const float d = a - mean;
+    float q = d * d;
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    if (lane == 0) red[2 + warp] = q;
+    __syncthreads();
+    const float rstd = 1.0f / sqrtf((red[2] + red[3]) * (1.0f / 64.0f) + 1e-5f);
+    float y = fmaxf(fmaf(d * rstd, ln_g[o], ln_b[o]), 0.0f) * w2[o];
+    for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = y;
+    __syncthreads();
+    if (o == 0) out[i] = red[0] + red[1] + b2[0];
+}
+
 // ---- P4t trend features (device function in lstm_tile.cuh) ----
 __global__ void trend_kernel(const float* __restrict__ conc, int batch, int W, const float* __restrict__ pos,
                              const double* __restrict__ src, double conc_peak, float* __restrict__ out) {
@@ -351,6 +383,18 @@ extern "C" int plume_lstm_forward(const float* params, int32_t layers, int32_t h
     PLUME_CHECK_ARG(steps >= 1, "empty window");
     if (batch <= 0) return 0;
     return launch_generic(params, layers, hidden, windows, batch, steps, h_out, as_stream(stream));
+}
+
+extern "C" int plume_threshold_head(const float* h, int32_t batch, int32_t hidden, const float* w1, const float* b1,
+                                    const float* ln_weight, const float* ln_bias, const float* w2, const float* b2,
+                                    float* out, void* stream) {
+    PLUME_CHECK_ARG(h && w1 && b1 && ln_weight && ln_bias && w2 && b2 && out, "null pointer");
+    PLUME_CHECK_ARG(hidden >= 1, "hidden must be positive");
+    if (batch <= 0) return 0;
+    threshold_head_kernel<<<batch, 64, 0, as_stream(stream)>>>(h, batch, hidden, w1, b1, ln_weight, ln_bias, w2, b2,
+                                                              out);
+    PLUME_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int plume_trend_features(const float* conc, int32_t batch, int32_t window, const float* pos_last,

@@ -226,7 +226,7 @@ class VecMethaneEnv:
         st = _lib.EnvState.from_buffer_copy(self._cstate)
         if ids is None:
             st.conc_field, st.tke_field = conc.data_ptr(), tke.data_ptr()
-            ccfg = _lib.make_env_config(self.cfg, mode, self.seed)
+            ccfg = _lib.make_env_config(self.cfg, mode, self.seed, self.plume_model)
             self._call("plume_generate_fields", C.byref(ccfg), C.byref(st), None, n, None, None, self._stream())
             return conc, tke
         # per-env generation into the compact buffers
@@ -236,7 +236,7 @@ class VecMethaneEnv:
             full.conc_field = conc[j].data_ptr() - off
             full.tke_field = tke[j].data_ptr() - off
             one = torch.tensor([e], dtype=torch.int32, device=self.device)
-            ccfg = _lib.make_env_config(self.cfg, mode, self.seed)
+            ccfg = _lib.make_env_config(self.cfg, mode, self.seed, self.plume_model)
             self._call("plume_generate_fields", C.byref(ccfg), C.byref(full), one.data_ptr(), 1, None, None,
                        self._stream())
         del full_conc
@@ -244,13 +244,12 @@ class VecMethaneEnv:
 
     def conc_at(self, x, y) -> torch.Tensor:
         """``conc_field[x, y]`` for every env (x, y integer [N] tensors), float64."""
-        xx = torch.as_tensor(x, device=self.device).long().clamp(0, self.cfg.grid_size - 1)
-        yy = torch.as_tensor(y, device=self.device).long().clamp(0, self.cfg.grid_size - 1)
-        ar = torch.arange(self.num_envs, device=self.device)
-        if self.field_mode != FIELD_PROCEDURAL:
-            return self.conc_field_t[ar, xx, yy].double()
-        conc, _ = self.materialise_fields()
-        return conc[ar, xx, yy]
+        xx = torch.as_tensor(x, device=self.device).to(torch.int32).contiguous()
+        yy = torch.as_tensor(y, device=self.device).to(torch.int32).contiguous()
+        conc = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        self._call("plume_field_at", C.byref(self._ccfg), C.byref(self._cstate), xx.data_ptr(), yy.data_ptr(),
+                   conc.data_ptr(), None, self._stream())
+        return conc
 
     # -- reference attribute names ----------------------------------------------------------
     @property

@@ -205,3 +205,23 @@ class ConcentrationThresholdPredictor(nn.Module):
             _lib.check(lib.plume_lstm_forward(flat.data_ptr(), 3, self.hidden_size, x.data_ptr(), B, T,
                                               h.data_ptr(), _stream(dev)), "plume_lstm_forward")
         return h
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, lengths=None) -> torch.Tensor:
+        """``x`` [B,T,1] (or [B,T]) -> predicted source concentration [B] (PPOV2.0/model.py:229-240).
+        ``lengths`` is accepted for signature parity; the evaluator always passes full windows
+        (PPOV2.0/evaluate_with_lstm.py:26), which is what the kernels implement."""
+        T = x.shape[1]
+        if lengths is not None and any(int(l) != T for l in lengths):
+            raise NotImplementedError("ragged windows: the reference evaluator only passes lengths == window size")
+        h = self.lstm_last_hidden(x)
+        dev = h.device
+        lib = _lib.load()
+        out = torch.empty(h.shape[0], dtype=torch.float32, device=dev)
+        fc1, ln, fc2 = self.fc[0], self.fc[1], self.fc[4]
+        with torch.cuda.device(dev):
+            _lib.check(lib.plume_threshold_head(h.data_ptr(), h.shape[0], self.hidden_size, fc1.weight.data_ptr(),
+                                                fc1.bias.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(),
+                                                fc2.weight.data_ptr(), fc2.bias.data_ptr(), out.data_ptr(),
+                                                _stream(dev)), "plume_threshold_head")
+        return out

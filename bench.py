@@ -265,7 +265,7 @@ def run_cuda_arm(args) -> None:
         ev_roll[k][0].record()
         buf = trainer.engine.collect()
         ev_roll[k][1].record()
-        trainer.curriculum.update_from_rollout(buf)
+        trainer.curriculum.update_from_rollout(buf, pg)
         trainer.last_losses = pb.update_model(buf, trainer.model, trainer.optimizer, cfg=trainer.cfg,
                                               minibatch_size=trainer.minibatch_size, workspace=trainer.workspace,
                                               process_group=pg, perm_seed=trainer.iteration, check_nan=False)

@@ -281,6 +281,22 @@ int plume_gae_scan(const float* rewards, const float* values, const float* dones
 int plume_gae_normalise(float* advantages, const float* values, int64_t count, const double* stats,
                         float* returns, void* stream);
 
+/* P5' the GAE variants of the older drivers (kept as flags, not parity targets of the V2.x update):
+ *   PLUME_GAE_QUIRK      train_ppo2.0.py:17-39 (= plume_gae_scan / plume_gae_normalise)
+ *   PLUME_GAE_BOOTSTRAP  PPOV1.1/train_ppo1.0.py:66-89 (also V1.0, GAIL): bootstraps the last step with
+ *                        last_values[n] = V(next_state), masks with dones[t+1], returns = RAW advantage + value,
+ *                        normalises with std + 1e-8
+ *   PLUME_GAE_V12        PPOV1.2: next value masked with dones[t], no bootstrap at the last step, returns =
+ *                        normalised advantage + value, std + 1e-8 */
+#define PLUME_GAE_QUIRK 0
+#define PLUME_GAE_BOOTSTRAP 1
+#define PLUME_GAE_V12 2
+int plume_gae_scan_variant(const float* rewards, const float* values, const float* dones, const float* last_values,
+                           int32_t horizon, int32_t n_envs, double gamma, double lam, int32_t variant,
+                           float* advantages, double* stats, void* stream);
+int plume_gae_normalise_variant(float* advantages, const float* values, int64_t count, const double* stats,
+                                int32_t variant, float* returns, void* stream);
+
 /* ---- P6/P7 PPO minibatch update, train_ppo2.0.py:42-87 ---------------------------------- */
 typedef struct plume_ppo_batch {          /* DEVICE pointers over the flat [M] transition set */
     int64_t total;                        /* M = T*N */

@@ -118,6 +118,51 @@ def gae_standard(rewards, values, dones, last_value, gamma: float, lam: float) -
     return adv
 
 
+def gae_bootstrap_v10(rewards, values, dones, next_value, gamma: float, lam: float):
+    """P5' literal transcription of PPOV1.1/train_ppo1.0.py:72-89 (same loop in PPOV1.0/ppo0.0.py:330-353 and
+    train_ppo_gail.py) for one flat buffer: returns (normalised advantages, returns = RAW advantage + value)."""
+    rewards = torch.as_tensor(rewards, dtype=torch.float32)
+    values = torch.as_tensor(values, dtype=torch.float32)
+    dones = torch.as_tensor(dones, dtype=torch.float32)
+    next_value = torch.as_tensor(next_value, dtype=torch.float32)
+    advantages = torch.zeros_like(rewards)
+    returns = torch.zeros_like(rewards)
+    gae = 0
+    for t in reversed(range(len(rewards))):
+        if t == len(rewards) - 1:
+            next_non_terminal = 1.0 - dones[t]
+            next_value_t = next_value
+        else:
+            next_non_terminal = 1.0 - dones[t + 1]
+            next_value_t = values[t + 1]
+        delta = rewards[t] + gamma * next_value_t * next_non_terminal - values[t]
+        gae = delta + gamma * lam * next_non_terminal * gae
+        advantages[t] = gae
+        returns[t] = advantages[t] + values[t]
+    advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+    return advantages, returns
+
+
+def gae_v12(rewards, values, dones, gamma: float, lam: float):
+    """P5' literal transcription of PPOV1.2/ppo注释版.py:366-380 for one flat buffer: returns (normalised
+    advantages, returns = normalised advantage + value)."""
+    rewards = torch.as_tensor(rewards, dtype=torch.float32)
+    values = torch.as_tensor(values, dtype=torch.float32)
+    dones = torch.as_tensor(dones, dtype=torch.float32)
+    advantages = torch.zeros_like(rewards)
+    last_advantage = 0
+    for t in reversed(range(len(rewards))):
+        if t < len(rewards) - 1:
+            next_value = values[t + 1] * (1 - dones[t])
+        else:
+            next_value = 0
+        delta = rewards[t] + gamma * next_value - values[t]
+        advantages[t] = delta + gamma * lam * last_advantage * (1 - dones[t])
+        last_advantage = advantages[t]
+    advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+    return advantages, advantages + values
+
+
 # --------------------------------------------------------------------------------------
 # P6/P7: clipped-surrogate loss and optimiser step, train_ppo2.0.py:42-87
 # --------------------------------------------------------------------------------------

@@ -61,7 +61,11 @@ def _worker(rank, world, port, out):
     (total * local_mb / pd.global_minibatch(local_mb, pg)).backward()
     flat = torch.cat([p.grad.flatten() for p in model.parameters()])
     pd.allreduce_gradient(flat, pg)
-    out[rank] = (adv_n.numpy(), flat.numpy(), stats.numpy())
+    # curriculum flags: canonical order = step-major, then GLOBAL env id
+    dn = torch.full((3, 4), float(rank)) + torch.arange(4)[None, :] * 0.1 + torch.arange(3)[:, None] * 10
+    rc = (torch.arange(12).reshape(3, 4) + 100 * rank).to(torch.uint8)
+    d_all, r_all = pd.gather_episode_flags(dn, rc, pg)
+    out[rank] = (adv_n.numpy(), flat.numpy(), stats.numpy(), d_all.numpy(), r_all.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -95,6 +99,15 @@ def test_two_ranks_equal_one_rank():
     want = torch.cat([p.grad.flatten() for p in model.parameters()]).numpy()
     assert np.allclose(out[0][1], want, rtol=1e-4, atol=1e-7)
     assert np.array_equal(out[0][1], out[1][1])
+    # gathered curriculum flags: identical on both ranks, [T, world*N] with rank-major env ids
+    d_all, r_all = out[0][3], out[0][4]
+    assert np.array_equal(d_all, out[1][3]) and np.array_equal(r_all, out[1][4])
+    assert d_all.shape == (3, 8)
+    for t in range(3):
+        for rk in range(2):
+            for e in range(4):
+                assert np.isclose(d_all[t, rk * 4 + e], rk + 0.1 * e + 10 * t)
+                assert r_all[t, rk * 4 + e] == (t * 4 + e + 100 * rk) % 256
 
 
 def test_normalisation_from_stats_matches_oracle():

@@ -55,6 +55,42 @@ def test_gae_scan_bit_exact_and_normalise(T, N):
         assert torch.allclose(buf.returns.cpu(), r_ref, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("variant", ["bootstrap", "v12"])
+def test_gae_variants_of_the_older_drivers(variant):
+    """P5': PPOV1.1/train_ppo1.0.py:66-89 and PPOV1.2 advantage loops (flags, not the V2.x parity target)."""
+    m = pb()
+    cfg = m.config_for("2.1")
+    T, N = 96, 7
+    buf = _fill_buffer(m, T, N, 77)
+    ws = m.UpdateWorkspace("cuda", 256)
+    rng = np.random.default_rng(5)
+    last = torch.from_numpy(rng.normal(size=N).astype(np.float32))
+    m.compute_advantages(buf, cfg, ws, variant=variant, last_values=last if variant == "bootstrap" else None)
+    adv, ret = buf.advantages.cpu(), buf.returns.cpu()
+    # the reference loops run on one flat buffer: compare column by column on the raw scan via the returns
+    r, v, d = buf.rewards.cpu(), buf.values.cpu(), buf.dones.cpu()
+    raw = torch.zeros(T, N)
+    for n in range(N):
+        if variant == "bootstrap":
+            a_n, ret_n = pp.gae_bootstrap_v10(r[:, n], v[:, n], d[:, n], last[n], cfg.gamma, cfg.lam)
+            raw[:, n] = ret_n - v[:, n]
+            assert torch.allclose(ret[:, n], ret_n, rtol=1e-6, atol=1e-6)         # returns = raw advantage + value
+        else:
+            a_n, ret_n = pp.gae_v12(r[:, n], v[:, n], d[:, n], cfg.gamma, cfg.lam)
+            # un-normalise the column result to get the raw scan back
+            raw_n = torch.zeros(T)
+            last_adv = 0.0
+            for t in reversed(range(T)):
+                nv = v[t + 1, n] * (1 - d[t, n]) if t < T - 1 else 0.0
+                raw_n[t] = r[t, n] + cfg.gamma * nv - v[t, n] + cfg.gamma * cfg.lam * last_adv * (1 - d[t, n])
+                last_adv = raw_n[t]
+            raw[:, n] = raw_n
+    want = (raw - raw.mean()) / (raw.std() + 1e-8)
+    assert torch.allclose(adv, want, rtol=1e-5, atol=1e-5)
+    if variant == "v12":
+        assert torch.allclose(ret, want + v, rtol=1e-5, atol=1e-5)
+
+
 def test_gae_degenerate_std():
     """adv_std < 1e-6 -> divide by 1 (train_ppo2.0.py:36-37)."""
     m = pb()

@@ -62,6 +62,7 @@ class PpoBatch(C.Structure):
                 ("advantages", _vp), ("returns", _vp), ("old_values", _vp)]
 
 
+GAE_VARIANTS = {"quirk": 0, "bootstrap": 1, "v12": 2}
 MODEL_ISOTROPIC, MODEL_DISPERSION = 0, 1
 PLUME_MODELS = {"isotropic": MODEL_ISOTROPIC, "code": MODEL_ISOTROPIC, "dispersion": MODEL_DISPERSION,
                 "readme": MODEL_DISPERSION}
@@ -99,6 +100,9 @@ _SIGNATURES = {
                                 C.c_uint32, _vp, _vp]),
     "plume_gae_scan": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, _vp, _vp, _vp]),
     "plume_gae_normalise": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "plume_gae_scan_variant": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
+                                         _vp, _vp, _vp]),
+    "plume_gae_normalise_variant": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int32, _vp, _vp]),
     "plume_ppo_grad": (C.c_int, [_vp, _P(PpoBatch), _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "plume_ppo_workspace_bytes": (C.c_int64, [C.c_int64]),

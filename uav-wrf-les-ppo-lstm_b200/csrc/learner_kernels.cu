@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float* __restrict__
                                                        const float* __restrict__ values,
                                                        const float* __restrict__ dones, int T, int N, float gamma,
                                                        float gamma_lam, float* __restrict__ adv,
-                                                       double* __restrict__ stats) {
+                                                       double* __restrict__ stats, int variant,
+                                                       const float* __restrict__ last_values) {
     __shared__ double scratch[4];
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
@@ -35,16 +36,29 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float* __restrict__
         for (int t = T - 1; t >= 0; --t) {
             const size_t i = (size_t)t * N + n;
             const float r = rewards[i], v = values[i], d = dones[i];
-            float nnt, nv;
-            if (t == T - 1) {                      // :22-24 self-bootstrap
-                nnt = __fsub_rn(1.0f, d);
-                nv = __fmul_rn(v, nnt);
-            } else {                               // :26-27 masks with dones[t+1]
-                nnt = __fsub_rn(1.0f, d_next);
-                nv = __fmul_rn(v_next, nnt);
+            float a;
+            if (variant == PLUME_GAE_QUIRK) {
+                float nnt, nv;
+                if (t == T - 1) {                      // :22-24 self-bootstrap
+                    nnt = __fsub_rn(1.0f, d);
+                    nv = __fmul_rn(v, nnt);
+                } else {                               // :26-27 masks with dones[t+1]
+                    nnt = __fsub_rn(1.0f, d_next);
+                    nv = __fmul_rn(v_next, nnt);
+                }
+                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);          // :29
+                a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));              // :30
+            } else if (variant == PLUME_GAE_BOOTSTRAP) {   // PPOV1.1/train_ppo1.0.py:75-85
+                const float nnt = __fsub_rn(1.0f, t == T - 1 ? d : d_next);
+                const float nv = (t == T - 1) ? last_values[n] : v_next;
+                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nv), nnt)), v);
+                a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));
+            } else {                                       // PPOV1.2: masks with dones[t], no bootstrap (:368-376)
+                const float nt = __fsub_rn(1.0f, d);
+                const float nv = (t == T - 1) ? 0.0f : __fmul_rn(v_next, nt);
+                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);
+                a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, last), nt));
             }
-            const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);          // :29
-            const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));  // :30
             adv[i] = a;
             last = a;
             v_next = v;
@@ -66,20 +80,23 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) gae_normalise_kernel(float* __restrict__ adv, const float* __restrict__ values,
                                                             long long count, const double* __restrict__ stats,
-                                                            float* __restrict__ returns) {
+                                                            float* __restrict__ returns, int variant) {
     const double cnt = stats[2];
     const double mean = stats[0] / cnt;
     double var = (stats[1] - cnt * mean * mean) / (cnt - 1.0);       // unbiased, torch .std()
     var = var < 0.0 ? 0.0 : var;
     double sd = sqrt(var);
-    if (!(sd >= 1e-6)) sd = 1.0;                                       // :36-37 (also catches NaN)
+    if (variant == PLUME_GAE_QUIRK && !(sd >= 1e-6)) sd = 1.0;         // :36-37 (also catches NaN)
     const float mean32 = (float)mean;
-    const float denom = __fadd_rn((float)sd, 1e-6f);                   // :38
+    // :38 divides by std + 1e-6; the older drivers by std + 1e-8 (train_ppo1.0.py:89, ppo注释版.py:379)
+    const float denom = __fadd_rn((float)sd, variant == PLUME_GAE_QUIRK ? 1e-6f : 1e-8f);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        const float a = __fdiv_rn(__fsub_rn(adv[i], mean32), denom);
+        const float raw = adv[i];
+        const float a = __fdiv_rn(__fsub_rn(raw, mean32), denom);
         adv[i] = a;
-        returns[i] = __fadd_rn(a, values[i]);                          // :39 (sic)
+        // :39 (sic) returns = NORMALISED advantage + value; train_ppo1.0.py:86 adds the raw advantage
+        returns[i] = __fadd_rn(variant == PLUME_GAE_BOOTSTRAP ? raw : a, values[i]);
     }
 }
 
@@ -219,25 +236,42 @@ __global__ void __launch_bounds__(1024) curriculum_kernel(const float* __restric
 
 using namespace plume;
 
-extern "C" int plume_gae_scan(const float* rewards, const float* values, const float* dones, int32_t horizon,
-                              int32_t n_envs, double gamma, double lam, float* advantages, double* stats,
-                              void* stream) {
+extern "C" int plume_gae_scan_variant(const float* rewards, const float* values, const float* dones,
+                                      const float* last_values, int32_t horizon, int32_t n_envs, double gamma,
+                                      double lam, int32_t variant, float* advantages, double* stats, void* stream) {
     PLUME_CHECK_ARG(rewards && values && dones && advantages && stats, "null pointer");
+    PLUME_CHECK_ARG(variant >= PLUME_GAE_QUIRK && variant <= PLUME_GAE_V12, "unknown GAE variant");
+    PLUME_CHECK_ARG(variant != PLUME_GAE_BOOTSTRAP || last_values, "the bootstrap variant needs last_values");
     if (horizon <= 0 || n_envs <= 0) return 0;
     gae_scan_kernel<<<(n_envs + 127) / 128, 128, 0, as_stream(stream)>>>(
-        rewards, values, dones, horizon, n_envs, (float)gamma, (float)(gamma * lam), advantages, stats);
+        rewards, values, dones, horizon, n_envs, (float)gamma, (float)(gamma * lam), advantages, stats, variant,
+        last_values);
     PLUME_LAUNCH_CHECK();
     return 0;
 }
 
+extern "C" int plume_gae_scan(const float* rewards, const float* values, const float* dones, int32_t horizon,
+                              int32_t n_envs, double gamma, double lam, float* advantages, double* stats,
+                              void* stream) {
+    return plume_gae_scan_variant(rewards, values, dones, nullptr, horizon, n_envs, gamma, lam, PLUME_GAE_QUIRK,
+                                  advantages, stats, stream);
+}
+
 extern "C" int plume_gae_normalise(float* advantages, const float* values, int64_t count, const double* stats,
                                    float* returns, void* stream) {
+    return plume_gae_normalise_variant(advantages, values, count, stats, PLUME_GAE_QUIRK, returns, stream);
+}
+
+extern "C" int plume_gae_normalise_variant(float* advantages, const float* values, int64_t count, const double* stats,
+                                           int32_t variant, float* returns, void* stream) {
     PLUME_CHECK_ARG(advantages && values && stats && returns, "null pointer");
+    PLUME_CHECK_ARG(variant >= PLUME_GAE_QUIRK && variant <= PLUME_GAE_V12, "unknown GAE variant");
     if (count <= 0) return 0;
     long long blocks = (count + 255) / 256;
     const long long cap = 8LL * (sm_count() > 0 ? sm_count() : 148);
     if (blocks > cap) blocks = cap;
-    gae_normalise_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(advantages, values, count, stats, returns);
+    gae_normalise_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(advantages, values, count, stats, returns,
+                                                                          variant);
     PLUME_LAUNCH_CHECK();
     return 0;
 }

@@ -4,7 +4,10 @@ The only exchange steps of the path are (1) three doubles per update -- {sum, su
 count} of the raw advantages, so that every rank normalises with the *global* statistics
 (train_ppo2.0.py:34-38 over the whole batch) -- and (2) one all-reduce (sum) of the flat gradient
 per minibatch; each rank divides its loss by the global minibatch size, so the sum is the
-gradient of the global mean loss (train_ppo2.0.py:70-87).  NCCL on the GPUs, gloo in CPU tests."""
+gradient of the global mean loss (train_ppo2.0.py:70-87); and (3) one all-gather of the segment's
+done/reached flags per update (5 B per transition), so that every rank applies the curriculum
+(model.py:188-221) to the GLOBAL episode stream in canonical order (step-major, then global env id) and
+all ranks hold the same radius / explore bonus.  NCCL on the GPUs, gloo in CPU tests."""
 from __future__ import annotations
 
 import os
@@ -62,3 +65,18 @@ def normalisation_from_stats(stats: torch.Tensor):
     if not (sd >= 1e-6):
         sd = 1.0
     return mean, sd + 1e-6
+
+
+def gather_episode_flags(dones: torch.Tensor, reached: torch.Tensor, process_group=None):
+    """``dones`` float32 [T, N], ``reached`` uint8 [T, N] of this rank -> the same flags of ALL ranks in
+    canonical order [T, world * N] (global env id = rank * N + local id)."""
+    if process_group is None:
+        return dones, reached
+    world = dist.get_world_size(process_group)
+    T, N = dones.shape
+    d_all = torch.empty(world, T, N, dtype=dones.dtype, device=dones.device)
+    r_all = torch.empty(world, T, N, dtype=reached.dtype, device=reached.device)
+    dist.all_gather(list(d_all.unbind(0)), dones.contiguous(), group=process_group)
+    dist.all_gather(list(r_all.unbind(0)), reached.contiguous(), group=process_group)
+    return (d_all.permute(1, 0, 2).reshape(T, world * N).contiguous(),
+            r_all.permute(1, 0, 2).reshape(T, world * N).contiguous())

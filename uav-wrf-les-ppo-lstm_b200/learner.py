@@ -73,20 +73,27 @@ class UpdateWorkspace:
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
 
 
-def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_group=None) -> None:
+def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_group=None, variant: str = "quirk",
+                       last_values=None) -> None:
     """P5: GAE reverse scan per env column + global normalisation; fills ``buffer.advantages``
-    and ``buffer.returns`` (train_ppo2.0.py:17-39)."""
+    and ``buffer.returns`` (train_ppo2.0.py:17-39).  ``variant``: "quirk" (the V2.x/V1.1 update, the
+    parity target), "bootstrap" (PPOV1.1/train_ppo1.0.py:66-89, needs ``last_values`` [N] = V(next state))
+    or "v12" (PPOV1.2)."""
     lib = _lib.load()
     T, N, dev = buffer.filled, buffer.num_envs, buffer.device
+    var = _lib.GAE_VARIANTS[variant]
+    if last_values is not None:
+        last_values = torch.as_tensor(last_values, dtype=torch.float32, device=dev).reshape(N).contiguous()
     ws.stats.zero_()
     with torch.cuda.device(dev):
-        _lib.check(lib.plume_gae_scan(buffer.rewards.data_ptr(), buffer.values.data_ptr(), buffer.dones.data_ptr(), T,
-                                      N, cfg.gamma, cfg.lam, buffer.advantages.data_ptr(), ws.stats.data_ptr(),
-                                      _stream(dev)), "plume_gae_scan")
+        _lib.check(lib.plume_gae_scan_variant(buffer.rewards.data_ptr(), buffer.values.data_ptr(),
+                                              buffer.dones.data_ptr(), _lib.ptr(last_values), T, N, cfg.gamma, cfg.lam,
+                                              var, buffer.advantages.data_ptr(), ws.stats.data_ptr(), _stream(dev)),
+                   "plume_gae_scan_variant")
         pdist.allreduce_stats(ws.stats, process_group)
-        _lib.check(lib.plume_gae_normalise(buffer.advantages.data_ptr(), buffer.values.data_ptr(), T * N,
-                                           ws.stats.data_ptr(), buffer.returns.data_ptr(), _stream(dev)),
-                   "plume_gae_normalise")
+        _lib.check(lib.plume_gae_normalise_variant(buffer.advantages.data_ptr(), buffer.values.data_ptr(), T * N,
+                                                   ws.stats.data_ptr(), var, buffer.returns.data_ptr(), _stream(dev)),
+                   "plume_gae_normalise_variant")
 
 
 def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms=None,
@@ -187,12 +194,16 @@ class PPOTrainer:
             self._dev_state = s
         return self._dev_state
 
-    def update_from_rollout(self, buffer) -> None:
+    def update_from_rollout(self, buffer, process_group=None) -> None:
+        """With ``process_group`` the flags of all ranks are gathered first, so every rank replays the
+        same global episode stream and ends with identical curriculum scalars."""
         lib = _lib.load()
         c, st = self.cfg, self.device_state()
+        T = buffer.filled
+        dones, reached = pdist.gather_episode_flags(buffer.dones[:T], buffer.reached[:T], process_group)
         with torch.cuda.device(self.env.device):
-            rc = lib.plume_curriculum_update(buffer.dones.data_ptr(), buffer.reached.data_ptr(), buffer.filled,
-                                             buffer.num_envs, st.data_ptr(), self.env.curriculum.data_ptr(),
+            rc = lib.plume_curriculum_update(dones.data_ptr(), reached.data_ptr(), T,
+                                             dones.shape[1], st.data_ptr(), self.env.curriculum.data_ptr(),
                                              c.initial_radius, c.min_radius, c.radius_decay, c.success_threshold,
                                              c.window_size, c.decay_factor, _stream(self.env.device))
         _lib.check(rc, "plume_curriculum_update")

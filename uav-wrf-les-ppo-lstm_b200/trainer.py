@@ -46,7 +46,7 @@ class PlumeTrainer:
 
     def train_iteration(self, check_nan: bool = False):
         buf = self.engine.collect()
-        self.curriculum.update_from_rollout(buf)
+        self.curriculum.update_from_rollout(buf, self.process_group)
         self.last_losses = update_model(buf, self.model, self.optimizer, cfg=self.cfg,
                                         minibatch_size=self.minibatch_size, workspace=self.workspace,
                                         process_group=self.process_group, perm_seed=self.iteration,

@@ -2,7 +2,7 @@
 // (train_ppo2.0.py:42-85) with the three GEMM-shaped parts of the actor-critic's 256->128 layer
 // (model.py:23) on tcgen05.mma (kind::tf32, 3xTF32 split = fp32-grade accuracy, accumulators in
 // TMEM) and everything else (6->256 layer, both LayerNorms, heads, loss, all the reductions) on the
-// CUDA cores of the same persistent CTA.  One CTA per SM, 128-sample tiles, 256 threads.
+// CUDA cores of the same persistent CTA.  One CTA per SM, 128-sample tiles, 16 compute warps + 1 issuer warp.
 //
 //   G1  z2[s][o]   = sum_i  h1[s][i] W2[o][i]        A = h1 (produced chunk by chunk from the 6 inputs),
 //                                                     B = W2, pre-split, streamed from L2 with cp.async
@@ -30,7 +30,9 @@
 namespace plume {
 
 constexpr int kTcTile = 128;
-constexpr int kTcThreads = 256;
+constexpr int kTcGroups = 4;                       // 128-thread groups of compute threads
+constexpr int kTcThreads = 128 * kTcGroups;        // compute threads (producers + epilogues): 16 warps
+constexpr int kTcLaunchThreads = kTcThreads + 32;  // + one warp whose lane 0 only issues the MMAs
 constexpr int kXhStride = 132;             // [128][132]: conflict-free float4 rows and columns
 constexpr int kStageStride = 129;          // [128][129]: transposed dy1 staging
 constexpr int kChunkFloats = 128 * tc::kChunkK;
@@ -46,9 +48,12 @@ struct TcSmem {
     static constexpr int x = bh + 8;                                 // [128][8] x0..x5, rstd1, 0
     static constexpr int dout = x + kTcTile * 8;                     // [128][8] d loss / d (logits, value)
     static constexpr int sc = dout + kTcTile * 8;                    // [128][4] rstd2, m1, m2, 0
-    static constexpr int exch = sc + kTcTile * 4;                    // [2][128][8] column-half exchange
-    static constexpr int total = exch + 2 * kTcTile * 8;
+    static constexpr int total = sc + kTcTile * 4;
+    // [groups][128][8] exchange of partial sums between the column groups of one sample row: aliases the last
+    // operand buffer of the ring, which is idle whenever it is used (no MMA in flight, no production running)
+    static constexpr int exch = ring + 7 * kChunkFloats;
 };
+static_assert(kTcGroups * kTcTile * 8 <= kChunkFloats, "exchange area must fit one operand buffer");
 static_assert(TcSmem::total * 4 + 64 <= 227 * 1024, "ppo_tc_kernel: shared memory plan exceeds 227 KB");
 static_assert(kTcTile * kStageStride <= kTcTile * kXhStride, "dy1 staging must fit in the xhat region");
 
@@ -63,6 +68,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// barrier of the 256 compute threads (the issuer warp never takes part)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTcThreads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
     tc::split_tf32(v.x, h.x, l.x);
@@ -86,55 +96,72 @@ __global__ void ppo_tc_prep_kernel(const float* __restrict__ params, float* __re
     w2s[kW2SplitG2Lo + g2] = lo;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcLaunchThreads, 1)
 ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s) {
     extern __shared__ __align__(128) float sm[];     // no-swizzle operand layouts need 16 B alignment only
-    __shared__ uint64_t bar[2];
+    __shared__ uint64_t bar[2];           // "stage free": arrived by tcgen05.commit
+    __shared__ uint64_t full[2];          // "operands of the stage written": one arrival per compute thread
     __shared__ uint32_t tmem_slot;
+    __shared__ float cta_acc[48];         // per-CTA sums of the per-sample scalars (see the flush)
+    __shared__ double cta_loss[4];
+
+    constexpr int G = kTcGroups;
+    constexpr int CW = 128 / G;           // columns per thread in the TMEM epilogues (32)
+    constexpr int UPT = 8 / G;            // 16-byte operand units per thread and chunk (2)
+    constexpr int SPT = 128 / G;          // samples per thread in the column-oriented phases (32)
+    static_assert(CW == 32 && UPT >= 1, "the epilogues read one 32-column TMEM slab per thread");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wq = warp & 3, ch = warp >> 2;          // TMEM lane quarter / column half of this warp
-    const int srow = wq * 32 + lane;                  // TMEM lane = tile row owned in the epilogues
-    const int r128 = tid & 127, uh = tid >> 7;        // (row, half) mapping of the producer phases
+    const int wq = warp & 3, cg = (warp >> 2) & (G - 1);   // TMEM lane quarter / column group of this warp
+    const int srow = wq * 32 + lane;                       // TMEM lane = tile row owned in the epilogues
+    const int r128 = tid & 127, ug = (tid >> 7) & (G - 1); // (row, group) mapping of the producer phases
 
     // ---- one-time setup ----------------------------------------------------------------------------
     if (tid == 0) {
         tc::mbar_init(&bar[0], 1);
         tc::mbar_init(&bar[1], 1);
+        tc::mbar_init(&full[0], kTcThreads);
+        tc::mbar_init(&full[1], kTcThreads);
         tc::mbar_fence_init();
     }
+    if (tid < 48) cta_acc[tid] = 0.0f;
+    if (tid < 4) cta_loss[tid] = 0.0;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    float* const exch = sm + TcSmem::exch;
     if (tid < 7) {          // column means of feature.0.weight (k < 6) and the mean of feature.0.bias
         float m = 0.0f;
         for (int o = 0; o < 256; ++o) m += (tid < 6) ? params[PLUME_OFF_W1 + o * 6 + tid] : params[PLUME_OFF_B1 + o];
-        sm[TcSmem::exch + tid] = m * (1.0f / 256.0f);
+        exch[tid] = m * (1.0f / 256.0f);
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    for (int i = tid; i < 6 * 256; i += kTcThreads) {
-        const int o = i / 6, k = i - o * 6;
-        sm[TcSmem::W1c + k * 256 + o] = params[PLUME_OFF_W1 + i] - sm[TcSmem::exch + k];
+    if (tid < kTcThreads) {
+        for (int i = tid; i < 6 * 256; i += kTcThreads) {
+            const int o = i / 6, k = i - o * 6;
+            sm[TcSmem::W1c + k * 256 + o] = params[PLUME_OFF_W1 + i] - exch[k];
+        }
+        for (int i = tid; i < 256; i += kTcThreads) {
+            sm[TcSmem::P1 + i] = params[PLUME_OFF_B1 + i] - exch[6];
+            sm[TcSmem::P1 + 256 + i] = params[PLUME_OFF_G1 + i];
+            sm[TcSmem::P1 + 512 + i] = params[PLUME_OFF_BE1 + i];
+        }
+        for (int i = tid; i < 128; i += kTcThreads) {
+            sm[TcSmem::P2 + i] = params[PLUME_OFF_B2 + i];
+            sm[TcSmem::P2 + 128 + i] = params[PLUME_OFF_G2 + i];
+            sm[TcSmem::P2 + 256 + i] = params[PLUME_OFF_BE2 + i];
+        }
+        for (int i = tid; i < 128 * 8; i += kTcThreads) {
+            const int k = i >> 3, o = i & 7;
+            float w = 0.0f;
+            if (o < 5) w = params[PLUME_OFF_WA + o * 128 + k];
+            else if (o == 5) w = params[PLUME_OFF_WC + k];
+            sm[TcSmem::Wh + i] = w;
+        }
+        if (tid < 8)
+            sm[TcSmem::bh + tid] = tid < 5 ? params[PLUME_OFF_BA + tid] : (tid == 5 ? params[PLUME_OFF_BC] : 0.0f);
     }
-    for (int i = tid; i < 256; i += kTcThreads) {
-        sm[TcSmem::P1 + i] = params[PLUME_OFF_B1 + i] - sm[TcSmem::exch + 6];
-        sm[TcSmem::P1 + 256 + i] = params[PLUME_OFF_G1 + i];
-        sm[TcSmem::P1 + 512 + i] = params[PLUME_OFF_BE1 + i];
-    }
-    for (int i = tid; i < 128; i += kTcThreads) {
-        sm[TcSmem::P2 + i] = params[PLUME_OFF_B2 + i];
-        sm[TcSmem::P2 + 128 + i] = params[PLUME_OFF_G2 + i];
-        sm[TcSmem::P2 + 256 + i] = params[PLUME_OFF_BE2 + i];
-    }
-    for (int i = tid; i < 128 * 8; i += kTcThreads) {
-        const int k = i >> 3, o = i & 7;
-        float w = 0.0f;
-        if (o < 5) w = params[PLUME_OFF_WA + o * 128 + k];
-        else if (o == 5) w = params[PLUME_OFF_WC + k];
-        sm[TcSmem::Wh + i] = w;
-    }
-    if (tid < 8) sm[TcSmem::bh + tid] = tid < 5 ? params[PLUME_OFF_BA + tid] : (tid == 5 ? params[PLUME_OFF_BC] : 0.0f);
     __syncthreads();
 
     const uint32_t idesc = tc::make_idesc_tf32(128, 128);
@@ -144,9 +171,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     const float* const P2 = sm + TcSmem::P2;
     const float* const Wh = sm + TcSmem::Wh;
     float* const xt = sm + TcSmem::x;
-    float* const exch = sm + TcSmem::exch;
 
-    uint32_t step = 0;        // ring steps issued so far (uniform across the CTA)
+    uint32_t step = 0;        // ring steps so far (every compute thread counts them identically)
     // stage buffers of ring step st: which = 0 A_hi, 1 A_lo, 2 B_hi, 3 B_lo
     auto stage_buf = [&](uint32_t st, int which) -> float* {
         return sm + TcSmem::ring + ((st & 1u) * 4 + which) * kChunkFloats;
@@ -156,58 +182,73 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         const uint32_t use = st >> 1;
         if (use >= 1) tc::mbar_wait(&bar[st & 1u], (use - 1) & 1u);
     };
-    // B operand chunk (hi + lo, 16 KB each) from the pre-split weights: 8 x 16 B per thread
+    // B operand chunk (hi + lo, 16 KB each) from the pre-split weights, cp.async straight into shared memory
     auto load_b = [&](uint32_t st, const float* hi, const float* lo) {
         float4* bh4 = reinterpret_cast<float4*>(stage_buf(st, 2));
         float4* bl4 = reinterpret_cast<float4*>(stage_buf(st, 3));
         const float4* gh = reinterpret_cast<const float4*>(hi);
         const float4* gl = reinterpret_cast<const float4*>(lo);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 1024 / kTcThreads; ++q) {
             cp_async16(bh4 + tid + q * kTcThreads, gh + tid + q * kTcThreads);
             cp_async16(bl4 + tid + q * kTcThreads, gl + tid + q * kTcThreads);
         }
     };
-    // operands of step st are complete in shared memory: make them visible to the tensor core, issue
-    // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
-    auto publish_and_issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {
+    // producers: the operands of step st are complete in shared memory -> visible to the async proxy, arrive
+    auto publish = [&](uint32_t st) {
         cp_async_wait_all();
         tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-            if (col_small != col)
-                tc::mma_chunk_3xtf32_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),
-                                           stage_buf(st, 2), stage_buf(st, 3), idesc, first);
-            else
-                tc::mma_chunk_3xtf32(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2),
-                                     stage_buf(st, 3), idesc, first);
-            tc::mma_commit(&bar[st & 1u]);
-        }
+        tc::tc_fence_before();
+        mbar_arrive(&full[st & 1u]);
     };
-    // every MMA issued so far has completed
+    // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs, commit to "stage free"
+    // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
+    auto issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {
+        tc::mbar_wait(&full[st & 1u], (st >> 1) & 1u);
+        tc::tc_fence_after();
+        if (col_small != col)
+            tc::mma_chunk_3xtf32_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),
+                                       stage_buf(st, 2), stage_buf(st, 3), idesc, first);
+        else
+            tc::mma_chunk_3xtf32(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
+                                 idesc, first);
+        tc::mma_commit(&bar[st & 1u]);
+    };
+    // every MMA of the steps counted so far has completed
     auto wait_all_mma = [&]() {
         const uint32_t last = step - 1;
         tc::mbar_wait(&bar[last & 1u], (last >> 1) & 1u);
         tc::tc_fence_after();
     };
 
-    // ---- persistent accumulators ---------------------------------------------------------------------
-    float g_b2 = 0.0f, g_g2 = 0.0f, g_be2 = 0.0f, g_wh[6] = {0, 0, 0, 0, 0, 0};   // (o = r128, half uh)
-    float g_bh[6] = {0, 0, 0, 0, 0, 0};                                          // sample threads (tid < 128)
-    float Pacc[2][8];                                                             // (input r128 + 128 h, half uh)
+    const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
+
+    // ---- the MMA issuer: lane 0 of the last warp replays the step sequence of every tile -----------------
+    // (a dedicated warp keeps the blocking tcgen05.mma issue out of the producers' instruction streams and
+    // lets the ring run on mbarriers only: producers never meet at a CTA barrier inside a GEMM)
+    if (warp == kTcThreads / 32) {
+        if (lane == 0) {
+            uint32_t st = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const bool first_tile = (tile == (long long)blockIdx.x);
+                for (int c = 0; c < 8; ++c, ++st) issue(st, 0u, c == 0, 128u);                          // G1
+                for (int hN = 0; hN < 2; ++hN)
+                    for (int c = 0; c < 4; ++c, ++st) issue(st, (uint32_t)(128 * hN), c == 0, (uint32_t)(128 * hN));   // G2
+                for (int c = 0; c < 4; ++c)
+                    for (int hN = 0; hN < 2; ++hN, ++st)
+                        issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0, (uint32_t)(256 + 128 * hN));       // G3
+            }
+        }
+    } else {
+    // ---- persistent accumulators (everything else is reduced into shared memory tile by tile) -----------
+    float g_b2 = 0.0f, g_g2 = 0.0f, g_be2 = 0.0f, g_wh[6] = {0, 0, 0, 0, 0, 0};   // (output r128, sample group ug)
+    float Pacc[2][8];                                                             // (input r128 + 128 h, group ug)
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int c = 0; c < 8; ++c) Pacc[h][c] = 0.0f;
-    float sS0 = 0.0f, sS[6] = {0, 0, 0, 0, 0, 0}, sR[7] = {0, 0, 0, 0, 0, 0, 0}, sQ[21];   // sample threads
-#pragma unroll
-    for (int i = 0; i < 21; ++i) sQ[i] = 0.0f;
-    double l_tot = 0.0, l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
 
-    const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const bool first_tile = (tile == (long long)blockIdx.x);
         const long long base = tile * kTcTile;
         const int n_valid = (int)((a.mb_size - base) < kTcTile ? (a.mb_size - base) : kTcTile);
 
@@ -232,9 +273,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             *reinterpret_cast<float4*>(xt + tid * 8) = make_float4(xv[0], xv[1], xv[2], xv[3]);
             *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(xv[4], xv[5], 0.0f, 0.0f);
         }
-        __syncthreads();
+        compute_sync();
 
-        // ---- Ph1: LayerNorm-1 statistics: thread = (sample r128, 128 of the 256 outputs) ----------------
+        // ---- Ph1: LayerNorm-1 statistics: thread = (sample r128, 256/G of the 256 outputs) --------------
         float xr[6];
         {
             const float4 x0 = *reinterpret_cast<const float4*>(xt + r128 * 8);
@@ -242,8 +283,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             xr[0] = x0.x; xr[1] = x0.y; xr[2] = x0.z; xr[3] = x0.w; xr[4] = x1.x; xr[5] = x1.y;
             float sq = 0.0f;
 #pragma unroll 4
-            for (int u = 0; u < 32; ++u) {
-                const int in0 = uh * 128 + 4 * u;
+            for (int u = 0; u < 64 / G; ++u) {
+                const int in0 = ug * (256 / G) + 4 * u;
                 float4 z = *reinterpret_cast<const float4*>(P1 + in0);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
@@ -258,17 +299,19 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 sq = fmaf(z.z, z.z, sq);
                 sq = fmaf(z.w, z.w, sq);
             }
-            exch[(uh * kTcTile + r128) * 8] = sq;
+            exch[(ug * kTcTile + r128) * 8] = sq;
         }
-        __syncthreads();
+        compute_sync();
         if (tid < kTcTile) {
-            const float var = (exch[tid * 8] + exch[(kTcTile + tid) * 8]) * (1.0f / 256.0f);
-            xt[tid * 8 + 6] = 1.0f / sqrtf(var + kLnEps);
+            float var = 0.0f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) var += exch[(g * kTcTile + tid) * 8];
+            xt[tid * 8 + 6] = 1.0f / sqrtf(var * (1.0f / 256.0f) + kLnEps);
         }
-        __syncthreads();
+        compute_sync();
         const float rstd1 = xt[r128 * 8 + 6];
 
-        // ---- Ph2: G1 forward, K = 256 inputs in 8 chunks; thread = (sample r128, 4 of the 8 units) ----
+        // ---- Ph2: G1 forward, K = 256 inputs in 8 chunks; thread = (sample r128, 8/G of the 8 units) ----
         for (int c = 0; c < 8; ++c) {
             const uint32_t st = step;
             acquire(st);
@@ -276,8 +319,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
             float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
 #pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-                const int u = 4 * uh + uu, in0 = 32 * c + 4 * u;
+            for (int uu = 0; uu < UPT; ++uu) {
+                const int u = UPT * ug + uu, in0 = 32 * c + 4 * u;
                 float4 z = *reinterpret_cast<const float4*>(P1 + in0);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
@@ -300,51 +343,55 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 ah[f] = hi;
                 al[f] = lo;
             }
-            publish_and_issue(st, 0u, c == 0, 128u);     // columns [128,256) are free until G2 starts
+            publish(st);          // issuer: G1 -> columns [0,128), small terms -> [128,256) (free until G2)
             ++step;
         }
         wait_all_mma();
 
-        // ---- Ph3: LN2, heads, loss, LN2-backward means: thread = (sample srow, 64 of the 128 outputs) ----
-        float v[64];
+        // ---- Ph3: LN2, heads, loss, LN2-backward means: thread = (sample srow, 32 of the 128 outputs) ----
+        float v[CW];
         {
-            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * ch);
+            const int c0 = CW * cg;
+            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
             tc::tmem_ld32(taddr, v);
-            tc::tmem_ld32(taddr + 32u, v + 32);
             tc::tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {               // + the small cross terms (separate accumulator)
+            {                                               // + the small cross terms (separate accumulator)
                 float sm_terms[32];
-                tc::tmem_ld32(taddr + 128u + 32u * q, sm_terms);
+                tc::tmem_ld32(taddr + 128u, sm_terms);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[32 * q + j] += sm_terms[j];
+                for (int j = 0; j < 32; ++j) v[j] += sm_terms[j];
             }
             tc::tc_fence_before();
             float sum = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                v[j] += P2[64 * ch + j];
+            for (int j = 0; j < CW; ++j) {
+                v[j] += P2[c0 + j];
                 sum += v[j];
             }
-            float* mine = exch + (ch * kTcTile + srow) * 8;
-            const float* other = exch + ((ch ^ 1) * kTcTile + srow) * 8;
+            float* mine = exch + (cg * kTcTile + srow) * 8;
             mine[6] = sum;
-            __syncthreads();
-            const float mean = (sum + other[6]) * (1.0f / 128.0f);
+            compute_sync();
+            float tot = 0.0f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) tot += exch[(g * kTcTile + srow) * 8 + 6];
+            const float mean = tot * (1.0f / 128.0f);
             float sq = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
+            for (int j = 0; j < CW; ++j) {
                 const float d = v[j] - mean;
                 sq = fmaf(d, d, sq);
             }
             mine[7] = sq;
-            __syncthreads();
-            const float rstd2 = 1.0f / sqrtf((sq + other[7]) * (1.0f / 128.0f) + kLnEps);
+            compute_sync();
+            tot = 0.0f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) tot += exch[(g * kTcTile + srow) * 8 + 7];
+            const float rstd2 = 1.0f / sqrtf(tot * (1.0f / 128.0f) + kLnEps);
             float head[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int o = 64 * ch + j;
+            for (int j = 0; j < CW; ++j) {
+                const int o = c0 + j;
                 const float x_hat = (v[j] - mean) * rstd2;
                 v[j] = x_hat;
                 const float h2 = fmaxf(fmaf(x_hat, P2[128 + o], P2[256 + o]), 0.0f);
@@ -358,41 +405,68 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 head[5] = fmaf(h2, w1.y, head[5]);
             }
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-                *reinterpret_cast<float4*>(xh + srow * kXhStride + 64 * ch + 4 * q) =
+            for (int q = 0; q < CW / 4; ++q)
+                *reinterpret_cast<float4*>(xh + srow * kXhStride + c0 + 4 * q) =
                     make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 #pragma unroll
             for (int k = 0; k < 6; ++k) mine[k] = head[k];
-            __syncthreads();
-            if (ch == 0) {          // srow == tid: the thread that gathered this sample
+            compute_sync();
+            if (cg == 0) {          // srow == tid: the thread that gathered this sample
                 float dl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                double l_tot = 0.0, l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
                 if (srow < n_valid) {
                     float o6[6];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) o6[k] = head[k] + other[k] + sm[TcSmem::bh + k];
+                    for (int k = 0; k < 6; ++k) {
+                        float t = sm[TcSmem::bh + k];
+#pragma unroll
+                        for (int g = 0; g < G; ++g) t += exch[(g * kTcTile + srow) * 8 + k];
+                        o6[k] = t;
+                    }
                     const SampleLoss L = ppo_sample_loss(o6, r_act, r_adv, r_ret, r_vold, r_lpold, a.clip_eps,
                                                          a.entropy_beta, a.inv_global);
                     if (L.nan) atomicExch(a.nan_flag, 1);                           // train_ppo2.0.py:57-61
 #pragma unroll
+                    for (int k = 0; k < 6; ++k) dl[k] = L.dout[k];
+                    l_pol = (double)L.pol;
+                    l_val = (double)L.val;
+                    l_ent = (double)L.ent;
+                    l_tot = (double)L.pol + (double)L.val - (double)a.entropy_beta * (double)L.ent;
+                }
+                // head-bias gradients and the loss sums of this warp's 32 samples -> per-CTA accumulators
+                {
+                    float gb[6];
+#pragma unroll
                     for (int k = 0; k < 6; ++k) {
-                        dl[k] = L.dout[k];
-                        g_bh[k] += L.dout[k];
+                        gb[k] = dl[k];
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) gb[k] += __shfl_xor_sync(0xffffffffu, gb[k], off);
                     }
-                    l_pol += (double)L.pol;
-                    l_val += (double)L.val;
-                    l_ent += (double)L.ent;
-                    l_tot += (double)L.pol + (double)L.val - (double)a.entropy_beta * (double)L.ent;
+                    for (int off = 16; off > 0; off >>= 1) {
+                        l_tot += __shfl_xor_sync(0xffffffffu, l_tot, off);
+                        l_pol += __shfl_xor_sync(0xffffffffu, l_pol, off);
+                        l_val += __shfl_xor_sync(0xffffffffu, l_val, off);
+                        l_ent += __shfl_xor_sync(0xffffffffu, l_ent, off);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) atomicAdd(&cta_acc[35 + k], gb[k]);
+                        atomicAdd(&cta_loss[0], l_tot);
+                        atomicAdd(&cta_loss[1], l_pol);
+                        atomicAdd(&cta_loss[2], l_val);
+                        atomicAdd(&cta_loss[3], l_ent);
+                    }
                 }
                 *reinterpret_cast<float4*>(sm + TcSmem::dout + srow * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
                 *reinterpret_cast<float4*>(sm + TcSmem::dout + srow * 8 + 4) = make_float4(dl[4], dl[5], 0.0f, 0.0f);
             }
-            __syncthreads();
+            compute_sync();
             const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8);
             const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8 + 4);
             float m1p = 0.0f, m2p = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int o = 64 * ch + j;
+            for (int j = 0; j < CW; ++j) {
+                const int o = c0 + j;
                 const float g2 = P2[128 + o];
                 const float y = fmaf(v[j], g2, P2[256 + o]);
                 const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
@@ -409,14 +483,21 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             }
             mine[6] = m1p;
             mine[7] = m2p;
-            __syncthreads();
-            if (ch == 0)
+            compute_sync();
+            if (cg == 0) {
+                float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    t1 += exch[(g * kTcTile + srow) * 8 + 6];
+                    t2 += exch[(g * kTcTile + srow) * 8 + 7];
+                }
                 *reinterpret_cast<float4*>(sm + TcSmem::sc + srow * 4) =
-                    make_float4(rstd2, (m1p + other[6]) * (1.0f / 128.0f), (m2p + other[7]) * (1.0f / 128.0f), 0.0f);
-            __syncthreads();
+                    make_float4(rstd2, t1 * (1.0f / 128.0f), t2 * (1.0f / 128.0f), 0.0f);
+            }
+            compute_sync();
         }
 
-        // ---- Ph4: heads + LN2 backward per column: thread = (output r128, 64 of the 128 samples) ---------
+        // ---- Ph4: heads + LN2 backward per column: thread = (output r128, 128/G of the 128 samples) ------
         {
             const int o = r128;
             const float g2 = P2[128 + o], be2 = P2[256 + o];
@@ -424,8 +505,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
             for (int j = 0; j < 6; ++j) wrow[j] = Wh[o * 8 + j];
 #pragma unroll 4
-            for (int q = 0; q < 64; ++q) {
-                const int s = 64 * uh + q;
+            for (int q = 0; q < SPT; ++q) {
+                const int s = SPT * ug + q;
                 const float x_hat = xh[s * kXhStride + o];
                 const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8);
                 const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8 + 4);
@@ -447,7 +528,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 xh[s * kXhStride + o] = dz;                       // dz2 replaces xhat2
             }
         }
-        __syncthreads();
+        compute_sync();
 
         // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 4 chunks ------------
         for (int hN = 0; hN < 2; ++hN) {
@@ -459,8 +540,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
                 float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
 #pragma unroll
-                for (int uu = 0; uu < 4; ++uu) {
-                    const int u = 4 * uh + uu;
+                for (int uu = 0; uu < UPT; ++uu) {
+                    const int u = UPT * ug + uu;
                     const float4 d = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 32 * c + 4 * u);
                     float4 hi, lo;
                     split4(d, hi, lo);
@@ -468,7 +549,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     ah[f] = hi;
                     al[f] = lo;
                 }
-                publish_and_issue(st, (uint32_t)(128 * hN), c == 0, (uint32_t)(128 * hN));
+                publish(st);
                 ++step;
             }
         }
@@ -488,8 +569,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];
                 const float b1c = P1[in], g1 = P1[256 + in], be1 = P1[512 + in];
 #pragma unroll
-                for (int uu = 0; uu < 4; ++uu) {
-                    const int u = 4 * uh + uu, s0 = 32 * c + 4 * u;
+                for (int uu = 0; uu < UPT; ++uu) {
+                    const int u = UPT * ug + uu, s0 = 32 * c + 4 * u;
                     const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
                     // A: dz2^T, row = output r128, 4 consecutive samples
                     float4 d;
@@ -520,30 +601,30 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     bh4[f] = hi;
                     bl4[f] = lo;
                 }
-                publish_and_issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0, (uint32_t)(256 + 128 * hN));
+                publish(st);
                 ++step;
             }
         }
-        // (the acquires above waited for every G2 MMA; the xhat region is free after the last publish)
+        // (the acquires above waited for every G2 MMA)
 
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
+            compute_sync();        // every thread has read dz2 for its last G3 chunk: the region becomes staging
             tc::tc_fence_after();
             float m1p = 0.0f, m2p = 0.0f;
+            // this thread's sample: inputs + rstd1
+            const float4 sx0 = *reinterpret_cast<const float4*>(xt + srow * 8);
+            const float4 sx1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
+            const float xs[6] = {sx0.x, sx0.y, sx0.z, sx0.w, sx1.x, sx1.y};
 #pragma unroll
             for (int hN = 0; hN < 2; ++hN) {          // unrolled: Pacc[hN] must stay in registers
-                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 * hN + 64 * ch);
+                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 * hN + CW * cg);
                 tc::tmem_ld32(taddr, v);
-                tc::tmem_ld32(taddr + 32u, v + 32);
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
-                // this thread's sample: inputs + rstd1
-                const float4 x0 = *reinterpret_cast<const float4*>(xt + srow * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
-                const float xs[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
 #pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4) {
-                    const int in0 = 128 * hN + 64 * ch + 4 * j4;
+                for (int j4 = 0; j4 < CW / 4; ++j4) {
+                    const int in0 = 128 * hN + CW * cg + 4 * j4;
                     float4 z = *reinterpret_cast<const float4*>(P1 + in0);
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
@@ -559,20 +640,20 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                                 bb[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        const float x_hat = zz[jj] * x1.z;
+                        const float x_hat = zz[jj] * sx1.z;
                         const float y = fmaf(x_hat, gg[jj], bb[jj]);
                         const float dy = (y > 0.0f) ? v[4 * j4 + jj] : 0.0f;
                         const float t = dy * gg[jj];
                         m1p += t;
                         m2p = fmaf(t, x_hat, m2p);
-                        xh[(64 * ch + 4 * j4 + jj) * kStageStride + srow] = dy;     // staging [input][sample]
+                        xh[(CW * cg + 4 * j4 + jj) * kStageStride + srow] = dy;     // staging [input][sample]
                     }
                 }
-                __syncthreads();
-                // column sums: thread = (input r128 of this half, 64 of the 128 samples)
+                compute_sync();
+                // column sums: thread = (input r128 of this half, 128/G of the 128 samples)
 #pragma unroll 4
-                for (int q = 0; q < 64; ++q) {
-                    const int s = 64 * uh + q;
+                for (int q = 0; q < SPT; ++q) {
+                    const int s = SPT * ug + q;
                     const float dy = xh[r128 * kStageStride + s];
                     const float4 y0 = *reinterpret_cast<const float4*>(xt + s * 8);
                     const float4 y1 = *reinterpret_cast<const float4*>(xt + s * 8 + 4);
@@ -586,36 +667,51 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     Pacc[hN][6] += dr;
                     Pacc[hN][7] += dy;
                 }
-                __syncthreads();
+                compute_sync();
             }
-            float* mine = exch + (ch * kTcTile + srow) * 8;
-            const float* other = exch + ((ch ^ 1) * kTcTile + srow) * 8;
+            wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
+            float* mine = exch + (cg * kTcTile + srow) * 8;
             mine[6] = m1p;
             mine[7] = m2p;
-            __syncthreads();
-            if (ch == 0) {          // per-sample scalar sums of the layer-1 backward
-                const float m1 = (m1p + other[6]) * (1.0f / 256.0f), m2 = (m2p + other[7]) * (1.0f / 256.0f);
-                const float4 x0 = *reinterpret_cast<const float4*>(xt + srow * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
-                const float xs[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-                const float rs = x1.z;
+            compute_sync();
+            if (cg == 0) {          // per-sample scalar sums of the layer-1 backward -> per-CTA accumulators
+                float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    t1 += exch[(g * kTcTile + srow) * 8 + 6];
+                    t2 += exch[(g * kTcTile + srow) * 8 + 7];
+                }
+                const float m1 = t1 * (1.0f / 256.0f), m2 = t2 * (1.0f / 256.0f);
+                const float rs = sx1.z;
                 const float a1 = rs * m1, a2 = rs * rs * m2;
-                sS0 += a1;
-                sR[6] += a2;
-                int qi = 0;
+                float red[35];
+                red[0] = a1;
+                red[13] = a2;
+                {
+                    int qi = 0;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    sS[k] = fmaf(a1, xs[k], sS[k]);
-                    const float ax = a2 * xs[k];
-                    sR[k] += ax;
+                    for (int k = 0; k < 6; ++k) {
+                        red[1 + k] = a1 * xs[k];
+                        const float ax = a2 * xs[k];
+                        red[7 + k] = ax;
 #pragma unroll
-                    for (int k2 = k; k2 < 6; ++k2) {
-                        sQ[qi] = fmaf(ax, xs[k2], sQ[qi]);
-                        ++qi;
+                        for (int k2 = k; k2 < 6; ++k2) {
+                            red[14 + qi] = ax * xs[k2];
+                            ++qi;
+                        }
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < 35; ++k) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 35; ++k) atomicAdd(&cta_acc[k], red[k]);
+                }
             }
-            __syncthreads();       // exch / x tile / staging are rewritten by the next tile
+            compute_sync();       // exch / x tile / staging are rewritten by the next tile
         }
     }
 
@@ -623,13 +719,14 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     float* g = a.grads;
     if (step > 0) {
         wait_all_mma();
-        // dW2 accumulator: TMEM lane = output srow, this warp's column half = inputs [128 ch, 128 ch + 128)
+        // dW2 accumulator: TMEM lane = output srow, this warp's column group = inputs [64 cg, 64 cg + 64)
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 256 / G / 32; ++q) {
             float vv[32];
-            tc::tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(256 + 128 * ch + 32 * q), vv);
+            const int col = (256 / G) * cg + 32 * q;
+            tc::tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(256 + col), vv);
             tc::tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(g + PLUME_OFF_W2 + srow * 256 + 128 * ch + 32 * q);
+            float4* dst = reinterpret_cast<float4*>(g + PLUME_OFF_W2 + srow * 256 + col);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 atomicAdd(dst + i, make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]));
@@ -645,59 +742,30 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         for (int j = 0; j < 5; ++j) atomicAdd(g + PLUME_OFF_WA + j * 128 + o, g_wh[j]);
         atomicAdd(g + PLUME_OFF_WC + o, g_wh[5]);
     }
-    // layer 1: combine the two sample halves of P and the CTA's per-sample scalar sums
-    __syncthreads();
-    float* pbuf = xh;                      // [2 uh][256 inputs][8]
-    float* sbuf = xh + 2 * 256 * 8;        // [4 warps][48]
+    // layer 1: combine the sample groups of P and the CTA's per-sample scalar sums
+    compute_sync();
+    float* pbuf = xh;                      // [G][256 inputs][8]
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) pbuf[(uh * 256 + 128 * h + r128) * 8 + c] = Pacc[h][c];
-    if (tid < kTcTile) {
-        float red[41];
-        red[0] = sS0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) red[1 + k] = sS[k];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) red[7 + k] = sR[k];
-#pragma unroll
-        for (int k = 0; k < 21; ++k) red[14 + k] = sQ[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) red[35 + k] = g_bh[k];
-#pragma unroll
-        for (int k = 0; k < 41; ++k) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 41; ++k) sbuf[warp * 48 + k] = red[k];
-        }
-        for (int off = 16; off > 0; off >>= 1) {
-            l_tot += __shfl_xor_sync(0xffffffffu, l_tot, off);
-            l_pol += __shfl_xor_sync(0xffffffffu, l_pol, off);
-            l_val += __shfl_xor_sync(0xffffffffu, l_val, off);
-            l_ent += __shfl_xor_sync(0xffffffffu, l_ent, off);
-        }
-        if (lane == 0) {
-            const double inv = (double)a.inv_global;
-            atomicAdd(a.loss_out + 0, l_tot * inv);
-            atomicAdd(a.loss_out + 1, l_pol * inv);
-            atomicAdd(a.loss_out + 2, l_val * inv);
-            atomicAdd(a.loss_out + 3, l_ent * inv);
-        }
-    }
-    __syncthreads();
-    {
+        for (int c = 0; c < 8; ++c) pbuf[(ug * 256 + 128 * h + r128) * 8 + c] = Pacc[h][c];
+    compute_sync();
+    if (tid < 4) atomicAdd(a.loss_out + tid, cta_loss[tid] * (double)a.inv_global);
+    if (tid < 256) {
         float S[41];
 #pragma unroll
-        for (int k = 0; k < 41; ++k) S[k] = sbuf[k] + sbuf[48 + k] + sbuf[96 + k] + sbuf[144 + k];
+        for (int k = 0; k < 41; ++k) S[k] = cta_acc[k];
         if (tid < 5) atomicAdd(g + PLUME_OFF_BA + tid, S[35 + tid]);
         if (tid == 5) atomicAdd(g + PLUME_OFF_BC, S[40]);
         const int in = tid;                  // 256 threads = 256 layer-1 outputs
         float P[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) P[c] = pbuf[in * 8 + c] + pbuf[(256 + in) * 8 + c];
+        for (int c = 0; c < 8; ++c) {
+            float t = 0.0f;
+#pragma unroll
+            for (int gq = 0; gq < G; ++gq) t += pbuf[(gq * 256 + in) * 8 + c];
+            P[c] = t;
+        }
         float w[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];
@@ -732,6 +800,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             atomicAdd(g + PLUME_OFF_W1 + in * 6 + k2, g1 * P[k2] - S[1 + k2] - wq2);
         }
     }
+    }   // compute warps
+    tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
@@ -754,7 +824,7 @@ int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaSt
     int grid = sm_count();
     if (grid <= 0) return fail("no CUDA device");
     if (tiles < grid) grid = (int)tiles;
-    ppo_tc_kernel<<<grid, kTcThreads, smem, s>>>(params, a, w2s);
+    ppo_tc_kernel<<<grid, kTcLaunchThreads, smem, s>>>(params, a, w2s);
     if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_kernel launch failed");
     return 0;
 }

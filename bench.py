@@ -121,7 +121,7 @@ def _cpu_worker(args):
     return steps, time.perf_counter() - t0
 
 
-def cpu_baseline_single(n_steps: int = 12000) -> dict:
+def cpu_baseline_single(n_steps: int = 40000) -> dict:
     steps, dt = _cpu_worker((0, n_steps))
     return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{steps} env-steps of the reference loop (batch-1 policy forward + env.step + "
@@ -400,7 +400,7 @@ def main() -> None:
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--horizon", type=int, default=HORIZON)
-    ap.add_argument("--cpu-steps", type=int, default=12000)
+    ap.add_argument("--cpu-steps", type=int, default=40000)     # ~13 s of the reference loop on one core
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-aux", action="store_true")
     args = ap.parse_args()

@@ -19,7 +19,7 @@
 // and of 35 per-sample scalar sums (S0, S[6], R[7], Q[6][6] symmetric); see the epilogue at the end
 // of the kernel.  z1 - mean(z1) is evaluated directly from centred weights (W1 - column mean), so
 // no mean pass is needed.  The algebra was checked against autograd in float64 and its float32
-// error matches autograd's own (profiles/r1_notes.md).
+// error matches autograd's own.
 //
 // Algorithmic bytes per sample: 44 B gathered (obs 24, action 4, old logp 4, adv 4, ret 4, old value 4);
 // nothing else leaves the SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 for the split),

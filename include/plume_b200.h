@@ -250,6 +250,9 @@ typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major u
                             * (evaluate_with_lstm.py:67-70) */
     uint8_t* fill_t;       /* samples of the current episode in the window after the push (saturates at window) */
     double* src_dist;      /* ||agent_pos - source_pos|| after the step (environment.py:155), for the trend label */
+    /* trajectory logging in the training_data.nc layout (train_ppo2.0.py:166-170,207-233), optional: */
+    float* pos_out;        /* [T][N][2] agent_pos after the step, before a reset */
+    float* src_out;        /* [T][N][2] source_pos of the episode, written at its last transition only */
 } plume_rollout_buffers;
 
 /* T lockstep iterations of: policy forward + sample, env step, stop head, auto-reset; one

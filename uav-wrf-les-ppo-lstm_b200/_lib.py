@@ -54,7 +54,7 @@ class RolloutBuffers(C.Structure):
     _fields_ = [(n, _vp) for n in ("obs", "actions", "rewards", "values", "log_probs", "dones", "reached",
                                    "stop_prob", "stop_flag", "peak_pred", "trend", "info", "episode_idx",
                                    "forced_actions", "step_noise", "noise_out", "conc_window", "window_fill",
-                                   "last_obs", "conc_sample", "fill_t", "src_dist")]
+                                   "last_obs", "conc_sample", "fill_t", "src_dist", "pos_out", "src_out")]
 
 
 class PpoBatch(C.Structure):

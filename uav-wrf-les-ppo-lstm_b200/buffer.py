@@ -14,7 +14,8 @@ from . import _lib
 
 class PPOBuffer:
     def __init__(self, horizon: int = 256, num_envs: int = 1, device="cuda", with_info: bool = False,
-                 with_stop: bool = True, with_trend: bool = False, with_episode: bool = True):
+                 with_stop: bool = True, with_trend: bool = False, with_episode: bool = True,
+                 with_trajectory: bool = False):
         self.horizon, self.num_envs, self.device = int(horizon), int(num_envs), torch.device(device)
         T, N, dev = self.horizon, self.num_envs, self.device
         z = lambda dt, *s: torch.zeros(*s, dtype=dt, device=dev)
@@ -35,6 +36,9 @@ class PPOBuffer:
         self.conc_sample = z(torch.float32, T, N) if with_stop else None
         self.fill_t = z(torch.uint8, T, N) if with_stop else None
         self.src_dist = z(torch.float64, T, N) if (with_stop and with_trend) else None
+        # trajectory logging (trajectory_log.TrajectoryLogger): post-step positions, source at the episode's last step
+        self.pos_out = z(torch.float32, T, N, 2) if with_trajectory else None
+        self.src_out = z(torch.float32, T, N, 2) if with_trajectory else None
         self.advantages = z(torch.float32, T, N)
         self.returns = z(torch.float32, T, N)
         self.filled = 0          # rows written
@@ -81,4 +85,5 @@ class PPOBuffer:
                                    p(self.dones), p(self.reached), p(self.stop_prob), p(self.stop_flag),
                                    p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
                                    p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
-                                   p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist))
+                                   p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist),
+                                   p(self.pos_out), p(self.src_out))

@@ -133,11 +133,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 cell_tke = r.cell_tke;
                 // sliding window of obs[2] (= conc_field[int(x),int(y)]/100 as float32, evaluate_with_lstm.py:67-74)
                 fill = fill < W ? fill + 1 : W;
-                if (defer) {
-                    a.buf.conc_sample[row + env] = r.obs[2];
-                    a.buf.fill_t[row + env] = (uint8_t)fill;
-                    if (a.buf.src_dist) a.buf.src_dist[row + env] = r.distance;
-                } else {
+                if (a.buf.conc_sample) a.buf.conc_sample[row + env] = r.obs[2];
+                if (a.buf.fill_t) a.buf.fill_t[row + env] = (uint8_t)fill;
+                if (a.buf.src_dist) a.buf.src_dist[row + env] = r.distance;
+                if (!defer) {
                     for (int k = 0; k + 1 < W; ++k) win[k * 32 + tid] = win[(k + 1) * 32 + tid];
                     win[(W - 1) * 32 + tid] = r.obs[2];
                 }
@@ -174,6 +173,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                     if (a.buf.peak_pred) a.buf.peak_pred[i] = peak;
                 }
                 if (a.buf.episode_idx) a.buf.episode_idx[i] = (int32_t)ep_of_transition;
+                if (a.buf.pos_out) reinterpret_cast<float2*>(a.buf.pos_out)[i] = make_float2(e.px, e.py);
+                if (a.buf.src_out && done) reinterpret_cast<float2*>(a.buf.src_out)[i] = make_float2((float)e.sx, (float)e.sy);
                 if (a.buf.info) {
                     float* inf = a.buf.info + (size_t)t * 5 * N + env;
                     inf[0] = r.conc_reward;

@@ -19,7 +19,7 @@ from .config import FIELD_PROCEDURAL
 
 class RolloutEngine:
     def __init__(self, env, model, stop_head=None, horizon: int = 256, with_info: bool = False,
-                 with_trend: bool = False):
+                 with_trend: bool = False, with_trajectory: bool = False):
         if env.field_mode != FIELD_PROCEDURAL:
             raise ValueError("the fused rollout needs field_mode='procedural'")
         self.env, self.model, self.stop_head = env, model, stop_head
@@ -28,7 +28,7 @@ class RolloutEngine:
         dev, N = env.device, env.num_envs
         self.window = env.cfg.lstm_window
         self.buffer = PPOBuffer(horizon, N, dev, with_info=with_info, with_stop=stop_head is not None,
-                                with_trend=with_trend)
+                                with_trend=with_trend, with_trajectory=with_trajectory)
         self.conc_window = torch.zeros(N, self.window, dtype=torch.float32, device=dev)
         self._window_next = torch.zeros_like(self.conc_window)      # ring written by the deferred head
         self.window_fill = torch.zeros(N, dtype=torch.int32, device=dev)

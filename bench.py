@@ -281,10 +281,20 @@ def run_cuda_arm(args) -> None:
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(roll_ms, op=dist.ReduceOp.MAX)
+    skew = None
+    if world > 1:      # the rollout has no communication: its per-rank time shows how evenly the GPUs run
+        mine = torch.tensor([sum(ms_roll), sum(ms_steps)], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rr = torch.stack(allr).cpu() / args.steps
+        skew = {"rollout_ms_per_rank": [round(float(x), 3) for x in rr[:, 0]],
+                "iteration_ms_per_rank": [round(float(x), 3) for x in rr[:, 1]]}
     total_ms, roll_ms = float(total_ms.item()), float(roll_ms.item())
     trainer.engine.check_nan()
     if int(trainer.workspace.nan_flag.item()) != 0:
         raise RuntimeError("NaN in probs")
+    if trainer.comm is not None:
+        trainer.comm.check()
     env_steps_global = N * T * world * args.steps
     value = env_steps_global / (total_ms / 1e3)
     rollout_value = env_steps_global / (roll_ms / 1e3)
@@ -383,10 +393,13 @@ def run_cuda_arm(args) -> None:
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "horizon": T, "version": "2.1",
                        "minibatch": trainer.minibatch_size, "epochs": cfg.epochs, "field_mode": "procedural",
                        "lstm_hidden": 32, "lstm_window": cfg.lstm_window, "parallelism": f"env-shard x{world}",
+                       "gradient_exchange": ("none" if world == 1 else
+                                             ("fused all-reduce+clip+Adam kernel over NVLink peer memory"
+                                              if trainer.comm is not None else "NCCL all-reduce")),
                        "l2_flush": "256 MB write between timed steps"},
             "rollout_env_steps_per_sec": rollout_value,
             "roofline": roofline, "kernels": kernels, "plume_kernels": plume, "cpu_baseline": cpu, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": trainer.launches_per_iteration * args.steps}
+            "e2e": e2e, "gpu_launches": trainer.launches_per_iteration * args.steps, "rank_skew": skew}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

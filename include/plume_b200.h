@@ -253,6 +253,8 @@ typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major u
     /* trajectory logging in the training_data.nc layout (train_ppo2.0.py:166-170,207-233), optional: */
     float* pos_out;        /* [T][N][2] agent_pos after the step, before a reset */
     float* src_out;        /* [T][N][2] source_pos of the episode, written at its last transition only */
+    uint8_t* flag_code;    /* [T][N] bit 0 = done, bit 1 = reached: what the curriculum (and its multi-GPU
+                            * all-gather, 1 B per transition) consumes; may be NULL */
 } plume_rollout_buffers;
 
 /* T lockstep iterations of: policy forward + sample, env step, stop head, auto-reset; one
@@ -330,6 +332,25 @@ int plume_clip_adam(float* params, const float* grads, float* exp_avg, float* ex
                     float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
                     float* grad_norm_out, void* stream);
 
+/* ---- fused gradient all-reduce + clip + Adam over NVLink peer memory (one process per GPU) ------------------
+ * The only exchange step of the update (train_ppo2.0.py:85-87 on N data-parallel ranks) as ONE kernel: every
+ * rank publishes its gradient in a CUDA-IPC mapped buffer, a system-scope flag exchange replaces the
+ * collective's rendezvous, each rank sums all ranks' buffers in rank order (bitwise identical on every rank)
+ * and finishes clip_grad_norm_ + Adam from registers.
+ *   plume_comm_create   allocates this rank's block, returns an opaque communicator and its 64-byte IPC handle
+ *   plume_comm_connect  maps the peers' blocks: all_handles = the handles of ranks 0..world-1, 64 bytes each
+ *                       (exchange them with any host-side all-gather)
+ *   plume_allreduce_clip_adam  = all-reduce(sum) of grads over the ranks, then plume_clip_adam; grads receives
+ *                       the reduced gradient.  Every rank must call it the same number of times.
+ *   plume_comm_error    HOST out 0 ok / 1 a peer did not arrive (bounded spin) / 2 grid barrier timeout */
+int plume_comm_create(int32_t world, int32_t rank, int32_t n_params, void** comm_out, uint8_t* handle_out);
+int plume_comm_connect(void* comm, const uint8_t* all_handles);
+int plume_comm_destroy(void* comm);
+int plume_comm_error(void* comm, int32_t* error_out, void* stream);
+int plume_allreduce_clip_adam(void* comm, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int32_t n,
+                              float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
+                              float* grad_norm_out, void* stream);
+
 /* The index permutation plume_ppo_grad uses when perm == NULL: out int64[count] = positions
  * [start, start+count) of the bijection of [0,total) keyed by (seed, epoch). */
 int plume_permutation(int64_t total, uint64_t seed, int32_t epoch, int64_t start, int64_t count, int64_t* out,
@@ -351,6 +372,13 @@ int plume_curriculum_update(const float* dones, const uint8_t* reached, int32_t 
                             double* state, double* curriculum, double initial_radius, double min_radius,
                             double radius_decay, double success_threshold, int32_t window,
                             double decay_factor, void* stream);
+
+/* Same rule on packed flags of ALL ranks: flag_code uint8 [world][T][N] (bit 0 done, bit 1 reached; the layout an
+ * all-gather of the ranks' [T][N] arrays produces); canonical order = step-major, then global env id. */
+int plume_curriculum_update_packed(const uint8_t* flag_code, int32_t horizon, int32_t n_envs, int32_t world,
+                                   double* state, double* curriculum, double initial_radius, double min_radius,
+                                   double radius_decay, double success_threshold, int32_t window,
+                                   double decay_factor, void* stream);
 
 #ifdef __cplusplus
 }

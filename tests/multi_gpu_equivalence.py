@@ -36,6 +36,8 @@ def main():
         b = tr.engine.buffer
         snaps.append((b.obs.clone(), b.actions.clone(), b.rewards.clone(), b.dones.clone(), b.stop_prob.clone()))
     torch.cuda.synchronize()
+    if tr.comm is not None:
+        tr.comm.check()
     params = tr.model.flat.clone()
     cur = tr.curriculum.device_state().clone()
     gathered = [torch.empty_like(params) for _ in range(world)]
@@ -64,6 +66,7 @@ def main():
         moved = (ref.model.flat - ref.model.flat.new_tensor(0)).abs().max()
         err = (ref.model.flat - params).abs().max().item()
         step = ref.cfg.learning_rate * ref.cfg.epochs * iters
+        print(f"exchange: {'peer-memory fused all-reduce+clip+Adam' if tr.comm is not None else 'NCCL all-reduce'}")
         print(f"multi-gpu equivalence: {world} ranks x {M} envs vs 1 x {M * world}: max |dparam| = {err:.3e} "
               f"(total Adam movement {step:.1e}), episodes {int(rc[6])}, successes {int(rc[7])}")
         ok = err < 0.05 * step

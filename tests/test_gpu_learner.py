@@ -339,3 +339,41 @@ def test_curriculum_kernel_vs_oracle():
         assert st["window_successes"] == int(np.sum(ora.success_history))
         assert np.isclose(env.current_radius, ora.current_radius, rtol=1e-12)
     assert ora.current_radius < 50.0
+
+
+@pytest.mark.parametrize("world,T,N", [(3, 96, 40), (2, 48, 512), (1, 20, 1024)])
+def test_curriculum_packed_flags_of_several_ranks(world, T, N):
+    """plume_curriculum_update_packed on the all-gathered [world][T][N] flag codes == the reference rule applied
+    in canonical order (step-major, then global env id = rank * N + local id).  N % 512 == 0 takes the
+    four-kernel scalable path, other sizes the single-CTA scan."""
+    m = pb()
+    cfg = po.config_for("2.1")
+    rng = np.random.default_rng(9)
+
+    class E:
+        current_radius = 50.0
+        explore_bonus = 0.6
+    ora = pp.OracleCurriculum(E(), cfg)
+    lib = m._lib.load()
+    state = torch.zeros(8, dtype=torch.float64, device="cuda")
+    state[0], state[1], state[2], state[3] = 50.0, 0.6, 50.0, 0.6
+    cur = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for seg in range(4):
+        done = rng.random((world, T, N)) < 0.07
+        reached = done & (rng.random((world, T, N)) < [0.9, 0.8, 0.1, 0.95][seg])
+        code = torch.from_numpy((done.astype(np.uint8) | (reached.astype(np.uint8) << 1))).cuda().contiguous()
+        rc = lib.plume_curriculum_update_packed(code.data_ptr(), T, N, world, state.data_ptr(), cur.data_ptr(),
+                                                cfg.initial_radius, cfg.min_radius, cfg.radius_decay,
+                                                cfg.success_threshold, cfg.window_size, cfg.decay_factor,
+                                                torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        for t in range(T):
+            for r in range(world):
+                for n in range(N):
+                    if done[r, t, n]:
+                        ora.update(bool(reached[r, t, n]))
+        s = state.cpu().numpy()
+        assert np.isclose(s[0], ora.current_radius, rtol=1e-12) and np.isclose(s[1], ora.explore_bonus, rtol=1e-12)
+        assert int(s[4]) == len(ora.success_history) and int(s[5]) == int(np.sum(ora.success_history))
+        assert np.isclose(float(cur[0]), ora.current_radius, rtol=1e-12)
+    assert ora.current_radius < 50.0

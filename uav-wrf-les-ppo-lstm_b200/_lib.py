@@ -54,7 +54,7 @@ class RolloutBuffers(C.Structure):
     _fields_ = [(n, _vp) for n in ("obs", "actions", "rewards", "values", "log_probs", "dones", "reached",
                                    "stop_prob", "stop_flag", "peak_pred", "trend", "info", "episode_idx",
                                    "forced_actions", "step_noise", "noise_out", "conc_window", "window_fill",
-                                   "last_obs", "conc_sample", "fill_t", "src_dist", "pos_out", "src_out")]
+                                   "last_obs", "conc_sample", "fill_t", "src_dist", "pos_out", "src_out", "flag_code")]
 
 
 class PpoBatch(C.Structure):
@@ -108,10 +108,18 @@ _SIGNATURES = {
     "plume_ppo_workspace_bytes": (C.c_int64, [C.c_int64]),
     "plume_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_int32, _vp, _vp]),
+    "plume_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P(_vp), _vp]),
+    "plume_comm_connect": (C.c_int, [_vp, _vp]),
+    "plume_comm_destroy": (C.c_int, [_vp]),
+    "plume_comm_error": (C.c_int, [_vp, _P(C.c_int32), _vp]),
+    "plume_allreduce_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_float, C.c_int32, _vp, _vp]),
     "plume_permutation": (C.c_int, [C.c_int64, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, _vp, _vp]),
     "plume_tc_gemm": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "plume_curriculum_update": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double,
                                           C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
+    "plume_curriculum_update_packed": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_double,
+                                                 C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

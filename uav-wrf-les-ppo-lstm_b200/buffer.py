@@ -26,6 +26,8 @@ class PPOBuffer:
         self.log_probs = z(torch.float32, T, N)
         self.dones = z(torch.float32, T, N)
         self.reached = z(torch.uint8, T, N)
+        self.flag_code = z(torch.uint8, T, N)        # bit 0 done, bit 1 reached (curriculum input)
+        self.flag_code_valid = False                  # written by the rollout kernel (not by store())
         self.stop_prob = z(torch.float32, T, N) if with_stop else None
         self.stop_flag = z(torch.uint8, T, N) if with_stop else None
         self.peak_pred = z(torch.float32, T, N) if with_stop else None
@@ -46,6 +48,7 @@ class PPOBuffer:
     # -- reference API ----------------------------------------------------------------------
     def clear(self) -> None:
         self.filled = 0
+        self.flag_code_valid = False
 
     def store(self, state, action, reward, value, log_prob, done) -> None:
         """Appends one lockstep row (each argument ``[N]``-shaped, ``state`` ``[N,6]``)."""
@@ -86,4 +89,4 @@ class PPOBuffer:
                                    p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
                                    p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
                                    p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist),
-                                   p(self.pos_out), p(self.src_out))
+                                   p(self.pos_out), p(self.src_out), p(self.flag_code))

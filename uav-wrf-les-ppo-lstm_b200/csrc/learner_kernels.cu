@@ -146,8 +146,107 @@ __global__ void permutation_kernel(long long total, unsigned long long seed, int
 // ---- K8: curriculum over the finished episodes of a [T][N] segment, canonical order ----------
 constexpr int kCurMaxBlocks = 8192;
 
-__global__ void __launch_bounds__(1024) curriculum_kernel(const float* __restrict__ dones,
-                                                          const uint8_t* __restrict__ reached, long long total,
+// PPOTrainer.update (model.py:188-221) for the `total_eps` episodes of a segment whose successes have been binned
+// per curriculum window (blk_succ[b] = successes among episodes [b*window, (b+1)*window) counted from the start
+// of the carried partial window).  One thread.
+__device__ void curriculum_apply(const int* blk_succ, bool overflow, long long total_eps, double* state,
+                                 double* curriculum, double initial_radius, double min_radius, double radius_decay,
+                                 double thr, int window, double decay_factor) {
+    if (overflow) {
+        state[4] = -1.0;   // host raises
+        return;
+    }
+    const long long hist_len = (long long)state[4];
+    double radius = state[0], eb = state[1];
+    double env_radius = state[2], env_eb = state[3];
+    long long succ_total = 0;
+    const long long n_done = hist_len + total_eps;
+    const long long full = n_done / window;
+    for (long long b = 0; b <= full && b < kCurMaxBlocks; ++b) {
+        long long s = blk_succ[b];
+        succ_total += s;
+        if (b == 0) s += (long long)state[5];
+        if (b < full) {
+            // the env sees the trainer's values from before this update (model.py:189-190)
+            env_radius = radius;
+            env_eb = eb;
+            const double rate = (double)s / (double)window;
+            eb *= pow(decay_factor, 1.0 + rate);                         // :197-199
+            eb = eb > 0.1 ? eb : 0.1;                                    // :201
+            if (rate > thr) {                                            // :205-209
+                const double r2 = radius * pow(radius_decay, 2.0 + 3.0 * (rate - thr));
+                radius = r2 > min_radius ? r2 : min_radius;
+            } else if (rate < 0.25) {                                    // :210-214
+                const double r2 = radius * 1.1;
+                radius = r2 < initial_radius ? r2 : initial_radius;
+            }
+            if (fabs(radius - env_radius) > 5.0)                         // :217-218
+                radius = env_radius + 5.0 * ((radius > env_radius) - (radius < env_radius));
+        } else {
+            state[5] = (double)s;                                        // partial window carried over
+        }
+    }
+    (void)env_eb;
+    state[0] = radius;
+    state[1] = eb;
+    state[2] = radius;      // envs latch the trainer's current values at their next reset
+    state[3] = eb;
+    state[4] = (double)(n_done % window);
+    state[6] += (double)total_eps;
+    state[7] += (double)succ_total;
+    curriculum[0] = radius;
+    curriculum[1] = eb;
+}
+
+// Where the (done, reached) flags of canonical position p come from: per-warp cursors that walk 32 positions
+// at a time (seek once per warp, no per-element division).
+struct FlagsSeparate {            // float dones + uint8 reached, one rank: position = index
+    const float* dones;
+    const uint8_t* reached;
+    long long pos;
+    __device__ __forceinline__ void seek(long long p) { pos = p; }
+    __device__ __forceinline__ unsigned get(int lane) const {
+        const unsigned d = dones[pos + lane] != 0.0f;
+        return d ? (d | ((reached[pos + lane] != 0) << 1)) : 0u;
+    }
+    __device__ __forceinline__ void next() { pos += 32; }
+};
+struct FlagsPacked {              // uint8 code (bit 0 done, bit 1 reached) laid out [world][T][N]; canonical
+    const uint8_t* code;          // order = step-major, then GLOBAL env id = rank * N + local id
+    int T, N, world;
+    int t, r, n;                  // cursor: position of lane 0
+    __device__ __forceinline__ void seek(long long p) {
+        const long long row = (long long)world * N;
+        const long long tt = p / row, g = p - tt * row;
+        t = (int)tt;
+        r = (int)(g / N);
+        n = (int)(g - (long long)r * N);
+    }
+    __device__ __forceinline__ unsigned get(int lane) const {
+        int tt = t, rr = r, nn = n + lane;
+        while (nn >= N) {          // at most once when N >= 32 (never when N % 32 == 0)
+            nn -= N;
+            if (++rr == world) {
+                rr = 0;
+                ++tt;
+            }
+        }
+        return code[((size_t)rr * T + tt) * N + nn];
+    }
+    __device__ __forceinline__ void next() {
+        n += 32;
+        while (n >= N) {
+            n -= N;
+            if (++r == world) {
+                r = 0;
+                ++t;
+            }
+        }
+    }
+};
+
+template <typename Flags>
+__global__ void __launch_bounds__(1024) curriculum_kernel(Flags flags, long long total,
                                                           double* state, double* curriculum, double initial_radius,
                                                           double min_radius, double radius_decay, double thr,
                                                           int window, double decay_factor) {
@@ -161,10 +260,12 @@ __global__ void __launch_bounds__(1024) curriculum_kernel(const float* __restric
     const long long chunk = (((total + 31) / 32) + 31) / 32 * 32;     // multiple of 32 flags per warp
     const long long lo = chunk * warp, hi = (lo + chunk < total) ? lo + chunk : total;
     int eps = 0;
+    if (lo < hi) flags.seek(lo);
 #pragma unroll 4
     for (long long i = lo; i < hi; i += 32) {
-        const bool d = (i + lane < hi) && dones[i + lane] != 0.0f;
+        const bool d = (i + lane < hi) && (flags.get(lane) & 1u);
         eps += __popc(__ballot_sync(0xffffffffu, d));
+        flags.next();
     }
     if (lane == 0) ep_cnt[warp] = eps;
     for (int i = tid; i < kCurMaxBlocks; i += blockDim.x) blk_succ[i] = 0;
@@ -173,63 +274,135 @@ __global__ void __launch_bounds__(1024) curriculum_kernel(const float* __restric
     long long ord = hist_len;                                          // ordinal of this warp's first episode
     for (int w = 0; w < warp; ++w) ord += ep_cnt[w];
     bool overflow = false;
+    if (lo < hi) flags.seek(lo);
     for (long long i = lo; i < hi; i += 32) {
-        const bool d = (i + lane < hi) && dones[i + lane] != 0.0f;
+        const unsigned f = (i + lane < hi) ? flags.get(lane) : 0u;
+        const bool d = f & 1u;
         const unsigned mask = __ballot_sync(0xffffffffu, d);
         if (d) {
             const long long b = (ord + __popc(mask & ((1u << lane) - 1u))) / window;
             if (b >= kCurMaxBlocks) overflow = true;
-            else if (reached[i + lane]) atomicAdd(&blk_succ[(int)b], 1);
+            else if (f & 2u) atomicAdd(&blk_succ[(int)b], 1);
         }
         ord += __popc(mask);
+        flags.next();
     }
     if (overflow) atomicOr(&overflow_any, 1);
     __syncthreads();
-    if (tid == (int)blockDim.x - 1) {
-        if (overflow_any) {
-            state[4] = -1.0;   // host raises
-            return;
+    if (tid == (int)blockDim.x - 1)
+        curriculum_apply(blk_succ, overflow_any != 0, ord - hist_len, state, curriculum, initial_radius, min_radius,
+                         radius_decay, thr, window, decay_factor);
+}
+
+
+// ---- K8, scalable form for the packed [world][T][N] flags (N % 512 == 0): four small kernels ---------------
+// count (many warps, 16 flags per lane and load) -> exclusive scan over the chunks (one CTA) -> bin the
+// successes per curriculum window (many warps, global atomics on the few done&reached flags) -> apply the
+// rule (one thread).  Independent of the world size up to the all-gather itself.
+constexpr int kCurChunk = 2048;                 // canonical positions per warp (4 loads of 512)
+constexpr int kCurMaxChunks = 1 << 16;
+
+__device__ __forceinline__ const uint4* packed_chunk_ptr(const uint8_t* code, int T, int N, int world, long long p) {
+    const long long row = (long long)world * N;
+    const long long t = p / row, g = p - t * row;
+    const long long r = g / N, n = g - r * N;
+    return reinterpret_cast<const uint4*>(code + ((size_t)r * T + t) * N + n);
+}
+__device__ __forceinline__ int count_done16(const uint4 v) {
+    return __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+           __popc(v.w & 0x01010101u);
+}
+
+__global__ void __launch_bounds__(256) cur_count_kernel(const uint8_t* __restrict__ code, int T, int N, int world,
+                                                        long long total, int* __restrict__ chunk_cnt, int n_chunks) {
+    const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < kCurChunk / 512; ++q) {
+        const long long p = (long long)chunk * kCurChunk + q * 512;
+        if (p < total) c += count_done16(__ldg(packed_chunk_ptr(code, T, N, world, p) + lane));
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) chunk_cnt[chunk] = c;
+}
+
+__global__ void __launch_bounds__(1024) cur_scan_kernel(int* __restrict__ chunk_cnt, int n_chunks, int* __restrict__ bins,
+                                                        int* __restrict__ total_out) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (n_chunks + 1023) / 1024;
+    int s = 0;
+    for (int i = tid * per; i < (tid + 1) * per && i < n_chunks; ++i) s += chunk_cnt[i];
+    part[tid] = s;
+    for (int i = tid; i < kCurMaxBlocks; i += 1024) bins[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const int c = part[i];
+            part[i] = run;
+            run += c;
         }
-        const long long total_eps = ord - hist_len;      // last thread's ordinal = all episodes
-        double radius = state[0], eb = state[1];
-        double env_radius = state[2], env_eb = state[3];
-        long long succ_total = 0;
-        const long long n_done = hist_len + total_eps;
-        const long long full = n_done / window;
-        for (long long b = 0; b <= full && b < kCurMaxBlocks; ++b) {
-            long long s = blk_succ[b];
-            succ_total += s;
-            if (b == 0) s += (long long)state[5];
-            if (b < full) {
-                // the env sees the trainer's values from before this update (model.py:189-190)
-                env_radius = radius;
-                env_eb = eb;
-                const double rate = (double)s / (double)window;
-                eb *= pow(decay_factor, 1.0 + rate);                         // :197-199
-                eb = eb > 0.1 ? eb : 0.1;                                    // :201
-                if (rate > thr) {                                            // :205-209
-                    const double r2 = radius * pow(radius_decay, 2.0 + 3.0 * (rate - thr));
-                    radius = r2 > min_radius ? r2 : min_radius;
-                } else if (rate < 0.25) {                                    // :210-214
-                    const double r2 = radius * 1.1;
-                    radius = r2 < initial_radius ? r2 : initial_radius;
+        total_out[0] = run;
+        total_out[1] = 0;        // overflow flag
+    }
+    __syncthreads();
+    int run = part[tid];
+    for (int i = tid * per; i < (tid + 1) * per && i < n_chunks; ++i) {
+        const int c = chunk_cnt[i];
+        chunk_cnt[i] = run;      // exclusive prefix
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) cur_bin_kernel(const uint8_t* __restrict__ code, int T, int N, int world,
+                                                      long long total, const int* __restrict__ chunk_base, int n_chunks,
+                                                      const double* __restrict__ state, int window,
+                                                      int* __restrict__ bins, int* __restrict__ total_out) {
+    const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    long long ord = (long long)state[4] + chunk_base[chunk];     // ordinal of the chunk's first episode
+    for (int q = 0; q < kCurChunk / 512; ++q) {
+        const long long p = (long long)chunk * kCurChunk + q * 512;
+        if (p >= total) break;
+        const uint4 v = __ldg(packed_chunk_ptr(code, T, N, world, p) + lane);
+        const int c = count_done16(v);
+        int incl = c;                                            // inclusive warp scan of the per-lane counts
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (c) {
+            long long mine = ord + incl - c;
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned f = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                if (f & 1u) {
+                    const long long b = mine / window;
+                    if (b >= kCurMaxBlocks) atomicExch(total_out + 1, 1);
+                    else if (f & 2u) atomicAdd(bins + (int)b, 1);
+                    ++mine;
                 }
-                if (fabs(radius - env_radius) > 5.0)                         // :217-218
-                    radius = env_radius + 5.0 * ((radius > env_radius) - (radius < env_radius));
-            } else {
-                state[5] = (double)s;                                        // partial window carried over
             }
         }
-        state[0] = radius;
-        state[1] = eb;
-        state[2] = radius;      // envs latch the trainer's current values at their next reset
-        state[3] = eb;
-        state[4] = (double)(n_done % window);
-        state[6] += (double)total_eps;
-        state[7] += (double)succ_total;
-        curriculum[0] = radius;
-        curriculum[1] = eb;
+        ord += __shfl_sync(0xffffffffu, incl, 31);
     }
+}
+
+__global__ void cur_apply_kernel(const int* bins, const int* total_in, double* state, double* curriculum,
+                                 double initial_radius, double min_radius, double radius_decay, double thr, int window,
+                                 double decay_factor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        curriculum_apply(bins, total_in[1] != 0, (long long)total_in[0], state, curriculum, initial_radius, min_radius,
+                         radius_decay, thr, window, decay_factor);
+}
+
+static int* curriculum_scratch() {       // chunk counts + window bins + {total, overflow}; stream-ordered reuse
+    static int* buf = nullptr;
+    if (!buf && cudaMalloc(&buf, (kCurMaxChunks + kCurMaxBlocks + 8) * sizeof(int)) != cudaSuccess) buf = nullptr;
+    return buf;
 }
 
 }  // namespace plume
@@ -309,9 +482,41 @@ extern "C" int plume_curriculum_update(const float* dones, const uint8_t* reache
     PLUME_CHECK_ARG(dones && reached && state && curriculum, "null pointer");
     PLUME_CHECK_ARG(window > 0, "window must be positive");
     if (horizon <= 0 || n_envs <= 0) return 0;
-    curriculum_kernel<<<1, 1024, 0, as_stream(stream)>>>(dones, reached, (long long)horizon * n_envs, state,
-                                                         curriculum, initial_radius, min_radius, radius_decay,
+    curriculum_kernel<<<1, 1024, 0, as_stream(stream)>>>(FlagsSeparate{dones, reached, 0}, (long long)horizon * n_envs,
+                                                         state, curriculum, initial_radius, min_radius, radius_decay,
                                                          success_threshold, window, decay_factor);
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plume_curriculum_update_packed(const uint8_t* flag_code, int32_t horizon, int32_t n_envs, int32_t world,
+                                              double* state, double* curriculum, double initial_radius,
+                                              double min_radius, double radius_decay, double success_threshold,
+                                              int32_t window, double decay_factor, void* stream) {
+    PLUME_CHECK_ARG(flag_code && state && curriculum, "null pointer");
+    PLUME_CHECK_ARG(window > 0 && world >= 1, "window and world must be positive");
+    if (horizon <= 0 || n_envs <= 0) return 0;
+    const long long total = (long long)horizon * n_envs * world;
+    const long long n_chunks = (total + kCurChunk - 1) / kCurChunk;
+    if (n_envs % 512 == 0 && n_chunks <= kCurMaxChunks && (reinterpret_cast<uintptr_t>(flag_code) & 15) == 0) {
+        int* scratch = curriculum_scratch();
+        if (!scratch) return fail("plume_curriculum_update_packed: cannot allocate scratch");
+        int *chunk_cnt = scratch, *bins = scratch + kCurMaxChunks, *tot = bins + kCurMaxBlocks;
+        cudaStream_t s = as_stream(stream);
+        const int blocks = (int)((n_chunks * 32 + 255) / 256);
+        cur_count_kernel<<<blocks, 256, 0, s>>>(flag_code, horizon, n_envs, world, total, chunk_cnt, (int)n_chunks);
+        cur_scan_kernel<<<1, 1024, 0, s>>>(chunk_cnt, (int)n_chunks, bins, tot);
+        cur_bin_kernel<<<blocks, 256, 0, s>>>(flag_code, horizon, n_envs, world, total, chunk_cnt, (int)n_chunks, state,
+                                              window, bins, tot);
+        cur_apply_kernel<<<1, 32, 0, s>>>(bins, tot, state, curriculum, initial_radius, min_radius, radius_decay,
+                                          success_threshold, window, decay_factor);
+        PLUME_LAUNCH_CHECK();
+        return 0;
+    }
+    curriculum_kernel<<<1, 1024, 0, as_stream(stream)>>>(FlagsPacked{flag_code, horizon, n_envs, world, 0, 0, 0},
+                                                         (long long)horizon * n_envs * world, state, curriculum,
+                                                         initial_radius, min_radius, radius_decay, success_threshold,
+                                                         window, decay_factor);
     PLUME_LAUNCH_CHECK();
     return 0;
 }

@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 a.buf.log_probs[i] = logp;
                 a.buf.dones[i] = done ? 1.0f : 0.0f;
                 a.buf.reached[i] = r.reached ? 1 : 0;
+                if (a.buf.flag_code) a.buf.flag_code[i] = (uint8_t)((done ? 1 : 0) | (r.reached ? 2 : 0));
                 if (!defer) {
                     if (a.buf.stop_prob) a.buf.stop_prob[i] = stop_p;
                     if (a.buf.stop_flag) a.buf.stop_flag[i] = stop ? 1 : 0;

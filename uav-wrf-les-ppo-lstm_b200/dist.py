@@ -80,3 +80,59 @@ def gather_episode_flags(dones: torch.Tensor, reached: torch.Tensor, process_gro
     dist.all_gather(list(r_all.unbind(0)), reached.contiguous(), group=process_group)
     return (d_all.permute(1, 0, 2).reshape(T, world * N).contiguous(),
             r_all.permute(1, 0, 2).reshape(T, world * N).contiguous())
+
+
+def gather_flag_codes(code: torch.Tensor, process_group=None) -> torch.Tensor:
+    """``code`` uint8 [T, N] (bit 0 done, bit 1 reached) of this rank -> [world, T, N] of all ranks (1 byte per
+    transition over the wire; the curriculum kernel indexes this layout directly)."""
+    if process_group is None:
+        return code.unsqueeze(0)
+    world = dist.get_world_size(process_group)
+    out = torch.empty((world,) + tuple(code.shape), dtype=code.dtype, device=code.device)
+    if code.is_cuda:
+        dist.all_gather_into_tensor(out, code.contiguous(), group=process_group)
+    else:
+        dist.all_gather(list(out.unbind(0)), code.contiguous(), group=process_group)
+    return out
+
+
+class PeerComm:
+    """The update's exchange step without NCCL: every rank's gradient buffer is mapped into every peer (CUDA
+    IPC over NVLink) and ``plume_allreduce_clip_adam`` does all-reduce + clip + Adam in one kernel
+    (csrc/comm_kernels.cu).  The 64-byte IPC handles travel through one ``all_gather_object`` at start-up."""
+
+    def __init__(self, process_group, n_params: int, device):
+        import ctypes as C
+
+        from . import _lib
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.device = torch.device(device)
+        self._h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.plume_comm_create(self.world, self.rank, int(n_params), C.byref(self._h), handle),
+                       "plume_comm_create")
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(handle), group=process_group)
+            blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(gathered))
+            _lib.check(self.lib.plume_comm_connect(self._h, blob), "plume_comm_connect")
+        dist.barrier(group=process_group)
+
+    def check(self) -> None:
+        import ctypes as C
+
+        from . import _lib
+        err = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.plume_comm_error(self._h, C.byref(err),
+                                                 torch.cuda.current_stream(self.device).cuda_stream), "plume_comm_error")
+        if err.value:
+            raise RuntimeError({1: "peer-memory all-reduce: a rank did not publish its gradient in time",
+                                2: "peer-memory all-reduce: grid barrier timed out"}.get(err.value, "comm error"))
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.plume_comm_destroy(self._h)
+            self._h = None

@@ -35,6 +35,12 @@ class FusedAdam:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=model.flat.device)
         self.step_count = 0
         self.launches = 0
+        self.comm = None          # dist.PeerComm: all-reduce fused into the step (multi-GPU)
+
+    def attach_comm(self, comm) -> None:
+        """With a ``dist.PeerComm`` attached, ``step()`` = gradient all-reduce over NVLink peer memory + clip +
+        Adam in ONE kernel; callers must then not all-reduce ``flat_grad`` themselves."""
+        self.comm = comm
 
     def zero_grad(self) -> None:
         self.model.flat_grad.zero_()
@@ -44,10 +50,17 @@ class FusedAdam:
         self.step_count += 1
         lib = _lib.load()
         with torch.cuda.device(m.flat.device):
-            rc = lib.plume_clip_adam(m.flat.data_ptr(), m.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
-                                     self.exp_avg_sq.data_ptr(), _lib.MLP_PARAMS, self.max_grad_norm, self.lr,
-                                     self.betas[0], self.betas[1], self.eps, self.step_count,
-                                     self.grad_norm.data_ptr(), _stream(m.flat.device))
+            if self.comm is not None:
+                rc = lib.plume_allreduce_clip_adam(self.comm._h, m.flat.data_ptr(), m.flat_grad.data_ptr(),
+                                                   self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                                   _lib.MLP_PARAMS, self.max_grad_norm, self.lr, self.betas[0],
+                                                   self.betas[1], self.eps, self.step_count,
+                                                   self.grad_norm.data_ptr(), _stream(m.flat.device))
+            else:
+                rc = lib.plume_clip_adam(m.flat.data_ptr(), m.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                         self.exp_avg_sq.data_ptr(), _lib.MLP_PARAMS, self.max_grad_norm, self.lr,
+                                         self.betas[0], self.betas[1], self.eps, self.step_count,
+                                         self.grad_norm.data_ptr(), _stream(m.flat.device))
         _lib.check(rc, "plume_clip_adam")
         self.launches += 1
 
@@ -137,7 +150,8 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
                                         workspace.nan_flag.data_ptr(), workspace.ws.data_ptr(), workspace.bytes,
                                         _stream(dev))
                 _lib.check(rc, "plume_ppo_grad")
-                pdist.allreduce_gradient(model.flat_grad, process_group)
+                if getattr(optimizer, "comm", None) is None:
+                    pdist.allreduce_gradient(model.flat_grad, process_group)      # NCCL; else fused into step()
                 optimizer.step()
                 if record is not None:
                     record.append(optimizer.grad_norm.clone())
@@ -200,12 +214,17 @@ class PPOTrainer:
         lib = _lib.load()
         c, st = self.cfg, self.device_state()
         T = buffer.filled
-        dones, reached = pdist.gather_episode_flags(buffer.dones[:T], buffer.reached[:T], process_group)
+        if getattr(buffer, "flag_code_valid", False):
+            code = buffer.flag_code[:T]
+        else:      # rows appended with store(): derive the packed flags
+            code = (buffer.dones[:T] != 0).to(torch.uint8) | (buffer.reached[:T] != 0).to(torch.uint8) * 2
+        codes = pdist.gather_flag_codes(code.contiguous(), process_group)       # [world, T, N]
         with torch.cuda.device(self.env.device):
-            rc = lib.plume_curriculum_update(dones.data_ptr(), reached.data_ptr(), T,
-                                             dones.shape[1], st.data_ptr(), self.env.curriculum.data_ptr(),
-                                             c.initial_radius, c.min_radius, c.radius_decay, c.success_threshold,
-                                             c.window_size, c.decay_factor, _stream(self.env.device))
+            rc = lib.plume_curriculum_update_packed(codes.data_ptr(), T, buffer.num_envs, codes.shape[0],
+                                                    st.data_ptr(), self.env.curriculum.data_ptr(),
+                                                    c.initial_radius, c.min_radius, c.radius_decay,
+                                                    c.success_threshold, c.window_size, c.decay_factor,
+                                                    _stream(self.env.device))
         _lib.check(rc, "plume_curriculum_update")
 
     def sync_from_device(self) -> dict:

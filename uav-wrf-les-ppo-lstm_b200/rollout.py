@@ -85,6 +85,7 @@ class RolloutEngine:
                 self.conc_window, self._window_next = self._window_next, self.conc_window
                 self.launches += 1
         self.buffer.filled = T
+        self.buffer.flag_code_valid = True
         return self.buffer
 
     def check_nan(self) -> None:

@@ -6,6 +6,8 @@ One ``train_iteration()`` = one fused rollout segment of ``horizon`` lockstep st
 ``epochs x minibatches`` optimiser steps.  Nothing returns to the host inside an iteration."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -34,6 +36,13 @@ class PlumeTrainer:
         self.engine = RolloutEngine(self.env, self.model, self.head, horizon=horizon, with_info=with_info,
                                     with_trend=with_trend and stop_head)
         self.optimizer = FusedAdam(self.model, lr=self.cfg.learning_rate, max_grad_norm=self.cfg.max_grad_norm)
+        # multi-GPU: gradient all-reduce fused with clip + Adam over NVLink peer memory (PLUME_COMM=nccl keeps
+        # the torch.distributed all-reduce)
+        self.comm = None
+        if process_group is not None and world_size > 1 and os.environ.get("PLUME_COMM", "peer") != "nccl":
+            from .dist import PeerComm
+            self.comm = PeerComm(process_group, _lib.MLP_PARAMS, self.device)
+            self.optimizer.attach_comm(self.comm)
         self.curriculum = PPOTrainer(self.env, self.model, self.optimizer, cfg=self.cfg)
         self.minibatch_size = int(minibatch_size or (num_envs * horizon) // 4)
         self.workspace = UpdateWorkspace(self.device, min(self.minibatch_size, num_envs * horizon))

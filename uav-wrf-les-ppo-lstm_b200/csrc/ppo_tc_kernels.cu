@@ -48,7 +48,8 @@ struct TcSmem {
     static constexpr int x = bh + 8;                                 // [128][8] x0..x5, rstd1, 0
     static constexpr int dout = x + kTcTile * 8;                     // [128][8] d loss / d (logits, value)
     static constexpr int sc = dout + kTcTile * 8;                    // [128][4] rstd2, m1, m2, 0
-    static constexpr int total = sc + kTcTile * 4;
+    static constexpr int pf = sc + kTcTile * 4;                      // [128][12] next tile's gathered sample
+    static constexpr int total = pf + kTcTile * 12;
     // [groups][128][8] exchange of partial sums between the column groups of one sample row: aliases the last
     // operand buffer of the ring, which is idle whenever it is used (no MMA in flight, no production running)
     static constexpr int exch = ring + 7 * kChunkFloats;
@@ -66,6 +67,9 @@ constexpr int kW2SplitFloats = 131072;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // barrier of the 256 compute threads (the issuer warp never takes part)
@@ -128,6 +132,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     if (tid < 4) cta_loss[tid] = 0.0;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
     float* const exch = sm + TcSmem::exch;
+    // exchange slot k of column group g, row r: slot-major, so that the 32 rows of a warp hit 32 banks
+    auto EX = [&](int k, int g, int r) -> float& { return exch[(k * G + g) * kTcTile + r]; };
     if (tid < 7) {          // column means of feature.0.weight (k < 6) and the mean of feature.0.bias
         float m = 0.0f;
         for (int o = 0; o < 256; ++o) m += (tid < 6) ? params[PLUME_OFF_W1 + o * 6 + tid] : params[PLUME_OFF_B1 + o];
@@ -248,30 +254,53 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
         for (int c = 0; c < 8; ++c) Pacc[h][c] = 0.0f;
 
+    float* const pf = sm + TcSmem::pf;
+    // gather of one tile's samples into pf with 4-byte cp.async (sample threads; rows beyond the minibatch = 0);
+    // issued after the tile's last publish(), waited for at the next tile's Ph0
+    auto prefetch_tile = [&](long long tl) {
+        if (tid >= kTcTile || tl >= tiles) return;
+        const long long b0 = tl * kTcTile;
+        float* dst = pf + tid * 12;
+        if (b0 + tid < a.mb_size) {
+            const long long pos = a.mb_start + b0 + tid;
+            const long long idx = a.perm ? a.perm[pos]
+                                         : (long long)feistel_permute((uint64_t)pos, (uint64_t)a.batch.total,
+                                                                      a.perm_seed, (uint32_t)a.epoch);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cp_async4(dst + k, a.batch.obs + idx * 6 + k);
+            cp_async4(dst + 6, a.batch.advantages + idx);
+            cp_async4(dst + 7, a.batch.returns + idx);
+            cp_async4(dst + 8, a.batch.old_values + idx);
+            cp_async4(dst + 9, a.batch.old_log_probs + idx);
+            cp_async4(dst + 10, a.batch.actions + idx);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) dst[k] = 0.0f;
+        }
+    };
+
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long base = tile * kTcTile;
         const int n_valid = (int)((a.mb_size - base) < kTcTile ? (a.mb_size - base) : kTcTile);
 
-        // ---- Ph0: gather (sample thread tid < 128 keeps the scalars of its sample in registers) --------
+        // ---- Ph0: this tile's samples: gathered by cp.async during the previous tile (first tile: now) --------
+        // pf[s] = {obs 0..5, adv, ret, old value, old logp, action (int bits), 0}
+        if (tile == (long long)blockIdx.x) prefetch_tile(tile);
+        cp_async_wait_all();
+        compute_sync();
         float r_adv = 0.0f, r_ret = 0.0f, r_vold = 0.0f, r_lpold = 0.0f;
         int r_act = 0;
         if (tid < kTcTile) {
-            float xv[6] = {0, 0, 0, 0, 0, 0};
-            if (tid < n_valid) {
-                const long long pos = a.mb_start + base + tid;
-                const long long idx = a.perm ? a.perm[pos]
-                                             : (long long)feistel_permute((uint64_t)pos, (uint64_t)a.batch.total,
-                                                                          a.perm_seed, (uint32_t)a.epoch);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) xv[k] = a.batch.obs[idx * 6 + k];
-                r_adv = a.batch.advantages[idx];
-                r_ret = a.batch.returns[idx];
-                r_vold = a.batch.old_values[idx];
-                r_lpold = a.batch.old_log_probs[idx];
-                r_act = a.batch.actions[idx];
-            }
-            *reinterpret_cast<float4*>(xt + tid * 8) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-            *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(xv[4], xv[5], 0.0f, 0.0f);
+            const float4 q0 = *reinterpret_cast<const float4*>(pf + tid * 12);
+            const float4 q1 = *reinterpret_cast<const float4*>(pf + tid * 12 + 4);
+            const float4 q2 = *reinterpret_cast<const float4*>(pf + tid * 12 + 8);
+            r_adv = q1.z;
+            r_ret = q1.w;
+            r_vold = q2.x;
+            r_lpold = q2.y;
+            r_act = __float_as_int(q2.z);
+            *reinterpret_cast<float4*>(xt + tid * 8) = q0;
+            *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(q1.x, q1.y, 0.0f, 0.0f);
         }
         compute_sync();
 
@@ -299,13 +328,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 sq = fmaf(z.z, z.z, sq);
                 sq = fmaf(z.w, z.w, sq);
             }
-            exch[(ug * kTcTile + r128) * 8] = sq;
+            EX(0, ug, r128) = sq;
         }
         compute_sync();
         if (tid < kTcTile) {
             float var = 0.0f;
 #pragma unroll
-            for (int g = 0; g < G; ++g) var += exch[(g * kTcTile + tid) * 8];
+            for (int g = 0; g < G; ++g) var += EX(0, g, tid);
             xt[tid * 8 + 6] = 1.0f / sqrtf(var * (1.0f / 256.0f) + kLnEps);
         }
         compute_sync();
@@ -369,12 +398,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 v[j] += P2[c0 + j];
                 sum += v[j];
             }
-            float* mine = exch + (cg * kTcTile + srow) * 8;
-            mine[6] = sum;
+            EX(6, cg, srow) = sum;
             compute_sync();
             float tot = 0.0f;
 #pragma unroll
-            for (int g = 0; g < G; ++g) tot += exch[(g * kTcTile + srow) * 8 + 6];
+            for (int g = 0; g < G; ++g) tot += EX(6, g, srow);
             const float mean = tot * (1.0f / 128.0f);
             float sq = 0.0f;
 #pragma unroll
@@ -382,11 +410,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const float d = v[j] - mean;
                 sq = fmaf(d, d, sq);
             }
-            mine[7] = sq;
+            EX(7, cg, srow) = sq;
             compute_sync();
             tot = 0.0f;
 #pragma unroll
-            for (int g = 0; g < G; ++g) tot += exch[(g * kTcTile + srow) * 8 + 7];
+            for (int g = 0; g < G; ++g) tot += EX(7, g, srow);
             const float rstd2 = 1.0f / sqrtf(tot * (1.0f / 128.0f) + kLnEps);
             float head[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -409,7 +437,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 *reinterpret_cast<float4*>(xh + srow * kXhStride + c0 + 4 * q) =
                     make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) mine[k] = head[k];
+            for (int k = 0; k < 6; ++k) EX(k, cg, srow) = head[k];
             compute_sync();
             if (cg == 0) {          // srow == tid: the thread that gathered this sample
                 float dl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -420,7 +448,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     for (int k = 0; k < 6; ++k) {
                         float t = sm[TcSmem::bh + k];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) t += exch[(g * kTcTile + srow) * 8 + k];
+                        for (int g = 0; g < G; ++g) t += EX(k, g, srow);
                         o6[k] = t;
                     }
                     const SampleLoss L = ppo_sample_loss(o6, r_act, r_adv, r_ret, r_vold, r_lpold, a.clip_eps,
@@ -481,15 +509,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 m1p += dxh;
                 m2p = fmaf(dxh, v[j], m2p);
             }
-            mine[6] = m1p;
-            mine[7] = m2p;
+            EX(6, cg, srow) = m1p;
+            EX(7, cg, srow) = m2p;
             compute_sync();
             if (cg == 0) {
                 float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    t1 += exch[(g * kTcTile + srow) * 8 + 6];
-                    t2 += exch[(g * kTcTile + srow) * 8 + 7];
+                    t1 += EX(6, g, srow);
+                    t2 += EX(7, g, srow);
                 }
                 *reinterpret_cast<float4*>(sm + TcSmem::sc + srow * 4) =
                     make_float4(rstd2, t1 * (1.0f / 128.0f), t2 * (1.0f / 128.0f), 0.0f);
@@ -610,6 +638,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
             compute_sync();        // every thread has read dz2 for its last G3 chunk: the region becomes staging
+            prefetch_tile(tile + gridDim.x);      // the next tile's gather rides under this CUDA-core phase
             tc::tc_fence_after();
             float m1p = 0.0f, m2p = 0.0f;
             // this thread's sample: inputs + rstd1
@@ -670,16 +699,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 compute_sync();
             }
             wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
-            float* mine = exch + (cg * kTcTile + srow) * 8;
-            mine[6] = m1p;
-            mine[7] = m2p;
+            EX(6, cg, srow) = m1p;
+            EX(7, cg, srow) = m2p;
             compute_sync();
             if (cg == 0) {          // per-sample scalar sums of the layer-1 backward -> per-CTA accumulators
                 float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    t1 += exch[(g * kTcTile + srow) * 8 + 6];
-                    t2 += exch[(g * kTcTile + srow) * 8 + 7];
+                    t1 += EX(6, g, srow);
+                    t2 += EX(7, g, srow);
                 }
                 const float m1 = t1 * (1.0f / 256.0f), m2 = t2 * (1.0f / 256.0f);
                 const float rs = sx1.z;

@@ -141,6 +141,19 @@ struct FieldF32Cfg {
     float peak, ti, exp_scale;     // exp_scale = -log2(e) / (2 sigma^2)
 };
 
+// float copies of 0.3*sin(0.05 x) and cos(0.07 y) (double -> float conversions run on the XU pipe, which this
+// kernel saturates together with the MUFU ops: ncu/SASS r1: 32 XU-pipe instructions per 4 cells)
+__device__ float g_wave_sin_f32[512];
+__device__ float g_wave_cos_f32[512];
+
+__global__ void wave_tables_f32_kernel(const double* __restrict__ sin_tab, const double* __restrict__ cos_tab, int G) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G) {
+        g_wave_sin_f32[i] = 0.3f * (float)sin_tab[i];
+        g_wave_cos_f32[i] = (float)cos_tab[i];
+    }
+}
+
 __global__ void __launch_bounds__(128) generate_fields_f32_kernel(Cfg c, FieldF32Cfg fc, plume_env_state st,
                                                                   const int32_t* env_list) {
     const int x = blockIdx.x, li = blockIdx.y;
@@ -161,15 +174,18 @@ __global__ void __launch_bounds__(128) generate_fields_f32_kernel(Cfg c, FieldF3
 
     const float ddx = (float)x - sx;
     const float ddx2 = ddx * ddx;
-    const float s3 = 0.3f * (float)st.sin_tab[x];
-    const double2 c01 = *reinterpret_cast<const double2*>(st.cos_tab + y0);
-    const double2 c23 = *reinterpret_cast<const double2*>(st.cos_tab + y0 + 2);
-    const float cosy[4] = {(float)c01.x, (float)c01.y, (float)c23.x, (float)c23.y};
+    const float s3 = g_wave_sin_f32[x];
+    const float4 cosy4 = *reinterpret_cast<const float4*>(g_wave_cos_f32 + y0);
+    const float cosy[4] = {cosy4.x, cosy4.y, cosy4.z, cosy4.w};
+    const float fy0 = (float)y0 - sy;                 // one conversion, the other three by addition
     float conc[4], tke[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float ddy = (float)(y0 + k) - sy;
-        const float base = fc.peak * exp2f_approx(fmaf(ddy, ddy, ddx2) * fc.exp_scale);
+        const float ddy = fy0 + (float)k;
+        const float arg = fmaf(ddy, ddy, ddx2) * fc.exp_scale;
+        // far from the source the Gaussian underflows: skip the ex2 (warps are 128 consecutive cells of one
+        // row, so the branch is uniform for most of the field)
+        const float base = (arg > -126.0f) ? fc.peak * exp2f_approx(arg) : 0.0f;
         tke[k] = fc.ti * (fmaf(0.2f, u[k], fmaf(s3, cosy[k], fabsf(z[k]))));
         conc[k] = fminf(fmaxf(base + tke[k], 0.0f), fc.peak);
     }
@@ -377,6 +393,7 @@ extern "C" int plume_generate_fields(const plume_env_config* cfg, const plume_en
             fc.peak = (float)c.conc_peak;
             fc.ti = (float)c.ti;
             fc.exp_scale = (float)(-1.4426950408889634 / c.two_sigma_sq);
+            wave_tables_f32_kernel<<<(c.G + 255) / 256, 256, 0, s>>>(st->sin_tab, st->cos_tab, c.G);
             generate_fields_f32_kernel<<<dim3((unsigned)c.G, (unsigned)n_list), 128, 0, s>>>(c, fc, *st, env_list);
         } else {
             generate_fields_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(c, *st, env_list, bpe, z_out, u_out);

@@ -354,7 +354,7 @@ def run_cuda_arm(args) -> None:
     # costs three MMAs), so the ceiling this kernel can reach is peak/6 -- reported next to it.
     roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peak_tf,
-                "traffic": 43.5e6 if dom.startswith("ppo_grad") else None,
+                "traffic": 43.75e6 if dom.startswith("ppo_grad") else None,   # profiles/r1e_ncu_summary.txt
                 "peak_source": f"{peaks['source']} bf16 dense (sustained), of measured",
                 "tf32x3_ceiling": peak_tf / 6.0, "frac_of_tf32x3_ceiling": kernels[dom]["tflops"] / (peak_tf / 6.0),
                 "note": "tcgen05.mma kind::tf32 with the 3xTF32 split (fp32 rel 1e-5 parity bar), accumulators in "

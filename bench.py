@@ -198,15 +198,15 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
     del env
     torch.cuda.empty_cache()
     # K2: procedural, 102 B per env-step (csrc/env_kernels.cu header) + 20 B info
-    for n2 in (4096, 1 << 20):
-        env = pb.VecMethaneEnv(n2, device=dev, field_mode="procedural", auto_reset=True, seed=2)
+    for n2, fast in ((4096, False), (1 << 20, False), (1 << 20, True)):
+        env = pb.VecMethaneEnv(n2, device=dev, field_mode="procedural", auto_reset=True, seed=2, fast_reward=fast)
         acts = torch.randint(0, 5, (n2,), dtype=torch.int32, device=dev)
         for _ in range(3):
             env.step(acts)
         sync()
         ms = min(timed(lambda: env.step(acts), sync) for _ in range(10))
         b = n2 * 122
-        out[f"plume_step_{n2}"] = {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        out[f"plume_step_{n2}" + ("_fast_reward" if fast else "")] = {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                    "frac": b / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "envs": n2,
                                    "algorithmic_bytes": b, "env_steps_per_s": n2 / ms * 1e3,
                                    "peak_source": peaks["source"]}

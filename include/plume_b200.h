@@ -57,6 +57,11 @@ extern "C" {
                                        * features for the whole [T][N] segment afterwards.  Identical results;
                                        * not combinable with PLUME_FLAG_STOP_TERMINATES. */
 
+#define PLUME_FLAG_FAST_REWARD 16u   /* plume_env_step / plume_rollout: flags and indices (position, cells, visit
+                                     * counters, reached, done) stay the float64 arithmetic of environment.py, the
+                                     * concentration / tke observation entries and the reward terms are float32
+                                     * (fp32 rel 1e-5 bar instead of bit-exact float64 rewards) */
+
 /* Constants of one reference version (PPOV x/config.py; environment.py). HOST struct. */
 typedef struct plume_env_config {
     int32_t grid_size;            /* config.py:6 */

@@ -256,3 +256,40 @@ def test_readme_dispersion_model_vs_oracle():
                                 (wc, ws))
         assert np.allclose(conc[i], ref, rtol=1e-9, atol=1e-9)
         assert (ref > 50).sum() > 50 and (ref > 50).sum() < 20000      # a narrow plume, not a disc
+
+
+@pytest.mark.parametrize("version,mode", [("2.1", "procedural"), ("1.1", "procedural"), ("2.0", "f64")])
+def test_fast_reward_mode_keeps_flags_and_indices_exact(version, mode):
+    """PLUME_FLAG_FAST_REWARD: positions, cells, visit tables, reached/done flags are bit-identical to the exact
+    kernel (float64 arithmetic of environment.py:105-117,134-137,155-161); observations and rewards agree to the
+    north-star tolerance (fp32 rel 1e-5)."""
+    m = pb()
+    n, T = 256, 300
+    kw = dict(version=version, seed=13, field_mode=mode)
+    ex = m.VecMethaneEnv(n, **kw)
+    fa = m.VecMethaneEnv(n, fast_reward=True, **kw)
+    for env in (ex, fa):
+        env.current_radius = 30.0
+    rng = np.random.default_rng(1)
+    noise = torch.zeros(n, 2, dtype=torch.float64, device=ex.device)
+    done_seen = torch.zeros(n, dtype=torch.bool, device=ex.device)
+    worst = 0.0
+    for t in range(T):
+        src = ex.source_pos - ex.agent_pos.double()
+        greedy = torch.where(src[:, 0].abs() > src[:, 1].abs(), torch.where(src[:, 0] > 0, 3, 4),
+                             torch.where(src[:, 1] > 0, 1, 2))
+        rnd = torch.from_numpy(rng.integers(0, 5, n)).to(ex.device)
+        a = torch.where(torch.from_numpy(rng.random(n) < 0.4).to(ex.device), rnd, greedy).int()
+        o1, r1, d1, i1 = ex.step(a, noise_out=noise)
+        o1, r1, d1 = o1.clone(), r1.clone(), d1.clone()
+        o2, r2, d2, i2 = fa.step(a, step_noise=noise)
+        live = ~done_seen
+        assert torch.equal(d1[live], d2[live]) and torch.equal(i1["reached"][live], i2["reached"][live]), t
+        assert torch.equal(ex.pos_x[live], fa.pos_x[live]) and torch.equal(ex.pos_y[live], fa.pos_y[live]), t
+        assert torch.equal(ex.visited_t[live], fa.visited_t[live])
+        assert torch.equal(o1[live][:, [0, 1]], o2[live][:, [0, 1]])
+        assert torch.allclose(o1[live], o2[live], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(r1[live], r2[live], rtol=1e-5, atol=1e-5), t
+        worst = max(worst, float((r1[live] - r2[live]).abs().max())) if bool(live.any()) else worst
+        done_seen |= d1
+    assert bool(done_seen.any()) and worst < 1e-5

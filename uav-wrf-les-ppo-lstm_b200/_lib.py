@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplume_b200.so")
 
 OBS_DIM, NUM_ACTIONS, INFO_DIM, VISIT_STRIDE = 6, 5, 5, 104
-FLAG_AUTO_RESET, FLAG_GREEDY, FLAG_STOP_TERMINATES, FLAG_DEFER_STOP_HEAD = 1, 2, 4, 8
+FLAG_AUTO_RESET, FLAG_GREEDY, FLAG_STOP_TERMINATES, FLAG_DEFER_STOP_HEAD, FLAG_FAST_REWARD = 1, 2, 4, 8, 16
 
 # flat MLP parameter layout (include/plume_b200.h)
 MLP_OFFSETS = {

@@ -296,11 +296,15 @@ __global__ void __launch_bounds__(128) step_kernel(Cfg c, plume_env_state st, Fi
 
     int px, py;
     cell32_of(c, e, px, py);
+    const bool fast = (flags & PLUME_FLAG_FAST_REWARD) != 0;
     double pconc, ptke;
-    f.eval(c, i, gid, e.episode, e.sx, e.sy, px, py, pconc, ptke);
+    float pconc_f = 0.0f;
+    if (fast) f.eval_fast(c, i, gid, e.episode, e.sx, e.sy, px, py, pconc_f, ptke);
+    else f.eval(c, i, gid, e.episode, e.sx, e.sy, px, py, pconc, ptke);
 
     StepResult r;
-    env_step(c, f, i, gid, e, vis, actions[i], z0, z1, pconc, ptke, r);
+    if (fast) env_step_fast(c, f, i, gid, e, vis, actions[i], z0, z1, pconc_f, ptke, r);
+    else env_step(c, f, i, gid, e, vis, actions[i], z0, z1, pconc, ptke, r);
 
     reward[i] = r.reward;
     done[i] = r.done ? 1 : 0;

@@ -33,38 +33,57 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float* __restrict__
     if (n < N) {
         float last = 0.0f;
         float v_next = 0.0f, d_next = 0.0f;
-        for (int t = T - 1; t >= 0; --t) {
-            const size_t i = (size_t)t * N + n;
-            const float r = rewards[i], v = values[i], d = dones[i];
-            float a;
-            if (variant == PLUME_GAE_QUIRK) {
-                float nnt, nv;
-                if (t == T - 1) {                      // :22-24 self-bootstrap
-                    nnt = __fsub_rn(1.0f, d);
-                    nv = __fmul_rn(v, nnt);
-                } else {                               // :26-27 masks with dones[t+1]
-                    nnt = __fsub_rn(1.0f, d_next);
-                    nv = __fmul_rn(v_next, nnt);
+        // The recurrence is serial in t, the loads are not: fetch kGaeBatch rows ahead so that 3 x kGaeBatch
+        // independent loads are in flight per thread (4096 threads cannot hide HBM latency otherwise).
+        constexpr int kGaeBatch = 8;
+        for (int t1 = T - 1; t1 >= 0; t1 -= kGaeBatch) {
+            float rr[kGaeBatch], vv[kGaeBatch], dd[kGaeBatch];
+#pragma unroll
+            for (int q = 0; q < kGaeBatch; ++q) {
+                const int t = t1 - q;
+                if (t >= 0) {
+                    const size_t i = (size_t)t * N + n;
+                    rr[q] = __ldg(rewards + i);
+                    vv[q] = __ldg(values + i);
+                    dd[q] = __ldg(dones + i);
                 }
-                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);          // :29
-                a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));              // :30
-            } else if (variant == PLUME_GAE_BOOTSTRAP) {   // PPOV1.1/train_ppo1.0.py:75-85
-                const float nnt = __fsub_rn(1.0f, t == T - 1 ? d : d_next);
-                const float nv = (t == T - 1) ? last_values[n] : v_next;
-                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nv), nnt)), v);
-                a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));
-            } else {                                       // PPOV1.2: masks with dones[t], no bootstrap (:368-376)
-                const float nt = __fsub_rn(1.0f, d);
-                const float nv = (t == T - 1) ? 0.0f : __fmul_rn(v_next, nt);
-                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);
-                a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, last), nt));
             }
-            adv[i] = a;
-            last = a;
-            v_next = v;
-            d_next = d;
-            s1 += (double)a;
-            s2 += (double)a * (double)a;
+#pragma unroll
+            for (int q = 0; q < kGaeBatch; ++q) {
+                const int t = t1 - q;
+                if (t < 0) break;
+                const size_t i = (size_t)t * N + n;
+                const float r = rr[q], v = vv[q], d = dd[q];
+                float a;
+                if (variant == PLUME_GAE_QUIRK) {
+                    float nnt, nv;
+                    if (t == T - 1) {                      // :22-24 self-bootstrap
+                        nnt = __fsub_rn(1.0f, d);
+                        nv = __fmul_rn(v, nnt);
+                    } else {                               // :26-27 masks with dones[t+1]
+                        nnt = __fsub_rn(1.0f, d_next);
+                        nv = __fmul_rn(v_next, nnt);
+                    }
+                    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);          // :29
+                    a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));              // :30
+                } else if (variant == PLUME_GAE_BOOTSTRAP) {   // PPOV1.1/train_ppo1.0.py:75-85
+                    const float nnt = __fsub_rn(1.0f, t == T - 1 ? d : d_next);
+                    const float nv = (t == T - 1) ? last_values[n] : v_next;
+                    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nv), nnt)), v);
+                    a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));
+                } else {                                       // PPOV1.2: masks with dones[t], no bootstrap (:368-376)
+                    const float nt = __fsub_rn(1.0f, d);
+                    const float nv = (t == T - 1) ? 0.0f : __fmul_rn(v_next, nt);
+                    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);
+                    a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, last), nt));
+                }
+                adv[i] = a;
+                last = a;
+                v_next = v;
+                d_next = d;
+                s1 += (double)a;
+                s2 += (double)a * (double)a;
+            }
         }
     }
     const double b1 = block_sum(s1, scratch);

@@ -108,6 +108,7 @@ struct Cfg {
     double conc_peak, ti, two_sigma_sq, clip_hi, move_step;
     double conc_coef, tke_factor, bnd_penalty, bnd_start, initial_radius;
     uint32_t k0, k1;
+    float peak_f, inv_peak_f, exp2_scale, inv_nine_f, inv_G_f;      // float constants of the fast reward path
 };
 
 inline Cfg make_cfg(const plume_env_config& c) {
@@ -128,6 +129,11 @@ inline Cfg make_cfg(const plume_env_config& c) {
     o.bnd_penalty = c.boundary_penalty;
     o.bnd_start = c.boundary_decay_start;
     o.initial_radius = c.initial_radius;
+    o.peak_f = (float)c.conc_peak;
+    o.inv_peak_f = (float)(1.0 / c.conc_peak);
+    o.exp2_scale = (float)(-1.4426950408889634 / o.two_sigma_sq);
+    o.inv_nine_f = (float)(1.0 / (c.turbulence_intensity * 3.0));
+    o.inv_G_f = (float)(1.0 / (double)c.grid_size);
     o.k0 = (uint32_t)(c.seed & 0xFFFFFFFFu);
     o.k1 = (uint32_t)(c.seed >> 32);
     return o;
@@ -205,6 +211,31 @@ struct ProceduralField {
             plume_cell(c, sx, sy, x, y, (double)z, (double)u, sin_tab[x], cos_tab[y], conc, tke);
         }
     }
+    // PLUME_FLAG_FAST_REWARD: tke exactly as above (it drives the float64 position update, i.e. the flags),
+    // the concentration in float32 (it only feeds the observation and the reward: fp32 rel 1e-5 bar)
+    PLUME_HD void eval_fast(const Cfg& c, int env_local, uint32_t env_gid, uint32_t episode, double sx, double sy, int x,
+                            int y, float& conc, double& tke) const {
+        if (c.plume_model == PLUME_MODEL_DISPERSION) {
+            double cc;
+            eval(c, env_local, env_gid, episode, sx, sy, x, y, cc, tke);
+            conc = (float)cc;
+            return;
+        }
+        float z, u;
+        field_noise(c, env_gid, episode, x, y, z, u);
+        const double wave = dmul(dmul(0.3, sin_tab[x]), cos_tab[y]);
+        tke = dmul(c.ti, dadd(dadd(fabs((double)z), wave), dmul(0.2, (double)u)));      // env:57-61,63 (exact)
+        const float ddx = (float)x - (float)sx, ddy = (float)y - (float)sy;
+        const float arg = (ddx * ddx + ddy * ddy) * c.exp2_scale;
+#if defined(__CUDA_ARCH__)
+        float base;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(base) : "f"(arg));
+#else
+        const float base = exp2f(arg);
+#endif
+        const float v = c.peak_f * base + (float)tke;
+        conc = v < 0.0f ? 0.0f : (v > c.peak_f ? c.peak_f : v);                          // env:62
+    }
 };
 
 template <typename T>
@@ -215,6 +246,12 @@ struct MaterialisedField {
                        double& tke) const {
         const size_t off = ((size_t)env_local * c.G + x) * c.G + y;      // field[x, y], x = first axis
         conc = (double)conc_field[off];
+        tke = (double)tke_field[off];
+    }
+    PLUME_HD void eval_fast(const Cfg& c, int env_local, uint32_t, uint32_t, double, double, int x, int y, float& conc,
+                            double& tke) const {
+        const size_t off = ((size_t)env_local * c.G + x) * c.G + y;
+        conc = (float)conc_field[off];
         tke = (double)tke_field[off];
     }
 };
@@ -382,6 +419,108 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     out.boundary_penalty = info_bnd;
     out.cur_conc = cur_conc;
     out.cell_conc = conc32;
+    out.cell_tke = tke32;
+    out.distance = distance;
+}
+
+// P2 with PLUME_FLAG_FAST_REWARD: everything that decides a FLAG or an INDEX (position update, float32 rounding
+// of the position, cells, visit counters, distance <= radius, step limit) is the float64 arithmetic of env_step,
+// line for line; the observation's concentration/tke entries and the reward terms are float32 with reciprocal
+// multiplies (north_star bar: fp32 rel 1e-5; measured ~1e-7).  prev_cell_conc is the float32 field value.
+template <typename Field>
+PLUME_HD void env_step_fast(const Cfg& c, const Field& f, int env_local, uint32_t env_gid, EnvRegs& e,
+                            uint16_t* visited, int action, double z0, double z1, float prev_cell_conc,
+                            double prev_cell_tke, StepResult& out) {
+    e.step += 1;                                                              // env:90
+    const double ms = c.move_step;
+    double dx = 0.0, dy = 0.0;
+    if (action == 1) dy = ms;
+    else if (action == 2) dy = -ms;
+    else if (action == 3) dx = ms;
+    else if (action == 4) dx = -ms;
+    const float dnorm = (action == 0) ? 0.0f : (float)ms;
+    const float move_penalty = (action == 0) ? -0.15f : 0.0f;                 // env:101-102
+    // env:105-113, exact
+    const double nine = dmul(c.ti, 3.0);
+    const double gain = dmul(ms, 0.2);
+    const double tx = dmul(gain, ddiv(dmul(z0, prev_cell_tke), nine));
+    const double ty = dmul(gain, ddiv(dmul(z1, prev_cell_tke), nine));
+    double nx = dadd(dadd((double)e.px, dx), tx);
+    double ny = dadd(dadd((double)e.py, dy), ty);
+    nx = nx < 0.0 ? 0.0 : (nx > c.clip_hi ? c.clip_hi : nx);
+    ny = ny < 0.0 ? 0.0 : (ny > c.clip_hi ? c.clip_hi : ny);
+    e.px = (float)nx;
+    e.py = (float)ny;
+    // env:116-119
+    const int cx = clip_cell((int)nx, c.G), cy = clip_cell((int)ny, c.G);
+    int ox, oy;
+    cell32_of(c, e, ox, oy);
+    float conc64;
+    double tke64;
+    f.eval_fast(c, env_local, env_gid, e.episode, e.sx, e.sy, cx, cy, conc64, tke64);
+    float conc32 = conc64;
+    double tke32 = tke64;
+    if (ox != cx || oy != cy) f.eval_fast(c, env_local, env_gid, e.episode, e.sx, e.sy, ox, oy, conc32, tke32);
+    const float prev_conc = prev_cell_conc * c.inv_peak_f, cur_conc = conc64 * c.inv_peak_f;
+    const float grad = (cur_conc - prev_conc) / (dnorm + 1e-6f);
+    // env:121-131
+    const float fx = (float)nx, fy = (float)ny, G = (float)c.G;
+    const float bd = fminf(fminf(fx, G - fx), fminf(fy, G - fy)) * c.inv_G_f;
+    float bpen = 0.0f;
+    if (bd < (float)c.bnd_start && grad < -0.01f) {
+        const float gap = (float)c.bnd_start - bd;
+        bpen = -(float)c.bnd_penalty * gap * gap;
+    }
+    // env:134-137: floor(nx / cell_size) == int(nx) / cell_size for 0 <= nx < G (integer divisor)
+    const int gx = (int)nx / c.cell_size, gy = (int)ny / c.cell_size;
+    const int slot = gx * PLUME_MAX_GRID_DIVISIONS + gy;
+    const int vc = (int)visited[slot] + 1;
+    visited[slot] = (uint16_t)vc;
+    const int vis32 = visited[(ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size)];
+    // env:71-87
+    out.obs[0] = fdiv(e.px, G);
+    out.obs[1] = fdiv(e.py, G);
+    out.obs[2] = conc32 * c.inv_peak_f;
+    out.obs[3] = (float)tke32 * c.inv_nine_f;
+    out.obs[4] = fdiv((float)e.step, (float)c.max_steps);
+    out.obs[5] = fminf((float)vis32 * 0.2f, 1.0f);
+    if (c.plume_model == PLUME_MODEL_DISPERSION) make_obs(c, e, (double)conc32, tke32, vis32, out.obs, env_gid);
+    // env:140: vc ** 0.75 + 1
+    const float v3 = (float)vc * (float)vc * (float)vc;
+    const float explore = (float)e.ebonus * (1.0f - out.obs[5]) / (sqrtf(sqrtf(v3)) + 1.0f);
+    const float conc_reward = (float)c.conc_coef * out.obs[2];
+    const float tke_term = (float)c.tke_factor * out.obs[3];
+    double total = (double)((((conc_reward + explore) + move_penalty) - tke_term) + bpen);    // env:146-152
+    float info_conc = conc_reward, info_explore = explore, info_tke = -tke_term, info_move = move_penalty,
+          info_bnd = bpen;
+    if (c.plume_model == PLUME_MODEL_DISPERSION) {
+        const float dconc = cur_conc - prev_conc;
+        float dtheta = 0.0f;
+        if (action != 0 && e.last_move != 0 && action != e.last_move)
+            dtheta = ((action <= 2) == (e.last_move <= 2)) ? 3.14159265f : 1.57079633f;
+        if (action != 0) e.last_move = action;
+        total = (double)(dconc - 0.2f * dtheta);
+        info_conc = dconc;
+        info_explore = 0.0f;
+        info_tke = 0.0f;
+        info_move = -0.2f * dtheta;
+        info_bnd = 0.0f;
+    }
+    // env:155-161, exact
+    const double ex = dsub((double)e.px, e.sx), ey = dsub((double)e.py, e.sy);
+    const double distance = dsqrt(dadd(dmul(ex, ex), dmul(ey, ey)));
+    const bool reached = distance <= e.radius;
+    if (reached) total = dadd(total, fmin(500.0, dmul(150.0, ddiv(c.initial_radius, e.radius))));
+    out.reward = total;
+    out.reached = reached;
+    out.done = (e.step >= c.max_steps) || reached;
+    out.conc_reward = info_conc;
+    out.explore_reward = info_explore;
+    out.tke_penalty = info_tke;
+    out.move_penalty = (double)info_move;
+    out.boundary_penalty = (double)info_bnd;
+    out.cur_conc = (double)cur_conc;
+    out.cell_conc = (double)conc32;
     out.cell_tke = tke32;
     out.distance = distance;
 }

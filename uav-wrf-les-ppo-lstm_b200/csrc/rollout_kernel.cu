@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     const bool stop_terminates = (a.flags & PLUME_FLAG_STOP_TERMINATES) != 0;
     // deferred stop head: only record the window inputs; plume_stop_head_segment does the rest
     const bool defer = (a.flags & PLUME_FLAG_DEFER_STOP_HEAD) != 0;
+    const bool fast = (a.flags & PLUME_FLAG_FAST_REWARD) != 0;     // float32 reward terms, float64 flags
 
     const int tiles = (N + kTileM - 1) / kTileM;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                     step_noise(c, gid, e, z0, z1);
                 }
                 if (a.buf.noise_out) reinterpret_cast<double2*>(a.buf.noise_out)[row + env] = make_double2(z0, z1);
-                env_step(c, field, env, gid, e, vis, action, z0, z1, cell_conc, cell_tke, r);
+                if (fast) env_step_fast(c, field, env, gid, e, vis, action, z0, z1, (float)cell_conc, cell_tke, r);
+                else env_step(c, field, env, gid, e, vis, action, z0, z1, cell_conc, cell_tke, r);
                 cell_conc = r.cell_conc;
                 cell_tke = r.cell_tke;
                 // sliding window of obs[2] (= conc_field[int(x),int(y)]/100 as float32, evaluate_with_lstm.py:67-74)

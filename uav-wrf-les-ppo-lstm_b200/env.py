@@ -38,7 +38,7 @@ class VecMethaneEnv:
 
     def __init__(self, num_envs: int = 1, device="cuda", version: str = "2.1", seed: int = 0,
                  field_mode: str = "procedural", auto_reset: bool = False, env_id_base: int = 0,
-                 config: PlumeConfig | None = None, plume_model: str = "isotropic"):
+                 config: PlumeConfig | None = None, plume_model: str = "isotropic", fast_reward: bool = False):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.cfg = config if config is not None else config_for(version)
@@ -49,6 +49,9 @@ class VecMethaneEnv:
             raise ValueError("auto_reset needs field_mode='procedural' (materialised fields are regenerated "
                              "by reset(), which launches the field kernel)")
         self.seed = int(seed)
+        # fast_reward: flags / indices keep the reference's float64 arithmetic, reward terms and the concentration
+        # observation are float32 (fp32 rel 1e-5 instead of bit-exact float64 rewards); see PLUME_FLAG_FAST_REWARD
+        self.fast_reward = bool(fast_reward)
         # "isotropic" = the reference code (parity target); "dispersion" = the README's plume/state/reward
         self.plume_model = _lib.PLUME_MODELS[plume_model] if isinstance(plume_model, str) else int(plume_model)
         self.grid_size = self.cfg.grid_size                                   # environment.py:23
@@ -177,7 +180,7 @@ class VecMethaneEnv:
         zn = None
         if step_noise is not None:
             zn = torch.as_tensor(step_noise, dtype=torch.float64, device=self.device).reshape(self.num_envs, 2).contiguous()
-        flags = _lib.FLAG_AUTO_RESET if self.auto_reset else 0
+        flags = (_lib.FLAG_AUTO_RESET if self.auto_reset else 0) | (_lib.FLAG_FAST_REWARD if self.fast_reward else 0)
         self._call("plume_env_step", C.byref(self._ccfg), C.byref(self._cstate), a.data_ptr(), _lib.ptr(zn), flags,
                    self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.reached.data_ptr(),
                    self.info_t.data_ptr(), self.final_obs.data_ptr() if self.auto_reset else None,

@@ -53,6 +53,7 @@ class RolloutEngine:
             raise ValueError("defer_stop_head needs a stop head whose decision does not end the episode")
         flags = _lib.FLAG_AUTO_RESET
         flags |= _lib.FLAG_DEFER_STOP_HEAD if defer else 0
+        flags |= _lib.FLAG_FAST_REWARD if getattr(env, "fast_reward", False) else 0
         flags |= _lib.FLAG_GREEDY if greedy else 0
         flags |= _lib.FLAG_STOP_TERMINATES if stop_terminates else 0
         if forced_actions is not None:

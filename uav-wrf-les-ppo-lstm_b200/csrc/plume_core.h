@@ -275,7 +275,7 @@ struct StepResult {
     bool done, reached;
     float conc_reward, explore_reward, tke_penalty;
     double move_penalty, boundary_penalty;
-    double cur_conc;       // conc at the float64 cell / peak (env:118)
+    double cur_conc;       // conc at the float64 cell / peak (env:118); evaluated only where the reward needs it
     double cell_conc, cell_tke;   // field at the float32 cell after the move (what obs[2], obs[3] hold)
     double distance;       // ||agent_pos - source_pos|| after the move (env:155)
 };
@@ -297,8 +297,11 @@ PLUME_HD void make_obs(const Cfg& c, const EnvRegs& e, double cell_conc, double 
     obs[2] = (float)ddiv(cell_conc, c.conc_peak);                             // env:83
     obs[3] = (float)ddiv(cell_tke, dmul(c.ti, 3.0));                          // env:84
     obs[4] = (float)ddiv((double)e.step, (double)c.max_steps);                // env:85
-    const double lvl = ddiv((double)visit_here, 5.0);                         // env:78
-    obs[5] = (float)(lvl < 1.0 ? lvl : 1.0);
+    // env:78  min(visit / 5.0, 1.0): six possible values, folded at compile time (no float64 division)
+    obs[5] = visit_here >= 5 ? 1.0f
+             : (visit_here == 4 ? (float)(4.0 / 5.0)
+                : (visit_here == 3 ? (float)(3.0 / 5.0)
+                   : (visit_here == 2 ? (float)(2.0 / 5.0) : (visit_here == 1 ? (float)(1.0 / 5.0) : 0.0f))));
     if (c.plume_model == PLUME_MODEL_DISPERSION) {      // README state: [CH4], wind vector, UAV position
         const Wind w = wind_of(c, env_gid, e.episode);
         obs[3] = (float)(w.c * w.speed / kWindMaxSpeed);
@@ -329,7 +332,6 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
                        int action, double z0, double z1, double prev_cell_conc, double prev_cell_tke,
                        StepResult& out) {
     e.step += 1;                                                              // env:90
-    const double prev_conc = ddiv(prev_cell_conc, c.conc_peak);               // env:95
     // env:98-102
     const double ms = c.move_step;
     double dx = 0.0, dy = 0.0;
@@ -338,8 +340,8 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     else if (action == 3) dx = ms;
     else if (action == 4) dx = -ms;
     const double dnorm = (action == 0) ? 0.0 : ms;                            // ||(dx,dy)||, exact
-    const double move_mag = ddiv(dnorm, ms);
-    const double move_penalty = dmul(-0.15, dsub(1.0, move_mag));
+    // -0.15 * (1 - ||d|| / move_step): ||d|| is exactly 0 or move_step, so the product is -0.15 or -0.0
+    const double move_penalty = (action == 0) ? -0.15 : -0.0;
     // env:105-108   move_step*0.2*(randn(2)*tke/(TI*3))
     const double nine = dmul(c.ti, 3.0);
     const double gain = dmul(ms, 0.2);
@@ -361,19 +363,27 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     double conc32 = conc64, tke32 = tke64;
     if (ox != cx || oy != cy)   // float32 rounding of the position crossed a cell edge (rare)
         f.eval(c, env_local, env_gid, e.episode, e.sx, e.sy, ox, oy, conc32, tke32);
-    const double cur_conc = ddiv(conc64, c.conc_peak);
-    const double grad = ddiv(dsub(cur_conc, prev_conc), dadd(dnorm, 1e-6));
-    // env:121-131
+    // env:118-131.  boundary_dist = min over the four quotients v/G = (min v)/G (correctly rounded division is
+    // monotonic), and the penalty -- the only consumer of conc_gradient in the code model -- is zero unless
+    // boundary_dist < boundary_decay_start: the float64 divisions are evaluated only near the boundary (and
+    // always in the README model, whose reward needs the concentrations).  Bit-identical results.
     const double G = (double)c.G;
-    const double b0 = ddiv(nx, G), b1 = ddiv(dsub(G, nx), G), b2 = ddiv(ny, G), b3 = ddiv(dsub(G, ny), G);
-    const double bd = fmin(fmin(b0, b1), fmin(b2, b3));
-    double bpen = 0.0;
-    if (bd < c.bnd_start && grad < -0.01) {
-        const double gap = dsub(c.bnd_start, bd);
-        bpen = dmul(-c.bnd_penalty, dmul(gap, gap));
+    const double vmin = fmin(fmin(nx, dsub(G, nx)), fmin(ny, dsub(G, ny)));
+    double cur_conc = 0.0, bpen = 0.0;
+    const bool need_conc = c.plume_model == PLUME_MODEL_DISPERSION;
+    double prev_conc = 0.0;
+    if (need_conc || vmin < dmul(dadd(c.bnd_start, 1e-3), G)) {
+        prev_conc = ddiv(prev_cell_conc, c.conc_peak);                        // env:95
+        cur_conc = ddiv(conc64, c.conc_peak);
+        const double grad = ddiv(dsub(cur_conc, prev_conc), dadd(dnorm, 1e-6));
+        const double bd = ddiv(vmin, G);
+        if (bd < c.bnd_start && grad < -0.01) {
+            const double gap = dsub(c.bnd_start, bd);
+            bpen = dmul(-c.bnd_penalty, dmul(gap, gap));
+        }
     }
-    // env:134-137  (floor division of the float64 position)
-    const int gx = (int)floor(ddiv(nx, (double)c.cell_size)), gy = (int)floor(ddiv(ny, (double)c.cell_size));
+    // env:134-137: floor(nx / cell_size) == int(nx) / cell_size for 0 <= nx < grid (integer divisor)
+    const int gx = (int)nx / c.cell_size, gy = (int)ny / c.cell_size;
     const int slot = gx * PLUME_MAX_GRID_DIVISIONS + gy;
     const int vc = (int)visited[slot] + 1;
     visited[slot] = (uint16_t)vc;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PLUME_B200_ABI_VERSION 1
+#define PLUME_B200_ABI_VERSION 2
 
 #define PLUME_OBS_DIM 6          /* environment.py:80-87 */
 #define PLUME_NUM_ACTIONS 5      /* environment.py:23 */
@@ -102,6 +102,16 @@ typedef struct plume_env_state {
     const double* cos_tab;        /* [G] cos(0.07 y) */
     const double* curriculum;     /* [2] = {current_radius, explore_bonus} that resets latch (model.py:189-190) */
     int8_t* last_move;            /* last non-zero action (heading) per env, PLUME_MODEL_DISPERSION only; may be NULL */
+    /* ABI 2, all optional (NULL = evaluate in the kernel).  Host tables of the two integer-indexed terms:
+     * step_frac_tab[s] = (float)(s / MAX_STEPS), s in [0,max_steps] (environment.py:85);
+     * visit_denom_tab[v] = (float)(v**0.75 + 1), v in [0,max_steps+1] (environment.py:140). */
+    const float* step_frac_tab;
+    const float* visit_denom_tab;
+    /* procedural mode: tke_field at the float32 cell of the current position (the "prev" lookup of the next
+     * step, environment.py:93,106), tagged with (cell, episode) in cell_key so that a stale entry -- state
+     * edited from the host -- is recomputed, never trusted.  Zero-initialise cell_key. */
+    double* cell_tke;
+    uint32_t* cell_key;
 } plume_env_state;
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -360,6 +370,34 @@ int plume_allreduce_clip_adam(void* comm, float* params, float* grads, float* ex
  * [start, start+count) of the bijection of [0,total) keyed by (seed, epoch). */
 int plume_permutation(int64_t total, uint64_t seed, int32_t epoch, int64_t start, int64_t count, int64_t* out,
                       void* stream);
+
+/* ---- N3: supervised training of the V2.1 stop head (PPOV2.1/train_lstm.py) ------------------------------------
+ * Flat parameter vector in torch named_parameters() order of PeakAndStopPredictor(hidden 32):
+ *   lstm.weight_ih_l0[128] lstm.weight_hh_l0[128][32] lstm.bias_ih_l0[128] lstm.bias_hh_l0[128]
+ *   fc_peak.weight[32] fc_peak.bias[1] fc_stop.0.weight[32] fc_stop.0.bias[1]                                  */
+#define PLUME_LSTM_TRAIN_PARAMS 4546
+/* TrajectoryDataset._preprocess (train_lstm.py:28-65) for the episodes listed in episode_ids (int32[n_selected],
+ * each with at least `window` logged steps; the host picks them, train_lstm.py:40): from rows of the
+ * training_data.nc variables concentration / x / y (float[episodes][max_steps]) and source_x / source_y
+ * (float[episodes]) writes two samples per episode -- features float[2 n_selected][window] = conc[:window] / 100
+ * (twice: the reference's "positive" window is the same first window), labels float[2 n_selected][2] =
+ * {conc[window-1] / 100, 0} and {conc[window-1] / 100, ||pos[window-1] - source|| <= stop_radius}. */
+int plume_lstm_dataset(const float* conc, const float* x, const float* y, const float* src_x, const float* src_y,
+                       int32_t max_steps, const int32_t* episode_ids, int32_t n_selected, int32_t window,
+                       float stop_radius, float* features, float* labels, void* stream);
+/* One epoch of train_lstm.py:108-121: for every minibatch of `batch_size` samples taken in `order` (int32
+ * [n_samples] sample ids, NULL = identity; the last minibatch may be short) ONE kernel does forward, BPTT,
+ * loss = MSE(peak) + BCE(stop), clip_grad_norm_(max_norm) and the AdamW step (optimiser step numbers
+ * first_step, first_step+1, ...).  batch_losses float[ceil(n_samples / batch_size)] receives each minibatch's
+ * mean loss, grad_norms (may be NULL) the gradient norms before clipping, grad_out (may be NULL,
+ * float[PLUME_LSTM_TRAIN_PARAMS]) the unclipped gradient of the last minibatch.  workspace: device memory of
+ * plume_lstm_train_workspace_bytes(batch_size) bytes, 256-byte aligned.  hidden must be 32. */
+int64_t plume_lstm_train_workspace_bytes(int32_t batch_size);
+int plume_lstm_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int32_t hidden, const float* features,
+                           const float* labels, const int32_t* order, int32_t n_samples, int32_t window,
+                           int32_t batch_size, float max_norm, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int32_t first_step, void* workspace, int64_t workspace_bytes,
+                           float* batch_losses, float* grad_norms, float* grad_out, void* stream);
 
 /* ---- tensor-core GEMM building block ----------------------------------------------------- */
 /* C[M][N] = A[M][K] . B[N][K]^T, fp32 in/out, 3xTF32 on tcgen05 (fp32-grade accuracy); N in {128,256},

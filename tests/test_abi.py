@@ -24,7 +24,7 @@ def test_library_exports_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(pb._lib.EXPORTED_SYMBOLS) == declared
-    assert lib.plume_abi_version() == 1
+    assert lib.plume_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     import uav_wrf_les_ppo_lstm_b200 as pb
     L = pb._lib
     assert C.sizeof(L.EnvConfig) == 4 * 4 + 9 * 8 + 8 + 8
-    assert C.sizeof(L.EnvState) == 8 + 15 * 8
+    assert C.sizeof(L.EnvState) == 8 + 19 * 8
     assert C.sizeof(L.LstmParams) == 16 + 8 * 8
     assert C.sizeof(L.RolloutBuffers) == 25 * 8
     assert C.sizeof(L.PpoBatch) == 7 * 8

@@ -67,12 +67,54 @@ def test_feistel_is_a_permutation(sim, n):
         assert (other != out).mean() > 0.9
 
 
+def _set_variant(sim, variant, cfg):
+    """0: previous-cell concentration passed in, no tables; 1: evaluated on demand + host tables + reached test
+    without the sqrt (what the K2 kernel runs); 2: generic IEEE divisions.  Returns objects to keep alive."""
+    import uav_wrf_les_ppo_lstm_b200 as pb
+    sf, vd = pb.env.host_tables(cfg)
+    sim.sim_set_variant(variant, P(sf), P(vd))
+    return sf, vd
+
+
+def test_constant_division_is_correctly_rounded(sim):
+    """ddiv_const / fdiv_const (three FMA-pipe instructions) == IEEE division, on random numerators, on
+    numerators constructed next to rounding boundaries of the quotient, and on float positions."""
+    rng = np.random.default_rng(3)
+    sim.sim_reciprocal_ok.argtypes = [C.c_double]
+    sim.sim_div_const.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    for b in (9.0, 100.0, 500.0, 1000.0, 2.7):
+        assert sim.sim_reciprocal_ok(b) == 1
+        n = 200000
+        a = np.ldexp(rng.random(n) + 1.0, rng.integers(-30, 30, n)) * rng.choice([-1.0, 1.0], n)
+        q = np.ldexp(rng.random(n) + 1.0, rng.integers(-8, 8, n))
+        mid = (q.astype(np.longdouble) + np.nextafter(q, np.inf).astype(np.longdouble)) / 2
+        near = (mid * np.longdouble(b)).astype(np.float64)
+        near = np.concatenate([near, np.nextafter(near, np.inf), np.nextafter(near, -np.inf)])
+        z = rng.standard_normal(n).astype(np.float32).astype(np.float64) * (rng.random(n) * 14.0 - 0.9)
+        for arr in (a, near, z):
+            arr = np.ascontiguousarray(arr)
+            out = np.zeros_like(arr)
+            sim.sim_div_const(P(arr), len(arr), b, P(out))
+            assert np.array_equal(out, arr / b)
+    assert sim.sim_reciprocal_ok(0.0) == 0
+    cfg = po.config_for("2.1")
+    ec = _ccfg(cfg, 2, 0)
+    assert sim.sim_fastdiv_enabled(C.byref(ec)) == 1
+    pos = np.concatenate([(rng.random(2_000_000) * 500.0).astype(np.float32),
+                          np.arange(0, 500, dtype=np.float32), np.float32(499.0) + np.zeros(1, np.float32)])
+    outf = np.zeros_like(pos)
+    sim.sim_div_G(C.byref(ec), P(pos), len(pos), P(outf))
+    assert np.array_equal(outf, pos / np.float32(500.0))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", ["env_v21_s11.npz", "env_v21_s12.npz", "env_v20_s21.npz", "env_v11_s31.npz"])
-def test_device_step_logic_against_reference_golden(sim, name):
+def test_device_step_logic_against_reference_golden(sim, name, variant):
     """csrc env_step (host build) vs the trace the REAL reference produced."""
     g = load_golden(name)
     cfg, ora, z_steps = golden_oracle_env(g)
     ec = _ccfg(cfg, 2, 0)
+    keep = _set_variant(sim, variant, cfg)
     px = np.zeros(1, np.float32); py = np.zeros(1, np.float32)
     step = np.zeros(1, np.int32); ep = np.ones(1, np.int32)
     vis = np.zeros((1, 104), np.uint16)
@@ -96,10 +138,12 @@ def test_device_step_logic_against_reference_golden(sim, name):
     assert np.array_equal(vis[0, :100].reshape(10, 10).astype(np.int64), g["visited"])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("version", ["2.1", "1.1"])
-def test_device_step_logic_random_walk(sim, version):
+def test_device_step_logic_random_walk(sim, version, variant):
     cfg = po.config_for(version)
     ec = _ccfg(cfg, 2, 1234)
+    keep = _set_variant(sim, variant, cfg)
     n, T, G = 6, 300, cfg.grid_size
     rng = np.random.default_rng(5)
     ora = po.OracleVecEnv(cfg, n)

@@ -41,7 +41,8 @@ class EnvState(C.Structure):
     _fields_ = [("n_envs", C.c_int32), ("env_id_base", C.c_int32), ("pos_x", _vp), ("pos_y", _vp),
                 ("src_x", _vp), ("src_y", _vp), ("step_count", _vp), ("episode_idx", _vp), ("visited", _vp),
                 ("radius", _vp), ("explore_bonus", _vp), ("conc_field", _vp), ("tke_field", _vp),
-                ("sin_tab", _vp), ("cos_tab", _vp), ("curriculum", _vp), ("last_move", _vp)]
+                ("sin_tab", _vp), ("cos_tab", _vp), ("curriculum", _vp), ("last_move", _vp),
+                ("step_frac_tab", _vp), ("visit_denom_tab", _vp), ("cell_tke", _vp), ("cell_key", _vp)]
 
 
 class LstmParams(C.Structure):
@@ -114,6 +115,12 @@ _SIGNATURES = {
     "plume_comm_error": (C.c_int, [_vp, _P(C.c_int32), _vp]),
     "plume_allreduce_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_float, C.c_int32, _vp, _vp]),
+    "plume_lstm_dataset": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_float, _vp,
+                                     _vp, _vp]),
+    "plume_lstm_train_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "plume_lstm_train_epoch": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                         _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "plume_permutation": (C.c_int, [C.c_int64, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, _vp, _vp]),
     "plume_tc_gemm": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "plume_curriculum_update": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double,
@@ -144,7 +151,7 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError = a declared symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.plume_abi_version() != 1:
+    if lib.plume_abi_version() != 2:
         raise PlumeLibraryError("libplume_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libplume_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("PLUME_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

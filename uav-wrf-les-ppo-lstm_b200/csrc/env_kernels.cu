@@ -254,6 +254,7 @@ __global__ void reset_kernel(Cfg c, plume_env_state st, const int32_t* env_list,
     env_reset(c, (uint32_t)(st.env_id_base + env), e, st.visited + (size_t)env * PLUME_VISIT_STRIDE,
               u_src ? u_src + 2 * (size_t)li : nullptr, st.curriculum[0], st.curriculum[1]);
     store_env(st, env, e);
+    if (st.cell_key) st.cell_key[env] = 0u;      // cached tke belongs to the previous episode
 }
 
 // ---------------------------------------------------------------------------------------
@@ -273,16 +274,47 @@ __global__ void observe_kernel(Cfg c, plume_env_state st, Field f, float* obs) {
 // ---------------------------------------------------------------------------------------
 // K2: lockstep step, one thread per env
 // ---------------------------------------------------------------------------------------
+// kSpec selects a specialisation at compile time (smaller code, fewer registers, more resident warps):
+//   0  generic: plume model, PLUME_FLAG_FAST_REWARD and the division mode are read at run time
+//   1  reference code model, exact float64 reward, constant divisions by reciprocal (make_cfg checked them)
+//   2  as 1 with PLUME_FLAG_FAST_REWARD
+// Per step the kernel evaluates ONE Philox field cell (the cell after the move); the tke of the cell before
+// the move is carried in st.cell_tke (tagged, recomputed when stale), the concentration there is only needed
+// inside the boundary band and is evaluated on demand.
+#ifndef PLUME_STEP_MIN_BLOCKS
+#define PLUME_STEP_MIN_BLOCKS 8
+#endif
 template <typename Field>
-__global__ void __launch_bounds__(128) step_kernel(Cfg c, plume_env_state st, Field f, const int32_t* actions,
+struct FieldTraits {
+    static constexpr bool kCacheTke = false;
+};
+template <>
+struct FieldTraits<ProceduralField> {
+    static constexpr bool kCacheTke = true;
+};
+
+template <typename Field, int kSpec>
+__global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) step_kernel(Cfg c_in, plume_env_state st, Field f, const int32_t* actions,
                                                    const double* step_noise_in, uint32_t flags, float* obs,
                                                    double* reward, uint8_t* done, uint8_t* reached, float* info,
                                                    float* final_obs, double* noise_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st.n_envs) return;
+    Cfg c = c_in;
+    if (kSpec != 0) {               // constant-propagated through the inlined per-env code
+        c.plume_model = PLUME_MODEL_ISOTROPIC;
+        c.fastdiv = 1;
+    }
+    const bool fast = kSpec == 0 ? (flags & PLUME_FLAG_FAST_REWARD) != 0 : kSpec == 2;
+    const bool dispersion = c.plume_model == PLUME_MODEL_DISPERSION;
     const uint32_t gid = (uint32_t)(st.env_id_base + i);
     EnvRegs e = load_env(st, i);
     uint16_t* vis = st.visited + (size_t)i * PLUME_VISIT_STRIDE;
+    const int action = actions[i];
+    // every load whose address does not depend on data is issued here, ahead of the first use
+    const bool cache = FieldTraits<Field>::kCacheTke && st.cell_tke && st.cell_key;
+    const uint32_t cached_key = cache ? st.cell_key[i] : 0u;
+    const double cached_tke = cache ? st.cell_tke[i] : 0.0;
 
     double z0, z1;
     if (step_noise_in) {
@@ -296,15 +328,21 @@ __global__ void __launch_bounds__(128) step_kernel(Cfg c, plume_env_state st, Fi
 
     int px, py;
     cell32_of(c, e, px, py);
-    const bool fast = (flags & PLUME_FLAG_FAST_REWARD) != 0;
-    double pconc, ptke;
-    float pconc_f = 0.0f;
-    if (fast) f.eval_fast(c, i, gid, e.episode, e.sx, e.sy, px, py, pconc_f, ptke);
-    else f.eval(c, i, gid, e.episode, e.sx, e.sy, px, py, pconc, ptke);
+    double ptke = cached_tke;
+    if (!(cache && cached_key != 0u && cached_key == cell_key_of(c, px, py, e.episode)))
+        ptke = f.eval_tke(c, i, gid, e.episode, px, py);
+    // the visit-table line this step will most likely touch (cell of position + move, before the turbulence
+    // offset): requested now so that its DRAM latency overlaps the Philox / field arithmetic below
+    {
+        const int ms = (int)c.move_step;
+        const int qx = clip_cell(px + (action == 3 ? ms : (action == 4 ? -ms : 0)), c.G) / c.cell_size;
+        const int qy = clip_cell(py + (action == 1 ? ms : (action == 2 ? -ms : 0)), c.G) / c.cell_size;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vis + qx * PLUME_MAX_GRID_DIVISIONS + qy));
+    }
 
     StepResult r;
-    if (fast) env_step_fast(c, f, i, gid, e, vis, actions[i], z0, z1, pconc_f, ptke, r);
-    else env_step(c, f, i, gid, e, vis, actions[i], z0, z1, pconc, ptke, r);
+    if (fast) env_step_fast<false>(c, f, i, gid, e, vis, action, z0, z1, false, 0.0f, ptke, r);
+    else env_step<false>(c, f, i, gid, e, vis, action, z0, z1, false, 0.0, ptke, r);
 
     reward[i] = r.reward;
     done[i] = r.done ? 1 : 0;
@@ -317,17 +355,32 @@ __global__ void __launch_bounds__(128) step_kernel(Cfg c, plume_env_state st, Fi
         info[3 * (size_t)n + i] = r.tke_penalty;
         info[4 * (size_t)n + i] = (float)r.boundary_penalty;
     }
+    bool was_reset = false;
     if ((flags & PLUME_FLAG_AUTO_RESET) && r.done) {
         if (final_obs) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) final_obs[(size_t)i * 6 + k] = r.obs[k];
         }
         env_reset(c, gid, e, vis, nullptr, st.curriculum[0], st.curriculum[1]);
-        observe(c, f, i, gid, e, vis, r.obs);
+        double conc0;
+        f.eval(c, i, gid, e.episode, e.sx, e.sy, 0, 0, conc0, r.cell_tke);     // agent_pos = (0,0), env:46
+        make_obs(c, e, conc0, r.cell_tke, 0, r.obs, gid);
+        was_reset = true;
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) obs[(size_t)i * 6 + k] = r.obs[k];
-    store_env(st, i, e);
+    // state that a step changes: position, step counter (heading in the README model); the rest only on reset
+    st.pos_x[i] = e.px;
+    st.pos_y[i] = e.py;
+    st.step_count[i] = e.step;
+    if (dispersion && st.last_move) st.last_move[i] = (int8_t)e.last_move;
+    if (was_reset) store_env(st, i, e);
+    if (cache) {
+        int ox, oy;
+        cell32_of(c, e, ox, oy);
+        st.cell_tke[i] = r.cell_tke;
+        st.cell_key[i] = cell_key_of(c, ox, oy, e.episode);
+    }
 }
 
 }  // namespace plume
@@ -370,7 +423,7 @@ extern "C" int plume_env_reset(const plume_env_config* cfg, const plume_env_stat
     if (check_cfg(cfg, st)) return 1;
     if (!env_list) n_list = st->n_envs;
     if (n_list <= 0) return 0;
-    const Cfg c = make_cfg(*cfg);
+    const Cfg c = make_cfg(*cfg, *st);
     reset_kernel<<<(n_list + 127) / 128, 128, 0, as_stream(stream)>>>(c, *st, env_list, n_list, u_src);
     PLUME_LAUNCH_CHECK();
     return 0;
@@ -383,7 +436,7 @@ extern "C" int plume_generate_fields(const plume_env_config* cfg, const plume_en
     if (!env_list) n_list = st->n_envs;
     if (n_list <= 0) return 0;
     PLUME_CHECK_ARG((z_out == nullptr) == (u_out == nullptr), "z_out and u_out must be given together");
-    const Cfg c = make_cfg(*cfg);
+    const Cfg c = make_cfg(*cfg, *st);
     const int quads = c.G * c.G / 4;
     const int bpe = (quads + 255) / 256;
     const long long blocks = (long long)bpe * n_list;
@@ -418,7 +471,7 @@ extern "C" int plume_field_at(const plume_env_config* cfg, const plume_env_state
     if (check_cfg(cfg, st)) return 1;
     PLUME_CHECK_ARG(x && y && (conc || tke), "null pointer");
     if (st->n_envs == 0) return 0;
-    const Cfg c = make_cfg(*cfg);
+    const Cfg c = make_cfg(*cfg, *st);
     const int blocks = (st->n_envs + 127) / 128;
     cudaStream_t s = as_stream(stream);
     if (cfg->field_mode == PLUME_FIELD_PROCEDURAL)
@@ -439,7 +492,7 @@ extern "C" int plume_field_noise_at(const plume_env_config* cfg, const plume_env
                                     void* stream) {
     if (!cfg || !st) return fail("null config/state");
     if (n <= 0) return 0;
-    const Cfg c = make_cfg(*cfg);
+    const Cfg c = make_cfg(*cfg, *st);
     noise_at_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(c, *st, env_local, x, y, n, z_out, u_out);
     PLUME_LAUNCH_CHECK();
     return 0;
@@ -448,7 +501,7 @@ extern "C" int plume_field_noise_at(const plume_env_config* cfg, const plume_env
 extern "C" int plume_env_observe(const plume_env_config* cfg, const plume_env_state* st, float* obs, void* stream) {
     if (check_cfg(cfg, st)) return 1;
     if (st->n_envs == 0) return 0;
-    const Cfg c = make_cfg(*cfg);
+    const Cfg c = make_cfg(*cfg, *st);
     const int blocks = (st->n_envs + 127) / 128;
     cudaStream_t s = as_stream(stream);
     if (cfg->field_mode == PLUME_FIELD_PROCEDURAL) {
@@ -473,21 +526,23 @@ extern "C" int plume_env_step(const plume_env_config* cfg, const plume_env_state
     if ((flags & PLUME_FLAG_AUTO_RESET) && cfg->field_mode != PLUME_FIELD_PROCEDURAL)
         return fail("auto-reset inside the step needs the procedural field mode "
                     "(materialised fields are regenerated by plume_generate_fields)");
-    const Cfg c = make_cfg(*cfg);
+    const Cfg c = make_cfg(*cfg, *st);
     const int blocks = (st->n_envs + 127) / 128;
     cudaStream_t s = as_stream(stream);
+#define PLUME_STEP_LAUNCH(FIELD, SPEC, ...)                                                                         \
+    step_kernel<FIELD, SPEC><<<blocks, 128, 0, s>>>(c, *st, FIELD{__VA_ARGS__}, actions, step_noise_in, flags, obs, \
+                                                    reward, done, reached, info, final_obs, noise_out)
     if (cfg->field_mode == PLUME_FIELD_PROCEDURAL) {
-        step_kernel<<<blocks, 128, 0, s>>>(c, *st, ProceduralField{st->sin_tab, st->cos_tab}, actions, step_noise_in,
-                                           flags, obs, reward, done, reached, info, final_obs, noise_out);
+        const bool spec = c.plume_model == PLUME_MODEL_ISOTROPIC && c.fastdiv;
+        if (spec && !(flags & PLUME_FLAG_FAST_REWARD)) PLUME_STEP_LAUNCH(ProceduralField, 1, st->sin_tab, st->cos_tab);
+        else if (spec) PLUME_STEP_LAUNCH(ProceduralField, 2, st->sin_tab, st->cos_tab);
+        else PLUME_STEP_LAUNCH(ProceduralField, 0, st->sin_tab, st->cos_tab);
     } else if (cfg->field_mode == PLUME_FIELD_F32) {
-        step_kernel<<<blocks, 128, 0, s>>>(
-            c, *st, MaterialisedField<float>{(const float*)st->conc_field, (const float*)st->tke_field}, actions,
-            step_noise_in, flags, obs, reward, done, reached, info, final_obs, noise_out);
+        PLUME_STEP_LAUNCH(MaterialisedField<float>, 0, (const float*)st->conc_field, (const float*)st->tke_field);
     } else {
-        step_kernel<<<blocks, 128, 0, s>>>(
-            c, *st, MaterialisedField<double>{(const double*)st->conc_field, (const double*)st->tke_field}, actions,
-            step_noise_in, flags, obs, reward, done, reached, info, final_obs, noise_out);
+        PLUME_STEP_LAUNCH(MaterialisedField<double>, 0, (const double*)st->conc_field, (const double*)st->tke_field);
     }
+#undef PLUME_STEP_LAUNCH
     PLUME_LAUNCH_CHECK();
     return 0;
 }

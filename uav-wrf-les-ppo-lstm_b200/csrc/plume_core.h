@@ -47,6 +47,24 @@ PLUME_HD float fmul(float a, float b) { return a * b; }
 PLUME_HD float fdiv(float a, float b) { return a / b; }
 #endif
 
+// Correctly rounded a / b for a divisor b that is a configuration constant, y = RN(1 / b) precomputed on the
+// host: q0 = RN(a y) is within one ulp of a / b, the residual r = a - b q0 is exact in one FMA, and
+// RN(q0 + r y) is the correctly rounded quotient (Markstein's theorem; b must not have an all-ones mantissa).
+// Three FMA-pipe instructions instead of the ~27 of the generic IEEE division sequence.  Differs from a / b
+// only in the sign of a zero result.  make_cfg() enables it per divisor after checking |b y - 1| <= 2^-54;
+// tests/test_host_sim.py compares it with a / b on adversarial numerators.
+#if defined(__CUDA_ARCH__)
+PLUME_HD double ddiv_const(double a, double b, double y) {
+    const double q0 = __dmul_rn(a, y);
+    return __fma_rn(__fma_rn(-b, q0, a), y, q0);
+}
+#else
+PLUME_HD double ddiv_const(double a, double b, double y) {
+    const double q0 = a * y;
+    return fma(fma(-b, q0, a), y, q0);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Stream layout documented in oracle/philox.py.
 // ---------------------------------------------------------------------------------------
@@ -109,7 +127,21 @@ struct Cfg {
     double conc_coef, tke_factor, bnd_penalty, bnd_start, initial_radius;
     uint32_t k0, k1;
     float peak_f, inv_peak_f, exp2_scale, inv_nine_f, inv_G_f;      // float constants of the fast reward path
+    // exact division by the configuration constants (ddiv_const): nine = TI*3, conc_peak, G (float)
+    int32_t fastdiv;                 // 1 = the reciprocals below passed the host check
+    double nine, inv_nine, inv_peak;
+    double G_d, inv_G_d;             // float / G goes through the double quotient (see div_G)
+    // optional host tables (NULL = evaluate): (float)(step / max_steps) and (float)(count**0.75 + 1)
+    const float* step_frac_tab;
+    const float* visit_denom_tab;
 };
+
+inline bool reciprocal_ok(double b) {
+    if (!(b > 0.0) || !isfinite(b)) return false;
+    const double y = 1.0 / b;
+    return fabs(fma(b, y, -1.0)) <= 5.551115123125783e-17;      // 2^-54
+}
+
 
 inline Cfg make_cfg(const plume_env_config& c) {
     Cfg o;
@@ -136,7 +168,39 @@ inline Cfg make_cfg(const plume_env_config& c) {
     o.inv_G_f = (float)(1.0 / (double)c.grid_size);
     o.k0 = (uint32_t)(c.seed & 0xFFFFFFFFu);
     o.k1 = (uint32_t)(c.seed >> 32);
+    o.nine = c.turbulence_intensity * 3.0;                 // env:84,107
+    o.inv_nine = 1.0 / o.nine;
+    o.inv_peak = 1.0 / c.conc_peak;
+    o.G_d = (double)c.grid_size;
+    o.inv_G_d = 1.0 / o.G_d;
+    o.fastdiv = (reciprocal_ok(o.nine) && reciprocal_ok(c.conc_peak) && reciprocal_ok(o.G_d)) ? 1 : 0;
+    o.step_frac_tab = nullptr;
+    o.visit_denom_tab = nullptr;
     return o;
+}
+
+inline Cfg make_cfg(const plume_env_config& c, const plume_env_state& st) {
+    Cfg o = make_cfg(c);
+    o.step_frac_tab = st.step_frac_tab;
+    o.visit_denom_tab = st.visit_denom_tab;
+    return o;
+}
+
+// tag of a cached per-cell value: valid bit | 13 bits of the episode | linear cell index (G <= 512); 0 = none
+PLUME_HD uint32_t cell_key_of(const Cfg& c, int x, int y, uint32_t episode) {
+    if (c.G > 512) return 0u;
+    return 0x80000000u | ((episode & 0x1FFFu) << 18) | ((uint32_t)x * (uint32_t)c.G + (uint32_t)y);
+}
+
+// a / nine, a / conc_peak, a / G(float) -- exact either way, three instructions when the reciprocals qualify
+PLUME_HD double div_nine(const Cfg& c, double a) { return c.fastdiv ? ddiv_const(a, c.nine, c.inv_nine) : ddiv(a, c.nine); }
+PLUME_HD double div_peak(const Cfg& c, double a) {
+    return c.fastdiv ? ddiv_const(a, c.conc_peak, c.inv_peak) : ddiv(a, c.conc_peak);
+}
+// float32 a / float32 G (env:81): the float64 quotient of two float32 values rounded to float32 equals the
+// float32 quotient (double rounding is innocuous for division when the wide format has >= 2p+2 bits)
+PLUME_HD float div_G(const Cfg& c, float a) {
+    return c.fastdiv ? (float)ddiv_const((double)a, c.G_d, c.inv_G_d) : fdiv(a, (float)c.G);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -211,6 +275,14 @@ struct ProceduralField {
             plume_cell(c, sx, sy, x, y, (double)z, (double)u, sin_tab[x], cos_tab[y], conc, tke);
         }
     }
+    // tke alone (env:57-61,63): the position update of the next step needs only this, not the Gaussian
+    PLUME_HD double eval_tke(const Cfg& c, int env_local, uint32_t env_gid, uint32_t episode, int x, int y) const {
+        (void)env_local;
+        float z, u;
+        field_noise(c, env_gid, episode, x, y, z, u);
+        const double wave = dmul(dmul(0.3, sin_tab[x]), cos_tab[y]);
+        return dmul(c.ti, dadd(dadd(fabs((double)z), wave), dmul(0.2, (double)u)));
+    }
     // PLUME_FLAG_FAST_REWARD: tke exactly as above (it drives the float64 position update, i.e. the flags),
     // the concentration in float32 (it only feeds the observation and the reward: fp32 rel 1e-5 bar)
     PLUME_HD void eval_fast(const Cfg& c, int env_local, uint32_t env_gid, uint32_t episode, double sx, double sy, int x,
@@ -254,6 +326,9 @@ struct MaterialisedField {
         conc = (float)conc_field[off];
         tke = (double)tke_field[off];
     }
+    PLUME_HD double eval_tke(const Cfg& c, int env_local, uint32_t, uint32_t, int x, int y) const {
+        return (double)tke_field[((size_t)env_local * c.G + x) * c.G + y];
+    }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -288,15 +363,32 @@ PLUME_HD double visit_denominator(int vc) {
     return dadd(dsqrt(dsqrt(dmul(dmul(v, v), v))), 1.0);
 }
 
+// (float)(vc**0.75 + 1) and (float)(step / max_steps): host tables when the caller provides them
+PLUME_HD float visit_denominator_f(const Cfg& c, int vc) {
+#if defined(__CUDA_ARCH__)
+    if (c.visit_denom_tab) return __ldg(c.visit_denom_tab + vc);
+#else
+    if (c.visit_denom_tab) return c.visit_denom_tab[vc];
+#endif
+    return (float)visit_denominator(vc);
+}
+PLUME_HD float step_fraction_f(const Cfg& c, int step) {
+#if defined(__CUDA_ARCH__)
+    if (c.step_frac_tab) return __ldg(c.step_frac_tab + step);
+#else
+    if (c.step_frac_tab) return c.step_frac_tab[step];
+#endif
+    return (float)ddiv((double)step, (double)c.max_steps);
+}
+
 // P3 _get_obs, env:71-87, given the field values at the float32 cell.
 PLUME_HD void make_obs(const Cfg& c, const EnvRegs& e, double cell_conc, double cell_tke, int visit_here,
                        float* obs, uint32_t env_gid = 0) {
-    const float g = (float)c.G;
-    obs[0] = fdiv(e.px, g);                                                   // env:81
-    obs[1] = fdiv(e.py, g);
-    obs[2] = (float)ddiv(cell_conc, c.conc_peak);                             // env:83
-    obs[3] = (float)ddiv(cell_tke, dmul(c.ti, 3.0));                          // env:84
-    obs[4] = (float)ddiv((double)e.step, (double)c.max_steps);                // env:85
+    obs[0] = div_G(c, e.px);                                                  // env:81
+    obs[1] = div_G(c, e.py);
+    obs[2] = (float)div_peak(c, cell_conc);                                   // env:83
+    obs[3] = (float)div_nine(c, cell_tke);                                    // env:84
+    obs[4] = step_fraction_f(c, e.step);                                      // env:85
     // env:78  min(visit / 5.0, 1.0): six possible values, folded at compile time (no float64 division)
     obs[5] = visit_here >= 5 ? 1.0f
              : (visit_here == 4 ? (float)(4.0 / 5.0)
@@ -325,12 +417,30 @@ PLUME_HD void observe(const Cfg& c, const Field& f, int env_local, uint32_t env_
     make_obs(c, e, conc, tke, vis, obs, env_gid);
 }
 
+// reached = ||agent_pos - source_pos|| <= radius (env:155-156) without the square root when the squared
+// distance is clearly on one side of radius^2 (relative margin 1e-12 >> the few ulp of the two roundings);
+// inside the margin the correctly rounded sqrt decides, so the flag is bit-identical.
+PLUME_HD bool reached_test(double s2, double radius, double& distance, bool need_distance) {
+    if (!need_distance) {
+        const double r2 = dmul(radius, radius);
+        if (s2 < dmul(r2, 1.0 - 1e-12)) return true;
+        if (s2 > dmul(r2, 1.0 + 1e-12)) return false;
+    }
+    distance = dsqrt(s2);
+    return distance <= radius;
+}
+
 // P2 MethaneEnv.step, env:89-178.  `visited` points at this env's PLUME_VISIT_STRIDE counters.
-// prev_conc/prev_tke: field at the float32 cell before the move (env:93-95,105-108).
-template <typename Field>
+// prev_tke: tke at the float32 cell before the move (env:105-108).  prev_conc_known / prev_cell_conc: the
+// concentration there (env:93-95) if the caller has it; otherwise it is evaluated on demand -- the code model
+// needs it only inside the boundary band.  kDistance = false skips the sqrt of env:155 wherever the reached
+// test is decided without it (out.distance is then undefined).
+template <bool kDistance = true, typename Field>
 PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env_gid, EnvRegs& e, uint16_t* visited,
-                       int action, double z0, double z1, double prev_cell_conc, double prev_cell_tke,
-                       StepResult& out) {
+                       int action, double z0, double z1, bool prev_conc_known, double prev_cell_conc,
+                       double prev_cell_tke, StepResult& out) {
+    int ppx, ppy;
+    cell32_of(c, e, ppx, ppy);                                                // env:93 (before the move)
     e.step += 1;                                                              // env:90
     // env:98-102
     const double ms = c.move_step;
@@ -343,10 +453,9 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     // -0.15 * (1 - ||d|| / move_step): ||d|| is exactly 0 or move_step, so the product is -0.15 or -0.0
     const double move_penalty = (action == 0) ? -0.15 : -0.0;
     // env:105-108   move_step*0.2*(randn(2)*tke/(TI*3))
-    const double nine = dmul(c.ti, 3.0);
     const double gain = dmul(ms, 0.2);
-    const double tx = dmul(gain, ddiv(dmul(z0, prev_cell_tke), nine));
-    const double ty = dmul(gain, ddiv(dmul(z1, prev_cell_tke), nine));
+    const double tx = dmul(gain, div_nine(c, dmul(z0, prev_cell_tke)));
+    const double ty = dmul(gain, div_nine(c, dmul(z1, prev_cell_tke)));
     // env:111-113
     double nx = dadd(dadd((double)e.px, dx), tx);
     double ny = dadd(dadd((double)e.py, dy), ty);
@@ -373,8 +482,12 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     const bool need_conc = c.plume_model == PLUME_MODEL_DISPERSION;
     double prev_conc = 0.0;
     if (need_conc || vmin < dmul(dadd(c.bnd_start, 1e-3), G)) {
-        prev_conc = ddiv(prev_cell_conc, c.conc_peak);                        // env:95
-        cur_conc = ddiv(conc64, c.conc_peak);
+        if (!prev_conc_known) {
+            double unused;
+            f.eval(c, env_local, env_gid, e.episode, e.sx, e.sy, ppx, ppy, prev_cell_conc, unused);
+        }
+        prev_conc = div_peak(c, prev_cell_conc);                              // env:95
+        cur_conc = div_peak(c, conc64);
         const double grad = ddiv(dsub(cur_conc, prev_conc), dadd(dnorm, 1e-6));
         const double bd = ddiv(vmin, G);
         if (bd < c.bnd_start && grad < -0.01) {
@@ -388,9 +501,10 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     const int vc = (int)visited[slot] + 1;
     visited[slot] = (uint16_t)vc;
     // env:140-143
-    const int vis32 = visited[(ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size)];
+    const int slot32 = (ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size);
+    const int vis32 = slot32 == slot ? vc : (int)visited[slot32];
     make_obs(c, e, conc32, tke32, vis32, out.obs, env_gid);
-    const float explore = fdiv(fmul((float)e.ebonus, fsub(1.0f, out.obs[5])), (float)visit_denominator(vc));
+    const float explore = fdiv(fmul((float)e.ebonus, fsub(1.0f, out.obs[5])), visit_denominator_f(c, vc));
     // env:146-152 (numpy>=2 promotion: float32 terms, float64 from move_penalty on)
     const float conc_reward = fmul((float)c.conc_coef, out.obs[2]);
     const float tke_term = fmul((float)c.tke_factor, out.obs[3]);
@@ -416,8 +530,8 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
     }
     // env:155-158
     const double ex = dsub((double)e.px, e.sx), ey = dsub((double)e.py, e.sy);
-    const double distance = dsqrt(dadd(dmul(ex, ex), dmul(ey, ey)));
-    const bool reached = distance <= e.radius;
+    double distance = 0.0;
+    const bool reached = reached_test(dadd(dmul(ex, ex), dmul(ey, ey)), e.radius, distance, kDistance);
     if (reached) total = dadd(total, fmin(500.0, dmul(150.0, ddiv(c.initial_radius, e.radius))));
     out.reward = total;
     out.reached = reached;
@@ -437,10 +551,12 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
 // of the position, cells, visit counters, distance <= radius, step limit) is the float64 arithmetic of env_step,
 // line for line; the observation's concentration/tke entries and the reward terms are float32 with reciprocal
 // multiplies (north_star bar: fp32 rel 1e-5; measured ~1e-7).  prev_cell_conc is the float32 field value.
-template <typename Field>
+template <bool kDistance = true, typename Field>
 PLUME_HD void env_step_fast(const Cfg& c, const Field& f, int env_local, uint32_t env_gid, EnvRegs& e,
-                            uint16_t* visited, int action, double z0, double z1, float prev_cell_conc,
-                            double prev_cell_tke, StepResult& out) {
+                            uint16_t* visited, int action, double z0, double z1, bool prev_conc_known,
+                            float prev_cell_conc, double prev_cell_tke, StepResult& out) {
+    int ppx, ppy;
+    cell32_of(c, e, ppx, ppy);
     e.step += 1;                                                              // env:90
     const double ms = c.move_step;
     double dx = 0.0, dy = 0.0;
@@ -451,10 +567,9 @@ PLUME_HD void env_step_fast(const Cfg& c, const Field& f, int env_local, uint32_
     const float dnorm = (action == 0) ? 0.0f : (float)ms;
     const float move_penalty = (action == 0) ? -0.15f : 0.0f;                 // env:101-102
     // env:105-113, exact
-    const double nine = dmul(c.ti, 3.0);
     const double gain = dmul(ms, 0.2);
-    const double tx = dmul(gain, ddiv(dmul(z0, prev_cell_tke), nine));
-    const double ty = dmul(gain, ddiv(dmul(z1, prev_cell_tke), nine));
+    const double tx = dmul(gain, div_nine(c, dmul(z0, prev_cell_tke)));
+    const double ty = dmul(gain, div_nine(c, dmul(z1, prev_cell_tke)));
     double nx = dadd(dadd((double)e.px, dx), tx);
     double ny = dadd(dadd((double)e.py, dy), ty);
     nx = nx < 0.0 ? 0.0 : (nx > c.clip_hi ? c.clip_hi : nx);
@@ -471,33 +586,47 @@ PLUME_HD void env_step_fast(const Cfg& c, const Field& f, int env_local, uint32_
     float conc32 = conc64;
     double tke32 = tke64;
     if (ox != cx || oy != cy) f.eval_fast(c, env_local, env_gid, e.episode, e.sx, e.sy, ox, oy, conc32, tke32);
-    const float prev_conc = prev_cell_conc * c.inv_peak_f, cur_conc = conc64 * c.inv_peak_f;
-    const float grad = (cur_conc - prev_conc) / (dnorm + 1e-6f);
-    // env:121-131
+    // env:118-131 (the gradient only matters inside the boundary band, or for the README reward)
     const float fx = (float)nx, fy = (float)ny, G = (float)c.G;
     const float bd = fminf(fminf(fx, G - fx), fminf(fy, G - fy)) * c.inv_G_f;
-    float bpen = 0.0f;
-    if (bd < (float)c.bnd_start && grad < -0.01f) {
-        const float gap = (float)c.bnd_start - bd;
-        bpen = -(float)c.bnd_penalty * gap * gap;
+    float bpen = 0.0f, prev_conc = 0.0f, cur_conc = 0.0f;
+    if (c.plume_model == PLUME_MODEL_DISPERSION || bd < (float)c.bnd_start) {
+        if (!prev_conc_known) {
+            double unused;
+            f.eval_fast(c, env_local, env_gid, e.episode, e.sx, e.sy, ppx, ppy, prev_cell_conc, unused);
+        }
+        prev_conc = prev_cell_conc * c.inv_peak_f;
+        cur_conc = conc64 * c.inv_peak_f;
+        const float grad = (cur_conc - prev_conc) / (dnorm + 1e-6f);
+        if (bd < (float)c.bnd_start && grad < -0.01f) {
+            const float gap = (float)c.bnd_start - bd;
+            bpen = -(float)c.bnd_penalty * gap * gap;
+        }
     }
     // env:134-137: floor(nx / cell_size) == int(nx) / cell_size for 0 <= nx < G (integer divisor)
     const int gx = (int)nx / c.cell_size, gy = (int)ny / c.cell_size;
     const int slot = gx * PLUME_MAX_GRID_DIVISIONS + gy;
     const int vc = (int)visited[slot] + 1;
     visited[slot] = (uint16_t)vc;
-    const int vis32 = visited[(ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size)];
+    const int slot32 = (ox / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (oy / c.cell_size);
+    const int vis32 = slot32 == slot ? vc : (int)visited[slot32];
     // env:71-87
-    out.obs[0] = fdiv(e.px, G);
-    out.obs[1] = fdiv(e.py, G);
+    out.obs[0] = div_G(c, e.px);
+    out.obs[1] = div_G(c, e.py);
     out.obs[2] = conc32 * c.inv_peak_f;
     out.obs[3] = (float)tke32 * c.inv_nine_f;
-    out.obs[4] = fdiv((float)e.step, (float)c.max_steps);
+    out.obs[4] = step_fraction_f(c, e.step);
     out.obs[5] = fminf((float)vis32 * 0.2f, 1.0f);
     if (c.plume_model == PLUME_MODEL_DISPERSION) make_obs(c, e, (double)conc32, tke32, vis32, out.obs, env_gid);
     // env:140: vc ** 0.75 + 1
-    const float v3 = (float)vc * (float)vc * (float)vc;
-    const float explore = (float)e.ebonus * (1.0f - out.obs[5]) / (sqrtf(sqrtf(v3)) + 1.0f);
+    float denom;
+    if (c.visit_denom_tab) {
+        denom = visit_denominator_f(c, vc);
+    } else {
+        const float v3 = (float)vc * (float)vc * (float)vc;
+        denom = sqrtf(sqrtf(v3)) + 1.0f;
+    }
+    const float explore = (float)e.ebonus * (1.0f - out.obs[5]) / denom;
     const float conc_reward = (float)c.conc_coef * out.obs[2];
     const float tke_term = (float)c.tke_factor * out.obs[3];
     double total = (double)((((conc_reward + explore) + move_penalty) - tke_term) + bpen);    // env:146-152
@@ -518,8 +647,8 @@ PLUME_HD void env_step_fast(const Cfg& c, const Field& f, int env_local, uint32_
     }
     // env:155-161, exact
     const double ex = dsub((double)e.px, e.sx), ey = dsub((double)e.py, e.sy);
-    const double distance = dsqrt(dadd(dmul(ex, ex), dmul(ey, ey)));
-    const bool reached = distance <= e.radius;
+    double distance = 0.0;
+    const bool reached = reached_test(dadd(dmul(ex, ex), dmul(ey, ey)), e.radius, distance, kDistance);
     if (reached) total = dadd(total, fmin(500.0, dmul(150.0, ddiv(c.initial_radius, e.radius))));
     out.reward = total;
     out.reached = reached;

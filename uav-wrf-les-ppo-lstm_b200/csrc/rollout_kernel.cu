@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                     step_noise(c, gid, e, z0, z1);
                 }
                 if (a.buf.noise_out) reinterpret_cast<double2*>(a.buf.noise_out)[row + env] = make_double2(z0, z1);
-                if (fast) env_step_fast(c, field, env, gid, e, vis, action, z0, z1, (float)cell_conc, cell_tke, r);
-                else env_step(c, field, env, gid, e, vis, action, z0, z1, cell_conc, cell_tke, r);
+                if (fast) env_step_fast(c, field, env, gid, e, vis, action, z0, z1, true, (float)cell_conc, cell_tke, r);
+                else env_step(c, field, env, gid, e, vis, action, z0, z1, true, cell_conc, cell_tke, r);
                 cell_conc = r.cell_conc;
                 cell_tke = r.cell_tke;
                 // sliding window of obs[2] (= conc_field[int(x),int(y)]/100 as float32, evaluate_with_lstm.py:67-74)
@@ -208,6 +208,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
         // ---- persist the tile's state ----------------------------------------------------------------------
         if (owner) {
             store_env(a.st, env, e);
+            if (a.st.cell_tke && a.st.cell_key) {      // hand the carried tke to a following plume_env_step
+                int x, y;
+                cell32_of(c, e, x, y);
+                a.st.cell_tke[env] = cell_tke;
+                a.st.cell_key[env] = cell_key_of(c, x, y, e.episode);
+            }
             if (a.buf.window_fill) a.buf.window_fill[env] = fill;
             if (a.buf.conc_window && !defer)
                 for (int k = 0; k < W; ++k) a.buf.conc_window[(size_t)env * W + k] = win[k * 32 + tid];
@@ -261,7 +267,7 @@ extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state*
     }
     if (horizon <= 0 || st->n_envs <= 0) return 0;
     RolloutArgs a;
-    a.c = make_cfg(*cfg);
+    a.c = make_cfg(*cfg, *st);
     a.st = *st;
     a.mlp = mlp_params;
     a.buf = *buf;

@@ -20,6 +20,17 @@ from .config import FIELD_F32, FIELD_F64, FIELD_MODES, FIELD_PROCEDURAL, PlumeCo
 INFO_KEYS = ("concentration_reward", "explore_reward", "move_penalty", "tke_penalty", "boundary_penalty")
 
 
+def host_tables(cfg):
+    """The two per-step quantities of ``MethaneEnv.step`` that only depend on an integer, evaluated on the
+    host exactly as the reference does and handed to the kernels as float32 tables:
+    ``step_count / MAX_STEPS`` (environment.py:85, python int / int -> float64 -> float32) and
+    ``visit_count**0.75 + 1`` (environment.py:140, python int ** float -> C pow, weak float -> float32)."""
+    m = int(cfg.max_steps)
+    step_frac = (np.arange(m + 1, dtype=np.float64) / float(m)).astype(np.float32)
+    visit_denom = np.array([float(v) ** 0.75 + 1 for v in range(m + 2)], dtype=np.float64).astype(np.float32)
+    return np.ascontiguousarray(step_frac), np.ascontiguousarray(visit_denom)
+
+
 def _require_cuda(device) -> torch.device:
     device = torch.device(device)
     if device.type != "cuda" or not torch.cuda.is_available():
@@ -77,6 +88,12 @@ class VecMethaneEnv:
             g = np.arange(G)
             self.sin_tab = torch.from_numpy(np.sin(0.05 * g)).to(dev)          # environment.py:59
             self.cos_tab = torch.from_numpy(np.cos(0.07 * g)).to(dev)
+            sf, vd = host_tables(self.cfg)
+            self.step_frac_tab = torch.from_numpy(sf).to(dev)                  # environment.py:85
+            self.visit_denom_tab = torch.from_numpy(vd).to(dev)                # environment.py:140
+            # tke at the current float32 cell, carried from one step to the next (procedural mode)
+            self.cell_tke_t = z(torch.float64, N)
+            self.cell_key_t = z(torch.int32, N)
             self.conc_field_t = self.tke_field_t = None
             if self.field_mode in (FIELD_F32, FIELD_F64):
                 fdt = torch.float32 if self.field_mode == FIELD_F32 else torch.float64
@@ -94,7 +111,9 @@ class VecMethaneEnv:
             self.src_y.data_ptr(), self.step_count_t.data_ptr(), self.episode_idx.data_ptr(),
             self.visited_t.data_ptr(), self.radius_t.data_ptr(), self.explore_bonus_t.data_ptr(),
             _lib.ptr(self.conc_field_t), _lib.ptr(self.tke_field_t), self.sin_tab.data_ptr(),
-            self.cos_tab.data_ptr(), self.curriculum.data_ptr(), self.last_move_t.data_ptr())
+            self.cos_tab.data_ptr(), self.curriculum.data_ptr(), self.last_move_t.data_ptr(),
+            self.step_frac_tab.data_ptr(), self.visit_denom_tab.data_ptr(), self.cell_tke_t.data_ptr(),
+            self.cell_key_t.data_ptr())
         self.launches = 0
         self.reset()                                                           # environment.py:40
 

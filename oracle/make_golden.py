@@ -13,6 +13,7 @@ from __future__ import annotations
 import contextlib
 import io
 import os
+import sys
 
 import numpy as np
 import torch
@@ -153,7 +154,40 @@ def main():
     np.savez_compressed(os.path.join(OUT, "lstm_s7.npz"), **lstm_trace(7))
     np.savez_compressed(os.path.join(OUT, "curriculum_s3.npz"), **curriculum_trace(3))
     np.savez_compressed(os.path.join(OUT, "trend_s9.npz"), **trend_trace(9))
+    make_lstm_train(13)
+
+
+
+def make_lstm_train(seed: int = 13, n_episodes: int = 90, epochs: int = 8):
+    """N3 fixture: a synthetic training_data.nc record, the selected episodes, the initial weights, the epoch
+    orders and what the torch-CPU training loop (oracle/lstm_train_oracle.py, pinned bit-equal against the
+    reference's train() by tests/test_lstm_train_oracle.py) produces: every minibatch loss and gradient norm, the
+    first minibatch's gradient, the parameters after `epochs` epochs."""
+    import torch
+
+    from oracle import lstm_train_oracle as lo
+    nc = lo.synthetic_nc(n_episodes, seed=seed)
+    elig = lo.eligible_episodes(nc, 20)
+    sel = [int(elig[i]) for i in lo.select_episodes(len(elig), seed)]
+    f, l = lo.build_dataset(nc, sel)
+    torch.manual_seed(seed)
+    model = lo.PeakAndStopPredictor()
+    init = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    orders = np.stack([torch.randperm(len(l), generator=g).numpy() for _ in range(epochs)])
+    _, grad0 = lo.loss_and_grad(model, torch.from_numpy(f[orders[0][:64]]), torch.from_numpy(l[orders[0][:64]]))
+    res = lo.train(model, f, l, epochs=epochs, orders=orders)
+    out = {"selected": np.array(sel, np.int32), "features": f, "labels": l, "orders": orders,
+           "batch_losses": res["batch_losses"], "grad_norms": res["grad_norms"], "grad0": grad0.numpy(),
+           "epoch_means": np.array([h[0] for h in res["history"]])}
+    out.update({"nc_" + k: v for k, v in nc.items()})
+    out.update({"init_" + k: v for k, v in init.items()})
+    out.update({"final_" + k: v.numpy() for k, v in res["final"].items()})
+    np.savez_compressed(os.path.join(OUT, f"lstm_train_s{seed}.npz"), **out)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "lstm_train":
+        make_lstm_train(13)
+    else:
+        main()

@@ -156,7 +156,8 @@ def load_reference(version: str = "2.1") -> types.SimpleNamespace:
             _load("netcdf_writer.py", "netcdf_writer")
         train = _load(_TRAIN_SCRIPT[version], "train")
         extras = {}
-        for fname, key in (("evaluate_with_lstm.py", "evaluate_with_lstm"), ("evaluate_model.py", "evaluate_model")):
+        for fname, key in (("evaluate_with_lstm.py", "evaluate_with_lstm"), ("evaluate_model.py", "evaluate_model"),
+                           ("train_lstm.py", "train_lstm")):
             if os.path.exists(os.path.join(root, fname)):
                 try:
                     if key == "evaluate_with_lstm" and version == "2.1":
@@ -165,7 +166,7 @@ def load_reference(version: str = "2.1") -> types.SimpleNamespace:
                 except Exception as exc:  # pragma: no cover - optional pieces
                     extras[key] = exc
     finally:
-        for k in shadow + ["train", "evaluate_with_lstm", "evaluate_model", "check_gaussian"]:
+        for k in shadow + ["train", "evaluate_with_lstm", "evaluate_model", "check_gaussian", "train_lstm"]:
             if saved.get(k) is not None:
                 sys.modules[k] = saved[k]
             else:
@@ -187,3 +188,44 @@ def make_reference_env(version: str, feed) -> object:
     finally:
         pass  # the proxy stays installed: later reset()/step() calls keep drawing from `feed`
     return env
+
+
+class FakeNC:
+    """Stands in for ``netCDF4.Dataset`` (absent in this image) over a dict of numpy arrays with the
+    training_data.nc variable names: supports ``with``, ``nc[name]`` and ``name in nc.variables``, which is all
+    ``load_trajectory_segments`` (PPOV2.1/model.py:67-91) uses."""
+
+    def __init__(self, arrays: dict):
+        self.variables = dict(arrays)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def __getitem__(self, name):
+        return self.variables[name]
+
+
+class reference_modules:
+    """Context manager: while active, ``import config`` / ``import model`` inside reference code (e.g. the
+    function-local ``from config import GRID_SIZE`` of train_lstm.py:13) resolve to the loaded reference modules."""
+
+    def __init__(self, version: str = "2.1"):
+        self.ref = load_reference(version)
+        self.saved = {}
+
+    def __enter__(self):
+        for k, m in (("config", self.ref.config), ("model", self.ref.model)):
+            self.saved[k] = sys.modules.get(k)
+            sys.modules[k] = m
+        return self.ref
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)
+        return False

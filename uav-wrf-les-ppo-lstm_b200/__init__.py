@@ -14,10 +14,12 @@ from .learner import FusedAdam, PPOTrainer, UpdateWorkspace, compute_advantages,
 from .trainer import PlumeTrainer  # noqa: F401
 from .evaluate import EvalResult, ThresholdController, evaluate_policy  # noqa: F401
 from .trajectory_log import TrajectoryLogger  # noqa: F401
+from .lstm_train import LstmTrainer, build_dataset, eligible_episodes  # noqa: F401
 
 _update_model = update_model   # the reference's private name (train_ppo2.0.py:14)
 
 __all__ = ["PlumeConfig", "config_for", "MethaneEnv", "VecMethaneEnv", "PPOActorCritic", "PeakAndStopPredictor",
            "ConcentrationThresholdPredictor", "PPOBuffer", "RolloutEngine", "FusedAdam", "PPOTrainer",
            "UpdateWorkspace", "compute_advantages", "update_model", "PlumeTrainer", "EvalResult",
-           "ThresholdController", "evaluate_policy", "TrajectoryLogger"]
+           "ThresholdController", "evaluate_policy", "TrajectoryLogger", "LstmTrainer", "build_dataset",
+           "eligible_episodes"]

@@ -24,6 +24,13 @@ MLP_OFFSETS = {
     "critic.weight": (36104, (1, 128)), "critic.bias": (36232, (1,)),
 }
 MLP_PARAMS = 36236
+# flat layout of PeakAndStopPredictor(hidden 32) = named_parameters() order (include/plume_b200.h, N3)
+LSTM_TRAIN_OFFSETS = {
+    "lstm.weight_ih_l0": (0, (128, 1)), "lstm.weight_hh_l0": (128, (128, 32)), "lstm.bias_ih_l0": (4224, (128,)),
+    "lstm.bias_hh_l0": (4352, (128,)), "fc_peak.weight": (4480, (1, 32)), "fc_peak.bias": (4512, (1,)),
+    "fc_stop.0.weight": (4513, (1, 32)), "fc_stop.0.bias": (4545, (1,)),
+}
+LSTM_TRAIN_PARAMS = 4546
 
 _vp = C.c_void_p
 

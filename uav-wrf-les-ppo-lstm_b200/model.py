@@ -135,7 +135,34 @@ class PeakAndStopPredictor(nn.Module):
         self.lstm = nn.LSTM(input_dim, hidden_dim, num_layers=num_layers, batch_first=True)
         self.fc_peak = nn.Linear(hidden_dim, 1)
         self.fc_stop = nn.Sequential(nn.Linear(hidden_dim, 1), nn.Sigmoid())
+        self.flat = None
         self.to(torch.device(device))
+
+    def flatten_(self) -> torch.Tensor:
+        """Moves the eight parameters into one flat fp32 buffer (layout of include/plume_b200.h, = the
+        ``named_parameters()`` order) and re-points every ``nn.Parameter`` at its slice, so the training kernel
+        (csrc/lstm_train_kernels.cu) updates the tensors ``state_dict()`` returns.  Hidden size 32 only."""
+        if self.hidden_dim != 32:
+            raise ValueError("the training kernel implements the reference's hidden_dim=32 (train_lstm.py:85)")
+        dev = next(self.parameters()).device
+        if self.flat is not None and self.flat.device == dev:
+            return self.flat
+        flat = torch.zeros(_lib.LSTM_TRAIN_PARAMS, dtype=torch.float32, device=dev)
+        named = dict(self.named_parameters())
+        for name, (off, shape) in _lib.LSTM_TRAIN_OFFSETS.items():
+            p = named[name]
+            n = int(np.prod(shape))
+            flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = flat[off:off + n].view(shape)
+        self.flat = flat
+        return flat
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        if getattr(self, "flat", None) is not None:     # moved / cast: rebuild the flat view on the new storage
+            self.flat = None
+            self.flatten_()
+        return self
 
     def c_params(self, window: int = 20, threshold: float = 0.8) -> _lib.LstmParams:
         p = {k: v.detach() for k, v in self.named_parameters()}

@@ -197,21 +197,71 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
                                  "ms": ms, "envs": n1, "algorithmic_bytes": bytes_k1, "peak_source": peaks["source"]}
     del env
     torch.cuda.empty_cache()
-    # K2: procedural, 102 B per env-step (csrc/env_kernels.cu header) + 20 B info
+    # K2: procedural field.  Algorithmic bytes per env-step in the kernel's own layout (csrc/env_kernels.cu):
+    # read pos 8 + src 16 + step 4 + episode 4 + radius 8 + bonus 8 + action 4 + visit 2 + carried tke 8 + tag 4
+    # = 66, write pos 8 + step 4 + visit 2 + obs 24 + reward 8 + done 1 + reached 1 + carried tke 8 + tag 4 = 60,
+    # info 20  =>  146 B.  Timed as 20 back-to-back launches through the C ABI (CUDA events on the launch stream).
+    # `traffic` = DRAM bytes per launch of the 2^20-env run from the ncu capture (profiles/r1g_k2_ncu_summary.txt):
+    # the visit-table read-modify-write moves a whole 128 B line per env-step.
+    k2_bytes = 146
     for n2, fast in ((4096, False), (1 << 20, False), (1 << 20, True)):
         env = pb.VecMethaneEnv(n2, device=dev, field_mode="procedural", auto_reset=True, seed=2, fast_reward=fast)
         acts = torch.randint(0, 5, (n2,), dtype=torch.int32, device=dev)
-        for _ in range(3):
-            env.step(acts)
+        flags = pb._lib.FLAG_AUTO_RESET | (pb._lib.FLAG_FAST_REWARD if fast else 0)
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def step_call(reps=20):
+            for _ in range(reps):
+                lib.plume_env_step(C.byref(env.c_config), C.byref(env.c_state), acts.data_ptr(), None, flags,
+                                   env.obs.data_ptr(), env.reward.data_ptr(), env.done.data_ptr(),
+                                   env.reached.data_ptr(), env.info_t.data_ptr(), env.final_obs.data_ptr(), None, stream)
+        step_call(30)
         sync()
-        ms = min(timed(lambda: env.step(acts), sync) for _ in range(10))
-        b = n2 * 122
-        out[f"plume_step_{n2}" + ("_fast_reward" if fast else "")] = {"bound": "hbm", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": b / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "envs": n2,
-                                   "algorithmic_bytes": b, "env_steps_per_s": n2 / ms * 1e3,
-                                   "peak_source": peaks["source"]}
+        ms = min(timed(step_call, sync) for _ in range(5)) / 20
+        b = n2 * k2_bytes
+        out[f"plume_step_{n2}" + ("_fast_reward" if fast else "")] = {
+            "bound": "hbm" if n2 > 100000 else "latency", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": b / ms / 1e6 / peaks["hbm_gbs"],
+            "traffic": 290.2e6 if (n2 == 1 << 20 and not fast) else None, "ms": ms, "envs": n2,
+            "algorithmic_bytes": b, "env_steps_per_s": n2 / ms * 1e3, "peak_source": peaks["source"]}
         del env
         torch.cuda.empty_cache()
+    return out
+
+
+def lstm_train_aux(pb, torch, dev, cpu: bool) -> dict:
+    """N3 (train_lstm.py): optimiser steps/s of the one-launch forward + BPTT + clip + AdamW kernel at the
+    reference's shape (1000 episodes -> 2000 windows of 20, minibatch 64), and the same loop in torch on the host
+    cores (the oracle restatement, which is the reference's own torch code path)."""
+    n, T, B = 2000, 20, 64
+    g = torch.Generator().manual_seed(0)
+    feats = torch.rand(n, T, generator=g)
+    labels = torch.stack([torch.rand(n, generator=g), (torch.rand(n, generator=g) < 0.3).float()], dim=1)
+    head = pb.PeakAndStopPredictor(device=dev)
+    tr = pb.LstmTrainer(head, feats.to(dev), labels.to(dev), batch_size=B)
+    orders = [torch.randperm(n, generator=g) for _ in range(6)]
+    tr.train_epoch(orders[0])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for o in orders[1:]:
+        tr.train_epoch(o)
+    e1.record()
+    torch.cuda.synchronize()
+    steps = 5 * tr.n_batches
+    ms = e0.elapsed_time(e1)
+    out = {"optimizer_steps_per_s": steps / ms * 1e3, "us_per_step": 1e3 * ms / steps, "launches_per_step": 1,
+           "windows": n, "window": T, "minibatch": B, "final_epoch_loss": tr.history[-1][0],
+           "note": "includes the per-epoch loss read-back and the host-side plateau scheduler"}
+    if cpu:
+        from oracle import lstm_train_oracle as lo
+        torch.manual_seed(0)
+        ref = lo.PeakAndStopPredictor()
+        t0 = time.perf_counter()
+        lo.train(ref, feats, labels, epochs=2, batch_size=B, orders=orders[:2])
+        dt = time.perf_counter() - t0
+        out["cpu_optimizer_steps_per_s"] = 2 * tr.n_batches / dt
+        out["cpu_threads"] = torch.get_num_threads()
     return out
 
 
@@ -386,6 +436,7 @@ def run_cuda_arm(args) -> None:
             dist.destroy_process_group()
         return
     plume = plume_kernel_rooflines(pb, torch, peaks, dev) if not args.skip_aux else {}
+    lstm_aux = lstm_train_aux(pb, torch, dev, world == 1 and not args.skip_cpu) if not args.skip_aux else None
     cpu = cpu_baseline_single(args.cpu_steps) if (world == 1 and not args.skip_cpu) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -398,7 +449,8 @@ def run_cuda_arm(args) -> None:
                                               if trainer.comm is not None else "NCCL all-reduce")),
                        "l2_flush": "256 MB write between timed steps"},
             "rollout_env_steps_per_sec": rollout_value,
-            "roofline": roofline, "kernels": kernels, "plume_kernels": plume, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "kernels": kernels, "plume_kernels": plume, "lstm_train": lstm_aux,
+            "cpu_baseline": cpu, "clocks": clocks,
             "e2e": e2e, "gpu_launches": trainer.launches_per_iteration * args.steps, "rank_skew": skew}
     print(json.dumps(line), flush=True)
     if world > 1:

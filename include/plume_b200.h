@@ -107,10 +107,12 @@ typedef struct plume_env_state {
      * visit_denom_tab[v] = (float)(v**0.75 + 1), v in [0,max_steps+1] (environment.py:140). */
     const float* step_frac_tab;
     const float* visit_denom_tab;
-    /* procedural mode: tke_field at the float32 cell of the current position (the "prev" lookup of the next
-     * step, environment.py:93,106), tagged with (cell, episode) in cell_key so that a stale entry -- state
-     * edited from the host -- is recomputed, never trusted.  Zero-initialise cell_key. */
+    /* procedural mode: tke_field / conc_field at the float32 cell of the current position (the "prev" lookups
+     * of the next step, environment.py:93-95,106), tagged with (cell, episode) in cell_key so that a stale
+     * entry -- state edited from the host -- is recomputed, never trusted.  Zero-initialise cell_key; the
+     * concentration entry also depends on the source position: clear cell_key when src_x/src_y are edited. */
     double* cell_tke;
+    double* cell_conc;
     uint32_t* cell_key;
 } plume_env_state;
 

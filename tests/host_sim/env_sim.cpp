@@ -65,7 +65,7 @@ void sim_source(const plume_env_config* cfg, uint32_t gid, uint32_t episode, dou
     const Cfg c = make_cfg(*cfg);
     EnvRegs e{};
     e.episode = episode - 1;
-    uint16_t vis[PLUME_VISIT_STRIDE];
+    alignas(16) uint16_t vis[PLUME_VISIT_STRIDE];
     env_reset(c, gid, e, vis, nullptr, 50.0, 0.6);
     src[0] = e.sx; src[1] = e.sy;
 }

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     import uav_wrf_les_ppo_lstm_b200 as pb
     L = pb._lib
     assert C.sizeof(L.EnvConfig) == 4 * 4 + 9 * 8 + 8 + 8
-    assert C.sizeof(L.EnvState) == 8 + 19 * 8
+    assert C.sizeof(L.EnvState) == 8 + 20 * 8
     assert C.sizeof(L.LstmParams) == 16 + 8 * 8
     assert C.sizeof(L.RolloutBuffers) == 25 * 8
     assert C.sizeof(L.PpoBatch) == 7 * 8

@@ -49,7 +49,7 @@ class EnvState(C.Structure):
                 ("src_x", _vp), ("src_y", _vp), ("step_count", _vp), ("episode_idx", _vp), ("visited", _vp),
                 ("radius", _vp), ("explore_bonus", _vp), ("conc_field", _vp), ("tke_field", _vp),
                 ("sin_tab", _vp), ("cos_tab", _vp), ("curriculum", _vp), ("last_move", _vp),
-                ("step_frac_tab", _vp), ("visit_denom_tab", _vp), ("cell_tke", _vp), ("cell_key", _vp)]
+                ("step_frac_tab", _vp), ("visit_denom_tab", _vp), ("cell_tke", _vp), ("cell_conc", _vp), ("cell_key", _vp)]
 
 
 class LstmParams(C.Structure):

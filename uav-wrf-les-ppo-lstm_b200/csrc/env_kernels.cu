@@ -312,9 +312,10 @@ __global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) s
     uint16_t* vis = st.visited + (size_t)i * PLUME_VISIT_STRIDE;
     const int action = actions[i];
     // every load whose address does not depend on data is issued here, ahead of the first use
-    const bool cache = FieldTraits<Field>::kCacheTke && st.cell_tke && st.cell_key;
+    const bool cache = FieldTraits<Field>::kCacheTke && st.cell_tke && st.cell_conc && st.cell_key;
     const uint32_t cached_key = cache ? st.cell_key[i] : 0u;
     const double cached_tke = cache ? st.cell_tke[i] : 0.0;
+    const double cached_conc = cache ? st.cell_conc[i] : 0.0;
 
     double z0, z1;
     if (step_noise_in) {
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) s
     int px, py;
     cell32_of(c, e, px, py);
     double ptke = cached_tke;
-    if (!(cache && cached_key != 0u && cached_key == cell_key_of(c, px, py, e.episode)))
-        ptke = f.eval_tke(c, i, gid, e.episode, px, py);
+    const bool hit = cache && cached_key != 0u && cached_key == cell_key_of(c, px, py, e.episode);
+    if (!hit) ptke = f.eval_tke(c, i, gid, e.episode, px, py);
     // the visit-table line this step will most likely touch (cell of position + move, before the turbulence
     // offset): requested now so that its DRAM latency overlaps the Philox / field arithmetic below
     {
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) s
     }
 
     StepResult r;
-    if (fast) env_step_fast<false>(c, f, i, gid, e, vis, action, z0, z1, false, 0.0f, ptke, r);
-    else env_step<false>(c, f, i, gid, e, vis, action, z0, z1, false, 0.0, ptke, r);
+    if (fast) env_step_fast<false>(c, f, i, gid, e, vis, action, z0, z1, hit, (float)cached_conc, ptke, r);
+    else env_step<false>(c, f, i, gid, e, vis, action, z0, z1, hit, cached_conc, ptke, r);
 
     reward[i] = r.reward;
     done[i] = r.done ? 1 : 0;
@@ -362,9 +363,8 @@ __global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) s
             for (int k = 0; k < 6; ++k) final_obs[(size_t)i * 6 + k] = r.obs[k];
         }
         env_reset(c, gid, e, vis, nullptr, st.curriculum[0], st.curriculum[1]);
-        double conc0;
-        f.eval(c, i, gid, e.episode, e.sx, e.sy, 0, 0, conc0, r.cell_tke);     // agent_pos = (0,0), env:46
-        make_obs(c, e, conc0, r.cell_tke, 0, r.obs, gid);
+        f.eval(c, i, gid, e.episode, e.sx, e.sy, 0, 0, r.cell_conc, r.cell_tke);     // agent_pos = (0,0), env:46
+        make_obs(c, e, r.cell_conc, r.cell_tke, 0, r.obs, gid);
         was_reset = true;
     }
 #pragma unroll
@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) s
         int ox, oy;
         cell32_of(c, e, ox, oy);
         st.cell_tke[i] = r.cell_tke;
+        st.cell_conc[i] = r.cell_conc;
         st.cell_key[i] = cell_key_of(c, ox, oy, e.episode);
     }
 }

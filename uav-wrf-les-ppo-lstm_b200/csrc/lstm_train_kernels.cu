@@ -63,7 +63,14 @@ struct LstmTrainArgs {
     float* grad_out;         // [kLtParams] or NULL: the (unclipped) minibatch gradient
 };
 
-__device__ __forceinline__ float lt_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate activations on the critical path of a 20-step recurrence that runs one warp per scheduler: ex2.approx and
+// the fast divide (relative error ~3e-7, the same functions as the inference head in lstm_tile.cuh) instead of
+// expf / IEEE division / tanhf, whose 100+ dependent instructions per call dominated the first ncu capture.
+__device__ __forceinline__ float lt_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float lt_tanh(float x) {
+    const float t = __expf(-2.0f * fabsf(x));
+    return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -124,9 +131,9 @@ __global__ void __launch_bounds__(kLtThreads, 1) lstm_train_kernel(LstmTrainArgs
                     acc[g] = fmaf(wr[g][4 * k4 + 3], hv.w, acc[g]);
                 }
             }
-            const float gi = lt_sigmoid(acc[0]), gf = lt_sigmoid(acc[1]), gg = tanhf(acc[2]), go = lt_sigmoid(acc[3]);
+            const float gi = lt_sigmoid(acc[0]), gf = lt_sigmoid(acc[1]), gg = lt_tanh(acc[2]), go = lt_sigmoid(acc[3]);
             c = fmaf(gf, c, gi * gg);
-            h = go * tanhf(c);
+            h = go * lt_tanh(c);
             row[0 * kLtH + lane] = gi;
             row[1 * kLtH + lane] = gf;
             row[2 * kLtH + lane] = gg;
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lstm_train_kernel(LstmTrainArgs
     const float wp = a.params[kLtOffWp + lane], ws = a.params[kLtOffWs + lane];
     const float peak = warp_sum(wp * h) + a.params[kLtOffBp];
     const float logit = warp_sum(ws * h) + a.params[kLtOffBs];
-    const float p = lt_sigmoid(logit);
+    const float p = 1.0f / (1.0f + expf(-logit));          // once per sequence: the accurate form
     float dpeak = 0.0f, dlogit = 0.0f, loss = 0.0f;
     if (live) {
         const float y0 = a.labels[(size_t)sid * 2], y1 = a.labels[(size_t)sid * 2 + 1];
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lstm_train_kernel(LstmTrainArgs
             const float gi = row[lane], gf = row[kLtH + lane], gg = row[2 * kLtH + lane], go = row[3 * kLtH + lane];
             const float ct = row[4 * kLtH + lane];
             const float cprev = t > 0 ? row[4 * kLtH + lane - kLtRow] : 0.0f;
-            const float tc = tanhf(ct);
+            const float tc = lt_tanh(ct);
             const float d_o = dh * tc;
             dc = fmaf(dh * go, 1.0f - tc * tc, dc);
             const float d_i = dc * gg, d_g = dc * gi, d_f = dc * cprev;
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lstm_train_kernel(LstmTrainArgs
         for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
         float ax = 0.0f, ab = 0.0f;
         for (int w = 0; w < kLtWarps; ++w) {
+#pragma unroll 4
             for (int t = 0; t < T; ++t) {
                 const float* row = hist + ((size_t)w * T + t) * kLtRow;
                 const float d = row[r];
@@ -264,8 +272,10 @@ __global__ void __launch_bounds__(kLtThreads, 1) lstm_train_kernel(LstmTrainArgs
     for (int q = 0; q < kLtPerThread; ++q) {
         const int i = q * kLtThreads + tid;
         float s = 0.0f;
-        if (i < kLtParams)
+        if (i < kLtParams) {
+#pragma unroll 8
             for (unsigned int cta = 0; cta < gridDim.x; ++cta) s += __ldcg(a.partial + (size_t)cta * kLtStride + i);
+        }
         g[q] = s;
         ss += (double)s * (double)s;
         if (a.grad_out && i < kLtParams) a.grad_out[i] = s;

@@ -131,6 +131,7 @@ struct Cfg {
     int32_t fastdiv;                 // 1 = the reciprocals below passed the host check
     double nine, inv_nine, inv_peak;
     double G_d, inv_G_d;             // float / G goes through the double quotient (see div_G)
+    double ms_eps, inv_ms_eps, inv_eps;   // move_step + 1e-6 and the reciprocals of the two conc_gradient divisors
     // optional host tables (NULL = evaluate): (float)(step / max_steps) and (float)(count**0.75 + 1)
     const float* step_frac_tab;
     const float* visit_denom_tab;
@@ -173,7 +174,11 @@ inline Cfg make_cfg(const plume_env_config& c) {
     o.inv_peak = 1.0 / c.conc_peak;
     o.G_d = (double)c.grid_size;
     o.inv_G_d = 1.0 / o.G_d;
-    o.fastdiv = (reciprocal_ok(o.nine) && reciprocal_ok(c.conc_peak) && reciprocal_ok(o.G_d)) ? 1 : 0;
+    o.ms_eps = o.move_step + 1e-6;                         // env:119
+    o.inv_ms_eps = 1.0 / o.ms_eps;
+    o.inv_eps = 1.0 / 1e-6;
+    o.fastdiv = (reciprocal_ok(o.nine) && reciprocal_ok(c.conc_peak) && reciprocal_ok(o.G_d) &&
+                 reciprocal_ok(o.ms_eps) && reciprocal_ok(1e-6)) ? 1 : 0;
     o.step_frac_tab = nullptr;
     o.visit_denom_tab = nullptr;
     return o;
@@ -488,8 +493,11 @@ PLUME_HD void env_step(const Cfg& c, const Field& f, int env_local, uint32_t env
         }
         prev_conc = div_peak(c, prev_cell_conc);                              // env:95
         cur_conc = div_peak(c, conc64);
-        const double grad = ddiv(dsub(cur_conc, prev_conc), dadd(dnorm, 1e-6));
-        const double bd = ddiv(vmin, G);
+        // conc_gradient (env:119): the divisor ||d|| + 1e-6 is one of two constants
+        const double dc = dsub(cur_conc, prev_conc);
+        const double grad = !c.fastdiv ? ddiv(dc, dadd(dnorm, 1e-6))
+                            : (action == 0 ? ddiv_const(dc, 1e-6, c.inv_eps) : ddiv_const(dc, c.ms_eps, c.inv_ms_eps));
+        const double bd = c.fastdiv ? ddiv_const(vmin, c.G_d, c.inv_G_d) : ddiv(vmin, G);
         if (bd < c.bnd_start && grad < -0.01) {
             const double gap = dsub(c.bnd_start, bd);
             bpen = dmul(-c.bnd_penalty, dmul(gap, gap));
@@ -686,7 +694,13 @@ PLUME_HD void env_reset(const Cfg& c, uint32_t env_gid, EnvRegs& e, uint16_t* vi
     e.last_move = 0;
     e.radius = radius;
     e.ebonus = ebonus;
-    for (int i = 0; i < PLUME_VISIT_STRIDE; ++i) visited[i] = 0;              // env:49
+    // env:49 (the per-env table is PLUME_VISIT_STRIDE * 2 = 208 B = 13 x 16 B, 16-byte aligned)
+    static_assert(PLUME_VISIT_STRIDE % 8 == 0, "visit table rows are cleared 16 bytes at a time");
+    struct alignas(16) Zero16 {
+        uint64_t a, b;
+    };
+    Zero16* v16 = reinterpret_cast<Zero16*>(visited);
+    for (int i = 0; i < PLUME_VISIT_STRIDE / 8; ++i) v16[i] = Zero16{0ull, 0ull};
 }
 
 PLUME_HD void step_noise(const Cfg& c, uint32_t env_gid, const EnvRegs& e, double& z0, double& z1) {

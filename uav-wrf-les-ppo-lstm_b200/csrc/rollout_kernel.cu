@@ -35,7 +35,10 @@ struct RolloutSmem {
     static constexpr int total = misc + 96;     // [32] stop prob, [32] peak, [32] scratch
 };
 
-template <int H>
+// kSpec (as in the K2 step kernel): 0 = plume model / reward mode / division mode read at run time,
+// 1 = reference code model with exact float64 reward, 2 = code model with PLUME_FLAG_FAST_REWARD; 1 and 2 use the
+// constant divisions make_cfg() validated and contain only the per-env code of their mode.
+template <int H, int kSpec>
 __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) {
     extern __shared__ __align__(16) float sm[];
     constexpr int HH = H > 0 ? H : 32;
@@ -45,7 +48,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     float* s_stop = sm + RolloutSmem<H>::misc;
     float* s_peak = s_stop + 32;
 
-    const Cfg& c = a.c;
+    Cfg c = a.c;
+    if (kSpec != 0) {               // constant-propagated through the inlined per-env code
+        c.plume_model = PLUME_MODEL_ISOTROPIC;
+        c.fastdiv = 1;
+    }
     const int tid = threadIdx.x;
     const int N = a.st.n_envs;
     const int W = a.lstm.window;
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     const bool stop_terminates = (a.flags & PLUME_FLAG_STOP_TERMINATES) != 0;
     // deferred stop head: only record the window inputs; plume_stop_head_segment does the rest
     const bool defer = (a.flags & PLUME_FLAG_DEFER_STOP_HEAD) != 0;
-    const bool fast = (a.flags & PLUME_FLAG_FAST_REWARD) != 0;     // float32 reward terms, float64 flags
+    const bool fast = kSpec == 0 ? (a.flags & PLUME_FLAG_FAST_REWARD) != 0 : kSpec == 2;   // float32 reward terms
 
     const int tiles = (N + kTileM - 1) / kTileM;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -208,10 +215,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
         // ---- persist the tile's state ----------------------------------------------------------------------
         if (owner) {
             store_env(a.st, env, e);
-            if (a.st.cell_tke && a.st.cell_key) {      // hand the carried tke to a following plume_env_step
+            if (a.st.cell_tke && a.st.cell_conc && a.st.cell_key) {   // hand the carried cell to a following plume_env_step
                 int x, y;
                 cell32_of(c, e, x, y);
                 a.st.cell_tke[env] = cell_tke;
+                a.st.cell_conc[env] = cell_conc;
                 a.st.cell_key[env] = cell_key_of(c, x, y, e.episode);
             }
             if (a.buf.window_fill) a.buf.window_fill[env] = fill;
@@ -225,12 +233,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     }
 }
 
-template <int H>
-static int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
+template <int H, int kSpec>
+static int launch_rollout_spec(const RolloutArgs& a, cudaStream_t s) {
     static bool configured = false;
     const int smem = RolloutSmem<H>::total * (int)sizeof(float);
     if (!configured) {
-        if (cudaFuncSetAttribute(rollout_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(rollout_kernel<H, kSpec>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
             return fail("rollout kernel: cannot reserve %d B of shared memory", smem);
         configured = true;
     }
@@ -238,9 +247,16 @@ static int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
     int grid = sm_count();
     if (grid <= 0) return fail("no CUDA device");
     if (tiles < grid) grid = tiles;
-    rollout_kernel<H><<<grid, kMlpThreads, smem, s>>>(a);
+    rollout_kernel<H, kSpec><<<grid, kMlpThreads, smem, s>>>(a);
     if (cudaGetLastError() != cudaSuccess) return fail("rollout kernel launch failed");
     return 0;
+}
+
+template <int H>
+static int launch_rollout(const RolloutArgs& a, cudaStream_t s) {
+    if (a.c.plume_model == PLUME_MODEL_ISOTROPIC && a.c.fastdiv)
+        return (a.flags & PLUME_FLAG_FAST_REWARD) ? launch_rollout_spec<H, 2>(a, s) : launch_rollout_spec<H, 1>(a, s);
+    return launch_rollout_spec<H, 0>(a, s);
 }
 
 }  // namespace plume

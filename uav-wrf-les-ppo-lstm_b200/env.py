@@ -93,6 +93,7 @@ class VecMethaneEnv:
             self.visit_denom_tab = torch.from_numpy(vd).to(dev)                # environment.py:140
             # tke at the current float32 cell, carried from one step to the next (procedural mode)
             self.cell_tke_t = z(torch.float64, N)
+            self.cell_conc_t = z(torch.float64, N)
             self.cell_key_t = z(torch.int32, N)
             self.conc_field_t = self.tke_field_t = None
             if self.field_mode in (FIELD_F32, FIELD_F64):
@@ -113,7 +114,7 @@ class VecMethaneEnv:
             _lib.ptr(self.conc_field_t), _lib.ptr(self.tke_field_t), self.sin_tab.data_ptr(),
             self.cos_tab.data_ptr(), self.curriculum.data_ptr(), self.last_move_t.data_ptr(),
             self.step_frac_tab.data_ptr(), self.visit_denom_tab.data_ptr(), self.cell_tke_t.data_ptr(),
-            self.cell_key_t.data_ptr())
+            self.cell_conc_t.data_ptr(), self.cell_key_t.data_ptr())
         self.launches = 0
         self.reset()                                                           # environment.py:40
 
@@ -183,6 +184,7 @@ class VecMethaneEnv:
         sel = slice(None) if ids is None else ids.long()
         self.src_x[sel] = s[:, 0]
         self.src_y[sel] = s[:, 1]
+        self.cell_key_t[sel] = 0          # the carried concentration belongs to the old source
 
     def observe(self) -> torch.Tensor:
         """P3 ``_get_obs`` for every env, [N,6] float32."""

@@ -201,7 +201,7 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
     # read pos 8 + src 16 + step 4 + episode 4 + radius 8 + bonus 8 + action 4 + visit 2 + carried tke 8 + tag 4
     # = 66, write pos 8 + step 4 + visit 2 + obs 24 + reward 8 + done 1 + reached 1 + carried tke 8 + tag 4 = 60,
     # info 20  =>  146 B.  Timed as 20 back-to-back launches through the C ABI (CUDA events on the launch stream).
-    # `traffic` = DRAM bytes per launch of the 2^20-env run from the ncu capture (profiles/r1g_k2_ncu_summary.txt):
+    # `traffic` = DRAM bytes per launch of the 2^20-env run from the ncu capture (profiles/r1h_k2_ncu_summary.txt):
     # the visit-table read-modify-write moves a whole 128 B line per env-step.
     k2_bytes = 146
     for n2, fast in ((4096, False), (1 << 20, False), (1 << 20, True)):
@@ -222,7 +222,7 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
         out[f"plume_step_{n2}" + ("_fast_reward" if fast else "")] = {
             "bound": "hbm" if n2 > 100000 else "latency", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": b / ms / 1e6 / peaks["hbm_gbs"],
-            "traffic": 290.2e6 if (n2 == 1 << 20 and not fast) else None, "ms": ms, "envs": n2,
+            "traffic": 316.7e6 if (n2 == 1 << 20 and not fast) else None, "ms": ms, "envs": n2,
             "algorithmic_bytes": b, "env_steps_per_s": n2 / ms * 1e3, "peak_source": peaks["source"]}
         del env
         torch.cuda.empty_cache()

@@ -284,6 +284,9 @@ __global__ void observe_kernel(Cfg c, plume_env_state st, Field f, float* obs) {
 #ifndef PLUME_STEP_MIN_BLOCKS
 #define PLUME_STEP_MIN_BLOCKS 8
 #endif
+#ifndef PLUME_STEP_THREADS
+#define PLUME_STEP_THREADS 128
+#endif
 template <typename Field>
 struct FieldTraits {
     static constexpr bool kCacheTke = false;
@@ -294,7 +297,7 @@ struct FieldTraits<ProceduralField> {
 };
 
 template <typename Field, int kSpec>
-__global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) step_kernel(Cfg c_in, plume_env_state st, Field f, const int32_t* actions,
+__global__ void __launch_bounds__(PLUME_STEP_THREADS, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) step_kernel(Cfg c_in, plume_env_state st, Field f, const int32_t* actions,
                                                    const double* step_noise_in, uint32_t flags, float* obs,
                                                    double* reward, uint8_t* done, uint8_t* reached, float* info,
                                                    float* final_obs, double* noise_out) {
@@ -338,7 +341,9 @@ __global__ void __launch_bounds__(128, kSpec != 0 ? PLUME_STEP_MIN_BLOCKS : 1) s
         const int ms = (int)c.move_step;
         const int qx = clip_cell(px + (action == 3 ? ms : (action == 4 ? -ms : 0)), c.G) / c.cell_size;
         const int qy = clip_cell(py + (action == 1 ? ms : (action == 2 ? -ms : 0)), c.G) / c.cell_size;
+#ifndef PLUME_STEP_NO_PREFETCH
         asm volatile("prefetch.global.L2 [%0];" ::"l"(vis + qx * PLUME_MAX_GRID_DIVISIONS + qy));
+#endif
     }
 
     StepResult r;
@@ -528,10 +533,10 @@ extern "C" int plume_env_step(const plume_env_config* cfg, const plume_env_state
         return fail("auto-reset inside the step needs the procedural field mode "
                     "(materialised fields are regenerated by plume_generate_fields)");
     const Cfg c = make_cfg(*cfg, *st);
-    const int blocks = (st->n_envs + 127) / 128;
+    const int blocks = (st->n_envs + PLUME_STEP_THREADS - 1) / PLUME_STEP_THREADS;
     cudaStream_t s = as_stream(stream);
 #define PLUME_STEP_LAUNCH(FIELD, SPEC, ...)                                                                         \
-    step_kernel<FIELD, SPEC><<<blocks, 128, 0, s>>>(c, *st, FIELD{__VA_ARGS__}, actions, step_noise_in, flags, obs, \
+    step_kernel<FIELD, SPEC><<<blocks, PLUME_STEP_THREADS, 0, s>>>(c, *st, FIELD{__VA_ARGS__}, actions, step_noise_in, flags, obs, \
                                                     reward, done, reached, info, final_obs, noise_out)
     if (cfg->field_mode == PLUME_FIELD_PROCEDURAL) {
         const bool spec = c.plume_model == PLUME_MODEL_ISOTROPIC && c.fastdiv;

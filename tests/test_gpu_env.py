@@ -186,6 +186,42 @@ def test_auto_reset_step():
     assert np.all(env.radius_t.cpu().numpy() == 200.0)
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_carried_cell_values_are_transparent(fast):
+    """K2 carries tke / concentration of the current cell from one step to the next (cell_tke, cell_conc, tagged by
+    cell_key).  An env whose tags are wiped before every step (everything recomputed from the Philox stream) must
+    produce bit-identical results, also across auto-resets, host edits of the position and of the source."""
+    n, T = 2048, 160
+    mk = lambda: pb().VecMethaneEnv(n, version="2.1", seed=5, field_mode="procedural", auto_reset=True,
+                                    fast_reward=fast)
+    a, b = mk(), mk()
+    for env in (a, b):
+        env.curriculum[0] = 60.0
+        env.reset()
+    rng = np.random.default_rng(1)
+    hits = 0
+    for t in range(T):
+        act = torch.from_numpy(rng.integers(0, 5, n).astype(np.int32))
+        if t == 50:                     # host moves half of the agents: the tags of `a` no longer match
+            for env in (a, b):
+                env.pos_x[: n // 2] = 123.25
+                env.pos_y[: n // 2] = 77.5
+        if t == 90:                     # host moves the sources: set_source drops the carried concentration
+            src = np.stack([np.full(n, 300.0), np.full(n, 40.0)], axis=1)
+            a.set_source(src)
+            b.set_source(src)
+        b.cell_key_t.zero_()
+        hits += int((a.cell_key_t != 0).sum().item())
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+        for k in ia:
+            assert torch.equal(ia[k], ib[k]), (t, k)
+        assert torch.equal(a.visited, b.visited) and torch.equal(a.agent_pos, b.agent_pos)
+    assert hits >= n * (T - 2)          # the carried values were in use in `a` (not after reset / set_source)
+    assert int(a.episode_idx.max().item()) > 2
+
+
 def test_errors_are_loud():
     m = pb()
     with pytest.raises(ValueError):

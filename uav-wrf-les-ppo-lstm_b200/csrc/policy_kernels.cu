@@ -1,7 +1,7 @@
 // policy_kernels.cu -- K3: PPOActorCritic.forward (model.py:38-46) and the Categorical
 // sample / log_prob of the rollout (train_ppo2.0.py:158-162,185) for a batch of observations.
 // One CTA per SM (weights stay in shared memory), grid-stride over 32-sample tiles.
-#include "mlp_tile.cuh"
+#include "mlp_tc_tile.cuh"
 
 namespace plume {
 
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
 policy_kernel(const float* __restrict__ params, const float* __restrict__ x, int batch, float* __restrict__ probs_out,
               float* __restrict__ value_out, int32_t* nan_flag, ActArgs act, Cfg c, plume_env_state st) {
     extern __shared__ __align__(16) float sm[];
-    mlp_load_weights(sm, params);
+    policy_load_weights(sm, params);
     const int tid = threadIdx.x;
     const int tiles = (batch + kTileM - 1) / kTileM;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -27,12 +27,12 @@ policy_kernel(const float* __restrict__ params, const float* __restrict__ x, int
         {
             const int s = tid >> 3, k = tid & 7;
             const int row = base + s;
-            sm[MlpSmem::x + tid] = (k < 6 && row < batch) ? x[(size_t)row * 6 + k] : 0.0f;
+            sm[PolicySmem::x + tid] = (k < 6 && row < batch) ? x[(size_t)row * 6 + k] : 0.0f;
         }
-        mlp_forward_tile(sm);
+        policy_forward_tile(sm);
         if (tid < kTileM && base + tid < batch) {
             const int row = base + tid;
-            const float* o = sm + MlpSmem::out + tid * 8;
+            const float* o = sm + PolicySmem::out + tid * 8;
             bool bad = false;
 #pragma unroll
             for (int k = 0; k < 5; ++k) bad |= isnan(o[k]);
@@ -65,7 +65,7 @@ static int launch_policy(const float* params, const float* x, int batch, float* 
                          int32_t* nan_flag, const ActArgs& act, const Cfg& c, const plume_env_state& st,
                          cudaStream_t s) {
     static bool configured = false;
-    const int smem = MlpSmem::total * (int)sizeof(float);
+    const int smem = PolicySmem::total * (int)sizeof(float);
     if (!configured) {
         if (cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return fail("policy kernel: cannot reserve %d B of shared memory", smem);

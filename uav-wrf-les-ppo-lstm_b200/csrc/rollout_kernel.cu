@@ -4,7 +4,7 @@
 //     MethaneEnv.step                        (environment.py:89-178)
 //     LSTM stop head over the sliding window (evaluate_with_lstm.py:67-80), trend features
 //     auto-reset of finished episodes        (environment.py:42-50)
-// without returning to the host: MLP (145 KB) and LSTM (17 KB) weights stay in shared memory,
+// without returning to the host: MLP (fp16 hi/lo split, 141 KB) and LSTM (17 KB) weights stay in shared memory,
 // the per-env state stays in the registers of the tile's first warp, and only the [T][N]
 // rollout buffers are written to HBM.  Procedural field mode only (cells are evaluated from
 // the Philox stream, so a reset costs O(1)).
@@ -13,7 +13,7 @@
 // logp 4 + done 4 + reached 1 = 45 B written (+ stop 9, info 20, episode 4 when requested),
 // visit-table RMW 4 B; nothing else touches HBM.
 #include "lstm_tile.cuh"
-#include "mlp_tile.cuh"
+#include "mlp_tc_tile.cuh"
 
 namespace plume {
 
@@ -30,7 +30,7 @@ struct RolloutArgs {
 
 template <int H>
 struct RolloutSmem {
-    static constexpr int lstm = MlpSmem::total;
+    static constexpr int lstm = PolicySmem::total;
     static constexpr int misc = lstm + (H > 0 ? LstmSmem<(H > 0 ? H : 32)>::total : kLstmMaxSteps * 32);
     static constexpr int total = misc + 96;     // [32] stop prob, [32] peak, [32] scratch
 };
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     const int tid = threadIdx.x;
     const int N = a.st.n_envs;
     const int W = a.lstm.window;
-    mlp_load_weights(sm, a.mlp);
+    policy_load_weights(sm, a.mlp);
     if (H > 0) {
         const LstmWeights lw{a.lstm.w_ih, a.lstm.w_hh, a.lstm.b_ih, a.lstm.b_hh,
                              a.lstm.w_peak, a.lstm.b_peak, a.lstm.w_stop, a.lstm.b_stop};
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 fill = a.buf.window_fill ? a.buf.window_fill[env] : 0;
             }
 #pragma unroll
-            for (int k = 0; k < 6; ++k) sm[MlpSmem::x + tid * 8 + k] = o[k];
-            sm[MlpSmem::x + tid * 8 + 6] = 0.0f;
-            sm[MlpSmem::x + tid * 8 + 7] = 0.0f;
+            for (int k = 0; k < 6; ++k) sm[PolicySmem::x + tid * 8 + k] = o[k];
+            sm[PolicySmem::x + tid * 8 + 6] = 0.0f;
+            sm[PolicySmem::x + tid * 8 + 7] = 0.0f;
             if (!defer)
                 for (int k = 0; k < W; ++k)
                     win[k * 32 + tid] = (owner && a.buf.conc_window) ? a.buf.conc_window[(size_t)env * W + k] : 0.0f;
@@ -107,16 +107,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
             __syncthreads();
             if (tid < 6 * kTileM) {
                 const int s = tid / 6, k = tid - s * 6;
-                if (tile * kTileM + s < N) a.buf.obs[(row + (size_t)tile * kTileM) * 6 + tid] = sm[MlpSmem::x + s * 8 + k];
+                if (tile * kTileM + s < N) a.buf.obs[(row + (size_t)tile * kTileM) * 6 + tid] = sm[PolicySmem::x + s * 8 + k];
             }
-            mlp_forward_tile<false>(sm);
+            policy_forward_tile(sm);
             // ---- part A: sample, step, push the window ------------------------------------------------
             StepResult r{};
             int action = 0;
             float logp = 0.0f, value = 0.0f;
             uint32_t ep_of_transition = e.episode;
             if (owner) {
-                const float* o = sm + MlpSmem::out + tid * 8;
+                const float* o = sm + PolicySmem::out + tid * 8;
                 bool bad = false;
 #pragma unroll
                 for (int k = 0; k < 5; ++k) bad |= isnan(o[k]);
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                     make_obs(c, e, cell_conc, cell_tke, 0, r.obs, gid);
                 }
 #pragma unroll
-                for (int k = 0; k < 6; ++k) sm[MlpSmem::x + tid * 8 + k] = r.obs[k];
+                for (int k = 0; k < 6; ++k) sm[PolicySmem::x + tid * 8 + k] = r.obs[k];
             }
         }
         // ---- persist the tile's state ----------------------------------------------------------------------
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 for (int k = 0; k < W; ++k) a.buf.conc_window[(size_t)env * W + k] = win[k * 32 + tid];
             if (a.buf.last_obs) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) a.buf.last_obs[(size_t)env * 6 + k] = sm[MlpSmem::x + tid * 8 + k];
+                for (int k = 0; k < 6; ++k) a.buf.last_obs[(size_t)env * 6 + k] = sm[PolicySmem::x + tid * 8 + k];
             }
         }
     }

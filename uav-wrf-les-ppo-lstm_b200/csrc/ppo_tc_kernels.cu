@@ -108,6 +108,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __shared__ uint32_t tmem_slot;
     __shared__ float cta_acc[48];         // per-CTA sums of the per-sample scalars (see the flush)
     __shared__ double cta_loss[4];
+    // LayerNorm-1 variance as a quadratic form of the 6 inputs: sum_o z_o^2 = q0 + sum_k q1[k] x_k + sum_{k<=l} q2[kl] x_k x_l
+    // with z_o = b_o + sum_k x_k w_ko from the CENTRED weights (so mean_o z_o = 0); 28 coefficients per launch
+    __shared__ double ln1q[28];
 
     constexpr int G = kTcGroups;
     constexpr int CW = 128 / G;           // columns per thread in the TMEM epilogues (32)
@@ -167,6 +170,28 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         if (tid < 8)
             sm[TcSmem::bh + tid] = tid < 5 ? params[PLUME_OFF_BA + tid] : (tid == 5 ? params[PLUME_OFF_BC] : 0.0f);
+    }
+    __syncthreads();
+    if (tid < 28) {
+        int k = -1, l = -1;                 // tid 0: |b|^2; 1..6: 2 b.w_k; 7..27: (k <= l) pairs
+        if (tid >= 1 && tid <= 6) k = tid - 1;
+        if (tid >= 7) {
+            int r = tid - 7;
+            k = 0;
+            while (r >= 6 - k) {
+                r -= 6 - k;
+                ++k;
+            }
+            l = k + r;
+        }
+        double acc = 0.0;
+        for (int o = 0; o < 256; ++o) {
+            const double b = (double)sm[TcSmem::P1 + o];
+            const double wk = k >= 0 ? (double)sm[TcSmem::W1c + k * 256 + o] : 0.0;
+            const double wl = l >= 0 ? (double)sm[TcSmem::W1c + l * 256 + o] : 0.0;
+            acc += tid == 0 ? b * b : (tid <= 6 ? 2.0 * b * wk : (k == l ? wk * wl : 2.0 * wk * wl));
+        }
+        ln1q[tid] = acc;
     }
     __syncthreads();
 
@@ -299,45 +324,33 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             r_vold = q2.x;
             r_lpold = q2.y;
             r_act = __float_as_int(q2.z);
+            // LayerNorm-1 rstd of this sample from the quadratic form (float64: 48 operations instead of the
+            // 1800 FMAs of evaluating all 256 pre-activations once more just for their sum of squares)
+            const double xd[6] = {(double)q0.x, (double)q0.y, (double)q0.z, (double)q0.w, (double)q1.x, (double)q1.y};
+            double ssq = ln1q[0];
+            int qi = 7;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                ssq = fma(ln1q[1 + k], xd[k], ssq);
+#pragma unroll
+                for (int l = k; l < 6; ++l) {
+                    ssq = fma(ln1q[qi] * xd[k], xd[l], ssq);
+                    ++qi;
+                }
+            }
+            const float rstd1_s = (float)(1.0 / sqrt(ssq * (1.0 / 256.0) + (double)kLnEps));
             *reinterpret_cast<float4*>(xt + tid * 8) = q0;
-            *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(q1.x, q1.y, 0.0f, 0.0f);
+            *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(q1.x, q1.y, rstd1_s, 0.0f);
         }
         compute_sync();
 
-        // ---- Ph1: LayerNorm-1 statistics: thread = (sample r128, 256/G of the 256 outputs) --------------
+        // ---- Ph1: this thread's sample (r128) for the producer phases; rstd1 was computed in Ph0 ------------
         float xr[6];
         {
             const float4 x0 = *reinterpret_cast<const float4*>(xt + r128 * 8);
             const float4 x1 = *reinterpret_cast<const float4*>(xt + r128 * 8 + 4);
             xr[0] = x0.x; xr[1] = x0.y; xr[2] = x0.z; xr[3] = x0.w; xr[4] = x1.x; xr[5] = x1.y;
-            float sq = 0.0f;
-#pragma unroll 4
-            for (int u = 0; u < 64 / G; ++u) {
-                const int in0 = ug * (256 / G) + 4 * u;
-                float4 z = *reinterpret_cast<const float4*>(P1 + in0);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
-                    z.x = fmaf(xr[k], w.x, z.x);
-                    z.y = fmaf(xr[k], w.y, z.y);
-                    z.z = fmaf(xr[k], w.z, z.z);
-                    z.w = fmaf(xr[k], w.w, z.w);
-                }
-                sq = fmaf(z.x, z.x, sq);
-                sq = fmaf(z.y, z.y, sq);
-                sq = fmaf(z.z, z.z, sq);
-                sq = fmaf(z.w, z.w, sq);
-            }
-            EX(0, ug, r128) = sq;
         }
-        compute_sync();
-        if (tid < kTcTile) {
-            float var = 0.0f;
-#pragma unroll
-            for (int g = 0; g < G; ++g) var += EX(0, g, tid);
-            xt[tid * 8 + 6] = 1.0f / sqrtf(var * (1.0f / 256.0f) + kLnEps);
-        }
-        compute_sync();
         const float rstd1 = xt[r128 * 8 + 6];
 
         // ---- Ph2: G1 forward, K = 256 inputs in 8 chunks; thread = (sample r128, 8/G of the 8 units) ----

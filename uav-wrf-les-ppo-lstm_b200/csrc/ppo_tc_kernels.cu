@@ -305,9 +305,17 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     };
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+#ifdef PLUME_TC_TIMELINE
+        long long tl_[12];
+        const bool tl_on = blockIdx.x == 0 && tid == 0 && tile == (long long)blockIdx.x + 3 * gridDim.x;
+#define PLUME_TL(n) if (tl_on) tl_[n] = clock64()
+#else
+#define PLUME_TL(n)
+#endif
         const long long base = tile * kTcTile;
         const int n_valid = (int)((a.mb_size - base) < kTcTile ? (a.mb_size - base) : kTcTile);
 
+        PLUME_TL(0);
         // ---- Ph0: this tile's samples: gathered by cp.async during the previous tile (first tile: now) --------
         // pf[s] = {obs 0..5, adv, ret, old value, old logp, action (int bits), 0}
         if (tile == (long long)blockIdx.x) prefetch_tile(tile);
@@ -344,6 +352,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         compute_sync();
 
+        PLUME_TL(1);
         // ---- Ph1: this thread's sample (r128) for the producer phases; rstd1 was computed in Ph0 ------------
         float xr[6];
         {
@@ -388,8 +397,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             publish(st);          // issuer: G1 -> columns [0,128), small terms -> [128,256) (free until G2)
             ++step;
         }
+        PLUME_TL(2);
         wait_all_mma();
 
+        PLUME_TL(3);
         // ---- Ph3: LN2, heads, loss, LN2-backward means: thread = (sample srow, 32 of the 128 outputs) ----
         float v[CW];
         {
@@ -538,6 +549,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             compute_sync();
         }
 
+        PLUME_TL(4);
         // ---- Ph4: heads + LN2 backward per column: thread = (output r128, 128/G of the 128 samples) ------
         {
             const int o = r128;
@@ -571,6 +583,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         compute_sync();
 
+        PLUME_TL(5);
         // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 4 chunks ------------
         for (int hN = 0; hN < 2; ++hN) {
             for (int c = 0; c < 4; ++c) {
@@ -595,6 +608,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             }
         }
 
+        PLUME_TL(6);
         // ---- Ph7: G3 dW2 += dz2^T . h1, K = 128 samples in 4 chunks x two halves of the inputs -----------
         for (int c = 0; c < 4; ++c) {
             for (int hN = 0; hN < 2; ++hN) {
@@ -648,6 +662,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         // (the acquires above waited for every G2 MMA)
 
+        PLUME_TL(7);
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
             compute_sync();        // every thread has read dz2 for its last G3 chunk: the region becomes staging
@@ -711,6 +726,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 }
                 compute_sync();
             }
+        PLUME_TL(8);
             wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
             EX(6, cg, srow) = m1p;
             EX(7, cg, srow) = m2p;
@@ -742,18 +758,31 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                         }
                     }
                 }
+                // sums over the tile's 128 samples: transpose through the (now idle) staging region and let all 16
+                // warps add two or three of the 35 rows each, instead of 175 shuffles in each of these 4 warps
 #pragma unroll
-                for (int k = 0; k < 35; ++k) {
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 35; ++k) atomicAdd(&cta_acc[k], red[k]);
-                }
+                for (int k = 0; k < 35; ++k) xh[k * kTcTile + srow] = red[k];
             }
+            compute_sync();
+            for (int k = warp; k < 35; k += kTcThreads / 32) {
+                const float* rowp = xh + k * kTcTile + lane;
+                float sred = (rowp[0] + rowp[32]) + (rowp[64] + rowp[96]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, off);
+                if (lane == 0) cta_acc[k] += sred;          // row k belongs to exactly one warp
+            }
+        PLUME_TL(9);
             compute_sync();       // exch / x tile / staging are rewritten by the next tile
         }
+#ifdef PLUME_TC_TIMELINE
+        if (tl_on) {
+            const long long end = clock64();
+            printf("ppo_tc timeline (cycles): Ph0 gather+rstd %lld | G1 production %lld | G1 mma drain %lld | Ph3 LN2/loss %lld | "
+                   "Ph4 %lld | G2 production %lld | G3 production %lld | Ph6 columns %lld | drain %lld | Ph6 scalars %lld | tail %lld | total %lld\n",
+                   tl_[1] - tl_[0], tl_[2] - tl_[1], tl_[3] - tl_[2], tl_[4] - tl_[3], tl_[5] - tl_[4], tl_[6] - tl_[5],
+                   tl_[7] - tl_[6], tl_[8] - tl_[7], 0LL, tl_[9] - tl_[8], end - tl_[9], end - tl_[0]);
+        }
+#endif
     }
 
     // ---- flush ------------------------------------------------------------------------------------------

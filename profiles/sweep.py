@@ -26,13 +26,17 @@ def timed(fn, reps=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--hidden", type=int, nargs="+", default=[32, 64])
+    ap.add_argument("--hidden", type=int, nargs="+", default=[32, 64, 256])
+    ap.add_argument("--max-envs-generic", type=int, default=4096,
+                    help="largest envs/GPU for hidden sizes that run on the generic (L2-weights) LSTM kernel")
     ap.add_argument("--envs", type=int, nargs="+", default=[256, 1024, 4096, 16384, 65536])
     ap.add_argument("--horizon", type=int, default=256)
     args = ap.parse_args()
     T = args.horizon
     for H in args.hidden:
         for N in args.envs:
+            if H not in (32, 64) and N > args.max_envs_generic:
+                continue
             tr = pb.PlumeTrainer(num_envs=N, horizon=T, minibatch_size=max(N * T // 4, 256), seed=1)
             if H != 32:
                 tr.head = pb.PeakAndStopPredictor(hidden_dim=H, device=tr.device)
@@ -43,7 +47,8 @@ def main():
             roll = timed(lambda: tr.engine.collect())
             full = timed(lambda: tr.train_iteration())
             print(json.dumps({"envs_per_gpu": N, "horizon": T, "lstm_hidden": H,
-                              "stop_head": "tcgen05" if H == 32 else "cuda-core",
+                              "stop_head": "tcgen05" if H == 32 else ("cuda-core, smem weights" if H == 64 else
+                                                                         "cuda-core, L2 weights"),
                               "rollout_ms": round(roll, 3), "rollout_env_steps_per_s": N * T / roll * 1e3,
                               "us_per_lockstep_iteration": round(1e3 * roll / T, 2),
                               "iteration_ms": round(full, 3), "ppo_env_steps_per_s": N * T / full * 1e3}), flush=True)

@@ -99,7 +99,8 @@ def test_lstm_stop_head_golden():
     assert clear.sum() > 90
 
 
-@pytest.mark.parametrize("hidden,batch,steps", [(32, 1, 20), (32, 257, 20), (64, 100, 20), (32, 40, 7)])
+@pytest.mark.parametrize("hidden,batch,steps", [(32, 1, 20), (32, 257, 20), (64, 100, 20), (32, 40, 7), (48, 33, 20),
+                                                (256, 50, 20)])
 def test_lstm_stop_head_vs_oracle(hidden, batch, steps):
     torch.manual_seed(hidden + batch)
     ora = pp.OraclePeakAndStop(hidden_dim=hidden)

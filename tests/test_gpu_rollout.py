@@ -274,6 +274,50 @@ def test_deferred_stop_head_equals_in_loop_head(splits, path, monkeypatch):
     assert torch.equal(nxt_a, nxt_b)
 
 
+@pytest.mark.parametrize("hidden", [48, 256])
+def test_deferred_stop_head_other_hidden_sizes(hidden):
+    """BASELINE configs[4] sweeps the stop-head hidden size up to 256: sizes other than 32 / 64 run the deferred head
+    on the generic LSTM kernel (weights from L2).  Checked against the torch-CPU LSTM on the windows rebuilt from the
+    segment's samples (also across a segment boundary: the carried ring), trend features against the 32-unit run."""
+    import uav_wrf_les_ppo_lstm_b200 as m
+    from oracle import ppo_oracle as pp
+    N, splits, W = 40, (30, 34), 20
+    torch.manual_seed(hidden)
+    env = m.VecMethaneEnv(N, version="2.1", seed=17, field_mode="procedural", auto_reset=True)
+    env.curriculum[0] = 25.0
+    env.reset()
+    model = m.PPOActorCritic(device="cuda")
+    head = m.PeakAndStopPredictor(hidden_dim=hidden, device="cuda")
+    ora = pp.OraclePeakAndStop(hidden_dim=hidden)
+    ora.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
+    eng = m.RolloutEngine(env, model, head, horizon=max(splits), with_trend=True)
+    # the same rollout with the 32-unit head gives the reference trend features (they do not depend on the head)
+    env2 = m.VecMethaneEnv(N, version="2.1", seed=17, field_mode="procedural", auto_reset=True)
+    env2.curriculum[0] = 25.0
+    env2.reset()
+    eng2 = m.RolloutEngine(env2, model, m.PeakAndStopPredictor(device="cuda"), horizon=max(splits), with_trend=True)
+    samples, fills, probs, peaks, flags = [], [], [], [], []
+    for h in splits:
+        seg, seg2 = eng.collect(horizon=h), eng2.collect(horizon=h)
+        assert torch.equal(seg.rewards[:h], seg2.rewards[:h]) and torch.equal(seg.trend[:h], seg2.trend[:h])
+        samples.append(seg.conc_sample[:h].clone()); fills.append(seg.fill_t[:h].clone())
+        probs.append(seg.stop_prob[:h].clone()); peaks.append(seg.peak_pred[:h].clone()); flags.append(seg.stop_flag[:h].clone())
+    cs, fill = torch.cat(samples).cpu(), torch.cat(fills).cpu()
+    sp, pk, sf = torch.cat(probs).cpu(), torch.cat(peaks).cpu(), torch.cat(flags).cpu()
+    full = fill >= W
+    assert full.any() and (~full).any()
+    assert torch.all(sp[~full] == 0) and torch.all(pk[~full] == 0) and not sf[~full].any()
+    tt, nn = full.nonzero(as_tuple=True)
+    windows = torch.stack([cs[t - W + 1:t + 1, n] for t, n in zip(tt.tolist(), nn.tolist())])
+    assert (tt >= splits[0]).any()                       # some windows straddle the segment boundary
+    with torch.no_grad():
+        rp, rs = ora(windows)
+    assert torch.allclose(pk[full], rp, rtol=1e-5, atol=2e-6)
+    assert torch.allclose(sp[full], rs, rtol=1e-5, atol=2e-6)
+    clear = (rs - 0.8).abs() > 1e-5
+    assert torch.equal(sf[full][clear].bool(), (rs > 0.8)[clear])
+
+
 def test_deferred_stop_head_rejects_terminating_stop():
     N, T = 32, 8
     m, env, model, head, eng = _setup(N, T, seed=1)

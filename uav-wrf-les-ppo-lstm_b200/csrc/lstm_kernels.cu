@@ -268,6 +268,119 @@ static int launch_segment(const LstmWeights& w, const SegmentArgs& a, cudaStream
     return 0;
 }
 
+// ---- deferred stop head for any hidden size <= 256 (BASELINE configs[4]: hidden 256) -------------------------
+// Windows of a chunk of (t, env) pairs are assembled into a scratch array, the generic LSTM kernel (weights
+// streamed from L2) produces their last hidden states and one warp per window applies fc_peak / fc_stop and the
+// trend features.  Same outputs and window semantics as stop_head_segment_kernel.
+constexpr int kSegChunk = 32768;
+
+__global__ void segment_windows_kernel(SegmentArgs a, long long first, int count, float* __restrict__ windows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long idx = first + i;
+    const int t = (int)(idx / a.n_envs), env = (int)(idx - (long long)t * a.n_envs), W = a.W;
+    for (int k = 0; k < W; ++k) {
+        const int tt = t - (W - 1) + k;
+        const float v = tt >= 0 ? a.conc_sample[(size_t)tt * a.n_envs + env] : a.window_in[(size_t)env * W + (W + tt)];
+        windows[(size_t)i * W + k] = v;
+        if (t == a.horizon - 1 && a.window_out) a.window_out[(size_t)env * W + k] = v;
+    }
+}
+
+__global__ void segment_heads_kernel(SegmentArgs a, LstmWeights w, int H, long long first, int count,
+                                     const float* __restrict__ h, const float* __restrict__ windows) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= count) return;
+    const long long idx = first + i;
+    float p = 0.0f, q = 0.0f;
+    for (int k = lane; k < H; k += 32) {
+        const float v = h[(size_t)i * H + k];
+        p = fmaf(v, w.w_peak[k], p);
+        q = fmaf(v, w.w_stop[k], q);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        p += __shfl_xor_sync(0xffffffffu, p, off);
+        q += __shfl_xor_sync(0xffffffffu, q, off);
+    }
+    if (lane != 0) return;
+    const int W = a.W;
+    const bool full = a.fill_t[idx] >= W;
+    const float peak = full ? p + w.b_peak[0] : 0.0f, stop_p = full ? sigmoidf_acc(q + w.b_stop[0]) : 0.0f;
+    if (a.stop_prob) a.stop_prob[idx] = stop_p;
+    if (a.stop_flag) a.stop_flag[idx] = (full && stop_p > a.threshold) ? 1 : 0;
+    if (a.peak_pred) a.peak_pred[idx] = peak;
+    if (a.trend) {
+        float tr[4] = {0, 0, 0, 0};
+        const float* x = windows + (size_t)i * W;
+        if (full && W >= 4)
+            trend_from_last4(100.0 * (double)x[W - 4], 100.0 * (double)x[W - 3], 100.0 * (double)x[W - 2],
+                             100.0 * (double)x[W - 1], a.src_dist[idx], a.conc_peak, tr);
+        *reinterpret_cast<float4*>(a.trend + idx * 4) = make_float4(tr[0], tr[1], tr[2], tr[3]);
+    }
+}
+
+static int launch_generic(const float* params, int layers, int H, const float* windows, int batch, int steps,
+                          float* h_out, cudaStream_t s);
+
+// scratch of the generic-hidden-size paths: stream-ordered reuse, grown on demand (cudaFree synchronises)
+static float* generic_scratch(size_t need_floats) {
+    static float* scratch = nullptr;
+    static size_t scratch_floats = 0;
+    if (need_floats > scratch_floats) {
+        if (scratch) cudaFree(scratch);
+        scratch = nullptr;
+        scratch_floats = 0;
+        if (cudaMalloc(&scratch, need_floats * sizeof(float)) != cudaSuccess) return nullptr;
+        scratch_floats = need_floats;
+    }
+    return scratch;
+}
+
+// torch layout of layer 0: weight_ih [4H][1], weight_hh [4H][H], bias_ih [4H], bias_hh [4H]
+static int pack_layer0(float* par, const LstmWeights& w, int H, cudaStream_t s) {
+    PLUME_CUDA(cudaMemcpyAsync(par, w.w_ih, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, s));
+    PLUME_CUDA(cudaMemcpyAsync(par + 4 * H, w.w_hh, sizeof(float) * 4 * H * H, cudaMemcpyDeviceToDevice, s));
+    PLUME_CUDA(cudaMemcpyAsync(par + 4 * H + (size_t)4 * H * H, w.b_ih, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, s));
+    PLUME_CUDA(cudaMemcpyAsync(par + 8 * H + (size_t)4 * H * H, w.b_hh, sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// PeakAndStopPredictor.forward on explicit windows [batch][steps] for any hidden size <= 256
+static int launch_stop_head_generic(const LstmWeights& w, int H, const float* windows, int batch, int steps,
+                                    float* peak, float* stop_prob, cudaStream_t s) {
+    const size_t n_par = (size_t)4 * H + (size_t)4 * H * H + (size_t)8 * H;
+    float* par = generic_scratch(n_par + (size_t)kSegChunk * H);
+    if (!par) return fail("stop head: cannot allocate scratch");
+    float* hbuf = par + n_par;
+    if (pack_layer0(par, w, H, s)) return 1;
+    for (int first = 0; first < batch; first += kSegChunk) {
+        const int count = batch - first < kSegChunk ? batch - first : kSegChunk;
+        if (launch_generic(par, 1, H, windows + (size_t)first * steps, count, steps, hbuf, s)) return 1;
+        linear_heads_kernel<<<(count + 127) / 128, 128, 0, s>>>(hbuf, count, H, w.w_peak, w.b_peak, w.w_stop, w.b_stop,
+                                                               peak + first, stop_prob + first);
+    }
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_segment_generic(const LstmWeights& w, int H, const SegmentArgs& a, cudaStream_t s) {
+    const size_t n_par = (size_t)4 * H + (size_t)4 * H * H + (size_t)8 * H;
+    float* par = generic_scratch(n_par + (size_t)kSegChunk * a.W + (size_t)kSegChunk * H);
+    if (!par) return fail("stop head: cannot allocate scratch");
+    float* win = par + n_par;
+    float* hbuf = win + (size_t)kSegChunk * a.W;
+    if (pack_layer0(par, w, H, s)) return 1;
+    const long long total = (long long)a.horizon * a.n_envs;
+    for (long long first = 0; first < total; first += kSegChunk) {
+        const int count = (int)((total - first) < kSegChunk ? (total - first) : kSegChunk);
+        segment_windows_kernel<<<(count + 255) / 256, 256, 0, s>>>(a, first, count, win);
+        if (launch_generic(par, 1, H, win, count, a.W, hbuf, s)) return 1;
+        segment_heads_kernel<<<(count + 7) / 8, 256, 0, s>>>(a, w, H, first, count, hbuf, win);
+    }
+    PLUME_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int H>
 static int launch_stop_head(const LstmWeights& w, const float* windows, int batch, int steps, float* peak,
                             float* stop_prob, cudaStream_t s) {
@@ -316,7 +429,9 @@ extern "C" int plume_lstm_stop_head(const float* w_ih, const float* w_hh, const 
     const LstmWeights w{w_ih, w_hh, b_ih, b_hh, w_peak, b_peak, w_stop, b_stop};
     if (hidden == 32) return launch_stop_head<32>(w, windows, batch, steps, peak, stop_prob, as_stream(stream));
     if (hidden == 64) return launch_stop_head<64>(w, windows, batch, steps, peak, stop_prob, as_stream(stream));
-    return fail("plume_lstm_stop_head: hidden must be 32 or 64 (use plume_lstm_forward for other sizes)");
+    if (hidden >= 1 && hidden <= 256)
+        return launch_stop_head_generic(w, hidden, windows, batch, steps, peak, stop_prob, as_stream(stream));
+    return fail("plume_lstm_stop_head: hidden must be in [1,256]");
 }
 
 extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const float* conc_sample, const uint8_t* fill_t,
@@ -372,7 +487,8 @@ extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const floa
     a.stop_flag = stop_flag;
     if (lstm->hidden == 32) return launch_segment<32>(w, a, as_stream(stream));
     if (lstm->hidden == 64) return launch_segment<64>(w, a, as_stream(stream));
-    return fail("plume_stop_head_segment: hidden must be 32 or 64");
+    if (lstm->hidden >= 1 && lstm->hidden <= 256) return launch_segment_generic(w, lstm->hidden, a, as_stream(stream));
+    return fail("plume_stop_head_segment: hidden must be in [1,256]");
 }
 
 extern "C" int plume_lstm_forward(const float* params, int32_t layers, int32_t hidden, const float* windows,

@@ -189,13 +189,11 @@ class PeakAndStopPredictor(nn.Module):
         stop = torch.empty(B, dtype=torch.float32, device=dev)
         lp = self.c_params(T)
         with torch.cuda.device(dev):
-            if self.hidden_dim in (32, 64):
-                rc = lib.plume_lstm_stop_head(lp.w_ih, lp.w_hh, lp.b_ih, lp.b_hh, lp.w_peak, lp.b_peak, lp.w_stop,
-                                              lp.b_stop, self.hidden_dim, x.data_ptr(), B, T, peak.data_ptr(),
-                                              stop.data_ptr(), _stream(dev))
-                _lib.check(rc, "plume_lstm_stop_head")
-            else:
-                raise NotImplementedError("hidden sizes other than 32/64 go through plume_lstm_forward")
+            # hidden 32 / 64: weights resident in shared memory; any other size <= 256: generic kernel (L2 weights)
+            rc = lib.plume_lstm_stop_head(lp.w_ih, lp.w_hh, lp.b_ih, lp.b_hh, lp.w_peak, lp.b_peak, lp.w_stop,
+                                          lp.b_stop, self.hidden_dim, x.data_ptr(), B, T, peak.data_ptr(),
+                                          stop.data_ptr(), _stream(dev))
+            _lib.check(rc, "plume_lstm_stop_head")
         return peak, stop
 
 

@@ -200,7 +200,8 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
     # K2: procedural field.  Algorithmic bytes per env-step in the kernel's own layout (csrc/env_kernels.cu):
     # read pos 8 + src 16 + step 4 + episode 4 + radius 8 + bonus 8 + action 4 + visit 2 + carried tke 8 + tag 4
     # = 66, write pos 8 + step 4 + visit 2 + obs 24 + reward 8 + done 1 + reached 1 + carried tke 8 + tag 4 = 60,
-    # info 20  =>  146 B.  Timed as 20 back-to-back launches through the C ABI (CUDA events on the launch stream).
+    # info 20  =>  146 B (the carried concentration, 8 B each way, is left out: the reported GB/s is a lower
+    # bound).  Timed as 20 back-to-back launches through the C ABI (CUDA events on the launch stream).
     # `traffic` = DRAM bytes per launch of the 2^20-env run from the ncu capture (profiles/r1h_k2_ncu_summary.txt):
     # the visit-table read-modify-write moves a whole 128 B line per env-step.
     k2_bytes = 146

@@ -8,9 +8,11 @@
 // Algorithmic bytes (DESIGN.md "K1"/"K2"):
 //   K1 generate : 2 fields x G*G x sizeof(T) written per env-reset (2.0 MB float, 4.0 MB double)
 //   K2 step     : per env-step read pos 8 + src 16 + step 4 + episode 4 + radius 8 + bonus 8 +
-//                 action 4 + visit 2 = 54 B, write pos 8 + step 4 + visit 2 + obs 24 + reward 8 +
-//                 done 1 + reached 1 = 48 B  => 102 B (+20 B info, +16 B injected noise,
-//                 +4 field gathers x sizeof(T) in the materialised modes)
+//                 action 4 + visit 2 + carried cell (tke 8, conc 8, tag 4) = 74 B, write pos 8 + step 4 +
+//                 visit 2 + obs 24 + reward 8 + done 1 + reached 1 + carried cell 20 = 68 B  => 142 B
+//                 (+20 B info, +16 B injected noise, + field gathers x sizeof(T) in the materialised modes;
+//                 source / radius / bonus / episode are written back only by a reset).  bench.py counts
+//                 146 B = the procedural step with info and without the carried concentration's 16 B.
 #include <cstdarg>
 
 #include "common.cuh"

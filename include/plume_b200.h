@@ -406,6 +406,12 @@ int plume_lstm_train_epoch(float* params, float* exp_avg, float* exp_avg_sq, int
  * K a multiple of 32.  The GEMM-shaped parts of the PPO update (model.py:23 feature.3, forward and
  * backward, train_ppo2.0.py:54,85) run on this path; exported so it can be tested on its own. */
 int plume_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
+/* The same GEMM on tcgen05.mma kind::f16 with the two-term fp16 split (x = hi + lo / s): twice the MAC rate of TF32 and
+ * half the operand bytes at fp32-grade accuracy.  scaled_lo != 0: s = 2^11, cross terms in their own TMEM accumulator
+ * (no fp16 underflow of lo; the forward GEMM of the update); scaled_lo == 0: s = 1, one accumulator (inputs should be
+ * O(1): the backward GEMMs, whose operands the kernel pre-scales).  K a multiple of 64. */
+int plume_tc_gemm_f16(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t scaled_lo,
+                      void* stream);
 
 /* ---- P8 curriculum, model.py:188-221 ----------------------------------------------------- */
 /* Applies PPOTrainer.update once per finished episode of a [T][N] segment in canonical order

@@ -34,3 +34,28 @@ def test_tc_gemm_3xtf32(M, N, K):
     ref32 = (torch.from_numpy(A) @ torch.from_numpy(B).T).numpy().astype(np.float64)
     err32 = np.abs(ref32 - want) / scale
     assert err.max() < 20 * max(err32.max(), 1e-8)
+
+
+@pytest.mark.parametrize("scaled", [1, 0])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (1000, 128, 256), (384, 256, 128), (65536, 128, 256)])
+def test_tc_gemm_f16_two_term_split(M, N, K, scaled):
+    """kind::f16 with x = hi + lo/s.  Scaled lo (s = 2^11, separate accumulator): fp32-grade for any magnitude that fits
+    fp16's hi range; unscaled lo (one accumulator): fp32-grade for O(1) operands, which is what the update kernel feeds it."""
+    m = pb()
+    lib = m._lib.load()
+    rng = np.random.default_rng(M + N + K + scaled)
+    spread = 3.0 if scaled else 0.5
+    A = (rng.standard_normal((M, K)) * np.exp(rng.uniform(-spread, spread, (M, 1)))).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.plume_tc_gemm_f16(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, scaled,
+                               torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.plume_last_error()
+    torch.cuda.synchronize()
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    got = c.cpu().numpy().astype(np.float64)
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    err = np.abs(got - want) / scale
+    assert np.isfinite(got).all()
+    assert err.max() < (2e-6 if scaled else 4e-6), err.max()

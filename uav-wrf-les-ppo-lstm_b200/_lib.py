@@ -130,6 +130,7 @@ _SIGNATURES = {
                                          _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "plume_permutation": (C.c_int, [C.c_int64, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, _vp, _vp]),
     "plume_tc_gemm": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "plume_tc_gemm_f16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "plume_curriculum_update": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double,
                                           C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
     "plume_curriculum_update_packed": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_double,

@@ -15,6 +15,7 @@
 // Descriptor formats follow the PTX ISA / CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor,
 // InstrDescriptor); the guide is /opt/skills/guides/blackwell_cuda_programming.md.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -181,6 +182,99 @@ __device__ __forceinline__ void mma_chunk_3xtf32_split(uint32_t tmem_big, uint32
         mma_tf32(tmem_small, dal, dbh, idesc, acc);
         mma_tf32(tmem_small, dah, dbl, idesc, 1u);
         mma_tf32(tmem_big, dah, dbh, idesc, acc);
+    }
+}
+
+// ---- kind::f16 with the two-term fp16 split ----------------------------------------------------------------
+// x = hi + lo / s,  hi = fp16(x),  lo = fp16((x - hi) s)   (s = 2^11 keeps lo in the normal fp16 range: |x - hi| <=
+// 2^-11 |x|; s = 1 where the cross terms must share the accumulator of the main term).  A 64-element fp16 chunk has
+// the same 128 bytes per row as the 32-element tf32 chunk: the slot layout f = (row/8)*64 + (k/8)*8 + row%8, the
+// shared-memory descriptors (LBO 128, SBO 1024) and the 4 x 3 MMAs per chunk are unchanged -- each MMA now covers
+// K = 16 at twice the MAC rate, so a chunk step carries twice the K in the same tensor-pipe time and half the
+// operand bytes per element.
+constexpr int kChunkKH = 64;
+constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
+
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {      // D fp32, A/B fp16, both K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// two values -> packed fp16 hi and fp16 lo (scaled by s)
+__device__ __forceinline__ void split_f16x2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - hf.x) * s, (b - hf.y) * s);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// eight consecutive K values -> one 16-byte operand slot of each buffer
+__device__ __forceinline__ void split_f16x8(const float4 v0, const float4 v1, float s, uint4& hi, uint4& lo) {
+    split_f16x2(v0.x, v0.y, s, hi.x, lo.x);
+    split_f16x2(v0.z, v0.w, s, hi.y, lo.y);
+    split_f16x2(v1.x, v1.y, s, hi.z, lo.z);
+    split_f16x2(v1.z, v1.w, s, hi.w, lo.w);
+}
+
+// Cooperative load of a [ROWS][64] fp32 chunk (row-major, leading dimension ld) into fp16 hi / lo operand buffers.
+template <int ROWS, int kThreads>
+__device__ __forceinline__ void load_split_chunk_f16(float* __restrict__ s_hi, float* __restrict__ s_lo,
+                                                     const float* __restrict__ src, size_t ld, int valid_rows, int tid,
+                                                     float lo_scale) {
+    constexpr int kSlots = ROWS * 8;
+#pragma unroll
+    for (int f = tid; f < kSlots; f += kThreads) {
+        const int row = (f >> 6) * 8 + (f & 7), k8 = (f & 63) >> 3;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (row < valid_rows) {
+            v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + k8 * 8));
+            v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + k8 * 8 + 4));
+        }
+        uint4 h, l;
+        split_f16x8(v0, v1, lo_scale, h, l);
+        reinterpret_cast<uint4*>(s_hi)[f] = h;
+        reinterpret_cast<uint4*>(s_lo)[f] = l;
+    }
+}
+
+// The 12 MMAs of one 64-wide fp16 chunk, all into one accumulator (unscaled lo).
+__device__ __forceinline__ void mma_chunk_f16(uint32_t tmem_d, const float* a_hi, const float* a_lo, const float* b_hi,
+                                              const float* b_lo, uint32_t idesc, bool first_chunk) {
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+    for (int j = 0; j < kChunkKH / 16; ++j) {
+        const uint32_t off = j * 2 * kLBO;       // 16 halves = two 16-byte core-matrix columns
+        const uint64_t dah = make_smem_desc(ah + off, kLBO, kSBO), dal = make_smem_desc(al + off, kLBO, kSBO);
+        const uint64_t dbh = make_smem_desc(bh + off, kLBO, kSBO), dbl = make_smem_desc(bl + off, kLBO, kSBO);
+        mma_f16(tmem_d, dal, dbh, idesc, (first_chunk && j == 0) ? 0u : 1u);
+        mma_f16(tmem_d, dah, dbl, idesc, 1u);
+        mma_f16(tmem_d, dah, dbh, idesc, 1u);
+    }
+}
+
+// Same, the cross terms (lo scaled by 2^11) in their own accumulator: result = big + small * 2^-11.
+__device__ __forceinline__ void mma_chunk_f16_split(uint32_t tmem_big, uint32_t tmem_small, const float* a_hi,
+                                                    const float* a_lo, const float* b_hi, const float* b_lo,
+                                                    uint32_t idesc, bool first_chunk) {
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+    for (int j = 0; j < kChunkKH / 16; ++j) {
+        const uint32_t off = j * 2 * kLBO;
+        const uint64_t dah = make_smem_desc(ah + off, kLBO, kSBO), dal = make_smem_desc(al + off, kLBO, kSBO);
+        const uint64_t dbh = make_smem_desc(bh + off, kLBO, kSBO), dbl = make_smem_desc(bl + off, kLBO, kSBO);
+        const uint32_t acc = (first_chunk && j == 0) ? 0u : 1u;
+        mma_f16(tmem_small, dal, dbh, idesc, acc);
+        mma_f16(tmem_small, dah, dbl, idesc, 1u);
+        mma_f16(tmem_big, dah, dbh, idesc, acc);
     }
 }
 

@@ -88,9 +88,114 @@ static int launch_tc_gemm(const float* A, const float* B, float* C, int M, int K
     return 0;
 }
 
+// The same GEMM on kind::f16 with the two-term split (tc_gemm.cuh): 64-wide chunks, main and cross terms in two TMEM
+// accumulators (columns [0,BN) and [BN,2BN)), combined in the epilogue.  kScaled = false keeps lo unscaled and
+// everything in one accumulator (the form the backward GEMMs of the update kernel use).
+template <int BN, bool kScaled>
+__global__ void __launch_bounds__(128, 1) tc_gemm_f16_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                             float* __restrict__ C, int M, int K) {
+    extern __shared__ __align__(1024) float sm[];
+    constexpr int kA = 128 * tc::kChunkK, kB = BN * tc::kChunkK;      // floats: a 64-half chunk row is 128 bytes too
+    float* a_hi = sm;
+    float* a_lo = a_hi + 2 * kA;
+    float* b_hi = a_lo + 2 * kA;
+    float* b_lo = b_hi + 2 * kB;
+    __shared__ uint64_t mma_done[2];
+    __shared__ uint32_t tmem_slot;
+    constexpr uint32_t kCols = kScaled ? 2 * BN : BN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * 128;
+    if (tid == 0) {
+        tc::mbar_init(&mma_done[0], 1);
+        tc::mbar_init(&mma_done[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc<kCols>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = tc::make_idesc_f16(128, BN);
+    const float ls = kScaled ? tc::kLoScale : 1.0f;
+
+    const int chunks = K / tc::kChunkKH;
+    for (int kc = 0; kc < chunks; ++kc) {
+        const int s = kc & 1;
+        if (kc >= 2) tc::mbar_wait(&mma_done[s], (uint32_t)(((kc >> 1) - 1) & 1));
+        tc::load_split_chunk_f16<128, 128>(a_hi + s * kA, a_lo + s * kA, A + (size_t)m0 * K + kc * tc::kChunkKH, K, M - m0,
+                                           tid, ls);
+        tc::load_split_chunk_f16<BN, 128>(b_hi + s * kB, b_lo + s * kB, B + kc * tc::kChunkKH, K, BN, tid, ls);
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            if (kScaled)
+                tc::mma_chunk_f16_split(tmem_d, tmem_d + BN, a_hi + s * kA, a_lo + s * kA, b_hi + s * kB, b_lo + s * kB,
+                                        idesc, kc == 0);
+            else
+                tc::mma_chunk_f16(tmem_d, a_hi + s * kA, a_lo + s * kA, b_hi + s * kB, b_lo + s * kB, idesc, kc == 0);
+            tc::mma_commit(&mma_done[s]);
+        }
+    }
+    {
+        const int last = chunks - 1;
+        tc::mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
+    }
+    tc::tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        tc::tmem_ld_wait();
+        if (kScaled) {
+            float w[32];
+            tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(BN + c * 32), w);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(w[j], tc::kLoInv, v[j]);
+        }
+        if (row < M) {
+            float4* dst = reinterpret_cast<float4*>(C + (size_t)row * BN + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<kCols>(tmem_d);
+}
+
+template <int BN, bool kScaled>
+static int launch_tc_gemm_f16(const float* A, const float* B, float* C, int M, int K, cudaStream_t s) {
+    const int smem = (2 * 2 * 128 * tc::kChunkK + 2 * 2 * BN * tc::kChunkK) * (int)sizeof(float) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc_gemm_f16_kernel<BN, kScaled>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+            return fail("tc_gemm_f16: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    tc_gemm_f16_kernel<BN, kScaled><<<(M + 127) / 128, 128, smem, s>>>(A, B, C, M, K);
+    if (cudaGetLastError() != cudaSuccess) return fail("tc_gemm_f16 launch failed");
+    return 0;
+}
+
 }  // namespace plume
 
 using namespace plume;
+
+extern "C" int plume_tc_gemm_f16(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                 int32_t scaled_lo, void* stream) {
+    PLUME_CHECK_ARG(A && B && C, "null pointer");
+    PLUME_CHECK_ARG(M > 0 && K > 0 && K % tc::kChunkKH == 0, "K must be a positive multiple of 64");
+    if (N == 128 && scaled_lo) return launch_tc_gemm_f16<128, true>(A, B, C, M, K, as_stream(stream));
+    if (N == 128) return launch_tc_gemm_f16<128, false>(A, B, C, M, K, as_stream(stream));
+    if (N == 256 && scaled_lo) return launch_tc_gemm_f16<256, true>(A, B, C, M, K, as_stream(stream));
+    if (N == 256) return launch_tc_gemm_f16<256, false>(A, B, C, M, K, as_stream(stream));
+    return fail("plume_tc_gemm_f16: N must be 128 or 256");
+}
 
 extern "C" int plume_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, void* stream) {
     PLUME_CHECK_ARG(A && B && C, "null pointer");

@@ -384,7 +384,7 @@ def run_cuda_arm(args) -> None:
     flops_grad = 3 * 70144 * min(mb, M)
     flops_roll = N * T * (70144 + 20 * 2 * 4 * 32 * 33)
     kernels = {
-        "ppo_grad(tcgen05 3xTF32)": {"ms": grad_ms, "launches_per_step": 2 * n_opt, "tflops": flops_grad / grad_ms / 1e9,
+        "ppo_grad(tcgen05 f16 split)": {"ms": grad_ms, "launches_per_step": 2 * n_opt, "tflops": flops_grad / grad_ms / 1e9,
                                       "share_of_step": grad_ms * n_opt / (total_ms / args.steps)},
         "rollout": {"ms": roll_ms / args.steps, "launches_per_step": 2 if seg_ms else 1,
                     "tflops": flops_roll / (roll_ms / args.steps) / 1e9,
@@ -397,20 +397,21 @@ def run_cuda_arm(args) -> None:
                                 "hbm_frac": 32 * M / gae_ms / 1e6 / peaks["hbm_gbs"],
                                 "share_of_step": gae_ms / (total_ms / args.steps)},
     }
-    dom = max(("ppo_grad(tcgen05 3xTF32)", "rollout"), key=lambda k: kernels[k]["share_of_step"])
+    dom = max(("ppo_grad(tcgen05 f16 split)", "rollout"), key=lambda k: kernels[k]["share_of_step"])
     peak_tf = peaks["bf16_tflops_sustained"]
     # ALGORITHMIC FLOP (210 432 per sample for the update: forward 70 144 + backward 140 288)
-    # over the CUDA-event time of the launch.  The denominator is the measured bf16 peak the contract names;
-    # the fp32-grade parity bar forces the 3xTF32 split (TF32 runs at half the bf16 rate and every product
-    # costs three MMAs), so the ceiling this kernel can reach is peak/6 -- reported next to it.
+    # over the CUDA-event time of the launch.  The denominator is the measured bf16 peak the contract names
+    # (kind::f16 runs at the bf16 rate); the fp32-grade parity bar costs three MMAs per product (two-term fp16
+    # split), so the ceiling this kernel can reach is peak/3 -- reported next to it.
     roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peak_tf,
-                "traffic": 43.75e6 if dom.startswith("ppo_grad") else None,   # profiles/r1e_ncu_summary.txt
+                "traffic": 43.6e6 if dom.startswith("ppo_grad") else None,   # profiles/r1m_ncu_summary.txt
                 "peak_source": f"{peaks['source']} bf16 dense (sustained), of measured",
-                "tf32x3_ceiling": peak_tf / 6.0, "frac_of_tf32x3_ceiling": kernels[dom]["tflops"] / (peak_tf / 6.0),
-                "note": "tcgen05.mma kind::tf32 with the 3xTF32 split (fp32 rel 1e-5 parity bar), accumulators in "
-                        "TMEM; traffic = dram read+write per launch from the ncu --set full capture in "
-                        "profiles/ (algorithmic gather: 44 B x 262144 samples = 11.5 MB)"}
+                "split_ceiling": peak_tf / 3.0, "frac_of_split_ceiling": kernels[dom]["tflops"] / (peak_tf / 3.0),
+                "note": "tcgen05.mma kind::f16 with the two-term fp16 split x = hi + lo/s (fp32 rel 1e-5 parity bar), "
+                        "accumulators in TMEM; traffic = dram read+write per launch from the ncu --set full capture in "
+                        "profiles/ (algorithmic gather: 44 B x 262144 samples = 11.5 MB); 60 % of a tile's cycles are "
+                        "CUDA-core phases between the GEMMs (DESIGN.md section 5, phase timeline)"}
 
     # ---- end to end through the host-buffer API -------------------------------------------------------
     hb = trainer.make_host_buffers()

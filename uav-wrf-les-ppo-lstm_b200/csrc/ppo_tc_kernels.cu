@@ -1,7 +1,7 @@
 // ppo_tc_kernels.cu -- K6 on the sm_100a tensor cores: the PPO minibatch gradient
 // (train_ppo2.0.py:42-85) with the three GEMM-shaped parts of the actor-critic's 256->128 layer
-// (model.py:23) on tcgen05.mma (kind::tf32, 3xTF32 split = fp32-grade accuracy, accumulators in
-// TMEM) and everything else (6->256 layer, both LayerNorms, heads, loss, all the reductions) on the
+// (model.py:23) on tcgen05.mma (kind::f16 with the two-term fp16 split x = hi + lo/s of tc_gemm.cuh = fp32-grade
+// accuracy at twice the TF32 rate and half the operand bytes, accumulators in TMEM) and everything else (6->256 layer, both LayerNorms, heads, loss, all the reductions) on the
 // CUDA cores of the same persistent CTA.  One CTA per SM, 128-sample tiles, 16 compute warps + 1 issuer warp.
 //
 //   G1  z2[s][o]   = sum_i  h1[s][i] W2[o][i]        A = h1 (produced chunk by chunk from the 6 inputs),
@@ -10,8 +10,11 @@
 //   G3  dW2[o][i] += sum_s  dz2[s][o] h1[s][i]       A = dz2^T, B = h1^T (recomputed, K-major along s);
 //                                                     accumulates in TMEM across ALL tiles of the CTA
 //
-// TMEM map (512 columns): [0,128) G1 result, then G2 result for inputs 0..127; [128,256) G2 result for
-// inputs 128..255; [256,512) the persistent dW2 accumulator (row = output o, column = input i).
+// TMEM map (512 columns): [0,128) G1 result, then G2 result for inputs 0..127; [128,256) G1's scaled cross terms
+// (lo * 2^11, folded in with 2^-11 in the epilogue), then G2 result for inputs 128..255; [256,512) the persistent
+// dW2 accumulator (row = output o, column = input i).  G2 and G3 have no spare accumulator for their cross terms:
+// their lo parts are unscaled and the operands are pre-scaled to O(1) instead (dz_scale dz2, 16 W2^T), undone where
+// dh1 and dW2 are read.  K chunks are 64 fp16 values = the same 128 bytes per row as the former 32-value tf32 chunk.
 //
 // Layer 1 never materialises dz1: with dy1 = relu'(y1) o dh1 and the per-sample LayerNorm scalars
 // m1 = mean_i(g1 dy1), m2 = mean_i(g1 dy1 xhat1), every layer-1 gradient is a linear function of
@@ -22,7 +25,7 @@
 // error matches autograd's own.
 //
 // Algorithmic bytes per sample: 44 B gathered (obs 24, action 4, old logp 4, adv 4, ret 4, old value 4);
-// nothing else leaves the SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 for the split),
+// nothing else leaves the SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 MMAs for the split),
 // ~14 000 on the CUDA cores.
 #include "ppo_loss.cuh"
 #include "tc_gemm.cuh"
@@ -58,12 +61,16 @@ static_assert(kTcGroups * kTcTile * 8 <= kChunkFloats, "exchange area must fit o
 static_assert(TcSmem::total * 4 + 64 <= 227 * 1024, "ppo_tc_kernel: shared memory plan exceeds 227 KB");
 static_assert(kTcTile * kStageStride <= kTcTile * kXhStride, "dy1 staging must fit in the xhat region");
 
-// layout of the pre-split weight workspace (floats)
-constexpr int kW2SplitG1Hi = 0;                       // [8 chunks][128 out][32 in]   (K = in)
-constexpr int kW2SplitG1Lo = 32768;
-constexpr int kW2SplitG2Hi = 65536;                   // [2 halves][4 chunks][128 in][32 out] (K = out)
-constexpr int kW2SplitG2Lo = 98304;
-constexpr int kW2SplitFloats = 131072;
+// layout of the pre-split weight workspace (float units; fp16 hi / lo operand chunks of 128 rows x 64 K = 16 KB each)
+constexpr int kW2SplitG1Hi = 0;                       // [4 chunks][128 out][64 in]   (K = in), lo scaled by 2^11
+constexpr int kW2SplitG1Lo = 16384;
+constexpr int kW2SplitG2Hi = 32768;                   // [2 halves][2 chunks][128 in][64 out] (K = out), 16 W2^T, lo unscaled
+constexpr int kW2SplitG2Lo = 49152;
+constexpr int kW2SplitFloats = 65536;
+// The backward GEMMs keep main and cross terms in ONE accumulator (TMEM is full), so their lo parts are not scaled;
+// instead the operands are brought to O(1): W2^T is multiplied by 16 (|w| ~ 0.1) and dz2 by a power of two near the
+// global batch size (dz2 ~ 1/batch), passed to the kernel as dz_scale.  Both are undone where the results are read.
+constexpr float kW2BwdScale = 16.0f;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -78,30 +85,41 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
-    tc::split_tf32(v.x, h.x, l.x);
-    tc::split_tf32(v.y, h.y, l.y);
-    tc::split_tf32(v.z, h.z, l.z);
-    tc::split_tf32(v.w, h.w, l.w);
-}
-
-// ---- W2 -> hi/lo operand chunks in the canonical K-major layout (once per minibatch) ---------------
+// ---- W2 -> fp16 hi/lo operand chunks in the canonical K-major layout (once per minibatch) -------------
+// One thread per 16-byte operand slot (8 consecutive K values of one row).
 __global__ void ppo_tc_prep_kernel(const float* __restrict__ params, float* __restrict__ w2s) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // element of W2[o][in]
-    if (i >= 128 * 256) return;
-    const int o = i >> 8, in = i & 255;
-    float hi, lo;
-    tc::split_tf32(params[PLUME_OFF_W2 + i], hi, lo);
-    const int g1 = (in >> 5) * kChunkFloats + tc::chunk_offset(o, in & 31);
-    w2s[kW2SplitG1Hi + g1] = hi;
-    w2s[kW2SplitG1Lo + g1] = lo;
-    const int g2 = ((in >> 7) * 4 + (o >> 5)) * kChunkFloats + tc::chunk_offset(in & 127, o & 31);
-    w2s[kW2SplitG2Hi + g2] = hi;
-    w2s[kW2SplitG2Lo + g2] = lo;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 8192) return;
+    float4 v0, v1;
+    int chunk_base, f;
+    float scale;
+    if (i < 4096) {                                   // G1: row = out o, K = in
+        const int o = i >> 5, in0 = (i & 31) * 8;
+        v0 = *reinterpret_cast<const float4*>(params + PLUME_OFF_W2 + o * 256 + in0);
+        v1 = *reinterpret_cast<const float4*>(params + PLUME_OFF_W2 + o * 256 + in0 + 4);
+        chunk_base = kW2SplitG1Hi + (in0 >> 6) * kChunkFloats;
+        f = (o >> 3) * 64 + ((in0 & 63) >> 3) * 8 + (o & 7);
+        scale = tc::kLoScale;
+    } else {                                          // G2: row = in (two halves of 128), K = out, values 16 W2[out][in]
+        const int j = i - 4096, in = j >> 4, out0 = (j & 15) * 8;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = kW2BwdScale * params[PLUME_OFF_W2 + (out0 + e) * 256 + in];
+        v0 = make_float4(w[0], w[1], w[2], w[3]);
+        v1 = make_float4(w[4], w[5], w[6], w[7]);
+        const int row = in & 127;
+        chunk_base = kW2SplitG2Hi + ((in >> 7) * 2 + (out0 >> 6)) * kChunkFloats;
+        f = (row >> 3) * 64 + ((out0 & 63) >> 3) * 8 + (row & 7);
+        scale = 1.0f;
+    }
+    uint4 hi, lo;
+    tc::split_f16x8(v0, v1, scale, hi, lo);
+    reinterpret_cast<uint4*>(w2s + chunk_base)[f] = hi;
+    reinterpret_cast<uint4*>(w2s + chunk_base + (kW2SplitG1Lo - kW2SplitG1Hi))[f] = lo;
 }
 
 __global__ void __launch_bounds__(kTcLaunchThreads, 1)
-ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s) {
+ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s, float dz_scale) {
     extern __shared__ __align__(128) float sm[];     // no-swizzle operand layouts need 16 B alignment only
     __shared__ uint64_t bar[2];           // "stage free": arrived by tcgen05.commit
     __shared__ uint64_t full[2];          // "operands of the stage written": one arrival per compute thread
@@ -195,7 +213,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     }
     __syncthreads();
 
-    const uint32_t idesc = tc::make_idesc_tf32(128, 128);
+    const uint32_t idesc = tc::make_idesc_f16(128, 128);
     float* const xh = sm + TcSmem::xh;
     const float* const W1c = sm + TcSmem::W1c;
     const float* const P1 = sm + TcSmem::P1;
@@ -238,11 +256,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::mbar_wait(&full[st & 1u], (st >> 1) & 1u);
         tc::tc_fence_after();
         if (col_small != col)
-            tc::mma_chunk_3xtf32_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),
-                                       stage_buf(st, 2), stage_buf(st, 3), idesc, first);
+            tc::mma_chunk_f16_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),
+                                    stage_buf(st, 2), stage_buf(st, 3), idesc, first);
         else
-            tc::mma_chunk_3xtf32(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
-                                 idesc, first);
+            tc::mma_chunk_f16(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
+                              idesc, first);
         tc::mma_commit(&bar[st & 1u]);
     };
     // every MMA of the steps counted so far has completed
@@ -262,10 +280,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             uint32_t st = 0;
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const bool first_tile = (tile == (long long)blockIdx.x);
-                for (int c = 0; c < 8; ++c, ++st) issue(st, 0u, c == 0, 128u);                          // G1
+                for (int c = 0; c < 4; ++c, ++st) issue(st, 0u, c == 0, 128u);                          // G1
                 for (int hN = 0; hN < 2; ++hN)
-                    for (int c = 0; c < 4; ++c, ++st) issue(st, (uint32_t)(128 * hN), c == 0, (uint32_t)(128 * hN));   // G2
-                for (int c = 0; c < 4; ++c)
+                    for (int c = 0; c < 2; ++c, ++st) issue(st, (uint32_t)(128 * hN), c == 0, (uint32_t)(128 * hN));   // G2
+                for (int c = 0; c < 2; ++c)
                     for (int hN = 0; hN < 2; ++hN, ++st)
                         issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0, (uint32_t)(256 + 128 * hN));       // G3
             }
@@ -362,39 +380,43 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         const float rstd1 = xt[r128 * 8 + 6];
 
-        // ---- Ph2: G1 forward, K = 256 inputs in 8 chunks; thread = (sample r128, 8/G of the 8 units) ----
-        for (int c = 0; c < 8; ++c) {
+        // ---- Ph2: G1 forward, K = 256 inputs in 4 chunks of 64; thread = (sample r128, 8/G of the 8 slots) ----
+        for (int c = 0; c < 4; ++c) {
             const uint32_t st = step;
             acquire(st);
             load_b(st, w2s + kW2SplitG1Hi + c * kChunkFloats, w2s + kW2SplitG1Lo + c * kChunkFloats);
-            float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
-            float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
+            uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
+            uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
 #pragma unroll
             for (int uu = 0; uu < UPT; ++uu) {
-                const int u = UPT * ug + uu, in0 = 32 * c + 4 * u;
-                float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+                const int u = UPT * ug + uu;
+                float4 hq[2];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
-                    z.x = fmaf(xr[k], w.x, z.x);
-                    z.y = fmaf(xr[k], w.y, z.y);
-                    z.z = fmaf(xr[k], w.z, z.z);
-                    z.w = fmaf(xr[k], w.w, z.w);
+                for (int q = 0; q < 2; ++q) {
+                    const int in0 = 64 * c + 8 * u + 4 * q;
+                    float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
+                        z.x = fmaf(xr[k], w.x, z.x);
+                        z.y = fmaf(xr[k], w.y, z.y);
+                        z.z = fmaf(xr[k], w.z, z.z);
+                        z.w = fmaf(xr[k], w.w, z.w);
+                    }
+                    const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
+                    const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
+                    hq[q].x = fmaxf(fmaf(z.x * rstd1, g.x, be.x), 0.0f);
+                    hq[q].y = fmaxf(fmaf(z.y * rstd1, g.y, be.y), 0.0f);
+                    hq[q].z = fmaxf(fmaf(z.z * rstd1, g.z, be.z), 0.0f);
+                    hq[q].w = fmaxf(fmaf(z.w * rstd1, g.w, be.w), 0.0f);
                 }
-                const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
-                const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
-                float4 h;
-                h.x = fmaxf(fmaf(z.x * rstd1, g.x, be.x), 0.0f);
-                h.y = fmaxf(fmaf(z.y * rstd1, g.y, be.y), 0.0f);
-                h.z = fmaxf(fmaf(z.z * rstd1, g.z, be.z), 0.0f);
-                h.w = fmaxf(fmaf(z.w * rstd1, g.w, be.w), 0.0f);
-                float4 hi, lo;
-                split4(h, hi, lo);
+                uint4 hi, lo;
+                tc::split_f16x8(hq[0], hq[1], tc::kLoScale, hi, lo);
                 const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
                 ah[f] = hi;
                 al[f] = lo;
             }
-            publish(st);          // issuer: G1 -> columns [0,128), small terms -> [128,256) (free until G2)
+            publish(st);          // issuer: G1 -> columns [0,128), scaled cross terms -> [128,256) (free until G2)
             ++step;
         }
         PLUME_TL(2);
@@ -413,7 +435,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 tc::tmem_ld32(taddr + 128u, sm_terms);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += sm_terms[j];
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(sm_terms[j], tc::kLoInv, v[j]);
             }
             tc::tc_fence_before();
             float sum = 0.0f;
@@ -584,21 +606,25 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         compute_sync();
 
         PLUME_TL(5);
-        // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 4 chunks ------------
+        // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 2 chunks of 64 ------
+        // (operands pre-scaled: dz_scale dz2 and 16 W2^T, unscaled lo, one accumulator; undone in Ph6)
         for (int hN = 0; hN < 2; ++hN) {
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 const uint32_t st = step;
                 acquire(st);
-                load_b(st, w2s + kW2SplitG2Hi + (hN * 4 + c) * kChunkFloats,
-                       w2s + kW2SplitG2Lo + (hN * 4 + c) * kChunkFloats);
-                float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
-                float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
+                load_b(st, w2s + kW2SplitG2Hi + (hN * 2 + c) * kChunkFloats,
+                       w2s + kW2SplitG2Lo + (hN * 2 + c) * kChunkFloats);
+                uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
+                uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
 #pragma unroll
                 for (int uu = 0; uu < UPT; ++uu) {
                     const int u = UPT * ug + uu;
-                    const float4 d = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 32 * c + 4 * u);
-                    float4 hi, lo;
-                    split4(d, hi, lo);
+                    float4 d0 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u);
+                    float4 d1 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u + 4);
+                    d0.x *= dz_scale; d0.y *= dz_scale; d0.z *= dz_scale; d0.w *= dz_scale;
+                    d1.x *= dz_scale; d1.y *= dz_scale; d1.z *= dz_scale; d1.w *= dz_scale;
+                    uint4 hi, lo;
+                    tc::split_f16x8(d0, d1, 1.0f, hi, lo);
                     const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
                     ah[f] = hi;
                     al[f] = lo;
@@ -609,15 +635,16 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
 
         PLUME_TL(6);
-        // ---- Ph7: G3 dW2 += dz2^T . h1, K = 128 samples in 4 chunks x two halves of the inputs -----------
-        for (int c = 0; c < 4; ++c) {
+        // ---- Ph7: G3 dW2 += dz2^T . h1, K = 128 samples in 2 chunks of 64 x two halves of the inputs ------
+        // (A = dz_scale dz2^T, B = h1^T, unscaled lo; the accumulator holds dz_scale dW2 until the flush)
+        for (int c = 0; c < 2; ++c) {
             for (int hN = 0; hN < 2; ++hN) {
                 const uint32_t st = step;
                 acquire(st);
-                float4* ah = reinterpret_cast<float4*>(stage_buf(st, 0));
-                float4* al = reinterpret_cast<float4*>(stage_buf(st, 1));
-                float4* bh4 = reinterpret_cast<float4*>(stage_buf(st, 2));
-                float4* bl4 = reinterpret_cast<float4*>(stage_buf(st, 3));
+                uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
+                uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
+                uint4* bh4 = reinterpret_cast<uint4*>(stage_buf(st, 2));
+                uint4* bl4 = reinterpret_cast<uint4*>(stage_buf(st, 3));
                 const int in = 128 * hN + r128;
                 float w[6];
 #pragma unroll
@@ -625,22 +652,20 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const float b1c = P1[in], g1 = P1[256 + in], be1 = P1[512 + in];
 #pragma unroll
                 for (int uu = 0; uu < UPT; ++uu) {
-                    const int u = UPT * ug + uu, s0 = 32 * c + 4 * u;
+                    const int u = UPT * ug + uu, s0 = 64 * c + 8 * u;
                     const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
-                    // A: dz2^T, row = output r128, 4 consecutive samples
-                    float4 d;
-                    d.x = xh[(s0 + 0) * kXhStride + r128];
-                    d.y = xh[(s0 + 1) * kXhStride + r128];
-                    d.z = xh[(s0 + 2) * kXhStride + r128];
-                    d.w = xh[(s0 + 3) * kXhStride + r128];
-                    float4 hi, lo;
-                    split4(d, hi, lo);
+                    // A: dz2^T, row = output r128, 8 consecutive samples
+                    float d[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[i] = xh[(s0 + i) * kXhStride + r128] * dz_scale;
+                    uint4 hi, lo;
+                    tc::split_f16x8(make_float4(d[0], d[1], d[2], d[3]), make_float4(d[4], d[5], d[6], d[7]), 1.0f, hi, lo);
                     ah[f] = hi;
                     al[f] = lo;
-                    // B: h1^T, row = input `in`, the same 4 samples (recomputed from the 6 inputs)
-                    float hv[4];
+                    // B: h1^T, row = input `in`, the same 8 samples (recomputed from the 6 inputs)
+                    float hv[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         const float4 x0 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8);
                         const float4 x1 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8 + 4);
                         float z = b1c;
@@ -652,7 +677,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                         z = fmaf(x1.y, w[5], z);
                         hv[i] = fmaxf(fmaf(z * x1.z, g1, be1), 0.0f);
                     }
-                    split4(make_float4(hv[0], hv[1], hv[2], hv[3]), hi, lo);
+                    tc::split_f16x8(make_float4(hv[0], hv[1], hv[2], hv[3]), make_float4(hv[4], hv[5], hv[6], hv[7]), 1.0f,
+                                    hi, lo);
                     bh4[f] = hi;
                     bl4[f] = lo;
                 }
@@ -669,6 +695,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             prefetch_tile(tile + gridDim.x);      // the next tile's gather rides under this CUDA-core phase
             tc::tc_fence_after();
             float m1p = 0.0f, m2p = 0.0f;
+            const float dh_unscale = 1.0f / (dz_scale * kW2BwdScale);      // exact: both are powers of two
             // this thread's sample: inputs + rstd1
             const float4 sx0 = *reinterpret_cast<const float4*>(xt + srow * 8);
             const float4 sx1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
@@ -699,7 +726,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     for (int jj = 0; jj < 4; ++jj) {
                         const float x_hat = zz[jj] * sx1.z;
                         const float y = fmaf(x_hat, gg[jj], bb[jj]);
-                        const float dy = (y > 0.0f) ? v[4 * j4 + jj] : 0.0f;
+                        const float dy = (y > 0.0f) ? v[4 * j4 + jj] * dh_unscale : 0.0f;
                         const float t = dy * gg[jj];
                         m1p += t;
                         m2p = fmaf(t, x_hat, m2p);
@@ -797,9 +824,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(256 + col), vv);
             tc::tmem_ld_wait();
             float4* dst = reinterpret_cast<float4*>(g + PLUME_OFF_W2 + srow * 256 + col);
+            const float un = 1.0f / dz_scale;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                atomicAdd(dst + i, make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]));
+                atomicAdd(dst + i, make_float4(vv[4 * i] * un, vv[4 * i + 1] * un, vv[4 * i + 2] * un, vv[4 * i + 3] * un));
         }
         tc::tc_fence_before();
     }
@@ -888,13 +916,16 @@ int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaSt
         configured = true;
     }
     float* w2s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-    ppo_tc_prep_kernel<<<128, 256, 0, s>>>(params, w2s);
+    ppo_tc_prep_kernel<<<32, 256, 0, s>>>(params, w2s);
     if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_prep_kernel launch failed");
     const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
     int grid = sm_count();
     if (grid <= 0) return fail("no CUDA device");
     if (tiles < grid) grid = (int)tiles;
-    ppo_tc_kernel<<<grid, kTcLaunchThreads, smem, s>>>(params, a, w2s);
+    // dz2 ~ O(1..100) / global batch: a power of two 16x below the batch size brings it to O(0.1..10), four orders of
+    // magnitude under fp16's largest value
+    const float dz_scale = exp2f(floorf(log2f(1.0f / a.inv_global)) - 4.0f);
+    ppo_tc_kernel<<<grid, kTcLaunchThreads, smem, s>>>(params, a, w2s, dz_scale);
     if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_kernel launch failed");
     return 0;
 }

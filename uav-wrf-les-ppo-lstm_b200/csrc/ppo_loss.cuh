@@ -32,16 +32,17 @@ struct SampleLoss {
     bool nan;
 };
 
-// o[0..4] logits, o[5] value.
-__device__ __forceinline__ SampleLoss ppo_sample_loss(const float* o, int act, float adv, float ret, float vold,
-                                                      float lpold, float clip_eps, float entropy_beta,
-                                                      float inv_global) {
-    SampleLoss r;
-    r.nan = false;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) r.nan |= isnan(o[k]);                    // :57-61
-    float p[5];
-    softmax5(o, p);
+// The per-sample loss in two independent halves (each starts from the softmax of the 5 logits), so that the
+// tensor-core kernel can run them in two warps of the same scheduler instead of one long instruction stream.
+
+// Clipped surrogate + clipped value loss (train_ppo2.0.py:63-77).  dpol[k] = d pol / d logits[k], dv = d val / d value
+// (not yet divided by the batch size).
+struct PolicyValuePart {
+    float dpol[5], dv, pol, val;
+};
+__device__ __forceinline__ PolicyValuePart ppo_policy_value_part(const float* p, float v, int act, float adv, float ret,
+                                                                 float vold, float lpold, float clip_eps) {
+    PolicyValuePart r;
     float S = 0.0f;
 #pragma unroll
     for (int k = 0; k < 5; ++k) S += p[k];
@@ -66,17 +67,30 @@ __device__ __forceinline__ SampleLoss ppo_sample_loss(const float* o, int act, f
     const float dlp = q_inside ? dratio * ratio : 0.0f;
     r.pol = -fminf(s1, s2);                                           // :70
     // value loss :73-77
-    const float v = o[5];
     const float dvv = v - vold;
     const bool v_inside = (dvv >= -clip_eps) && (dvv <= clip_eps);
     const float vclip = vold + fminf(fmaxf(dvv, -clip_eps), clip_eps);
     const float e1 = (v - ret) * (v - ret), e2 = (vclip - ret) * (vclip - ret);
-    float dv;
-    if (e1 > e2) dv = (v - ret);
-    else if (e2 > e1) dv = v_inside ? (vclip - ret) : 0.0f;
-    else dv = 0.5f * (v - ret) + (v_inside ? 0.5f * (vclip - ret) : 0.0f);
+    if (e1 > e2) r.dv = (v - ret);
+    else if (e2 > e1) r.dv = v_inside ? (vclip - ret) : 0.0f;
+    else r.dv = 0.5f * (v - ret) + (v_inside ? 0.5f * (vclip - ret) : 0.0f);
     r.val = 0.5f * fmaxf(e1, e2);
-    // entropy :80
+    // log q = log p_a - log S: the renormalisation of Categorical(probs) contributes -(1 - S)/S p_k (S = 1 up to rounding)
+    const float renorm = (1.0f - S) / S;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float onehot = (act == k) ? 1.0f : 0.0f;
+        r.dpol[k] = dlp * ((onehot - p[k]) - p[k] * renorm);
+    }
+    return r;
+}
+
+// Entropy bonus -mean(sum p log(p + 1e-8)) (:80).  dent[k] = d(-beta ent) / d logits[k] (not yet divided by the batch).
+struct EntropyPart {
+    float dent[5], ent;
+};
+__device__ __forceinline__ EntropyPart ppo_entropy_part(const float* p, float entropy_beta) {
+    EntropyPart r;
     float ent = 0.0f, gbar = 0.0f, gk[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -86,15 +100,29 @@ __device__ __forceinline__ SampleLoss ppo_sample_loss(const float* o, int act, f
         gbar += gk[k] * p[k];
     }
     r.ent = ent;
-    // d total / d logits_j, total = pol + val - beta*ent (:82), all means over the batch
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const float onehot = (act == k) ? 1.0f : 0.0f;
-        const float d_pol = dlp * ((onehot - p[k]) - p[k] * (1.0f - S) / S);
-        const float d_ent = entropy_beta * p[k] * (gk[k] - gbar);
-        r.dout[k] = (d_pol + d_ent) * inv_global;
-    }
-    r.dout[5] = dv * inv_global;
+    for (int k = 0; k < 5; ++k) r.dent[k] = entropy_beta * p[k] * (gk[k] - gbar);
+    return r;
+}
+
+// o[0..4] logits, o[5] value; total = pol + val - beta*ent (:82), all means over the batch.
+__device__ __forceinline__ SampleLoss ppo_sample_loss(const float* o, int act, float adv, float ret, float vold,
+                                                      float lpold, float clip_eps, float entropy_beta,
+                                                      float inv_global) {
+    SampleLoss r;
+    r.nan = false;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r.nan |= isnan(o[k]);                    // :57-61
+    float p[5];
+    softmax5(o, p);
+    const PolicyValuePart pv = ppo_policy_value_part(p, o[5], act, adv, ret, vold, lpold, clip_eps);
+    const EntropyPart en = ppo_entropy_part(p, entropy_beta);
+    r.pol = pv.pol;
+    r.val = pv.val;
+    r.ent = en.ent;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r.dout[k] = pv.dpol[k] * inv_global + en.dent[k] * inv_global;
+    r.dout[5] = pv.dv * inv_global;
     return r;
 }
 

@@ -67,6 +67,12 @@ constexpr int kW2SplitG1Lo = 16384;
 constexpr int kW2SplitG2Hi = 32768;                   // [2 halves][2 chunks][128 in][64 out] (K = out), 16 W2^T, lo unscaled
 constexpr int kW2SplitG2Lo = 49152;
 constexpr int kW2SplitFloats = 65536;
+// per-launch invariants of layer 1, evaluated once by the last block of the prep kernel instead of by every CTA:
+constexpr int kWsW1c = kW2SplitFloats;                // [6][256] feature.0.weight minus its column means, k-major
+constexpr int kWsB1c = kWsW1c + 6 * 256;              // [256]    feature.0.bias minus its mean
+constexpr int kWsLn1q = kWsB1c + 256;                 // [28] doubles: the LayerNorm-1 quadratic form (see ln1q below)
+constexpr int kWsFloats = kWsLn1q + 2 * 28;
+static_assert((kWsLn1q % 2) == 0, "the float64 coefficients must be 8-byte aligned");
 // The backward GEMMs keep main and cross terms in ONE accumulator (TMEM is full), so their lo parts are not scaled;
 // instead the operands are brought to O(1): W2^T is multiplied by 16 (|w| ~ 0.1) and dz2 by a power of two near the
 // global batch size (dz2 ~ 1/batch), passed to the kernel as dz_scale.  Both are undone where the results are read.
@@ -87,7 +93,72 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // ---- W2 -> fp16 hi/lo operand chunks in the canonical K-major layout (once per minibatch) -------------
 // One thread per 16-byte operand slot (8 consecutive K values of one row).
-__global__ void ppo_tc_prep_kernel(const float* __restrict__ params, float* __restrict__ w2s) {
+constexpr int kPrepSplitBlocks = 32;                  // 32 x 256 threads = 8192 operand slots; block 32 = layer-1 block
+__global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restrict__ params, float* __restrict__ w2s) {
+    if (blockIdx.x == kPrepSplitBlocks) {
+        // ---- layer-1 invariants: thread = output o --------------------------------------------------------------
+        // z_o - mean_o(z) = (b_o - mean b) + sum_k x_k (w_ok - mean_o w_ok): centred weights make the LayerNorm-1 mean
+        // pass unnecessary, and sum_o z_o^2 = q0 + sum_k q1[k] x_k + sum_{k<=l} q2[kl] x_k x_l (28 float64 coefficients)
+        // replaces the variance pass.  Fixed reduction order (shuffle tree, then warps 0..7): deterministic.
+        __shared__ float s_part[8][7];
+        __shared__ float s_mean[7];
+        __shared__ double s_q[8][28];
+        const int o = threadIdx.x, warp = o >> 5, lane = o & 31;
+        float w[7];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = params[PLUME_OFF_W1 + o * 6 + k];
+        w[6] = params[PLUME_OFF_B1 + o];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            float t = w[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0) s_part[warp][k] = t;
+        }
+        __syncthreads();
+        if (o < 7) {
+            float t = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += s_part[q][o];
+            s_mean[o] = t * (1.0f / 256.0f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 7; ++k) w[k] -= s_mean[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w2s[kWsW1c + k * 256 + o] = w[k];
+        w2s[kWsB1c + o] = w[6];
+        double q[28];
+        const double b = (double)w[6];
+        q[0] = b * b;
+        {
+            int qi = 7;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                q[1 + k] = 2.0 * b * (double)w[k];
+#pragma unroll
+                for (int l = k; l < 6; ++l) {
+                    q[qi] = (k == l ? 1.0 : 2.0) * (double)w[k] * (double)w[l];
+                    ++qi;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 28; ++c) {
+            double t = q[c];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0) s_q[warp][c] = t;
+        }
+        __syncthreads();
+        if (o < 28) {
+            double t = 0.0;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) t += s_q[qq][o];
+            reinterpret_cast<double*>(w2s + kWsLn1q)[o] = t;
+        }
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 8192) return;
     float4 v0, v1;
@@ -127,7 +198,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __shared__ float cta_acc[48];         // per-CTA sums of the per-sample scalars (see the flush)
     __shared__ double cta_loss[4];
     // LayerNorm-1 variance as a quadratic form of the 6 inputs: sum_o z_o^2 = q0 + sum_k q1[k] x_k + sum_{k<=l} q2[kl] x_k x_l
-    // with z_o = b_o + sum_k x_k w_ko from the CENTRED weights (so mean_o z_o = 0); 28 coefficients per launch
+    // with z_o = b_o + sum_k x_k w_ko from the CENTRED weights (so mean_o z_o = 0); 28 coefficients per launch,
+    // evaluated by the prep kernel
     __shared__ double ln1q[28];
 
     constexpr int G = kTcGroups;
@@ -137,6 +209,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     static_assert(CW == 32 && UPT >= 1, "the epilogues read one 32-column TMEM slab per thread");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef PLUME_TC_TIMELINE
+    long long kt_[4] = {0, 0, 0, 0};
+    const bool kt_on = (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tid == 0;
+    if (kt_on) kt_[0] = clock64();
+#endif
     const int wq = warp & 3, cg = (warp >> 2) & (G - 1);   // TMEM lane quarter / column group of this warp
     const int srow = wq * 32 + lane;                       // TMEM lane = tile row owned in the epilogues
     const int r128 = tid & 127, ug = (tid >> 7) & (G - 1); // (row, group) mapping of the producer phases
@@ -155,22 +232,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     float* const exch = sm + TcSmem::exch;
     // exchange slot k of column group g, row r: slot-major, so that the 32 rows of a warp hit 32 banks
     auto EX = [&](int k, int g, int r) -> float& { return exch[(k * G + g) * kTcTile + r]; };
-    if (tid < 7) {          // column means of feature.0.weight (k < 6) and the mean of feature.0.bias
-        float m = 0.0f;
-        for (int o = 0; o < 256; ++o) m += (tid < 6) ? params[PLUME_OFF_W1 + o * 6 + tid] : params[PLUME_OFF_B1 + o];
-        exch[tid] = m * (1.0f / 256.0f);
-    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
     if (tid < kTcThreads) {
-        for (int i = tid; i < 6 * 256; i += kTcThreads) {
-            const int o = i / 6, k = i - o * 6;
-            sm[TcSmem::W1c + k * 256 + o] = params[PLUME_OFF_W1 + i] - exch[k];
-        }
+        // centred layer-1 weights / bias and the quadratic form come from the prep kernel's layer-1 block
+        for (int i = tid; i < 6 * 256; i += kTcThreads) sm[TcSmem::W1c + i] = w2s[kWsW1c + i];
         for (int i = tid; i < 256; i += kTcThreads) {
-            sm[TcSmem::P1 + i] = params[PLUME_OFF_B1 + i] - exch[6];
+            sm[TcSmem::P1 + i] = w2s[kWsB1c + i];
             sm[TcSmem::P1 + 256 + i] = params[PLUME_OFF_G1 + i];
             sm[TcSmem::P1 + 512 + i] = params[PLUME_OFF_BE1 + i];
         }
@@ -188,31 +258,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         if (tid < 8)
             sm[TcSmem::bh + tid] = tid < 5 ? params[PLUME_OFF_BA + tid] : (tid == 5 ? params[PLUME_OFF_BC] : 0.0f);
-    }
-    __syncthreads();
-    if (tid < 28) {
-        int k = -1, l = -1;                 // tid 0: |b|^2; 1..6: 2 b.w_k; 7..27: (k <= l) pairs
-        if (tid >= 1 && tid <= 6) k = tid - 1;
-        if (tid >= 7) {
-            int r = tid - 7;
-            k = 0;
-            while (r >= 6 - k) {
-                r -= 6 - k;
-                ++k;
-            }
-            l = k + r;
-        }
-        double acc = 0.0;
-        for (int o = 0; o < 256; ++o) {
-            const double b = (double)sm[TcSmem::P1 + o];
-            const double wk = k >= 0 ? (double)sm[TcSmem::W1c + k * 256 + o] : 0.0;
-            const double wl = l >= 0 ? (double)sm[TcSmem::W1c + l * 256 + o] : 0.0;
-            acc += tid == 0 ? b * b : (tid <= 6 ? 2.0 * b * wk : (k == l ? wk * wl : 2.0 * wk * wl));
-        }
-        ln1q[tid] = acc;
+        if (tid < 28) ln1q[tid] = reinterpret_cast<const double*>(w2s + kWsLn1q)[tid];
     }
     __syncthreads();
 
+#ifdef PLUME_TC_TIMELINE
+    if (kt_on) kt_[1] = clock64();
+#endif
     const uint32_t idesc = tc::make_idesc_f16(128, 128);
     float* const xh = sm + TcSmem::xh;
     const float* const W1c = sm + TcSmem::W1c;
@@ -324,7 +376,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 #ifdef PLUME_TC_TIMELINE
-        long long tl_[12];
+        long long tl_[16];
         const bool tl_on = blockIdx.x == 0 && tid == 0 && tile == (long long)blockIdx.x + 3 * gridDim.x;
 #define PLUME_TL(n) if (tl_on) tl_[n] = clock64()
 #else
@@ -339,17 +391,17 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         if (tile == (long long)blockIdx.x) prefetch_tile(tile);
         cp_async_wait_all();
         compute_sync();
-        float r_adv = 0.0f, r_ret = 0.0f, r_vold = 0.0f, r_lpold = 0.0f;
-        int r_act = 0;
+        float s_adv = 0.0f, s_ret = 0.0f, s_vold = 0.0f, s_lpold = 0.0f;
+        int s_act = 0;
         if (tid < kTcTile) {
             const float4 q0 = *reinterpret_cast<const float4*>(pf + tid * 12);
             const float4 q1 = *reinterpret_cast<const float4*>(pf + tid * 12 + 4);
             const float4 q2 = *reinterpret_cast<const float4*>(pf + tid * 12 + 8);
-            r_adv = q1.z;
-            r_ret = q1.w;
-            r_vold = q2.x;
-            r_lpold = q2.y;
-            r_act = __float_as_int(q2.z);
+            s_adv = q1.z;
+            s_ret = q1.w;
+            s_vold = q2.x;
+            s_lpold = q2.y;
+            s_act = __float_as_int(q2.z);
             // LayerNorm-1 rstd of this sample from the quadratic form (float64: 48 operations instead of the
             // 1800 FMAs of evaluating all 256 pre-activations once more just for their sum of squares)
             const double xd[6] = {(double)q0.x, (double)q0.y, (double)q0.z, (double)q0.w, (double)q1.x, (double)q1.y};
@@ -367,6 +419,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             const float rstd1_s = (float)(1.0 / sqrt(ssq * (1.0 / 256.0) + (double)kLnEps));
             *reinterpret_cast<float4*>(xt + tid * 8) = q0;
             *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(q1.x, q1.y, rstd1_s, 0.0f);
+            // d loss / d (logits, value) of this tile: the two loss halves of Ph3 add into it
+            *reinterpret_cast<float4*>(sm + TcSmem::dout + tid * 8) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            *reinterpret_cast<float4*>(sm + TcSmem::dout + tid * 8 + 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         compute_sync();
 
@@ -444,24 +499,31 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 v[j] += P2[c0 + j];
                 sum += v[j];
             }
+            // LayerNorm-2 statistics with ONE exchange: each column group contributes its sum and the sum of squares about
+            // its OWN mean; the groups are merged with the pairwise update M2 = sum_g [M2_g + 32 (mean_g - mean)^2]
+            // (as accurate as the two-pass form, one barrier less per tile)
+            const float mean_g = sum * (1.0f / (float)CW);
+            float sq = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                const float d = v[j] - mean_g;
+                sq = fmaf(d, d, sq);
+            }
             EX(6, cg, srow) = sum;
+            EX(7, cg, srow) = sq;
             compute_sync();
             float tot = 0.0f;
 #pragma unroll
             for (int g = 0; g < G; ++g) tot += EX(6, g, srow);
             const float mean = tot * (1.0f / 128.0f);
-            float sq = 0.0f;
+            float m2 = 0.0f;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-                const float d = v[j] - mean;
-                sq = fmaf(d, d, sq);
+            for (int g = 0; g < G; ++g) {
+                const float dm = EX(6, g, srow) * (1.0f / (float)CW) - mean;
+                m2 += fmaf((float)CW * dm, dm, EX(7, g, srow));
             }
-            EX(7, cg, srow) = sq;
-            compute_sync();
-            tot = 0.0f;
-#pragma unroll
-            for (int g = 0; g < G; ++g) tot += EX(7, g, srow);
-            const float rstd2 = 1.0f / sqrtf(tot * (1.0f / 128.0f) + kLnEps);
+            const float rstd2 = 1.0f / sqrtf(m2 * (1.0f / 128.0f) + kLnEps);
+            PLUME_TL(10);
             float head[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -485,9 +547,16 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
             for (int k = 0; k < 6; ++k) EX(k, cg, srow) = head[k];
             compute_sync();
-            if (cg == 0) {          // srow == tid: the thread that gathered this sample
-                float dl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                double l_tot = 0.0, l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
+            PLUME_TL(11);
+            // The per-sample loss runs as two halves in two warps of the SAME scheduler (cg = 0: surrogate + value,
+            // cg = 1: entropy; warps wq and 4 + wq), each from its own softmax; both add their part of d loss / d logits
+            // into dout[.][0..4] (zeroed in Ph0; two addends, so the order does not matter).  dout[.][5] = d loss / d value,
+            // dout[.][6], [7] and sc[.][3] carry the sample's policy / value / entropy terms: their sums over the tile
+            // (and those of dout = the head-bias gradients) are taken by all 16 warps in the scalar-sum phase at the end of
+            // the tile, not by these warps while the others wait.
+            if (cg < 2) {
+                float* dop = sm + TcSmem::dout + srow * 8;
+                float l_ent = 0.0f, dv = 0.0f, l_pol = 0.0f, l_val = 0.0f;
                 if (srow < n_valid) {
                     float o6[6];
 #pragma unroll
@@ -497,44 +566,38 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                         for (int g = 0; g < G; ++g) t += EX(k, g, srow);
                         o6[k] = t;
                     }
-                    const SampleLoss L = ppo_sample_loss(o6, r_act, r_adv, r_ret, r_vold, r_lpold, a.clip_eps,
-                                                         a.entropy_beta, a.inv_global);
-                    if (L.nan) atomicExch(a.nan_flag, 1);                           // train_ppo2.0.py:57-61
+                    float p[5];
+                    softmax5(o6, p);
+                    if (cg == 0) {
+                        bool bad = false;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) dl[k] = L.dout[k];
-                    l_pol = (double)L.pol;
-                    l_val = (double)L.val;
-                    l_ent = (double)L.ent;
-                    l_tot = (double)L.pol + (double)L.val - (double)a.entropy_beta * (double)L.ent;
-                }
-                // head-bias gradients and the loss sums of this warp's 32 samples -> per-CTA accumulators
-                {
-                    float gb[6];
+                        for (int k = 0; k < 5; ++k) bad |= isnan(o6[k]);
+                        if (bad) atomicExch(a.nan_flag, 1);                         // train_ppo2.0.py:57-61
+                        const PolicyValuePart pv = ppo_policy_value_part(p, o6[5], s_act, s_adv, s_ret, s_vold, s_lpold,
+                                                                         a.clip_eps);
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        gb[k] = dl[k];
+                        for (int k = 0; k < 5; ++k) atomicAdd(dop + k, pv.dpol[k] * a.inv_global);
+                        dv = pv.dv * a.inv_global;
+                        l_pol = pv.pol;
+                        l_val = pv.val;
+                    } else {
+                        const EntropyPart en = ppo_entropy_part(p, a.entropy_beta);
 #pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) gb[k] += __shfl_xor_sync(0xffffffffu, gb[k], off);
-                    }
-                    for (int off = 16; off > 0; off >>= 1) {
-                        l_tot += __shfl_xor_sync(0xffffffffu, l_tot, off);
-                        l_pol += __shfl_xor_sync(0xffffffffu, l_pol, off);
-                        l_val += __shfl_xor_sync(0xffffffffu, l_val, off);
-                        l_ent += __shfl_xor_sync(0xffffffffu, l_ent, off);
-                    }
-                    if (lane == 0) {
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) atomicAdd(&cta_acc[35 + k], gb[k]);
-                        atomicAdd(&cta_loss[0], l_tot);
-                        atomicAdd(&cta_loss[1], l_pol);
-                        atomicAdd(&cta_loss[2], l_val);
-                        atomicAdd(&cta_loss[3], l_ent);
+                        for (int k = 0; k < 5; ++k) atomicAdd(dop + k, en.dent[k] * a.inv_global);
+                        l_ent = en.ent;
                     }
                 }
-                *reinterpret_cast<float4*>(sm + TcSmem::dout + srow * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-                *reinterpret_cast<float4*>(sm + TcSmem::dout + srow * 8 + 4) = make_float4(dl[4], dl[5], 0.0f, 0.0f);
+                if (cg == 0) {
+                    dop[5] = dv;
+                    dop[6] = l_pol;
+                    dop[7] = l_val;
+                } else {
+                    sm[TcSmem::sc + srow * 4 + 3] = l_ent;
+                }
+                PLUME_TL(12);
             }
             compute_sync();
+            PLUME_TL(13);
             const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8);
             const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8 + 4);
             float m1p = 0.0f, m2p = 0.0f;
@@ -565,8 +628,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     t1 += EX(6, g, srow);
                     t2 += EX(7, g, srow);
                 }
-                *reinterpret_cast<float4*>(sm + TcSmem::sc + srow * 4) =
-                    make_float4(rstd2, t1 * (1.0f / 128.0f), t2 * (1.0f / 128.0f), 0.0f);
+                float* scp = sm + TcSmem::sc + srow * 4;          // [3] = the sample's entropy term (written above)
+                scp[0] = rstd2;
+                scp[1] = t1 * (1.0f / 128.0f);
+                scp[2] = t2 * (1.0f / 128.0f);
             }
             compute_sync();
         }
@@ -600,14 +665,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 g_be2 += dy;
                 const float dz = sc.x * (dy * g2 - sc.y - x_hat * sc.z);
                 g_b2 += dz;
-                xh[s * kXhStride + o] = dz;                       // dz2 replaces xhat2
+                xh[s * kXhStride + o] = dz * dz_scale;            // dz_scale dz2 (exact: a power of two) replaces xhat2
             }
         }
         compute_sync();
 
         PLUME_TL(5);
         // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 2 chunks of 64 ------
-        // (operands pre-scaled: dz_scale dz2 and 16 W2^T, unscaled lo, one accumulator; undone in Ph6)
+        // (operands pre-scaled: dz_scale dz2 -- stored that way by Ph4 -- and 16 W2^T, unscaled lo, one accumulator;
+        // undone in Ph6)
         for (int hN = 0; hN < 2; ++hN) {
             for (int c = 0; c < 2; ++c) {
                 const uint32_t st = step;
@@ -619,10 +685,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
                 for (int uu = 0; uu < UPT; ++uu) {
                     const int u = UPT * ug + uu;
-                    float4 d0 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u);
-                    float4 d1 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u + 4);
-                    d0.x *= dz_scale; d0.y *= dz_scale; d0.z *= dz_scale; d0.w *= dz_scale;
-                    d1.x *= dz_scale; d1.y *= dz_scale; d1.z *= dz_scale; d1.w *= dz_scale;
+                    const float4 d0 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u);
+                    const float4 d1 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u + 4);
                     uint4 hi, lo;
                     tc::split_f16x8(d0, d1, 1.0f, hi, lo);
                     const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
@@ -657,7 +721,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     // A: dz2^T, row = output r128, 8 consecutive samples
                     float d[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) d[i] = xh[(s0 + i) * kXhStride + r128] * dz_scale;
+                    for (int i = 0; i < 8; ++i) d[i] = xh[(s0 + i) * kXhStride + r128];
                     uint4 hi, lo;
                     tc::split_f16x8(make_float4(d[0], d[1], d[2], d[3]), make_float4(d[4], d[5], d[6], d[7]), 1.0f, hi, lo);
                     ah[f] = hi;
@@ -791,12 +855,35 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 for (int k = 0; k < 35; ++k) xh[k * kTcTile + srow] = red[k];
             }
             compute_sync();
-            for (int k = warp; k < 35; k += kTcThreads / 32) {
-                const float* rowp = xh + k * kTcTile + lane;
-                float sred = (rowp[0] + rowp[32]) + (rowp[64] + rowp[96]);
+            // rows 0..34: the layer-1 scalars staged above; 35..40: d loss / d head outputs (= head-bias gradients);
+            // 41, 42, 43: policy / value / entropy terms of the loss (tile sums in float32, accumulated in float64).
+            // Warp w owns rows w, w + 16, w + 32: three independent load + shuffle chains in flight.
+            {
+                float sred[3];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, off);
-                if (lane == 0) cta_acc[k] += sred;          // row k belongs to exactly one warp
+                for (int r = 0; r < 3; ++r) {
+                    const int k = warp + 16 * r;
+                    sred[r] = 0.0f;
+                    if (k < 44) {
+                        const float* rowp = k < 35 ? xh + k * kTcTile + lane
+                                                   : (k < 43 ? sm + TcSmem::dout + lane * 8 + (k - 35)
+                                                             : sm + TcSmem::sc + lane * 4 + 3);
+                        const int rs = k < 35 ? 32 : (k < 43 ? 32 * 8 : 32 * 4);
+                        sred[r] = (rowp[0] + rowp[rs]) + (rowp[2 * rs] + rowp[3 * rs]);
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) sred[r] += __shfl_xor_sync(0xffffffffu, sred[r], off);
+                if (lane == 0) {                            // every row belongs to exactly one warp
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const int k = warp + 16 * r;
+                        if (k < 41) cta_acc[k] += sred[r];
+                        else if (k < 44) cta_loss[k - 40] += (double)sred[r];
+                    }
+                }
             }
         PLUME_TL(9);
             compute_sync();       // exch / x tile / staging are rewritten by the next tile
@@ -805,14 +892,19 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         if (tl_on) {
             const long long end = clock64();
             printf("ppo_tc timeline (cycles): Ph0 gather+rstd %lld | G1 production %lld | G1 mma drain %lld | Ph3 LN2/loss %lld | "
-                   "Ph4 %lld | G2 production %lld | G3 production %lld | Ph6 columns %lld | drain %lld | Ph6 scalars %lld | tail %lld | total %lld\n",
+                   "Ph4 %lld | G2 production %lld | G3 production %lld | Ph6 columns %lld | drain %lld | Ph6 scalars %lld | tail %lld | total %lld"
+                   " || Ph3: stats %lld | heads %lld | loss %lld | loss barrier %lld | LN2-bwd means %lld\n",
                    tl_[1] - tl_[0], tl_[2] - tl_[1], tl_[3] - tl_[2], tl_[4] - tl_[3], tl_[5] - tl_[4], tl_[6] - tl_[5],
-                   tl_[7] - tl_[6], tl_[8] - tl_[7], 0LL, tl_[9] - tl_[8], end - tl_[9], end - tl_[0]);
+                   tl_[7] - tl_[6], tl_[8] - tl_[7], 0LL, tl_[9] - tl_[8], end - tl_[9], end - tl_[0],
+                   tl_[10] - tl_[3], tl_[11] - tl_[10], tl_[12] - tl_[11], tl_[13] - tl_[12], tl_[4] - tl_[13]);
         }
 #endif
     }
 
     // ---- flush ------------------------------------------------------------------------------------------
+#ifdef PLUME_TC_TIMELINE
+    if (kt_on) kt_[2] = clock64();
+#endif
     float* g = a.grads;
     if (step > 0) {
         wait_all_mma();
@@ -848,7 +940,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
         for (int c = 0; c < 8; ++c) pbuf[(ug * 256 + 128 * h + r128) * 8 + c] = Pacc[h][c];
     compute_sync();
-    if (tid < 4) atomicAdd(a.loss_out + tid, cta_loss[tid] * (double)a.inv_global);
+    if (tid < 4) {                       // total = policy + value - beta * entropy (train_ppo2.0.py:82)
+        const double lsum = tid == 0 ? cta_loss[1] + cta_loss[2] - (double)a.entropy_beta * cta_loss[3] : cta_loss[tid];
+        atomicAdd(a.loss_out + tid, lsum * (double)a.inv_global);
+    }
     if (tid < 256) {
         float S[41];
 #pragma unroll
@@ -898,6 +993,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             atomicAdd(g + PLUME_OFF_W1 + in * 6 + k2, g1 * P[k2] - S[1 + k2] - wq2);
         }
     }
+#ifdef PLUME_TC_TIMELINE
+    if (kt_on)
+        printf("ppo_tc kernel timeline CTA %d (cycles): prologue %lld | tiles %lld | flush %lld\n", (int)blockIdx.x,
+               kt_[1] - kt_[0], kt_[2] - kt_[1], clock64() - kt_[2]);
+#endif
     }   // compute warps
     tc::tc_fence_before();
     __syncthreads();
@@ -905,7 +1005,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------
-int64_t ppo_tc_workspace_bytes() { return (int64_t)kW2SplitFloats * (int64_t)sizeof(float) + 256; }
+int64_t ppo_tc_workspace_bytes() { return (int64_t)kWsFloats * (int64_t)sizeof(float) + 256; }
 
 int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s) {
     static bool configured = false;
@@ -916,7 +1016,7 @@ int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaSt
         configured = true;
     }
     float* w2s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-    ppo_tc_prep_kernel<<<32, 256, 0, s>>>(params, w2s);
+    ppo_tc_prep_kernel<<<kPrepSplitBlocks + 1, 256, 0, s>>>(params, w2s);
     if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_prep_kernel launch failed");
     const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
     int grid = sm_count();

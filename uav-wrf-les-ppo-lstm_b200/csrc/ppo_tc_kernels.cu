@@ -78,6 +78,11 @@ static_assert((kWsLn1q % 2) == 0, "the float64 coefficients must be 8-byte align
 // global batch size (dz2 ~ 1/batch), passed to the kernel as dz_scale.  Both are undone where the results are read.
 constexpr float kW2BwdScale = 16.0f;
 
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE-rn operations per issue slot; the kernel is bound by
+// instruction issue, not by the FMA pipe).  Each lane of a pair rounds exactly like the scalar instruction.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -342,12 +347,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
     } else {
     // ---- persistent accumulators (everything else is reduced into shared memory tile by tile) -----------
-    float g_b2 = 0.0f, g_g2 = 0.0f, g_be2 = 0.0f, g_wh[6] = {0, 0, 0, 0, 0, 0};   // (output r128, sample group ug)
-    float Pacc[2][8];                                                             // (input r128 + 128 h, group ug)
+    float g_b2 = 0.0f, g_g2 = 0.0f, g_be2 = 0.0f;                                  // (output r128, sample group ug)
+    float2 g_wh2[3] = {f2(0.0f, 0.0f), f2(0.0f, 0.0f), f2(0.0f, 0.0f)};           // head-weight gradients, 3 pairs
+    float2 Pacc[2][4];                               // 8 column sums as 4 pairs (input r128 + 128 h, group ug)
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) Pacc[h][c] = 0.0f;
+        for (int c = 0; c < 4; ++c) Pacc[h][c] = f2(0.0f, 0.0f);
 
     float* const pf = sm + TcSmem::pf;
     // gather of one tile's samples into pf with 4-byte cp.async (sample threads; rows beyond the minibatch = 0);
@@ -427,13 +433,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 
         PLUME_TL(1);
         // ---- Ph1: this thread's sample (r128) for the producer phases; rstd1 was computed in Ph0 ------------
-        float xr[6];
+        float2 xr2[6];            // (x_k, x_k): the broadcast operand of the packed layer-1 FMAs
+        float2 rs2;
         {
             const float4 x0 = *reinterpret_cast<const float4*>(xt + r128 * 8);
             const float4 x1 = *reinterpret_cast<const float4*>(xt + r128 * 8 + 4);
-            xr[0] = x0.x; xr[1] = x0.y; xr[2] = x0.z; xr[3] = x0.w; xr[4] = x1.x; xr[5] = x1.y;
+            xr2[0] = splat2(x0.x); xr2[1] = splat2(x0.y); xr2[2] = splat2(x0.z); xr2[3] = splat2(x0.w);
+            xr2[4] = splat2(x1.x); xr2[5] = splat2(x1.y);
+            rs2 = splat2(x1.z);
         }
-        const float rstd1 = xt[r128 * 8 + 6];
 
         // ---- Ph2: G1 forward, K = 256 inputs in 4 chunks of 64; thread = (sample r128, 8/G of the 8 slots) ----
         for (int c = 0; c < 4; ++c) {
@@ -449,21 +457,19 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int in0 = 64 * c + 8 * u + 4 * q;
-                    float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+                    const float4 b = *reinterpret_cast<const float4*>(P1 + in0);
+                    float2 z01 = f2(b.x, b.y), z23 = f2(b.z, b.w);
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
-                        z.x = fmaf(xr[k], w.x, z.x);
-                        z.y = fmaf(xr[k], w.y, z.y);
-                        z.z = fmaf(xr[k], w.z, z.z);
-                        z.w = fmaf(xr[k], w.w, z.w);
+                        z01 = __ffma2_rn(xr2[k], f2(w.x, w.y), z01);
+                        z23 = __ffma2_rn(xr2[k], f2(w.z, w.w), z23);
                     }
                     const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
                     const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
-                    hq[q].x = fmaxf(fmaf(z.x * rstd1, g.x, be.x), 0.0f);
-                    hq[q].y = fmaxf(fmaf(z.y * rstd1, g.y, be.y), 0.0f);
-                    hq[q].z = fmaxf(fmaf(z.z * rstd1, g.z, be.z), 0.0f);
-                    hq[q].w = fmaxf(fmaf(z.w * rstd1, g.w, be.w), 0.0f);
+                    const float2 y01 = __ffma2_rn(__fmul2_rn(z01, rs2), f2(g.x, g.y), f2(be.x, be.y));
+                    const float2 y23 = __ffma2_rn(__fmul2_rn(z23, rs2), f2(g.z, g.w), f2(be.z, be.w));
+                    hq[q] = make_float4(fmaxf(y01.x, 0.0f), fmaxf(y01.y, 0.0f), fmaxf(y23.x, 0.0f), fmaxf(y23.y, 0.0f));
                 }
                 uint4 hi, lo;
                 tc::split_f16x8(hq[0], hq[1], tc::kLoScale, hi, lo);
@@ -524,7 +530,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             }
             const float rstd2 = 1.0f / sqrtf(m2 * (1.0f / 128.0f) + kLnEps);
             PLUME_TL(10);
-            float head[6] = {0, 0, 0, 0, 0, 0};
+            float2 head2[3] = {f2(0.0f, 0.0f), f2(0.0f, 0.0f), f2(0.0f, 0.0f)};     // the 6 head outputs as 3 pairs
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
                 const int o = c0 + j;
@@ -533,19 +539,20 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const float h2 = fmaxf(fmaf(x_hat, P2[128 + o], P2[256 + o]), 0.0f);
                 const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);
-                head[0] = fmaf(h2, w0.x, head[0]);
-                head[1] = fmaf(h2, w0.y, head[1]);
-                head[2] = fmaf(h2, w0.z, head[2]);
-                head[3] = fmaf(h2, w0.w, head[3]);
-                head[4] = fmaf(h2, w1.x, head[4]);
-                head[5] = fmaf(h2, w1.y, head[5]);
+                const float2 h22 = splat2(h2);
+                head2[0] = __ffma2_rn(h22, f2(w0.x, w0.y), head2[0]);
+                head2[1] = __ffma2_rn(h22, f2(w0.z, w0.w), head2[1]);
+                head2[2] = __ffma2_rn(h22, f2(w1.x, w1.y), head2[2]);
             }
 #pragma unroll
             for (int q = 0; q < CW / 4; ++q)
                 *reinterpret_cast<float4*>(xh + srow * kXhStride + c0 + 4 * q) =
                     make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) EX(k, cg, srow) = head[k];
+            for (int k = 0; k < 3; ++k) {
+                EX(2 * k, cg, srow) = head2[k].x;
+                EX(2 * k + 1, cg, srow) = head2[k].y;
+            }
             compute_sync();
             PLUME_TL(11);
             // The per-sample loss runs as two halves in two warps of the SAME scheduler (cg = 0: surrogate + value,
@@ -600,6 +607,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             PLUME_TL(13);
             const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8);
             const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8 + 4);
+            const float2 d01 = f2(d0.x, d0.y), d23 = f2(d0.z, d0.w), d45 = f2(d1.x, d1.y);
             float m1p = 0.0f, m2p = 0.0f;
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -608,12 +616,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const float y = fmaf(v[j], g2, P2[256 + o]);
                 const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);
-                float dh = d0.x * w0.x;
-                dh = fmaf(d0.y, w0.y, dh);
-                dh = fmaf(d0.z, w0.z, dh);
-                dh = fmaf(d0.w, w0.w, dh);
-                dh = fmaf(d1.x, w1.x, dh);
-                dh = fmaf(d1.y, w1.y, dh);
+                float2 dh2 = __fmul2_rn(d01, f2(w0.x, w0.y));
+                dh2 = __ffma2_rn(d23, f2(w0.z, w0.w), dh2);
+                dh2 = __ffma2_rn(d45, f2(w1.x, w1.y), dh2);
+                const float dh = dh2.x + dh2.y;
                 const float dxh = (y > 0.0f) ? dh * g2 : 0.0f;
                 m1p += dxh;
                 m2p = fmaf(dxh, v[j], m2p);
@@ -641,9 +647,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         {
             const int o = r128;
             const float g2 = P2[128 + o], be2 = P2[256 + o];
-            float wrow[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) wrow[j] = Wh[o * 8 + j];
+            const float2 wrow2[3] = {f2(Wh[o * 8], Wh[o * 8 + 1]), f2(Wh[o * 8 + 2], Wh[o * 8 + 3]),
+                                     f2(Wh[o * 8 + 4], Wh[o * 8 + 5])};
 #pragma unroll 4
             for (int q = 0; q < SPT; ++q) {
                 const int s = SPT * ug + q;
@@ -651,16 +656,16 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8);
                 const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8 + 4);
                 const float4 sc = *reinterpret_cast<const float4*>(sm + TcSmem::sc + s * 4);
-                const float d[6] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y};
+                const float2 d01 = f2(d0.x, d0.y), d23 = f2(d0.z, d0.w), d45 = f2(d1.x, d1.y);
                 const float y = fmaf(x_hat, g2, be2);
-                const float h2v = fmaxf(y, 0.0f);
-                float dh = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    dh = fmaf(d[j], wrow[j], dh);
-                    g_wh[j] = fmaf(d[j], h2v, g_wh[j]);
-                }
-                const float dy = (y > 0.0f) ? dh : 0.0f;
+                const float2 h2v = splat2(fmaxf(y, 0.0f));
+                float2 dh2 = __fmul2_rn(d01, wrow2[0]);
+                dh2 = __ffma2_rn(d23, wrow2[1], dh2);
+                dh2 = __ffma2_rn(d45, wrow2[2], dh2);
+                g_wh2[0] = __ffma2_rn(d01, h2v, g_wh2[0]);
+                g_wh2[1] = __ffma2_rn(d23, h2v, g_wh2[1]);
+                g_wh2[2] = __ffma2_rn(d45, h2v, g_wh2[2]);
+                const float dy = (y > 0.0f) ? dh2.x + dh2.y : 0.0f;
                 g_g2 = fmaf(dy, x_hat, g_g2);
                 g_be2 += dy;
                 const float dz = sc.x * (dy * g2 - sc.y - x_hat * sc.z);
@@ -710,6 +715,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 uint4* bh4 = reinterpret_cast<uint4*>(stage_buf(st, 2));
                 uint4* bl4 = reinterpret_cast<uint4*>(stage_buf(st, 3));
                 const int in = 128 * hN + r128;
+                // (scalar FMAs in the forward's order: pairing (k, k+1) into FFMA2 measured 0.02 ms per iteration slower)
                 float w[6];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];
@@ -758,12 +764,14 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             compute_sync();        // every thread has read dz2 for its last G3 chunk: the region becomes staging
             prefetch_tile(tile + gridDim.x);      // the next tile's gather rides under this CUDA-core phase
             tc::tc_fence_after();
-            float m1p = 0.0f, m2p = 0.0f;
-            const float dh_unscale = 1.0f / (dz_scale * kW2BwdScale);      // exact: both are powers of two
+            float2 m1p2 = f2(0.0f, 0.0f), m2p2 = f2(0.0f, 0.0f);         // even / odd inputs of this thread's slab
+            const float2 un2 = splat2(1.0f / (dz_scale * kW2BwdScale));    // exact: both are powers of two
             // this thread's sample: inputs + rstd1
             const float4 sx0 = *reinterpret_cast<const float4*>(xt + srow * 8);
             const float4 sx1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
             const float xs[6] = {sx0.x, sx0.y, sx0.z, sx0.w, sx1.x, sx1.y};
+            const float2 xs2[6] = {splat2(sx0.x), splat2(sx0.y), splat2(sx0.z), splat2(sx0.w), splat2(sx1.x), splat2(sx1.y)};
+            const float2 srs2 = splat2(sx1.z);
 #pragma unroll
             for (int hN = 0; hN < 2; ++hN) {          // unrolled: Pacc[hN] must stay in registers
                 const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 * hN + CW * cg);
@@ -773,28 +781,28 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
                 for (int j4 = 0; j4 < CW / 4; ++j4) {
                     const int in0 = 128 * hN + CW * cg + 4 * j4;
-                    float4 z = *reinterpret_cast<const float4*>(P1 + in0);
+                    const float4 b = *reinterpret_cast<const float4*>(P1 + in0);
+                    float2 zz[2] = {f2(b.x, b.y), f2(b.z, b.w)};
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
-                        z.x = fmaf(xs[k], w.x, z.x);
-                        z.y = fmaf(xs[k], w.y, z.y);
-                        z.z = fmaf(xs[k], w.z, z.z);
-                        z.w = fmaf(xs[k], w.w, z.w);
+                        zz[0] = __ffma2_rn(xs2[k], f2(w.x, w.y), zz[0]);
+                        zz[1] = __ffma2_rn(xs2[k], f2(w.z, w.w), zz[1]);
                     }
                     const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
                     const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
-                    const float zz[4] = {z.x, z.y, z.z, z.w}, gg[4] = {g.x, g.y, g.z, g.w},
-                                bb[4] = {be.x, be.y, be.z, be.w};
+                    const float2 gg[2] = {f2(g.x, g.y), f2(g.z, g.w)}, bb[2] = {f2(be.x, be.y), f2(be.z, be.w)};
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float x_hat = zz[jj] * sx1.z;
-                        const float y = fmaf(x_hat, gg[jj], bb[jj]);
-                        const float dy = (y > 0.0f) ? v[4 * j4 + jj] * dh_unscale : 0.0f;
-                        const float t = dy * gg[jj];
-                        m1p += t;
-                        m2p = fmaf(t, x_hat, m2p);
-                        xh[(CW * cg + 4 * j4 + jj) * kStageStride + srow] = dy;     // staging [input][sample]
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const float2 x_hat = __fmul2_rn(zz[jj], srs2);
+                        const float2 y = __ffma2_rn(x_hat, gg[jj], bb[jj]);
+                        const float2 du = __fmul2_rn(f2(v[4 * j4 + 2 * jj], v[4 * j4 + 2 * jj + 1]), un2);
+                        const float2 dy = f2(y.x > 0.0f ? du.x : 0.0f, y.y > 0.0f ? du.y : 0.0f);
+                        const float2 t = __fmul2_rn(dy, gg[jj]);
+                        m1p2 = __fadd2_rn(m1p2, t);
+                        m2p2 = __ffma2_rn(t, x_hat, m2p2);
+                        xh[(CW * cg + 4 * j4 + 2 * jj) * kStageStride + srow] = dy.x;     // staging [input][sample]
+                        xh[(CW * cg + 4 * j4 + 2 * jj + 1) * kStageStride + srow] = dy.y;
                     }
                 }
                 compute_sync();
@@ -806,21 +814,18 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     const float4 y0 = *reinterpret_cast<const float4*>(xt + s * 8);
                     const float4 y1 = *reinterpret_cast<const float4*>(xt + s * 8 + 4);
                     const float dr = dy * y1.z;
-                    Pacc[hN][0] = fmaf(dr, y0.x, Pacc[hN][0]);
-                    Pacc[hN][1] = fmaf(dr, y0.y, Pacc[hN][1]);
-                    Pacc[hN][2] = fmaf(dr, y0.z, Pacc[hN][2]);
-                    Pacc[hN][3] = fmaf(dr, y0.w, Pacc[hN][3]);
-                    Pacc[hN][4] = fmaf(dr, y1.x, Pacc[hN][4]);
-                    Pacc[hN][5] = fmaf(dr, y1.y, Pacc[hN][5]);
-                    Pacc[hN][6] += dr;
-                    Pacc[hN][7] += dy;
+                    const float2 dr2 = splat2(dr);
+                    Pacc[hN][0] = __ffma2_rn(dr2, f2(y0.x, y0.y), Pacc[hN][0]);
+                    Pacc[hN][1] = __ffma2_rn(dr2, f2(y0.z, y0.w), Pacc[hN][1]);
+                    Pacc[hN][2] = __ffma2_rn(dr2, f2(y1.x, y1.y), Pacc[hN][2]);
+                    Pacc[hN][3] = __fadd2_rn(Pacc[hN][3], f2(dr, dy));
                 }
                 compute_sync();
             }
         PLUME_TL(8);
             wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
-            EX(6, cg, srow) = m1p;
-            EX(7, cg, srow) = m2p;
+            EX(6, cg, srow) = m1p2.x + m1p2.y;
+            EX(7, cg, srow) = m2p2.x + m2p2.y;
             compute_sync();
             if (cg == 0) {          // per-sample scalar sums of the layer-1 backward -> per-CTA accumulators
                 float t1 = 0.0f, t2 = 0.0f;
@@ -928,6 +933,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         atomicAdd(g + PLUME_OFF_B2 + o, g_b2);
         atomicAdd(g + PLUME_OFF_G2 + o, g_g2);
         atomicAdd(g + PLUME_OFF_BE2 + o, g_be2);
+        const float g_wh[6] = {g_wh2[0].x, g_wh2[0].y, g_wh2[1].x, g_wh2[1].y, g_wh2[2].x, g_wh2[2].y};
 #pragma unroll
         for (int j = 0; j < 5; ++j) atomicAdd(g + PLUME_OFF_WA + j * 128 + o, g_wh[j]);
         atomicAdd(g + PLUME_OFF_WC + o, g_wh[5]);
@@ -938,7 +944,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) pbuf[(ug * 256 + 128 * h + r128) * 8 + c] = Pacc[h][c];
+        for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float2*>(pbuf + (ug * 256 + 128 * h + r128) * 8 + 2 * c) = Pacc[h][c];
     compute_sync();
     if (tid < 4) {                       // total = policy + value - beta * entropy (train_ppo2.0.py:82)
         const double lsum = tid == 0 ? cta_loss[1] + cta_loss[2] - (double)a.entropy_beta * cta_loss[3] : cta_loss[tid];

@@ -30,6 +30,14 @@
 #include "ppo_loss.cuh"
 #include "tc_gemm.cuh"
 
+#define PLUME_STR(x) #x
+#define PLUME_UNROLL(n) _Pragma(PLUME_STR(unroll n))
+#ifndef PLUME_U4
+#define PLUME_U4 16
+#endif
+#ifndef PLUME_U6
+#define PLUME_U6 4
+#endif
 namespace plume {
 
 constexpr int kTcTile = 128;
@@ -46,7 +54,7 @@ struct TcSmem {
     static constexpr int W1c = xh + kTcTile * kXhStride;             // [6][256] centred feature.0.weight, k-major
     static constexpr int P1 = W1c + 6 * 256;                         // [3][256] centred bias, LN1 gamma, beta
     static constexpr int P2 = P1 + 3 * 256;                          // [3][128] feature.3.bias, LN2 gamma, beta
-    static constexpr int Wh = P2 + 3 * 128;                          // [128][8] heads
+    static constexpr int Wh = P2 + 3 * 128;                          // [128][8] heads (6), LN2 gamma, beta
     static constexpr int bh = Wh + 128 * 8;                          // [8]
     static constexpr int x = bh + 8;                                 // [128][8] x0..x5, rstd1, 0
     static constexpr int dout = x + kTcTile * 8;                     // [128][8] d loss / d (logits, value)
@@ -194,7 +202,11 @@ __global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restric
     reinterpret_cast<uint4*>(w2s + chunk_base + (kW2SplitG1Lo - kW2SplitG1Hi))[f] = lo;
 }
 
+#ifdef PLUME_TC_MAXNREG
+__global__ void __maxnreg__(PLUME_TC_MAXNREG)
+#else
 __global__ void __launch_bounds__(kTcLaunchThreads, 1)
+#endif
 ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s, float dz_scale) {
     extern __shared__ __align__(128) float sm[];     // no-swizzle operand layouts need 16 B alignment only
     __shared__ uint64_t bar[2];           // "stage free": arrived by tcgen05.commit
@@ -259,6 +271,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             float w = 0.0f;
             if (o < 5) w = params[PLUME_OFF_WA + o * 128 + k];
             else if (o == 5) w = params[PLUME_OFF_WC + k];
+            else if (o == 6) w = params[PLUME_OFF_G2 + k];          // LayerNorm-2 gamma / beta ride in the two spare
+            else w = params[PLUME_OFF_BE2 + k];                     // slots of the row: one LDS.128 pair per column
             sm[TcSmem::Wh + i] = w;
         }
         if (tid < 8)
@@ -501,10 +515,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::tc_fence_before();
             float sum = 0.0f;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-                v[j] += P2[c0 + j];
-                sum += v[j];
+            for (int j4 = 0; j4 < CW / 4; ++j4) {
+                const float4 b2 = *reinterpret_cast<const float4*>(P2 + c0 + 4 * j4);
+                v[4 * j4 + 0] += b2.x;
+                v[4 * j4 + 1] += b2.y;
+                v[4 * j4 + 2] += b2.z;
+                v[4 * j4 + 3] += b2.w;
             }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) sum += v[j];
             // LayerNorm-2 statistics with ONE exchange: each column group contributes its sum and the sum of squares about
             // its OWN mean; the groups are merged with the pairwise update M2 = sum_g [M2_g + 32 (mean_g - mean)^2]
             // (as accurate as the two-pass form, one barrier less per tile)
@@ -536,9 +555,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const int o = c0 + j;
                 const float x_hat = (v[j] - mean) * rstd2;
                 v[j] = x_hat;
-                const float h2 = fmaxf(fmaf(x_hat, P2[128 + o], P2[256 + o]), 0.0f);
                 const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
-                const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);          // .z = gamma2, .w = beta2
+                const float h2 = fmaxf(fmaf(x_hat, w1.z, w1.w), 0.0f);
                 const float2 h22 = splat2(h2);
                 head2[0] = __ffma2_rn(h22, f2(w0.x, w0.y), head2[0]);
                 head2[1] = __ffma2_rn(h22, f2(w0.z, w0.w), head2[1]);
@@ -612,10 +631,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
                 const int o = c0 + j;
-                const float g2 = P2[128 + o];
-                const float y = fmaf(v[j], g2, P2[256 + o]);
                 const float4 w0 = *reinterpret_cast<const float4*>(Wh + o * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(Wh + o * 8 + 4);
+                const float g2 = w1.z;
+                const float y = fmaf(v[j], g2, w1.w);
                 float2 dh2 = __fmul2_rn(d01, f2(w0.x, w0.y));
                 dh2 = __ffma2_rn(d23, f2(w0.z, w0.w), dh2);
                 dh2 = __ffma2_rn(d45, f2(w1.x, w1.y), dh2);
@@ -649,7 +668,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             const float g2 = P2[128 + o], be2 = P2[256 + o];
             const float2 wrow2[3] = {f2(Wh[o * 8], Wh[o * 8 + 1]), f2(Wh[o * 8 + 2], Wh[o * 8 + 3]),
                                      f2(Wh[o * 8 + 4], Wh[o * 8 + 5])};
-#pragma unroll 4
+PLUME_UNROLL(PLUME_U4)
             for (int q = 0; q < SPT; ++q) {
                 const int s = SPT * ug + q;
                 const float x_hat = xh[s * kXhStride + o];
@@ -807,7 +826,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 }
                 compute_sync();
                 // column sums: thread = (input r128 of this half, 128/G of the 128 samples)
-#pragma unroll 4
+PLUME_UNROLL(PLUME_U6)
                 for (int q = 0; q < SPT; ++q) {
                     const int s = SPT * ug + q;
                     const float dy = xh[r128 * kStageStride + s];

@@ -213,7 +213,9 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void split_f16x2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn((a - hf.x) * s, (b - hf.y) * s);
+    // remainder and scaling as packed fp32 pairs (FADD2 / FMUL2: same IEEE results, half the issue slots)
+    const float2 r = __fmul2_rn(__fadd2_rn(make_float2(a, b), make_float2(-hf.x, -hf.y)), make_float2(s, s));
+    const __half2 l = __floats2half2_rn(r.x, r.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }

@@ -10,8 +10,9 @@
 // the Philox stream, so a reset costs O(1)).
 //
 // Algorithmic bytes per env-step (DESIGN.md "rollout"): obs 24 + action 4 + reward 4 + value 4 +
-// logp 4 + done 4 + reached 1 = 45 B written (+ stop 9, info 20, episode 4 when requested),
-// visit-table RMW 4 B; nothing else touches HBM.
+// logp 4 + done 4 + reached 1 = 45 B written (+ stop 9, info 20, episode 4 when requested); the visit tables are read
+// into shared memory once per segment and written back at its end (2 x 208 B per env and segment); nothing else
+// touches HBM.
 #include "lstm_tile.cuh"
 #include "mlp_tc_tile.cuh"
 
@@ -32,8 +33,12 @@ template <int H>
 struct RolloutSmem {
     static constexpr int lstm = PolicySmem::total;
     static constexpr int misc = lstm + (H > 0 ? LstmSmem<(H > 0 ? H : 32)>::total : kLstmMaxSteps * 32);
-    static constexpr int total = misc + 96;     // [32] stop prob, [32] peak, [32] scratch
+    static constexpr int vis = misc + 96;       // [32] stop prob, [32] peak, [32] scratch; then the tile's visit tables
+    static constexpr int total = vis + kTileM * PLUME_VISIT_STRIDE / 2;     // [32][104] uint16 (16-byte aligned rows)
 };
+
+static_assert(RolloutSmem<0>::vis % 4 == 0 && RolloutSmem<32>::vis % 4 == 0, "visit-table rows are copied as uint4");
+static_assert(RolloutSmem<32>::total * 4 <= 227 * 1024, "rollout kernel: shared memory plan exceeds 227 KB");
 
 // kSpec (as in the K2 step kernel): 0 = plume model / reward mode / division mode read at run time,
 // 1 = reference code model with exact float64 reward, 2 = code model with PLUME_FLAG_FAST_REWARD; 1 and 2 use the
@@ -84,7 +89,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
             float o[6] = {0, 0, 0, 0, 0, 0};
             if (owner) {
                 e = load_env(a.st, env);
-                vis = a.st.visited + (size_t)env * PLUME_VISIT_STRIDE;
+                // the visit counters live in shared memory for the whole segment: their read-modify-write sits on the
+                // serial env-step chain of every lockstep iteration (an L2 round trip per step when left in global memory)
+                vis = reinterpret_cast<uint16_t*>(sm + RolloutSmem<H>::vis) + tid * PLUME_VISIT_STRIDE;
+                {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.st.visited + (size_t)env * PLUME_VISIT_STRIDE);
+                    uint4* dst = reinterpret_cast<uint4*>(vis);
+#pragma unroll
+                    for (int q = 0; q < PLUME_VISIT_STRIDE / 8; ++q) dst[q] = src[q];
+                }
                 int x, y;
                 cell32_of(c, e, x, y);
                 field.eval(c, env, gid, e.episode, e.sx, e.sy, x, y, cell_conc, cell_tke);
@@ -215,6 +228,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
         // ---- persist the tile's state ----------------------------------------------------------------------
         if (owner) {
             store_env(a.st, env, e);
+            {
+                uint4* dst = reinterpret_cast<uint4*>(a.st.visited + (size_t)env * PLUME_VISIT_STRIDE);
+                const uint4* src = reinterpret_cast<const uint4*>(vis);
+#pragma unroll
+                for (int q = 0; q < PLUME_VISIT_STRIDE / 8; ++q) dst[q] = src[q];
+            }
             if (a.st.cell_tke && a.st.cell_conc && a.st.cell_key) {   // hand the carried cell to a following plume_env_step
                 int x, y;
                 cell32_of(c, e, x, y);

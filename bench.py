@@ -359,9 +359,19 @@ def run_cuda_arm(args) -> None:
     batch = pb._lib.PpoBatch(M, buf.obs.data_ptr(), buf.actions.data_ptr(), buf.log_probs.data_ptr(),
                              buf.advantages.data_ptr(), buf.returns.data_ptr(), buf.values.data_ptr())
     loss = torch.zeros(4, dtype=torch.float64, device=dev)
+    # as update_model runs it: the epoch permutation and the 48-byte sample records are written out beforehand
+    perm_ptr = None
+    if M >= pb.learner.MATERIALISE_PERM_MIN:
+        perm0 = ws.perm_buffer(1, M)
+        pb.learner.materialise_permutations(lib, perm0, M, 1, [0], torch.cuda.current_stream().cuda_stream)
+        packed = ws.packed_buffer(M)
+        pb._lib.check(lib.plume_ppo_pack(C.byref(batch), packed.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                      "ppo_pack")
+        batch.packed = packed.data_ptr()
+        perm_ptr = perm0.data_ptr()
 
     def grad_call():
-        pb._lib.check(lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), None, 1, 0, 0, min(mb, M), min(mb, M),
+        pb._lib.check(lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), perm_ptr, 1, 0, 0, min(mb, M), min(mb, M),
                                          cfg.clip_epsilon, cfg.entropy_beta, model.flat_grad.data_ptr(),
                                          loss.data_ptr(), ws.nan_flag.data_ptr(), ws.ws.data_ptr(), ws.bytes,
                                          torch.cuda.current_stream().cuda_stream), "ppo_grad")

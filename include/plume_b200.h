@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PLUME_B200_ABI_VERSION 2
+#define PLUME_B200_ABI_VERSION 3
 
 #define PLUME_OBS_DIM 6          /* environment.py:80-87 */
 #define PLUME_NUM_ACTIONS 5      /* environment.py:23 */
@@ -328,7 +328,14 @@ typedef struct plume_ppo_batch {          /* DEVICE pointers over the flat [M] t
     const float* advantages;
     const float* returns;
     const float* old_values;
+    const float* packed;                  /* optional [M][12] sample records written by plume_ppo_pack (NULL = gather
+                                           * from the six arrays above) */
 } plume_ppo_batch;
+
+/* Interleaves the transition set into 48-byte records {obs[6], advantage, return, old value, old log-prob, action
+ * (int bits), 0}: the gradient kernel then gathers a permuted sample with three 16-byte copies (1.5 DRAM sectors)
+ * instead of eleven 4-byte ones (7 sectors).  Call after the advantages are final; batch->packed is not read. */
+int plume_ppo_pack(const plume_ppo_batch* batch, float* packed, void* stream);
 
 /* Forward + loss + backward of one minibatch: samples are perm[i] for i in [mb_start, mb_start+mb_size)
  * if perm (int64[M] device) is given, else the stateless bijection keyed by (perm_seed, epoch).

@@ -24,7 +24,7 @@ def test_library_exports_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(pb._lib.EXPORTED_SYMBOLS) == declared
-    assert lib.plume_abi_version() == 2
+    assert lib.plume_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(L.EnvState) == 8 + 20 * 8
     assert C.sizeof(L.LstmParams) == 16 + 8 * 8
     assert C.sizeof(L.RolloutBuffers) == 25 * 8
-    assert C.sizeof(L.PpoBatch) == 7 * 8
+    assert C.sizeof(L.PpoBatch) == 8 * 8
     header = open(os.path.join(ROOT, "include", "plume_b200.h")).read()
     for name, (off, _) in L.MLP_OFFSETS.items():
         pass

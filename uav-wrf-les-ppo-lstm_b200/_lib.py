@@ -67,7 +67,7 @@ class RolloutBuffers(C.Structure):
 
 class PpoBatch(C.Structure):
     _fields_ = [("total", C.c_int64), ("obs", _vp), ("actions", _vp), ("old_log_probs", _vp),
-                ("advantages", _vp), ("returns", _vp), ("old_values", _vp)]
+                ("advantages", _vp), ("returns", _vp), ("old_values", _vp), ("packed", _vp)]
 
 
 GAE_VARIANTS = {"quirk": 0, "bootstrap": 1, "v12": 2}
@@ -114,6 +114,7 @@ _SIGNATURES = {
     "plume_ppo_grad": (C.c_int, [_vp, _P(PpoBatch), _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "plume_ppo_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "plume_ppo_pack": (C.c_int, [_P(PpoBatch), _vp, _vp]),
     "plume_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_int32, _vp, _vp]),
     "plume_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P(_vp), _vp]),
@@ -159,7 +160,7 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError = a declared symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.plume_abi_version() != 2:
+    if lib.plume_abi_version() != 3:
         raise PlumeLibraryError("libplume_b200.so ABI version mismatch")
     _lib = lib
     return lib

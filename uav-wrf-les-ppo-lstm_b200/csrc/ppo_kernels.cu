@@ -414,6 +414,15 @@ extern "C" int64_t plume_ppo_workspace_bytes(int64_t mb_size) {
     return cuda_path > tc_path ? cuda_path : tc_path;
 }
 
+extern "C" int plume_ppo_pack(const plume_ppo_batch* batch, float* packed, void* stream) {
+    PLUME_CHECK_ARG(batch && packed, "null pointer");
+    PLUME_CHECK_ARG(batch->obs && batch->actions && batch->old_log_probs && batch->advantages && batch->returns &&
+                        batch->old_values, "null batch pointer");
+    PLUME_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(batch->obs) & 7) == 0,
+                    "packed must be 16-byte aligned, obs 8-byte aligned");
+    return launch_ppo_pack(*batch, packed, as_stream(stream));
+}
+
 extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int64_t* perm,
                               uint64_t perm_seed, int32_t epoch, int64_t mb_start, int64_t mb_size,
                               int64_t mb_size_global, float clip_eps, float entropy_beta, float* grads,
@@ -425,6 +434,7 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
     PLUME_CHECK_ARG(mb_start >= 0 && mb_size >= 0 && mb_start + mb_size <= batch->total, "minibatch outside [0,total)");
     PLUME_CHECK_ARG(mb_size_global >= mb_size && mb_size_global > 0, "mb_size_global must be >= mb_size");
     PLUME_CHECK_ARG(workspace_bytes >= plume_ppo_workspace_bytes(mb_size), "workspace too small");
+    PLUME_CHECK_ARG((reinterpret_cast<uintptr_t>(batch->packed) & 15) == 0, "packed records must be 16-byte aligned");
     if (mb_size == 0) return 0;
     static bool configured = false;
     const int smem_a = (MlpSmem::total + 7 * 32 + 64) * (int)sizeof(float);

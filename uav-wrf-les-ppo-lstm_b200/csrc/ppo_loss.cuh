@@ -25,6 +25,7 @@ struct PpoArgs {
 // tensor-core path (ppo_tc_kernels.cu)
 int64_t ppo_tc_workspace_bytes();
 int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s);
+int launch_ppo_pack(const plume_ppo_batch& b, float* packed, cudaStream_t s);
 
 struct SampleLoss {
     float dout[6];      // d total / d logits[0..4], d total / d value, already divided by the global batch

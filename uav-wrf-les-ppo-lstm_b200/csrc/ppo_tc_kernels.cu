@@ -370,17 +370,25 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         for (int c = 0; c < 4; ++c) Pacc[h][c] = f2(0.0f, 0.0f);
 
     float* const pf = sm + TcSmem::pf;
-    // gather of one tile's samples into pf with 4-byte cp.async (sample threads; rows beyond the minibatch = 0);
-    // issued after the tile's last publish(), waited for at the next tile's Ph0
-    auto prefetch_tile = [&](long long tl) {
-        if (tid >= kTcTile || tl >= tiles) return;
+    // gather of one tile's samples into pf with 4-byte cp.async (one thread per sample; rows beyond the minibatch = 0);
+    // the next tile's gather (its Feistel index is ~300 dependent instructions) is issued by the four warps that have
+    // nothing to do during the loss section of Ph3, and waited for at the next tile's Ph0
+    auto prefetch_tile = [&](long long tl, int row) {
+        if (tl >= tiles) return;
         const long long b0 = tl * kTcTile;
-        float* dst = pf + tid * 12;
-        if (b0 + tid < a.mb_size) {
-            const long long pos = a.mb_start + b0 + tid;
+        float* dst = pf + row * 12;
+        if (b0 + row < a.mb_size) {
+            const long long pos = a.mb_start + b0 + row;
             const long long idx = a.perm ? a.perm[pos]
                                          : (long long)feistel_permute((uint64_t)pos, (uint64_t)a.batch.total,
                                                                       a.perm_seed, (uint32_t)a.epoch);
+            if (a.batch.packed) {           // one 48-byte record per sample (plume_ppo_pack): three 16-byte copies
+                const float* src = a.batch.packed + idx * 12;
+                cp_async16(dst, src);
+                cp_async16(dst + 4, src + 4);
+                cp_async16(dst + 8, src + 8);
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < 6; ++k) cp_async4(dst + k, a.batch.obs + idx * 6 + k);
             cp_async4(dst + 6, a.batch.advantages + idx);
@@ -396,7 +404,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 #ifdef PLUME_TC_TIMELINE
-        long long tl_[16];
+        long long tl_[24];
         const bool tl_on = blockIdx.x == 0 && tid == 0 && tile == (long long)blockIdx.x + 3 * gridDim.x;
 #define PLUME_TL(n) if (tl_on) tl_[n] = clock64()
 #else
@@ -408,7 +416,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         PLUME_TL(0);
         // ---- Ph0: this tile's samples: gathered by cp.async during the previous tile (first tile: now) --------
         // pf[s] = {obs 0..5, adv, ret, old value, old logp, action (int bits), 0}
-        if (tile == (long long)blockIdx.x) prefetch_tile(tile);
+        if (tile == (long long)blockIdx.x && tid < kTcTile) prefetch_tile(tile, tid);
         cp_async_wait_all();
         compute_sync();
         float s_adv = 0.0f, s_ret = 0.0f, s_vold = 0.0f, s_lpold = 0.0f;
@@ -580,6 +588,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             // dout[.][6], [7] and sc[.][3] carry the sample's policy / value / entropy terms: their sums over the tile
             // (and those of dout = the head-bias gradients) are taken by all 16 warps in the scalar-sum phase at the end of
             // the tile, not by these warps while the others wait.
+            if (cg == 2) prefetch_tile(tile + gridDim.x, srow);      // pf was consumed in Ph0; see prefetch_tile
             if (cg < 2) {
                 float* dop = sm + TcSmem::dout + srow * 8;
                 float l_ent = 0.0f, dv = 0.0f, l_pol = 0.0f, l_val = 0.0f;
@@ -781,7 +790,6 @@ PLUME_UNROLL(PLUME_U4)
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
             compute_sync();        // every thread has read dz2 for its last G3 chunk: the region becomes staging
-            prefetch_tile(tile + gridDim.x);      // the next tile's gather rides under this CUDA-core phase
             tc::tc_fence_after();
             float2 m1p2 = f2(0.0f, 0.0f), m2p2 = f2(0.0f, 0.0f);         // even / odd inputs of this thread's slab
             const float2 un2 = splat2(1.0f / (dz_scale * kW2BwdScale));    // exact: both are powers of two
@@ -825,6 +833,7 @@ PLUME_UNROLL(PLUME_U4)
                     }
                 }
                 compute_sync();
+                PLUME_TL(14 + 2 * hN);
                 // column sums: thread = (input r128 of this half, 128/G of the 128 samples)
 PLUME_UNROLL(PLUME_U6)
                 for (int q = 0; q < SPT; ++q) {
@@ -840,6 +849,7 @@ PLUME_UNROLL(PLUME_U6)
                     Pacc[hN][3] = __fadd2_rn(Pacc[hN][3], f2(dr, dy));
                 }
                 compute_sync();
+                PLUME_TL(15 + 2 * hN);
             }
         PLUME_TL(8);
             wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
@@ -917,10 +927,12 @@ PLUME_UNROLL(PLUME_U6)
             const long long end = clock64();
             printf("ppo_tc timeline (cycles): Ph0 gather+rstd %lld | G1 production %lld | G1 mma drain %lld | Ph3 LN2/loss %lld | "
                    "Ph4 %lld | G2 production %lld | G3 production %lld | Ph6 columns %lld | drain %lld | Ph6 scalars %lld | tail %lld | total %lld"
-                   " || Ph3: stats %lld | heads %lld | loss %lld | loss barrier %lld | LN2-bwd means %lld\n",
+                   " || Ph3: stats %lld | heads %lld | loss %lld | loss barrier %lld | LN2-bwd means %lld"
+                   " || Ph6: A0 %lld | B0 %lld | A1 %lld | B1 %lld\n",
                    tl_[1] - tl_[0], tl_[2] - tl_[1], tl_[3] - tl_[2], tl_[4] - tl_[3], tl_[5] - tl_[4], tl_[6] - tl_[5],
                    tl_[7] - tl_[6], tl_[8] - tl_[7], 0LL, tl_[9] - tl_[8], end - tl_[9], end - tl_[0],
-                   tl_[10] - tl_[3], tl_[11] - tl_[10], tl_[12] - tl_[11], tl_[13] - tl_[12], tl_[4] - tl_[13]);
+                   tl_[10] - tl_[3], tl_[11] - tl_[10], tl_[12] - tl_[11], tl_[13] - tl_[12], tl_[4] - tl_[13],
+                   tl_[14] - tl_[7], tl_[15] - tl_[14], tl_[16] - tl_[15], tl_[17] - tl_[16]);
         }
 #endif
     }
@@ -1028,6 +1040,27 @@ PLUME_UNROLL(PLUME_U6)
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// ---- sample records ---------------------------------------------------------------------------------------
+// [M][12] = {obs 0..5, advantage, return, old value, old log-prob, action (int bits), 0}: the layout of the pf
+// staging rows, so a gathered record needs no rearrangement.  One thread per record, three float4 stores.
+__global__ void ppo_pack_kernel(plume_ppo_batch b, float* __restrict__ packed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.total) return;
+    const float2* o2 = reinterpret_cast<const float2*>(b.obs + i * 6);         // 24-byte rows: 8-byte aligned
+    const float2 o01 = o2[0], o23 = o2[1], o45 = o2[2];
+    float4* dst = reinterpret_cast<float4*>(packed + i * 12);
+    dst[0] = make_float4(o01.x, o01.y, o23.x, o23.y);
+    dst[1] = make_float4(o45.x, o45.y, b.advantages[i], b.returns[i]);
+    dst[2] = make_float4(b.old_values[i], b.old_log_probs[i], __int_as_float(b.actions[i]), 0.0f);
+}
+
+int launch_ppo_pack(const plume_ppo_batch& b, float* packed, cudaStream_t s) {
+    if (b.total <= 0) return 0;
+    ppo_pack_kernel<<<(unsigned)((b.total + 255) / 256), 256, 0, s>>>(b, packed);
+    if (cudaGetLastError() != cudaSuccess) return fail("ppo_pack_kernel launch failed");
+    return 0;
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------

@@ -84,6 +84,34 @@ class UpdateWorkspace:
         self.ws = torch.empty(self.bytes, dtype=torch.uint8, device=device)
         self.stats = torch.zeros(3, dtype=torch.float64, device=device)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._perm = None
+        self._packed = None
+
+    def packed_buffer(self, m: int) -> torch.Tensor:
+        """``[m, 12]`` float32 sample records (plume_ppo_pack), allocated on first use."""
+        if self._packed is None or self._packed.shape[0] < m:
+            self._packed = torch.empty(m, 12, dtype=torch.float32, device=self.ws.device)
+        return self._packed
+
+    def perm_buffer(self, rows: int, m: int) -> torch.Tensor:
+        """``[rows, m]`` int64 scratch for materialised epoch permutations (allocated on first use)."""
+        if self._perm is None or self._perm.shape[0] < rows or self._perm.shape[1] != m:
+            self._perm = torch.empty(rows, m, dtype=torch.int64, device=self.ws.device)
+        return self._perm
+
+
+# Above this many transitions the epoch permutation is written out by ``plume_permutation`` (one pass at full
+# occupancy) instead of being evaluated inside the gradient kernel, where the ~300 dependent instructions of the
+# Feistel index sit on a 4-warp path of every 128-sample tile (profiles/r1_notes.md, r1t)
+MATERIALISE_PERM_MIN = 32768
+
+
+def materialise_permutations(lib, out: torch.Tensor, m: int, perm_seed: int, epochs, stream) -> None:
+    """out[i] = the Feistel permutation of [0, m) keyed by (perm_seed, epochs[i]) -- the index set the gradient kernel
+    would otherwise derive per sample (same values, so results are unchanged)."""
+    for row, epoch in enumerate(epochs):
+        _lib.check(lib.plume_permutation(m, perm_seed, int(epoch), 0, m, out[row].data_ptr(), stream),
+                   "plume_permutation")
 
 
 def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_group=None, variant: str = "quirk",
@@ -132,7 +160,13 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
         workspace = UpdateWorkspace(dev, min(mb, M))
     compute_advantages(buffer, cfg, workspace, process_group)
     batch = _lib.PpoBatch(M, buffer.obs.data_ptr(), buffer.actions.data_ptr(), buffer.log_probs.data_ptr(),
-                          buffer.advantages.data_ptr(), buffer.returns.data_ptr(), buffer.values.data_ptr())
+                          buffer.advantages.data_ptr(), buffer.returns.data_ptr(), buffer.values.data_ptr(), None)
+    if M >= MATERIALISE_PERM_MIN:
+        # every sample is gathered epochs times: interleave the six arrays once into 48-byte records
+        packed = workspace.packed_buffer(M)
+        with torch.cuda.device(dev):
+            _lib.check(lib.plume_ppo_pack(C.byref(batch), packed.data_ptr(), _stream(dev)), "plume_ppo_pack")
+        batch.packed = packed.data_ptr()
     n_mb = (M + mb - 1) // mb
     losses = torch.zeros(cfg.epochs * n_mb, 4, dtype=torch.float64, device=dev)
     step = 0
@@ -141,6 +175,9 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
             perm = None
             if perms is not None:
                 perm = torch.as_tensor(perms[epoch], dtype=torch.int64, device=dev).contiguous()
+            elif M >= MATERIALISE_PERM_MIN:
+                perm = workspace.perm_buffer(1, M)[0]
+                materialise_permutations(lib, perm.unsqueeze(0), M, perm_seed, [epoch], _stream(dev))
             for start in range(0, M, mb):
                 size = min(mb, M - start)
                 optimizer.zero_grad()

@@ -13,7 +13,8 @@ import torch
 from . import _lib
 from .config import PlumeConfig, config_for
 from .env import VecMethaneEnv
-from .learner import FusedAdam, PPOTrainer, UpdateWorkspace, update_model
+from .learner import (MATERIALISE_PERM_MIN, FusedAdam, PPOTrainer, UpdateWorkspace, materialise_permutations,
+                      update_model)
 from .model import PeakAndStopPredictor, PPOActorCritic
 from .rollout import RolloutEngine
 
@@ -52,14 +53,42 @@ class PlumeTrainer:
         # my kernels per iteration: rollout (+ deferred stop head), curriculum, gae scan + normalise,
         # (fwd_bwd, wgrad2, clip_adam) per step
         self.launches_per_iteration = 4 + (1 if stop_head else 0) + 3 * self.cfg.epochs * n_mb
+        # the epoch permutations do not depend on the rollout: they are written out on a side stream while the
+        # (latency-bound) rollout kernel runs
+        self._perm_stream = None
+        if self.device.type == "cuda" and num_envs * horizon >= MATERIALISE_PERM_MIN:
+            self._perm_stream = torch.cuda.Stream(device=self.device)
+            self._perm_done = torch.cuda.Event()
+            self._perm_free = torch.cuda.Event()
+            self.launches_per_iteration += self.cfg.epochs
+
+    def _permutations_async(self):
+        """Launches this iteration's ``epochs`` permutations on the side stream; returns the ``[epochs, T*N]`` tensor."""
+        M = self.num_envs * self.horizon
+        out = self.workspace.perm_buffer(self.cfg.epochs, M)
+        with torch.cuda.stream(self._perm_stream):
+            if self.iteration > 0:
+                self._perm_stream.wait_event(self._perm_free)     # the previous update has consumed the buffer
+            materialise_permutations(_lib.load(), out, M, self.iteration, range(self.cfg.epochs),
+                                     self._perm_stream.cuda_stream)
+            self._perm_done.record(self._perm_stream)
+        return out
 
     def train_iteration(self, check_nan: bool = False):
         buf = self.engine.collect()
+        perms = None
+        if self._perm_stream is not None:          # launched after the rollout, so its CTAs are placed first
+            with torch.cuda.device(self.device):
+                perms = self._permutations_async()
         self.curriculum.update_from_rollout(buf, self.process_group)
+        if perms is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._perm_done)
         self.last_losses = update_model(buf, self.model, self.optimizer, cfg=self.cfg,
                                         minibatch_size=self.minibatch_size, workspace=self.workspace,
-                                        process_group=self.process_group, perm_seed=self.iteration,
+                                        process_group=self.process_group, perm_seed=self.iteration, perms=perms,
                                         check_nan=check_nan)
+        if perms is not None:
+            self._perm_free.record(torch.cuda.current_stream(self.device))
         self.iteration += 1
         return self.last_losses
 

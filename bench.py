@@ -415,13 +415,15 @@ def run_cuda_arm(args) -> None:
     # split), so the ceiling this kernel can reach is peak/3 -- reported next to it.
     roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peak_tf,
-                "traffic": 43.6e6 if dom.startswith("ppo_grad") else None,   # profiles/r1q_ncu_summary.txt
+                "traffic": 33.5e6 if dom.startswith("ppo_grad") else None,   # profiles/r1t_ncu_summary.txt
                 "peak_source": f"{peaks['source']} bf16 dense (sustained), of measured",
                 "split_ceiling": peak_tf / 3.0, "frac_of_split_ceiling": kernels[dom]["tflops"] / (peak_tf / 3.0),
                 "note": "tcgen05.mma kind::f16 with the two-term fp16 split x = hi + lo/s (fp32 rel 1e-5 parity bar), "
                         "accumulators in TMEM; traffic = dram read+write per launch from the ncu --set full capture in "
-                        "profiles/ (algorithmic gather: 44 B x 262144 samples = 11.5 MB); 60 % of a tile's cycles are "
-                        "CUDA-core phases between the GEMMs (DESIGN.md section 5, phase timeline)"}
+                        "profiles/ (algorithmic gather: a 48-byte record + an 8-byte permutation index x 262144 samples "
+                        "= 14.7 MB; a record straddles two 32-byte sectors); the kernel is bound by instruction issue in the "
+                        "CUDA-core phases between the GEMMs (issue slots 48 % busy, tensor pipe 16 %: DESIGN.md section 5, "
+                        "phase timeline)"}
 
     # ---- end to end through the host-buffer API -------------------------------------------------------
     hb = trainer.make_host_buffers()

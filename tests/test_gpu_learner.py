@@ -264,6 +264,47 @@ def test_update_model_reproduces_reference_update():
     assert np.allclose(losses.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
 
 
+def test_packed_records_and_materialised_permutation_change_nothing(monkeypatch):
+    """Above MATERIALISE_PERM_MIN transitions update_model writes the epoch permutation out with plume_permutation and
+    interleaves the transition set into 48-byte records (plume_ppo_pack); the gradient kernel must see exactly the samples
+    it derives itself (in-kernel Feistel index, six separate arrays) on the small path."""
+    m = pb()
+    cfg = m.config_for("2.1")
+    T, N, mb = 128, 512, 16384                       # 65 536 transitions, four tcgen05 minibatches per epoch
+    buf = _fill_buffer(m, T, N, 11)
+    torch.manual_seed(3)
+    init = m.PPOActorCritic(device="cuda").flat.clone()
+    lib = m._lib.load()
+    # the records hold the six arrays bit for bit
+    ws = m.UpdateWorkspace("cuda", mb)
+    m.compute_advantages(buf, cfg, ws, None)
+    batch = m._lib.PpoBatch(T * N, buf.obs.data_ptr(), buf.actions.data_ptr(), buf.log_probs.data_ptr(),
+                            buf.advantages.data_ptr(), buf.returns.data_ptr(), buf.values.data_ptr(), None)
+    packed = ws.packed_buffer(T * N)
+    m._lib.check(lib.plume_ppo_pack(C.byref(batch), packed.data_ptr(), torch.cuda.current_stream().cuda_stream), "pack")
+    rec = packed.cpu()
+    assert torch.equal(rec[:, :6], buf.obs.reshape(-1, 6).cpu())
+    assert torch.equal(rec[:, 6], buf.advantages.reshape(-1).cpu()) and torch.equal(rec[:, 7], buf.returns.reshape(-1).cpu())
+    assert torch.equal(rec[:, 8], buf.values.reshape(-1).cpu()) and torch.equal(rec[:, 9], buf.log_probs.reshape(-1).cpu())
+    assert torch.equal(rec[:, 10].view(torch.int32), buf.actions.reshape(-1).cpu())
+
+    results = []
+    for threshold in (m.learner.MATERIALISE_PERM_MIN, 1 << 62):
+        monkeypatch.setattr(m.learner, "MATERIALISE_PERM_MIN", threshold)
+        model = m.PPOActorCritic(device="cuda")
+        model.flat.data.copy_(init)
+        opt = m.FusedAdam(model, lr=cfg.learning_rate)
+        losses = m.update_model(buf, model, opt, cfg=cfg, minibatch_size=mb, workspace=m.UpdateWorkspace("cuda", mb),
+                                perm_seed=5)
+        results.append((losses.cpu().numpy(), model.flat.detach().cpu().clone()))
+    (la, pa), (lb, pb_) = results
+    assert la.shape == (cfg.epochs * 4, 4)
+    # same samples in the same tiles; only the order of the cross-CTA float atomics differs between two launches
+    assert np.allclose(la, lb, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(pa, pb_, rtol=0, atol=5e-6), (pa - pb_).abs().max()      # (one Adam step moves a weight by <= 3e-5)
+    assert (pa - init.cpu()).abs().max() > 1e-5           # and the update did something
+
+
 def test_clip_adam_vs_torch():
     m = pb()
     torch.manual_seed(0)

@@ -324,7 +324,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs, commit to "stage free"
     // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
     auto issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {
-        tc::mbar_wait(&full[st & 1u], (st >> 1) & 1u);
+        // (the issuer shares a scheduler with four producer warps: back off between polls instead of spinning)
+        while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
         tc::tc_fence_after();
         if (col_small != col)
             tc::mma_chunk_f16_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),

@@ -45,7 +45,8 @@ constexpr int kTcGroups = 4;                       // 128-thread groups of compu
 constexpr int kTcThreads = 128 * kTcGroups;        // compute threads (producers + epilogues): 16 warps
 constexpr int kTcLaunchThreads = kTcThreads + 32;  // + one warp whose lane 0 only issues the MMAs
 constexpr int kXhStride = 132;             // [128][132]: conflict-free float4 rows and columns
-constexpr int kStageStride = 129;          // [128][129]: transposed dy1 staging
+constexpr int kStageStride = 132;          // [128][132]: transposed dy1 staging (conflict-free scalar stores along the
+                                           // samples, float4 loads along the samples of one input)
 constexpr int kChunkFloats = 128 * tc::kChunkK;
 
 struct TcSmem {
@@ -837,17 +838,22 @@ PLUME_UNROLL(PLUME_U4)
                 PLUME_TL(14 + 2 * hN);
                 // column sums: thread = (input r128 of this half, 128/G of the 128 samples)
 PLUME_UNROLL(PLUME_U6)
-                for (int q = 0; q < SPT; ++q) {
-                    const int s = SPT * ug + q;
-                    const float dy = xh[r128 * kStageStride + s];
-                    const float4 y0 = *reinterpret_cast<const float4*>(xt + s * 8);
-                    const float4 y1 = *reinterpret_cast<const float4*>(xt + s * 8 + 4);
-                    const float dr = dy * y1.z;
-                    const float2 dr2 = splat2(dr);
-                    Pacc[hN][0] = __ffma2_rn(dr2, f2(y0.x, y0.y), Pacc[hN][0]);
-                    Pacc[hN][1] = __ffma2_rn(dr2, f2(y0.z, y0.w), Pacc[hN][1]);
-                    Pacc[hN][2] = __ffma2_rn(dr2, f2(y1.x, y1.y), Pacc[hN][2]);
-                    Pacc[hN][3] = __fadd2_rn(Pacc[hN][3], f2(dr, dy));
+                for (int q4 = 0; q4 < SPT / 4; ++q4) {
+                    const int s0 = SPT * ug + 4 * q4;
+                    const float4 dy4 = *reinterpret_cast<const float4*>(xh + r128 * kStageStride + s0);
+                    const float dys[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float dy = dys[i];
+                        const float4 y0 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8);
+                        const float4 y1 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8 + 4);
+                        const float dr = dy * y1.z;
+                        const float2 dr2 = splat2(dr);
+                        Pacc[hN][0] = __ffma2_rn(dr2, f2(y0.x, y0.y), Pacc[hN][0]);
+                        Pacc[hN][1] = __ffma2_rn(dr2, f2(y0.z, y0.w), Pacc[hN][1]);
+                        Pacc[hN][2] = __ffma2_rn(dr2, f2(y1.x, y1.y), Pacc[hN][2]);
+                        Pacc[hN][3] = __fadd2_rn(Pacc[hN][3], f2(dr, dy));
+                    }
                 }
                 compute_sync();
                 PLUME_TL(15 + 2 * hN);

@@ -119,17 +119,34 @@ __device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
         float xr[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) xr[k] = sm[MlpTcSmem::x + lane * 8 + k];
+        // four outputs per step: float4 weight loads (warp-uniform addresses) and packed fp32 pairs (FFMA2: two
+        // IEEE-rn FMAs per issue slot); every output still sums its six terms in the order k = 0..5, then the bias
         float z[32];
         float part = 0.0f;
+        float2 xr2[6];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int o = warp * 32 + j;
-            float a = 0.0f;
+        for (int k = 0; k < 6; ++k) xr2[k] = make_float2(xr[k], xr[k]);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) a = fmaf(xr[k], sm[MlpTcSmem::W1t + k * 256 + o], a);
-            a += sm[MlpTcSmem::P1 + o];
-            z[j] = a;
-            part += a;
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const int o = warp * 32 + 4 * j4;
+            float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(sm + MlpTcSmem::W1t + k * 256 + o);
+                a01 = __ffma2_rn(xr2[k], make_float2(w.x, w.y), a01);
+                a23 = __ffma2_rn(xr2[k], make_float2(w.z, w.w), a23);
+            }
+            const float4 b = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + o);
+            a01 = __fadd2_rn(a01, make_float2(b.x, b.y));
+            a23 = __fadd2_rn(a23, make_float2(b.z, b.w));
+            z[4 * j4 + 0] = a01.x;
+            z[4 * j4 + 1] = a01.y;
+            z[4 * j4 + 2] = a23.x;
+            z[4 * j4 + 3] = a23.y;
+            part += a01.x;
+            part += a01.y;
+            part += a23.x;
+            part += a23.y;
         }
         sm[MlpTcSmem::red + warp * 32 + lane] = part;
         __syncthreads();
@@ -153,13 +170,21 @@ __device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             __align__(16) __half2 hh[4], ll[4];
+            float gq[8], bq[8];           // LayerNorm-1 gamma / beta of the 8 outputs of this slot: four float4 loads
+#pragma unroll
+            for (int v4 = 0; v4 < 2; ++v4) {
+                const float4 gv = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + 256 + warp * 32 + 8 * q + 4 * v4);
+                const float4 bv = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + 512 + warp * 32 + 8 * q + 4 * v4);
+                gq[4 * v4] = gv.x; gq[4 * v4 + 1] = gv.y; gq[4 * v4 + 2] = gv.z; gq[4 * v4 + 3] = gv.w;
+                bq[4 * v4] = bv.x; bq[4 * v4 + 1] = bv.y; bq[4 * v4 + 2] = bv.z; bq[4 * v4 + 3] = bv.w;
+            }
 #pragma unroll
             for (int j2 = 0; j2 < 4; ++j2) {
                 float y[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int j = 8 * q + 2 * j2 + e, o = warp * 32 + j;
-                    y[e] = fmaxf((z[j] - mean) * rstd * sm[MlpTcSmem::P1 + 256 + o] + sm[MlpTcSmem::P1 + 512 + o], 0.0f);
+                    const int j = 8 * q + 2 * j2 + e;
+                    y[e] = fmaxf((z[j] - mean) * rstd * gq[2 * j2 + e] + bq[2 * j2 + e], 0.0f);
                 }
                 __half h0, l0, h1, l1;
                 split_f16(y[0], h0, l0);
@@ -298,18 +323,20 @@ __device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
     __syncthreads();
     // ---- heads: thread = (sample lane, output warp < 6), K = 128 ---------------------------------------------
     if (warp < 6) {
-        float a = 0.0f;
+        // four interleaved partial sums (k mod 4): a 32-deep instead of a 128-deep chain of dependent FMAs on the
+        // lockstep loop's critical path
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
         const float* hp = sm + MlpTcSmem::h2 + lane * kH2Stride;
         const float* wp = sm + MlpTcSmem::Wh + warp;
 #pragma unroll 8
         for (int k = 0; k < 128; k += 4) {
             const float4 h = *reinterpret_cast<const float4*>(hp + k);
-            a = fmaf(h.x, wp[(k + 0) * 8], a);
-            a = fmaf(h.y, wp[(k + 1) * 8], a);
-            a = fmaf(h.z, wp[(k + 2) * 8], a);
-            a = fmaf(h.w, wp[(k + 3) * 8], a);
+            a0 = fmaf(h.x, wp[(k + 0) * 8], a0);
+            a1 = fmaf(h.y, wp[(k + 1) * 8], a1);
+            a2 = fmaf(h.z, wp[(k + 2) * 8], a2);
+            a3 = fmaf(h.w, wp[(k + 3) * 8], a3);
         }
-        sm[MlpTcSmem::out + lane * 8 + warp] = a + sm[MlpTcSmem::bh + warp];
+        sm[MlpTcSmem::out + lane * 8 + warp] = ((a0 + a1) + (a2 + a3)) + sm[MlpTcSmem::bh + warp];
     }
     __syncthreads();
 }

@@ -415,7 +415,7 @@ def run_cuda_arm(args) -> None:
     # split), so the ceiling this kernel can reach is peak/3 -- reported next to it.
     roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peak_tf,
-                "traffic": 33.5e6 if dom.startswith("ppo_grad") else None,   # profiles/r1t_ncu_summary.txt
+                "traffic": 33.5e6 if dom.startswith("ppo_grad") else None,   # profiles/r1u_ncu_summary.txt
                 "peak_source": f"{peaks['source']} bf16 dense (sustained), of measured",
                 "split_ceiling": peak_tf / 3.0, "frac_of_split_ceiling": kernels[dom]["tflops"] / (peak_tf / 3.0),
                 "note": "tcgen05.mma kind::f16 with the two-term fp16 split x = hi + lo/s (fp32 rel 1e-5 parity bar), "

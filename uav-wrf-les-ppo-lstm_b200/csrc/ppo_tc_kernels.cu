@@ -303,6 +303,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         const uint32_t use = st >> 1;
         if (use >= 1) tc::mbar_wait(&bar[st & 1u], (use - 1) & 1u);
     };
+#ifndef PLUME_TC_TMA_B
     // B operand chunk (hi + lo, 16 KB each) from the pre-split weights, cp.async straight into shared memory
     auto load_b = [&](uint32_t st, const float* hi, const float* lo) {
         float4* bh4 = reinterpret_cast<float4*>(stage_buf(st, 2));
@@ -322,6 +323,29 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::tc_fence_before();
         mbar_arrive(&full[st & 1u]);
     };
+#else
+    // -DPLUME_TC_TMA_B: the same chunk as two TMA bulk copies issued by one thread, completing on the step's "full"
+    // barrier (transaction bytes) next to the producers' arrivals -- no LSU traffic and no per-thread wait, but measured
+    // 0.06 ms per iteration SLOWER than the 512-thread cp.async (12.999 vs 12.938 ms): the issuing thread's warp becomes
+    // the straggler of every ring step.  Kept for the comparison.
+    auto load_b = [&](uint32_t st, const float* hi, const float* lo) {
+        if (tid != 0) return;
+        tc::fence_proxy_async();          // earlier generic-proxy writes to this stage (the exchange area aliases it)
+        const uint32_t mb = tc::smem_u32(&full[st & 1u]);
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(2u * kChunkFloats * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tc::smem_u32(stage_buf(st, 2))), "l"(hi), "r"(kChunkFloats * 4u), "r"(mb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tc::smem_u32(stage_buf(st, 3))), "l"(lo), "r"(kChunkFloats * 4u), "r"(mb) : "memory");
+    };
+    // producers: the A operand of step st is complete in shared memory -> visible to the async proxy, arrive
+    auto publish = [&](uint32_t st) {
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        mbar_arrive(&full[st & 1u]);
+    };
+#endif
     // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs, commit to "stage free"
     // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
     auto issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {

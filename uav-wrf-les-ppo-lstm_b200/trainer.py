@@ -50,9 +50,10 @@ class PlumeTrainer:
         self.iteration = 0
         self.last_losses = None
         n_mb = (num_envs * horizon + self.minibatch_size - 1) // self.minibatch_size
-        # my kernels per iteration: rollout (+ deferred stop head), curriculum, gae scan + normalise,
-        # (fwd_bwd, wgrad2, clip_adam) per step
-        self.launches_per_iteration = 4 + (1 if stop_head else 0) + 3 * self.cfg.epochs * n_mb
+        # my kernels per iteration: rollout (+ deferred stop head), curriculum (count, scan, bin, apply), gae scan +
+        # normalise, (weight prep, gradient, clip + Adam) per optimiser step; + sample records and the epoch
+        # permutations when they are materialised (below)
+        self.launches_per_iteration = 1 + (1 if stop_head else 0) + 4 + 2 + 3 * self.cfg.epochs * n_mb
         # the epoch permutations do not depend on the rollout: they are written out on a side stream while the
         # (latency-bound) rollout kernel runs
         self._perm_stream = None
@@ -60,7 +61,7 @@ class PlumeTrainer:
             self._perm_stream = torch.cuda.Stream(device=self.device)
             self._perm_done = torch.cuda.Event()
             self._perm_free = torch.cuda.Event()
-            self.launches_per_iteration += self.cfg.epochs
+            self.launches_per_iteration += self.cfg.epochs + 1
 
     def _permutations_async(self):
         """Launches this iteration's ``epochs`` permutations on the side stream; returns the ``[epochs, T*N]`` tensor."""

@@ -1,8 +1,11 @@
 // ppo_tc_kernels.cu -- K6 on the sm_100a tensor cores: the PPO minibatch gradient
 // (train_ppo2.0.py:42-85) with the three GEMM-shaped parts of the actor-critic's 256->128 layer
 // (model.py:23) on tcgen05.mma (kind::f16 with the two-term fp16 split x = hi + lo/s of tc_gemm.cuh = fp32-grade
-// accuracy at twice the TF32 rate and half the operand bytes, accumulators in TMEM) and everything else (6->256 layer, both LayerNorms, heads, loss, all the reductions) on the
-// CUDA cores of the same persistent CTA.  One CTA per SM, 128-sample tiles, 16 compute warps + 1 issuer warp.
+// accuracy at twice the TF32 rate and half the operand bytes, accumulators in TMEM) and everything else (6->256 layer,
+// both LayerNorms, heads, loss, all the reductions) on the CUDA cores of the same persistent CTA -- with packed fp32
+// pairs (FFMA2 / FMUL2 / FADD2) wherever register pairs form naturally, because the kernel is bound by instruction
+// issue.  One CTA per SM, 128-sample tiles, 16 compute warps + 1 issuer warp.  Per-launch invariants (pre-split W2, the
+// centred layer-1 weights, the LayerNorm-1 quadratic form) come from ppo_tc_prep_kernel.
 //
 //   G1  z2[s][o]   = sum_i  h1[s][i] W2[o][i]        A = h1 (produced chunk by chunk from the 6 inputs),
 //                                                     B = W2, pre-split, streamed from L2 with cp.async
@@ -24,9 +27,13 @@
 // no mean pass is needed.  The algebra was checked against autograd in float64 and its float32
 // error matches autograd's own.
 //
-// Algorithmic bytes per sample: 44 B gathered (obs 24, action 4, old logp 4, adv 4, ret 4, old value 4);
-// nothing else leaves the SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 MMAs for the split),
-// ~14 000 on the CUDA cores.
+// Algorithmic bytes per sample: one 48-byte record (obs 24, adv 4, ret 4, old value 4, old logp 4, action 4, pad 4;
+// plume_ppo_pack) + an 8-byte permutation index; without the records 44 B from six arrays.  Nothing else leaves the
+// SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 MMAs for the split), ~14 000 on the CUDA cores.
+//
+// Build-time knobs (measured defaults, profiles/r1_notes.md): PLUME_U4 / PLUME_U6 unroll factors of the two
+// column-oriented loops, PLUME_TC_MAXNREG (register-sensitivity experiment), PLUME_TC_TMA_B (TMA bulk copies for the
+// B operand), PLUME_TC_TIMELINE (clock64 stamps per phase, printed by CTA 0).
 #include "ppo_loss.cuh"
 #include "tc_gemm.cuh"
 
@@ -58,8 +65,8 @@ struct TcSmem {
     static constexpr int Wh = P2 + 3 * 128;                          // [128][8] heads (6), LN2 gamma, beta
     static constexpr int bh = Wh + 128 * 8;                          // [8]
     static constexpr int x = bh + 8;                                 // [128][8] x0..x5, rstd1, 0
-    static constexpr int dout = x + kTcTile * 8;                     // [128][8] d loss / d (logits, value)
-    static constexpr int sc = dout + kTcTile * 8;                    // [128][4] rstd2, m1, m2, 0
+    static constexpr int dout = x + kTcTile * 8;                     // [128][8] d loss / d (logits, value), pol, val
+    static constexpr int sc = dout + kTcTile * 8;                    // [128][4] rstd2, m1, m2, entropy term
     static constexpr int pf = sc + kTcTile * 4;                      // [128][12] next tile's gathered sample
     static constexpr int total = pf + kTcTile * 12;
     // [groups][128][8] exchange of partial sums between the column groups of one sample row: aliases the last

@@ -374,7 +374,7 @@ def run_cuda_arm(args) -> None:
         pb._lib.check(lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), perm_ptr, 1, 0, 0, min(mb, M), min(mb, M),
                                          cfg.clip_epsilon, cfg.entropy_beta, model.flat_grad.data_ptr(),
                                          loss.data_ptr(), ws.nan_flag.data_ptr(), ws.ws.data_ptr(), ws.bytes,
-                                         torch.cuda.current_stream().cuda_stream), "ppo_grad")
+                                         pb._lib.KERNEL_AUTO, torch.cuda.current_stream().cuda_stream), "ppo_grad")
     grad_ms = min(timed(grad_call, sync) for _ in range(3))
     gae_ms = min(timed(lambda: pb.compute_advantages(buf, cfg, ws, None), sync) for _ in range(3))
     eng = trainer.engine
@@ -388,6 +388,7 @@ def run_cuda_arm(args) -> None:
                                                       eng._window_next.data_ptr(), cfg.conc_peak,
                                                       buf.stop_prob.data_ptr(), buf.stop_flag.data_ptr(),
                                                       buf.peak_pred.data_ptr(), pb._lib.ptr(buf.trend),
+                                                      pb._lib.KERNEL_AUTO,
                                                       torch.cuda.current_stream().cuda_stream), "stop_head_segment")
         seg_ms = min(timed(seg_call, sync) for _ in range(3))
     n_opt = cfg.epochs * ((M + mb - 1) // mb)

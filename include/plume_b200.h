@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PLUME_B200_ABI_VERSION 3
+#define PLUME_B200_ABI_VERSION 4
 
 #define PLUME_OBS_DIM 6          /* environment.py:80-87 */
 #define PLUME_NUM_ACTIONS 5      /* environment.py:23 */
@@ -288,10 +288,17 @@ int plume_rollout(const plume_env_config* cfg, const plume_env_state* st, const 
  * segment into window_out [N][W] (must not alias window_in).  Because the stop decision does not feed
  * back into the rollout unless PLUME_FLAG_STOP_TERMINATES is set, taking the head out of the lockstep
  * loop changes no result; it turns 20 latency-bound cell steps per env-step into a throughput kernel. */
+/* kernel_path: which of the library's two kernel families runs -- an explicit argument of the caller, never an
+ * environment switch.  PLUME_KERNEL_AUTO is a documented shape rule (tcgen05 where the shape has a tensor-core kernel:
+ * hidden 32/64/128/256 for the stop head, >= 1024 samples for plume_ppo_grad), PLUME_KERNEL_TENSOR / PLUME_KERNEL_SIMT
+ * name one (tests compare the two; SIMT = fp32 FMA on the CUDA cores, the in-loop head's exact arithmetic). */
+#define PLUME_KERNEL_AUTO 0
+#define PLUME_KERNEL_TENSOR 1
+#define PLUME_KERNEL_SIMT 2
 int plume_stop_head_segment(const plume_lstm_params* lstm, const float* conc_sample, const uint8_t* fill_t,
                             const double* src_dist, int32_t horizon, int32_t n_envs, const float* window_in,
                             float* window_out, double conc_peak, float* stop_prob, uint8_t* stop_flag,
-                            float* peak_pred, float* trend, void* stream);
+                            float* peak_pred, float* trend, int32_t kernel_path, void* stream);
 
 /* ---- P5 GAE + normalisation, train_ppo2.0.py:17-39 -------------------------------------- */
 /* Per-env reverse scan over [T][N] (the reference's quirks kept: self-bootstrap at T-1, mask with
@@ -341,11 +348,12 @@ int plume_ppo_pack(const plume_ppo_batch* batch, float* packed, void* stream);
  * if perm (int64[M] device) is given, else the stateless bijection keyed by (perm_seed, epoch).
  * Accumulates d(loss)/d(params) into grads float[PLUME_MLP_PARAMS] (caller zeroes) and
  * {loss, policy_loss, value_loss, entropy} sums into loss_out double[4] scaled by 1/mb_size_global.
- * mb_size_global is the divisor of the means (= mb_size on one GPU; sum over ranks otherwise). */
+ * mb_size_global is the divisor of the means (= mb_size on one GPU; sum over ranks otherwise).
+ * kernel_path: PLUME_KERNEL_AUTO / _TENSOR / _SIMT (above). */
 int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int64_t* perm, uint64_t perm_seed,
                    int32_t epoch, int64_t mb_start, int64_t mb_size, int64_t mb_size_global, float clip_eps,
                    float entropy_beta, float* grads, double* loss_out, int32_t* nan_flag, void* workspace,
-                   int64_t workspace_bytes, void* stream);
+                   int64_t workspace_bytes, int32_t kernel_path, void* stream);
 /* bytes of workspace plume_ppo_grad needs for a minibatch of mb_size samples */
 int64_t plume_ppo_workspace_bytes(int64_t mb_size);
 
@@ -356,24 +364,45 @@ int plume_clip_adam(float* params, const float* grads, float* exp_avg, float* ex
                     float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
                     float* grad_norm_out, void* stream);
 
-/* ---- fused gradient all-reduce + clip + Adam over NVLink peer memory (one process per GPU) ------------------
- * The only exchange step of the update (train_ppo2.0.py:85-87 on N data-parallel ranks) as ONE kernel: every
- * rank publishes its gradient in a CUDA-IPC mapped buffer, a system-scope flag exchange replaces the
- * collective's rendezvous, each rank sums all ranks' buffers in rank order (bitwise identical on every rank)
- * and finishes clip_grad_norm_ + Adam from registers.
- *   plume_comm_create   allocates this rank's block, returns an opaque communicator and its 64-byte IPC handle
+/* ---- the exchange steps of a data-parallel iteration over NVLink peer memory (one process per GPU) ----------
+ * No host-launched collective is on the path.  Every rank owns one block that all peers have mapped (CUDA IPC);
+ * a rank publishes into its own block, signals with system-scope release stores into the peers' flag arrays,
+ * waits for the flags of all ranks and reads the peers' blocks.
+ *   plume_comm_create   allocates this rank's block (room for two gradients of n_params floats and two flag-code
+ *                       segments of code_bytes bytes), returns an opaque communicator and its 64-byte IPC handle
  *   plume_comm_connect  maps the peers' blocks: all_handles = the handles of ranks 0..world-1, 64 bytes each
  *                       (exchange them with any host-side all-gather)
- *   plume_allreduce_clip_adam  = all-reduce(sum) of grads over the ranks, then plume_clip_adam; grads receives
- *                       the reduced gradient.  Every rank must call it the same number of times.
- *   plume_comm_error    HOST out 0 ok / 1 a peer did not arrive (bounded spin) / 2 grid barrier timeout */
-int plume_comm_create(int32_t world, int32_t rank, int32_t n_params, void** comm_out, uint8_t* handle_out);
+ *   plume_allreduce_clip_adam  the update's exchange step (train_ppo2.0.py:85-87 on N data-parallel ranks) as ONE
+ *                       kernel: all-reduce(sum) of grads in rank order (bitwise identical on every rank), then
+ *                       plume_clip_adam from registers; grads receives the reduced gradient.
+ *   plume_comm_allreduce_small  values[count <= 32] doubles <- sum over the ranks (the advantage statistics,
+ *                       train_ppo2.0.py:34-38 over the global batch)
+ *   plume_comm_publish_codes    copies this rank's [T][N] flag codes into its block and signals the peers (may run
+ *                       on a side stream while the stop-head kernel runs)
+ *   plume_curriculum_update_peer  waits for every rank's codes, then plume_curriculum_update_packed with the flags
+ *                       read straight from the peers' blocks (no gathered copy)
+ *   Every rank must make the same sequence of calls.  Spins are bounded: on a timeout the kernel applies NOTHING
+ *   (parameters, moments, curriculum stay as they were), records the error and every later exchange kernel returns
+ *   at once.
+ *   plume_comm_error    HOST out 0 ok / 1 a peer did not arrive / 2 grid barrier timeout (synchronises the stream)
+ *   plume_comm_error_async  queues a copy of that word into PINNED host memory behind the work in `stream`
+ *   plume_comm_reset    collective recovery: call on every rank between two host barriers, nothing in flight */
+int plume_comm_create(int32_t world, int32_t rank, int32_t n_params, int64_t code_bytes, void** comm_out,
+                      uint8_t* handle_out);
 int plume_comm_connect(void* comm, const uint8_t* all_handles);
 int plume_comm_destroy(void* comm);
 int plume_comm_error(void* comm, int32_t* error_out, void* stream);
+int plume_comm_error_async(void* comm, int32_t* pinned_error_out, void* stream);
+int plume_comm_reset(void* comm);
 int plume_allreduce_clip_adam(void* comm, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int32_t n,
                               float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
                               float* grad_norm_out, void* stream);
+int plume_comm_allreduce_small(void* comm, double* values, int32_t count, void* stream);
+int plume_comm_publish_codes(void* comm, const uint8_t* flag_code, int64_t bytes, void* stream);
+int plume_curriculum_update_peer(void* comm, int32_t horizon, int32_t n_envs, double* state, double* curriculum,
+                                 double initial_radius, double min_radius, double radius_decay,
+                                 double success_threshold, int32_t window, double decay_factor,
+                                 double* window_radius_out, void* stream);
 
 /* The index permutation plume_ppo_grad uses when perm == NULL: out int64[count] = positions
  * [start, start+count) of the bijection of [0,total) keyed by (seed, epoch). */
@@ -432,11 +461,16 @@ int plume_curriculum_update(const float* dones, const uint8_t* reached, int32_t 
                             double decay_factor, void* stream);
 
 /* Same rule on packed flags of ALL ranks: flag_code uint8 [world][T][N] (bit 0 done, bit 1 reached; the layout an
- * all-gather of the ranks' [T][N] arrays produces); canonical order = step-major, then global env id. */
+ * all-gather of the ranks' [T][N] arrays produces); canonical order = step-major, then global env id.
+ * window_radius_out (may be NULL) double[PLUME_CURRICULUM_MAX_WINDOWS + 2]: [0] = length of the carried partial
+ * window at entry, [1] = number of radii that follow, [2 + b] = the trainer's radius in force for the episodes whose
+ * ordinal (carried length + canonical position in this segment) falls into window b -- the 'Current_Radius' the
+ * reference logs per episode (train_ppo2.0.py:247). */
+#define PLUME_CURRICULUM_MAX_WINDOWS 8192
 int plume_curriculum_update_packed(const uint8_t* flag_code, int32_t horizon, int32_t n_envs, int32_t world,
                                    double* state, double* curriculum, double initial_radius, double min_radius,
                                    double radius_decay, double success_threshold, int32_t window,
-                                   double decay_factor, void* stream);
+                                   double decay_factor, double* window_radius_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_library_exports_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(pb._lib.EXPORTED_SYMBOLS) == declared
-    assert lib.plume_abi_version() == 3
+    assert lib.plume_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

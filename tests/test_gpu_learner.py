@@ -112,11 +112,11 @@ def _oracle_grads(ora, cfg, S, A, LP, ADV, RET, V):
 @pytest.mark.parametrize("path", ["cuda", "tc"])
 @pytest.mark.parametrize("M,mb_start,mb_size", [(256, 0, 256), (1000, 100, 333), (64, 0, 1), (4096, 1024, 2048),
                                                 (60000, 5000, 50001)])
-def test_ppo_gradient_vs_autograd(M, mb_start, mb_size, path, monkeypatch):
+def test_ppo_gradient_vs_autograd(M, mb_start, mb_size, path):
     """Both kernel families (CUDA-core 32-sample tiles, tcgen05 3xTF32 128-sample tiles) against autograd;
     the largest case gives every CTA several tiles (TMEM accumulation across tiles, ragged last tile)."""
-    monkeypatch.setenv("PLUME_PPO_PATH", path)
     m = pb()
+    kpath = m._lib.KERNEL_PATHS[path]
     cfg = po.config_for("2.1")
     torch.manual_seed(M)
     ora = pp.OracleActorCritic()
@@ -174,7 +174,8 @@ def test_ppo_gradient_vs_autograd(M, mb_start, mb_size, path, monkeypatch):
     permd = perm.to(dev)
     rc = lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), permd.data_ptr(), 0, 0, mb_start, mb_size, mb_size,
                             cfg.clip_epsilon, cfg.entropy_beta, model.flat_grad.data_ptr(), loss.data_ptr(),
-                            ws.nan_flag.data_ptr(), ws.ws.data_ptr(), ws.bytes, torch.cuda.current_stream().cuda_stream)
+                            ws.nan_flag.data_ptr(), ws.ws.data_ptr(), ws.bytes, kpath,
+                            torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.plume_last_error()
     got = loss.cpu().numpy()
     assert np.allclose(got, np.array(want), rtol=1e-5, atol=1e-7), (got, want)      # losses: fp32 rel 1e-5
@@ -405,7 +406,7 @@ def test_curriculum_packed_flags_of_several_ranks(world, T, N):
         code = torch.from_numpy((done.astype(np.uint8) | (reached.astype(np.uint8) << 1))).cuda().contiguous()
         rc = lib.plume_curriculum_update_packed(code.data_ptr(), T, N, world, state.data_ptr(), cur.data_ptr(),
                                                 cfg.initial_radius, cfg.min_radius, cfg.radius_decay,
-                                                cfg.success_threshold, cfg.window_size, cfg.decay_factor,
+                                                cfg.success_threshold, cfg.window_size, cfg.decay_factor, None,
                                                 torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         for t in range(T):

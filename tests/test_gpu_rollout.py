@@ -236,16 +236,16 @@ def test_full_size_invariants():
 
 @pytest.mark.parametrize("path", ["cuda", "tc"])
 @pytest.mark.parametrize("splits", [(64,), (7, 13, 44), (32, 32)])
-def test_deferred_stop_head_equals_in_loop_head(splits, path, monkeypatch):
+def test_deferred_stop_head_equals_in_loop_head(splits, path):
     """plume_stop_head_segment (the head taken out of the lockstep loop) reproduces the in-loop head:
     stop probability, flag, peak, trend features, and the window ring carried from one segment to the
     next (also for segments shorter than the window).  The CUDA-core kernel is bit-identical to the
     in-loop head; the tensor-core kernel (3xTF32 gate GEMM, ex2/rcp activations) agrees to fp32 rel 1e-5,
     flags equal wherever the probability is not within 1e-5 of the threshold."""
-    monkeypatch.setenv("PLUME_LSTM_PATH", path)
     N, T = 80, 64
     m, env_a, model_a, head_a, eng_a = _setup(N, T, seed=17, radius=25.0)
     m, env_b, model_b, head_b, eng_b = _setup(N, T, seed=17, radius=25.0)
+    eng_b.stop_head_path = m._lib.KERNEL_PATHS[path]
     ref = eng_a.collect(defer_stop_head=False)
     sp, sf, pk, tr = ref.stop_prob.clone(), ref.stop_flag.clone(), ref.peak_pred.clone(), ref.trend.clone()
     assert (sp > 0).any() and sf.any() and not sf.all()

@@ -71,6 +71,10 @@ class PpoBatch(C.Structure):
 
 
 GAE_VARIANTS = {"quirk": 0, "bootstrap": 1, "v12": 2}
+KERNEL_AUTO, KERNEL_TENSOR, KERNEL_SIMT = 0, 1, 2
+KERNEL_PATHS = {"auto": KERNEL_AUTO, "tensor": KERNEL_TENSOR, "tc": KERNEL_TENSOR, "simt": KERNEL_SIMT,
+                "cuda": KERNEL_SIMT}
+CURRICULUM_MAX_WINDOWS = 8192
 MODEL_ISOTROPIC, MODEL_DISPERSION = 0, 1
 PLUME_MODELS = {"isotropic": MODEL_ISOTROPIC, "code": MODEL_ISOTROPIC, "dispersion": MODEL_DISPERSION,
                 "readme": MODEL_DISPERSION}
@@ -100,7 +104,7 @@ _SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp]),
     "plume_lstm_stop_head": (C.c_int, [_vp] * 8 + [C.c_int32, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "plume_stop_head_segment": (C.c_int, [_P(LstmParams), _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double,
-                                          _vp, _vp, _vp, _vp, _vp]),
+                                          _vp, _vp, _vp, _vp, C.c_int32, _vp]),
     "plume_lstm_forward": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp, _vp]),
     "plume_threshold_head": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plume_trend_features": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, _vp, _vp]),
@@ -112,15 +116,21 @@ _SIGNATURES = {
                                          _vp, _vp, _vp]),
     "plume_gae_normalise_variant": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int32, _vp, _vp]),
     "plume_ppo_grad": (C.c_int, [_vp, _P(PpoBatch), _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
-                                 C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
+                                 C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _vp]),
     "plume_ppo_workspace_bytes": (C.c_int64, [C.c_int64]),
     "plume_ppo_pack": (C.c_int, [_P(PpoBatch), _vp, _vp]),
     "plume_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_int32, _vp, _vp]),
-    "plume_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P(_vp), _vp]),
+    "plume_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P(_vp), _vp]),
     "plume_comm_connect": (C.c_int, [_vp, _vp]),
     "plume_comm_destroy": (C.c_int, [_vp]),
     "plume_comm_error": (C.c_int, [_vp, _P(C.c_int32), _vp]),
+    "plume_comm_error_async": (C.c_int, [_vp, _vp, _vp]),
+    "plume_comm_reset": (C.c_int, [_vp]),
+    "plume_comm_allreduce_small": (C.c_int, [_vp, _vp, C.c_int32, _vp]),
+    "plume_comm_publish_codes": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "plume_curriculum_update_peer": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double, C.c_double,
+                                               C.c_double, C.c_int32, C.c_double, _vp, _vp]),
     "plume_allreduce_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_float, C.c_int32, _vp, _vp]),
     "plume_lstm_dataset": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_float, _vp,
@@ -135,7 +145,7 @@ _SIGNATURES = {
     "plume_curriculum_update": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double,
                                           C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
     "plume_curriculum_update_packed": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_double,
-                                                 C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
+                                                 C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -160,7 +170,7 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError = a declared symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.plume_abi_version() != 3:
+    if lib.plume_abi_version() != 4:
         raise PlumeLibraryError("libplume_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -44,14 +44,18 @@ class PPOBuffer:
         self.advantages = z(torch.float32, T, N)
         self.returns = z(torch.float32, T, N)
         self.filled = 0          # rows written
+        self.reached_stored = True    # False once a row was stored without its `reached` flags
 
     # -- reference API ----------------------------------------------------------------------
     def clear(self) -> None:
         self.filled = 0
         self.flag_code_valid = False
+        self.reached_stored = True
 
-    def store(self, state, action, reward, value, log_prob, done) -> None:
-        """Appends one lockstep row (each argument ``[N]``-shaped, ``state`` ``[N,6]``)."""
+    def store(self, state, action, reward, value, log_prob, done, reached=None) -> None:
+        """Appends one lockstep row (each argument ``[N]``-shaped, ``state`` ``[N,6]``).  ``reached`` (optional, the
+        env's ``info["reached"]``) feeds the batched curriculum (``PPOTrainer.update_from_rollout``); the
+        reference's six-argument call leaves it at "not reached" and drives ``PPOTrainer.update(success)`` itself."""
         t = self.filled
         if t >= self.horizon:
             raise IndexError("PPOBuffer is full: call clear() after update_model()")
@@ -62,6 +66,12 @@ class PPOBuffer:
         self.values[t] = torch.as_tensor(value, device=dev).to(torch.float32).reshape(self.num_envs)
         self.log_probs[t] = torch.as_tensor(log_prob, device=dev).to(torch.float32).reshape(self.num_envs)
         self.dones[t] = torch.as_tensor(done, device=dev).to(torch.float32).reshape(self.num_envs)
+        if reached is None:
+            self.reached[t].zero_()
+            self.reached_stored = False
+        else:
+            self.reached[t] = torch.as_tensor(reached, device=dev).to(torch.uint8).reshape(self.num_envs)
+        self.flag_code_valid = False
         self.filled = t + 1
 
     @property

@@ -5,6 +5,7 @@
 // Algorithmic bytes (DESIGN.md "K5"): scan reads r,V,done (12 B) and writes A (4 B); the
 // normalise pass reads A,V (8 B) and writes A,ret (8 B) => 32 B per transition.
 #include "common.cuh"
+#include "curriculum.cuh"
 
 namespace plume {
 
@@ -163,14 +164,13 @@ __global__ void permutation_kernel(long long total, unsigned long long seed, int
 }
 
 // ---- K8: curriculum over the finished episodes of a [T][N] segment, canonical order ----------
-constexpr int kCurMaxBlocks = 8192;
 
 // PPOTrainer.update (model.py:188-221) for the `total_eps` episodes of a segment whose successes have been binned
 // per curriculum window (blk_succ[b] = successes among episodes [b*window, (b+1)*window) counted from the start
 // of the carried partial window).  One thread.
 __device__ void curriculum_apply(const int* blk_succ, bool overflow, long long total_eps, double* state,
                                  double* curriculum, double initial_radius, double min_radius, double radius_decay,
-                                 double thr, int window, double decay_factor) {
+                                 double thr, int window, double decay_factor, double* win_out) {
     if (overflow) {
         state[4] = -1.0;   // host raises
         return;
@@ -181,10 +181,15 @@ __device__ void curriculum_apply(const int* blk_succ, bool overflow, long long t
     long long succ_total = 0;
     const long long n_done = hist_len + total_eps;
     const long long full = n_done / window;
+    if (win_out) {
+        win_out[0] = (double)hist_len;
+        win_out[1] = (double)((full < kCurMaxBlocks ? full : kCurMaxBlocks - 1) + 1);
+    }
     for (long long b = 0; b <= full && b < kCurMaxBlocks; ++b) {
         long long s = blk_succ[b];
         succ_total += s;
         if (b == 0) s += (long long)state[5];
+        if (win_out) win_out[2 + b] = radius;       // what train_ppo2.0.py:247 logs for the episodes of window b
         if (b < full) {
             // the env sees the trainer's values from before this update (model.py:189-190)
             env_radius = radius;
@@ -230,8 +235,8 @@ struct FlagsSeparate {            // float dones + uint8 reached, one rank: posi
     }
     __device__ __forceinline__ void next() { pos += 32; }
 };
-struct FlagsPacked {              // uint8 code (bit 0 done, bit 1 reached) laid out [world][T][N]; canonical
-    const uint8_t* code;          // order = step-major, then GLOBAL env id = rank * N + local id
+struct FlagsPacked {              // uint8 code (bit 0 done, bit 1 reached), one [T][N] array per rank; canonical
+    CodeSrc code;                 // order = step-major, then GLOBAL env id = rank * N + local id
     int T, N, world;
     int t, r, n;                  // cursor: position of lane 0
     __device__ __forceinline__ void seek(long long p) {
@@ -250,7 +255,7 @@ struct FlagsPacked {              // uint8 code (bit 0 done, bit 1 reached) laid
                 ++tt;
             }
         }
-        return code[((size_t)rr * T + tt) * N + nn];
+        return code.base[rr][(size_t)tt * N + nn];
     }
     __device__ __forceinline__ void next() {
         n += 32;
@@ -268,7 +273,8 @@ template <typename Flags>
 __global__ void __launch_bounds__(1024) curriculum_kernel(Flags flags, long long total,
                                                           double* state, double* curriculum, double initial_radius,
                                                           double min_radius, double radius_decay, double thr,
-                                                          int window, double decay_factor) {
+                                                          int window, double decay_factor, double* win_out,
+                                                          const uint32_t* comm_error) {
     // One CTA (the episode order is a serial dependency), 32 warps; warp w owns the contiguous range
     // [w*chunk, (w+1)*chunk) and walks it 32 flags at a time with coalesced loads + ballots.
     __shared__ int ep_cnt[32];
@@ -308,9 +314,9 @@ __global__ void __launch_bounds__(1024) curriculum_kernel(Flags flags, long long
     }
     if (overflow) atomicOr(&overflow_any, 1);
     __syncthreads();
-    if (tid == (int)blockDim.x - 1)
+    if (tid == (int)blockDim.x - 1 && !(comm_error && *comm_error))
         curriculum_apply(blk_succ, overflow_any != 0, ord - hist_len, state, curriculum, initial_radius, min_radius,
-                         radius_decay, thr, window, decay_factor);
+                         radius_decay, thr, window, decay_factor, win_out);
 }
 
 
@@ -321,18 +327,18 @@ __global__ void __launch_bounds__(1024) curriculum_kernel(Flags flags, long long
 constexpr int kCurChunk = 2048;                 // canonical positions per warp (4 loads of 512)
 constexpr int kCurMaxChunks = 1 << 16;
 
-__device__ __forceinline__ const uint4* packed_chunk_ptr(const uint8_t* code, int T, int N, int world, long long p) {
+__device__ __forceinline__ const uint4* packed_chunk_ptr(const CodeSrc& code, int N, int world, long long p) {
     const long long row = (long long)world * N;
     const long long t = p / row, g = p - t * row;
     const long long r = g / N, n = g - r * N;
-    return reinterpret_cast<const uint4*>(code + ((size_t)r * T + t) * N + n);
+    return reinterpret_cast<const uint4*>(code.base[r] + (size_t)t * N + n);
 }
 __device__ __forceinline__ int count_done16(const uint4 v) {
     return __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
            __popc(v.w & 0x01010101u);
 }
 
-__global__ void __launch_bounds__(256) cur_count_kernel(const uint8_t* __restrict__ code, int T, int N, int world,
+__global__ void __launch_bounds__(256) cur_count_kernel(const CodeSrc code, int N, int world,
                                                         long long total, int* __restrict__ chunk_cnt, int n_chunks) {
     const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (chunk >= n_chunks) return;
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(256) cur_count_kernel(const uint8_t* __restric
 #pragma unroll
     for (int q = 0; q < kCurChunk / 512; ++q) {
         const long long p = (long long)chunk * kCurChunk + q * 512;
-        if (p < total) c += count_done16(__ldg(packed_chunk_ptr(code, T, N, world, p) + lane));
+        if (p < total) c += count_done16(__ldg(packed_chunk_ptr(code, N, world, p) + lane));
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) chunk_cnt[chunk] = c;
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(1024) cur_scan_kernel(int* __restrict__ chunk_
     }
 }
 
-__global__ void __launch_bounds__(256) cur_bin_kernel(const uint8_t* __restrict__ code, int T, int N, int world,
+__global__ void __launch_bounds__(256) cur_bin_kernel(const CodeSrc code, int N, int world,
                                                       long long total, const int* __restrict__ chunk_base, int n_chunks,
                                                       const double* __restrict__ state, int window,
                                                       int* __restrict__ bins, int* __restrict__ total_out) {
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(256) cur_bin_kernel(const uint8_t* __restrict_
     for (int q = 0; q < kCurChunk / 512; ++q) {
         const long long p = (long long)chunk * kCurChunk + q * 512;
         if (p >= total) break;
-        const uint4 v = __ldg(packed_chunk_ptr(code, T, N, world, p) + lane);
+        const uint4 v = __ldg(packed_chunk_ptr(code, N, world, p) + lane);
         const int c = count_done16(v);
         int incl = c;                                            // inclusive warp scan of the per-lane counts
         for (int o = 1; o < 32; o <<= 1) {
@@ -412,16 +418,45 @@ __global__ void __launch_bounds__(256) cur_bin_kernel(const uint8_t* __restrict_
 
 __global__ void cur_apply_kernel(const int* bins, const int* total_in, double* state, double* curriculum,
                                  double initial_radius, double min_radius, double radius_decay, double thr, int window,
-                                 double decay_factor) {
-    if (threadIdx.x == 0 && blockIdx.x == 0)
+                                 double decay_factor, double* win_out, const uint32_t* comm_error) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !(comm_error && *comm_error))
         curriculum_apply(bins, total_in[1] != 0, (long long)total_in[0], state, curriculum, initial_radius, min_radius,
-                         radius_decay, thr, window, decay_factor);
+                         radius_decay, thr, window, decay_factor, win_out);
 }
 
 static int* curriculum_scratch() {       // chunk counts + window bins + {total, overflow}; stream-ordered reuse
     static int* buf = nullptr;
     if (!buf && cudaMalloc(&buf, (kCurMaxChunks + kCurMaxBlocks + 8) * sizeof(int)) != cudaSuccess) buf = nullptr;
     return buf;
+}
+
+int launch_curriculum_packed(const CodeSrc& src, int horizon, int n_envs, int world, double* state, double* curriculum,
+                             double initial_radius, double min_radius, double radius_decay, double success_threshold,
+                             int window, double decay_factor, double* window_radius_out, const uint32_t* comm_error,
+                             cudaStream_t s) {
+    const long long total = (long long)horizon * n_envs * world;
+    const long long n_chunks = (total + kCurChunk - 1) / kCurChunk;
+    bool aligned = true;
+    for (int r = 0; r < world; ++r) aligned = aligned && (reinterpret_cast<uintptr_t>(src.base[r]) & 15) == 0;
+    if (n_envs % 512 == 0 && n_chunks <= kCurMaxChunks && aligned) {
+        int* scratch = curriculum_scratch();
+        if (!scratch) return fail("curriculum: cannot allocate scratch");
+        int *chunk_cnt = scratch, *bins = scratch + kCurMaxChunks, *tot = bins + kCurMaxBlocks;
+        const int blocks = (int)((n_chunks * 32 + 255) / 256);
+        cur_count_kernel<<<blocks, 256, 0, s>>>(src, n_envs, world, total, chunk_cnt, (int)n_chunks);
+        cur_scan_kernel<<<1, 1024, 0, s>>>(chunk_cnt, (int)n_chunks, bins, tot);
+        cur_bin_kernel<<<blocks, 256, 0, s>>>(src, n_envs, world, total, chunk_cnt, (int)n_chunks, state, window, bins,
+                                              tot);
+        cur_apply_kernel<<<1, 32, 0, s>>>(bins, tot, state, curriculum, initial_radius, min_radius, radius_decay,
+                                          success_threshold, window, decay_factor, window_radius_out, comm_error);
+        PLUME_LAUNCH_CHECK();
+        return 0;
+    }
+    curriculum_kernel<<<1, 1024, 0, s>>>(FlagsPacked{src, horizon, n_envs, world, 0, 0, 0}, total, state, curriculum,
+                                         initial_radius, min_radius, radius_decay, success_threshold, window,
+                                         decay_factor, window_radius_out, comm_error);
+    PLUME_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace plume
@@ -503,7 +538,7 @@ extern "C" int plume_curriculum_update(const float* dones, const uint8_t* reache
     if (horizon <= 0 || n_envs <= 0) return 0;
     curriculum_kernel<<<1, 1024, 0, as_stream(stream)>>>(FlagsSeparate{dones, reached, 0}, (long long)horizon * n_envs,
                                                          state, curriculum, initial_radius, min_radius, radius_decay,
-                                                         success_threshold, window, decay_factor);
+                                                         success_threshold, window, decay_factor, nullptr, nullptr);
     PLUME_LAUNCH_CHECK();
     return 0;
 }
@@ -511,31 +546,15 @@ extern "C" int plume_curriculum_update(const float* dones, const uint8_t* reache
 extern "C" int plume_curriculum_update_packed(const uint8_t* flag_code, int32_t horizon, int32_t n_envs, int32_t world,
                                               double* state, double* curriculum, double initial_radius,
                                               double min_radius, double radius_decay, double success_threshold,
-                                              int32_t window, double decay_factor, void* stream) {
+                                              int32_t window, double decay_factor, double* window_radius_out,
+                                              void* stream) {
     PLUME_CHECK_ARG(flag_code && state && curriculum, "null pointer");
-    PLUME_CHECK_ARG(window > 0 && world >= 1, "window and world must be positive");
+    PLUME_CHECK_ARG(window > 0 && world >= 1 && world <= kCommMaxWorld, "window and world must be positive");
     if (horizon <= 0 || n_envs <= 0) return 0;
-    const long long total = (long long)horizon * n_envs * world;
-    const long long n_chunks = (total + kCurChunk - 1) / kCurChunk;
-    if (n_envs % 512 == 0 && n_chunks <= kCurMaxChunks && (reinterpret_cast<uintptr_t>(flag_code) & 15) == 0) {
-        int* scratch = curriculum_scratch();
-        if (!scratch) return fail("plume_curriculum_update_packed: cannot allocate scratch");
-        int *chunk_cnt = scratch, *bins = scratch + kCurMaxChunks, *tot = bins + kCurMaxBlocks;
-        cudaStream_t s = as_stream(stream);
-        const int blocks = (int)((n_chunks * 32 + 255) / 256);
-        cur_count_kernel<<<blocks, 256, 0, s>>>(flag_code, horizon, n_envs, world, total, chunk_cnt, (int)n_chunks);
-        cur_scan_kernel<<<1, 1024, 0, s>>>(chunk_cnt, (int)n_chunks, bins, tot);
-        cur_bin_kernel<<<blocks, 256, 0, s>>>(flag_code, horizon, n_envs, world, total, chunk_cnt, (int)n_chunks, state,
-                                              window, bins, tot);
-        cur_apply_kernel<<<1, 32, 0, s>>>(bins, tot, state, curriculum, initial_radius, min_radius, radius_decay,
-                                          success_threshold, window, decay_factor);
-        PLUME_LAUNCH_CHECK();
-        return 0;
-    }
-    curriculum_kernel<<<1, 1024, 0, as_stream(stream)>>>(FlagsPacked{flag_code, horizon, n_envs, world, 0, 0, 0},
-                                                         (long long)horizon * n_envs * world, state, curriculum,
-                                                         initial_radius, min_radius, radius_decay, success_threshold,
-                                                         window, decay_factor);
-    PLUME_LAUNCH_CHECK();
-    return 0;
+    CodeSrc src;
+    for (int r = 0; r < kCommMaxWorld; ++r)
+        src.base[r] = r < world ? flag_code + (size_t)r * horizon * n_envs : nullptr;
+    return launch_curriculum_packed(src, horizon, n_envs, world, state, curriculum, initial_radius, min_radius,
+                                    radius_decay, success_threshold, window, decay_factor, window_radius_out, nullptr,
+                                    as_stream(stream));
 }

@@ -437,18 +437,19 @@ extern "C" int plume_lstm_stop_head(const float* w_ih, const float* w_hh, const 
 extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const float* conc_sample, const uint8_t* fill_t,
                                        const double* src_dist, int32_t horizon, int32_t n_envs,
                                        const float* window_in, float* window_out, double conc_peak, float* stop_prob,
-                                       uint8_t* stop_flag, float* peak_pred, float* trend, void* stream) {
+                                       uint8_t* stop_flag, float* peak_pred, float* trend, int32_t kernel_path,
+                                       void* stream) {
     PLUME_CHECK_ARG(lstm && conc_sample && fill_t && window_in, "null pointer");
+    PLUME_CHECK_ARG(kernel_path >= PLUME_KERNEL_AUTO && kernel_path <= PLUME_KERNEL_SIMT, "unknown kernel_path");
     PLUME_CHECK_ARG(lstm->w_ih && lstm->w_hh && lstm->b_ih && lstm->b_hh && lstm->w_peak && lstm->b_peak &&
                         lstm->w_stop && lstm->b_stop, "null LSTM parameter");
     PLUME_CHECK_ARG(lstm->window >= 1 && lstm->window <= kLstmMaxSteps, "stop-head window must be in [1,32]");
     PLUME_CHECK_ARG(!trend || src_dist, "trend features need src_dist");
     PLUME_CHECK_ARG(window_out != window_in, "window_out must not alias window_in");
     if (horizon <= 0 || n_envs <= 0) return 0;
-    // hidden = 32: gate GEMM on the tensor cores (lstm_tc_kernels.cu); PLUME_LSTM_PATH=cuda forces the
+    // hidden = 32: gate GEMM on the tensor cores (lstm_tc_kernels.cu); kernel_path = PLUME_KERNEL_SIMT selects the
     // CUDA-core kernel, whose arithmetic is bit-identical to the in-loop head of plume_rollout
-    const char* path = getenv("PLUME_LSTM_PATH");
-    if (lstm->hidden == 32 && !(path && path[0] == 'c')) {
+    if (lstm->hidden == 32 && kernel_path != PLUME_KERNEL_SIMT) {
         LtArgs t;
         t.conc_sample = conc_sample;
         t.fill_t = fill_t;

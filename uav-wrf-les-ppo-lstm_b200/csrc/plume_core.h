@@ -368,21 +368,27 @@ PLUME_HD double visit_denominator(int vc) {
     return dadd(dsqrt(dsqrt(dmul(dmul(v, v), v))), 1.0);
 }
 
-// (float)(vc**0.75 + 1) and (float)(step / max_steps): host tables when the caller provides them
+// (float)(vc**0.75 + 1) and (float)(step / max_steps): host tables when the caller provides them.  The tables hold
+// max_steps + 2 and max_steps + 1 entries; an env stepped past `done` (the reference allows it: evaluators run a
+// fixed number of steps, environment.py has no guard) leaves them and takes the arithmetic form.
 PLUME_HD float visit_denominator_f(const Cfg& c, int vc) {
+    if (c.visit_denom_tab && vc <= c.max_steps + 1) {
 #if defined(__CUDA_ARCH__)
-    if (c.visit_denom_tab) return __ldg(c.visit_denom_tab + vc);
+        return __ldg(c.visit_denom_tab + vc);
 #else
-    if (c.visit_denom_tab) return c.visit_denom_tab[vc];
+        return c.visit_denom_tab[vc];
 #endif
+    }
     return (float)visit_denominator(vc);
 }
 PLUME_HD float step_fraction_f(const Cfg& c, int step) {
+    if (c.step_frac_tab && step <= c.max_steps) {
 #if defined(__CUDA_ARCH__)
-    if (c.step_frac_tab) return __ldg(c.step_frac_tab + step);
+        return __ldg(c.step_frac_tab + step);
 #else
-    if (c.step_frac_tab) return c.step_frac_tab[step];
+        return c.step_frac_tab[step];
 #endif
+    }
     return (float)ddiv((double)step, (double)c.max_steps);
 }
 

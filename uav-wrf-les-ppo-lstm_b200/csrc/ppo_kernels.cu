@@ -396,14 +396,14 @@ __global__ void __launch_bounds__(256, 1) ppo_wgrad2_kernel(const float* __restr
 
 using namespace plume;
 
-// Which kernel family computes a minibatch: the tensor-core path (ppo_tc_kernels.cu, 128-sample tiles) from
-// kTcMinBatch samples on, the CUDA-core path (32-sample tiles, more CTAs for tiny batches such as the
-// reference's 256) below.  PLUME_PPO_PATH=tc|cuda forces one of them (tests compare the two).
+// Which kernels compute a minibatch is the CALLER's choice (kernel_path argument of plume_ppo_grad): the tcgen05
+// kernel (ppo_tc_kernels.cu, 128-sample tiles, one CTA per SM) or the fp32-FMA kernels below (32-sample tiles, more
+// CTAs for tiny batches such as the reference's 256).  PLUME_KERNEL_AUTO is a size rule, not a fallback: tcgen05 from
+// kTcMinBatch samples on.
 constexpr int64_t kTcMinBatch = 1024;
-static bool use_tc_path(int64_t mb_size) {
-    const char* e = getenv("PLUME_PPO_PATH");
-    if (e && e[0] == 't') return true;
-    if (e && e[0] == 'c') return false;
+static bool use_tc_path(int64_t mb_size, int32_t kernel_path) {
+    if (kernel_path == PLUME_KERNEL_TENSOR) return true;
+    if (kernel_path == PLUME_KERNEL_SIMT) return false;
     return mb_size >= kTcMinBatch;
 }
 
@@ -427,8 +427,9 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
                               uint64_t perm_seed, int32_t epoch, int64_t mb_start, int64_t mb_size,
                               int64_t mb_size_global, float clip_eps, float entropy_beta, float* grads,
                               double* loss_out, int32_t* nan_flag, void* workspace, int64_t workspace_bytes,
-                              void* stream) {
+                              int32_t kernel_path, void* stream) {
     PLUME_CHECK_ARG(params && batch && grads && loss_out && nan_flag && workspace, "null pointer");
+    PLUME_CHECK_ARG(kernel_path >= PLUME_KERNEL_AUTO && kernel_path <= PLUME_KERNEL_SIMT, "unknown kernel_path");
     PLUME_CHECK_ARG(batch->obs && batch->actions && batch->old_log_probs && batch->advantages && batch->returns &&
                         batch->old_values, "null batch pointer");
     PLUME_CHECK_ARG(mb_start >= 0 && mb_size >= 0 && mb_start + mb_size <= batch->total, "minibatch outside [0,total)");
@@ -459,7 +460,7 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
     a.loss_out = loss_out;
     a.nan_flag = nan_flag;
     a.ws_dz2 = a.ws_x = a.ws_stat = nullptr;
-    if (use_tc_path(mb_size)) return launch_ppo_tc(params, a, workspace, as_stream(stream));
+    if (use_tc_path(mb_size, kernel_path)) return launch_ppo_tc(params, a, workspace, as_stream(stream));
     const int64_t padded = ((mb_size + kTileM - 1) / kTileM) * kTileM;
     uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
     a.ws_dz2 = reinterpret_cast<float*>(wsp);

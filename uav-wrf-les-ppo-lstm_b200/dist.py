@@ -97,40 +97,102 @@ def gather_flag_codes(code: torch.Tensor, process_group=None) -> torch.Tensor:
 
 
 class PeerComm:
-    """The update's exchange step without NCCL: every rank's gradient buffer is mapped into every peer (CUDA
-    IPC over NVLink) and ``plume_allreduce_clip_adam`` does all-reduce + clip + Adam in one kernel
+    """The exchange steps of a data-parallel iteration without NCCL: every rank's block (two gradient buffers, two
+    flag-code segments, small vectors) is mapped into every peer (CUDA IPC over NVLink).
+    ``plume_allreduce_clip_adam`` does all-reduce + clip + Adam in one kernel, ``allreduce_small`` sums the
+    advantage statistics, ``publish_codes`` + ``plume_curriculum_update_peer`` replace the flag all-gather
     (csrc/comm_kernels.cu).  The 64-byte IPC handles travel through one ``all_gather_object`` at start-up."""
 
-    def __init__(self, process_group, n_params: int, device):
+    def __init__(self, process_group, n_params: int, device, code_bytes: int = 0):
         import ctypes as C
 
         from . import _lib
         self.lib = _lib.load()
+        self.process_group = process_group
         self.world = dist.get_world_size(process_group)
         self.rank = dist.get_rank(process_group)
         self.device = torch.device(device)
         self._h = C.c_void_p()
         handle = (C.c_uint8 * 64)()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.plume_comm_create(self.world, self.rank, int(n_params), C.byref(self._h), handle),
-                       "plume_comm_create")
+            _lib.check(self.lib.plume_comm_create(self.world, self.rank, int(n_params), int(code_bytes),
+                                                  C.byref(self._h), handle), "plume_comm_create")
             gathered = [None] * self.world
             dist.all_gather_object(gathered, bytes(handle), group=process_group)
             blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(gathered))
             _lib.check(self.lib.plume_comm_connect(self._h, blob), "plume_comm_connect")
         dist.barrier(group=process_group)
+        # asynchronous read-back of the error word: a pinned host word + an event per iteration
+        self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._err_event = None
 
-    def check(self) -> None:
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def allreduce_small(self, values: torch.Tensor) -> None:
+        """``values`` (<= 32 doubles, device) <- sum over the ranks, in rank order."""
+        from . import _lib
+        assert values.dtype == torch.float64 and values.is_contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.plume_comm_allreduce_small(self._h, values.data_ptr(), int(values.numel()),
+                                                           self._stream()), "plume_comm_allreduce_small")
+
+    def publish_codes(self, code: torch.Tensor, stream=None) -> None:
+        """Copies this rank's ``[T, N]`` uint8 flag codes into its mapped block and signals the peers."""
+        from . import _lib
+        code = code.contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.plume_comm_publish_codes(self._h, code.data_ptr(), int(code.numel()),
+                                                         stream if stream is not None else self._stream()),
+                       "plume_comm_publish_codes")
+
+    def error_code(self) -> int:
         import ctypes as C
 
         from . import _lib
         err = C.c_int32(0)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.plume_comm_error(self._h, C.byref(err),
-                                                 torch.cuda.current_stream(self.device).cuda_stream), "plume_comm_error")
-        if err.value:
-            raise RuntimeError({1: "peer-memory all-reduce: a rank did not publish its gradient in time",
-                                2: "peer-memory all-reduce: grid barrier timed out"}.get(err.value, "comm error"))
+            _lib.check(self.lib.plume_comm_error(self._h, C.byref(err), self._stream()), "plume_comm_error")
+        return int(err.value)
+
+    _MESSAGES = {1: "peer-memory exchange: a rank did not publish in time (the step was NOT applied)",
+                 2: "peer-memory exchange: grid barrier timed out (the step was NOT applied)"}
+
+    def check(self) -> None:
+        """Synchronous check: raises if any exchange kernel of this communicator timed out."""
+        err = self.error_code()
+        if err:
+            raise RuntimeError(self._MESSAGES.get(err, "comm error") + "; call reset() on every rank to continue")
+
+    def check_async_begin(self) -> None:
+        """Queues a read-back of the error word behind the work enqueued so far (no host synchronisation)."""
+        from . import _lib
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.plume_comm_error_async(self._h, self._err_host.data_ptr(), self._stream()),
+                       "plume_comm_error_async")
+            self._err_event = torch.cuda.Event()
+            self._err_event.record(torch.cuda.current_stream(self.device))
+
+    def check_async_end(self) -> None:
+        """Waits for the read-back queued by ``check_async_begin`` (i.e. for the previous iteration) and raises on
+        a recorded timeout."""
+        if self._err_event is None:
+            return
+        self._err_event.synchronize()
+        self._err_event = None
+        err = int(self._err_host[0])
+        if err:
+            raise RuntimeError(self._MESSAGES.get(err, "comm error") + "; call reset() on every rank to continue")
+
+    def reset(self) -> None:
+        """Collective recovery after a reported timeout: clears the error word and the exchange counters."""
+        from . import _lib
+        dist.barrier(group=self.process_group)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.plume_comm_reset(self._h), "plume_comm_reset")
+        self._err_host.zero_()
+        self._err_event = None
+        dist.barrier(group=self.process_group)
 
     def close(self) -> None:
         if self._h:

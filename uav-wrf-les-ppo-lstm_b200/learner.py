@@ -115,7 +115,7 @@ def materialise_permutations(lib, out: torch.Tensor, m: int, perm_seed: int, epo
 
 
 def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_group=None, variant: str = "quirk",
-                       last_values=None) -> None:
+                       last_values=None, comm=None) -> None:
     """P5: GAE reverse scan per env column + global normalisation; fills ``buffer.advantages``
     and ``buffer.returns`` (train_ppo2.0.py:17-39).  ``variant``: "quirk" (the V2.x/V1.1 update, the
     parity target), "bootstrap" (PPOV1.1/train_ppo1.0.py:66-89, needs ``last_values`` [N] = V(next state))
@@ -131,7 +131,10 @@ def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_gr
                                               buffer.dones.data_ptr(), _lib.ptr(last_values), T, N, cfg.gamma, cfg.lam,
                                               var, buffer.advantages.data_ptr(), ws.stats.data_ptr(), _stream(dev)),
                    "plume_gae_scan_variant")
-        pdist.allreduce_stats(ws.stats, process_group)
+        if comm is not None:             # three doubles over NVLink peer memory, no host-launched collective
+            comm.allreduce_small(ws.stats)
+        else:
+            pdist.allreduce_stats(ws.stats, process_group)
         _lib.check(lib.plume_gae_normalise_variant(buffer.advantages.data_ptr(), buffer.values.data_ptr(), T * N,
                                                    ws.stats.data_ptr(), var, buffer.returns.data_ptr(), _stream(dev)),
                    "plume_gae_normalise_variant")
@@ -139,8 +142,13 @@ def compute_advantages(buffer, cfg: PlumeConfig, ws: UpdateWorkspace, process_gr
 
 def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms=None,
                  minibatch_size: int | None = None, workspace: UpdateWorkspace | None = None,
-                 process_group=None, perm_seed: int = 0, check_nan: bool = True, record=None):
+                 process_group=None, perm_seed: int = 0, check_nan: bool = True, record=None,
+                 kernel_path: str = "auto"):
     """Drop-in for ``_update_model(buffer, model, optimizer)`` (train_ppo2.0.py:14-87).
+
+    ``optimizer`` must be a ``FusedAdam`` over ``model`` (``torch.optim.Adam`` cannot see the kernels' flat
+    gradient buffer: its ``zero_grad()`` drops ``p.grad``).  ``kernel_path``: "auto" (tcgen05 from 1024 samples per
+    minibatch), "tensor" or "simt" -- which of the two kernel families computes the gradient.
 
     ``perms``: optional list of ``cfg.epochs`` int64 index permutations of the flat ``[T*N]``
     transition set (what ``torch.randperm`` gives the reference, :43); by default the kernels use
@@ -149,6 +157,10 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
     gradient are all-reduced (each rank holds its own envs).  Returns a ``[steps, 4]`` float64
     device tensor of (loss, policy loss, value loss, entropy) per optimiser step."""
     cfg = cfg or config_for("2.1")
+    if not isinstance(optimizer, FusedAdam) or optimizer.model is not model:
+        raise TypeError("update_model needs a FusedAdam built over this model (the gradient kernels accumulate into "
+                        "model.flat_grad, which torch.optim optimisers neither zero nor read)")
+    kpath = _lib.KERNEL_PATHS[kernel_path]
     lib = _lib.load()
     dev = buffer.device
     T, N = buffer.filled, buffer.num_envs
@@ -158,7 +170,8 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
     mb = int(minibatch_size or cfg.batch_size)
     if workspace is None or workspace.max_minibatch < min(mb, M):
         workspace = UpdateWorkspace(dev, min(mb, M))
-    compute_advantages(buffer, cfg, workspace, process_group)
+    comm = getattr(optimizer, "comm", None)
+    compute_advantages(buffer, cfg, workspace, process_group, comm=comm)
     batch = _lib.PpoBatch(M, buffer.obs.data_ptr(), buffer.actions.data_ptr(), buffer.log_probs.data_ptr(),
                           buffer.advantages.data_ptr(), buffer.returns.data_ptr(), buffer.values.data_ptr(), None)
     if M >= MATERIALISE_PERM_MIN:
@@ -185,9 +198,9 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
                                         size, pdist.global_minibatch(size, process_group), cfg.clip_epsilon, cfg.entropy_beta,
                                         model.flat_grad.data_ptr(), losses[step].data_ptr(),
                                         workspace.nan_flag.data_ptr(), workspace.ws.data_ptr(), workspace.bytes,
-                                        _stream(dev))
+                                        kpath, _stream(dev))
                 _lib.check(rc, "plume_ppo_grad")
-                if getattr(optimizer, "comm", None) is None:
+                if comm is None:
                     pdist.allreduce_gradient(model.flat_grad, process_group)      # NCCL; else fused into step()
                 optimizer.step()
                 if record is not None:
@@ -212,6 +225,7 @@ class PPOTrainer:
         self.current_radius = self.cfg.initial_radius
         self.explore_bonus = self.cfg.explore_bonus
         self._dev_state = None
+        self._window_radius = None
 
     def update(self, success) -> None:
         c = self.cfg
@@ -245,23 +259,46 @@ class PPOTrainer:
             self._dev_state = s
         return self._dev_state
 
-    def update_from_rollout(self, buffer, process_group=None) -> None:
-        """With ``process_group`` the flags of all ranks are gathered first, so every rank replays the
-        same global episode stream and ends with identical curriculum scalars."""
+    def window_radius(self) -> torch.Tensor:
+        """double[MAX_WINDOWS + 2] written by the last ``update_from_rollout``: [0] length of the carried partial
+        window at entry, [1] count, [2 + b] the trainer's radius in force for the episodes of window b -- the
+        per-episode 'Current_Radius' of the reference's CSV (train_ppo2.0.py:247)."""
+        if self._window_radius is None:
+            self._window_radius = torch.zeros(_lib.CURRICULUM_MAX_WINDOWS + 2, dtype=torch.float64,
+                                              device=self.env.device)
+        return self._window_radius
+
+    def flag_codes(self, buffer) -> torch.Tensor:
+        T = buffer.filled
+        if getattr(buffer, "flag_code_valid", False):
+            return buffer.flag_code[:T]
+        # rows appended with store(): derive the packed flags
+        if not getattr(buffer, "reached_stored", True):
+            raise ValueError("update_from_rollout: rows were stored without `reached` (PPOBuffer.store(..., reached=)); "
+                             "the curriculum would count every episode as a failure")
+        return ((buffer.dones[:T] != 0).to(torch.uint8) | (buffer.reached[:T] != 0).to(torch.uint8) * 2).contiguous()
+
+    def update_from_rollout(self, buffer, process_group=None, comm=None, codes_published: bool = False) -> None:
+        """With ``process_group`` the flags of all ranks are gathered first (or, with a ``dist.PeerComm``, read
+        straight from the peers' mapped buffers), so every rank replays the same global episode stream and ends
+        with identical curriculum scalars."""
         lib = _lib.load()
         c, st = self.cfg, self.device_state()
         T = buffer.filled
-        if getattr(buffer, "flag_code_valid", False):
-            code = buffer.flag_code[:T]
-        else:      # rows appended with store(): derive the packed flags
-            code = (buffer.dones[:T] != 0).to(torch.uint8) | (buffer.reached[:T] != 0).to(torch.uint8) * 2
-        codes = pdist.gather_flag_codes(code.contiguous(), process_group)       # [world, T, N]
+        consts = (c.initial_radius, c.min_radius, c.radius_decay, c.success_threshold, c.window_size, c.decay_factor)
+        wr = self.window_radius()
         with torch.cuda.device(self.env.device):
-            rc = lib.plume_curriculum_update_packed(codes.data_ptr(), T, buffer.num_envs, codes.shape[0],
-                                                    st.data_ptr(), self.env.curriculum.data_ptr(),
-                                                    c.initial_radius, c.min_radius, c.radius_decay,
-                                                    c.success_threshold, c.window_size, c.decay_factor,
-                                                    _stream(self.env.device))
+            if comm is not None:
+                if not codes_published:
+                    comm.publish_codes(self.flag_codes(buffer))
+                rc = lib.plume_curriculum_update_peer(comm._h, T, buffer.num_envs, st.data_ptr(),
+                                                      self.env.curriculum.data_ptr(), *consts, wr.data_ptr(),
+                                                      _stream(self.env.device))
+            else:
+                codes = pdist.gather_flag_codes(self.flag_codes(buffer).contiguous(), process_group)   # [world, T, N]
+                rc = lib.plume_curriculum_update_packed(codes.data_ptr(), T, buffer.num_envs, codes.shape[0],
+                                                        st.data_ptr(), self.env.curriculum.data_ptr(), *consts,
+                                                        wr.data_ptr(), _stream(self.env.device))
         _lib.check(rc, "plume_curriculum_update")
 
     def sync_from_device(self) -> dict:

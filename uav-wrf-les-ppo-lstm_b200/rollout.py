@@ -19,12 +19,16 @@ from .config import FIELD_PROCEDURAL
 
 class RolloutEngine:
     def __init__(self, env, model, stop_head=None, horizon: int = 256, with_info: bool = False,
-                 with_trend: bool = False, with_trajectory: bool = False):
+                 with_trend: bool = False, with_trajectory: bool = False, stop_head_path: str = "auto"):
         if env.field_mode != FIELD_PROCEDURAL:
             raise ValueError("the fused rollout needs field_mode='procedural'")
         self.env, self.model, self.stop_head = env, model, stop_head
         self.lib = _lib.load()
         self.horizon = int(horizon)
+        # which kernel family evaluates the deferred stop head: "auto" (tcgen05 where the hidden size has a
+        # tensor-core kernel), "tensor", "simt" (bit-identical to the in-loop head)
+        self.stop_head_path = _lib.KERNEL_PATHS[stop_head_path]
+        self.after_loop = None        # optional callable run between the lockstep kernel and the stop-head kernel
         dev, N = env.device, env.num_envs
         self.window = env.cfg.lstm_window
         self.buffer = PPOBuffer(horizon, N, dev, with_info=with_info, with_stop=stop_head is not None,
@@ -73,6 +77,8 @@ class RolloutEngine:
                                         torch.cuda.current_stream(env.device).cuda_stream)
             _lib.check(rc, "plume_rollout")
             self.launches += 1
+            if self.after_loop is not None:
+                self.after_loop(self.buffer, T)
             if defer:
                 b = self.buffer
                 rc = self.lib.plume_stop_head_segment(C.byref(lp), b.conc_sample.data_ptr(), b.fill_t.data_ptr(),
@@ -80,7 +86,7 @@ class RolloutEngine:
                                                       self.conc_window.data_ptr(), self._window_next.data_ptr(),
                                                       env.cfg.conc_peak, b.stop_prob.data_ptr(),
                                                       b.stop_flag.data_ptr(), b.peak_pred.data_ptr(),
-                                                      _lib.ptr(b.trend),
+                                                      _lib.ptr(b.trend), self.stop_head_path,
                                                       torch.cuda.current_stream(env.device).cuda_stream)
                 _lib.check(rc, "plume_stop_head_segment")
                 self.conc_window, self._window_next = self._window_next, self.conc_window

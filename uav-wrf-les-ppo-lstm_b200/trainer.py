@@ -6,8 +6,6 @@ One ``train_iteration()`` = one fused rollout segment of ``horizon`` lockstep st
 ``epochs x minibatches`` optimiser steps.  Nothing returns to the host inside an iteration."""
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import _lib
@@ -23,7 +21,8 @@ class PlumeTrainer:
     def __init__(self, num_envs: int = 4096, horizon: int = 256, version: str = "2.1", device="cuda",
                  seed: int = 0, minibatch_size: int | None = None, stop_head: bool = True,
                  rank: int = 0, world_size: int = 1, process_group=None, with_info: bool = False,
-                 with_trend: bool = True, cfg: PlumeConfig | None = None):
+                 with_trend: bool = True, cfg: PlumeConfig | None = None, gradient_exchange: str = "peer",
+                 with_trajectory: bool = False, lstm_hidden: int = 32):
         self.cfg = cfg or config_for(version)
         self.device = torch.device(device)
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
@@ -33,17 +32,25 @@ class PlumeTrainer:
                                  field_mode="procedural", auto_reset=True, env_id_base=rank * num_envs,
                                  config=self.cfg)
         self.model = PPOActorCritic(device=self.device)
-        self.head = PeakAndStopPredictor(device=self.device) if stop_head else None
+        self.head = PeakAndStopPredictor(hidden_dim=lstm_hidden, device=self.device) if stop_head else None
         self.engine = RolloutEngine(self.env, self.model, self.head, horizon=horizon, with_info=with_info,
-                                    with_trend=with_trend and stop_head)
+                                    with_trend=with_trend and stop_head, with_trajectory=with_trajectory)
         self.optimizer = FusedAdam(self.model, lr=self.cfg.learning_rate, max_grad_norm=self.cfg.max_grad_norm)
-        # multi-GPU: gradient all-reduce fused with clip + Adam over NVLink peer memory (PLUME_COMM=nccl keeps
-        # the torch.distributed all-reduce)
+        # multi-GPU, gradient_exchange="peer" (default): every exchange step of the iteration -- gradient all-reduce
+        # fused with clip + Adam, the advantage statistics, the curriculum's flag codes -- goes over NVLink peer
+        # memory (csrc/comm_kernels.cu), no host-launched collective.  "nccl" keeps torch.distributed for all three.
+        if gradient_exchange not in ("peer", "nccl"):
+            raise ValueError("gradient_exchange must be 'peer' or 'nccl'")
         self.comm = None
-        if process_group is not None and world_size > 1 and os.environ.get("PLUME_COMM", "peer") != "nccl":
+        if process_group is not None and world_size > 1 and gradient_exchange == "peer":
             from .dist import PeerComm
-            self.comm = PeerComm(process_group, _lib.MLP_PARAMS, self.device)
+            self.comm = PeerComm(process_group, _lib.MLP_PARAMS, self.device, code_bytes=num_envs * horizon)
             self.optimizer.attach_comm(self.comm)
+            # the flag codes are published on a side stream right after the lockstep kernel, under the stop-head kernel
+            self._code_stream = torch.cuda.Stream(device=self.device)
+            self._loop_done = torch.cuda.Event()
+            self._codes_done = torch.cuda.Event()
+            self.engine.after_loop = self._publish_codes
         self.curriculum = PPOTrainer(self.env, self.model, self.optimizer, cfg=self.cfg)
         self.minibatch_size = int(minibatch_size or (num_envs * horizon) // 4)
         self.workspace = UpdateWorkspace(self.device, min(self.minibatch_size, num_envs * horizon))
@@ -75,13 +82,30 @@ class PlumeTrainer:
             self._perm_done.record(self._perm_stream)
         return out
 
+    def _publish_codes(self, buf, T: int) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        self._loop_done.record(cur)
+        self._code_stream.wait_event(self._loop_done)
+        self.comm.publish_codes(buf.flag_code[:T], stream=self._code_stream.cuda_stream)
+        self._codes_done.record(self._code_stream)
+
+    def check(self) -> None:
+        """Raises if an exchange kernel of the PREVIOUS iteration timed out (that step was not applied)."""
+        if self.comm is not None:
+            self.comm.check_async_end()
+
     def train_iteration(self, check_nan: bool = False):
+        self.check()                               # waits for the previous iteration's error word, not for this one
         buf = self.engine.collect()
         perms = None
         if self._perm_stream is not None:          # launched after the rollout, so its CTAs are placed first
             with torch.cuda.device(self.device):
                 perms = self._permutations_async()
-        self.curriculum.update_from_rollout(buf, self.process_group)
+        if self.comm is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._codes_done)
+            self.curriculum.update_from_rollout(buf, self.process_group, comm=self.comm, codes_published=True)
+        else:
+            self.curriculum.update_from_rollout(buf, self.process_group)
         if perms is not None:
             torch.cuda.current_stream(self.device).wait_event(self._perm_done)
         self.last_losses = update_model(buf, self.model, self.optimizer, cfg=self.cfg,
@@ -90,6 +114,8 @@ class PlumeTrainer:
                                         check_nan=check_nan)
         if perms is not None:
             self._perm_free.record(torch.cuda.current_stream(self.device))
+        if self.comm is not None:
+            self.comm.check_async_begin()
         self.iteration += 1
         return self.last_losses
 

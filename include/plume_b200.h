@@ -270,6 +270,8 @@ typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major u
     /* trajectory logging in the training_data.nc layout (train_ppo2.0.py:166-170,207-233), optional: */
     float* pos_out;        /* [T][N][2] agent_pos after the step, before a reset */
     float* src_out;        /* [T][N][2] source_pos of the episode, written at its last transition only */
+    float* conc_out;       /* [T][N] conc_field[int(x), int(y)] at the position after the step, as float32: what the
+                            * reference driver logs per step (train_ppo2.0.py:167-173); may be NULL */
     uint8_t* flag_code;    /* [T][N] bit 0 = done, bit 1 = reached: what the curriculum (and its multi-GPU
                             * all-gather, 1 B per transition) consumes; may be NULL */
 } plume_rollout_buffers;
@@ -471,6 +473,39 @@ int plume_curriculum_update_packed(const uint8_t* flag_code, int32_t horizon, in
                                    double* state, double* curriculum, double initial_radius, double min_radius,
                                    double radius_decay, double success_threshold, int32_t window,
                                    double decay_factor, double* window_radius_out, void* stream);
+
+/* ---- N2: trajectory / per-episode logging (training_data.nc + training_results.csv layouts) ------------------
+ * NetCDFWriter.write_episode_data (PPOV2.1/model.py:351-419) and the per-episode statistics of
+ * train_ppo2.0.py:128-134,140-180,194-199,236-248, assembled on the device from one [T][N] rollout segment.
+ * Episodes are appended in canonical order (step-major, then env id); an episode that spans segments is kept in
+ * the env's carry row until it closes.  Tables (DEVICE, caller-owned; x / y / conc NaN-filled once by the caller):
+ * E = max_episodes, S = max_steps. */
+typedef struct plume_traj_log {
+    int32_t max_episodes, max_steps, n_envs, reserved;
+    float* x;               /* [E][S] agent x after each step */
+    float* y;
+    float* conc;            /* [E][S] conc_field[int(x), int(y)] after each step */
+    int32_t* steps;         /* [E] episode length */
+    float* source;          /* [E][2] */
+    uint8_t* success;       /* [E] trajectory[-1]['reached'] */
+    double* radius;         /* [E] trainer.current_radius when the episode ended ('Current_Radius') */
+    double* sums;           /* [E][6] total reward, then the five info components, summed in time order */
+    float* final_conc;      /* [E] 'Final_Conc': conc at the final cell if reached, else 0 */
+    float* c_x;             /* [N][S] carry rows of the open episode of every env */
+    float* c_y;
+    float* c_conc;
+    double* c_sums;         /* [N][6] */
+    int32_t* c_len;         /* [N] steps of the open episode so far */
+    int32_t* count;         /* [1] episodes logged so far (clamped to E) */
+} plume_traj_log;
+int64_t plume_trajectory_workspace_bytes(int32_t horizon, int32_t n_envs);
+/* buf: dones, reached, rewards, info (may be NULL), pos_out, src_out, conc_out of the segment.  comm (may be NULL):
+ * with several ranks, the communicator whose flag codes of this segment are published -- the global episode ordinal
+ * (for the radius lookup) then counts the other ranks' episodes too.  window / window_radius: the curriculum window
+ * length and the array plume_curriculum_update_packed / _peer wrote for THIS segment (NULL: radius_fallback). */
+int plume_trajectory_log(const plume_traj_log* log, const plume_rollout_buffers* buf, int32_t horizon, void* comm,
+                         int32_t window, const double* window_radius, double radius_fallback, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

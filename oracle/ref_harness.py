@@ -229,3 +229,52 @@ class reference_modules:
             else:
                 sys.modules.pop(k, None)
         return False
+
+
+class _MemVariable:
+    """One variable of ``MemDataset``: a numpy array with item assignment and free attributes."""
+
+    def __init__(self, dtype, shape, fill_value):
+        self.data = np.full(shape, fill_value if fill_value is not None else 0, dtype=dtype)
+
+    def __setitem__(self, key, value):
+        self.data[key] = value
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+
+class MemDataset:
+    """Writable in-memory stand-in for ``netCDF4.Dataset`` (absent in this image): exactly what
+    ``NetCDFWriter`` (PPOV2.1/model.py:351-422) calls -- createDimension, createVariable(name, dtype, dims,
+    fill_value=, zlib=), attribute assignment, close."""
+
+    def __init__(self, filename=None, mode="w", format=None):
+        self.dimensions, self.variables = {}, {}
+
+    def createDimension(self, name, size):
+        self.dimensions[name] = size
+
+    def createVariable(self, name, dtype, dims, fill_value=None, zlib=False):
+        var = _MemVariable(dtype, tuple(self.dimensions[d] for d in dims), fill_value)
+        self.variables[name] = var
+        return var
+
+    def close(self):
+        pass
+
+
+def run_reference_lines(relpath: str, first: str, last: str, namespace: dict) -> dict:
+    """Executes a block of an UNMODIFIED reference script in ``namespace``: the lines from the first one containing
+    ``first`` to the first later one containing ``last`` (inclusive), dedented.  The reference's older drivers keep
+    their GAE loops inline in ``train_ppo()`` (PPOV1.1/train_ppo1.0.py:72-89, PPOV1.0/ppo0.0.py:337-353,
+    PPOV1.2's driver :369-382), so running them means running those source lines; the text is read from
+    ``/root/reference`` at test time and never stored in this repository."""
+    import textwrap
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    with open(path, encoding="utf-8") as f:
+        lines = f.read().splitlines()
+    start = next(i for i, l in enumerate(lines) if first in l)
+    end = next(i for i in range(start, len(lines)) if last in lines[i])
+    exec(compile(textwrap.dedent("\n".join(lines[start:end + 1])), path, "exec"), namespace)
+    return namespace

@@ -33,3 +33,16 @@ def golden_oracle_env(g):
     env.reset_env(0, u_src, z_field, u_field)
     env.current_radius[:] = float(g["radius"])
     return cfg, env, z_steps
+
+
+def golden_update_inputs(g):
+    """Rebuilds what oracle/make_golden.py::update_trace drew from ``RandomState(seed)`` for a compact update
+    fixture (states, actions, rewards, dones -- in exactly that order); values / log-probs / permutations / the
+    parameters before and after come from the fixture itself."""
+    m = int(g["m"])
+    rng = np.random.RandomState(int(g["seed"]))
+    states = rng.rand(m, 6).astype(np.float32)
+    actions = rng.randint(0, 5, m).astype(np.int64)
+    rewards = rng.randn(m).astype(np.float32)
+    dones = (rng.rand(m) < 0.04).astype(np.float32)
+    return states, actions, rewards, dones

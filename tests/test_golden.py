@@ -6,7 +6,7 @@ import torch
 
 from oracle import plume_oracle as po
 from oracle import ppo_oracle as pp
-from tests.helpers import INFO_KEYS, golden_oracle_env, load_golden
+from tests.helpers import INFO_KEYS, golden_oracle_env, golden_update_inputs, load_golden
 
 ENV_FIXTURES = ["env_v21_s11.npz", "env_v21_s12.npz", "env_v20_s21.npz", "env_v11_s31.npz"]
 
@@ -42,6 +42,26 @@ def test_update_golden():
     pp.ppo_update(model, opt, torch.from_numpy(g["states"]), torch.from_numpy(g["actions"]),
                   torch.from_numpy(g["rewards"]), torch.from_numpy(g["values"]), torch.from_numpy(g["log_probs"]),
                   torch.from_numpy(g["dones"]), cfg, perms=list(g["perms"]))
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), g["final." + k]), k
+
+
+def test_update_large_minibatch_golden():
+    """The reference's _update_model with BATCH_SIZE = 2048 on 8192 transitions (the shape class the tcgen05
+    gradient kernel handles): the oracle reproduces the reference's parameters bit for bit."""
+    import dataclasses
+    g = load_golden("update_large_s6.npz")
+    cfg = dataclasses.replace(po.config_for("2.1"), batch_size=int(g["batch_size"]))
+    states, actions, rewards, dones = golden_update_inputs(g)
+    model = pp.OracleActorCritic()
+    model.load_state_dict({k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init.")})
+    with torch.no_grad():
+        _, values = model(torch.from_numpy(states))
+    assert np.array_equal(values.squeeze(-1).numpy(), g["values"])           # the regenerated inputs are the fixture's
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.learning_rate)
+    pp.ppo_update(model, opt, torch.from_numpy(states), torch.from_numpy(actions), torch.from_numpy(rewards),
+                  torch.from_numpy(g["values"]), torch.from_numpy(g["log_probs"]), torch.from_numpy(dones), cfg,
+                  perms=list(g["perms"].astype(np.int64)))
     for k, v in model.state_dict().items():
         assert np.array_equal(v.numpy(), g["final." + k]), k
 

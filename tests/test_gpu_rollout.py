@@ -213,6 +213,73 @@ def test_forced_actions_noise_and_stop_termination():
     assert torch.equal(g.actions.reshape(-1).long(), p.argmax(-1))
 
 
+def test_baseline_shape_rollout_sample_through_oracle():
+    """BASELINE shape (4096 envs x 256 steps, radius 50, unscaled actor): 64 envs sampled across the tiles are
+    replayed through the oracle on the kernel's own actions and draws -- flags and indices bit-exact, rewards /
+    observations within fp32 rel 1e-5 -- and the policy outputs of ALL 1 M transitions are checked against the
+    oracle MLP."""
+    N, T = 4096, 256
+    m, env, model, head, eng = _setup(N, T, seed=5, radius=None, actor_gain=1.0)
+    cfg = po.config_for("2.1")
+    rng = np.random.default_rng(0)
+    ids = np.sort(rng.choice(N, size=64, replace=False)).astype(np.int64)
+    ids[0], ids[-1] = 0, N - 1                      # first and last env of the grid
+    src0 = env.source_pos.cpu().numpy().copy()
+    ep0 = env.episode_idx.cpu().numpy().copy()
+    noise = torch.zeros(T, N, 2, dtype=torch.float64, device="cuda")
+    buf = eng.collect(noise_out=noise)
+    eng.check_nan()
+    obs = buf.obs.cpu().numpy()
+    acts = buf.actions.cpu().numpy()
+    rew = buf.rewards.cpu().numpy()
+    dones = buf.dones.cpu().numpy() != 0
+    reached = buf.reached.cpu().numpy() != 0
+    epi = buf.episode_idx.cpu().numpy()
+    info = buf.info.cpu().numpy()
+    zs = noise.cpu().numpy()
+
+    frozen = m.VecMethaneEnv(N, version="2.1", seed=5, field_mode="procedural")
+    assert np.array_equal(frozen.episode_idx.cpu().numpy(), ep0)
+
+    def noise_cb(idx, x, y):
+        z, u = frozen.field_noise_at(ids[np.asarray(idx)].astype(np.int32), np.asarray(x, dtype=np.int32),
+                                     np.asarray(y, dtype=np.int32))
+        return z.cpu().numpy(), u.cpu().numpy()
+
+    n = len(ids)
+    ora = po.OracleVecEnv(cfg, n, fields=po.CellNoiseFields(cfg, n, noise_cb))
+    for i in range(n):
+        ora.set_source(i, src0[ids[i]])
+    alive = np.ones(n, dtype=bool)
+    assert np.allclose(ora.observe(), obs[0][ids], rtol=2e-7, atol=1e-9)
+    checked = 0
+    for t in range(T):
+        o, r, d, inf = ora.step(acts[t][ids], zs[t][ids])
+        assert np.array_equal(d[alive], dones[t][ids][alive]), t
+        assert np.array_equal(inf["reached"][alive], reached[t][ids][alive]), t
+        assert np.allclose(r[alive], rew[t][ids][alive], rtol=1e-5, atol=1e-6), t
+        for k, key in enumerate(("concentration_reward", "explore_reward", "move_penalty", "tke_penalty",
+                                 "boundary_penalty")):
+            assert np.allclose(np.asarray(inf[key], dtype=np.float32)[alive], info[t, k][ids][alive], rtol=1e-5,
+                               atol=1e-7), (t, key)
+        assert np.all(epi[t][ids][alive] == ep0[ids][alive])
+        checked += int(alive.sum())
+        if t + 1 < T:
+            cont = alive & ~d
+            assert np.array_equal(o[cont][:, [0, 1, 4, 5]], obs[t + 1][ids][cont][:, [0, 1, 4, 5]]), t
+            assert np.allclose(o[cont], obs[t + 1][ids][cont], rtol=2e-7, atol=1e-9), t
+        alive &= ~d
+    assert checked > 0.6 * n * T and 0 < (~alive).sum() < n        # most transitions replayed; some episodes ended
+
+    ora_m = pp.OracleActorCritic()
+    ora_m.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    with torch.no_grad():
+        p, v = ora_m(torch.from_numpy(obs.reshape(-1, 6)))
+    lp = pp.categorical_log_prob(p, torch.from_numpy(acts.reshape(-1)).long())
+    assert torch.allclose(buf.values.cpu().reshape(-1), v.squeeze(-1), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(buf.log_probs.cpu().reshape(-1), lp, rtol=1e-5, atol=2e-6)
+
+
 def test_full_size_invariants():
     """BASELINE size (4096 envs): size-independent properties of the rollout."""
     N, T = 4096, 64

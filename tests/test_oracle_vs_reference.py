@@ -9,7 +9,8 @@ import torch
 
 from oracle import plume_oracle as po
 from oracle import ppo_oracle as pp
-from oracle.ref_harness import QueueFeed, load_reference, make_reference_env, reference_available
+from oracle.ref_harness import (QueueFeed, load_reference, make_reference_env, reference_available,
+                                run_reference_lines)
 
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
 INFO_KEYS = ("concentration_reward", "explore_reward", "move_penalty", "tke_penalty", "boundary_penalty")
@@ -241,3 +242,43 @@ def test_trend_label():
         src = rng.random(2) * 400 + 50
         want = ref.model.calculate_dynamic_label({"concentrations": conc, "positions": pos, "source_pos": src})
         assert pp.trend_label(conc, pos[-1], src)[0] == want
+
+
+def _gae_case(seed, T=257):
+    rng = np.random.RandomState(seed)
+    rewards = torch.from_numpy(rng.randn(T).astype(np.float32) * 3)
+    values = torch.from_numpy(rng.randn(T).astype(np.float32))
+    dones = torch.from_numpy((rng.rand(T) < 0.08).astype(np.float32))
+    dones[-1] = float(seed % 2)
+    next_value = torch.from_numpy(rng.randn(1).astype(np.float32))
+    return rewards, values, dones, next_value
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("script", ["PPOV1.1/train_ppo1.0.py", "PPOV1.0/ppo0.0.py", "PPOV1.1/train_ppo_gail.py"])
+def test_older_gae_loop_bootstrap_bit_exact(script, seed):
+    """P5' bootstrap variant: the reference's own inline loop (its source lines, executed) == oracle, bit for bit."""
+    import os
+    from oracle.ref_harness import REFERENCE_ROOT
+    if not os.path.exists(os.path.join(REFERENCE_ROOT, script)):
+        pytest.skip("script not in this reference tree")
+    rewards, values, dones, next_value = _gae_case(seed)
+    ns = dict(torch=torch, rewards=rewards.clone(), values=values.clone(), dones=dones.clone(),
+              next_value=next_value.clone(), GAMMA=0.99, LAMBDA=0.95)
+    try:
+        run_reference_lines(script, "advantages = torch.zeros_like(rewards)", "advantages.std() + 1e-8", ns)
+    except StopIteration:
+        pytest.skip("this script has no such loop")
+    adv, ret = pp.gae_bootstrap_v10(rewards, values, dones, next_value, 0.99, 0.95)
+    assert torch.equal(adv, ns["advantages"]) and torch.equal(ret, ns["returns"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_older_gae_loop_v12_bit_exact(seed):
+    """P5' PPOV1.2 variant, same method."""
+    rewards, values, dones, _ = _gae_case(seed)
+    ns = dict(torch=torch, rewards=rewards.clone(), values=values.clone(), dones=dones.clone(), GAMMA=0.99,
+              LAMBDA=0.95)
+    run_reference_lines("PPOV1.2/ppo注释版.py", "advantages = torch.zeros_like(rewards)", "returns = advantages + values", ns)
+    adv, ret = pp.gae_v12(rewards, values, dones, 0.99, 0.95)
+    assert torch.equal(adv, ns["advantages"]) and torch.equal(ret, ns["returns"])

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplume_b200.so")
 
 OBS_DIM, NUM_ACTIONS, INFO_DIM, VISIT_STRIDE = 6, 5, 5, 104
+INFO_KEYS = ("concentration_reward", "explore_reward", "move_penalty", "tke_penalty", "boundary_penalty")
 FLAG_AUTO_RESET, FLAG_GREEDY, FLAG_STOP_TERMINATES, FLAG_DEFER_STOP_HEAD, FLAG_FAST_REWARD = 1, 2, 4, 8, 16
 
 # flat MLP parameter layout (include/plume_b200.h)
@@ -62,12 +63,19 @@ class RolloutBuffers(C.Structure):
     _fields_ = [(n, _vp) for n in ("obs", "actions", "rewards", "values", "log_probs", "dones", "reached",
                                    "stop_prob", "stop_flag", "peak_pred", "trend", "info", "episode_idx",
                                    "forced_actions", "step_noise", "noise_out", "conc_window", "window_fill",
-                                   "last_obs", "conc_sample", "fill_t", "src_dist", "pos_out", "src_out", "flag_code")]
+                                   "last_obs", "conc_sample", "fill_t", "src_dist", "pos_out", "src_out", "conc_out",
+                                   "flag_code")]
 
 
 class PpoBatch(C.Structure):
     _fields_ = [("total", C.c_int64), ("obs", _vp), ("actions", _vp), ("old_log_probs", _vp),
                 ("advantages", _vp), ("returns", _vp), ("old_values", _vp), ("packed", _vp)]
+
+
+class TrajLog(C.Structure):
+    _fields_ = [("max_episodes", C.c_int32), ("max_steps", C.c_int32), ("n_envs", C.c_int32), ("reserved", C.c_int32)] + \
+               [(n, _vp) for n in ("x", "y", "conc", "steps", "source", "success", "radius", "sums", "final_conc",
+                                   "c_x", "c_y", "c_conc", "c_sums", "c_len", "count")]
 
 
 GAE_VARIANTS = {"quirk": 0, "bootstrap": 1, "v12": 2}
@@ -144,6 +152,9 @@ _SIGNATURES = {
     "plume_tc_gemm_f16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "plume_curriculum_update": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double,
                                           C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
+    "plume_trajectory_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "plume_trajectory_log": (C.c_int, [_P(TrajLog), _P(RolloutBuffers), C.c_int32, _vp, C.c_int32, _vp, C.c_double,
+                                       _vp, C.c_int64, _vp]),
     "plume_curriculum_update_packed": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_double,
                                                  C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, _vp, _vp]),
 }

@@ -41,6 +41,7 @@ class PPOBuffer:
         # trajectory logging (trajectory_log.TrajectoryLogger): post-step positions, source at the episode's last step
         self.pos_out = z(torch.float32, T, N, 2) if with_trajectory else None
         self.src_out = z(torch.float32, T, N, 2) if with_trajectory else None
+        self.conc_out = z(torch.float32, T, N) if with_trajectory else None
         self.advantages = z(torch.float32, T, N)
         self.returns = z(torch.float32, T, N)
         self.filled = 0          # rows written
@@ -52,10 +53,14 @@ class PPOBuffer:
         self.flag_code_valid = False
         self.reached_stored = True
 
-    def store(self, state, action, reward, value, log_prob, done, reached=None) -> None:
+    def store(self, state, action, reward, value, log_prob, done, reached=None, info=None, pos=None, conc=None,
+              src=None) -> None:
         """Appends one lockstep row (each argument ``[N]``-shaped, ``state`` ``[N,6]``).  ``reached`` (optional, the
         env's ``info["reached"]``) feeds the batched curriculum (``PPOTrainer.update_from_rollout``); the
-        reference's six-argument call leaves it at "not reached" and drives ``PPOTrainer.update(success)`` itself."""
+        reference's six-argument call leaves it at "not reached" and drives ``PPOTrainer.update(success)`` itself.
+        ``info`` (the step's info dict), ``pos`` (``env.agent_pos``), ``conc`` (``env.conc_field[x, y]``) and ``src``
+        (``env.source_pos``) are what the reference driver logs per step (train_ppo2.0.py:166-180); a buffer built
+        with ``with_info`` / ``with_trajectory`` keeps them for ``TrajectoryLogger.consume``."""
         t = self.filled
         if t >= self.horizon:
             raise IndexError("PPOBuffer is full: call clear() after update_model()")
@@ -71,6 +76,16 @@ class PPOBuffer:
             self.reached_stored = False
         else:
             self.reached[t] = torch.as_tensor(reached, device=dev).to(torch.uint8).reshape(self.num_envs)
+        N = self.num_envs
+        if info is not None and self.info is not None:
+            for k, key in enumerate(_lib.INFO_KEYS):
+                self.info[t, k] = torch.as_tensor(info[key], device=dev).to(torch.float32).reshape(N)
+        if pos is not None and self.pos_out is not None:
+            self.pos_out[t] = torch.as_tensor(pos, device=dev).to(torch.float32).reshape(N, 2)
+        if conc is not None and self.conc_out is not None:
+            self.conc_out[t] = torch.as_tensor(conc, device=dev).to(torch.float32).reshape(N)
+        if src is not None and self.src_out is not None:
+            self.src_out[t] = torch.as_tensor(src, device=dev).to(torch.float32).reshape(N, 2)
         self.flag_code_valid = False
         self.filled = t + 1
 
@@ -99,4 +114,4 @@ class PPOBuffer:
                                    p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
                                    p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
                                    p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist),
-                                   p(self.pos_out), p(self.src_out), p(self.flag_code))
+                                   p(self.pos_out), p(self.src_out), p(self.conc_out), p(self.flag_code))

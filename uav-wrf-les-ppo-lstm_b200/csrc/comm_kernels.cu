@@ -242,6 +242,20 @@ __global__ void __launch_bounds__(32) comm_wait_codes_kernel(CommPtrs ptrs, int 
     signal_and_wait(ptrs, world, rank, CommLayout::cflags, epoch, false, err);
 }
 
+int comm_code_sources(void* comm, int64_t bytes, CodeSrc* out, int* world, int* rank) {
+    Comm* c = static_cast<Comm*>(comm);
+    if (c->code_epoch == 0 || c->code_bytes_published != bytes)
+        return fail("the communicator has not published this segment's flag codes (%lld B wanted, %lld B published)",
+                    (long long)bytes, (long long)c->code_bytes_published);
+    for (int r = 0; r < kCommMaxWorld; ++r)
+        out->base[r] = r < c->world ? reinterpret_cast<const uint8_t*>(c->peer[r] + c->codes_off()) +
+                                          (size_t)(c->code_epoch & 1u) * c->code_pad
+                                    : nullptr;
+    *world = c->world;
+    *rank = c->rank;
+    return 0;
+}
+
 static CommPtrs comm_ptrs(const Comm* c) {
     CommPtrs ptrs;
     for (int r = 0; r < kCommMaxWorld; ++r) ptrs.peer[r] = c->peer[r];
@@ -410,10 +424,8 @@ extern "C" int plume_curriculum_update_peer(void* comm, int32_t horizon, int32_t
     comm_wait_codes_kernel<<<1, 32, 0, as_stream(stream)>>>(comm_ptrs(c), c->world, c->rank, c->code_epoch);
     PLUME_LAUNCH_CHECK();
     CodeSrc src;
-    for (int r = 0; r < kCommMaxWorld; ++r)
-        src.base[r] = r < c->world ? reinterpret_cast<const uint8_t*>(c->peer[r] + c->codes_off()) +
-                                         (size_t)(c->code_epoch & 1u) * c->code_pad
-                                   : nullptr;
+    int world = 0, rank = 0;
+    if (comm_code_sources(comm, (int64_t)horizon * n_envs, &src, &world, &rank) != 0) return -1;
     return launch_curriculum_packed(src, horizon, n_envs, c->world, state, curriculum, initial_radius, min_radius,
                                     radius_decay, success_threshold, window, decay_factor, window_radius_out,
                                     reinterpret_cast<const uint32_t*>(c->local + CommLayout::grid) + 2,

@@ -26,4 +26,8 @@ int launch_curriculum_packed(const CodeSrc& src, int horizon, int n_envs, int wo
                              int window, double decay_factor, double* window_radius_out, const uint32_t* comm_error,
                              cudaStream_t stream);
 
+// the published flag-code buffers of all ranks (after plume_comm_publish_codes + the wait of
+// plume_curriculum_update_peer for the same segment of `bytes` bytes); 0 on success
+int comm_code_sources(void* comm, int64_t bytes, CodeSrc* out, int* world, int* rank);
+
 }  // namespace plume

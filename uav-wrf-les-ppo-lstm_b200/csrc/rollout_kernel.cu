@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
                 if (a.buf.episode_idx) a.buf.episode_idx[i] = (int32_t)ep_of_transition;
                 if (a.buf.pos_out) reinterpret_cast<float2*>(a.buf.pos_out)[i] = make_float2(e.px, e.py);
                 if (a.buf.src_out && done) reinterpret_cast<float2*>(a.buf.src_out)[i] = make_float2((float)e.sx, (float)e.sy);
+                if (a.buf.conc_out) a.buf.conc_out[i] = (float)cell_conc;       // train_ppo2.0.py:167-173
                 if (a.buf.info) {
                     float* inf = a.buf.info + (size_t)t * 5 * N + env;
                     inf[0] = r.conc_reward;

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from .config import FIELD_F32, FIELD_F64, FIELD_MODES, FIELD_PROCEDURAL, PlumeConfig, config_for
 
-INFO_KEYS = ("concentration_reward", "explore_reward", "move_penalty", "tke_penalty", "boundary_penalty")
+INFO_KEYS = _lib.INFO_KEYS
 
 
 def host_tables(cfg):
@@ -312,17 +312,27 @@ class MethaneEnv(VecMethaneEnv):
 
     def __init__(self, device="cuda", version: str = "2.1", seed: int = 0, field_mode: str = "f64", **kw):
         self.trajectory: list = []
+        self._fields_host = None          # (conc, tke) numpy arrays of the CURRENT episode, downloaded on first use
         super().__init__(1, device=device, version=version, seed=seed, field_mode=field_mode, **kw)
 
     def reset(self, *a, **k):
         self.trajectory = []
+        self._fields_host = None
         return super().reset(*a, **k)[0].cpu().numpy()
+
+    def set_source(self, *a, **k):
+        self._fields_host = None
+        return super().set_source(*a, **k)
 
     def _get_obs(self):
         return self.observe()[0].cpu().numpy()
 
-    def step(self, action):
-        obs, reward, done, info = super().step(torch.tensor([int(action)]))
+    def step(self, action, step_noise=None):
+        """``step(action)`` as in the reference; ``step_noise`` (float64 [2]) optionally injects the ``randn(2)`` of
+        environment.py:108 (parity tests replay the reference's draws)."""
+        if step_noise is not None:
+            step_noise = np.asarray(step_noise, dtype=np.float64).reshape(1, 2)
+        obs, reward, done, info = super().step(torch.tensor([int(action)]), step_noise=step_noise)
         torch.cuda.current_stream(self.device).synchronize()
         o = obs[0].cpu().numpy()
         out_info = {k: float(info[k][0].item()) for k in INFO_KEYS}
@@ -342,15 +352,21 @@ class MethaneEnv(VecMethaneEnv):
     def step_count(self):
         return int(self.step_count_t[0].item())
 
+    def _host_fields(self):
+        # the reference driver indexes env.conc_field every step (train_ppo2.0.py:167-170): one download per
+        # episode, not per access (the plume only changes in reset())
+        if self._fields_host is None:
+            conc, tke = self.materialise_fields()
+            self._fields_host = (conc[0].cpu().numpy(), tke[0].cpu().numpy())
+        return self._fields_host
+
     @property
     def conc_field(self):
-        conc, _ = self.materialise_fields()
-        return conc[0].cpu().numpy()
+        return self._host_fields()[0]
 
     @property
     def tke_field(self):
-        _, tke = self.materialise_fields()
-        return tke[0].cpu().numpy()
+        return self._host_fields()[1]
 
     @property
     def gaussian_params(self):

@@ -1,4 +1,4 @@
-"""Philox4x32-10 counter-based generator in numpy -- TEST INFRASTRUCTURE ONLY.
+"""Philox4x32 counter-based generator (10 rounds; 7 for the field stream) in numpy -- TEST INFRASTRUCTURE ONLY.
 
 The reference draws from unseeded global generators (numpy MT19937:
 PPOV2.1/environment.py:44,58,60,108; torch: train_ppo2.0.py:43,162), which cannot be
@@ -10,14 +10,18 @@ sharded over GPUs.  This file restates the published algorithm so that the integ
 of the device generator can be checked bit-exactly (known-answer vectors of Random123's
 ``kat_vectors`` are in ``tests/test_philox.py``).
 
-Stream layout (must match ``csrc/plume_rng.cuh``):
+Stream layout (must match ``csrc/plume_core.h``):
 
 =========  =====================================================================
 tag        counter = (c0, c1, c2, c3)
 =========  =====================================================================
 TAG_SRC=1  (0, episode, env, 1): words 0,1 -> u_x (53-bit double), words 2,3 -> u_y
-TAG_FIELD=2 (cell>>1, episode, env, 2): Box-Muller(words 0,1) -> (z_even, z_odd) cells,
-           words 2,3 -> (u_even, u_odd); cell = x*G + y
+TAG_FIELD=2 (cell>>2, episode, env, 2), Philox4x32-7 (FIELD_ROUNDS): one call per FOUR cells, cell = x*G + y;
+           word 0: [31..12] radius uniform (m+1) 2^-20 of cells 4q, 4q+1, [11..0] u = m 2^-12 of cell 4q
+           word 1: [31..12] radius uniform of cells 4q+2, 4q+3,          [11..0] u of cell 4q+1
+           word 2: [15..0] angle uniform m 2^-16 of the first pair, [31..16] of the second pair
+           word 3: [11..0] u of cell 4q+2, [23..12] u of cell 4q+3
+           Box-Muller per pair: z_even = r cos(2 pi a), z_odd = r sin(2 pi a)
 TAG_STEP=3 (step, episode, env, 3): Box-Muller(words 0,1) -> the two randn of one step;
            step = step_count BEFORE the step (0 for the first step of an episode)
 TAG_ACT=4  (step, episode, env, 4): word 0 -> uniform for the inverse-CDF action draw (same step index)
@@ -38,12 +42,19 @@ MASK = np.uint64(0xFFFFFFFF)
 TAG_SRC, TAG_FIELD, TAG_STEP, TAG_ACT, TAG_WIND = 1, 2, 3, 4, 5
 
 
+FIELD_ROUNDS = 7      # the field stream's reduced-round variant (Random123's Crush-resistant minimum); others: 10
+
+
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    return philox4x32(c0, c1, c2, c3, k0, k1, 10)
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds: int = 10):
     """Vectorised over equally shaped integer arrays; returns 4 uint32 arrays."""
     c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in np.broadcast_arrays(c0, c1, c2, c3))
     k0 = int(k0) & 0xFFFFFFFF
     k1 = int(k1) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
@@ -92,17 +103,25 @@ def source_uniforms(seed: int, env, episode):
 
 
 def field_words(seed: int, env, episode, cell):
+    """The four words of the quad a cell belongs to."""
     k0, k1 = seed_key(seed)
-    return philox4x32_10(np.asarray(cell) >> 1, episode, env, TAG_FIELD, k0, k1)
+    return philox4x32(np.asarray(cell) >> 2, episode, env, TAG_FIELD, k0, k1, FIELD_ROUNDS)
 
 
 def field_noise64(seed: int, env, episode, cell):
     """(z, u) of a cell in float64 Box-Muller precision; u is exact."""
     cell = np.asarray(cell)
-    r = field_words(seed, env, episode, cell)
-    z0, z1 = box_muller64(r[0], r[1])
-    odd = (cell & 1).astype(bool)
-    return np.where(odd, z1, z0), np.where(odd, uniform24(r[3]), uniform24(r[2]))
+    r = [np.asarray(w, dtype=np.uint32) for w in field_words(seed, env, episode, cell)]
+    k = cell & 3
+    second = k >= 2
+    radius = np.where(second, r[1] >> np.uint32(12), r[0] >> np.uint32(12)).astype(np.float64)
+    angle = np.where(second, r[2] >> np.uint32(16), r[2] & np.uint32(0xFFFF)).astype(np.float64)
+    u1 = (radius + 1.0) * 2.0 ** -20
+    u2 = angle * 2.0 ** -16
+    rad = np.sqrt(-2.0 * np.log(u1))
+    z = np.where((k & 1).astype(bool), rad * np.sin(2 * np.pi * u2), rad * np.cos(2 * np.pi * u2))
+    m = np.select([k == 0, k == 1, k == 2], [r[0], r[1], r[3]], r[3] >> np.uint32(12)) & np.uint32(0xFFF)
+    return z, (m.astype(np.float32) * np.float32(2.0 ** -12))
 
 
 def step_noise64(seed: int, env, episode, step):

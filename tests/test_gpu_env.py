@@ -89,7 +89,7 @@ def test_philox_streams_on_device():
     for j, e in enumerate([0, 7, 39]):
         z64, u64 = ph.field_noise64(seed, base + e, 1, cells)
         assert np.array_equal(u[j].reshape(-1), u64.astype(np.float32))
-        assert np.abs(z[j].reshape(-1) - z64).max() < 2e-5
+        assert np.abs(z[j].reshape(-1) - z64).max() < 5e-5      # float32 fast intrinsics vs float64 Box-Muller
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
     # lookups of single cells agree with the dump
     xs = np.array([0, 3, 499, 250], dtype=np.int32)

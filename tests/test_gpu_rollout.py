@@ -341,14 +341,16 @@ def test_deferred_stop_head_equals_in_loop_head(splits, path):
     assert torch.equal(nxt_a, nxt_b)
 
 
-@pytest.mark.parametrize("hidden", [48, 256])
-def test_deferred_stop_head_other_hidden_sizes(hidden):
-    """BASELINE configs[4] sweeps the stop-head hidden size up to 256: sizes other than 32 / 64 run the deferred head
-    on the generic LSTM kernel (weights from L2).  Checked against the torch-CPU LSTM on the windows rebuilt from the
-    segment's samples (also across a segment boundary: the carried ring), trend features against the 32-unit run."""
+@pytest.mark.parametrize("hidden,path", [(48, "auto"), (64, "tensor"), (64, "simt"), (128, "auto"), (256, "auto")])
+def test_deferred_stop_head_other_hidden_sizes(hidden, path):
+    """BASELINE configs[4] sweeps the stop-head hidden size up to 256: 64 has a resident-weight tcgen05 kernel (and the
+    CUDA-core one), the others run on the kernels the library has for them.  Checked against the torch-CPU LSTM
+    (the oracle, bit-pinned to the reference's PeakAndStopPredictor) on the windows rebuilt from the segment's samples
+    (also across a segment boundary: the carried ring), trend features against the 32-unit run.  N = 300 envs: three
+    128-window tiles per step, the last one ragged."""
     import uav_wrf_les_ppo_lstm_b200 as m
     from oracle import ppo_oracle as pp
-    N, splits, W = 40, (30, 34), 20
+    N, splits, W = 300, (30, 34), 20
     torch.manual_seed(hidden)
     env = m.VecMethaneEnv(N, version="2.1", seed=17, field_mode="procedural", auto_reset=True)
     env.curriculum[0] = 25.0
@@ -357,7 +359,7 @@ def test_deferred_stop_head_other_hidden_sizes(hidden):
     head = m.PeakAndStopPredictor(hidden_dim=hidden, device="cuda")
     ora = pp.OraclePeakAndStop(hidden_dim=hidden)
     ora.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
-    eng = m.RolloutEngine(env, model, head, horizon=max(splits), with_trend=True)
+    eng = m.RolloutEngine(env, model, head, horizon=max(splits), with_trend=True, stop_head_path=path)
     # the same rollout with the 32-unit head gives the reference trend features (they do not depend on the head)
     env2 = m.VecMethaneEnv(N, version="2.1", seed=17, field_mode="procedural", auto_reset=True)
     env2.curriculum[0] = 25.0

@@ -92,7 +92,7 @@ def test_trajectory_logger_matches_per_step_replay(tmp_path):
     assert np.all(nc["gaussian_sigma"] == 15.0) and np.all(nc["peak_concentration"] == 100.0)
     radii = rows[:, 10]
     assert len(np.unique(radii)) > 1, "the radius never changed: the per-episode radius lookup is untested"
-    assert (rows[:, 9] > 0).any() and (rows[:, 9] == 0).any()
+    assert (rows[:, 9] > 0).any()          # (Final_Conc = 0.0 of a failed episode: tests/test_gpu_driver_loop.py)
     log.save(str(tmp_path / "training_data_like.npz"), str(tmp_path / "training_results.csv"))
     back = np.load(tmp_path / "training_data_like.npz")
     assert np.array_equal(back["is_source"], nc["is_source"])

@@ -34,3 +34,20 @@ def test_box_muller_moments():
     z = np.concatenate([z0, z1])
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
     assert abs(np.mean(z0 * z1)) < 0.01
+
+
+def test_field_stream_moments_and_layout():
+    """The field stream (one Philox4x32-7 call per four cells): the draws of a whole plume are standard normal /
+    uniform, pairs are uncorrelated, and the four cells of a quad take their bits from the documented places."""
+    cells = np.arange(500 * 500)
+    z, u = ph.field_noise64(99, 5, 2, cells)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01 and np.abs(z).max() < 5.3     # 20-bit radius
+    assert abs(u.mean() - 0.5) < 0.005 and u.min() >= 0.0 and u.max() < 1.0
+    assert abs(np.mean(z[0::2] * z[1::2])) < 0.01 and abs(np.corrcoef(z, u)[0, 1]) < 0.01
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 0.01
+    w = [int(x) for x in ph.field_words(99, 5, 2, 1000)]              # quad 250
+    k0, k1 = ph.seed_key(99)
+    assert tuple(w) == tuple(int(x) for x in ph.philox4x32(250, 2, 5, ph.TAG_FIELD, k0, k1, 7))
+    _, uq = ph.field_noise64(99, 5, 2, np.arange(1000, 1004))
+    want = [(w[0] & 0xFFF), (w[1] & 0xFFF), (w[3] & 0xFFF), ((w[3] >> 12) & 0xFFF)]
+    assert [int(round(float(x) * 4096)) for x in uq] == want

@@ -94,15 +94,8 @@ __global__ void __launch_bounds__(256) generate_fields_kernel(Cfg c, plume_env_s
     const int cell0 = quad * 4;
     const int x = cell0 / c.G, y = cell0 - x * c.G;    // G % 4 == 0: the 4 cells share the row
 
-    const U4 ra = philox4x32_10((uint32_t)(cell0 >> 1), episode, gid, kTagField, c.k0, c.k1);
-    const U4 rb = philox4x32_10((uint32_t)(cell0 >> 1) + 1u, episode, gid, kTagField, c.k0, c.k1);
     float z[4], u[4];
-    box_muller(ra.x, ra.y, z[0], z[1]);
-    box_muller(rb.x, rb.y, z[2], z[3]);
-    u[0] = uniform24(ra.z);
-    u[1] = uniform24(ra.w);
-    u[2] = uniform24(rb.z);
-    u[3] = uniform24(rb.w);
+    field_noise_quad(c, gid, episode, (uint32_t)quad, z, u);
 
     T conc[4], tke[4];
     const double sinx = st.sin_tab[x];
@@ -167,12 +160,8 @@ __global__ void __launch_bounds__(128) generate_fields_f32_kernel(Cfg c, FieldF3
     const float sx = (float)st.src_x[env], sy = (float)st.src_y[env];
     const int cell0 = x * c.G + y0;
 
-    const U4 ra = philox4x32_10((uint32_t)(cell0 >> 1), episode, gid, kTagField, c.k0, c.k1);
-    const U4 rb = philox4x32_10((uint32_t)(cell0 >> 1) + 1u, episode, gid, kTagField, c.k0, c.k1);
-    float z[4];
-    box_muller(ra.x, ra.y, z[0], z[1]);
-    box_muller(rb.x, rb.y, z[2], z[3]);
-    const float u[4] = {uniform24(ra.z), uniform24(ra.w), uniform24(rb.z), uniform24(rb.w)};
+    float z[4], u[4];
+    field_noise_quad(c, gid, episode, (uint32_t)(cell0 >> 2), z, u);      // one Philox4x32-7 call for the four cells
 
     const float ddx = (float)x - sx;
     const float ddx2 = ddx * ddx;
@@ -209,15 +198,11 @@ __global__ void __launch_bounds__(256) dump_noise_kernel(Cfg c, plume_env_state 
     const uint32_t gid = (uint32_t)(st.env_id_base + env);
     const uint32_t episode = (uint32_t)st.episode_idx[env];
     const int cell0 = quad * 4;
-    const U4 ra = philox4x32_10((uint32_t)(cell0 >> 1), episode, gid, kTagField, c.k0, c.k1);
-    const U4 rb = philox4x32_10((uint32_t)(cell0 >> 1) + 1u, episode, gid, kTagField, c.k0, c.k1);
-    float z[4];
-    box_muller(ra.x, ra.y, z[0], z[1]);
-    box_muller(rb.x, rb.y, z[2], z[3]);
+    float z[4], u[4];
+    field_noise_quad(c, gid, episode, (uint32_t)quad, z, u);
     const size_t o2 = (size_t)li * cells + cell0;
     *reinterpret_cast<float4*>(z_out + o2) = make_float4(z[0], z[1], z[2], z[3]);
-    *reinterpret_cast<float4*>(u_out + o2) =
-        make_float4(uniform24(ra.z), uniform24(ra.w), uniform24(rb.z), uniform24(rb.w));
+    *reinterpret_cast<float4*>(u_out + o2) = make_float4(u[0], u[1], u[2], u[3]);
 }
 
 // conc_field[x, y] / tke_field[x, y] of every env at one cell per env (the accessor the evaluators use,

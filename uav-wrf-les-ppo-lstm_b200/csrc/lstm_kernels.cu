@@ -447,9 +447,12 @@ extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const floa
     PLUME_CHECK_ARG(!trend || src_dist, "trend features need src_dist");
     PLUME_CHECK_ARG(window_out != window_in, "window_out must not alias window_in");
     if (horizon <= 0 || n_envs <= 0) return 0;
-    // hidden = 32: gate GEMM on the tensor cores (lstm_tc_kernels.cu); kernel_path = PLUME_KERNEL_SIMT selects the
-    // CUDA-core kernel, whose arithmetic is bit-identical to the in-loop head of plume_rollout
-    if (lstm->hidden == 32 && kernel_path != PLUME_KERNEL_SIMT) {
+    // gate GEMM on the tensor cores where the hidden size has a tcgen05 kernel (lstm_tc_kernels.cu); kernel_path =
+    // PLUME_KERNEL_SIMT selects the CUDA-core kernel, whose arithmetic is bit-identical to the in-loop head of
+    // plume_rollout
+    PLUME_CHECK_ARG(kernel_path != PLUME_KERNEL_TENSOR || stop_head_segment_tc_supports(lstm->hidden),
+                    "no tensor-core stop-head kernel for this hidden size");
+    if (stop_head_segment_tc_supports(lstm->hidden) && kernel_path != PLUME_KERNEL_SIMT) {
         LtArgs t;
         t.conc_sample = conc_sample;
         t.fill_t = fill_t;
@@ -467,7 +470,7 @@ extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const floa
         t.stop_flag = stop_flag;
         t.w_ih = lstm->w_ih; t.w_hh = lstm->w_hh; t.b_ih = lstm->b_ih; t.b_hh = lstm->b_hh;
         t.w_peak = lstm->w_peak; t.b_peak = lstm->b_peak; t.w_stop = lstm->w_stop; t.b_stop = lstm->b_stop;
-        return launch_stop_head_segment_tc(t, as_stream(stream));
+        return launch_stop_head_segment_tc(t, lstm->hidden, as_stream(stream));
     }
     const LstmWeights w{lstm->w_ih, lstm->w_hh, lstm->b_ih, lstm->b_hh, lstm->w_peak, lstm->b_peak, lstm->w_stop,
                         lstm->b_stop};

@@ -158,7 +158,8 @@ struct LtArgs {
     uint8_t* stop_flag;
     const float *w_ih, *w_hh, *b_ih, *b_hh, *w_peak, *b_peak, *w_stop, *b_stop;
 };
-int launch_stop_head_segment_tc(const LtArgs& a, cudaStream_t s);
+bool stop_head_segment_tc_supports(int hidden);
+int launch_stop_head_segment_tc(const LtArgs& a, int hidden, cudaStream_t s);
 
 // ---- P4t trend features (calculate_dynamic_label, PPOV2.1/model.py:113-127) ------------------------
 // m = mean of the last three np.gradient values of the window; dist = ||pos[-1] - src||

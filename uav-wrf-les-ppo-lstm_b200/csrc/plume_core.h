@@ -76,9 +76,10 @@ struct U4 {
     uint32_t x, y, z, w;
 };
 
-PLUME_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+template <int kRounds>
+PLUME_HD U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kRounds; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -90,6 +91,9 @@ PLUME_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
         k1 += kPhiloxW1;
     }
     return U4{c0, c1, c2, c3};
+}
+PLUME_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32<10>(c0, c1, c2, c3, k0, k1);
 }
 
 PLUME_HD float uniform24(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }           // [0,1)
@@ -253,15 +257,62 @@ PLUME_HD void plume_cell(const Cfg& c, double sx, double sy, int x, int y, doubl
     conc = v < 0.0 ? 0.0 : (v > c.conc_peak ? c.conc_peak : v);               // env:62
 }
 
-// the two draws of cell (x,y) of (env, episode) from the Philox field stream
+// ---- the field stream: ONE Philox4x32-7 call per FOUR consecutive cells ------------------------------------------
+// (the plume of an episode is 2 x 250 000 draws per env; K1 was bound by instruction issue with 40 % of its
+// instructions in two Philox4x32-10 calls per four cells -- profiles/r1d_k1_ncu_summary.txt.  Seven rounds are the
+// reduced-round variant Random123 documents as Crush-resistant (Salmon et al. SC'11, Table 2); the other streams keep
+// ten.)  Counter (cell >> 2, episode, env, TAG_FIELD); the 128 bits of a call are cut into
+//   word 0: [31..12] radius uniform of cells 4q, 4q+1 (20 bits, (m + 1) 2^-20 in (0, 1])   [11..0] u of cell 4q
+//   word 1: [31..12] radius uniform of cells 4q+2, 4q+3                                    [11..0] u of cell 4q+1
+//   word 2: [15..0]  angle uniform of the first pair (16 bits, m 2^-16)   [31..16] angle uniform of the second pair
+//   word 3: [11..0]  u of cell 4q+2   [23..12] u of cell 4q+3   (u = m 2^-12 in [0, 1))
+// Box-Muller per pair: z_even = r cos(2 pi a), z_odd = r sin(2 pi a), r = sqrt(-2 ln(radius uniform)).
+// The conversions are exact in float32 (the bit patterns below equal m * 2^-b), so oracle/philox.py states them
+// arithmetically.
+constexpr int kFieldRounds = 7;
+PLUME_HD float field_unit_bits(uint32_t m, int bits) {      // m * 2^-bits for m < 2^bits <= 2^23, without int->float
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(0x3F800000u | (m << (23 - bits))) - 1.0f;
+#else
+    return (float)m * (1.0f / (float)(1u << bits));
+#endif
+}
+PLUME_HD void box_muller_pair(uint32_t radius20, uint32_t angle16, float& z0, float& z1) {
+    const float u1 = field_unit_bits(radius20, 20) + 9.5367431640625e-07f;      // (m + 1) 2^-20, exact
+    const float u2 = field_unit_bits(angle16, 16);
+#if defined(__CUDA_ARCH__)
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+#else
+    const float rad = sqrtf(-2.0f * logf(u1));
+    const float s = sinf(6.283185307179586f * u2), c = cosf(6.283185307179586f * u2);
+#endif
+    z0 = rad * c;
+    z1 = rad * s;
+}
+// the draws of the four cells 4q .. 4q+3 (cell = x*G + y) of (env, episode)
+PLUME_HD void field_noise_quad(const Cfg& c, uint32_t env_gid, uint32_t episode, uint32_t quad, float* z, float* u) {
+    const U4 r = philox4x32<kFieldRounds>(quad, episode, env_gid, kTagField, c.k0, c.k1);
+    box_muller_pair(r.x >> 12, r.z & 0xFFFFu, z[0], z[1]);
+    box_muller_pair(r.y >> 12, r.z >> 16, z[2], z[3]);
+    u[0] = field_unit_bits(r.x & 0xFFFu, 12);
+    u[1] = field_unit_bits(r.y & 0xFFFu, 12);
+    u[2] = field_unit_bits(r.w & 0xFFFu, 12);
+    u[3] = field_unit_bits((r.w >> 12) & 0xFFFu, 12);
+}
+// the two draws of cell (x,y) of (env, episode): only this cell's pair is evaluated
 PLUME_HD void field_noise(const Cfg& c, uint32_t env_gid, uint32_t episode, int x, int y, float& z, float& u) {
     const uint32_t cell = (uint32_t)x * (uint32_t)c.G + (uint32_t)y;
-    const U4 r = philox4x32_10(cell >> 1, episode, env_gid, kTagField, c.k0, c.k1);
+    const U4 r = philox4x32<kFieldRounds>(cell >> 2, episode, env_gid, kTagField, c.k0, c.k1);
+    const uint32_t k = cell & 3u;
     float z0, z1;
-    box_muller(r.x, r.y, z0, z1);
-    const bool odd = cell & 1u;
-    z = odd ? z1 : z0;
-    u = uniform24(odd ? r.w : r.z);
+    if (k < 2u) box_muller_pair(r.x >> 12, r.z & 0xFFFFu, z0, z1);
+    else box_muller_pair(r.y >> 12, r.z >> 16, z0, z1);
+    z = (k & 1u) ? z1 : z0;
+    const uint32_t m = k == 0u ? r.x : (k == 1u ? r.y : (k == 2u ? r.w : r.w >> 12));
+    u = field_unit_bits(m & 0xFFFu, 12);
 }
 
 // Field access policies -------------------------------------------------------------------

@@ -108,6 +108,13 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // barrier of the 256 compute threads (the issuer warp never takes part)
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTcThreads) : "memory"); }
+// barrier of the four warps that share a sample row (the TMEM lane quarter wq x the four column groups): the exchanges
+// of per-sample partial sums in Ph3 / Ph6 only involve them, so the quarters need not wait for one another there
+#ifndef PLUME_TC_NO_QBAR
+__device__ __forceinline__ void quarter_sync(int wq) { asm volatile("bar.sync %0, 128;" ::"r"(2 + wq) : "memory"); }
+#else
+__device__ __forceinline__ void quarter_sync(int) { compute_sync(); }
+#endif
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
@@ -577,7 +584,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             }
             EX(6, cg, srow) = sum;
             EX(7, cg, srow) = sq;
-            compute_sync();
+            quarter_sync(wq);
             float tot = 0.0f;
 #pragma unroll
             for (int g = 0; g < G; ++g) tot += EX(6, g, srow);
@@ -613,7 +620,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 EX(2 * k, cg, srow) = head2[k].x;
                 EX(2 * k + 1, cg, srow) = head2[k].y;
             }
-            compute_sync();
+            quarter_sync(wq);
             PLUME_TL(11);
             // The per-sample loss runs as two halves in two warps of the SAME scheduler (cg = 0: surrogate + value,
             // cg = 1: entropy; warps wq and 4 + wq), each from its own softmax; both add their part of d loss / d logits
@@ -664,7 +671,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 }
                 PLUME_TL(12);
             }
-            compute_sync();
+            quarter_sync(wq);
             PLUME_TL(13);
             const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8);
             const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + srow * 8 + 4);
@@ -687,7 +694,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             }
             EX(6, cg, srow) = m1p;
             EX(7, cg, srow) = m2p;
-            compute_sync();
+            quarter_sync(wq);
             if (cg == 0) {
                 float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
@@ -893,7 +900,7 @@ PLUME_UNROLL(PLUME_U6)
             wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
             EX(6, cg, srow) = m1p2.x + m1p2.y;
             EX(7, cg, srow) = m2p2.x + m2p2.y;
-            compute_sync();
+            quarter_sync(wq);
             if (cg == 0) {          // per-sample scalar sums of the layer-1 backward -> per-CTA accumulators
                 float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll

@@ -10,6 +10,7 @@ for f in $root/uav-wrf-les-ppo-lstm_b200/csrc/*.cu; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $f -o $tmp/$(basename $f .cu).o &
 done
 wait
+for f in $root/uav-wrf-les-ppo-lstm_b200/csrc/*.cu; do test -f $tmp/$(basename $f .cu).o || { echo "compile of $f failed"; exit 1; }; done
 nvcc -shared -o $out $tmp/*.o -gencode arch=compute_100a,code=sm_100a -cudart static
 rm -rf $tmp
 echo $out

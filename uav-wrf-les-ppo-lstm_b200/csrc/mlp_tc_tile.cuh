@@ -17,9 +17,11 @@
 // (tests/test_gpu_policy.py).
 //
 // Shared-memory plan (float units; the fp16 arrays are addressed as half):
-//   W1t [6][256]  P1 [3][256]  P2 [3][128]  Wh [128][8]  bh [8]  x [32][8]  red [2][8][32]  out [32][8]  stat [4][32]
+//   W1t [6][256]  P1 [3][256]  P2 [3][128]  Wh [128][8]  bh [8]  x [32][8]  red [2][8][16] (+ spare)  out [32][8]
+//   stat [4][32]
 //   W2h, W2l [128][264] half   feature.3.weight[o][k] split, row padded to 528 B (conflict-free ldmatrix rows)
-//   Ah,  Al  [32][264]  half   layer-1 activations split; the region is reused for h2 [32][132] float
+//   Ah,  Al  [16][264]  half   layer-1 activations of the half tile in flight, split (the arrays keep room for 32
+//                              rows); the region is reused for h2 [16][132] float
 #pragma once
 #include <cuda_fp16.h>
 
@@ -107,28 +109,52 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], u
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Forward of the tile in sm[x] (rows beyond the valid ones must hold finite values, e.g. zeros).  On return
-// sm[out][s][0..4] = logits, [5] = value.  Every thread of the 256-thread CTA must call it; ends with __syncthreads().
-__device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
+// barrier of the 256 MLP threads: the whole CTA (__syncthreads) or, where the CTA has more warps than these eight
+// (the pipelined rollout kernel), named barrier 1
+template <bool kNamed>
+__device__ __forceinline__ void mlp_sync() {
+    if (kNamed) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+
+// Forward of HALF a tile: the 16 samples in rows 16*half .. 16*half+15 of sm[x] (rows beyond the valid ones must hold
+// finite values, e.g. zeros) -> sm[out][same rows][0..4] = logits, [5] = value.  Executed by the 256 threads of warps
+// 0..7.  The caller makes x visible before the call and synchronises before it reads sm[out]; between two calls no
+// barrier is needed (the first barrier inside the next call orders the reuse of the A / h2 region).
+// A 16-sample unit is what the pipelined rollout kernel steps at a time (one half's policy forward overlaps the other
+// half's env step); every other user (policy_kernel, the rollout kernel with the in-loop stop head) runs two halves,
+// so all paths compute bit-identical logits.
+#ifdef PLUME_ROLLOUT_TIMELINE
+#define PLUME_MLP_TL(n) mtl[n] = clock64()
+static __device__ int g_mlp_tl_calls = 0;
+#else
+#define PLUME_MLP_TL(n)
+#endif
+template <bool kNamed>
+__device__ __forceinline__ void mlp_tc_forward_half(float* sm, int half) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef PLUME_ROLLOUT_TIMELINE
+    long long mtl[5];
+#endif
+    PLUME_MLP_TL(0);
     __half* Ah = reinterpret_cast<__half*>(sm + MlpTcSmem::Ah);
     __half* Al = reinterpret_cast<__half*>(sm + MlpTcSmem::Al);
-    __syncthreads();   // x tile visible; the previous call's h2 (aliasing A) has been consumed
-    // ---- layer 1 on the CUDA cores: thread = (sample lane, 32 outputs of chunk `warp`) ---------------------
+    // ---- layer 1 on the CUDA cores: thread = (sample s, 16 outputs of block ob) -----------------------------
     {
-        float xr[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) xr[k] = sm[MlpTcSmem::x + lane * 8 + k];
-        // four outputs per step: float4 weight loads (warp-uniform addresses) and packed fp32 pairs (FFMA2: two
-        // IEEE-rn FMAs per issue slot); every output still sums its six terms in the order k = 0..5, then the bias
-        float z[32];
-        float part = 0.0f;
+        const int s = lane & 15, ob = 2 * warp + (lane >> 4);
         float2 xr2[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) xr2[k] = make_float2(xr[k], xr[k]);
+        for (int k = 0; k < 6; ++k) {
+            const float v = sm[MlpTcSmem::x + (16 * half + s) * 8 + k];
+            xr2[k] = make_float2(v, v);
+        }
+        // four outputs per step: float4 weight loads and packed fp32 pairs (FFMA2: two IEEE-rn FMAs per issue slot);
+        // every output sums its six terms in the order k = 0..5, then the bias
+        float z[16];
+        float part = 0.0f;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const int o = warp * 32 + 4 * j4;
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const int o = ob * 16 + 4 * j4;
             float2 a01 = make_float2(0.0f, 0.0f), a23 = a01;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
@@ -143,38 +169,50 @@ __device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
             z[4 * j4 + 1] = a01.y;
             z[4 * j4 + 2] = a23.x;
             z[4 * j4 + 3] = a23.y;
-            part += a01.x;
-            part += a01.y;
-            part += a23.x;
-            part += a23.y;
+            part += (a01.x + a01.y) + (a23.x + a23.y);
         }
-        sm[MlpTcSmem::red + warp * 32 + lane] = part;
-        __syncthreads();
+        // LayerNorm-1 statistics with ONE exchange: every partial carries its sum and its sum of squares about its OWN
+        // mean; partials merge with M2 = sum_g [M2_g + n_g (mean_g - mean)^2] (as accurate as the two-pass form)
+        const float mean_t = part * (1.0f / 16.0f);
+        float m2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float d = z[j] - mean_t;
+            m2 = fmaf(d, d, m2);
+        }
+        {
+            const float part_p = __shfl_xor_sync(0xffffffffu, part, 16), m2_p = __shfl_xor_sync(0xffffffffu, m2, 16);
+            const float sum32 = part + part_p, mean32 = sum32 * (1.0f / 32.0f);
+            const float da = mean_t - mean32, db = part_p * (1.0f / 16.0f) - mean32;
+            m2 = (m2 + m2_p) + 16.0f * fmaf(da, da, db * db);
+            part = sum32;
+        }
+        if (lane < 16) {
+            sm[MlpTcSmem::red + warp * 16 + s] = part;
+            sm[MlpTcSmem::red + 128 + warp * 16 + s] = m2;
+        }
+        mlp_sync<kNamed>();
+        PLUME_MLP_TL(1);
         float mean = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) mean += sm[MlpTcSmem::red + w * 32 + lane];
+        for (int w = 0; w < 8; ++w) mean += sm[MlpTcSmem::red + w * 16 + s];
         mean *= (1.0f / 256.0f);
-        float sq = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float d = z[j] - mean;
-            sq = fmaf(d, d, sq);
-        }
-        sm[MlpTcSmem::red + 256 + warp * 32 + lane] = sq;
-        __syncthreads();
         float var = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) var += sm[MlpTcSmem::red + 256 + w * 32 + lane];
+        for (int w = 0; w < 8; ++w) {
+            const float dm = sm[MlpTcSmem::red + w * 16 + s] * (1.0f / 32.0f) - mean;
+            var += fmaf(32.0f * dm, dm, sm[MlpTcSmem::red + 128 + w * 16 + s]);
+        }
         const float rstd = 1.0f / sqrtf(var * (1.0f / 256.0f) + kLnEps);
         // relu(LN) -> fp16 hi / scaled lo, 8 values = one 16-byte store per array (conflict-free per quarter warp)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             __align__(16) __half2 hh[4], ll[4];
-            float gq[8], bq[8];           // LayerNorm-1 gamma / beta of the 8 outputs of this slot: four float4 loads
+            float gq[8], bq[8];
 #pragma unroll
             for (int v4 = 0; v4 < 2; ++v4) {
-                const float4 gv = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + 256 + warp * 32 + 8 * q + 4 * v4);
-                const float4 bv = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + 512 + warp * 32 + 8 * q + 4 * v4);
+                const float4 gv = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + 256 + ob * 16 + 8 * q + 4 * v4);
+                const float4 bv = *reinterpret_cast<const float4*>(sm + MlpTcSmem::P1 + 512 + ob * 16 + 8 * q + 4 * v4);
                 gq[4 * v4] = gv.x; gq[4 * v4 + 1] = gv.y; gq[4 * v4 + 2] = gv.z; gq[4 * v4 + 3] = gv.w;
                 bq[4 * v4] = bv.x; bq[4 * v4 + 1] = bv.y; bq[4 * v4 + 2] = bv.z; bq[4 * v4 + 3] = bv.w;
             }
@@ -192,24 +230,23 @@ __device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
                 hh[j2] = __halves2half2(h0, h1);
                 ll[j2] = __halves2half2(l0, l1);
             }
-            const int off = lane * kTcLd + warp * 32 + 8 * q;
+            const int off = s * kTcLd + ob * 16 + 8 * q;
             *reinterpret_cast<uint4*>(Ah + off) = *reinterpret_cast<const uint4*>(hh);
             *reinterpret_cast<uint4*>(Al + off) = *reinterpret_cast<const uint4*>(ll);
         }
     }
-    __syncthreads();
-    // ---- layer 2 on the tensor cores: warp = 32 samples x 16 outputs, K = 256 in 16 steps of 3 x 4 MMAs ----
-    float zacc[2][2][4];          // [m tile][n tile][fragment]: z2 without the bias
+    mlp_sync<kNamed>();
+    PLUME_MLP_TL(2);
+    // ---- layer 2 on the tensor cores: warp = 16 samples x 16 outputs, K = 256 in 16 steps of 3 x 2 MMAs ----
+    float zacc[2][4];             // [n tile][fragment]: z2 without the bias
     {
         const __half* W2h = reinterpret_cast<const __half*>(sm + MlpTcSmem::W2h);
         const __half* W2l = reinterpret_cast<const __half*>(sm + MlpTcSmem::W2l);
-        float cm[2][2][4], cs[2][2][4];
+        float cm[2][4], cs[2][4], ct[2][4];       // main terms; hi x lo and lo x hi cross terms in separate chains
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) cm[mt][nt][e] = cs[mt][nt][e] = 0.0f;
+            for (int e = 0; e < 4; ++e) cm[nt][e] = cs[nt][e] = ct[nt][e] = 0.0f;
         const int mj = lane >> 3, mi = lane & 7;        // ldmatrix: this lane addresses row mi of matrix mj
         // A fragment matrices: 0 = rows 0-7 / k 0-7, 1 = rows 8-15 / k 0-7, 2 = rows 0-7 / k 8-15, 3 = rows 8-15 / k 8-15
         const int a_off = ((mj & 1) * 8 + mi) * kTcLd + (mj >> 1) * 8;
@@ -218,126 +255,149 @@ __device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
 #pragma unroll 4
         for (int ks = 0; ks < 16; ++ks) {
             const int k0 = 16 * ks;
-            uint32_t ah[2][4], al[2][4], bh[4], bl[4];
+            uint32_t ah[4], al[4], bh[4], bl[4];
             ldmatrix_x4(bh, W2h + b_off + k0);
             ldmatrix_x4(bl, W2l + b_off + k0);
+            ldmatrix_x4(ah, Ah + a_off + k0);
+            ldmatrix_x4(al, Al + a_off + k0);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                ldmatrix_x4(ah[mt], Ah + 16 * mt * kTcLd + a_off + k0);
-                ldmatrix_x4(al[mt], Al + 16 * mt * kTcLd + a_off + k0);
+            for (int nt = 0; nt < 2; ++nt) {
+                mma_f16(cm[nt], ah, bh[2 * nt], bh[2 * nt + 1]);
+                mma_f16(cs[nt], ah, bl[2 * nt], bl[2 * nt + 1]);
+                mma_f16(ct[nt], al, bh[2 * nt], bh[2 * nt + 1]);
             }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    mma_f16(cm[mt][nt], ah[mt], bh[2 * nt], bh[2 * nt + 1]);
-                    mma_f16(cs[mt][nt], ah[mt], bl[2 * nt], bl[2 * nt + 1]);
-                    mma_f16(cs[mt][nt], al[mt], bh[2 * nt], bh[2 * nt + 1]);
-                }
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) zacc[mt][nt][e] = fmaf(cs[mt][nt][e], kSplitInv, cm[mt][nt][e]);
+            for (int e = 0; e < 4; ++e) zacc[nt][e] = fmaf(cs[nt][e] + ct[nt][e], kSplitInv, cm[nt][e]);
     }
-    // ---- bias, LayerNorm-2, ReLU: fragment (mt, nt, e) = row 16 mt + 8 (e >> 1) + g, column 16 warp + 8 nt + 2 t + (e & 1)
+    PLUME_MLP_TL(3);
+    // ---- bias, LayerNorm-2, ReLU: fragment (nt, e) = row 8 (e >> 1) + g, column 16 warp + 8 nt + 2 t + (e & 1)
+    const int g = lane >> 2, t = lane & 3;
+    float y2[2][4];               // relu(LN2(z2)) in the accumulator layout
     {
-        const int g = lane >> 2, t = lane & 3;
-        float part[4];            // rows: [mt][e >> 1]
+        float part[2] = {0.0f, 0.0f};       // rows g and 8 + g
 #pragma unroll
-        for (int r = 0; r < 4; ++r) part[r] = 0.0f;
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+            for (int e = 0; e < 4; ++e) {
+                zacc[nt][e] += sm[MlpTcSmem::P2 + 16 * warp + 8 * nt + 2 * t + (e & 1)];
+                part[e >> 1] += zacc[nt][e];
+            }
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    zacc[mt][nt][e] += sm[MlpTcSmem::P2 + 16 * warp + 8 * nt + 2 * t + (e & 1)];
-                    part[2 * mt + (e >> 1)] += zacc[mt][nt][e];
-                }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 2; ++r) {
             part[r] += __shfl_xor_sync(0xffffffffu, part[r], 1);
             part[r] += __shfl_xor_sync(0xffffffffu, part[r], 2);
         }
-        if (t == 0) {
+        // one exchange (see LayerNorm-1): the warp's 16 columns of a row carry their sum and their M2 about their mean
+        float sq[2] = {0.0f, 0.0f};
 #pragma unroll
-            for (int r = 0; r < 4; ++r) sm[MlpTcSmem::red + warp * 32 + 16 * (r >> 1) + 8 * (r & 1) + g] = part[r];
-        }
-        __syncthreads();          // also: every warp has finished reading the A operands (h2 aliases them)
-        float mean[4], sq[4];
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int row = 16 * (r >> 1) + 8 * (r & 1) + g;
-            float m = 0.0f;
+            for (int e = 0; e < 4; ++e) {
+                const float d = zacc[nt][e] - part[e >> 1] * (1.0f / 16.0f);
+                sq[e >> 1] = fmaf(d, d, sq[e >> 1]);
+            }
 #pragma unroll
-            for (int w = 0; w < 8; ++w) m += sm[MlpTcSmem::red + w * 32 + row];
-            mean[r] = m * (1.0f / 128.0f);
-            sq[r] = 0.0f;
-        }
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float d = zacc[mt][nt][e] - mean[2 * mt + (e >> 1)];
-                    sq[2 * mt + (e >> 1)] = fmaf(d, d, sq[2 * mt + (e >> 1)]);
-                }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 2; ++r) {
             sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], 1);
             sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], 2);
         }
         if (t == 0) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) sm[MlpTcSmem::red + 256 + warp * 32 + 16 * (r >> 1) + 8 * (r & 1) + g] = sq[r];
+            for (int r = 0; r < 2; ++r) {
+                sm[MlpTcSmem::red + warp * 16 + 8 * r + g] = part[r];
+                sm[MlpTcSmem::red + 128 + warp * 16 + 8 * r + g] = sq[r];
+            }
         }
-        __syncthreads();
-        float rstd[4];
+        mlp_sync<kNamed>();       // also: every warp has finished reading the A operands (the head partials alias them)
+        float mean[2], rstd[2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int row = 16 * (r >> 1) + 8 * (r & 1) + g;
+        for (int r = 0; r < 2; ++r) {
+            float m = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) m += sm[MlpTcSmem::red + w * 16 + 8 * r + g];
+            mean[r] = m * (1.0f / 128.0f);
             float v = 0.0f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) v += sm[MlpTcSmem::red + 256 + w * 32 + row];
+            for (int w = 0; w < 8; ++w) {
+                const float dm = sm[MlpTcSmem::red + w * 16 + 8 * r + g] * (1.0f / 16.0f) - mean[r];
+                v += fmaf(16.0f * dm, dm, sm[MlpTcSmem::red + 128 + w * 16 + 8 * r + g]);
+            }
             rstd[r] = 1.0f / sqrtf(v * (1.0f / 128.0f) + kLnEps);
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int hrow = 0; hrow < 2; ++hrow) {
-                    const int r = 2 * mt + hrow, row = 16 * mt + 8 * hrow + g, col = 16 * warp + 8 * nt + 2 * t;
-                    float2 y;
-                    y.x = fmaxf((zacc[mt][nt][2 * hrow] - mean[r]) * rstd[r] * sm[MlpTcSmem::P2 + 128 + col] +
-                                    sm[MlpTcSmem::P2 + 256 + col], 0.0f);
-                    y.y = fmaxf((zacc[mt][nt][2 * hrow + 1] - mean[r]) * rstd[r] * sm[MlpTcSmem::P2 + 128 + col + 1] +
-                                    sm[MlpTcSmem::P2 + 256 + col + 1], 0.0f);
-                    *reinterpret_cast<float2*>(sm + MlpTcSmem::h2 + row * kH2Stride + col) = y;
-                }
+            for (int e = 0; e < 4; ++e) {
+                const int col = 16 * warp + 8 * nt + 2 * t + (e & 1);
+                y2[nt][e] = fmaxf((zacc[nt][e] - mean[e >> 1]) * rstd[e >> 1] * sm[MlpTcSmem::P2 + 128 + col] +
+                                      sm[MlpTcSmem::P2 + 256 + col], 0.0f);
+            }
     }
-    __syncthreads();
-    // ---- heads: thread = (sample lane, output warp < 6), K = 128 ---------------------------------------------
-    if (warp < 6) {
-        // four interleaved partial sums (k mod 4): a 32-deep instead of a 128-deep chain of dependent FMAs on the
-        // lockstep loop's critical path
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        const float* hp = sm + MlpTcSmem::h2 + lane * kH2Stride;
-        const float* wp = sm + MlpTcSmem::Wh + warp;
-#pragma unroll 8
-        for (int k = 0; k < 128; k += 4) {
-            const float4 h = *reinterpret_cast<const float4*>(hp + k);
-            a0 = fmaf(h.x, wp[(k + 0) * 8], a0);
-            a1 = fmaf(h.y, wp[(k + 1) * 8], a1);
-            a2 = fmaf(h.z, wp[(k + 2) * 8], a2);
-            a3 = fmaf(h.w, wp[(k + 3) * 8], a3);
+    PLUME_MLP_TL(4);
+    // ---- heads on the tensor cores, straight from the registers: the warp's 16 columns of h2 are the K slice
+    // [16 warp, 16 warp + 16) of the 128 -> 6 head GEMM, and the accumulator layout of two n tiles IS the A fragment
+    // layout of one m16n8k16 step (a0 = (g, 2t..) of n tile 0, a1 = (g+8, ..) of n tile 0, a2 / a3 = n tile 1).
+    // One split MMA triple per warp, the eight K-slice partials are added through shared memory.
+    {
+        uint32_t ahi[4], alo[4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                __half h0, l0, h1, l1;
+                split_f16(y2[nt][2 * r], h0, l0);
+                split_f16(y2[nt][2 * r + 1], h1, l1);
+                const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+                ahi[2 * nt + r] = *reinterpret_cast<const uint32_t*>(&hh);
+                alo[2 * nt + r] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+        // B fragment: b0 = (k = 2t, 2t+1; n = g), b1 = (k = 2t+8, 2t+9; n = g) of Wh[16 warp + k][n] (n = 6, 7 are zero)
+        uint32_t bhi[2], blo[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float w0 = sm[MlpTcSmem::Wh + (16 * warp + 8 * q + 2 * t) * 8 + g];
+            const float w1 = sm[MlpTcSmem::Wh + (16 * warp + 8 * q + 2 * t + 1) * 8 + g];
+            __half h0, l0, h1, l1;
+            split_f16(w0, h0, l0);
+            split_f16(w1, h1, l1);
+            const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+            bhi[q] = *reinterpret_cast<const uint32_t*>(&hh);
+            blo[q] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        sm[MlpTcSmem::out + lane * 8 + warp] = ((a0 + a1) + (a2 + a3)) + sm[MlpTcSmem::bh + warp];
+        float cmh[4] = {0.0f, 0.0f, 0.0f, 0.0f}, csh[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        mma_f16(cmh, ahi, bhi[0], bhi[1]);
+        mma_f16(csh, ahi, blo[0], blo[1]);
+        mma_f16(csh, alo, bhi[0], bhi[1]);
+        float* pout = sm + MlpTcSmem::h2;          // [8 warps][16 rows][8]: partial head outputs of the K slices
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            *reinterpret_cast<float2*>(pout + (warp * 16 + 8 * r + g) * 8 + 2 * t) =
+                make_float2(fmaf(csh[2 * r], kSplitInv, cmh[2 * r]), fmaf(csh[2 * r + 1], kSplitInv, cmh[2 * r + 1]));
+        mlp_sync<kNamed>();
+        if (tid < 128) {
+            const int s = tid >> 3, n = tid & 7;
+            float acc = sm[MlpTcSmem::bh + n];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += pout[(w * 16 + s) * 8 + n];
+            sm[MlpTcSmem::out + (16 * half + s) * 8 + n] = acc;
+        }
     }
+#ifdef PLUME_ROLLOUT_TIMELINE
+    if (blockIdx.x == 0 && tid == 0 && atomicAdd(&g_mlp_tl_calls, 1) % 3001 == 700)
+        printf("mlp half timeline: layer 1 + LN1 stats %lld | normalise + split + barrier %lld | layer 2 %lld | LN2 %lld | heads %lld\n",
+               mtl[1] - mtl[0], mtl[2] - mtl[1], mtl[3] - mtl[2], mtl[4] - mtl[3], clock64() - mtl[4]);
+#endif
+}
+
+// Forward of the 32-sample tile in sm[x]: two halves.  Every thread of the 256-thread CTA must call it; ends with
+// __syncthreads().
+__device__ __forceinline__ void mlp_tc_forward_tile(float* sm) {
+    __syncthreads();   // x tile visible; the previous call's h2 (aliasing A) has been consumed
+    mlp_tc_forward_half<false>(sm, 0);
+    mlp_tc_forward_half<false>(sm, 1);
     __syncthreads();
 }
 

@@ -253,6 +253,271 @@ __global__ void __launch_bounds__(kMlpThreads, 1) rollout_kernel(RolloutArgs a) 
     }
 }
 
+// ---- the pipelined form (no in-loop stop head: training rollouts, deferred head) -----------------------------------
+// ncu of the kernel above (profiles/r1u_rollout_ncu_summary.txt): 33 % of the samples sit at the top-of-loop barrier --
+// seven warps wait while one warp steps the tile's 32 envs (a ~1200-instruction float64 dependency chain), then that
+// warp waits for the policy forward.  Here the tile is two HALVES of 16 envs with their own env warp each, next to the
+// eight MLP warps: while the MLP warps run the policy forward of half A (mlp_tc_forward_half), the env warp of half B
+// steps its envs, and vice versa.  The hand-over is four named barriers (bar.arrive by the producer, bar.sync by the
+// consumer; 256 + 32 threads each): OBS(h) "x[h] holds the observations of the next step", LOGITS(h) "out[h] holds
+// the logits".  The action-independent Philox draws of a step (action uniform, step noise) are taken by the env warp
+// BEFORE it waits for the logits, i.e. off the critical path.  Same per-env arithmetic as the kernel above: the
+// transitions are bit-identical.
+constexpr int kPipeThreads = kMlpThreads + 64;       // 8 MLP warps + 2 env warps
+constexpr int kBarObs = 2, kBarLogits = 4;           // named barrier ids: kBarObs + h, kBarLogits + h
+constexpr int kPipeBarThreads = kMlpThreads + 32;
+
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) {
+    __threadfence_block();           // the producer's shared-memory writes are ordered before its arrival
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+template <int kSpec>
+__global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* lsm = sm + RolloutSmem<0>::lstm;          // the [W][32] window ring (only maintained without `defer`)
+    float* win = lsm;
+    Cfg c = a.c;
+    if (kSpec != 0) {               // constant-propagated through the inlined per-env code
+        c.plume_model = PLUME_MODEL_ISOTROPIC;
+        c.fastdiv = 1;
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.st.n_envs;
+    const int W = a.lstm.window;
+    if (warp < 8) policy_load_weights(sm, a.mlp);
+    const ProceduralField field{a.st.sin_tab, a.st.cos_tab};
+    const double cur_radius = a.st.curriculum[0], cur_bonus = a.st.curriculum[1];
+    const bool greedy = (a.flags & PLUME_FLAG_GREEDY) != 0;
+    const bool defer = (a.flags & PLUME_FLAG_DEFER_STOP_HEAD) != 0;
+    const bool fast = kSpec == 0 ? (a.flags & PLUME_FLAG_FAST_REWARD) != 0 : kSpec == 2;   // float32 reward terms
+    const int tiles = (N + kTileM - 1) / kTileM;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        __syncthreads();            // weights loaded / the previous tile is finished everywhere
+        if (warp < 8) {
+            // ---- MLP warps: policy forward of half 0, half 1, half 0, ... as their observations arrive -------------
+            for (int t = 0; t < a.horizon; ++t) {
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+#ifdef PLUME_ROLLOUT_TIMELINE
+                    const long long tl0 = clock64();
+#endif
+                    bar_sync_n(kBarObs + h, kPipeBarThreads);           // x[h] of step t is in shared memory
+#ifdef PLUME_ROLLOUT_TIMELINE
+                    const long long tl1 = clock64();
+#endif
+                    mlp_tc_forward_half<true>(sm, h);
+                    bar_arrive_n(kBarLogits + h, kPipeBarThreads);      // out[h] written by this thread
+#ifdef PLUME_ROLLOUT_TIMELINE
+                    if (blockIdx.x == 0 && tid == 0 && (t == 100 || t == 101))
+                        printf("rollout timeline t=%d half %d: MLP warps waited %lld cycles for the observations, forward %lld\n",
+                               t, h, tl1 - tl0, clock64() - tl1);
+#endif
+                }
+            }
+            continue;
+        }
+        // ---- env warps: warp 8 + h owns envs 16 h .. 16 h + 15 of the tile (lanes 0..15) ------------------------------
+        const int h = warp - 8;
+        const int slot = 16 * h + (lane & 15);       // row of the tile in x / out / vis / win
+        const int env = tile * kTileM + slot;
+        const bool owner = lane < 16 && env < N;
+        const uint32_t gid = (uint32_t)(a.st.env_id_base + env);
+        EnvRegs e{};
+        uint16_t* vis = reinterpret_cast<uint16_t*>(sm + RolloutSmem<0>::vis) + slot * PLUME_VISIT_STRIDE;
+        double cell_conc = 0.0, cell_tke = 0.0;      // field at the float32 cell of the current position
+        int fill = 0;
+        {
+            float o[6] = {0, 0, 0, 0, 0, 0};
+            if (owner) {
+                e = load_env(a.st, env);
+                {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.st.visited + (size_t)env * PLUME_VISIT_STRIDE);
+                    uint4* dst = reinterpret_cast<uint4*>(vis);
+#pragma unroll
+                    for (int q = 0; q < PLUME_VISIT_STRIDE / 8; ++q) dst[q] = src[q];
+                }
+                int x, y;
+                cell32_of(c, e, x, y);
+                field.eval(c, env, gid, e.episode, e.sx, e.sy, x, y, cell_conc, cell_tke);
+                make_obs(c, e, cell_conc, cell_tke,
+                         vis[(x / c.cell_size) * PLUME_MAX_GRID_DIVISIONS + (y / c.cell_size)], o, gid);
+                fill = a.buf.window_fill ? a.buf.window_fill[env] : 0;
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sm[PolicySmem::x + slot * 8 + k] = o[k];
+                sm[PolicySmem::x + slot * 8 + 6] = 0.0f;
+                sm[PolicySmem::x + slot * 8 + 7] = 0.0f;
+                if (!defer)
+                    for (int k = 0; k < W; ++k)
+                        win[k * 32 + slot] = (owner && a.buf.conc_window) ? a.buf.conc_window[(size_t)env * W + k] : 0.0f;
+            }
+        }
+        for (int t = 0; t < a.horizon; ++t) {
+            const size_t row = (size_t)t * N;
+            // the observation the policy acts on: x[h] -> buf.obs[t][tile*32 + 16h ..][6], 96 consecutive floats
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int j = lane + 32 * q, s16 = j / 6, k = j - 6 * s16;
+                if (tile * kTileM + 16 * h + s16 < N)
+                    a.buf.obs[(row + (size_t)tile * kTileM + 16 * h) * 6 + j] = sm[PolicySmem::x + (16 * h + s16) * 8 + k];
+            }
+            bar_arrive_n(kBarObs + h, kPipeBarThreads);
+#ifdef PLUME_ROLLOUT_TIMELINE
+            const long long te0 = clock64();
+#endif
+            // the draws of this step do not depend on the action: taken while the MLP warps work
+            const int forced = (owner && a.buf.forced_actions) ? a.buf.forced_actions[row + env] : -1;
+            float u = 0.0f;
+            double z0 = 0.0, z1 = 0.0;
+            if (owner) {
+                if (forced < 0 && !greedy) u = action_uniform(c, gid, e);
+                if (a.buf.step_noise) {
+                    const double2 z = reinterpret_cast<const double2*>(a.buf.step_noise)[row + env];
+                    z0 = z.x;
+                    z1 = z.y;
+                } else {
+                    step_noise(c, gid, e, z0, z1);
+                }
+            }
+#ifdef PLUME_ROLLOUT_TIMELINE
+            const long long te1 = clock64();
+#endif
+            bar_sync_n(kBarLogits + h, kPipeBarThreads);                // out[h] of step t is complete
+#ifdef PLUME_ROLLOUT_TIMELINE
+            const long long te2 = clock64();
+#endif
+            if (owner) {
+                const float* o = sm + PolicySmem::out + slot * 8;
+                bool bad = false;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) bad |= isnan(o[k]);
+                if (bad) atomicExch(a.nan_flag, 1);
+                float p[5];
+                softmax5(o, p);
+                const float value = o[5];
+                float logp;
+                const int action = categorical_pick(p, u, greedy, forced, logp);
+                const uint32_t ep_of_transition = e.episode;
+                if (a.buf.noise_out) reinterpret_cast<double2*>(a.buf.noise_out)[row + env] = make_double2(z0, z1);
+                StepResult r{};
+                if (fast) env_step_fast(c, field, env, gid, e, vis, action, z0, z1, true, (float)cell_conc, cell_tke, r);
+                else env_step(c, field, env, gid, e, vis, action, z0, z1, true, cell_conc, cell_tke, r);
+                cell_conc = r.cell_conc;
+                cell_tke = r.cell_tke;
+                // sliding window of obs[2] (= conc_field[int(x),int(y)]/100 as float32, evaluate_with_lstm.py:67-74)
+                fill = fill < W ? fill + 1 : W;
+                const size_t i = row + env;
+                if (a.buf.conc_sample) a.buf.conc_sample[i] = r.obs[2];
+                if (a.buf.fill_t) a.buf.fill_t[i] = (uint8_t)fill;
+                if (a.buf.src_dist) a.buf.src_dist[i] = r.distance;
+                if (!defer) {
+                    for (int k = 0; k + 1 < W; ++k) win[k * 32 + slot] = win[(k + 1) * 32 + slot];
+                    win[(W - 1) * 32 + slot] = r.obs[2];
+                }
+                const bool done = r.done;
+                a.buf.actions[i] = action;
+                a.buf.rewards[i] = (float)r.reward;
+                a.buf.values[i] = value;
+                a.buf.log_probs[i] = logp;
+                a.buf.dones[i] = done ? 1.0f : 0.0f;
+                a.buf.reached[i] = r.reached ? 1 : 0;
+                if (a.buf.flag_code) a.buf.flag_code[i] = (uint8_t)((done ? 1 : 0) | (r.reached ? 2 : 0));
+                if (!defer) {                       // no stop head in this kernel: its outputs are zero
+                    if (a.buf.stop_prob) a.buf.stop_prob[i] = 0.0f;
+                    if (a.buf.stop_flag) a.buf.stop_flag[i] = 0;
+                    if (a.buf.peak_pred) a.buf.peak_pred[i] = 0.0f;
+                }
+                if (a.buf.episode_idx) a.buf.episode_idx[i] = (int32_t)ep_of_transition;
+                if (a.buf.pos_out) reinterpret_cast<float2*>(a.buf.pos_out)[i] = make_float2(e.px, e.py);
+                if (a.buf.src_out && done) reinterpret_cast<float2*>(a.buf.src_out)[i] = make_float2((float)e.sx, (float)e.sy);
+                if (a.buf.conc_out) a.buf.conc_out[i] = (float)cell_conc;       // train_ppo2.0.py:167-173
+                if (a.buf.info) {
+                    float* inf = a.buf.info + (size_t)t * 5 * N + env;
+                    inf[0] = r.conc_reward;
+                    inf[(size_t)N] = r.explore_reward;
+                    inf[2 * (size_t)N] = (float)r.move_penalty;
+                    inf[3 * (size_t)N] = r.tke_penalty;
+                    inf[4 * (size_t)N] = (float)r.boundary_penalty;
+                }
+                if (a.buf.trend && !defer) {
+                    float tr[4] = {0, 0, 0, 0};
+                    if (fill >= W && W >= 4) {
+                        trend_from_last4(100.0 * (double)win[(W - 4) * 32 + slot], 100.0 * (double)win[(W - 3) * 32 + slot],
+                                         100.0 * (double)win[(W - 2) * 32 + slot], 100.0 * (double)win[(W - 1) * 32 + slot],
+                                         r.distance, c.conc_peak, tr);
+                    }
+                    *reinterpret_cast<float4*>(a.buf.trend + i * 4) = make_float4(tr[0], tr[1], tr[2], tr[3]);
+                }
+                if (done) {
+                    env_reset(c, gid, e, vis, nullptr, cur_radius, cur_bonus);
+                    fill = 0;
+                    field.eval(c, env, gid, e.episode, e.sx, e.sy, 0, 0, cell_conc, cell_tke);
+                    make_obs(c, e, cell_conc, cell_tke, 0, r.obs, gid);
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sm[PolicySmem::x + slot * 8 + k] = r.obs[k];
+            }
+#ifdef PLUME_ROLLOUT_TIMELINE
+            if (blockIdx.x == 0 && lane == 0 && (t == 100 || t == 101))
+                printf("rollout timeline t=%d env warp %d: draws %lld cycles, waited %lld for the logits, step + outputs %lld\n", t,
+                       h, te1 - te0, te2 - te1, clock64() - te2);
+#endif
+        }
+        // ---- persist the half tile's state --------------------------------------------------------------------
+        if (owner) {
+            store_env(a.st, env, e);
+            {
+                uint4* dst = reinterpret_cast<uint4*>(a.st.visited + (size_t)env * PLUME_VISIT_STRIDE);
+                const uint4* src = reinterpret_cast<const uint4*>(vis);
+#pragma unroll
+                for (int q = 0; q < PLUME_VISIT_STRIDE / 8; ++q) dst[q] = src[q];
+            }
+            if (a.st.cell_tke && a.st.cell_conc && a.st.cell_key) {   // hand the carried cell to a following plume_env_step
+                int x, y;
+                cell32_of(c, e, x, y);
+                a.st.cell_tke[env] = cell_tke;
+                a.st.cell_conc[env] = cell_conc;
+                a.st.cell_key[env] = cell_key_of(c, x, y, e.episode);
+            }
+            if (a.buf.window_fill) a.buf.window_fill[env] = fill;
+            if (a.buf.conc_window && !defer)
+                for (int k = 0; k < W; ++k) a.buf.conc_window[(size_t)env * W + k] = win[k * 32 + slot];
+            if (a.buf.last_obs) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a.buf.last_obs[(size_t)env * 6 + k] = sm[PolicySmem::x + slot * 8 + k];
+            }
+        }
+    }
+}
+
+template <int kSpec>
+static int launch_rollout_pipe_spec(const RolloutArgs& a, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = RolloutSmem<0>::total * (int)sizeof(float);
+    if (!configured) {
+        if (cudaFuncSetAttribute(rollout_pipe_kernel<kSpec>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return fail("pipelined rollout kernel: cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    const int tiles = (a.st.n_envs + kTileM - 1) / kTileM;
+    int grid = sm_count();
+    if (grid <= 0) return fail("no CUDA device");
+    if (tiles < grid) grid = tiles;
+    rollout_pipe_kernel<kSpec><<<grid, kPipeThreads, smem, s>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return fail("pipelined rollout kernel launch failed");
+    return 0;
+}
+
+static int launch_rollout_pipe(const RolloutArgs& a, cudaStream_t s) {
+    if (a.c.plume_model == PLUME_MODEL_ISOTROPIC && a.c.fastdiv)
+        return (a.flags & PLUME_FLAG_FAST_REWARD) ? launch_rollout_pipe_spec<2>(a, s) : launch_rollout_pipe_spec<1>(a, s);
+    return launch_rollout_pipe_spec<0>(a, s);
+}
+
 template <int H, int kSpec>
 static int launch_rollout_spec(const RolloutArgs& a, cudaStream_t s) {
     static bool configured = false;
@@ -321,5 +586,9 @@ extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state*
     }
     a.lstm = plume_lstm_params{};
     a.lstm.window = (lstm && lstm->window > 0 && lstm->window <= kLstmMaxSteps) ? lstm->window : 20;
+#ifdef PLUME_ROLLOUT_LOCKSTEP          // A/B build: the single-env-warp kernel also for rollouts without an in-loop head
     return launch_rollout<0>(a, as_stream(stream));
+#else
+    return launch_rollout_pipe(a, as_stream(stream));
+#endif
 }

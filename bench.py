@@ -8,7 +8,7 @@ A *step* is one PPO iteration at the BASELINE.json configuration "PPOV2.1, 4096 
 LSTM policy": a fused rollout of 256 lockstep env steps over 4096 envs (MLP policy + Categorical
 sample + env step + LSTM(1->32) stop head over the 20-sample window + trend features, auto-reset),
 the curriculum, GAE and 5 epochs x 4 minibatches of the clipped-surrogate update with Adam (and,
-for N > 1, one NCCL all-reduce of the flat gradient per minibatch).  ``value`` = env-steps/s of the
+for N > 1, one fused all-reduce + clip + Adam kernel over NVLink peer memory per minibatch).  ``value`` = env-steps/s of the
 whole job with everything resident in HBM; ``e2e`` = the same through the host-buffer API (model
 parameters uploaded from / downloaded to pinned host memory every iteration).
 
@@ -35,6 +35,12 @@ ENVS_PER_GPU = 4096
 HORIZON = 256
 WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(1->32) stop head, window 20, "
             "trend features) x 256 steps + curriculum + GAE + 5 epochs x 4 minibatches PPO update")
+
+
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture; counters are not
+# readable from inside an unprofiled run, so the line cites the committed capture it copies the number from)
+PPO_TC_TRAFFIC = {"bytes": 33.5e6, "source": "profiles/r1u_ncu_summary.txt (prof_r1u_ppo_tc: 33.46 MB read + 0.03 MB written)"}
+K2_TRAFFIC = {"bytes": 316.7e6, "source": "profiles/r1h_k2_ncu_summary.txt (prof_r1h_k2, 2^20 envs)"}
 
 
 def measured_peaks():
@@ -103,11 +109,21 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference loop)
 # ----------------------------------------------------------------------------------------------
+def reference_kind() -> str:
+    """"reference": the unmodified reference's own scripts (oracle/_ref, shipped by build()) are timed;
+    "port": the oracle restatement of the same loop."""
+    from oracle import ref_loop
+    return "reference" if (os.path.isdir("/root/reference/PPOV2.1") or ref_loop.shipped_reference_available()) else "port"
+
+
 def _cpu_worker(args):
     seed, n_steps = args
     import numpy as np
     import torch
     torch.set_num_threads(1)
+    if reference_kind() == "reference":
+        from oracle import ref_loop
+        return ref_loop.reference_loop(seed, n_steps)
     from oracle import plume_oracle as po
     from oracle import ppo_oracle as pp
     cfg = po.config_for("2.1")
@@ -123,14 +139,17 @@ def _cpu_worker(args):
 
 def cpu_baseline_single(n_steps: int = 40000) -> dict:
     steps, dt = _cpu_worker((0, n_steps))
-    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    kind = reference_kind()
+    return {"value": steps / dt, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": f"{steps} env-steps of the reference loop (batch-1 policy forward + env.step + "
-                      f"_update_model every 256 transitions), oracle port, 1 thread, {dt:.1f} s"}
+                      f"_update_model every 256 transitions), "
+                      f"{'the unmodified PPOV2.1 scripts' if kind == 'reference' else 'oracle port'}, 1 thread, {dt:.1f} s"}
 
 
 def run_reference_arm(args) -> None:
-    """`--impl reference`: the reference's CPU loop (oracle port; the reference is pure Python and
-    cannot travel to the GPU box) on all host cores, one independent single-env process per core."""
+    """`--impl reference`: the reference's CPU loop on all host cores, one independent single-env process per core:
+    the unmodified PPOV2.1 scripts where build() has shipped them (oracle/_ref, kind "reference"), else the oracle
+    port of the same loop (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -149,13 +168,15 @@ def run_reference_arm(args) -> None:
     total_steps = sum(t[0] for t in times)
     total_time = sum(t[1] for t in times)
     value = total_steps / total_time
+    kind = reference_kind()
     sample = (f"{cores} processes x {per_proc} env-steps per step of the reference loop (policy + env.step + "
-              f"_update_model every 256), oracle port")
+              f"_update_model every 256), {'unmodified PPOV2.1 scripts' if kind == 'reference' else 'oracle port'}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_time / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference_arm": "CPU, all host cores"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "horizon": HORIZON, "version": "2.1",
+                       "reference_arm": "CPU, all host cores, one env per process, update every 256 transitions"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -223,10 +244,96 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
         out[f"plume_step_{n2}" + ("_fast_reward" if fast else "")] = {
             "bound": "hbm" if n2 > 100000 else "latency", "achieved": b / ms / 1e6, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": b / ms / 1e6 / peaks["hbm_gbs"],
-            "traffic": 316.7e6 if (n2 == 1 << 20 and not fast) else None, "ms": ms, "envs": n2,
+            "traffic": K2_TRAFFIC["bytes"] if (n2 == 1 << 20 and not fast) else None,
+            "traffic_source": K2_TRAFFIC["source"] if (n2 == 1 << 20 and not fast) else None, "ms": ms, "envs": n2,
             "algorithmic_bytes": b, "env_steps_per_s": n2 / ms * 1e3, "peak_source": peaks["source"]}
         del env
         torch.cuda.empty_cache()
+    return out
+
+
+def config_lines_aux(pb, torch, dev, peaks) -> dict:
+    """Outside the headline: the other BASELINE configs and schedules on one GPU (each a few iterations, CUDA events).
+      reference_schedule   PPOV2.1 with the reference's BATCH_SIZE = 256 minibatches (config.py:21, train_ppo2.0.py:42-47):
+                           5 x 4096 optimiser steps per iteration on the same 1 M transitions
+      v20 / v11            configs[1] / configs[0] at 4096 envs: sigma = G/16 (V1.1 also MAX_STEPS = 5000 and the
+                           G - 1e-6 clip), no stop head in the training loop (PPOV2.0/train_ppo2.0.py has none)
+      v20_threshold_head   the 3 x 128 LSTM + FC threshold predictor (PPOV2.0/model.py:203-240) over the windows a
+                           4096 x 256 segment evaluates (every 10th step: 104 448 windows of 10)
+      evaluators           greedy evaluation episodes per second of the three reference evaluation drivers"""
+    out = {}
+    N, T = ENVS_PER_GPU, HORIZON
+
+    def iteration_ms(tr, warm=2, reps=3):
+        for _ in range(warm):
+            tr.train_iteration()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            tr.train_iteration()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    tr = pb.PlumeTrainer(num_envs=N, horizon=T, version="2.1", device=dev, seed=0, minibatch_size=256)
+    ms = iteration_ms(tr, warm=1, reps=1)
+    n_opt = tr.cfg.epochs * (N * T // 256)
+    out["reference_schedule_minibatch_256"] = {
+        "ms_per_iteration": ms, "env_steps_per_s": N * T / ms * 1e3, "optimizer_steps_per_iteration": n_opt,
+        "us_per_optimizer_step": 1e3 * (ms - 3.4) / n_opt,
+        "note": "the reference's BATCH_SIZE: 256-sample minibatches run on the fp32-FMA gradient kernels (3 launches per "
+                "step); the headline uses N*T/4 = 262144 (SURVEY section 8(d) asks for both)"}
+    del tr
+    torch.cuda.empty_cache()
+    for version in ("2.0", "1.1"):
+        tr = pb.PlumeTrainer(num_envs=N, horizon=T, version=version, device=dev, seed=0, minibatch_size=N * T // 4,
+                             stop_head=False)
+        ms = iteration_ms(tr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            tr.rollout_only()
+        e1.record()
+        torch.cuda.synchronize()
+        rms = e0.elapsed_time(e1) / 3
+        out["v" + version.replace(".", "")] = {"ms_per_iteration": ms, "env_steps_per_s": N * T / ms * 1e3,
+                                                "rollout_ms": rms, "rollout_env_steps_per_s": N * T / rms * 1e3,
+                                                "config": f"PPOV{version}, {N} envs x {T} steps, sigma = G/16, "
+                                                          f"max_steps {tr.cfg.max_steps}, no in-loop stop head"}
+        del tr
+        torch.cuda.empty_cache()
+    head = pb.ConcentrationThresholdPredictor(device=dev)
+    nwin = N * (T // 10)
+    win = torch.rand(nwin, 10, 1, device=dev)
+    for _ in range(2):
+        head(win, lengths=[10] * nwin)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    head(win, lengths=[10] * nwin)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    flop = nwin * 10 * 2 * 4 * 128 * ((1 + 128) + 2 * (128 + 128))
+    out["v20_threshold_head"] = {"windows": nwin, "ms": ms, "windows_per_s": nwin / ms * 1e3,
+                                 "tflops": flop / ms / 1e9, "env_steps_per_s_equivalent": N * T / ms * 1e3}
+    del head, win
+    torch.cuda.empty_cache()
+    ev = {}
+    torch.manual_seed(0)
+    model = pb.PPOActorCritic(device=dev)
+    for stop, kw in (("lstm", {"head": pb.PeakAndStopPredictor(device=dev)}),
+                     ("threshold", {"head": pb.ConcentrationThresholdPredictor(device=dev), "scaler": (0.0, 100.0)}),
+                     ("fixed", {})):
+        t0 = time.perf_counter()
+        res = pb.evaluate_policy(model, stop=stop, num_envs=1024, seed=1, device=dev, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ev[stop] = {"episodes": int(res.steps.numel()), "seconds": dt, "episodes_per_s": int(res.steps.numel()) / dt,
+                    "env_steps_per_s": float(res.steps.double().sum()) / dt, "mean_steps": float(res.steps.double().mean())}
+    out["evaluators"] = ev
     return out
 
 
@@ -313,14 +420,7 @@ def run_cuda_arm(args) -> None:
     for k in range(args.steps):
         flush.zero_()
         ev[k][0].record()
-        ev_roll[k][0].record()
-        buf = trainer.engine.collect()
-        ev_roll[k][1].record()
-        trainer.curriculum.update_from_rollout(buf, pg)
-        trainer.last_losses = pb.update_model(buf, trainer.model, trainer.optimizer, cfg=trainer.cfg,
-                                              minibatch_size=trainer.minibatch_size, workspace=trainer.workspace,
-                                              process_group=pg, perm_seed=trainer.iteration, check_nan=False)
-        trainer.iteration += 1
+        trainer.train_iteration(rollout_events=ev_roll[k])          # the product's own iteration, nothing bench-specific
         ev[k][1].record()
     barrier()
     t_wall1 = time.time()
@@ -416,7 +516,8 @@ def run_cuda_arm(args) -> None:
     # split), so the ceiling this kernel can reach is peak/3 -- reported next to it.
     roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / peak_tf,
-                "traffic": 33.5e6 if dom.startswith("ppo_grad") else None,   # profiles/r1u_ncu_summary.txt
+                "traffic": PPO_TC_TRAFFIC["bytes"] if dom.startswith("ppo_grad") else None,
+                "traffic_source": PPO_TC_TRAFFIC["source"] if dom.startswith("ppo_grad") else None,
                 "peak_source": f"{peaks['source']} bf16 dense (sustained), of measured",
                 "split_ceiling": peak_tf / 3.0, "frac_of_split_ceiling": kernels[dom]["tflops"] / (peak_tf / 3.0),
                 "note": "tcgen05.mma kind::f16 with the two-term fp16 split x = hi + lo/s (fp32 rel 1e-5 parity bar), "
@@ -451,6 +552,7 @@ def run_cuda_arm(args) -> None:
             dist.destroy_process_group()
         return
     plume = plume_kernel_rooflines(pb, torch, peaks, dev) if not args.skip_aux else {}
+    other = config_lines_aux(pb, torch, dev, peaks) if (world == 1 and not args.skip_aux) else None
     lstm_aux = lstm_train_aux(pb, torch, dev, world == 1 and not args.skip_cpu) if not args.skip_aux else None
     cpu = cpu_baseline_single(args.cpu_steps) if (world == 1 and not args.skip_cpu) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -464,7 +566,8 @@ def run_cuda_arm(args) -> None:
                                               if trainer.comm is not None else "NCCL all-reduce")),
                        "l2_flush": "256 MB write between timed steps"},
             "rollout_env_steps_per_sec": rollout_value,
-            "roofline": roofline, "kernels": kernels, "plume_kernels": plume, "lstm_train": lstm_aux,
+            "roofline": roofline, "kernels": kernels, "plume_kernels": plume, "other_configs": other,
+            "lstm_train": lstm_aux,
             "cpu_baseline": cpu, "clocks": clocks,
             "e2e": e2e, "gpu_launches": trainer.launches_per_iteration * args.steps, "rank_skew": skew}
     print(json.dumps(line), flush=True)

@@ -15,16 +15,21 @@ for _ in range(3):
     tr.train_iteration()
 torch.cuda.synchronize(); dist.barrier()
 def ev(): return torch.cuda.Event(enable_timing=True)
-names = ["rollout", "curriculum(+gather)", "advantages(+stats allreduce)", "20 x (grad + exchange + adam)"]
+names = ["rollout", "curriculum(+flag exchange)", "advantages(+stats exchange)", "20 x (grad + exchange + adam)"]
 acc = [0.0] * 4
 K = 5
 for _ in range(K):
     e = [ev() for _ in range(5)]
     e[0].record(); buf = tr.engine.collect()
-    e[1].record(); tr.curriculum.update_from_rollout(buf, pg)
+    e[1].record()
+    if tr.comm is not None:
+        torch.cuda.current_stream().wait_event(tr._codes_done)
+        tr.curriculum.update_from_rollout(buf, pg, comm=tr.comm, codes_published=True)
+    else:
+        tr.curriculum.update_from_rollout(buf, pg)
     e[2].record()
     ws = tr.workspace
-    pb.compute_advantages(buf, tr.cfg, ws, pg)
+    pb.compute_advantages(buf, tr.cfg, ws, pg, comm=tr.comm)
     e[3].record()
     # the update without recomputing advantages is not exposed; time the whole update and subtract
     pb.update_model(buf, tr.model, tr.optimizer, cfg=tr.cfg, minibatch_size=tr.minibatch_size, workspace=ws,

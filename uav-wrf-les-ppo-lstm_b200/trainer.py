@@ -94,9 +94,14 @@ class PlumeTrainer:
         if self.comm is not None:
             self.comm.check_async_end()
 
-    def train_iteration(self, check_nan: bool = False):
+    def train_iteration(self, check_nan: bool = False, rollout_events=None):
+        """``rollout_events``: optional (start, end) CUDA events recorded around the rollout (bench.py)."""
         self.check()                               # waits for the previous iteration's error word, not for this one
+        if rollout_events is not None:
+            rollout_events[0].record(torch.cuda.current_stream(self.device))
         buf = self.engine.collect()
+        if rollout_events is not None:
+            rollout_events[1].record(torch.cuda.current_stream(self.device))
         perms = None
         if self._perm_stream is not None:          # launched after the rollout, so its CTAs are placed first
             with torch.cuda.device(self.device):

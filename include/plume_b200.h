@@ -356,6 +356,17 @@ int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int6
                    int32_t epoch, int64_t mb_start, int64_t mb_size, int64_t mb_size_global, float clip_eps,
                    float entropy_beta, float* grads, double* loss_out, int32_t* nan_flag, void* workspace,
                    int64_t workspace_bytes, int32_t kernel_path, void* stream);
+/* The whole optimiser loop of _update_model (train_ppo2.0.py:42-87) in one call: `epochs` passes over the
+ * batch->total transitions in minibatches of mb_size; per step: zero grads, plume_ppo_grad (divisor mb * world),
+ * plume_clip_adam -- or plume_allreduce_clip_adam when comm != NULL.  perms: int64 [epochs][M] (NULL = the stateless
+ * bijection keyed by (perm_seed, epoch)); first_step = the optimiser's step number of the first step (1-based);
+ * losses double[epochs * ceil(M / mb_size)][4] (zeroed by the caller); grad_norm_out (may be NULL) receives the last
+ * step's gradient norm. */
+int plume_ppo_update(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const plume_ppo_batch* batch,
+                     const int64_t* perms, uint64_t perm_seed, int32_t epochs, int64_t mb_size, int32_t world,
+                     float clip_eps, float entropy_beta, float max_norm, float lr, float beta1, float beta2, float eps,
+                     int32_t first_step, void* comm, double* losses, float* grad_norm_out, int32_t* nan_flag,
+                     void* workspace, int64_t workspace_bytes, int32_t kernel_path, void* stream);
 /* bytes of workspace plume_ppo_grad needs for a minibatch of mb_size samples */
 int64_t plume_ppo_workspace_bytes(int64_t mb_size);
 

@@ -125,6 +125,9 @@ _SIGNATURES = {
     "plume_gae_normalise_variant": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int32, _vp, _vp]),
     "plume_ppo_grad": (C.c_int, [_vp, _P(PpoBatch), _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _vp]),
+    "plume_ppo_update": (C.c_int, [_vp, _vp, _vp, _vp, _P(PpoBatch), _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_int32,
+                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _vp]),
     "plume_ppo_workspace_bytes": (C.c_int64, [C.c_int64]),
     "plume_ppo_pack": (C.c_int, [_P(PpoBatch), _vp, _vp]),
     "plume_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -450,9 +450,11 @@ extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const floa
     // gate GEMM on the tensor cores where the hidden size has a tcgen05 kernel (lstm_tc_kernels.cu); kernel_path =
     // PLUME_KERNEL_SIMT selects the CUDA-core kernel, whose arithmetic is bit-identical to the in-loop head of
     // plume_rollout
-    PLUME_CHECK_ARG(kernel_path != PLUME_KERNEL_TENSOR || stop_head_segment_tc_supports(lstm->hidden),
+    const bool resident = stop_head_segment_tc_supports(lstm->hidden);
+    const bool streamed = stop_head_segment_stream_supports(lstm->hidden) && lstm->window <= 20;
+    PLUME_CHECK_ARG(kernel_path != PLUME_KERNEL_TENSOR || resident || streamed,
                     "no tensor-core stop-head kernel for this hidden size");
-    if (stop_head_segment_tc_supports(lstm->hidden) && kernel_path != PLUME_KERNEL_SIMT) {
+    if ((resident || streamed) && kernel_path != PLUME_KERNEL_SIMT) {
         LtArgs t;
         t.conc_sample = conc_sample;
         t.fill_t = fill_t;
@@ -470,7 +472,8 @@ extern "C" int plume_stop_head_segment(const plume_lstm_params* lstm, const floa
         t.stop_flag = stop_flag;
         t.w_ih = lstm->w_ih; t.w_hh = lstm->w_hh; t.b_ih = lstm->b_ih; t.b_hh = lstm->b_hh;
         t.w_peak = lstm->w_peak; t.b_peak = lstm->b_peak; t.w_stop = lstm->w_stop; t.b_stop = lstm->b_stop;
-        return launch_stop_head_segment_tc(t, lstm->hidden, as_stream(stream));
+        return resident ? launch_stop_head_segment_tc(t, lstm->hidden, as_stream(stream))
+                        : launch_stop_head_segment_stream(t, lstm->hidden, as_stream(stream));
     }
     const LstmWeights w{lstm->w_ih, lstm->w_hh, lstm->b_ih, lstm->b_hh, lstm->w_peak, lstm->b_peak, lstm->w_stop,
                         lstm->b_stop};

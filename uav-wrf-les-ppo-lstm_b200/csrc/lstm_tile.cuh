@@ -160,6 +160,9 @@ struct LtArgs {
 };
 bool stop_head_segment_tc_supports(int hidden);
 int launch_stop_head_segment_tc(const LtArgs& a, int hidden, cudaStream_t s);
+// hidden 128 / 256: gate weights streamed from L2 (lstm_tc_stream.cu)
+bool stop_head_segment_stream_supports(int hidden);
+int launch_stop_head_segment_stream(const LtArgs& a, int hidden, cudaStream_t s);
 
 // ---- P4t trend features (calculate_dynamic_label, PPOV2.1/model.py:113-127) ------------------------
 // m = mean of the last three np.gradient values of the window; dist = ||pos[-1] - src||

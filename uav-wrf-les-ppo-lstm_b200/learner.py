@@ -182,30 +182,56 @@ def update_model(buffer, model, optimizer, cfg: PlumeConfig | None = None, perms
         batch.packed = packed.data_ptr()
     n_mb = (M + mb - 1) // mb
     losses = torch.zeros(cfg.epochs * n_mb, 4, dtype=torch.float64, device=dev)
-    step = 0
-    with torch.cuda.device(dev):
-        for epoch in range(cfg.epochs):
-            perm = None
-            if perms is not None:
-                perm = torch.as_tensor(perms[epoch], dtype=torch.int64, device=dev).contiguous()
-            elif M >= MATERIALISE_PERM_MIN:
-                perm = workspace.perm_buffer(1, M)[0]
-                materialise_permutations(lib, perm.unsqueeze(0), M, perm_seed, [epoch], _stream(dev))
-            for start in range(0, M, mb):
-                size = min(mb, M - start)
-                optimizer.zero_grad()
-                rc = lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), _lib.ptr(perm), perm_seed, epoch, start,
-                                        size, pdist.global_minibatch(size, process_group), cfg.clip_epsilon, cfg.entropy_beta,
-                                        model.flat_grad.data_ptr(), losses[step].data_ptr(),
-                                        workspace.nan_flag.data_ptr(), workspace.ws.data_ptr(), workspace.bytes,
-                                        kpath, _stream(dev))
-                _lib.check(rc, "plume_ppo_grad")
-                if comm is None:
-                    pdist.allreduce_gradient(model.flat_grad, process_group)      # NCCL; else fused into step()
-                optimizer.step()
-                if record is not None:
-                    record.append(optimizer.grad_norm.clone())
-                step += 1
+    nccl_exchange = process_group is not None and comm is None
+    if record is None and not nccl_exchange:
+        # the optimiser loop runs behind the ABI (plume_ppo_update): same launches, no Python call per minibatch
+        perm_all = None
+        if perms is not None:
+            if torch.is_tensor(perms) and perms.dim() == 2:
+                perm_all = perms.to(device=dev, dtype=torch.int64).contiguous()
+            else:
+                perm_all = torch.stack([torch.as_tensor(p, dtype=torch.int64) for p in perms]).to(dev).contiguous()
+            assert perm_all.shape == (cfg.epochs, M), "perms: one permutation of the M transitions per epoch"
+        elif M >= MATERIALISE_PERM_MIN:
+            perm_all = workspace.perm_buffer(cfg.epochs, M)
+            materialise_permutations(lib, perm_all, M, perm_seed, range(cfg.epochs), _stream(dev))
+        world = pdist.global_minibatch(1, process_group)
+        with torch.cuda.device(dev):
+            rc = lib.plume_ppo_update(model.flat.data_ptr(), model.flat_grad.data_ptr(), optimizer.exp_avg.data_ptr(),
+                                      optimizer.exp_avg_sq.data_ptr(), C.byref(batch), _lib.ptr(perm_all), perm_seed,
+                                      cfg.epochs, mb, world, cfg.clip_epsilon, cfg.entropy_beta, optimizer.max_grad_norm,
+                                      optimizer.lr, optimizer.betas[0], optimizer.betas[1], optimizer.eps,
+                                      optimizer.step_count + 1, comm._h if comm is not None else None,
+                                      losses.data_ptr(), optimizer.grad_norm.data_ptr(), workspace.nan_flag.data_ptr(),
+                                      workspace.ws.data_ptr(), workspace.bytes, kpath, _stream(dev))
+        _lib.check(rc, "plume_ppo_update")
+        optimizer.step_count += cfg.epochs * n_mb
+        optimizer.launches += cfg.epochs * n_mb
+    else:
+        step = 0
+        with torch.cuda.device(dev):
+            for epoch in range(cfg.epochs):
+                perm = None
+                if perms is not None:
+                    perm = torch.as_tensor(perms[epoch], dtype=torch.int64, device=dev).contiguous()
+                elif M >= MATERIALISE_PERM_MIN:
+                    perm = workspace.perm_buffer(1, M)[0]
+                    materialise_permutations(lib, perm.unsqueeze(0), M, perm_seed, [epoch], _stream(dev))
+                for start in range(0, M, mb):
+                    size = min(mb, M - start)
+                    optimizer.zero_grad()
+                    rc = lib.plume_ppo_grad(model.flat.data_ptr(), C.byref(batch), _lib.ptr(perm), perm_seed, epoch, start,
+                                            size, pdist.global_minibatch(size, process_group), cfg.clip_epsilon,
+                                            cfg.entropy_beta, model.flat_grad.data_ptr(), losses[step].data_ptr(),
+                                            workspace.nan_flag.data_ptr(), workspace.ws.data_ptr(), workspace.bytes,
+                                            kpath, _stream(dev))
+                    _lib.check(rc, "plume_ppo_grad")
+                    if comm is None:
+                        pdist.allreduce_gradient(model.flat_grad, process_group)      # NCCL; else fused into step()
+                    optimizer.step()
+                    if record is not None:
+                        record.append(optimizer.grad_norm.clone())
+                    step += 1
     if check_nan and int(workspace.nan_flag.item()) != 0:            # train_ppo2.0.py:57-61
         workspace.nan_flag.zero_()
         raise RuntimeError("NaN in probs")

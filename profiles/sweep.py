@@ -35,7 +35,7 @@ def main():
     T = args.horizon
     for H in args.hidden:
         for N in args.envs:
-            if H not in (32, 64) and N > args.max_envs_generic:
+            if H not in (32, 64, 128, 256) and N > args.max_envs_generic:
                 continue
             tr = pb.PlumeTrainer(num_envs=N, horizon=T, minibatch_size=max(N * T // 4, 256), seed=1)
             if H != 32:
@@ -47,7 +47,9 @@ def main():
             roll = timed(lambda: tr.engine.collect())
             full = timed(lambda: tr.train_iteration())
             print(json.dumps({"envs_per_gpu": N, "horizon": T, "lstm_hidden": H,
-                              "stop_head": "tcgen05, resident weights" if H in (32, 64) else "cuda-core, L2 weights",
+                              "stop_head": ("tcgen05, resident weights" if H in (32, 64) else
+                                            ("tcgen05, weights streamed from L2 (TMA)" if H in (128, 256) else
+                                             "cuda-core, L2 weights")),
                               "rollout_ms": round(roll, 3), "rollout_env_steps_per_s": N * T / roll * 1e3,
                               "us_per_lockstep_iteration": round(1e3 * roll / T, 2),
                               "iteration_ms": round(full, 3), "ppo_env_steps_per_s": N * T / full * 1e3}), flush=True)

@@ -3,7 +3,7 @@
 // (H = 256: 4H x (H + 16) x (hi + lo) fp16 = 1.1 MB).
 //
 // One persistent CTA per SM, tile = 128 windows (TMEM lane = window), 16 compute warps (TMEM lane quarter x four column
-// groups) + one warp whose lane 0 is TMA producer and MMA issuer.  Per cell step
+// groups) + one warp whose lane 0 issues the MMAs + one warp whose lane 0 is the TMA producer.  Per cell step
 //
 //     gates[128][4H] = [h_{t-1} (H) | x_t | 1 | 0 x 14] (K = H + 16)  .  Wg[4H][K]^T          (kind::f16, hi/lo split)
 //
@@ -12,7 +12,7 @@
 //   * A = the tile's h operand (hi + lo, 128 x K) stays RESIDENT in shared memory for the whole step (H = 256: 139 KB);
 //   * B = the chunk's weights, pre-split and pre-arranged in operand layout by lstm_stream_prep_kernel, arrive as
 //     cp.async.bulk (TMA) copies of 32 KB per (column chunk, K chunk of 64) through a two-stage ring
-//     (mbarrier complete_tx / tcgen05.commit);
+//     (mbarrier complete_tx / tcgen05.commit) filled by a producer thread of its own;
 //   * two TMEM accumulators of 128 columns ping-pong: while the tensor core works on chunk c + 1, the compute warps run
 //     the activations of chunk c (7 MUFU per unit: 1792 cycles per chunk, hidden behind the chunk's
 //     3 x (K / 16) x 64 = 3264 MMA cycles at H = 256);
@@ -20,8 +20,12 @@
 //   * the new h of a chunk cannot overwrite A while later chunks of the same step still read the old h, and 128 KB of
 //     pending h fit neither registers nor a second A buffer: it goes to a per-CTA scratch in global memory (L2 resident,
 //     written in operand layout) and is copied back into A once the step's last MMA has completed.
-// Bound: the tensor pipe (three MMAs per product for the fp32-grade split), then the L2 -> shared-memory stream
-// (4H x K x 4 B per tile and step = 42 B per cycle and SM at the MMA-bound rate for H = 256).
+// Bound: the L2 -> shared-memory weight stream.  Every SM pulls the whole 4H x K x 4 B of weights through its ring in
+// every cell step: at the MMA-bound rate (8 chunks x 3264 cycles per step and tile at H = 256) that is 42 B per cycle
+// and SM = 6.2 KB per cycle for the chip, the L2's whole delivery rate, so the tensor pipe runs at about a third of
+// its rate (measured, 4096 x 256 windows: H = 256 37.4 ms = 2.8e7 env-steps/s with the rollout, H = 128 14.0 ms;
+// round 1 on the CUDA cores: 2400 ms / 4.3e5).  What would lift it: a 2- or 4-CTA cluster that multicasts each
+// chunk (one L2 read per cluster), or cta_group::2 pairs that hold half of B each.
 // FLOP per window 2 * 4H * (1 + H) * W as in lstm_kernels.cu.
 #include "lstm_tile.cuh"
 #include "tc_gemm.cuh"
@@ -29,17 +33,29 @@
 namespace plume {
 
 constexpr int kLsComputeThreads = 512;
-constexpr int kLsThreads = kLsComputeThreads + 32;
-constexpr int kLsFullSlots = 1024;          // 16-byte slots of a [128][64] fp16 operand chunk (16 KB)
+constexpr int kLsThreads = kLsComputeThreads + 64;     // + the MMA issuer warp + the TMA producer warp
+constexpr int kLsFullSlots = 1024;          // 16-byte slots of a [128][64] fp16 chunk of the A operand (16 KB)
 constexpr int kLsTailSlots = 256;           // of the [128][16] tail chunk (x, 1, zeros): 4 KB
-constexpr uint32_t kLsStageBytes = 2 * kLsFullSlots * 16;      // hi + lo of one B chunk
+// B travels in [128][kLsBK] chunks (hi + lo per ring stage, 64 KB of ring in all), filled by a producer thread of its
+// own: the thread that waits for a stage to drain must not be the one that issues the MMAs (with one thread in both
+// roles every chunk waited for the completion of the previous chunk's MMAs).  Measured at H = 256, 4096 x 256 windows
+// incl. the rollout loop: one thread, 2 x 32 KB 42.9 ms; one thread, 4 x 16 KB 56.1 ms; own producer, 4 x 16 KB
+// 45.2 ms; own producer, 2 x 32 KB 37.4 ms (fewer, larger chunks: fewer mbarrier round trips per byte)
+#ifndef PLUME_LS_BK
+#define PLUME_LS_BK 64
+#endif
+constexpr int kLsBK = PLUME_LS_BK;          // K width of a B chunk: 64 (two ring stages of 32 KB) or 32 (four of 16 KB)
+constexpr int kLsBSlots = 16 * kLsBK;       // 16-byte slots of a [128][kLsBK] fp16 chunk of the B operand
+constexpr int kLsStages = 128 / kLsBK;
+constexpr uint32_t kLsStageBytes = 2 * kLsBSlots * 16;         // hi + lo of one B chunk
 
 template <int H>
 struct LsShape {
-    static constexpr int KCF = H / 64;                   // full K chunks (h part)
+    static constexpr int KCF = H / 64;                   // full K chunks of A (h part)
+    static constexpr int KB = H / kLsBK;                 // K chunks of B per column chunk (+ the tail)
     static constexpr int NC = 4 * H / 128;               // column chunks of 128 gate columns = 32 units
     static constexpr int a_slots = KCF * 2 * kLsFullSlots + 2 * kLsTailSlots;
-    static constexpr int w_chunk_slots = KCF * 2 * kLsFullSlots + 2 * kLsTailSlots;   // weights of one column chunk
+    static constexpr int w_chunk_slots = KB * 2 * kLsBSlots + 2 * kLsTailSlots;       // weights of one column chunk
     static constexpr int scratch_slots = KCF * 2 * kLsFullSlots;                       // per CTA
 };
 
@@ -47,8 +63,8 @@ template <int H>
 struct LsSmem {                                          // offsets in 16-byte slots, then floats
     using S = LsShape<H>;
     static constexpr int a = 0;                                  // [KCF][hi | lo][1024], then tail [hi | lo][256]
-    static constexpr int ring = a + S::a_slots;                  // [2 stages][hi | lo][1024]
-    static constexpr int f_base = (ring + 2 * 2 * kLsFullSlots) * 4;
+    static constexpr int ring = a + S::a_slots;                  // [kLsStages][hi | lo][kLsBSlots]
+    static constexpr int f_base = (ring + kLsStages * 2 * kLsBSlots) * 4;
     static constexpr int xs = f_base;                            // [20 steps][128] window values
     static constexpr int hd = xs + 20 * 128;                     // [2][H] head weights, [4]
     static constexpr int exch = hd + 2 * H + 4;                  // [4 column groups][128][2]
@@ -86,7 +102,7 @@ __device__ __forceinline__ void ls_tmem_st8(uint32_t taddr, const float* v) {
 }
 
 // ---- weights -> operand chunks (once per launch) ---------------------------------------------------------------
-// w_ops[cc][ K chunk kc < KCF: hi 1024 slots, lo 1024 slots ; tail: hi 256, lo 256 ]; row n of chunk cc = gate
+// w_ops[cc][ K chunk kc < H / kLsBK: hi, lo of kLsBSlots slots each ; tail: hi 256, lo 256 ]; row n of chunk cc = gate
 // g = n & 3 of unit 32 cc + (n >> 2); K = [w_hh row (H) | w_ih | b_ih + b_hh | 0 x 14]
 template <int H>
 __global__ void __launch_bounds__(256) lstm_stream_prep_kernel(LtArgs a, uint4* __restrict__ w_ops) {
@@ -113,15 +129,16 @@ __global__ void __launch_bounds__(256) lstm_stream_prep_kernel(LtArgs a, uint4* 
     tc::split_f16x8(w0, w1, 1.0f, hi, lo);
     uint4* chunk = w_ops + (size_t)cc * S::w_chunk_slots;
     if (unit < H / 8) {
-        const int kc = unit >> 3, u = unit & 7;
-        const int f = (n >> 3) * 64 + u * 8 + (n & 7);
-        chunk[kc * 2 * kLsFullSlots + f] = hi;
-        chunk[kc * 2 * kLsFullSlots + kLsFullSlots + f] = lo;
+        constexpr int upc = kLsBK / 8;                           // 16-byte units per chunk row
+        const int kc = unit / upc, u = unit % upc;
+        const int f = (n >> 3) * (upc * 8) + u * 8 + (n & 7);
+        chunk[kc * 2 * kLsBSlots + f] = hi;
+        chunk[kc * 2 * kLsBSlots + kLsBSlots + f] = lo;
     } else {
         const int u = unit - H / 8;
         const int f = (n >> 3) * 16 + u * 8 + (n & 7);
-        chunk[S::KCF * 2 * kLsFullSlots + f] = hi;
-        chunk[S::KCF * 2 * kLsFullSlots + kLsTailSlots + f] = lo;
+        chunk[S::KB * 2 * kLsBSlots + f] = hi;
+        chunk[S::KB * 2 * kLsBSlots + kLsTailSlots + f] = lo;
     }
 }
 
@@ -131,7 +148,7 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
     using S = LsShape<H>;
     using L = LsSmem<H>;
     extern __shared__ __align__(128) float sm[];
-    __shared__ uint64_t full[2], empty[2], acc_full[2], acc_free[2], a_ready;
+    __shared__ uint64_t full[kLsStages], empty[kLsStages], acc_full[2], acc_free[2], a_ready;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wq = warp & 3, cg = (warp >> 2) & 3;    // TMEM lane quarter / column group (8 of a chunk's 32 units)
@@ -146,10 +163,10 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
     uint4* const scratch = scratch_all + (size_t)blockIdx.x * S::scratch_slots;
 
     if (tid == 0) {
-        tc::mbar_init(&full[0], 1);
-        tc::mbar_init(&full[1], 1);
-        tc::mbar_init(&empty[0], 1);
-        tc::mbar_init(&empty[1], 1);
+        for (int q = 0; q < kLsStages; ++q) {
+            tc::mbar_init(&full[q], 1);
+            tc::mbar_init(&empty[q], 1);
+        }
         tc::mbar_init(&acc_full[0], 1);
         tc::mbar_init(&acc_full[1], 1);
         tc::mbar_init(&acc_free[0], 16);
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
 
     const int env_tiles = (N + 127) / 128;
     const long long tiles = (long long)env_tiles * a.horizon;
-    uint32_t item = 0;            // issuer: B chunks streamed so far
+    uint32_t item = 0;            // producer / issuer: B chunks streamed / consumed so far (each role counts its own)
     uint32_t chunk_q = 0;         // column chunks processed so far (both roles count them identically)
     uint32_t steps_done = 0;      // cell steps so far (phase of a_ready)
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -199,52 +216,59 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
         const bool full_w = fill >= W;                             // meaningful for tid < 128 (row = tid)
         const bool any = __syncthreads_or(full_w);                 // also publishes xs
         float pp = 0.0f, ps = 0.0f;
-        if (any && warp == kLsComputeThreads / 32) {
-            // ---- TMA producer + MMA issuer (one thread) ---------------------------------------------------------
+        if (any && warp == kLsComputeThreads / 32 + 1) {
+            // ---- TMA producer (one thread): the weight chunks of the W steps, in the order the issuer consumes them -----
             if (lane == 0) {
-                auto load_item = [&](uint32_t it) {                // stream B chunk number `it` into its ring stage
-                    const uint32_t st = it & 1u, use = it >> 1;
+                constexpr uint32_t per_step = (uint32_t)(S::NC * (S::KB + 1));
+                for (uint32_t n = 0; n < (uint32_t)W * per_step; ++n, ++item) {
+                    const uint32_t st = item % kLsStages, use = item / kLsStages;
                     if (use >= 1) tc::mbar_wait(&empty[st], (use - 1) & 1u);
-                    const uint32_t within = it % (uint32_t)(S::NC * (S::KCF + 1));
-                    const uint32_t cc = within / (S::KCF + 1), kc = within % (S::KCF + 1);
-                    const bool tail = kc == (uint32_t)S::KCF;
-                    const uint4* src = w_ops + (size_t)cc * S::w_chunk_slots + (size_t)kc * 2 * kLsFullSlots;
+                    const uint32_t within = n % per_step;
+                    const uint32_t cc = within / (S::KB + 1), kc = within % (S::KB + 1);
+                    const bool tail = kc == (uint32_t)S::KB;
+                    const uint4* src = w_ops + (size_t)cc * S::w_chunk_slots + (size_t)kc * 2 * kLsBSlots;
                     const uint32_t bytes = tail ? 2u * kLsTailSlots * 16u : kLsStageBytes;
                     const uint32_t mb = tc::smem_u32(&full[st]);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(tc::smem_u32(ring + st * 2 * kLsFullSlots)), "l"(src), "r"(bytes), "r"(mb) : "memory");
-                };
-                const uint32_t per_step = (uint32_t)(S::NC * (S::KCF + 1));
+                                 ::"r"(tc::smem_u32(ring + st * 2 * kLsBSlots)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+                }
+            }
+        } else if (any && warp == kLsComputeThreads / 32) {
+            // ---- MMA issuer (one thread) --------------------------------------------------------------------------------
+            if (lane == 0) {
+                constexpr uint32_t per_step = (uint32_t)(S::NC * (S::KB + 1));
                 for (int step = 0; step < W; ++step) {
-                    if (step == 0 && item == 0) load_item(0);      // very first chunk of the kernel
                     tc::mbar_wait(&a_ready, steps_done & 1u);      // A of this step is in shared memory
                     ++steps_done;
                     tc::tc_fence_after();
                     for (uint32_t w = 0; w < per_step; ++w, ++item) {
-                        load_item(item + 1);                       // prefetch (the weights repeat every step)
-                        const uint32_t st = item & 1u;
-                        const uint32_t cc = w / (S::KCF + 1), kc = w % (S::KCF + 1);
-                        const bool tail = kc == (uint32_t)S::KCF;
+                        const uint32_t st = item % kLsStages;
+                        const uint32_t cc = w / (S::KB + 1), kc = w % (S::KB + 1);
+                        (void)cc;
+                        const bool tail = kc == (uint32_t)S::KB;
                         const uint32_t b = chunk_q & 1u, use = chunk_q >> 1;
                         if (kc == 0 && use >= 1) {                 // the accumulator's previous contents have been read
                             tc::mbar_wait(&acc_free[b], (use - 1) & 1u);
                             tc::tc_fence_after();
                         }
-                        tc::mbar_wait(&full[st], (item >> 1) & 1u);
+                        tc::mbar_wait(&full[st], (item / kLsStages) & 1u);
                         tc::tc_fence_after();
-                        const uint32_t sbo = tail ? 256u : 1024u;
-                        const uint32_t ah = tc::smem_u32(tail ? a_tail_hi : A + kc * 2 * kLsFullSlots);
-                        const uint32_t al = tc::smem_u32(tail ? a_tail_lo : A + kc * 2 * kLsFullSlots + kLsFullSlots);
-                        const uint32_t bh = tc::smem_u32(ring + st * 2 * kLsFullSlots);
-                        const uint32_t bl = bh + (tail ? kLsTailSlots : kLsFullSlots) * 16u;
-                        const int ksteps = tail ? 1 : 4;
+                        // A: the K chunk of 64 that holds column kc * kLsBK, plus 256 bytes per K step of 16 inside it
+                        const uint32_t a_sbo = tail ? 256u : 1024u, b_sbo = tail ? 256u : (uint32_t)(kLsBK / 8) * 128u;
+                        const uint32_t k0 = kc * (uint32_t)kLsBK;
+                        const uint32_t ah = tail ? tc::smem_u32(a_tail_hi)
+                                                 : tc::smem_u32(A + (k0 >> 6) * 2 * kLsFullSlots) + ((k0 & 63u) >> 4) * 256u;
+                        const uint32_t al = tail ? tc::smem_u32(a_tail_lo) : ah + kLsFullSlots * 16u;
+                        const uint32_t bh = tc::smem_u32(ring + st * 2 * kLsBSlots);
+                        const uint32_t bl = bh + (tail ? kLsTailSlots : kLsBSlots) * 16u;
+                        const int ksteps = tail ? 1 : kLsBK / 16;
                         for (int j = 0; j < ksteps; ++j) {
                             const uint32_t off = j * 2 * tc::kLBO;
-                            const uint64_t dah = tc::make_smem_desc(ah + off, tc::kLBO, sbo);
-                            const uint64_t dal = tc::make_smem_desc(al + off, tc::kLBO, sbo);
-                            const uint64_t dbh = tc::make_smem_desc(bh + off, tc::kLBO, sbo);
-                            const uint64_t dbl = tc::make_smem_desc(bl + off, tc::kLBO, sbo);
+                            const uint64_t dah = tc::make_smem_desc(ah + off, tc::kLBO, a_sbo);
+                            const uint64_t dal = tc::make_smem_desc(al + off, tc::kLBO, a_sbo);
+                            const uint64_t dbh = tc::make_smem_desc(bh + off, tc::kLBO, b_sbo);
+                            const uint64_t dbl = tc::make_smem_desc(bl + off, tc::kLBO, b_sbo);
                             const uint32_t d = tmem + 128u * b;
                             tc::mma_f16(d, dal, dbh, idesc, (kc == 0 && j == 0) ? 0u : 1u);
                             tc::mma_f16(d, dah, dbl, idesc, 1u);
@@ -257,8 +281,6 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
                         }
                     }
                 }
-                // the prefetch ran one chunk ahead: consume it so that the ring state stays consistent
-                // (the next tile / the end of the kernel starts with chunk `item` already in flight)
             }
         } else if (any) {
             // ---- compute warps --------------------------------------------------------------------------------------
@@ -364,8 +386,6 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
                 for (int k = 0; k < W; ++k) a.window_out[(size_t)(env0 + tid) * W + k] = xs[k * 128 + tid];
         }
     }
-    // the producer ran one chunk ahead: wait for that copy before the shared memory goes away
-    if (warp == kLsComputeThreads / 32 && lane == 0 && item > 0) tc::mbar_wait(&full[item & 1u], (item >> 1) & 1u);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem);

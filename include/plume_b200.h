@@ -61,6 +61,15 @@ extern "C" {
                                      * counters, reached, done) stay the float64 arithmetic of environment.py, the
                                      * concentration / tke observation entries and the reward terms are float32
                                      * (fp32 rel 1e-5 bar instead of bit-exact float64 rewards) */
+/* Evaluator stop tests inside plume_rollout (they end the episode like `done`; the kernel without an in-loop LSTM head
+ * only).  STOP_FIXED: PPOV1.1/evaluate_model.py:25-37 -- std of the last 10 positions < 2 px and the (sic, twice-scaled)
+ * concentration above 0.8 CONC_PEAK, from step 10 on.  STOP_THRESHOLD: ThresholdController.should_stop
+ * (PPOV2.0/evaluate_with_lstm.py:28-37) against the per-env threshold in buf.stop_threshold (NaN = none yet) -- from
+ * step 20 on, concentration or mean of the last 10 >= threshold; the test of the segment's LAST step is left to the host,
+ * which refreshes the threshold from that step's sample first (:89-92).  Bits 16..31 of flags: step guard (an episode
+ * ends when step_count reaches it; evaluate_model.py:52 uses 2000), 0 = none. */
+#define PLUME_FLAG_STOP_FIXED 32u
+#define PLUME_FLAG_STOP_THRESHOLD 64u
 
 /* Constants of one reference version (PPOV x/config.py; environment.py). HOST struct. */
 typedef struct plume_env_config {
@@ -272,6 +281,9 @@ typedef struct plume_rollout_buffers {    /* DEVICE pointers, [T][N] row-major u
     float* src_out;        /* [T][N][2] source_pos of the episode, written at its last transition only */
     float* conc_out;       /* [T][N] conc_field[int(x), int(y)] at the position after the step, as float32: what the
                             * reference driver logs per step (train_ppo2.0.py:167-173); may be NULL */
+    double* eval_ring;     /* [N][10] evaluator stop tests: the last 10 samples of every env, oldest first, carried across
+                            * segments (STOP_THRESHOLD: concentrations; STOP_FIXED: (x, y) float pairs); may be NULL */
+    const double* stop_threshold;   /* [N] STOP_THRESHOLD: 0.95 x predicted source concentration, NaN = none yet */
     uint8_t* flag_code;    /* [T][N] bit 0 = done, bit 1 = reached: what the curriculum (and its multi-GPU
                             * all-gather, 1 B per transition) consumes; may be NULL */
 } plume_rollout_buffers;
@@ -484,6 +496,15 @@ int plume_curriculum_update_packed(const uint8_t* flag_code, int32_t horizon, in
                                    double* state, double* curriculum, double initial_radius, double min_radius,
                                    double radius_decay, double success_threshold, int32_t window,
                                    double decay_factor, double* window_radius_out, void* stream);
+
+/* ---- N1: evaluator bookkeeping (evaluate_with_lstm.py:83-113 of PPOV2.1 / PPOV2.0, evaluate_model.py:70-82) ----------
+ * Records, for every env that has not finished its evaluation episode yet, the first transition of the segment that ends
+ * it (stop_flag or done): steps = base_step + t + 1, early = stopped by the stop test, stop_step, deviation =
+ * ||agent_pos - source_pos|| there (buf->src_dist).  pending_threshold (may be NULL): the STOP_THRESHOLD test of the
+ * segment's last step, evaluated here against the refreshed threshold on eval_ring. */
+int plume_eval_collect(const plume_rollout_buffers* buf, int32_t horizon, int32_t n_envs, int32_t base_step,
+                       uint8_t* finished, int32_t* steps, uint8_t* early, int32_t* stop_step, double* deviation,
+                       const double* pending_threshold, void* stream);
 
 /* ---- N2: trajectory / per-episode logging (training_data.nc + training_results.csv layouts) ------------------
  * NetCDFWriter.write_episode_data (PPOV2.1/model.py:351-419) and the per-episode statistics of

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(L.EnvConfig) == 4 * 4 + 9 * 8 + 8 + 8
     assert C.sizeof(L.EnvState) == 8 + 20 * 8
     assert C.sizeof(L.LstmParams) == 16 + 8 * 8
-    assert C.sizeof(L.RolloutBuffers) == 26 * 8
+    assert C.sizeof(L.RolloutBuffers) == 28 * 8
     assert C.sizeof(L.PpoBatch) == 8 * 8
     header = open(os.path.join(ROOT, "include", "plume_b200.h")).read()
     for name, (off, _) in L.MLP_OFFSETS.items():

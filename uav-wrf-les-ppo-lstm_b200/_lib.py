@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libplume_b200.so")
 OBS_DIM, NUM_ACTIONS, INFO_DIM, VISIT_STRIDE = 6, 5, 5, 104
 INFO_KEYS = ("concentration_reward", "explore_reward", "move_penalty", "tke_penalty", "boundary_penalty")
 FLAG_AUTO_RESET, FLAG_GREEDY, FLAG_STOP_TERMINATES, FLAG_DEFER_STOP_HEAD, FLAG_FAST_REWARD = 1, 2, 4, 8, 16
+FLAG_STOP_FIXED, FLAG_STOP_THRESHOLD = 32, 64
 
 # flat MLP parameter layout (include/plume_b200.h)
 MLP_OFFSETS = {
@@ -64,7 +65,7 @@ class RolloutBuffers(C.Structure):
                                    "stop_prob", "stop_flag", "peak_pred", "trend", "info", "episode_idx",
                                    "forced_actions", "step_noise", "noise_out", "conc_window", "window_fill",
                                    "last_obs", "conc_sample", "fill_t", "src_dist", "pos_out", "src_out", "conc_out",
-                                   "flag_code")]
+                                   "eval_ring", "stop_threshold", "flag_code")]
 
 
 class PpoBatch(C.Structure):
@@ -155,6 +156,7 @@ _SIGNATURES = {
     "plume_tc_gemm_f16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "plume_curriculum_update": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.c_double,
                                           C.c_double, C.c_double, C.c_int32, C.c_double, _vp]),
+    "plume_eval_collect": (C.c_int, [_P(RolloutBuffers), C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plume_trajectory_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "plume_trajectory_log": (C.c_int, [_P(TrajLog), _P(RolloutBuffers), C.c_int32, _vp, C.c_int32, _vp, C.c_double,
                                        _vp, C.c_int64, _vp]),

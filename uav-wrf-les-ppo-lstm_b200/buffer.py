@@ -37,7 +37,7 @@ class PPOBuffer:
         # inputs of the deferred stop head (csrc/lstm_kernels.cu::stop_head_segment_kernel)
         self.conc_sample = z(torch.float32, T, N) if with_stop else None
         self.fill_t = z(torch.uint8, T, N) if with_stop else None
-        self.src_dist = z(torch.float64, T, N) if (with_stop and with_trend) else None
+        self.src_dist = z(torch.float64, T, N) if ((with_stop and with_trend) or with_trajectory) else None
         # trajectory logging (trajectory_log.TrajectoryLogger): post-step positions, source at the episode's last step
         self.pos_out = z(torch.float32, T, N, 2) if with_trajectory else None
         self.src_out = z(torch.float32, T, N, 2) if with_trajectory else None
@@ -107,11 +107,12 @@ class PPOBuffer:
 
     # -- C view -----------------------------------------------------------------------------
     def c_rollout_buffers(self, conc_window, window_fill, last_obs, forced_actions=None, step_noise=None,
-                          noise_out=None) -> _lib.RolloutBuffers:
+                          noise_out=None, eval_ring=None, stop_threshold=None) -> _lib.RolloutBuffers:
         p = _lib.ptr
         return _lib.RolloutBuffers(p(self.obs), p(self.actions), p(self.rewards), p(self.values), p(self.log_probs),
                                    p(self.dones), p(self.reached), p(self.stop_prob), p(self.stop_flag),
                                    p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
                                    p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
                                    p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist),
-                                   p(self.pos_out), p(self.src_out), p(self.conc_out), p(self.flag_code))
+                                   p(self.pos_out), p(self.src_out), p(self.conc_out), p(eval_ring), p(stop_threshold),
+                                   p(self.flag_code))

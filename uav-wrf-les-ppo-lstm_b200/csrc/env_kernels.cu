@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(256) generate_fields_kernel(Cfg c, plume_env_s
 // (shared with every other consumer of the field stream through box_muller), rows mapped to blockIdx.x.
 struct FieldF32Cfg {
     float peak, ti, exp_scale;     // exp_scale = -log2(e) / (2 sigma^2)
+    FieldKeys keys;                // the field stream's Philox round keys (k + r W), bumped on the host
 };
 
 // float copies of 0.3*sin(0.05 x) and cos(0.07 y) (double -> float conversions run on the XU pipe, which this
@@ -149,42 +150,48 @@ __global__ void wave_tables_f32_kernel(const double* __restrict__ sin_tab, const
     }
 }
 
-__global__ void __launch_bounds__(128) generate_fields_f32_kernel(Cfg c, FieldF32Cfg fc, plume_env_state st,
-                                                                  const int32_t* env_list) {
-    const int x = blockIdx.x, li = blockIdx.y;
-    const int y0 = 4 * threadIdx.x;
-    if (y0 >= c.G) return;
+// One CTA per (kK1Rows rows, env); a thread owns EIGHT consecutive cells of a row (two Philox4x32-7 calls, two 16-byte
+// stores per field): the per-thread setup (row terms, env state, addresses) is paid once per eight cells, and a CTA is
+// large enough (512 threads) that the grid is not bound by CTA launches (one row per CTA: 512 000 CTAs of two warps
+// for 1024 envs ran no faster with 20 % fewer instructions).
+constexpr int kK1Rows = 8;
+__global__ void __launch_bounds__(64 * kK1Rows) generate_fields_f32_kernel(Cfg c, FieldF32Cfg fc, plume_env_state st,
+                                                                           const int32_t* env_list) {
+    const int x = blockIdx.x * kK1Rows + threadIdx.y, li = blockIdx.y;
+    const int y0 = 8 * threadIdx.x;
+    if (y0 >= c.G || x >= c.G) return;
     const int env = env_list ? env_list[li] : li;
     const uint32_t gid = (uint32_t)(st.env_id_base + env);
     const uint32_t episode = (uint32_t)st.episode_idx[env];
     const float sx = (float)st.src_x[env], sy = (float)st.src_y[env];
     const int cell0 = x * c.G + y0;
-
-    float z[4], u[4];
-    field_noise_quad(c, gid, episode, (uint32_t)(cell0 >> 2), z, u);      // one Philox4x32-7 call for the four cells
-
     const float ddx = (float)x - sx;
     const float ddx2 = ddx * ddx;
     const float s3 = g_wave_sin_f32[x];
-    const float4 cosy4 = *reinterpret_cast<const float4*>(g_wave_cos_f32 + y0);
-    const float cosy[4] = {cosy4.x, cosy4.y, cosy4.z, cosy4.w};
-    const float fy0 = (float)y0 - sy;                 // one conversion, the other three by addition
-    float conc[4], tke[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float ddy = fy0 + (float)k;
-        const float arg = fmaf(ddy, ddy, ddx2) * fc.exp_scale;
-        // far from the source the Gaussian underflows: skip the ex2 (warps are 128 consecutive cells of one
-        // row, so the branch is uniform for most of the field)
-        const float base = (arg > -126.0f) ? fc.peak * exp2f_approx(arg) : 0.0f;
-        tke[k] = fc.ti * (fmaf(0.2f, u[k], fmaf(s3, cosy[k], fabsf(z[k]))));
-        conc[k] = fminf(fmaxf(base + tke[k], 0.0f), fc.peak);
-    }
     const size_t off = (size_t)env * c.G * c.G + cell0;
-    __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(st.conc_field) + off),
-           make_float4(conc[0], conc[1], conc[2], conc[3]));
-    __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(st.tke_field) + off),
-           make_float4(tke[0], tke[1], tke[2], tke[3]));
+    float* const conc_p = reinterpret_cast<float*>(st.conc_field) + off;
+    float* const tke_p = reinterpret_cast<float*>(st.tke_field) + off;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (y0 + 4 * h >= c.G) break;                  // G % 8 == 4: the row's last thread owns one quad
+        float z[4], u[4];
+        field_noise_from_words(philox4x32_field((uint32_t)(cell0 >> 2) + h, episode, gid, kTagField, fc.keys), z, u);
+        const float4 cosy4 = *reinterpret_cast<const float4*>(g_wave_cos_f32 + y0 + 4 * h);
+        const float cosy[4] = {cosy4.x, cosy4.y, cosy4.z, cosy4.w};
+        const float fy0 = (float)(y0 + 4 * h) - sy;       // one conversion, the other three by addition
+        float conc[4], tke[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ddy = fy0 + (float)k;
+            const float arg = fmaf(ddy, ddy, ddx2) * fc.exp_scale;
+            // far from the source the Gaussian underflows: skip the ex2
+            const float base = (arg > -126.0f) ? fc.peak * exp2f_approx(arg) : 0.0f;
+            tke[k] = fc.ti * (fmaf(0.2f, u[k], fmaf(s3, cosy[k], fabsf(z[k]))));
+            conc[k] = fminf(fmaxf(base + tke[k], 0.0f), fc.peak);
+        }
+        __stcs(reinterpret_cast<float4*>(conc_p + 4 * h), make_float4(conc[0], conc[1], conc[2], conc[3]));
+        __stcs(reinterpret_cast<float4*>(tke_p + 4 * h), make_float4(tke[0], tke[1], tke[2], tke[3]));
+    }
 }
 
 // dump-only variant (no field pointers needed): the draws of the listed envs
@@ -443,8 +450,10 @@ extern "C" int plume_generate_fields(const plume_env_config* cfg, const plume_en
             fc.peak = (float)c.conc_peak;
             fc.ti = (float)c.ti;
             fc.exp_scale = (float)(-1.4426950408889634 / c.two_sigma_sq);
+            fc.keys = make_field_keys(c.k0, c.k1);
             wave_tables_f32_kernel<<<(c.G + 255) / 256, 256, 0, s>>>(st->sin_tab, st->cos_tab, c.G);
-            generate_fields_f32_kernel<<<dim3((unsigned)c.G, (unsigned)n_list), 128, 0, s>>>(c, fc, *st, env_list);
+            generate_fields_f32_kernel<<<dim3((unsigned)((c.G + kK1Rows - 1) / kK1Rows), (unsigned)n_list), dim3(64, kK1Rows), 0,
+                                         s>>>(c, fc, *st, env_list);
         } else {
             generate_fields_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(c, *st, env_list, bpe, z_out, u_out);
         }

@@ -292,6 +292,39 @@ PLUME_HD void box_muller_pair(uint32_t radius20, uint32_t angle16, float& z0, fl
     z0 = rad * c;
     z1 = rad * s;
 }
+// Philox with the round keys k + r * W precomputed (K1: the key bumps are 2 of the ~10 instructions of a round)
+struct FieldKeys {
+    uint32_t k[2 * kFieldRounds];
+};
+PLUME_HD FieldKeys make_field_keys(uint32_t k0, uint32_t k1) {
+    FieldKeys f;
+    for (int r = 0; r < kFieldRounds; ++r) {
+        f.k[2 * r] = k0 + (uint32_t)r * kPhiloxW0;
+        f.k[2 * r + 1] = k1 + (uint32_t)r * kPhiloxW1;
+    }
+    return f;
+}
+PLUME_HD U4 philox4x32_field(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const FieldKeys& fk) {
+#pragma unroll
+    for (int r = 0; r < kFieldRounds; ++r) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ fk.k[2 * r];
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ fk.k[2 * r + 1];
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+    return U4{c0, c1, c2, c3};
+}
+PLUME_HD void field_noise_from_words(const U4& r, float* z, float* u) {
+    box_muller_pair(r.x >> 12, r.z & 0xFFFFu, z[0], z[1]);
+    box_muller_pair(r.y >> 12, r.z >> 16, z[2], z[3]);
+    u[0] = field_unit_bits(r.x & 0xFFFu, 12);
+    u[1] = field_unit_bits(r.y & 0xFFFu, 12);
+    u[2] = field_unit_bits(r.w & 0xFFFu, 12);
+    u[3] = field_unit_bits((r.w >> 12) & 0xFFFu, 12);
+}
 // the draws of the four cells 4q .. 4q+3 (cell = x*G + y) of (env, episode)
 PLUME_HD void field_noise_quad(const Cfg& c, uint32_t env_gid, uint32_t episode, uint32_t quad, float* z, float* u) {
     const U4 r = philox4x32<kFieldRounds>(quad, episode, env_gid, kTagField, c.k0, c.k1);

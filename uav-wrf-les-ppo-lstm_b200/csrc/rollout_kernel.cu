@@ -292,6 +292,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutAr
     const bool greedy = (a.flags & PLUME_FLAG_GREEDY) != 0;
     const bool defer = (a.flags & PLUME_FLAG_DEFER_STOP_HEAD) != 0;
     const bool fast = kSpec == 0 ? (a.flags & PLUME_FLAG_FAST_REWARD) != 0 : kSpec == 2;   // float32 reward terms
+    // evaluator stop tests (N1): 0 none, 1 fixed (PPOV1.1/evaluate_model.py:25-37), 2 threshold controller
+    // (PPOV2.0/evaluate_with_lstm.py:28-37); the last 10 samples of every env live in the window region
+    const int stop_mode = (a.flags & PLUME_FLAG_STOP_FIXED) ? 1 : ((a.flags & PLUME_FLAG_STOP_THRESHOLD) ? 2 : 0);
+    const int step_guard = (int)(a.flags >> 16);
+    double* const ring = reinterpret_cast<double*>(lsm);          // [10][32] doubles (or float pairs)
     const int tiles = (N + kTileM - 1) / kTileM;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         __syncthreads();            // weights loaded / the previous tile is finished everywhere
@@ -350,9 +355,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutAr
                 for (int k = 0; k < 6; ++k) sm[PolicySmem::x + slot * 8 + k] = o[k];
                 sm[PolicySmem::x + slot * 8 + 6] = 0.0f;
                 sm[PolicySmem::x + slot * 8 + 7] = 0.0f;
-                if (!defer)
+                if (stop_mode) {
+                    for (int k = 0; k < 10; ++k)
+                        ring[k * 32 + slot] = (owner && a.buf.eval_ring) ? a.buf.eval_ring[(size_t)env * 10 + k] : 0.0;
+                } else if (!defer) {
                     for (int k = 0; k < W; ++k)
                         win[k * 32 + slot] = (owner && a.buf.conc_window) ? a.buf.conc_window[(size_t)env * W + k] : 0.0f;
+                }
             }
         }
         for (int t = 0; t < a.horizon; ++t) {
@@ -414,11 +423,52 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutAr
                 if (a.buf.conc_sample) a.buf.conc_sample[i] = r.obs[2];
                 if (a.buf.fill_t) a.buf.fill_t[i] = (uint8_t)fill;
                 if (a.buf.src_dist) a.buf.src_dist[i] = r.distance;
-                if (!defer) {
+                bool stop = false;
+                if (stop_mode) {
+                    for (int k = 0; k + 1 < 10; ++k) ring[k * 32 + slot] = ring[(k + 1) * 32 + slot];
+                    if (stop_mode == 1) {
+                        // np.std(last 10 positions, axis=0).mean() < 2 (float32, like the reference's float32 arrays) and
+                        // info['concentration_reward'] * CONC_PEAK * CONC_PEAK (sic) > 0.8 * CONC_PEAK
+                        ring[9 * 32 + slot] = __hiloint2double(__float_as_int(e.py), __float_as_int(e.px));
+                        if (e.step >= 10) {
+                            float mx = 0.0f, my = 0.0f;
+                            for (int k = 0; k < 10; ++k) {
+                                const double v = ring[k * 32 + slot];
+                                mx += __int_as_float(__double2loint(v));
+                                my += __int_as_float(__double2hiint(v));
+                            }
+                            mx *= 0.1f;
+                            my *= 0.1f;
+                            float vx = 0.0f, vy = 0.0f;
+                            for (int k = 0; k < 10; ++k) {
+                                const double v = ring[k * 32 + slot];
+                                const float dx = __int_as_float(__double2loint(v)) - mx, dy = __int_as_float(__double2hiint(v)) - my;
+                                vx = fmaf(dx, dx, vx);
+                                vy = fmaf(dy, dy, vy);
+                            }
+                            const float pos_std = 0.5f * (sqrtf(vx * 0.1f) + sqrtf(vy * 0.1f));
+                            const float cur = r.conc_reward * (float)c.conc_peak * (float)c.conc_peak;
+                            stop = pos_std < 2.0f && cur > 0.8f * (float)c.conc_peak;
+                        }
+                    } else {
+                        ring[9 * 32 + slot] = cell_conc;
+                        // the segment's last step is tested by the host against the threshold refreshed from this very
+                        // sample (evaluate_with_lstm.py:89-92: update_threshold precedes should_stop)
+                        if (e.step >= 20 && t + 1 < a.horizon && a.buf.stop_threshold) {
+                            const double thr = a.buf.stop_threshold[env];
+                            if (thr == thr) {
+                                const int n = e.step < 10 ? e.step : 10;
+                                double sum = 0.0;
+                                for (int k = 10 - n; k < 10; ++k) sum += ring[k * 32 + slot];
+                                stop = cell_conc >= thr || sum / (double)n >= thr;
+                            }
+                        }
+                    }
+                } else if (!defer) {
                     for (int k = 0; k + 1 < W; ++k) win[k * 32 + slot] = win[(k + 1) * 32 + slot];
                     win[(W - 1) * 32 + slot] = r.obs[2];
                 }
-                const bool done = r.done;
+                const bool done = r.done || stop || (step_guard > 0 && e.step >= step_guard);
                 a.buf.actions[i] = action;
                 a.buf.rewards[i] = (float)r.reward;
                 a.buf.values[i] = value;
@@ -428,7 +478,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutAr
                 if (a.buf.flag_code) a.buf.flag_code[i] = (uint8_t)((done ? 1 : 0) | (r.reached ? 2 : 0));
                 if (!defer) {                       // no stop head in this kernel: its outputs are zero
                     if (a.buf.stop_prob) a.buf.stop_prob[i] = 0.0f;
-                    if (a.buf.stop_flag) a.buf.stop_flag[i] = 0;
+                    if (a.buf.stop_flag) a.buf.stop_flag[i] = stop ? 1 : 0;
                     if (a.buf.peak_pred) a.buf.peak_pred[i] = 0.0f;
                 }
                 if (a.buf.episode_idx) a.buf.episode_idx[i] = (int32_t)ep_of_transition;
@@ -443,7 +493,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutAr
                     inf[3 * (size_t)N] = r.tke_penalty;
                     inf[4 * (size_t)N] = (float)r.boundary_penalty;
                 }
-                if (a.buf.trend && !defer) {
+                if (a.buf.trend && !defer && !stop_mode) {
                     float tr[4] = {0, 0, 0, 0};
                     if (fill >= W && W >= 4) {
                         trend_from_last4(100.0 * (double)win[(W - 4) * 32 + slot], 100.0 * (double)win[(W - 3) * 32 + slot],
@@ -484,11 +534,51 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rollout_pipe_kernel(RolloutAr
                 a.st.cell_key[env] = cell_key_of(c, x, y, e.episode);
             }
             if (a.buf.window_fill) a.buf.window_fill[env] = fill;
-            if (a.buf.conc_window && !defer)
+            if (stop_mode) {
+                if (a.buf.eval_ring)
+                    for (int k = 0; k < 10; ++k) a.buf.eval_ring[(size_t)env * 10 + k] = ring[k * 32 + slot];
+            } else if (a.buf.conc_window && !defer) {
                 for (int k = 0; k < W; ++k) a.buf.conc_window[(size_t)env * W + k] = win[k * 32 + slot];
+            }
             if (a.buf.last_obs) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) a.buf.last_obs[(size_t)env * 6 + k] = sm[PolicySmem::x + slot * 8 + k];
+            }
+        }
+    }
+}
+
+// ---- N1: evaluator bookkeeping -----------------------------------------------------------------------------------------
+__global__ void eval_collect_kernel(plume_rollout_buffers buf, int T, int N, int base_step, uint8_t* finished, int32_t* steps,
+                                    uint8_t* early, int32_t* stop_step, double* deviation, const double* pending) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N || finished[n]) return;
+    for (int t = 0; t < T; ++t) {
+        const size_t i = (size_t)t * N + n;
+        const bool stop = buf.stop_flag && buf.stop_flag[i] != 0;
+        if (stop || buf.dones[i] != 0.0f) {
+            steps[n] = base_step + t + 1;
+            early[n] = stop ? 1 : 0;
+            stop_step[n] = stop ? base_step + t + 1 : 0;
+            deviation[n] = buf.src_dist[i];
+            finished[n] = 1;
+            return;
+        }
+    }
+    if (pending && buf.eval_ring) {       // ThresholdController.should_stop for the segment's last step
+        const int s = base_step + T;
+        const double thr = pending[n];
+        if (s >= 20 && thr == thr) {
+            const double* ring = buf.eval_ring + (size_t)n * 10;
+            const int cnt = s < 10 ? s : 10;
+            double sum = 0.0;
+            for (int k = 10 - cnt; k < 10; ++k) sum += ring[k];
+            if (ring[9] >= thr || sum / (double)cnt >= thr) {
+                steps[n] = s;
+                early[n] = 1;
+                stop_step[n] = s;
+                deviation[n] = buf.src_dist[(size_t)(T - 1) * N + n];
+                finished[n] = 1;
             }
         }
     }
@@ -566,6 +656,13 @@ extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state*
         PLUME_CHECK_ARG(buf->conc_sample && buf->fill_t && buf->window_fill,
                         "the deferred stop head needs conc_sample, fill_t and window_fill");
     }
+    if (flags & (PLUME_FLAG_STOP_FIXED | PLUME_FLAG_STOP_THRESHOLD)) {
+        PLUME_CHECK_ARG(!(lstm && lstm->hidden > 0 && !(flags & PLUME_FLAG_DEFER_STOP_HEAD)),
+                        "the evaluator stop tests run in the kernel without an in-loop LSTM head");
+        PLUME_CHECK_ARG(!(flags & PLUME_FLAG_DEFER_STOP_HEAD), "evaluator stop tests and a deferred stop head exclude each other");
+        PLUME_CHECK_ARG(buf->eval_ring, "evaluator stop tests need eval_ring");
+        PLUME_CHECK_ARG(!(flags & PLUME_FLAG_STOP_THRESHOLD) || buf->stop_threshold, "STOP_THRESHOLD needs stop_threshold");
+    }
     if (horizon <= 0 || st->n_envs <= 0) return 0;
     RolloutArgs a;
     a.c = make_cfg(*cfg, *st);
@@ -591,4 +688,16 @@ extern "C" int plume_rollout(const plume_env_config* cfg, const plume_env_state*
 #else
     return launch_rollout_pipe(a, as_stream(stream));
 #endif
+}
+
+extern "C" int plume_eval_collect(const plume_rollout_buffers* buf, int32_t horizon, int32_t n_envs, int32_t base_step,
+                                  uint8_t* finished, int32_t* steps, uint8_t* early, int32_t* stop_step, double* deviation,
+                                  const double* pending_threshold, void* stream) {
+    PLUME_CHECK_ARG(buf && finished && steps && early && stop_step && deviation, "null pointer");
+    PLUME_CHECK_ARG(buf->dones && buf->src_dist, "the evaluator bookkeeping needs dones and src_dist");
+    if (horizon <= 0 || n_envs <= 0) return 0;
+    eval_collect_kernel<<<(n_envs + 127) / 128, 128, 0, as_stream(stream)>>>(*buf, horizon, n_envs, base_step, finished, steps,
+                                                                           early, stop_step, deviation, pending_threshold);
+    PLUME_LAUNCH_CHECK();
+    return 0;
 }

@@ -10,10 +10,10 @@
                        the (sic, twice-scaled) concentration above 0.8 * CONC_PEAK; 2000-step guard;
                        success = deviation < current_radius.
 
-All envs of a round start together and run without auto-reset, so every live env is at the same step and the
-"every 10th step" / "from step 20" conditions are uniform; a finished env is masked out.  The policy forward,
-the env step, the field accessor and the LSTM heads are the library's kernels; the few ``[N, 10]`` ring-buffer
-updates in between are torch ops (evaluator glue, not the training hot path).
+All envs of a round start together, so every env's first episode is at the lockstep step count and the
+"every 10th step" / "from step 20" conditions are uniform.  Policy forward, env step and the stop test of every step
+run inside the fused rollout kernel (``plume_rollout`` with ``PLUME_FLAG_STOP_*`` / the in-loop LSTM head), the
+bookkeeping of where each env's episode ended in ``plume_eval_collect``; nothing returns to Python per step.
 """
 from __future__ import annotations
 
@@ -91,76 +91,89 @@ def evaluate_policy(model, stop: str | None = "lstm", head=None, version: str | 
     """Runs ``rounds`` x ``num_envs`` greedy evaluation episodes.  ``head``: ``PeakAndStopPredictor`` for
     ``stop="lstm"``, ``ConcentrationThresholdPredictor`` for ``stop="threshold"``.  ``trace`` (optional
     dict) receives the per-step tensors of the first round (positions, concentrations, stop flags) for
-    parity tests."""
+    parity tests.
+
+    A round is a sequence of FUSED rollout segments (policy + env step + stop test inside ``plume_rollout``, greedy
+    actions): all envs start their episode together, every env's FIRST episode of the round is what counts
+    (``plume_eval_collect`` records where it ends), and the round is over when every env has finished one -- envs
+    that finish earlier are auto-reset and keep running, their later transitions are ignored.  ``stop="lstm"`` runs
+    the in-loop LSTM head, ``"fixed"`` / ``"threshold"`` the kernel's own stop tests; the V2.0 controller's 3 x 128
+    LSTM is evaluated for all envs at once between the 10-step segments (its "every 10th step")."""
+    import ctypes as C
+
+    from . import _lib
+    from .rollout import RolloutEngine
     version = version or {"lstm": "2.1", "threshold": "2.0", "fixed": "1.1", None: "2.1"}[stop]
     cfg = config_for(version)
     dev = torch.device(device)
     if env is None:
         env = VecMethaneEnv(num_envs, device=dev, version=version, seed=seed, field_mode="procedural",
-                            plume_model=plume_model)
+                            plume_model=plume_model, auto_reset=True)
+    elif not env.auto_reset:
+        raise ValueError("evaluate_policy drives the fused rollout: the env must be built with auto_reset=True")
     N = env.num_envs
+    lib = _lib.load()
     max_steps = 2000 if stop == "fixed" else cfg.max_steps                  # PPOV1.1/evaluate_model.py:52
-    window = {"lstm": cfg.lstm_window, "threshold": 10, "fixed": 10, None: 1}[stop]
-    out = {k: [] for k in ("deviations", "steps", "success", "stopped_early", "stop_step")}
+    seg = {"lstm": 50, "threshold": 10, "fixed": 50, None: 50}[stop]
+    eng = RolloutEngine(env, model, head if stop == "lstm" else None, horizon=seg, with_info=True, with_trajectory=True)
     ctrl = ThresholdController(head, scaler, N, 10, dev) if stop == "threshold" else None
+    ring = torch.zeros(N, 10, dtype=torch.float64, device=dev) if stop in ("fixed", "threshold") else None
+    out = {k: [] for k in ("deviations", "steps", "success", "stopped_early", "stop_step")}
+    stream = lambda: torch.cuda.current_stream(dev).cuda_stream
     for rnd in range(rounds):
-        obs = env.reset().clone()
-        if ctrl is not None:
-            ctrl.reset()
-        alive = torch.ones(N, dtype=torch.bool, device=dev)
+        env.reset()
+        eng.reset_windows()
+        finished = torch.zeros(N, dtype=torch.uint8, device=dev)
         steps = torch.zeros(N, dtype=torch.int32, device=dev)
-        early = torch.zeros(N, dtype=torch.bool, device=dev)
+        early = torch.zeros(N, dtype=torch.uint8, device=dev)
         stop_step = torch.zeros(N, dtype=torch.int32, device=dev)
-        final_pos = torch.zeros(N, 2, dtype=torch.float32, device=dev)
-        conc_win = torch.zeros(N, window, dtype=torch.float64, device=dev)
-        pos_win = torch.zeros(N, 10, 2, dtype=torch.float32, device=dev)
-        for step in range(1, max_steps + 1):
-            action, _, _, _ = model.act(obs, env=env, greedy=True)                    # argmax, evaluate_with_lstm.py:65
-            obs, _, done, info = env.step(action)
-            obs = obs.clone()
-            pos = env.agent_pos
-            conc = env.conc_at(pos[:, 0].int(), pos[:, 1].int())             # conc_field[int(x), int(y)]
-            stop_now = torch.zeros(N, dtype=torch.bool, device=dev)
-            if stop == "lstm":
-                conc_win = torch.roll(conc_win, -1, dims=1)
-                conc_win[:, -1] = conc
-                if step >= window:                                           # evaluate_with_lstm.py:73-80
-                    _, prob = head((conc_win / 100.0).float())
-                    stop_now = prob > cfg.lstm_stop_threshold
-            elif stop == "threshold":
-                ctrl.push(conc)
-                if step % 10 == 0:                                           # PPOV2.0/evaluate_with_lstm.py:89-90
-                    ctrl.update_threshold()
-                stop_now = ctrl.should_stop(conc, step)
-            elif stop == "fixed":
-                pos_win = torch.roll(pos_win, -1, dims=1)
-                pos_win[:, -1] = pos
-                if step >= 10:                                               # PPOV1.1/evaluate_model.py:25-37
-                    pos_std = pos_win.std(dim=1, unbiased=False).mean(dim=1)
-                    current = info["concentration_reward"].double() * cfg.conc_peak * cfg.conc_peak
-                    stop_now = (pos_std < 2.0) & (current > 0.8 * cfg.conc_peak)
+        deviation = torch.zeros(N, dtype=torch.float64, device=dev)
+        radius_at_start = env.radius_t.clone()
+        thr = torch.full((N,), float("nan"), dtype=torch.float64, device=dev) if ctrl is not None else None
+        if ring is not None:
+            ring.zero_()
+        base = 0
+        while base < max_steps:
+            T = min(seg, max_steps - base)
+            buf = eng.collect(greedy=True, horizon=T, stop_terminates=(stop == "lstm"),
+                              defer_stop_head=False if stop == "lstm" else None,
+                              stop_mode=stop if stop in ("fixed", "threshold") else None,
+                              step_guard=max_steps if stop == "fixed" else 0, eval_ring=ring, stop_threshold=thr)
+            alive_before = finished == 0
+            pending = None
+            if ctrl is not None and base + T >= ctrl.min_activate_steps:       # update_threshold at every 10th step
+                scaled = (ring * ctrl.scale + ctrl.offset).float()             # FloatTensor(scaler.transform(window))
+                thr = ctrl.model(scaled.unsqueeze(-1), lengths=[ctrl.window_size] * N).double() * 0.95
+                pending = thr
+            cb = buf.c_rollout_buffers(None, None, None, eval_ring=ring)
+            with torch.cuda.device(dev):
+                _lib.check(lib.plume_eval_collect(C.byref(cb), T, N, base, finished.data_ptr(), steps.data_ptr(),
+                                                  early.data_ptr(), stop_step.data_ptr(), deviation.data_ptr(),
+                                                  _lib.ptr(pending), stream()), "plume_eval_collect")
             if trace is not None and rnd == 0:
-                for k, v in (("pos", pos), ("conc", conc), ("stop", stop_now), ("done", done), ("alive", alive),
-                             ("conc_reward", info["concentration_reward"]), ("action", action)):
-                    trace.setdefault(k, []).append(v.clone())
-            finish = alive & (done | stop_now)
-            steps = torch.where(finish, torch.full_like(steps, step), steps)
-            early = torch.where(finish, stop_now, early)
-            stop_step = torch.where(finish & stop_now, torch.full_like(stop_step, step), stop_step)
-            final_pos = torch.where(finish.unsqueeze(1), pos, final_pos)
-            alive = alive & ~finish
-            if step % 16 == 0 and not bool(alive.any()):
+                trace.setdefault("segments", []).append({
+                    "pos": buf.pos_out[:T].clone(), "conc": buf.conc_out[:T].double(),
+                    "stop": (buf.stop_flag[:T] != 0) if buf.stop_flag is not None else torch.zeros(T, N, dtype=torch.bool, device=dev),
+                    "done": buf.dones[:T] != 0, "conc_reward": buf.info[:T, 0].clone(), "action": buf.actions[:T].clone(),
+                    "alive_at_start": alive_before.clone()})
+            base += T
+            if bool((finished != 0).all()):
                 break
-        # envs still running at the guard count as finished there
-        pos = env.agent_pos
-        steps = torch.where(alive, torch.full_like(steps, max_steps), steps)
-        final_pos = torch.where(alive.unsqueeze(1), pos, final_pos)
-        dev_ = (final_pos.double() - env.source_pos).norm(dim=1)
+        # envs still running at the guard count as finished there (the env's own MAX_STEPS / the 2000-step guard end
+        # every first episode by then; this only covers a guard that is not a multiple of the segment length)
+        still = finished == 0
+        if bool(still.any()):
+            steps = torch.where(still, torch.full_like(steps, base), steps)
+            deviation = torch.where(still, (env.agent_pos.double() - env.source_pos).norm(dim=1), deviation)
         if stop == "fixed":
-            ok = dev_ < env.radius_t                                         # PPOV1.1/evaluate_model.py:75
+            ok = deviation < radius_at_start                                 # PPOV1.1/evaluate_model.py:75
         else:
-            ok = dev_ <= cfg.success_distance_threshold
-        for k, v in (("deviations", dev_), ("steps", steps), ("success", ok), ("stopped_early", early),
+            ok = deviation <= cfg.success_distance_threshold
+        for k, v in (("deviations", deviation), ("steps", steps), ("success", ok), ("stopped_early", early != 0),
                      ("stop_step", stop_step)):
             out[k].append(v)
+    if trace is not None and "segments" in trace:
+        segs = trace.pop("segments")
+        for k in ("pos", "conc", "stop", "done", "conc_reward", "action"):
+            trace[k] = list(torch.cat([s_[k] for s_ in segs]).unbind(0))
     return EvalResult(**{k: torch.cat(v) for k, v in out.items()})

@@ -46,10 +46,15 @@ class RolloutEngine:
     @torch.no_grad()
     def collect(self, greedy: bool = False, stop_terminates: bool = False, forced_actions=None,
                 step_noise=None, noise_out=None, horizon: int | None = None,
-                defer_stop_head: bool | None = None) -> PPOBuffer:
+                defer_stop_head: bool | None = None, stop_mode: str | None = None, step_guard: int = 0,
+                eval_ring=None, stop_threshold=None) -> PPOBuffer:
         """Runs ``horizon`` lockstep iterations and returns the filled buffer (asynchronous).
         ``defer_stop_head`` (default: whenever the stop decision does not terminate episodes)
-        evaluates the LSTM head and the trend features after the loop in one batched kernel."""
+        evaluates the LSTM head and the trend features after the loop in one batched kernel.
+        ``stop_mode`` ("fixed" / "threshold"; engines without a stop head): the V1.1 / V2.0 evaluator stop test runs
+        inside the kernel and ends the episode; ``eval_ring`` [N,10] float64 carries the last 10 samples across
+        segments, ``stop_threshold`` [N] float64 holds the V2.0 controller's current thresholds, ``step_guard`` ends
+        an episode at that step count (evaluate_model.py:52)."""
         env, T = self.env, int(horizon or self.horizon)
         assert T <= self.horizon
         defer = (self.stop_head is not None and not stop_terminates) if defer_stop_head is None else bool(defer_stop_head)
@@ -60,12 +65,21 @@ class RolloutEngine:
         flags |= _lib.FLAG_FAST_REWARD if getattr(env, "fast_reward", False) else 0
         flags |= _lib.FLAG_GREEDY if greedy else 0
         flags |= _lib.FLAG_STOP_TERMINATES if stop_terminates else 0
+        if stop_mode is not None:
+            if self.stop_head is not None:
+                raise ValueError("stop_mode needs an engine without an LSTM stop head")
+            flags |= {"fixed": _lib.FLAG_STOP_FIXED, "threshold": _lib.FLAG_STOP_THRESHOLD}[stop_mode]
+            if self.buffer.stop_flag is None:        # the kernel's stop decisions go where the LSTM head's would
+                self.buffer.stop_flag = torch.zeros(self.horizon, env.num_envs, dtype=torch.uint8, device=env.device)
+        if not 0 <= int(step_guard) < 65536:
+            raise ValueError("step_guard must fit 16 bits")
+        flags |= int(step_guard) << 16
         if forced_actions is not None:
             forced_actions = forced_actions.to(device=env.device, dtype=torch.int32).contiguous()
         if step_noise is not None:
             step_noise = step_noise.to(device=env.device, dtype=torch.float64).contiguous()
         bufs = self.buffer.c_rollout_buffers(self.conc_window, self.window_fill, self.last_obs, forced_actions,
-                                             step_noise, noise_out)
+                                             step_noise, noise_out, eval_ring, stop_threshold)
         if self.stop_head is not None:
             lp = self.stop_head.c_params(self.window, env.cfg.lstm_stop_threshold)
         else:

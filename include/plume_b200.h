@@ -470,7 +470,8 @@ int plume_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N
 /* The same GEMM on tcgen05.mma kind::f16 with the two-term fp16 split (x = hi + lo / s): twice the MAC rate of TF32 and
  * half the operand bytes at fp32-grade accuracy.  scaled_lo != 0: s = 2^11, cross terms in their own TMEM accumulator
  * (no fp16 underflow of lo; the forward GEMM of the update); scaled_lo == 0: s = 1, one accumulator (inputs should be
- * O(1): the backward GEMMs, whose operands the kernel pre-scales).  K a multiple of 64. */
+ * O(1): the backward GEMMs, whose operands the kernel pre-scales); scaled_lo == 2: as 0, with the A operand staged
+ * MN-major (the descriptor form the update kernel's G2 reads dz2 with).  K a multiple of 64. */
 int plume_tc_gemm_f16(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t scaled_lo,
                       void* stream);
 

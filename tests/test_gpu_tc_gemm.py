@@ -36,15 +36,17 @@ def test_tc_gemm_3xtf32(M, N, K):
     assert err.max() < 20 * max(err32.max(), 1e-8)
 
 
-@pytest.mark.parametrize("scaled", [1, 0])
+@pytest.mark.parametrize("scaled", [1, 0, 2])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (1000, 128, 256), (384, 256, 128), (65536, 128, 256)])
 def test_tc_gemm_f16_two_term_split(M, N, K, scaled):
     """kind::f16 with x = hi + lo/s.  Scaled lo (s = 2^11, separate accumulator): fp32-grade for any magnitude that fits
-    fp16's hi range; unscaled lo (one accumulator): fp32-grade for O(1) operands, which is what the update kernel feeds it."""
+    fp16's hi range; unscaled lo (one accumulator): fp32-grade for O(1) operands, which is what the update kernel feeds it;
+    scaled = 2: unscaled lo with the A operand staged MN-major (instruction-descriptor bit 15, leading / stride byte
+    offsets swapped roles): the form in which the update kernel's G2 reads the resident dz2 operand."""
     m = pb()
     lib = m._lib.load()
     rng = np.random.default_rng(M + N + K + scaled)
-    spread = 3.0 if scaled else 0.5
+    spread = 3.0 if scaled == 1 else 0.5
     A = (rng.standard_normal((M, K)) * np.exp(rng.uniform(-spread, spread, (M, 1)))).astype(np.float32)
     B = rng.standard_normal((N, K)).astype(np.float32)
     a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
@@ -58,4 +60,4 @@ def test_tc_gemm_f16_two_term_split(M, N, K, scaled):
     scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
     err = np.abs(got - want) / scale
     assert np.isfinite(got).all()
-    assert err.max() < (2e-6 if scaled else 4e-6), err.max()
+    assert err.max() < (2e-6 if scaled == 1 else 4e-6), err.max()

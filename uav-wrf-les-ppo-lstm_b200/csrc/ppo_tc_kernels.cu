@@ -312,16 +312,26 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     auto stage_buf = [&](uint32_t st, int which) -> float* {
         return sm + TcSmem::ring + ((st & 1u) * 4 + which) * kChunkFloats;
     };
+    // Backward GEMMs (G2, G3): stage 0 of the ring (64 KB) holds the RESIDENT dz2 operand of the tile -- 16-byte slot
+    // (og, sg, o & 7) at og * 2048 + sg * 128 + (o & 7) * 16 bytes = dz_scale dz2[8 sg .. 8 sg + 7][o], og = o >> 3,
+    // sg = s >> 3; hi in the first 32 KB, lo in the second -- written once by Ph4.  G3 reads it K-major along the samples
+    // (A = dz2^T: LBO 128, SBO 2048), G2 reads the SAME bytes MN-major along the outputs (A = dz2: LBO 2048, SBO 128,
+    // tc_gemm.cuh make_idesc_f16_a_mn): neither GEMM produces an A operand any more.  Their B operands go through the
+    // two halves of stage 1.
+    float* const dz_hi = sm + TcSmem::ring;
+    float* const dz_lo = dz_hi + 2 * kChunkFloats;
+    auto bstage_buf = [&](uint32_t st, int which) -> float* {     // which = 0 B_hi, 1 B_lo
+        return sm + TcSmem::ring + (4 + (st & 1u) * 2 + which) * kChunkFloats;
+    };
     // wait until the MMAs that last read this step's stage have completed
     auto acquire = [&](uint32_t st) {
         const uint32_t use = st >> 1;
         if (use >= 1) tc::mbar_wait(&bar[st & 1u], (use - 1) & 1u);
     };
-#ifndef PLUME_TC_TMA_B
     // B operand chunk (hi + lo, 16 KB each) from the pre-split weights, cp.async straight into shared memory
-    auto load_b = [&](uint32_t st, const float* hi, const float* lo) {
-        float4* bh4 = reinterpret_cast<float4*>(stage_buf(st, 2));
-        float4* bl4 = reinterpret_cast<float4*>(stage_buf(st, 3));
+    auto load_b_into = [&](float* dst_hi, float* dst_lo, const float* hi, const float* lo) {
+        float4* bh4 = reinterpret_cast<float4*>(dst_hi);
+        float4* bl4 = reinterpret_cast<float4*>(dst_lo);
         const float4* gh = reinterpret_cast<const float4*>(hi);
         const float4* gl = reinterpret_cast<const float4*>(lo);
 #pragma unroll
@@ -337,29 +347,6 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::tc_fence_before();
         mbar_arrive(&full[st & 1u]);
     };
-#else
-    // -DPLUME_TC_TMA_B: the same chunk as two TMA bulk copies issued by one thread, completing on the step's "full"
-    // barrier (transaction bytes) next to the producers' arrivals -- no LSU traffic and no per-thread wait, but measured
-    // 0.06 ms per iteration SLOWER than the 512-thread cp.async (12.999 vs 12.938 ms): the issuing thread's warp becomes
-    // the straggler of every ring step.  Kept for the comparison.
-    auto load_b = [&](uint32_t st, const float* hi, const float* lo) {
-        if (tid != 0) return;
-        tc::fence_proxy_async();          // earlier generic-proxy writes to this stage (the exchange area aliases it)
-        const uint32_t mb = tc::smem_u32(&full[st & 1u]);
-        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(2u * kChunkFloats * 4u)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(tc::smem_u32(stage_buf(st, 2))), "l"(hi), "r"(kChunkFloats * 4u), "r"(mb) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(tc::smem_u32(stage_buf(st, 3))), "l"(lo), "r"(kChunkFloats * 4u), "r"(mb) : "memory");
-    };
-    // producers: the A operand of step st is complete in shared memory -> visible to the async proxy, arrive
-    auto publish = [&](uint32_t st) {
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        mbar_arrive(&full[st & 1u]);
-    };
-#endif
     // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs, commit to "stage free"
     // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
     auto issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {
@@ -372,6 +359,43 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         else
             tc::mma_chunk_f16(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
                               idesc, first);
+        tc::mma_commit(&bar[st & 1u]);
+    };
+    // G2 ring step: A = resident dz2, MN-major, K = outputs [64 c, 64 c + 64); B = the step's W2^T chunk
+    const uint32_t idesc_amn = tc::make_idesc_f16_a_mn(128, 128);
+    auto issue_g2 = [&](uint32_t st, uint32_t col, int c, bool first) {
+        while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
+        tc::tc_fence_after();
+        const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
+        const uint32_t bh = tc::smem_u32(bstage_buf(st, 0)), bl = tc::smem_u32(bstage_buf(st, 1));
+#pragma unroll
+        for (int j = 0; j < tc::kChunkKH / 16; ++j) {
+            const uint32_t aoff = (uint32_t)(8 * c + 2 * j) * 2048u, boff = j * 2 * tc::kLBO;
+            const uint64_t dah = tc::make_smem_desc(ah + aoff, 2048, 128), dal = tc::make_smem_desc(al + aoff, 2048, 128);
+            const uint64_t dbh = tc::make_smem_desc(bh + boff, tc::kLBO, tc::kSBO);
+            const uint64_t dbl = tc::make_smem_desc(bl + boff, tc::kLBO, tc::kSBO);
+            tc::mma_f16(tmem + col, dal, dbh, idesc_amn, (first && j == 0) ? 0u : 1u);
+            tc::mma_f16(tmem + col, dah, dbl, idesc_amn, 1u);
+            tc::mma_f16(tmem + col, dah, dbh, idesc_amn, 1u);
+        }
+        tc::mma_commit(&bar[st & 1u]);
+    };
+    // G3 ring step: A = resident dz2^T, K-major, K = samples [64 c, 64 c + 64); B = the step's recomputed h1^T chunk
+    auto issue_g3 = [&](uint32_t st, uint32_t col, int c, bool first) {
+        while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
+        tc::tc_fence_after();
+        const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
+        const uint32_t bh = tc::smem_u32(bstage_buf(st, 0)), bl = tc::smem_u32(bstage_buf(st, 1));
+#pragma unroll
+        for (int j = 0; j < tc::kChunkKH / 16; ++j) {
+            const uint32_t aoff = (uint32_t)(8 * c + 2 * j) * 128u, boff = j * 2 * tc::kLBO;
+            const uint64_t dah = tc::make_smem_desc(ah + aoff, 128, 2048), dal = tc::make_smem_desc(al + aoff, 128, 2048);
+            const uint64_t dbh = tc::make_smem_desc(bh + boff, tc::kLBO, tc::kSBO);
+            const uint64_t dbl = tc::make_smem_desc(bl + boff, tc::kLBO, tc::kSBO);
+            tc::mma_f16(tmem + col, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);
+            tc::mma_f16(tmem + col, dah, dbl, idesc, 1u);
+            tc::mma_f16(tmem + col, dah, dbh, idesc, 1u);
+        }
         tc::mma_commit(&bar[st & 1u]);
     };
     // every MMA of the steps counted so far has completed
@@ -393,10 +417,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 const bool first_tile = (tile == (long long)blockIdx.x);
                 for (int c = 0; c < 4; ++c, ++st) issue(st, 0u, c == 0, 128u);                          // G1
                 for (int hN = 0; hN < 2; ++hN)
-                    for (int c = 0; c < 2; ++c, ++st) issue(st, (uint32_t)(128 * hN), c == 0, (uint32_t)(128 * hN));   // G2
+                    for (int c = 0; c < 2; ++c, ++st) issue_g2(st, (uint32_t)(128 * hN), c, c == 0);                    // G2
                 for (int c = 0; c < 2; ++c)
                     for (int hN = 0; hN < 2; ++hN, ++st)
-                        issue(st, (uint32_t)(256 + 128 * hN), first_tile && c == 0, (uint32_t)(256 + 128 * hN));       // G3
+                        issue_g3(st, (uint32_t)(256 + 128 * hN), c, first_tile && c == 0);                              // G3
             }
         }
     } else {
@@ -509,7 +533,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         for (int c = 0; c < 4; ++c) {
             const uint32_t st = step;
             acquire(st);
-            load_b(st, w2s + kW2SplitG1Hi + c * kChunkFloats, w2s + kW2SplitG1Lo + c * kChunkFloats);
+            load_b_into(stage_buf(st, 2), stage_buf(st, 3), w2s + kW2SplitG1Hi + c * kChunkFloats,
+                        w2s + kW2SplitG1Lo + c * kChunkFloats);
             uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
             uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
 #pragma unroll
@@ -717,55 +742,55 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             const float g2 = P2[128 + o], be2 = P2[256 + o];
             const float2 wrow2[3] = {f2(Wh[o * 8], Wh[o * 8 + 1]), f2(Wh[o * 8 + 2], Wh[o * 8 + 3]),
                                      f2(Wh[o * 8 + 4], Wh[o * 8 + 5])};
-PLUME_UNROLL(PLUME_U4)
-            for (int q = 0; q < SPT; ++q) {
-                const int s = SPT * ug + q;
-                const float x_hat = xh[s * kXhStride + o];
-                const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8);
-                const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8 + 4);
-                const float4 sc = *reinterpret_cast<const float4*>(sm + TcSmem::sc + s * 4);
-                const float2 d01 = f2(d0.x, d0.y), d23 = f2(d0.z, d0.w), d45 = f2(d1.x, d1.y);
-                const float y = fmaf(x_hat, g2, be2);
-                const float2 h2v = splat2(fmaxf(y, 0.0f));
-                float2 dh2 = __fmul2_rn(d01, wrow2[0]);
-                dh2 = __ffma2_rn(d23, wrow2[1], dh2);
-                dh2 = __ffma2_rn(d45, wrow2[2], dh2);
-                g_wh2[0] = __ffma2_rn(d01, h2v, g_wh2[0]);
-                g_wh2[1] = __ffma2_rn(d23, h2v, g_wh2[1]);
-                g_wh2[2] = __ffma2_rn(d45, h2v, g_wh2[2]);
-                const float dy = (y > 0.0f) ? dh2.x + dh2.y : 0.0f;
-                g_g2 = fmaf(dy, x_hat, g_g2);
-                g_be2 += dy;
-                const float dz = sc.x * (dy * g2 - sc.y - x_hat * sc.z);
-                g_b2 += dz;
-                xh[s * kXhStride + o] = dz * dz_scale;            // dz_scale dz2 (exact: a power of two) replaces xhat2
+            uint4* const dzh = reinterpret_cast<uint4*>(dz_hi);
+            uint4* const dzl = reinterpret_cast<uint4*>(dz_lo);
+#pragma unroll
+            for (int g8 = 0; g8 < SPT / 8; ++g8) {
+                float dzv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int s = SPT * ug + 8 * g8 + i;
+                    const float x_hat = xh[s * kXhStride + o];
+                    const float4 d0 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8);
+                    const float4 d1 = *reinterpret_cast<const float4*>(sm + TcSmem::dout + s * 8 + 4);
+                    const float4 sc = *reinterpret_cast<const float4*>(sm + TcSmem::sc + s * 4);
+                    const float2 d01 = f2(d0.x, d0.y), d23 = f2(d0.z, d0.w), d45 = f2(d1.x, d1.y);
+                    const float y = fmaf(x_hat, g2, be2);
+                    const float2 h2v = splat2(fmaxf(y, 0.0f));
+                    float2 dh2 = __fmul2_rn(d01, wrow2[0]);
+                    dh2 = __ffma2_rn(d23, wrow2[1], dh2);
+                    dh2 = __ffma2_rn(d45, wrow2[2], dh2);
+                    g_wh2[0] = __ffma2_rn(d01, h2v, g_wh2[0]);
+                    g_wh2[1] = __ffma2_rn(d23, h2v, g_wh2[1]);
+                    g_wh2[2] = __ffma2_rn(d45, h2v, g_wh2[2]);
+                    const float dy = (y > 0.0f) ? dh2.x + dh2.y : 0.0f;
+                    g_g2 = fmaf(dy, x_hat, g_g2);
+                    g_be2 += dy;
+                    const float dz = sc.x * (dy * g2 - sc.y - x_hat * sc.z);
+                    g_b2 += dz;
+                    dzv[i] = dz * dz_scale;                         // exact: a power of two
+                }
+                // eight consecutive samples of output o = one 16-byte slot of the resident dz2 operand (hi and lo)
+                uint4 hi, lo;
+                tc::split_f16x8(make_float4(dzv[0], dzv[1], dzv[2], dzv[3]), make_float4(dzv[4], dzv[5], dzv[6], dzv[7]), 1.0f,
+                                hi, lo);
+                const int f = (o >> 3) * 128 + ((SPT / 8) * ug + g8) * 8 + (o & 7);
+                dzh[f] = hi;
+                dzl[f] = lo;
             }
         }
         compute_sync();
 
         PLUME_TL(5);
         // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 2 chunks of 64 ------
-        // (operands pre-scaled: dz_scale dz2 -- stored that way by Ph4 -- and 16 W2^T, unscaled lo, one accumulator;
-        // undone in Ph6)
+        // (A = the resident dz_scale dz2 operand read MN-major: nothing to produce; B = 16 W2^T chunks from L2, unscaled lo,
+        // one accumulator; both scales undone in Ph6)
         for (int hN = 0; hN < 2; ++hN) {
             for (int c = 0; c < 2; ++c) {
                 const uint32_t st = step;
                 acquire(st);
-                load_b(st, w2s + kW2SplitG2Hi + (hN * 2 + c) * kChunkFloats,
-                       w2s + kW2SplitG2Lo + (hN * 2 + c) * kChunkFloats);
-                uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
-                uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
-#pragma unroll
-                for (int uu = 0; uu < UPT; ++uu) {
-                    const int u = UPT * ug + uu;
-                    const float4 d0 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u);
-                    const float4 d1 = *reinterpret_cast<const float4*>(xh + r128 * kXhStride + 64 * c + 8 * u + 4);
-                    uint4 hi, lo;
-                    tc::split_f16x8(d0, d1, 1.0f, hi, lo);
-                    const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
-                    ah[f] = hi;
-                    al[f] = lo;
-                }
+                load_b_into(bstage_buf(st, 0), bstage_buf(st, 1), w2s + kW2SplitG2Hi + (hN * 2 + c) * kChunkFloats,
+                            w2s + kW2SplitG2Lo + (hN * 2 + c) * kChunkFloats);
                 publish(st);
                 ++step;
             }
@@ -773,15 +798,14 @@ PLUME_UNROLL(PLUME_U4)
 
         PLUME_TL(6);
         // ---- Ph7: G3 dW2 += dz2^T . h1, K = 128 samples in 2 chunks of 64 x two halves of the inputs ------
-        // (A = dz_scale dz2^T, B = h1^T, unscaled lo; the accumulator holds dz_scale dW2 until the flush)
+        // (A = the resident dz_scale dz2^T operand, K-major; B = h1^T, recomputed, unscaled lo; the accumulator holds
+        // dz_scale dW2 until the flush)
         for (int c = 0; c < 2; ++c) {
             for (int hN = 0; hN < 2; ++hN) {
                 const uint32_t st = step;
                 acquire(st);
-                uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
-                uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
-                uint4* bh4 = reinterpret_cast<uint4*>(stage_buf(st, 2));
-                uint4* bl4 = reinterpret_cast<uint4*>(stage_buf(st, 3));
+                uint4* bh4 = reinterpret_cast<uint4*>(bstage_buf(st, 0));
+                uint4* bl4 = reinterpret_cast<uint4*>(bstage_buf(st, 1));
                 const int in = 128 * hN + r128;
                 // (scalar FMAs in the forward's order: pairing (k, k+1) into FFMA2 measured 0.02 ms per iteration slower)
                 float w[6];
@@ -792,15 +816,7 @@ PLUME_UNROLL(PLUME_U4)
                 for (int uu = 0; uu < UPT; ++uu) {
                     const int u = UPT * ug + uu, s0 = 64 * c + 8 * u;
                     const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
-                    // A: dz2^T, row = output r128, 8 consecutive samples
-                    float d[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) d[i] = xh[(s0 + i) * kXhStride + r128];
-                    uint4 hi, lo;
-                    tc::split_f16x8(make_float4(d[0], d[1], d[2], d[3]), make_float4(d[4], d[5], d[6], d[7]), 1.0f, hi, lo);
-                    ah[f] = hi;
-                    al[f] = lo;
-                    // B: h1^T, row = input `in`, the same 8 samples (recomputed from the 6 inputs)
+                    // B: h1^T, row = input `in`, 8 consecutive samples (recomputed from the 6 inputs)
                     float hv[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -815,6 +831,7 @@ PLUME_UNROLL(PLUME_U4)
                         z = fmaf(x1.y, w[5], z);
                         hv[i] = fmaxf(fmaf(z * x1.z, g1, be1), 0.0f);
                     }
+                    uint4 hi, lo;
                     tc::split_f16x8(make_float4(hv[0], hv[1], hv[2], hv[3]), make_float4(hv[4], hv[5], hv[6], hv[7]), 1.0f,
                                     hi, lo);
                     bh4[f] = hi;
@@ -829,8 +846,7 @@ PLUME_UNROLL(PLUME_U4)
         PLUME_TL(7);
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
-            compute_sync();        // every thread has read dz2 for its last G3 chunk: the region becomes staging
-            tc::tc_fence_after();
+            tc::tc_fence_after();  // (the xhat2 / staging region was last read in Ph4, which ended with a barrier)
             float2 m1p2 = f2(0.0f, 0.0f), m2p2 = f2(0.0f, 0.0f);         // even / odd inputs of this thread's slab
             const float2 un2 = splat2(1.0f / (dz_scale * kW2BwdScale));    // exact: both are powers of two
             // this thread's sample: inputs + rstd1

@@ -209,6 +209,13 @@ constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {      // D fp32, A/B fp16, both K-major
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// The same with A read MN-major (instruction-descriptor bit 15): a 16-byte slot of A then holds 8 consecutive M for ONE
+// k, the eight k of a core matrix are consecutive slots; in the shared-memory descriptor the leading byte offset is the
+// distance between core matrices along K, the stride byte offset the distance along M (CUTLASS
+// cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>, LayoutType::INTERLEAVE).  This is what lets ONE copy of
+// dz2 serve as A of both backward GEMMs of the update: K-major along the samples for G3 (dW2 = dz2^T h1), MN-major
+// along the outputs for G2 (dh1 = dz2 W2).
+__host__ __device__ constexpr uint32_t make_idesc_f16_a_mn(int M, int N) { return make_idesc_f16(M, N) | (1u << 15); }
 
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {

@@ -167,6 +167,107 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_f16_kernel(const float* __rest
     if (warp == 0) tc::tmem_dealloc<kCols>(tmem_d);
 }
 
+// The unscaled-lo GEMM with A staged MN-major (unit test of the descriptor form the update kernel's G2 uses): per
+// 64-wide K chunk, slot (kg, mg, k & 7) at kg * 2048 + mg * 128 + (k & 7) * 16 bytes holds A[8 mg .. 8 mg + 7][k].
+template <int BN>
+__global__ void __launch_bounds__(128, 1) tc_gemm_f16_amn_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                 float* __restrict__ C, int M, int K) {
+    extern __shared__ __align__(1024) float sm[];
+    constexpr int kA = 128 * tc::kChunkK, kB = BN * tc::kChunkK;
+    float* a_hi = sm;
+    float* a_lo = a_hi + 2 * kA;
+    float* b_hi = a_lo + 2 * kA;
+    float* b_lo = b_hi + 2 * kB;
+    __shared__ uint64_t mma_done[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * 128;
+    if (tid == 0) {
+        tc::mbar_init(&mma_done[0], 1);
+        tc::mbar_init(&mma_done[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc<BN>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = tc::make_idesc_f16_a_mn(128, BN);
+    const int chunks = K / tc::kChunkKH;
+    for (int kc = 0; kc < chunks; ++kc) {
+        const int s = kc & 1;
+        if (kc >= 2) tc::mbar_wait(&mma_done[s], (uint32_t)(((kc >> 1) - 1) & 1));
+        uint4* ah = reinterpret_cast<uint4*>(a_hi + s * kA);
+        uint4* al = reinterpret_cast<uint4*>(a_lo + s * kA);
+        for (int f = tid; f < 1024; f += 128) {               // slot f = kg * 128 + mg * 8 + (k & 7)
+            const int kg = f >> 7, mg = (f >> 3) & 15, k = kc * tc::kChunkKH + kg * 8 + (f & 7);
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = m0 + 8 * mg + i;
+                v[i] = row < M ? A[(size_t)row * K + k] : 0.0f;
+            }
+            uint4 hi, lo;
+            tc::split_f16x8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), 1.0f, hi, lo);
+            ah[f] = hi;
+            al[f] = lo;
+        }
+        tc::load_split_chunk_f16<BN, 128>(b_hi + s * kB, b_lo + s * kB, B + kc * tc::kChunkKH, K, BN, tid, 1.0f);
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            const uint32_t sah = tc::smem_u32(ah), sal = tc::smem_u32(al);
+            const uint32_t sbh = tc::smem_u32(b_hi + s * kB), sbl = tc::smem_u32(b_lo + s * kB);
+#pragma unroll
+            for (int j = 0; j < tc::kChunkKH / 16; ++j) {
+                const uint32_t aoff = j * 2 * 2048, boff = j * 2 * tc::kLBO;       // two core matrices along K per step
+                const uint64_t dah = tc::make_smem_desc(sah + aoff, 2048, 128), dal = tc::make_smem_desc(sal + aoff, 2048, 128);
+                const uint64_t dbh = tc::make_smem_desc(sbh + boff, tc::kLBO, tc::kSBO);
+                const uint64_t dbl = tc::make_smem_desc(sbl + boff, tc::kLBO, tc::kSBO);
+                tc::mma_f16(tmem_d, dal, dbh, idesc, (kc == 0 && j == 0) ? 0u : 1u);
+                tc::mma_f16(tmem_d, dah, dbl, idesc, 1u);
+                tc::mma_f16(tmem_d, dah, dbh, idesc, 1u);
+            }
+            tc::mma_commit(&mma_done[s]);
+        }
+    }
+    {
+        const int last = chunks - 1;
+        tc::mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
+    }
+    tc::tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        tc::tmem_ld_wait();
+        if (row < M) {
+            float4* dst = reinterpret_cast<float4*>(C + (size_t)row * BN + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<BN>(tmem_d);
+}
+
+template <int BN>
+static int launch_tc_gemm_f16_amn(const float* A, const float* B, float* C, int M, int K, cudaStream_t s) {
+    const int smem = (2 * 2 * 128 * tc::kChunkK + 2 * 2 * BN * tc::kChunkK) * (int)sizeof(float) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc_gemm_f16_amn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return fail("tc_gemm_f16 (A MN-major): cannot reserve %d B of shared memory", smem);
+        configured = true;
+    }
+    tc_gemm_f16_amn_kernel<BN><<<(M + 127) / 128, 128, smem, s>>>(A, B, C, M, K);
+    if (cudaGetLastError() != cudaSuccess) return fail("tc_gemm_f16 (A MN-major) launch failed");
+    return 0;
+}
+
 template <int BN, bool kScaled>
 static int launch_tc_gemm_f16(const float* A, const float* B, float* C, int M, int K, cudaStream_t s) {
     const int smem = (2 * 2 * 128 * tc::kChunkK + 2 * 2 * BN * tc::kChunkK) * (int)sizeof(float) + 1024;
@@ -190,6 +291,11 @@ extern "C" int plume_tc_gemm_f16(const float* A, const float* B, float* C, int32
                                  int32_t scaled_lo, void* stream) {
     PLUME_CHECK_ARG(A && B && C, "null pointer");
     PLUME_CHECK_ARG(M > 0 && K > 0 && K % tc::kChunkKH == 0, "K must be a positive multiple of 64");
+    if (scaled_lo == 2) {             // A staged MN-major, unscaled lo
+        if (N == 128) return launch_tc_gemm_f16_amn<128>(A, B, C, M, K, as_stream(stream));
+        if (N == 256) return launch_tc_gemm_f16_amn<256>(A, B, C, M, K, as_stream(stream));
+        return fail("plume_tc_gemm_f16: N must be 128 or 256");
+    }
     if (N == 128 && scaled_lo) return launch_tc_gemm_f16<128, true>(A, B, C, M, K, as_stream(stream));
     if (N == 128) return launch_tc_gemm_f16<128, false>(A, B, C, M, K, as_stream(stream));
     if (N == 256 && scaled_lo) return launch_tc_gemm_f16<256, true>(A, B, C, M, K, as_stream(stream));

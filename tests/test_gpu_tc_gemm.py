@@ -61,3 +61,26 @@ def test_tc_gemm_f16_two_term_split(M, N, K, scaled):
     err = np.abs(got - want) / scale
     assert np.isfinite(got).all()
     assert err.max() < (2e-6 if scaled == 1 else 4e-6), err.max()
+
+
+@pytest.mark.parametrize("M,K", [(128, 128), (256, 256), (1024, 384)])
+def test_tc_gemm_f16_b_mn_major_bulk_round_trip(M, K):
+    """The form of the update kernel's dW2 GEMM: A K-major with the strides of the resident dz2 operand, B (N = 64)
+    staged MN-major in the layout of a forward-activation chunk (instruction-descriptor bit 16) after a cp.async.bulk
+    round trip shared -> global -> shared (the activation stash)."""
+    m = pb()
+    lib = m._lib.load()
+    N = 64
+    rng = np.random.default_rng(M + K)
+    A = (rng.standard_normal((M, K)) * np.exp(rng.uniform(-0.5, 0.5, (M, 1)))).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.plume_tc_gemm_f16(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, 3, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.plume_last_error()
+    torch.cuda.synchronize()
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    got = c.cpu().numpy().astype(np.float64)
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    assert np.isfinite(got).all()
+    assert (np.abs(got - want) / scale).max() < 4e-6

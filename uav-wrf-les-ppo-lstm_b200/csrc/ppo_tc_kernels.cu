@@ -87,7 +87,15 @@ constexpr int kW2SplitFloats = 65536;
 constexpr int kWsW1c = kW2SplitFloats;                // [6][256] feature.0.weight minus its column means, k-major
 constexpr int kWsB1c = kWsW1c + 6 * 256;              // [256]    feature.0.bias minus its mean
 constexpr int kWsLn1q = kWsB1c + 256;                 // [28] doubles: the LayerNorm-1 quadratic form (see ln1q below)
-constexpr int kWsFloats = kWsLn1q + 2 * 28;
+constexpr int kWsStash = (kWsLn1q + 2 * 28 + 63) & ~63;   // per-CTA activation stash (below), 256-byte aligned
+// The forward activations h1 of a tile are produced ONCE, as the A operand of G1 (four 32 KB chunks: fp16 hi + lo of
+// 128 samples x 64 inputs).  Each chunk is copied to this L2-resident scratch by a bulk copy (cp.async.bulk, issued by
+// the MMA thread) as soon as its MMAs are issued, and comes back by a bulk copy as the B operand of G3 (read MN-major:
+// the same bytes) -- the CUDA cores no longer recompute h1^T for the weight-gradient GEMM.
+constexpr int kStashChunkBytes = 2 * kChunkFloats * 4;                  // hi + lo of one chunk (32 KB)
+constexpr int kStashFloatsPerCta = 4 * kStashChunkBytes / 4;            // 128 KB per CTA
+constexpr int kTcMaxCtas = 192;                                         // >= the SM count (B200: 148)
+constexpr long long kWsFloats = (long long)kWsStash + (long long)kTcMaxCtas * kStashFloatsPerCta;
 static_assert((kWsLn1q % 2) == 0, "the float64 coefficients must be 8-byte aligned");
 // The backward GEMMs keep main and cross terms in ONE accumulator (TMEM is full), so their lo parts are not scaled;
 // instead the operands are brought to O(1): W2^T is multiplied by 16 (|w| ~ 0.1) and dz2 by a power of two near the
@@ -196,9 +204,11 @@ __global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restric
         const int o = i >> 5, in0 = (i & 31) * 8;
         v0 = *reinterpret_cast<const float4*>(params + PLUME_OFF_W2 + o * 256 + in0);
         v1 = *reinterpret_cast<const float4*>(params + PLUME_OFF_W2 + o * 256 + in0 + 4);
+        v0 = make_float4(kW2BwdScale * v0.x, kW2BwdScale * v0.y, kW2BwdScale * v0.z, kW2BwdScale * v0.w);
+        v1 = make_float4(kW2BwdScale * v1.x, kW2BwdScale * v1.y, kW2BwdScale * v1.z, kW2BwdScale * v1.w);
         chunk_base = kW2SplitG1Hi + (in0 >> 6) * kChunkFloats;
         f = (o >> 3) * 64 + ((in0 & 63) >> 3) * 8 + (o & 7);
-        scale = tc::kLoScale;
+        scale = 1.0f;
     } else {                                          // G2: row = in (two halves of 128), K = out, values 16 W2[out][in]
         const int j = i - 4096, in = j >> 4, out0 = (j & 15) * 8;
         float w[8];
@@ -226,6 +236,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     extern __shared__ __align__(128) float sm[];     // no-swizzle operand layouts need 16 B alignment only
     __shared__ uint64_t bar[2];           // "stage free": arrived by tcgen05.commit
     __shared__ uint64_t full[2];          // "operands of the stage written": one arrival per compute thread
+    __shared__ uint64_t sdone[2];         // "the stage's activation chunk has been read by its bulk store to the stash"
+    __shared__ uint64_t hfull[2];         // "a stashed activation chunk has landed in this half of stage 1" (bulk-copy bytes)
+    __shared__ uint64_t hfree[2];         // "the G3 MMAs reading this half have completed"
+    __shared__ uint64_t g3done;           // "every G3 MMA of the tile has completed"
     __shared__ uint32_t tmem_slot;
     __shared__ float cta_acc[48];         // per-CTA sums of the per-sample scalars (see the flush)
     __shared__ double cta_loss[4];
@@ -256,6 +270,12 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::mbar_init(&bar[1], 1);
         tc::mbar_init(&full[0], kTcThreads);
         tc::mbar_init(&full[1], kTcThreads);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&sdone[i], 1);
+            tc::mbar_init(&hfull[i], 1);
+            tc::mbar_init(&hfree[i], 1);
+        }
+        tc::mbar_init(&g3done, 1);
         tc::mbar_fence_init();
     }
     if (tid < 48) cta_acc[tid] = 0.0f;
@@ -347,18 +367,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::tc_fence_before();
         mbar_arrive(&full[st & 1u]);
     };
-    // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs, commit to "stage free"
-    // (col_small != col: the small cross terms accumulate in their own TMEM region, see tc_gemm.cuh)
-    auto issue = [&](uint32_t st, uint32_t col, bool first, uint32_t col_small) {
+    // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs (main and cross terms in one accumulator:
+    // both operands are O(1), lo unscaled), commit to "stage free"
+    auto issue = [&](uint32_t st, uint32_t col, bool first) {
         // (the issuer shares a scheduler with four producer warps: back off between polls instead of spinning)
         while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
         tc::tc_fence_after();
-        if (col_small != col)
-            tc::mma_chunk_f16_split(tmem + col, tmem + col_small, stage_buf(st, 0), stage_buf(st, 1),
-                                    stage_buf(st, 2), stage_buf(st, 3), idesc, first);
-        else
-            tc::mma_chunk_f16(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3),
-                              idesc, first);
+        tc::mma_chunk_f16(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3), idesc, first);
         tc::mma_commit(&bar[st & 1u]);
     };
     // G2 ring step: A = resident dz2, MN-major, K = outputs [64 c, 64 c + 64); B = the step's W2^T chunk
@@ -380,23 +395,23 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
         tc::mma_commit(&bar[st & 1u]);
     };
-    // G3 ring step: A = resident dz2^T, K-major, K = samples [64 c, 64 c + 64); B = the step's recomputed h1^T chunk
-    auto issue_g3 = [&](uint32_t st, uint32_t col, int c, bool first) {
-        while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
-        tc::tc_fence_after();
+    // G3 for the 64 inputs of activation chunk c (N = 64, all 128 samples = 8 K-steps): A = resident dz2^T, K-major
+    // along the samples; B = the stashed chunk in half `half` of stage 1 -- written K-major as A of G1 (slot (sg, u, s & 7)
+    // at sg * 1024 + u * 128 + (s & 7) * 16 bytes = h1[s][64 c + 8 u .. + 7]), read here MN-major (N = inputs: next 8
+    // inputs 128 bytes on, next 8 samples 1024 bytes on)
+    const uint32_t idesc_g3 = tc::make_idesc_f16_b_mn(128, 64);
+    auto issue_g3 = [&](int half, uint32_t col, bool first) {
         const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
-        const uint32_t bh = tc::smem_u32(bstage_buf(st, 0)), bl = tc::smem_u32(bstage_buf(st, 1));
+        const uint32_t bh = tc::smem_u32(bstage_buf((uint32_t)half, 0)), bl = tc::smem_u32(bstage_buf((uint32_t)half, 1));
 #pragma unroll
-        for (int j = 0; j < tc::kChunkKH / 16; ++j) {
-            const uint32_t aoff = (uint32_t)(8 * c + 2 * j) * 128u, boff = j * 2 * tc::kLBO;
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t aoff = (uint32_t)(2 * j) * 128u, boff = (uint32_t)(2 * j) * 1024u;
             const uint64_t dah = tc::make_smem_desc(ah + aoff, 128, 2048), dal = tc::make_smem_desc(al + aoff, 128, 2048);
-            const uint64_t dbh = tc::make_smem_desc(bh + boff, tc::kLBO, tc::kSBO);
-            const uint64_t dbl = tc::make_smem_desc(bl + boff, tc::kLBO, tc::kSBO);
-            tc::mma_f16(tmem + col, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);
-            tc::mma_f16(tmem + col, dah, dbl, idesc, 1u);
-            tc::mma_f16(tmem + col, dah, dbh, idesc, 1u);
+            const uint64_t dbh = tc::make_smem_desc(bh + boff, 1024, 128), dbl = tc::make_smem_desc(bl + boff, 1024, 128);
+            tc::mma_f16(tmem + col, dal, dbh, idesc_g3, (first && j == 0) ? 0u : 1u);
+            tc::mma_f16(tmem + col, dah, dbl, idesc_g3, 1u);
+            tc::mma_f16(tmem + col, dah, dbh, idesc_g3, 1u);
         }
-        tc::mma_commit(&bar[st & 1u]);
     };
     // every MMA of the steps counted so far has completed
     auto wait_all_mma = [&]() {
@@ -412,15 +427,48 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     // lets the ring run on mbarriers only: producers never meet at a CTA barrier inside a GEMM)
     if (warp == kTcThreads / 32) {
         if (lane == 0) {
-            uint32_t st = 0;
+            uint32_t st = 0;                   // producer steps so far: 8 per tile (G1 4, G2 4), so (st & 1) == (c & 1)
+            char* const stash = reinterpret_cast<char*>(const_cast<float*>(w2s) + kWsStash) +
+                                (size_t)blockIdx.x * (size_t)kStashFloatsPerCta * 4;
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const bool first_tile = (tile == (long long)blockIdx.x);
-                for (int c = 0; c < 4; ++c, ++st) issue(st, 0u, c == 0, 128u);                          // G1
+                for (int c = 0; c < 4; ++c, ++st) {                                                      // G1
+                    issue(st, 0u, c == 0);
+                    // stash the activation chunk (A_hi, A_lo of the stage: 32 KB contiguous); the producers' fence.proxy.async
+                    // + the `full` barrier made their writes visible to the async proxy
+                    tc::bulk_store(stash + (size_t)c * kStashChunkBytes, stage_buf(st, 0), (uint32_t)kStashChunkBytes);
+                    tc::bulk_commit_group();
+                    tc::bulk_wait_group_read_all();         // (this thread has nothing else to do until the next chunk is produced)
+                    mbar_arrive(&sdone[st & 1u]);
+                }
                 for (int hN = 0; hN < 2; ++hN)
-                    for (int c = 0; c < 2; ++c, ++st) issue_g2(st, (uint32_t)(128 * hN), c, c == 0);                    // G2
-                for (int c = 0; c < 2; ++c)
-                    for (int hN = 0; hN < 2; ++hN, ++st)
-                        issue_g3(st, (uint32_t)(256 + 128 * hN), c, first_tile && c == 0);                              // G3
+                    for (int c = 0; c < 2; ++c, ++st) issue_g2(st, (uint32_t)(128 * hN), c, c == 0);    // G2
+                // G3: the four stashed chunks come back through the two halves of stage 1, which the G2 steps st - 2 (half 0)
+                // and st - 1 (half 1) read last; nothing for the compute warps to do
+                tc::bulk_wait_group_all();                  // the stash holds the tile's four chunks
+                for (int c = 0; c < 4; ++c) {
+                    const int half = c & 1;
+                    if (c < 2) {
+                        const uint32_t g2st = st - 2u + (uint32_t)c;
+                        tc::mbar_wait(&bar[g2st & 1u], (g2st >> 1) & 1u);
+                    } else {
+                        tc::mbar_wait(&hfree[half], 0u);    // the half's first G3 of this tile (two commits per tile and half)
+                    }
+                    tc::bulk_load(bstage_buf((uint32_t)half, 0), stash + (size_t)c * kStashChunkBytes, (uint32_t)kStashChunkBytes,
+                                  &hfull[half]);
+                    if (c >= 1) {                           // MMAs of the previous chunk, whose load was issued one round ago
+                        const int pc = c - 1;
+                        tc::mbar_wait(&hfull[pc & 1], (uint32_t)(pc >> 1));
+                        tc::tc_fence_after();
+                        issue_g3(pc & 1, (uint32_t)(256 + 64 * pc), first_tile);
+                        tc::mma_commit(&hfree[pc & 1]);
+                    }
+                }
+                tc::mbar_wait(&hfull[1], 1u);
+                tc::tc_fence_after();
+                issue_g3(1, (uint32_t)(256 + 64 * 3), first_tile);
+                tc::mma_commit(&hfree[1]);
+                tc::mma_commit(&g3done);
             }
         }
     } else {
@@ -466,7 +514,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
     };
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    uint32_t lt = 0;          // tiles of this CTA so far
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
 #ifdef PLUME_TC_TIMELINE
         long long tl_[24];
         const bool tl_on = blockIdx.x == 0 && tid == 0 && tile == (long long)blockIdx.x + 3 * gridDim.x;
@@ -533,6 +582,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         for (int c = 0; c < 4; ++c) {
             const uint32_t st = step;
             acquire(st);
+            if (c >= 2) tc::mbar_wait(&sdone[st & 1u], 0u);     // chunk c - 2 of this stage has been read by its bulk store
             load_b_into(stage_buf(st, 2), stage_buf(st, 3), w2s + kW2SplitG1Hi + c * kChunkFloats,
                         w2s + kW2SplitG1Lo + c * kChunkFloats);
             uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
@@ -559,16 +609,18 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     hq[q] = make_float4(fmaxf(y01.x, 0.0f), fmaxf(y01.y, 0.0f), fmaxf(y23.x, 0.0f), fmaxf(y23.y, 0.0f));
                 }
                 uint4 hi, lo;
-                tc::split_f16x8(hq[0], hq[1], tc::kLoScale, hi, lo);
+                tc::split_f16x8(hq[0], hq[1], 1.0f, hi, lo);
                 const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
                 ah[f] = hi;
                 al[f] = lo;
             }
-            publish(st);          // issuer: G1 -> columns [0,128), scaled cross terms -> [128,256) (free until G2)
+            publish(st);          // issuer: G1 -> columns [0,128), then the chunk's bulk store to the stash
             ++step;
         }
         PLUME_TL(2);
         wait_all_mma();
+        tc::mbar_wait(&sdone[0], 1u);     // chunks 2 and 3 have left for the stash: Ph4 / G2 may overwrite their stages
+        tc::mbar_wait(&sdone[1], 1u);
 
         PLUME_TL(3);
         // ---- Ph3: LN2, heads, loss, LN2-backward means: thread = (sample srow, 32 of the 128 outputs) ----
@@ -578,22 +630,16 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
             tc::tmem_ld32(taddr, v);
             tc::tmem_ld_wait();
-            {                                               // + the small cross terms (separate accumulator)
-                float sm_terms[32];
-                tc::tmem_ld32(taddr + 128u, sm_terms);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaf(sm_terms[j], tc::kLoInv, v[j]);
-            }
             tc::tc_fence_before();
             float sum = 0.0f;
+            constexpr float kUnW = 1.0f / kW2BwdScale;      // the accumulator holds h1 . (16 W2)^T; exact power of two
 #pragma unroll
             for (int j4 = 0; j4 < CW / 4; ++j4) {
                 const float4 b2 = *reinterpret_cast<const float4*>(P2 + c0 + 4 * j4);
-                v[4 * j4 + 0] += b2.x;
-                v[4 * j4 + 1] += b2.y;
-                v[4 * j4 + 2] += b2.z;
-                v[4 * j4 + 3] += b2.w;
+                v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], kUnW, b2.x);
+                v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], kUnW, b2.y);
+                v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], kUnW, b2.z);
+                v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], kUnW, b2.w);
             }
 #pragma unroll
             for (int j = 0; j < CW; ++j) sum += v[j];
@@ -797,51 +843,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         }
 
         PLUME_TL(6);
-        // ---- Ph7: G3 dW2 += dz2^T . h1, K = 128 samples in 2 chunks of 64 x two halves of the inputs ------
-        // (A = the resident dz_scale dz2^T operand, K-major; B = h1^T, recomputed, unscaled lo; the accumulator holds
-        // dz_scale dW2 until the flush)
-        for (int c = 0; c < 2; ++c) {
-            for (int hN = 0; hN < 2; ++hN) {
-                const uint32_t st = step;
-                acquire(st);
-                uint4* bh4 = reinterpret_cast<uint4*>(bstage_buf(st, 0));
-                uint4* bl4 = reinterpret_cast<uint4*>(bstage_buf(st, 1));
-                const int in = 128 * hN + r128;
-                // (scalar FMAs in the forward's order: pairing (k, k+1) into FFMA2 measured 0.02 ms per iteration slower)
-                float w[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];
-                const float b1c = P1[in], g1 = P1[256 + in], be1 = P1[512 + in];
-#pragma unroll
-                for (int uu = 0; uu < UPT; ++uu) {
-                    const int u = UPT * ug + uu, s0 = 64 * c + 8 * u;
-                    const int f = (r128 >> 3) * 64 + u * 8 + (r128 & 7);
-                    // B: h1^T, row = input `in`, 8 consecutive samples (recomputed from the 6 inputs)
-                    float hv[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8);
-                        const float4 x1 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8 + 4);
-                        float z = b1c;
-                        z = fmaf(x0.x, w[0], z);
-                        z = fmaf(x0.y, w[1], z);
-                        z = fmaf(x0.z, w[2], z);
-                        z = fmaf(x0.w, w[3], z);
-                        z = fmaf(x1.x, w[4], z);
-                        z = fmaf(x1.y, w[5], z);
-                        hv[i] = fmaxf(fmaf(z * x1.z, g1, be1), 0.0f);
-                    }
-                    uint4 hi, lo;
-                    tc::split_f16x8(make_float4(hv[0], hv[1], hv[2], hv[3]), make_float4(hv[4], hv[5], hv[6], hv[7]), 1.0f,
-                                    hi, lo);
-                    bh4[f] = hi;
-                    bl4[f] = lo;
-                }
-                publish(st);
-                ++step;
-            }
-        }
-        // (the acquires above waited for every G2 MMA)
+        // ---- G3 dW2 += dz2^T . h1 runs on the MMA thread alone: B = the stashed activation chunks, bulk-copied back into
+        // the halves of stage 1 as the G2 MMAs release them (A = the resident dz2^T operand; the accumulator holds dz_scale
+        // dW2 until the flush).  The compute warps only need dh1:
+        wait_all_mma();
 
         PLUME_TL(7);
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
@@ -913,7 +918,8 @@ PLUME_UNROLL(PLUME_U6)
                 PLUME_TL(15 + 2 * hN);
             }
         PLUME_TL(8);
-            wait_all_mma();        // the exchange area aliases the ring: the last G3 MMAs must have read it
+            tc::mbar_wait(&g3done, lt & 1u);   // the exchange area aliases stage 1 and the next tile rewrites the ring: every
+            tc::tc_fence_after();              // G3 MMA must have read its operands
             EX(6, cg, srow) = m1p2.x + m1p2.y;
             EX(7, cg, srow) = m2p2.x + m2p2.y;
             quarter_sync(wq);
@@ -1141,6 +1147,7 @@ int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaSt
     const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
     int grid = sm_count();
     if (grid <= 0) return fail("no CUDA device");
+    if (grid > kTcMaxCtas) grid = kTcMaxCtas;       // the workspace holds one activation stash per CTA
     if (tiles < grid) grid = (int)tiles;
     // dz2 ~ O(1..100) / global batch: a power of two 16x below the batch size brings it to O(0.1..10), four orders of
     // magnitude under fp16's largest value

@@ -123,6 +123,25 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- bulk copies (TMA, no tensor map): one thread moves a contiguous block; sizes and addresses multiples of 16 bytes ----
+// shared -> global, tracked by the thread's bulk groups
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the sources of all committed groups have been read (the shared-memory buffers may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed groups are complete (their global-memory writes included)
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// global -> shared, completion (byte count) signalled on an mbarrier of count 1
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    const uint32_t mb = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(mb) : "memory");
+}
+
 // ---- operand staging -----------------------------------------------------------------------
 // hi = RN_tf32(x) (ties away from zero, like cvt.rna.tf32.f32, which ptxas expands into 4 instructions
 // per value because of its Inf/NaN handling -- ncu r1b: 13 % of the update kernel's instructions).  Done
@@ -216,6 +235,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {      // D 
 // dz2 serve as A of both backward GEMMs of the update: K-major along the samples for G3 (dW2 = dz2^T h1), MN-major
 // along the outputs for G2 (dh1 = dz2 W2).
 __host__ __device__ constexpr uint32_t make_idesc_f16_a_mn(int M, int N) { return make_idesc_f16(M, N) | (1u << 15); }
+
+// B read MN-major (bit 16): a 16-byte slot of B holds 8 consecutive N for ONE k -- the form in which the update kernel's G3
+// reads a stashed forward-activation chunk (written K-major as A of G1: the same bytes).
+__host__ __device__ constexpr uint32_t make_idesc_f16_b_mn(int M, int N) { return make_idesc_f16(M, N) | (1u << 16); }
 
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {

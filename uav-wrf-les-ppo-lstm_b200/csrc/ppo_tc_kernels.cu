@@ -69,9 +69,11 @@ struct TcSmem {
     static constexpr int sc = dout + kTcTile * 8;                    // [128][4] rstd2, m1, m2, entropy term
     static constexpr int pf = sc + kTcTile * 4;                      // [128][12] next tile's gathered sample
     static constexpr int total = pf + kTcTile * 12;
-    // [groups][128][8] exchange of partial sums between the column groups of one sample row: aliases the last
-    // operand buffer of the ring, which is idle whenever it is used (no MMA in flight, no production running)
-    static constexpr int exch = ring + 7 * kChunkFloats;
+    // [groups][128][8] exchange of partial sums between the column groups of one sample row: aliases the last operand
+    // buffer of stage 0, which is idle whenever it is used (Ph3: G1 is complete and Ph4 has not yet written dz2 there;
+    // end of Ph6: every G2 / G3 MMA of the tile has completed).  Stage 1 is not available: the MMA thread prefetches the
+    // first W2^T chunks into it while Ph3 runs.
+    static constexpr int exch = ring + 3 * kChunkFloats;
 };
 static_assert(kTcGroups * kTcTile * 8 <= kChunkFloats, "exchange area must fit one operand buffer");
 static_assert(TcSmem::total * 4 + 64 <= 227 * 1024, "ppo_tc_kernel: shared memory plan exceeds 227 KB");
@@ -80,8 +82,8 @@ static_assert(kTcTile * kStageStride <= kTcTile * kXhStride, "dy1 staging must f
 // layout of the pre-split weight workspace (float units; fp16 hi / lo operand chunks of 128 rows x 64 K = 16 KB each)
 constexpr int kW2SplitG1Hi = 0;                       // [4 chunks][128 out][64 in]   (K = in), lo scaled by 2^11
 constexpr int kW2SplitG1Lo = 16384;
-constexpr int kW2SplitG2Hi = 32768;                   // [2 halves][2 chunks][128 in][64 out] (K = out), 16 W2^T, lo unscaled
-constexpr int kW2SplitG2Lo = 49152;
+constexpr int kW2SplitG2 = 32768;                     // [2 halves][2 chunks][hi, lo][128 in][64 out] (K = out), 16 W2^T, lo
+                                                      // unscaled; hi and lo of a chunk are contiguous: one 32 KB bulk copy
 constexpr int kW2SplitFloats = 65536;
 // per-launch invariants of layer 1, evaluated once by the last block of the prep kernel instead of by every CTA:
 constexpr int kWsW1c = kW2SplitFloats;                // [6][256] feature.0.weight minus its column means, k-major
@@ -217,14 +219,14 @@ __global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restric
         v0 = make_float4(w[0], w[1], w[2], w[3]);
         v1 = make_float4(w[4], w[5], w[6], w[7]);
         const int row = in & 127;
-        chunk_base = kW2SplitG2Hi + ((in >> 7) * 2 + (out0 >> 6)) * kChunkFloats;
+        chunk_base = kW2SplitG2 + ((in >> 7) * 2 + (out0 >> 6)) * 2 * kChunkFloats;
         f = (row >> 3) * 64 + ((out0 & 63) >> 3) * 8 + (row & 7);
         scale = 1.0f;
     }
     uint4 hi, lo;
     tc::split_f16x8(v0, v1, scale, hi, lo);
     reinterpret_cast<uint4*>(w2s + chunk_base)[f] = hi;
-    reinterpret_cast<uint4*>(w2s + chunk_base + (kW2SplitG1Lo - kW2SplitG1Hi))[f] = lo;
+    reinterpret_cast<uint4*>(w2s + chunk_base + (i < 4096 ? kW2SplitG1Lo - kW2SplitG1Hi : kChunkFloats))[f] = lo;
 }
 
 #ifdef PLUME_TC_MAXNREG
@@ -237,8 +239,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __shared__ uint64_t bar[2];           // "stage free": arrived by tcgen05.commit
     __shared__ uint64_t full[2];          // "operands of the stage written": one arrival per compute thread
     __shared__ uint64_t sdone[2];         // "the stage's activation chunk has been read by its bulk store to the stash"
-    __shared__ uint64_t hfull[2];         // "a stashed activation chunk has landed in this half of stage 1" (bulk-copy bytes)
-    __shared__ uint64_t hfree[2];         // "the G3 MMAs reading this half have completed"
+    __shared__ uint64_t bfull[2];         // "a bulk copy has landed in this half of stage 1" (W2^T chunk or stashed activations)
+    __shared__ uint64_t bfree[2];         // "the MMAs reading this half have completed"
+    __shared__ uint64_t dzfull;           // "Ph4 has written the tile's dz2 operand": one arrival per compute thread
+    __shared__ uint64_t g2half[2];        // "dh1 of inputs [128 h, 128 h + 128) is complete in TMEM"
     __shared__ uint64_t g3done;           // "every G3 MMA of the tile has completed"
     __shared__ uint32_t tmem_slot;
     __shared__ float cta_acc[48];         // per-CTA sums of the per-sample scalars (see the flush)
@@ -272,9 +276,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::mbar_init(&full[1], kTcThreads);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&sdone[i], 1);
-            tc::mbar_init(&hfull[i], 1);
-            tc::mbar_init(&hfree[i], 1);
+            tc::mbar_init(&bfull[i], 1);
+            tc::mbar_init(&bfree[i], 1);
+            tc::mbar_init(&g2half[i], 1);
         }
+        tc::mbar_init(&dzfull, kTcThreads);
         tc::mbar_init(&g3done, 1);
         tc::mbar_fence_init();
     }
@@ -378,11 +384,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     };
     // G2 ring step: A = resident dz2, MN-major, K = outputs [64 c, 64 c + 64); B = the step's W2^T chunk
     const uint32_t idesc_amn = tc::make_idesc_f16_a_mn(128, 128);
-    auto issue_g2 = [&](uint32_t st, uint32_t col, int c, bool first) {
-        while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
-        tc::tc_fence_after();
+    auto issue_g2 = [&](uint32_t half, uint32_t col, int c, bool first) {
         const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
-        const uint32_t bh = tc::smem_u32(bstage_buf(st, 0)), bl = tc::smem_u32(bstage_buf(st, 1));
+        const uint32_t bh = tc::smem_u32(bstage_buf(half, 0)), bl = tc::smem_u32(bstage_buf(half, 1));
 #pragma unroll
         for (int j = 0; j < tc::kChunkKH / 16; ++j) {
             const uint32_t aoff = (uint32_t)(8 * c + 2 * j) * 2048u, boff = j * 2 * tc::kLBO;
@@ -393,7 +397,6 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::mma_f16(tmem + col, dah, dbl, idesc_amn, 1u);
             tc::mma_f16(tmem + col, dah, dbh, idesc_amn, 1u);
         }
-        tc::mma_commit(&bar[st & 1u]);
     };
     // G3 for the 64 inputs of activation chunk c (N = 64, all 128 samples = 8 K-steps): A = resident dz2^T, K-major
     // along the samples; B = the stashed chunk in half `half` of stage 1 -- written K-major as A of G1 (slot (sg, u, s & 7)
@@ -427,10 +430,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     // lets the ring run on mbarriers only: producers never meet at a CTA barrier inside a GEMM)
     if (warp == kTcThreads / 32) {
         if (lane == 0) {
-            uint32_t st = 0;                   // producer steps so far: 8 per tile (G1 4, G2 4), so (st & 1) == (c & 1)
+            uint32_t st = 0;                   // producer steps so far: 4 per tile (G1), so (st & 1) == (c & 1)
+            uint32_t lt = 0;                   // tiles of this CTA so far
             char* const stash = reinterpret_cast<char*>(const_cast<float*>(w2s) + kWsStash) +
                                 (size_t)blockIdx.x * (size_t)kStashFloatsPerCta * 4;
-            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
                 const bool first_tile = (tile == (long long)blockIdx.x);
                 for (int c = 0; c < 4; ++c, ++st) {                                                      // G1
                     issue(st, 0u, c == 0);
@@ -441,33 +445,46 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     tc::bulk_wait_group_read_all();         // (this thread has nothing else to do until the next chunk is produced)
                     mbar_arrive(&sdone[st & 1u]);
                 }
-                for (int hN = 0; hN < 2; ++hN)
-                    for (int c = 0; c < 2; ++c, ++st) issue_g2(st, (uint32_t)(128 * hN), c, c == 0);    // G2
-                // G3: the four stashed chunks come back through the two halves of stage 1, which the G2 steps st - 2 (half 0)
-                // and st - 1 (half 1) read last; nothing for the compute warps to do
-                tc::bulk_wait_group_all();                  // the stash holds the tile's four chunks
-                for (int c = 0; c < 4; ++c) {
-                    const int half = c & 1;
-                    if (c < 2) {
-                        const uint32_t g2st = st - 2u + (uint32_t)c;
-                        tc::mbar_wait(&bar[g2st & 1u], (g2st >> 1) & 1u);
-                    } else {
-                        tc::mbar_wait(&hfree[half], 0u);    // the half's first G3 of this tile (two commits per tile and half)
-                    }
-                    tc::bulk_load(bstage_buf((uint32_t)half, 0), stash + (size_t)c * kStashChunkBytes, (uint32_t)kStashChunkBytes,
-                                  &hfull[half]);
-                    if (c >= 1) {                           // MMAs of the previous chunk, whose load was issued one round ago
-                        const int pc = c - 1;
-                        tc::mbar_wait(&hfull[pc & 1], (uint32_t)(pc >> 1));
+                // ---- backward: eight 32 KB bulk copies per tile go through the two halves of stage 1, in this order per half h:
+                // W2^T chunk h (G2, inputs 0..127), W2^T chunk 2 + h (G2, inputs 128..255), stashed activation chunks h and
+                // 2 + h (G3).  bfull / bfree see four phases per tile and half: the parity of phase k is k & 1.
+                tc::mbar_wait(&bar[1], 1u);                 // G1's last step (st - 1 = 4 lt + 3) has completed: stage 1 is free
+                const char* const w2t = reinterpret_cast<const char*>(w2s + kW2SplitG2);
+                tc::bulk_load(bstage_buf(0u, 0), w2t, (uint32_t)kStashChunkBytes, &bfull[0]);
+                tc::bulk_load(bstage_buf(1u, 0), w2t + kStashChunkBytes, (uint32_t)kStashChunkBytes, &bfull[1]);
+                while (!tc::mbar_try_wait(&dzfull, lt & 1u)) __nanosleep(100);     // Ph4 has written dz2
+                tc::tc_fence_after();
+                for (int hN = 0; hN < 2; ++hN) {                                                         // G2
+                    for (int c = 0; c < 2; ++c) {
+                        tc::mbar_wait(&bfull[c], (uint32_t)hN);
                         tc::tc_fence_after();
-                        issue_g3(pc & 1, (uint32_t)(256 + 64 * pc), first_tile);
-                        tc::mma_commit(&hfree[pc & 1]);
+                        issue_g2((uint32_t)c, (uint32_t)(128 * hN), c, c == 0);
+                        tc::mma_commit(&bfree[c]);
+                    }
+                    tc::mma_commit(&g2half[hN]);
+                    if (hN == 0) {
+                        for (int c = 0; c < 2; ++c) {
+                            tc::mbar_wait(&bfree[c], 0u);
+                            tc::bulk_load(bstage_buf((uint32_t)c, 0), w2t + (size_t)(2 + c) * kStashChunkBytes,
+                                          (uint32_t)kStashChunkBytes, &bfull[c]);
+                        }
                     }
                 }
-                tc::mbar_wait(&hfull[1], 1u);
-                tc::tc_fence_after();
-                issue_g3(1, (uint32_t)(256 + 64 * 3), first_tile);
-                tc::mma_commit(&hfree[1]);
+                // G3: the four stashed chunks; nothing for the compute warps to do
+                tc::bulk_wait_group_all();                  // the stash holds the tile's four chunks
+                for (int r = 0; r < 2; ++r) {
+                    for (int c = 0; c < 2; ++c) {
+                        tc::mbar_wait(&bfree[c], (uint32_t)((1 + r) & 1));
+                        tc::bulk_load(bstage_buf((uint32_t)c, 0), stash + (size_t)(2 * r + c) * kStashChunkBytes,
+                                      (uint32_t)kStashChunkBytes, &bfull[c]);
+                    }
+                    for (int c = 0; c < 2; ++c) {
+                        tc::mbar_wait(&bfull[c], (uint32_t)((2 + r) & 1));
+                        tc::tc_fence_after();
+                        issue_g3(c, (uint32_t)(256 + 64 * (2 * r + c)), first_tile);
+                        tc::mma_commit(&bfree[c]);
+                    }
+                }
                 tc::mma_commit(&g3done);
             }
         }
@@ -825,36 +842,22 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 dzl[f] = lo;
             }
         }
-        compute_sync();
+        // the tile's dz2 operand is complete: visible to the async proxy, hand over to the MMA thread, which runs G2 (B = the
+        // W2^T chunks it bulk-copies into the halves of stage 1; dh1 -> TMEM columns [0,256)) and then G3 (B = the stashed
+        // activation chunks; the accumulator holds dz_scale dW2 until the flush) on its own
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        mbar_arrive(&dzfull);
 
         PLUME_TL(5);
-        // ---- Ph5: G2 dh1 = dz2 . W2, two halves of the 256 inputs, K = 128 outputs in 2 chunks of 64 ------
-        // (A = the resident dz_scale dz2 operand read MN-major: nothing to produce; B = 16 W2^T chunks from L2, unscaled lo,
-        // one accumulator; both scales undone in Ph6)
-        for (int hN = 0; hN < 2; ++hN) {
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t st = step;
-                acquire(st);
-                load_b_into(bstage_buf(st, 0), bstage_buf(st, 1), w2s + kW2SplitG2Hi + (hN * 2 + c) * kChunkFloats,
-                            w2s + kW2SplitG2Lo + (hN * 2 + c) * kChunkFloats);
-                publish(st);
-                ++step;
-            }
-        }
-
         PLUME_TL(6);
-        // ---- G3 dW2 += dz2^T . h1 runs on the MMA thread alone: B = the stashed activation chunks, bulk-copied back into
-        // the halves of stage 1 as the G2 MMAs release them (A = the resident dz2^T operand; the accumulator holds dz_scale
-        // dW2 until the flush).  The compute warps only need dh1:
-        wait_all_mma();
-
         PLUME_TL(7);
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
-            tc::tc_fence_after();  // (the xhat2 / staging region was last read in Ph4, which ended with a barrier)
+            // (the xhat2 / staging region was last read in Ph4, which ended with a barrier)
             float2 m1p2 = f2(0.0f, 0.0f), m2p2 = f2(0.0f, 0.0f);         // even / odd inputs of this thread's slab
             const float2 un2 = splat2(1.0f / (dz_scale * kW2BwdScale));    // exact: both are powers of two
-            // this thread's sample: inputs + rstd1
+            // this thread's sample: inputs + rstd1 (for the per-sample scalars at the end)
             const float4 sx0 = *reinterpret_cast<const float4*>(xt + srow * 8);
             const float4 sx1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
             const float xs[6] = {sx0.x, sx0.y, sx0.z, sx0.w, sx1.x, sx1.y};
@@ -862,6 +865,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             const float2 srs2 = splat2(sx1.z);
 #pragma unroll
             for (int hN = 0; hN < 2; ++hN) {          // unrolled: Pacc[hN] must stay in registers
+                tc::mbar_wait(&g2half[hN], lt & 1u);   // dh1 of this half is complete (the other half's MMAs may still run)
+                tc::tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 * hN + CW * cg);
                 tc::tmem_ld32(taddr, v);
                 tc::tmem_ld_wait();

@@ -369,7 +369,13 @@ def test_packed_records_and_materialised_permutation_change_nothing(monkeypatch)
     assert la.shape == (cfg.epochs * 4, 4)
     # same samples in the same tiles; only the order of the cross-CTA float atomics differs between two launches
     assert np.allclose(la, lb, rtol=1e-6, atol=1e-9)
-    assert torch.allclose(pa, pb_, rtol=0, atol=5e-6), (pa - pb_).abs().max()      # (one Adam step moves a weight by <= 3e-5)
+    # (one Adam step moves a weight by <= 3e-5.)  The atomics' 1e-7 noise in a gradient moves the parameters by ~1e-10 after
+    # a step, which is enough to flip the ReLU mask of a sample whose LayerNorm-2 output lies that close to 0 (random data:
+    # nothing keeps it away from the kinks) -- ONE sample's contribution to one row of feature.3.weight then differs between
+    # two runs of the SAME path (profiles/debug/flaky_probe.py, step_probe.py: 4-10 of 24 identical runs, always the same
+    # row and the same 1.44e-5).  A wrong sample set would move every parameter: demand agreement of all but a handful.
+    diff = (pa - pb_).abs()
+    assert int((diff > 5e-6).sum()) <= 8 and float(diff.max()) < 1e-4, (int((diff > 5e-6).sum()), float(diff.max()))
     assert (pa - init.cpu()).abs().max() > 1e-5           # and the update did something
 
 

@@ -45,12 +45,20 @@
 #ifndef PLUME_U6
 #define PLUME_U6 4
 #endif
+// shape of the column-sum GEMM's instruction: M = 64 / N = 8 reads only the 64 real rows of its A operand; M = 128 / N = 16
+// (rows 64..127 and columns 8..15 garbage that nobody reads) is the form whose accumulator layout needs no explanation
+#ifndef PLUME_TC_PM
+#define PLUME_TC_PM 64
+#endif
+#ifndef PLUME_TC_PN
+#define PLUME_TC_PN 8
+#endif
 namespace plume {
 
 constexpr int kTcTile = 128;
 constexpr int kTcGroups = 4;                       // 128-thread groups of compute threads
 constexpr int kTcThreads = 128 * kTcGroups;        // compute threads (producers + epilogues): 16 warps
-constexpr int kTcLaunchThreads = kTcThreads + 32;  // + one warp whose lane 0 only issues the MMAs
+constexpr int kTcLaunchThreads = kTcThreads + 64;  // + two warps whose lane 0 only issues MMAs (G1/G2/G3; column-sum GEMM)
 constexpr int kXhStride = 132;             // [128][132]: conflict-free float4 rows and columns
 constexpr int kStageStride = 132;          // [128][132]: transposed dy1 staging (conflict-free scalar stores along the
                                            // samples, float4 loads along the samples of one input)
@@ -244,6 +252,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __shared__ uint64_t dzfull;           // "Ph4 has written the tile's dz2 operand": one arrival per compute thread
     __shared__ uint64_t g2half[2];        // "dh1 of inputs [128 h, 128 h + 128) is complete in TMEM"
     __shared__ uint64_t g3done;           // "every G3 MMA of the tile has completed"
+    __shared__ uint64_t dyfull[2];        // "the dy1 operand chunk in this buffer is written": one arrival per compute thread
+    __shared__ uint64_t pdone[2];         // "the column-sum MMAs reading this buffer have completed"
     __shared__ uint32_t tmem_slot;
     __shared__ float cta_acc[48];         // per-CTA sums of the per-sample scalars (see the flush)
     __shared__ double cta_loss[4];
@@ -279,6 +289,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::mbar_init(&bfull[i], 1);
             tc::mbar_init(&bfree[i], 1);
             tc::mbar_init(&g2half[i], 1);
+            tc::mbar_init(&dyfull[i], kTcThreads);
+            tc::mbar_init(&pdone[i], 1);
         }
         tc::mbar_init(&dzfull, kTcThreads);
         tc::mbar_init(&g3done, 1);
@@ -373,15 +385,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         tc::tc_fence_before();
         mbar_arrive(&full[st & 1u]);
     };
-    // issuer (one thread): wait for the arrivals of step st, issue its 12 MMAs (main and cross terms in one accumulator:
-    // both operands are O(1), lo unscaled), commit to "stage free"
-    auto issue = [&](uint32_t st, uint32_t col, bool first) {
-        // (the issuer shares a scheduler with four producer warps: back off between polls instead of spinning)
-        while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(200);
-        tc::tc_fence_after();
-        tc::mma_chunk_f16(tmem + col, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3), idesc, first);
-        tc::mma_commit(&bar[st & 1u]);
-    };
+    // (the MMA threads share their schedulers with compute warps: they back off between polls instead of spinning)
+#ifndef PLUME_TC_POLL_NS
+#define PLUME_TC_POLL_NS 40
+#endif
     // G2 ring step: A = resident dz2, MN-major, K = outputs [64 c, 64 c + 64); B = the step's W2^T chunk
     const uint32_t idesc_amn = tc::make_idesc_f16_a_mn(128, 128);
     auto issue_g2 = [&](uint32_t half, uint32_t col, int c, bool first) {
@@ -437,23 +444,35 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
                 const bool first_tile = (tile == (long long)blockIdx.x);
                 for (int c = 0; c < 4; ++c, ++st) {                                                      // G1
-                    issue(st, 0u, c == 0);
+                    while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(PLUME_TC_POLL_NS);
+                    tc::tc_fence_after();
                     // stash the activation chunk (A_hi, A_lo of the stage: 32 KB contiguous); the producers' fence.proxy.async
                     // + the `full` barrier made their writes visible to the async proxy
                     tc::bulk_store(stash + (size_t)c * kStashChunkBytes, stage_buf(st, 0), (uint32_t)kStashChunkBytes);
                     tc::bulk_commit_group();
+                    tc::mma_chunk_f16(tmem, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3), idesc, c == 0);
+                    tc::mma_commit(&bar[st & 1u]);
                     tc::bulk_wait_group_read_all();         // (this thread has nothing else to do until the next chunk is produced)
                     mbar_arrive(&sdone[st & 1u]);
                 }
                 // ---- backward: eight 32 KB bulk copies per tile go through the two halves of stage 1, in this order per half h:
                 // W2^T chunk h (G2, inputs 0..127), W2^T chunk 2 + h (G2, inputs 128..255), stashed activation chunks h and
                 // 2 + h (G3).  bfull / bfree see four phases per tile and half: the parity of phase k is k & 1.
+#ifdef PLUME_TC_TIMELINE
+                long long is_[24];
+                const bool is_on = blockIdx.x == 0 && lt == 3;
+#define PLUME_IS(n) if (is_on) is_[n] = clock64()
+#else
+#define PLUME_IS(n)
+#endif
                 tc::mbar_wait(&bar[1], 1u);                 // G1's last step (st - 1 = 4 lt + 3) has completed: stage 1 is free
+                PLUME_IS(0);
                 const char* const w2t = reinterpret_cast<const char*>(w2s + kW2SplitG2);
                 tc::bulk_load(bstage_buf(0u, 0), w2t, (uint32_t)kStashChunkBytes, &bfull[0]);
                 tc::bulk_load(bstage_buf(1u, 0), w2t + kStashChunkBytes, (uint32_t)kStashChunkBytes, &bfull[1]);
-                while (!tc::mbar_try_wait(&dzfull, lt & 1u)) __nanosleep(100);     // Ph4 has written dz2
+                while (!tc::mbar_try_wait(&dzfull, lt & 1u)) __nanosleep(PLUME_TC_POLL_NS);     // Ph4 has written dz2
                 tc::tc_fence_after();
+                PLUME_IS(1);
                 for (int hN = 0; hN < 2; ++hN) {                                                         // G2
                     for (int c = 0; c < 2; ++c) {
                         tc::mbar_wait(&bfull[c], (uint32_t)hN);
@@ -462,9 +481,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                         tc::mma_commit(&bfree[c]);
                     }
                     tc::mma_commit(&g2half[hN]);
+                    PLUME_IS(2 + 3 * hN);
                     if (hN == 0) {
                         for (int c = 0; c < 2; ++c) {
                             tc::mbar_wait(&bfree[c], 0u);
+                            PLUME_IS(3 + c);
                             tc::bulk_load(bstage_buf((uint32_t)c, 0), w2t + (size_t)(2 + c) * kStashChunkBytes,
                                           (uint32_t)kStashChunkBytes, &bfull[c]);
                         }
@@ -475,28 +496,69 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 for (int r = 0; r < 2; ++r) {
                     for (int c = 0; c < 2; ++c) {
                         tc::mbar_wait(&bfree[c], (uint32_t)((1 + r) & 1));
+                        PLUME_IS(6 + 4 * r + c);
                         tc::bulk_load(bstage_buf((uint32_t)c, 0), stash + (size_t)(2 * r + c) * kStashChunkBytes,
                                       (uint32_t)kStashChunkBytes, &bfull[c]);
                     }
                     for (int c = 0; c < 2; ++c) {
                         tc::mbar_wait(&bfull[c], (uint32_t)((2 + r) & 1));
+                        PLUME_IS(8 + 4 * r + c);
                         tc::tc_fence_after();
                         issue_g3(c, (uint32_t)(256 + 64 * (2 * r + c)), first_tile);
                         tc::mma_commit(&bfree[c]);
                     }
                 }
                 tc::mma_commit(&g3done);
+#ifdef PLUME_TC_TIMELINE
+                if (is_on) {
+                    tc::mbar_wait(&g3done, lt & 1u);
+                    const long long e = clock64();
+                    printf("issuer (cycles after G1 done): dz ready %lld | G2h0 issued %lld | bfree0 %lld | bfree1 %lld | G2h1 issued %lld | "
+                           "G3: bfree0 %lld bfree1 %lld | H0 landed %lld H1 landed %lld | bfree0 %lld bfree1 %lld | H2 landed %lld H3 landed "
+                           "%lld | all done %lld\n", is_[1] - is_[0], is_[2] - is_[0], is_[3] - is_[0], is_[4] - is_[0], is_[5] - is_[0],
+                           is_[6] - is_[0], is_[7] - is_[0], is_[8] - is_[0], is_[9] - is_[0], is_[10] - is_[0], is_[11] - is_[0],
+                           is_[12] - is_[0], is_[13] - is_[0], e - is_[0]);
+                }
+#endif
+            }
+        }
+    } else if (warp == kTcThreads / 32 + 1) {
+        // ---- the column-sum GEMM of the LayerNorm-1 backward (its own issuing thread: its operands become ready while the
+        // other MMA thread sits in the bulk-copy waits of G3) -----------------------------------------------------------------
+        //   P[i][c] = sum_s dy1[s][i] X[s][c],   X[s][.] = {rstd1 x_0..x_5, rstd1, 1}
+        // per chunk of 64 inputs: A = the dy1 chunk written by Ph6 (fp16 hi / lo in the layout of an activation chunk, read
+        // MN-major with M = inputs: next 8 inputs 128 bytes on, next 8 samples 1024 bytes on; the instruction's M is 128, rows
+        // 64..127 read whatever follows and land in TMEM lanes that nobody reads), B = X (one 16-byte slot per sample, read
+        // MN-major with N = 16: columns 8..15 are the next sample's slot, ignored), K = the tile's 128 samples; the result
+        // overwrites the first 16 of the chunk's own dh1 columns, which every thread has consumed by then.
+        if (lane == 0) {
+            const uint32_t idesc_p = tc::make_idesc_f16(PLUME_TC_PM, PLUME_TC_PN) | (1u << 15) | (1u << 16);
+            const uint32_t xph = tc::smem_u32(sm + TcSmem::x), xpl = xph + 2048u;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int c = 0; c < 4; ++c) {
+                    while (!tc::mbar_try_wait(&dyfull[c & 1], (uint32_t)(c >> 1))) __nanosleep(PLUME_TC_POLL_NS);
+                    tc::tc_fence_after();
+                    const uint32_t ah = tc::smem_u32(sm + TcSmem::xh) + (uint32_t)(c & 1) * 32768u, al = ah + 16384u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t aoff = (uint32_t)(2 * j) * 1024u, boff = (uint32_t)(2 * j) * 128u;
+                        const uint64_t dah = tc::make_smem_desc(ah + aoff, 1024, 128), dal = tc::make_smem_desc(al + aoff, 1024, 128);
+                        const uint64_t dbh = tc::make_smem_desc(xph + boff, 128, 16), dbl = tc::make_smem_desc(xpl + boff, 128, 16);
+                        tc::mma_f16(tmem + (uint32_t)(64 * c), dal, dbh, idesc_p, j == 0 ? 0u : 1u);
+                        tc::mma_f16(tmem + (uint32_t)(64 * c), dah, dbl, idesc_p, 1u);
+                        tc::mma_f16(tmem + (uint32_t)(64 * c), dah, dbh, idesc_p, 1u);
+                    }
+                    tc::mma_commit(&pdone[c & 1]);
+                }
             }
         }
     } else {
     // ---- persistent accumulators (everything else is reduced into shared memory tile by tile) -----------
     float g_b2 = 0.0f, g_g2 = 0.0f, g_be2 = 0.0f;                                  // (output r128, sample group ug)
     float2 g_wh2[3] = {f2(0.0f, 0.0f), f2(0.0f, 0.0f), f2(0.0f, 0.0f)};           // head-weight gradients, 3 pairs
-    float2 Pacc[2][4];                               // 8 column sums as 4 pairs (input r128 + 128 h, group ug)
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Pacc[h][c] = f2(0.0f, 0.0f);
+    float Pacc[8];                                   // the 8 column sums of input 64 cg + 16 wq + lane (lanes 0..15),
+#pragma unroll                                        // in units of dz_scale * kW2BwdScale
+    for (int c = 0; c < 8; ++c) Pacc[c] = 0.0f;
 
     float* const pf = sm + TcSmem::pf;
     // gather of one tile's samples into pf with 4-byte cp.async (one thread per sample; rows beyond the minibatch = 0);
@@ -854,26 +916,43 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         PLUME_TL(7);
         // ---- Ph6: LN1 backward: dy1 from TMEM, per-sample means, column sums P through shared memory -----
         {
-            // (the xhat2 / staging region was last read in Ph4, which ended with a barrier)
             float2 m1p2 = f2(0.0f, 0.0f), m2p2 = f2(0.0f, 0.0f);         // even / odd inputs of this thread's slab
             const float2 un2 = splat2(1.0f / (dz_scale * kW2BwdScale));    // exact: both are powers of two
-            // this thread's sample: inputs + rstd1 (for the per-sample scalars at the end)
+            // this thread's sample: inputs + rstd1
             const float4 sx0 = *reinterpret_cast<const float4*>(xt + srow * 8);
             const float4 sx1 = *reinterpret_cast<const float4*>(xt + srow * 8 + 4);
             const float xs[6] = {sx0.x, sx0.y, sx0.z, sx0.w, sx1.x, sx1.y};
             const float2 xs2[6] = {splat2(sx0.x), splat2(sx0.y), splat2(sx0.z), splat2(sx0.w), splat2(sx1.x), splat2(sx1.y)};
             const float2 srs2 = splat2(sx1.z);
+            // The B operand of the column-sum GEMM takes the place of the x tile (nobody reads it after this point): per sample
+            // one 16-byte slot of fp16 hi and one of lo holding X[s][.] = {rstd1 x_0..x_5, rstd1, 1}.
+            compute_sync();
+            if (tid < kTcTile) {           // tid < 128: srow == tid, cg == 0
+                const float r = sx1.z;
+                uint4 hi, lo;
+                tc::split_f16x8(make_float4(r * sx0.x, r * sx0.y, r * sx0.z, r * sx0.w), make_float4(r * sx1.x, r * sx1.y, r, 1.0f),
+                                1.0f, hi, lo);
+                reinterpret_cast<uint4*>(xt)[tid] = hi;
+                reinterpret_cast<uint4*>(xt)[kTcTile + tid] = lo;
+            }
+            // Per chunk c of 64 inputs: thread = (sample srow, the 16 inputs 64 c + 16 cg ..).  dh1 comes from the TMEM columns
+            // of those inputs, the ReLU mask and xhat1 from a re-evaluation of layer 1; the masked dh1 (still in units of
+            // dz_scale * kW2BwdScale, O(1)) goes, split into fp16 hi / lo, into the chunk's operand buffer (the xhat2 / staging
+            // region: two buffers of 32 KB) as A of the column-sum GEMM, which the second MMA thread issues as soon as all
+            // compute threads have arrived.  No CTA barrier inside the loop.
 #pragma unroll
-            for (int hN = 0; hN < 2; ++hN) {          // unrolled: Pacc[hN] must stay in registers
-                tc::mbar_wait(&g2half[hN], lt & 1u);   // dh1 of this half is complete (the other half's MMAs may still run)
-                tc::tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 * hN + CW * cg);
-                tc::tmem_ld32(taddr, v);
+            for (int c = 0; c < 4; ++c) {
+                if ((c & 1) == 0) {
+                    tc::mbar_wait(&g2half[c >> 1], lt & 1u);   // dh1 of this half is complete (the other half's MMAs may still run)
+                    tc::tc_fence_after();
+                }
+                float dv[16];
+                tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * c + 16 * cg), dv);
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
 #pragma unroll
-                for (int j4 = 0; j4 < CW / 4; ++j4) {
-                    const int in0 = 128 * hN + CW * cg + 4 * j4;
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int in0 = 64 * c + 16 * cg + 4 * j4;
                     const float4 b = *reinterpret_cast<const float4*>(P1 + in0);
                     float2 zz[2] = {f2(b.x, b.y), f2(b.z, b.w)};
 #pragma unroll
@@ -889,42 +968,46 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     for (int jj = 0; jj < 2; ++jj) {
                         const float2 x_hat = __fmul2_rn(zz[jj], srs2);
                         const float2 y = __ffma2_rn(x_hat, gg[jj], bb[jj]);
-                        const float2 du = __fmul2_rn(f2(v[4 * j4 + 2 * jj], v[4 * j4 + 2 * jj + 1]), un2);
-                        const float2 dy = f2(y.x > 0.0f ? du.x : 0.0f, y.y > 0.0f ? du.y : 0.0f);
-                        const float2 t = __fmul2_rn(dy, gg[jj]);
+                        const float d0 = y.x > 0.0f ? dv[4 * j4 + 2 * jj] : 0.0f;
+                        const float d1 = y.y > 0.0f ? dv[4 * j4 + 2 * jj + 1] : 0.0f;
+                        dv[4 * j4 + 2 * jj] = d0;
+                        dv[4 * j4 + 2 * jj + 1] = d1;
+                        const float2 t = __fmul2_rn(__fmul2_rn(f2(d0, d1), un2), gg[jj]);
                         m1p2 = __fadd2_rn(m1p2, t);
                         m2p2 = __ffma2_rn(t, x_hat, m2p2);
-                        xh[(CW * cg + 4 * j4 + 2 * jj) * kStageStride + srow] = dy.x;     // staging [input][sample]
-                        xh[(CW * cg + 4 * j4 + 2 * jj + 1) * kStageStride + srow] = dy.y;
                     }
                 }
-                compute_sync();
-                PLUME_TL(14 + 2 * hN);
-                // column sums: thread = (input r128 of this half, 128/G of the 128 samples)
-PLUME_UNROLL(PLUME_U6)
-                for (int q4 = 0; q4 < SPT / 4; ++q4) {
-                    const int s0 = SPT * ug + 4 * q4;
-                    const float4 dy4 = *reinterpret_cast<const float4*>(xh + r128 * kStageStride + s0);
-                    const float dys[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+                if (c >= 2) tc::mbar_wait(&pdone[c & 1], 0u);       // the column-sum MMAs of chunk c - 2 have read the buffer
+                uint4* const dyh = reinterpret_cast<uint4*>(xh + (c & 1) * 8192);
+                uint4* const dyl = dyh + 1024;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float dy = dys[i];
-                        const float4 y0 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8);
-                        const float4 y1 = *reinterpret_cast<const float4*>(xt + (s0 + i) * 8 + 4);
-                        const float dr = dy * y1.z;
-                        const float2 dr2 = splat2(dr);
-                        Pacc[hN][0] = __ffma2_rn(dr2, f2(y0.x, y0.y), Pacc[hN][0]);
-                        Pacc[hN][1] = __ffma2_rn(dr2, f2(y0.z, y0.w), Pacc[hN][1]);
-                        Pacc[hN][2] = __ffma2_rn(dr2, f2(y1.x, y1.y), Pacc[hN][2]);
-                        Pacc[hN][3] = __fadd2_rn(Pacc[hN][3], f2(dr, dy));
-                    }
+                for (int uu = 0; uu < 2; ++uu) {
+                    uint4 hi, lo;
+                    tc::split_f16x8(make_float4(dv[8 * uu], dv[8 * uu + 1], dv[8 * uu + 2], dv[8 * uu + 3]),
+                                    make_float4(dv[8 * uu + 4], dv[8 * uu + 5], dv[8 * uu + 6], dv[8 * uu + 7]), 1.0f, hi, lo);
+                    const int f = (srow >> 3) * 64 + (2 * cg + uu) * 8 + (srow & 7);
+                    dyh[f] = hi;
+                    dyl[f] = lo;
                 }
-                compute_sync();
-                PLUME_TL(15 + 2 * hN);
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                mbar_arrive(&dyfull[c & 1]);
+                PLUME_TL(14 + c);
             }
         PLUME_TL(8);
             tc::mbar_wait(&g3done, lt & 1u);   // the exchange area aliases stage 1 and the next tile rewrites the ring: every
             tc::tc_fence_after();              // G3 MMA must have read its operands
+            tc::mbar_wait(&pdone[0], 1u);      // the column-sum GEMMs of chunks 2 and 3 (and with them 0 and 1) are complete
+            tc::mbar_wait(&pdone[1], 1u);
+            tc::tc_fence_after();
+            {                                  // an M = 64 accumulator keeps row r in TMEM lane 32 (r / 16) + r % 16: lanes 0..15
+                float pv[8];                   // of warp (wq, cg) hold inputs 64 cg + 16 wq .. of chunk cg
+                tc::tmem_ld8(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * cg), pv);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) Pacc[k] += pv[k];      // (lanes 16..31 accumulate columns nobody reads)
+            }
             EX(6, cg, srow) = m1p2.x + m1p2.y;
             EX(7, cg, srow) = m2p2.x + m2p2.y;
             quarter_sync(wq);
@@ -1043,12 +1126,18 @@ PLUME_UNROLL(PLUME_U6)
     }
     // layer 1: combine the sample groups of P and the CTA's per-sample scalar sums
     compute_sync();
-    float* pbuf = xh;                      // [G][256 inputs][8]
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<float2*>(pbuf + (ug * 256 + 128 * h + r128) * 8 + 2 * c) = Pacc[h][c];
+    float* pbuf = xh;                      // [256 inputs][8]
+#if PLUME_TC_PM == 64
+    if (lane < 16) {
+        const int in = 64 * cg + 16 * wq + lane;
+#else
+    if (wq < 2) {                          // an M = 128 accumulator keeps row r in lane r
+        const int in = 64 * cg + 32 * wq + lane;
+#endif
+        const float unp = 1.0f / (dz_scale * kW2BwdScale);
+        *reinterpret_cast<float4*>(pbuf + in * 8) = make_float4(Pacc[0] * unp, Pacc[1] * unp, Pacc[2] * unp, Pacc[3] * unp);
+        *reinterpret_cast<float4*>(pbuf + in * 8 + 4) = make_float4(Pacc[4] * unp, Pacc[5] * unp, Pacc[6] * unp, Pacc[7] * unp);
+    }
     compute_sync();
     if (tid < 4) {                       // total = policy + value - beta * entropy (train_ppo2.0.py:82)
         const double lsum = tid == 0 ? cta_loss[1] + cta_loss[2] - (double)a.entropy_beta * cta_loss[3] : cta_loss[tid];
@@ -1063,12 +1152,7 @@ PLUME_UNROLL(PLUME_U6)
         const int in = tid;                  // 256 threads = 256 layer-1 outputs
         float P[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float t = 0.0f;
-#pragma unroll
-            for (int gq = 0; gq < G; ++gq) t += pbuf[(gq * 256 + in) * 8 + c];
-            P[c] = t;
-        }
+        for (int c = 0; c < 8; ++c) P[c] = pbuf[in * 8 + c];
         float w[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) w[k] = W1c[k * 256 + in];

@@ -34,6 +34,8 @@
 // Build-time knobs (measured defaults, profiles/r1_notes.md): PLUME_U4 / PLUME_U6 unroll factors of the two
 // column-oriented loops, PLUME_TC_MAXNREG (register-sensitivity experiment), PLUME_TC_TMA_B (TMA bulk copies for the
 // B operand), PLUME_TC_TIMELINE (clock64 stamps per phase, printed by CTA 0).
+#include <cuda.h>            // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
+
 #include "ppo_loss.cuh"
 #include "tc_gemm.cuh"
 
@@ -88,8 +90,8 @@ static_assert(TcSmem::total * 4 + 64 <= 227 * 1024, "ppo_tc_kernel: shared memor
 static_assert(kTcTile * kStageStride <= kTcTile * kXhStride, "dy1 staging must fit in the xhat region");
 
 // layout of the pre-split weight workspace (float units; fp16 hi / lo operand chunks of 128 rows x 64 K = 16 KB each)
-constexpr int kW2SplitG1Hi = 0;                       // [4 chunks][128 out][64 in]   (K = in), lo scaled by 2^11
-constexpr int kW2SplitG1Lo = 16384;
+constexpr int kW2SplitG1 = 0;                         // [4 chunks][hi, lo][128 out][64 in] (K = in), 16 W2, lo unscaled; hi and
+                                                      // lo of a chunk are contiguous: one 32 KB bulk copy
 constexpr int kW2SplitG2 = 32768;                     // [2 halves][2 chunks][hi, lo][128 in][64 out] (K = out), 16 W2^T, lo
                                                       // unscaled; hi and lo of a chunk are contiguous: one 32 KB bulk copy
 constexpr int kW2SplitFloats = 65536;
@@ -97,7 +99,12 @@ constexpr int kW2SplitFloats = 65536;
 constexpr int kWsW1c = kW2SplitFloats;                // [6][256] feature.0.weight minus its column means, k-major
 constexpr int kWsB1c = kWsW1c + 6 * 256;              // [256]    feature.0.bias minus its mean
 constexpr int kWsLn1q = kWsB1c + 256;                 // [28] doubles: the LayerNorm-1 quadratic form (see ln1q below)
-constexpr int kWsStash = (kWsLn1q + 2 * 28 + 63) & ~63;   // per-CTA activation stash (below), 256-byte aligned
+// B operands of the layer-1 GEMM (below): per chunk of 64 inputs [B1 2 KB][B2 2 KB], row n = input, two 16-byte K slots
+// per row at (n >> 3) * 256 + slot * 128 + (n & 7) * 16 bytes: B1 = [w_hi | w_hi], B2 = [w_lo | 0] with w = (centred
+// feature.0.weight row, centred bias, 0)
+constexpr int kWsL1Ops = (kWsLn1q + 2 * 28 + 63) & ~63;
+constexpr int kL1OpsFloats = 4 * 1024;                                  // 16 KB
+constexpr int kWsStash = kWsL1Ops + kL1OpsFloats;          // per-CTA activation stash (below), 256-byte aligned
 // The forward activations h1 of a tile are produced ONCE, as the A operand of G1 (four 32 KB chunks: fp16 hi + lo of
 // 128 samples x 64 inputs).  Each chunk is copied to this L2-resident scratch by a bulk copy (cp.async.bulk, issued by
 // the MMA thread) as soon as its MMAs are issued, and comes back by a bulk copy as the B operand of G3 (read MN-major:
@@ -174,6 +181,16 @@ __global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restric
 #pragma unroll
         for (int k = 0; k < 6; ++k) w2s[kWsW1c + k * 256 + o] = w[k];
         w2s[kWsB1c + o] = w[6];
+        {   // B operands of the layer-1 GEMM: z1c[s][o] = sum_k x_k w_ok + b_o as [x_hi | x_lo] . [w_hi | w_hi] + [x_hi | x_lo] . [w_lo | 0]
+            uint4 hi, lo;
+            tc::split_f16x8(make_float4(w[0], w[1], w[2], w[3]), make_float4(w[4], w[5], w[6], 0.0f), 1.0f, hi, lo);
+            uint4* ops = reinterpret_cast<uint4*>(w2s + kWsL1Ops) + (o >> 6) * 256;      // 4 KB per chunk of 64 inputs
+            const int n = o & 63, f = (n >> 3) * 16 + (n & 7);
+            ops[f] = hi;
+            ops[f + 8] = hi;
+            ops[128 + f] = lo;
+            ops[128 + f + 8] = make_uint4(0u, 0u, 0u, 0u);
+        }
         double q[28];
         const double b = (double)w[6];
         q[0] = b * b;
@@ -216,7 +233,7 @@ __global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restric
         v1 = *reinterpret_cast<const float4*>(params + PLUME_OFF_W2 + o * 256 + in0 + 4);
         v0 = make_float4(kW2BwdScale * v0.x, kW2BwdScale * v0.y, kW2BwdScale * v0.z, kW2BwdScale * v0.w);
         v1 = make_float4(kW2BwdScale * v1.x, kW2BwdScale * v1.y, kW2BwdScale * v1.z, kW2BwdScale * v1.w);
-        chunk_base = kW2SplitG1Hi + (in0 >> 6) * kChunkFloats;
+        chunk_base = kW2SplitG1 + (in0 >> 6) * 2 * kChunkFloats;
         f = (o >> 3) * 64 + ((in0 & 63) >> 3) * 8 + (o & 7);
         scale = 1.0f;
     } else {                                          // G2: row = in (two halves of 128), K = out, values 16 W2[out][in]
@@ -234,7 +251,7 @@ __global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restric
     uint4 hi, lo;
     tc::split_f16x8(v0, v1, scale, hi, lo);
     reinterpret_cast<uint4*>(w2s + chunk_base)[f] = hi;
-    reinterpret_cast<uint4*>(w2s + chunk_base + (i < 4096 ? kW2SplitG1Lo - kW2SplitG1Hi : kChunkFloats))[f] = lo;
+    reinterpret_cast<uint4*>(w2s + chunk_base + kChunkFloats)[f] = lo;
 }
 
 #ifdef PLUME_TC_MAXNREG
@@ -242,7 +259,8 @@ __global__ void __maxnreg__(PLUME_TC_MAXNREG)
 #else
 __global__ void __launch_bounds__(kTcLaunchThreads, 1)
 #endif
-ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s, float dz_scale) {
+ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restrict__ w2s, float dz_scale,
+              const __grid_constant__ CUtensorMap stash_map) {
     extern __shared__ __align__(128) float sm[];     // no-swizzle operand layouts need 16 B alignment only
     __shared__ uint64_t bar[2];           // "stage free": arrived by tcgen05.commit
     __shared__ uint64_t full[2];          // "operands of the stage written": one arrival per compute thread
@@ -252,6 +270,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __shared__ uint64_t dzfull;           // "Ph4 has written the tile's dz2 operand": one arrival per compute thread
     __shared__ uint64_t g2half[2];        // "dh1 of inputs [128 h, 128 h + 128) is complete in TMEM"
     __shared__ uint64_t g3done;           // "every G3 MMA of the tile has completed"
+    __shared__ uint64_t x0full;           // "Ph0 has written the tile's x operand of the layer-1 GEMM": one arrival per compute thread
+    __shared__ uint64_t l1full;           // "the layer-1 B operands have landed" (bulk-copy bytes)
+    __shared__ uint64_t zfull[2];         // "the layer-1 pre-activations of a chunk are complete in this TMEM buffer"
+    __shared__ uint64_t wfull[2];         // "the W2 chunk of a G1 step has landed in the stage's B buffers" (bulk-copy bytes)
     __shared__ uint64_t dyfull[2];        // "the dy1 operand chunk in this buffer is written": one arrival per compute thread
     __shared__ uint64_t pdone[2];         // "the column-sum MMAs reading this buffer have completed"
     __shared__ uint32_t tmem_slot;
@@ -290,9 +312,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::mbar_init(&bfree[i], 1);
             tc::mbar_init(&g2half[i], 1);
             tc::mbar_init(&dyfull[i], kTcThreads);
+            tc::mbar_init(&zfull[i], 1);
+            tc::mbar_init(&wfull[i], 1);
             tc::mbar_init(&pdone[i], 1);
         }
         tc::mbar_init(&dzfull, kTcThreads);
+        tc::mbar_init(&x0full, kTcThreads);
+        tc::mbar_init(&l1full, 1);
         tc::mbar_init(&g3done, 1);
         tc::mbar_fence_init();
     }
@@ -346,10 +372,15 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     float* const xt = sm + TcSmem::x;
 
     uint32_t step = 0;        // ring steps so far (every compute thread counts them identically)
-    // stage buffers of ring step st: which = 0 A_hi, 1 A_lo, 2 B_hi, 3 B_lo
-    auto stage_buf = [&](uint32_t st, int which) -> float* {
-        return sm + TcSmem::ring + ((st & 1u) * 4 + which) * kChunkFloats;
-    };
+    // Forward (G1) use of the ring.  First 64 KB = the two A stages: stage q = [A_hi 16 KB][A_lo 16 KB], the activation chunk
+    // c = 2 p + q in the canonical K-major layout (slot (sg, u, s & 7) at sg * 1024 + u * 128 + (s & 7) * 16 bytes = h1[s][64 c
+    // + 8 u .. + 7]).  ONE tensor copy per chunk (cp.async.bulk.tensor, 5-D map built by launch_ppo_tc) scatters the stage
+    // into the stash, where the two chunks of a pair (128 inputs) are interleaved per group of 8 samples -- slot (sg, q, u,
+    // s & 7) at sg * 2048 + q * 1024 + u * 128 + (s & 7) * 16 bytes, hi in the pair's first 32 KB, lo in the second -- so that
+    // a pair comes back as ONE MN-major B operand with N = 128 for G3 (next 8 inputs 128 bytes on, next 8 samples 2048 bytes
+    // on).  Second 64 KB = the B stages: stage q holds a W2 chunk as [B_hi 16 KB][B_lo 16 KB].
+    auto a_stage = [&](uint32_t st) -> float* { return sm + TcSmem::ring + (st & 1u) * 2 * kChunkFloats; };
+    auto b_stage = [&](uint32_t st) -> float* { return sm + TcSmem::ring + (4 + (st & 1u) * 2) * kChunkFloats; };
     // Backward GEMMs (G2, G3): stage 0 of the ring (64 KB) holds the RESIDENT dz2 operand of the tile -- 16-byte slot
     // (og, sg, o & 7) at og * 2048 + sg * 128 + (o & 7) * 16 bytes = dz_scale dz2[8 sg .. 8 sg + 7][o], og = o >> 3,
     // sg = s >> 3; hi in the first 32 KB, lo in the second -- written once by Ph4.  G3 reads it K-major along the samples
@@ -366,21 +397,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         const uint32_t use = st >> 1;
         if (use >= 1) tc::mbar_wait(&bar[st & 1u], (use - 1) & 1u);
     };
-    // B operand chunk (hi + lo, 16 KB each) from the pre-split weights, cp.async straight into shared memory
-    auto load_b_into = [&](float* dst_hi, float* dst_lo, const float* hi, const float* lo) {
-        float4* bh4 = reinterpret_cast<float4*>(dst_hi);
-        float4* bl4 = reinterpret_cast<float4*>(dst_lo);
-        const float4* gh = reinterpret_cast<const float4*>(hi);
-        const float4* gl = reinterpret_cast<const float4*>(lo);
-#pragma unroll
-        for (int q = 0; q < 1024 / kTcThreads; ++q) {
-            cp_async16(bh4 + tid + q * kTcThreads, gh + tid + q * kTcThreads);
-            cp_async16(bl4 + tid + q * kTcThreads, gl + tid + q * kTcThreads);
-        }
-    };
     // producers: the operands of step st are complete in shared memory -> visible to the async proxy, arrive
     auto publish = [&](uint32_t st) {
-        cp_async_wait_all();
         tc::fence_proxy_async();
         tc::tc_fence_before();
         mbar_arrive(&full[st & 1u]);
@@ -405,19 +423,17 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::mma_f16(tmem + col, dah, dbh, idesc_amn, 1u);
         }
     };
-    // G3 for the 64 inputs of activation chunk c (N = 64, all 128 samples = 8 K-steps): A = resident dz2^T, K-major
-    // along the samples; B = the stashed chunk in half `half` of stage 1 -- written K-major as A of G1 (slot (sg, u, s & 7)
-    // at sg * 1024 + u * 128 + (s & 7) * 16 bytes = h1[s][64 c + 8 u .. + 7]), read here MN-major (N = inputs: next 8
-    // inputs 128 bytes on, next 8 samples 1024 bytes on)
-    const uint32_t idesc_g3 = tc::make_idesc_f16_b_mn(128, 64);
-    auto issue_g3 = [&](int half, uint32_t col, bool first) {
+    // G3 for the 128 inputs of activation pair p and the 64 samples of half kh (4 K-steps): A = resident dz2^T, K-major along
+    // the samples; B = that half of the stashed pair in half `half` of the B region, MN-major, N = 128
+    const uint32_t idesc_g3 = tc::make_idesc_f16_b_mn(128, 128);
+    auto issue_g3 = [&](int half, int kh, uint32_t col, bool first) {
         const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
         const uint32_t bh = tc::smem_u32(bstage_buf((uint32_t)half, 0)), bl = tc::smem_u32(bstage_buf((uint32_t)half, 1));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t aoff = (uint32_t)(2 * j) * 128u, boff = (uint32_t)(2 * j) * 1024u;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t aoff = (uint32_t)(8 * kh + 2 * j) * 128u, boff = (uint32_t)(2 * j) * 2048u;
             const uint64_t dah = tc::make_smem_desc(ah + aoff, 128, 2048), dal = tc::make_smem_desc(al + aoff, 128, 2048);
-            const uint64_t dbh = tc::make_smem_desc(bh + boff, 1024, 128), dbl = tc::make_smem_desc(bl + boff, 1024, 128);
+            const uint64_t dbh = tc::make_smem_desc(bh + boff, 2048, 128), dbl = tc::make_smem_desc(bl + boff, 2048, 128);
             tc::mma_f16(tmem + col, dal, dbh, idesc_g3, (first && j == 0) ? 0u : 1u);
             tc::mma_f16(tmem + col, dah, dbl, idesc_g3, 1u);
             tc::mma_f16(tmem + col, dah, dbh, idesc_g3, 1u);
@@ -443,18 +459,63 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                                 (size_t)blockIdx.x * (size_t)kStashFloatsPerCta * 4;
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
                 const bool first_tile = (tile == (long long)blockIdx.x);
+                // ---- forward.  Layer 1 runs on the tensor cores too: z1c[s][i] = sum_k x_k w_ik + b_i (centred weights: the
+                // LayerNorm-1 mean is 0) as a K = 16 GEMM per chunk of 64 inputs, A = [x_hi | x_lo] (written by Ph0), B1 = [w_hi |
+                // w_hi], B2 = [w_lo | 0]: two MMAs give x_hi w_hi + x_lo w_hi + x_hi w_lo.  The result goes to one of two 64-column
+                // TMEM buffers in [128,256) (free until G2), from where the compute warps turn it into the chunk's G1 operand.
+                if (lt > 0) {                               // the previous tile's G3 and column-sum MMAs have read the ring / xh
+                    tc::mbar_wait(&g3done, (lt - 1u) & 1u);
+                    tc::mbar_wait(&pdone[0], 1u);
+                    tc::mbar_wait(&pdone[1], 1u);
+                }
+                // (the B operands go behind the first 20 KB of the region: the compute threads transpose the previous tile's
+                // per-sample scalars through its first 18 KB while this copy is in flight)
+                const uint32_t l1a = tc::smem_u32(sm + TcSmem::xh), l1b = l1a + 20480u;
+                tc::bulk_load(sm + TcSmem::xh + 5120, w2s + kWsL1Ops, (uint32_t)(kL1OpsFloats * 4), &l1full);
+                const char* const w2g1 = reinterpret_cast<const char*>(w2s + kW2SplitG1);
+                const uint32_t idesc_l1 = tc::make_idesc_f16(128, 64);
+                auto issue_l1 = [&](int c) {                // chunk c -> TMEM buffer c & 1
+                    const uint64_t da = tc::make_smem_desc(l1a, 128, 256);
+                    const uint64_t db1 = tc::make_smem_desc(l1b + (uint32_t)c * 4096u, 128, 256);
+                    const uint64_t db2 = tc::make_smem_desc(l1b + (uint32_t)c * 4096u + 2048u, 128, 256);
+                    tc::mma_f16(tmem + 128u + 64u * (uint32_t)(c & 1), da, db1, idesc_l1, 0u);
+                    tc::mma_f16(tmem + 128u + 64u * (uint32_t)(c & 1), da, db2, idesc_l1, 1u);
+                    tc::mma_commit(&zfull[c & 1]);
+                };
+                tc::bulk_load(b_stage(0u), w2g1, (uint32_t)kStashChunkBytes, &wfull[0]);
+                tc::bulk_load(b_stage(1u), w2g1 + kStashChunkBytes, (uint32_t)kStashChunkBytes, &wfull[1]);
+                while (!tc::mbar_try_wait(&x0full, lt & 1u)) __nanosleep(PLUME_TC_POLL_NS);
+                tc::mbar_wait(&l1full, lt & 1u);
+                tc::tc_fence_after();
+                issue_l1(0);
+                issue_l1(1);
                 for (int c = 0; c < 4; ++c, ++st) {                                                      // G1
                     while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(PLUME_TC_POLL_NS);
+                    tc::mbar_wait(&wfull[c & 1], (uint32_t)(c >> 1));
                     tc::tc_fence_after();
-                    // stash the activation chunk (A_hi, A_lo of the stage: 32 KB contiguous); the producers' fence.proxy.async
-                    // + the `full` barrier made their writes visible to the async proxy
-                    tc::bulk_store(stash + (size_t)c * kStashChunkBytes, stage_buf(st, 0), (uint32_t)kStashChunkBytes);
+                    if (c >= 1) {
+                        // Nothing in a turn waits for work issued in the same turn (issuing the 12 MMAs blocks this thread while
+                        // the tensor pipe's queue is full): the previous chunk's store has had a whole turn to read its source ...
+                        const uint32_t pst = st - 1u;
+                        tc::bulk_wait_group_read_all();
+                        mbar_arrive(&sdone[pst & 1u]);
+                        if (c + 1 < 4) {                    // ... and its MMAs to complete: W2 chunk c + 1 into their stage
+                            tc::mbar_wait(&bar[pst & 1u], (pst >> 1) & 1u);
+                            tc::bulk_load(b_stage(pst), w2g1 + (size_t)(c + 1) * kStashChunkBytes, (uint32_t)kStashChunkBytes,
+                                          &wfull[(c + 1) & 1]);
+                        }
+                    }
+                    if (c + 2 < 4) issue_l1(c + 2);         // every compute thread has read buffer c & 1 (it arrived on `full`)
+                    // stash the chunk (one tensor copy: the stage's 32 KB -> the chunk's interleaved half of pair c >> 1; the
+                    // producers' fence.proxy.async + the `full` barrier made their writes visible to the async proxy), then G1
+                    tc::tensor_store_5d(&stash_map, a_stage(st), 0, c & 1, 0, 0, (int)blockIdx.x * 2 + (c >> 1));
                     tc::bulk_commit_group();
-                    tc::mma_chunk_f16(tmem, stage_buf(st, 0), stage_buf(st, 1), stage_buf(st, 2), stage_buf(st, 3), idesc, c == 0);
+                    tc::mma_chunk_f16(tmem, a_stage(st), a_stage(st) + kChunkFloats, b_stage(st), b_stage(st) + kChunkFloats, idesc,
+                                      c == 0);
                     tc::mma_commit(&bar[st & 1u]);
-                    tc::bulk_wait_group_read_all();         // (this thread has nothing else to do until the next chunk is produced)
-                    mbar_arrive(&sdone[st & 1u]);
                 }
+                tc::bulk_wait_group_read_all();
+                mbar_arrive(&sdone[(st - 1u) & 1u]);
                 // ---- backward: eight 32 KB bulk copies per tile go through the two halves of stage 1, in this order per half h:
                 // W2^T chunk h (G2, inputs 0..127), W2^T chunk 2 + h (G2, inputs 128..255), stashed activation chunks h and
                 // 2 + h (G3).  bfull / bfree see four phases per tile and half: the parity of phase k is k & 1.
@@ -493,18 +554,19 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 }
                 // G3: the four stashed chunks; nothing for the compute warps to do
                 tc::bulk_wait_group_all();                  // the stash holds the tile's four chunks
-                for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < 2; ++r) {              // pair r = inputs [128 r, 128 r + 128); c = half of the samples
                     for (int c = 0; c < 2; ++c) {
                         tc::mbar_wait(&bfree[c], (uint32_t)((1 + r) & 1));
                         PLUME_IS(6 + 4 * r + c);
-                        tc::bulk_load(bstage_buf((uint32_t)c, 0), stash + (size_t)(2 * r + c) * kStashChunkBytes,
-                                      (uint32_t)kStashChunkBytes, &bfull[c]);
+                        const char* const src = stash + (size_t)r * (2 * kStashChunkBytes) + (size_t)c * 16384;
+                        tc::bulk_load2(bstage_buf((uint32_t)c, 0), src, bstage_buf((uint32_t)c, 1), src + kStashChunkBytes, 16384u,
+                                       &bfull[c]);
                     }
                     for (int c = 0; c < 2; ++c) {
                         tc::mbar_wait(&bfull[c], (uint32_t)((2 + r) & 1));
                         PLUME_IS(8 + 4 * r + c);
                         tc::tc_fence_after();
-                        issue_g3(c, (uint32_t)(256 + 64 * (2 * r + c)), first_tile);
+                        issue_g3(c, c, (uint32_t)(256 + 128 * r), first_tile && c == 0);
                         tc::mma_commit(&bfree[c]);
                     }
                 }
@@ -639,33 +701,45 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             const float rstd1_s = (float)(1.0 / sqrt(ssq * (1.0 / 256.0) + (double)kLnEps));
             *reinterpret_cast<float4*>(xt + tid * 8) = q0;
             *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(q1.x, q1.y, rstd1_s, 0.0f);
+            // A operand of the layer-1 GEMM (in the xhat2 / staging region, idle until Ph3): row = sample, K slot 0 = fp16 hi of
+            // (x_0..x_5, 1, 0), K slot 1 = the fp16 remainders; slot (s, k) at (s >> 3) * 256 + k * 128 + (s & 7) * 16 bytes
+            {
+                uint4 hi, lo;
+                tc::split_f16x8(q0, make_float4(q1.x, q1.y, 1.0f, 0.0f), 1.0f, hi, lo);
+                uint4* xa = reinterpret_cast<uint4*>(xh);
+                const int f = (tid >> 3) * 16 + (tid & 7);
+                xa[f] = hi;
+                xa[f + 8] = lo;
+            }
             // d loss / d (logits, value) of this tile: the two loss halves of Ph3 add into it
             *reinterpret_cast<float4*>(sm + TcSmem::dout + tid * 8) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             *reinterpret_cast<float4*>(sm + TcSmem::dout + tid * 8 + 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
+        tc::fence_proxy_async();
+        mbar_arrive(&x0full);     // the MMA thread starts the layer-1 GEMM of the first two chunks
         compute_sync();
 
         PLUME_TL(1);
-        // ---- Ph1: this thread's sample (r128) for the producer phases; rstd1 was computed in Ph0 ------------
-        float2 xr2[6];            // (x_k, x_k): the broadcast operand of the packed layer-1 FMAs
-        float2 rs2;
-        {
-            const float4 x0 = *reinterpret_cast<const float4*>(xt + r128 * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(xt + r128 * 8 + 4);
-            xr2[0] = splat2(x0.x); xr2[1] = splat2(x0.y); xr2[2] = splat2(x0.z); xr2[3] = splat2(x0.w);
-            xr2[4] = splat2(x1.x); xr2[5] = splat2(x1.y);
-            rs2 = splat2(x1.z);
-        }
+        // ---- Ph1: rstd1 of this thread's sample (r128), computed in Ph0 ------------------------------------
+        const float2 rs2 = splat2(xt[r128 * 8 + 6]);
 
         // ---- Ph2: G1 forward, K = 256 inputs in 4 chunks of 64; thread = (sample r128, 8/G of the 8 slots) ----
+        // (the previous tile's G3 reads dz2 in stage 0 and the stashed chunks in stage 1 until here: its tail overlaps that
+        // tile's scalar sums and this tile's Ph0)
+        if (lt > 0) tc::mbar_wait(&g3done, (lt - 1u) & 1u);
         for (int c = 0; c < 4; ++c) {
             const uint32_t st = step;
             acquire(st);
             if (c >= 2) tc::mbar_wait(&sdone[st & 1u], 0u);     // chunk c - 2 of this stage has been read by its bulk store
-            load_b_into(stage_buf(st, 2), stage_buf(st, 3), w2s + kW2SplitG1Hi + c * kChunkFloats,
-                        w2s + kW2SplitG1Lo + c * kChunkFloats);
-            uint4* ah = reinterpret_cast<uint4*>(stage_buf(st, 0));
-            uint4* al = reinterpret_cast<uint4*>(stage_buf(st, 1));
+            uint4* ah = reinterpret_cast<uint4*>(a_stage(st));
+            uint4* al = ah + 1024;
+            // the centred pre-activations of this thread's sample and 16 inputs (64 c + 16 ug ..) from the chunk's TMEM buffer
+            float z[16];
+            tc::mbar_wait(&zfull[c & 1], (uint32_t)(c >> 1));
+            tc::tc_fence_after();
+            tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + 64 * (c & 1) + 16 * ug), z);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
 #pragma unroll
             for (int uu = 0; uu < UPT; ++uu) {
                 const int u = UPT * ug + uu;
@@ -673,16 +747,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int in0 = 64 * c + 8 * u + 4 * q;
-                    const float4 b = *reinterpret_cast<const float4*>(P1 + in0);
-                    float2 z01 = f2(b.x, b.y), z23 = f2(b.z, b.w);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const float4 w = *reinterpret_cast<const float4*>(W1c + k * 256 + in0);
-                        z01 = __ffma2_rn(xr2[k], f2(w.x, w.y), z01);
-                        z23 = __ffma2_rn(xr2[k], f2(w.z, w.w), z23);
-                    }
                     const float4 g = *reinterpret_cast<const float4*>(P1 + 256 + in0);
                     const float4 be = *reinterpret_cast<const float4*>(P1 + 512 + in0);
+                    const float2 z01 = f2(z[8 * uu + 4 * q], z[8 * uu + 4 * q + 1]), z23 = f2(z[8 * uu + 4 * q + 2], z[8 * uu + 4 * q + 3]);
                     const float2 y01 = __ffma2_rn(__fmul2_rn(z01, rs2), f2(g.x, g.y), f2(be.x, be.y));
                     const float2 y23 = __ffma2_rn(__fmul2_rn(z23, rs2), f2(g.z, g.w), f2(be.z, be.w));
                     hq[q] = make_float4(fmaxf(y01.x, 0.0f), fmaxf(y01.y, 0.0f), fmaxf(y23.x, 0.0f), fmaxf(y23.y, 0.0f));
@@ -995,8 +1062,6 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 PLUME_TL(14 + c);
             }
         PLUME_TL(8);
-            tc::mbar_wait(&g3done, lt & 1u);   // the exchange area aliases stage 1 and the next tile rewrites the ring: every
-            tc::tc_fence_after();              // G3 MMA must have read its operands
             tc::mbar_wait(&pdone[0], 1u);      // the column-sum GEMMs of chunks 2 and 3 (and with them 0 and 1) are complete
             tc::mbar_wait(&pdone[1], 1u);
             tc::tc_fence_after();
@@ -1008,15 +1073,18 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
                 for (int k = 0; k < 8; ++k) Pacc[k] += pv[k];      // (lanes 16..31 accumulate columns nobody reads)
             }
-            EX(6, cg, srow) = m1p2.x + m1p2.y;
-            EX(7, cg, srow) = m2p2.x + m2p2.y;
+            // (G3 may still be running: this exchange has its own area behind the scalar transposition rows and the next
+            // tile's layer-1 operands, in what was the second dy1 buffer)
+            float* const ex6 = xh + 9216;
+            ex6[(0 * G + cg) * kTcTile + srow] = m1p2.x + m1p2.y;
+            ex6[(1 * G + cg) * kTcTile + srow] = m2p2.x + m2p2.y;
             quarter_sync(wq);
             if (cg == 0) {          // per-sample scalar sums of the layer-1 backward -> per-CTA accumulators
                 float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    t1 += EX(6, g, srow);
-                    t2 += EX(7, g, srow);
+                    t1 += ex6[(0 * G + g) * kTcTile + srow];
+                    t2 += ex6[(1 * G + g) * kTcTile + srow];
                 }
                 const float m1 = t1 * (1.0f / 256.0f), m2 = t2 * (1.0f / 256.0f);
                 const float rs = sx1.z;
@@ -1098,7 +1166,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #endif
     float* g = a.grads;
     if (step > 0) {
-        wait_all_mma();
+        tc::mbar_wait(&g3done, (lt - 1u) & 1u);        // the last tile's G3
+        tc::tc_fence_after();
         // dW2 accumulator: TMEM lane = output srow, this warp's column group = inputs [64 cg, 64 cg + 64)
 #pragma unroll 1
         for (int q = 0; q < 256 / G / 32; ++q) {
@@ -1222,6 +1291,32 @@ int launch_ppo_pack(const plume_ppo_batch& b, float* packed, cudaStream_t s) {
 // ---- launch ---------------------------------------------------------------------------------------------
 int64_t ppo_tc_workspace_bytes() { return (int64_t)kWsFloats * (int64_t)sizeof(float) + 256; }
 
+// The stash as a 5-D tensor of 32-bit words for the per-chunk tensor store: (256 words = one 1 KB piece: 8 samples x 64 inputs
+// of hi or lo) x (q: chunk of the pair, 1 KB on) x (16 groups of 8 samples, 2 KB on) x (hi / lo, 32 KB on) x (pair, 64 KB on).
+// The box {256, 1, 16, 2, 1} is the 32 KB of an A stage in shared-memory order.
+static int make_stash_map(CUtensorMap* map, void* stash, int pairs) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess)
+            return fail("ppo_tc: cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[5] = {256, 2, 16, 2, (cuuint64_t)pairs};
+    const cuuint64_t strides[4] = {1024, 2048, 32768, 65536};            // bytes, dimensions 1..4
+    const cuuint32_t box[5] = {256, 1, 16, 2, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, stash, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("ppo_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
 int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s) {
     static bool configured = false;
     const int smem = TcSmem::total * (int)sizeof(float);
@@ -1241,7 +1336,14 @@ int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaSt
     // dz2 ~ O(1..100) / global batch: a power of two 16x below the batch size brings it to O(0.1..10), four orders of
     // magnitude under fp16's largest value
     const float dz_scale = exp2f(floorf(log2f(1.0f / a.inv_global)) - 4.0f);
-    ppo_tc_kernel<<<grid, kTcLaunchThreads, smem, s>>>(params, a, w2s, dz_scale);
+    // (one map per workspace address; rebuilt when the caller comes with another buffer)
+    static CUtensorMap stash_map;
+    static void* mapped = nullptr;
+    if (mapped != (void*)(w2s + kWsStash)) {
+        if (make_stash_map(&stash_map, w2s + kWsStash, 2 * kTcMaxCtas)) return -1;
+        mapped = (void*)(w2s + kWsStash);
+    }
+    ppo_tc_kernel<<<grid, kTcLaunchThreads, smem, s>>>(params, a, w2s, dz_scale, stash_map);
     if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_kernel launch failed");
     return 0;
 }

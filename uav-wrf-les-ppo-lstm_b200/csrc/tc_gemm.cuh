@@ -151,6 +151,8 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uin
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the sources of all committed groups have been read (the shared-memory buffers may be overwritten)
 __device__ __forceinline__ void bulk_wait_group_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... of all committed groups but the most recent one
+__device__ __forceinline__ void bulk_wait_group_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // all committed groups are complete (their global-memory writes included)
 __device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // global -> shared, completion (byte count) signalled on an mbarrier of count 1
@@ -159,6 +161,24 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(mb) : "memory");
+}
+
+// shared -> global through a 5-D tensor map (box = the contiguous shared-memory source), tracked by the thread's bulk groups
+__device__ __forceinline__ void tensor_store_5d(const void* tensor_map, const void* smem_src, int c0, int c1, int c2, int c3,
+                                                int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                 ::"l"(reinterpret_cast<uint64_t>(tensor_map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+// two copies of `bytes` each on one phase of the mbarrier
+__device__ __forceinline__ void bulk_load2(void* dst0, const void* src0, void* dst1, const void* src1, uint32_t bytes,
+                                           uint64_t* bar) {
+    const uint32_t mb = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst0)), "l"(src0), "r"(bytes), "r"(mb) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst1)), "l"(src1), "r"(bytes), "r"(mb) : "memory");
 }
 
 // ---- operand staging -----------------------------------------------------------------------

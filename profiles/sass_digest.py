@@ -1,6 +1,6 @@
 """SASS digest of libplume_b200.so: per kernel, how many of the instructions that prove a Blackwell-native path
 (profiling guide, "What proves a Blackwell-native kernel"): UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st,
-UBLKCP / UTMALDG = TMA (cp.async.bulk / .tensor), HMMA = mma.sync, LDGSTS = cp.async, SYNCS = mbarrier,
+UBLKCP / UTMALDG / UTMASTG = TMA (cp.async.bulk / .tensor load / .tensor store), HMMA = mma.sync, LDGSTS = cp.async, SYNCS = mbarrier,
 FFMA2 / FMUL2 / FADD2 = packed fp32 pairs, MUFU.
     python profiles/sass_digest.py > profiles/r2_sass_digest.txt"""
 import collections
@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "uav-wrf-les-ppo-lstm_b200", "build")
-KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "HMMA", "LDSM", "LDGSTS", "SYNCS", "BAR",
+KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "HMMA", "LDSM", "LDGSTS", "SYNCS", "BAR",
         "FFMA2", "FMUL2", "FADD2", "FFMA", "DFMA", "MUFU", "IMAD", "LDG", "STG", "LDS", "STS", "ATOM", "RED"]
 
 

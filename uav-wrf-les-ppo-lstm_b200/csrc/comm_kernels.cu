@@ -149,12 +149,21 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_clip_adam_kernel(
     signal_and_wait(ptrs, world, rank, CommLayout::gflags, step + 1u, blockIdx.x == 0, err);
     __syncthreads();
     // 3. one-shot all-reduce of this thread's element, in rank order
+    // (all peer loads are issued before the first one is used: a load over NVLink takes ~1.5 us, and a loop over a run-time
+    // `world` would pay that once per rank)
     float gi = 0.0f;
     if (i < n) {
-        for (int r = 0; r < world; ++r) {
-            const float* src = reinterpret_cast<const float*>(ptrs.peer[r] + CommLayout::pub) + (size_t)buf * n_pad;
-            gi += __ldcv(src + i);
+        float part[kCommMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kCommMaxWorld; ++r) {
+            part[r] = 0.0f;
+            if (r < world) {
+                const float* src = reinterpret_cast<const float*>(ptrs.peer[r] + CommLayout::pub) + (size_t)buf * n_pad;
+                part[r] = __ldcv(src + i);
+            }
         }
+#pragma unroll
+        for (int r = 0; r < kCommMaxWorld; ++r) gi += part[r];          // rank order: every rank gets the bitwise identical sum
     }
     const double ss = comm_block_sum((double)gi * (double)gi, scratch);
     if (threadIdx.x == 0) partial[blockIdx.x] = ss;

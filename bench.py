@@ -39,7 +39,8 @@ WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture; counters are not
 # readable from inside an unprofiled run, so the line cites the committed capture it copies the number from)
-PPO_TC_TRAFFIC = {"bytes": 33.5e6, "source": "profiles/r1u_ncu_summary.txt (prof_r1u_ppo_tc: 33.46 MB read + 0.03 MB written)"}
+PPO_TC_TRAFFIC = {"bytes": 35.2e6,
+                  "source": "profiles/r2b_ppo_tc_ncu_summary.txt (prof_r2b_ppo_tc: 34.10 MB read + 1.13 MB written)"}
 K2_TRAFFIC = {"bytes": 316.7e6, "source": "profiles/r1h_k2_ncu_summary.txt (prof_r1h_k2, 2^20 envs)"}
 
 
@@ -523,9 +524,10 @@ def run_cuda_arm(args) -> None:
                 "note": "tcgen05.mma kind::f16 with the two-term fp16 split x = hi + lo/s (fp32 rel 1e-5 parity bar), "
                         "accumulators in TMEM; traffic = dram read+write per launch from the ncu --set full capture in "
                         "profiles/ (algorithmic gather: a 48-byte record + an 8-byte permutation index x 262144 samples "
-                        "= 14.7 MB; a record straddles two 32-byte sectors); the kernel is bound by instruction issue in the "
-                        "CUDA-core phases between the GEMMs (issue slots 48 % busy, tensor pipe 16 %: DESIGN.md section 5, "
-                        "phase timeline)"}
+                        "= 14.7 MB; a record straddles two 32-byte sectors; the operand chunks and the activation stash, 2 KB per "
+                        "sample, stay in L2); the kernel is bound by the dependencies between its CUDA-core phases and the "
+                        "tensor / copy work (issue slots 37 % busy, tensor pipe 20 %, 30 % of the samples waiting on MMAs or "
+                        "bulk copies: DESIGN.md section 5)"}
 
     # ---- end to end through the host-buffer API -------------------------------------------------------
     hb = trainer.make_host_buffers()

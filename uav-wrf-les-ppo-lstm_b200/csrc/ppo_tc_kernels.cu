@@ -55,6 +55,10 @@
 #ifndef PLUME_TC_PN
 #define PLUME_TC_PN 8
 #endif
+// back-off of the compute warps between polls of an mbarrier they wait on for long (measured: no effect between 20 and 200 ns)
+#ifndef PLUME_TC_WAIT_NS
+#define PLUME_TC_WAIT_NS 64
+#endif
 namespace plume {
 
 constexpr int kTcTile = 128;
@@ -290,7 +294,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     constexpr int SPT = 128 / G;          // samples per thread in the column-oriented phases (32)
     static_assert(CW == 32 && UPT >= 1, "the epilogues read one 32-column TMEM slab per thread");
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a value the compiler knows to be warp-uniform)
 #ifdef PLUME_TC_TIMELINE
     long long kt_[4] = {0, 0, 0, 0};
     const bool kt_on = (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tid == 0;
@@ -395,7 +400,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     // wait until the MMAs that last read this step's stage have completed
     auto acquire = [&](uint32_t st) {
         const uint32_t use = st >> 1;
-        if (use >= 1) tc::mbar_wait(&bar[st & 1u], (use - 1) & 1u);
+        if (use >= 1) tc::mbar_wait_sleep(&bar[st & 1u], (use - 1) & 1u, PLUME_TC_WAIT_NS);
     };
     // producers: the operands of step st are complete in shared memory -> visible to the async proxy, arrive
     auto publish = [&](uint32_t st) {
@@ -407,42 +412,26 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #ifndef PLUME_TC_POLL_NS
 #define PLUME_TC_POLL_NS 40
 #endif
-    // G2 ring step: A = resident dz2, MN-major, K = outputs [64 c, 64 c + 64); B = the step's W2^T chunk
+
+    // G2 step: A = resident dz2, MN-major, K = outputs [64 c, 64 c + 64); B = the W2^T chunk in half `half` of the B region
     const uint32_t idesc_amn = tc::make_idesc_f16_a_mn(128, 128);
-    auto issue_g2 = [&](uint32_t half, uint32_t col, int c, bool first) {
-        const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
-        const uint32_t bh = tc::smem_u32(bstage_buf(half, 0)), bl = tc::smem_u32(bstage_buf(half, 1));
-#pragma unroll
-        for (int j = 0; j < tc::kChunkKH / 16; ++j) {
-            const uint32_t aoff = (uint32_t)(8 * c + 2 * j) * 2048u, boff = j * 2 * tc::kLBO;
-            const uint64_t dah = tc::make_smem_desc(ah + aoff, 2048, 128), dal = tc::make_smem_desc(al + aoff, 2048, 128);
-            const uint64_t dbh = tc::make_smem_desc(bh + boff, tc::kLBO, tc::kSBO);
-            const uint64_t dbl = tc::make_smem_desc(bl + boff, tc::kLBO, tc::kSBO);
-            tc::mma_f16(tmem + col, dal, dbh, idesc_amn, (first && j == 0) ? 0u : 1u);
-            tc::mma_f16(tmem + col, dah, dbl, idesc_amn, 1u);
-            tc::mma_f16(tmem + col, dah, dbh, idesc_amn, 1u);
-        }
+    auto step_g2 = [&](uint32_t half, int c) {
+        const uint32_t ah = tc::smem_u32(dz_hi) + (uint32_t)(8 * c) * 2048u, al = tc::smem_u32(dz_lo) + (uint32_t)(8 * c) * 2048u;
+        const uint32_t bh = tc::smem_u32(bstage_buf(half, 0));
+        return tc::make_operands(ah, al, 2 * 2048u, 2048, 128, bh, bh + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO);
     };
-    // G3 for the 128 inputs of activation pair p and the 64 samples of half kh (4 K-steps): A = resident dz2^T, K-major along
-    // the samples; B = that half of the stashed pair in half `half` of the B region, MN-major, N = 128
+    // G3 step for the 128 inputs of an activation pair and the 64 samples of half kh (4 K-steps): A = resident dz2^T, K-major
+    // along the samples; B = that half of the stashed pair in half `half` of the B region, MN-major, N = 128
     const uint32_t idesc_g3 = tc::make_idesc_f16_b_mn(128, 128);
-    auto issue_g3 = [&](int half, int kh, uint32_t col, bool first) {
-        const uint32_t ah = tc::smem_u32(dz_hi), al = tc::smem_u32(dz_lo);
-        const uint32_t bh = tc::smem_u32(bstage_buf((uint32_t)half, 0)), bl = tc::smem_u32(bstage_buf((uint32_t)half, 1));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t aoff = (uint32_t)(8 * kh + 2 * j) * 128u, boff = (uint32_t)(2 * j) * 2048u;
-            const uint64_t dah = tc::make_smem_desc(ah + aoff, 128, 2048), dal = tc::make_smem_desc(al + aoff, 128, 2048);
-            const uint64_t dbh = tc::make_smem_desc(bh + boff, 2048, 128), dbl = tc::make_smem_desc(bl + boff, 2048, 128);
-            tc::mma_f16(tmem + col, dal, dbh, idesc_g3, (first && j == 0) ? 0u : 1u);
-            tc::mma_f16(tmem + col, dah, dbl, idesc_g3, 1u);
-            tc::mma_f16(tmem + col, dah, dbh, idesc_g3, 1u);
-        }
+    auto step_g3 = [&](uint32_t half, int kh) {
+        const uint32_t ah = tc::smem_u32(dz_hi) + (uint32_t)(8 * kh) * 128u, al = tc::smem_u32(dz_lo) + (uint32_t)(8 * kh) * 128u;
+        const uint32_t bh = tc::smem_u32(bstage_buf(half, 0));
+        return tc::make_operands(ah, al, 2 * 128u, 128, 2048, bh, bh + 16384u, 2 * 2048u, 2048, 128);
     };
     // every MMA of the steps counted so far has completed
     auto wait_all_mma = [&]() {
         const uint32_t last = step - 1;
-        tc::mbar_wait(&bar[last & 1u], (last >> 1) & 1u);
+        tc::mbar_wait_sleep(&bar[last & 1u], (last >> 1) & 1u, PLUME_TC_WAIT_NS);
         tc::tc_fence_after();
     };
 
@@ -451,8 +440,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     // ---- the MMA issuer: lane 0 of the last warp replays the step sequence of every tile -----------------
     // (a dedicated warp keeps the blocking tcgen05.mma issue out of the producers' instruction streams and
     // lets the ring run on mbarriers only: producers never meet at a CTA barrier inside a GEMM)
+    const bool ld = lane == 0;        // the lane of an MMA warp that issues MMAs, copies and commits
     if (warp == kTcThreads / 32) {
-        if (lane == 0) {
+        {   // all 32 lanes run the control flow (descriptors stay in uniform registers); `ld` issues
             uint32_t st = 0;                   // producer steps so far: 4 per tile (G1), so (st & 1) == (c & 1)
             uint32_t lt = 0;                   // tiles of this CTA so far
             char* const stash = reinterpret_cast<char*>(const_cast<float*>(w2s) + kWsStash) +
@@ -464,58 +454,65 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 // w_hi], B2 = [w_lo | 0]: two MMAs give x_hi w_hi + x_lo w_hi + x_hi w_lo.  The result goes to one of two 64-column
                 // TMEM buffers in [128,256) (free until G2), from where the compute warps turn it into the chunk's G1 operand.
                 if (lt > 0) {                               // the previous tile's G3 and column-sum MMAs have read the ring / xh
-                    tc::mbar_wait(&g3done, (lt - 1u) & 1u);
-                    tc::mbar_wait(&pdone[0], 1u);
-                    tc::mbar_wait(&pdone[1], 1u);
+                    tc::mbar_wait_warp(&g3done, (lt - 1u) & 1u, PLUME_TC_POLL_NS);
+                    tc::mbar_wait_warp(&pdone[0], 1u, PLUME_TC_POLL_NS);
+                    tc::mbar_wait_warp(&pdone[1], 1u, PLUME_TC_POLL_NS);
                 }
                 // (the B operands go behind the first 20 KB of the region: the compute threads transpose the previous tile's
                 // per-sample scalars through its first 18 KB while this copy is in flight)
                 const uint32_t l1a = tc::smem_u32(sm + TcSmem::xh), l1b = l1a + 20480u;
-                tc::bulk_load(sm + TcSmem::xh + 5120, w2s + kWsL1Ops, (uint32_t)(kL1OpsFloats * 4), &l1full);
+                if (ld) tc::bulk_load(sm + TcSmem::xh + 5120, w2s + kWsL1Ops, (uint32_t)(kL1OpsFloats * 4), &l1full);
                 const char* const w2g1 = reinterpret_cast<const char*>(w2s + kW2SplitG1);
                 const uint32_t idesc_l1 = tc::make_idesc_f16(128, 64);
+                const uint64_t l1_da = tc::make_smem_desc(l1a, 128, 256);
+                uint64_t l1_db[4][2];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    l1_db[c][0] = tc::make_smem_desc(l1b + (uint32_t)c * 4096u, 128, 256);
+                    l1_db[c][1] = tc::make_smem_desc(l1b + (uint32_t)c * 4096u + 2048u, 128, 256);
+                }
                 auto issue_l1 = [&](int c) {                // chunk c -> TMEM buffer c & 1
-                    const uint64_t da = tc::make_smem_desc(l1a, 128, 256);
-                    const uint64_t db1 = tc::make_smem_desc(l1b + (uint32_t)c * 4096u, 128, 256);
-                    const uint64_t db2 = tc::make_smem_desc(l1b + (uint32_t)c * 4096u + 2048u, 128, 256);
-                    tc::mma_f16(tmem + 128u + 64u * (uint32_t)(c & 1), da, db1, idesc_l1, 0u);
-                    tc::mma_f16(tmem + 128u + 64u * (uint32_t)(c & 1), da, db2, idesc_l1, 1u);
-                    tc::mma_commit(&zfull[c & 1]);
+                    if (ld) tc::mma_f16(tmem + 128u + 64u * (uint32_t)(c & 1), l1_da, l1_db[c][0], idesc_l1, 0u);
+                    if (ld) tc::mma_f16(tmem + 128u + 64u * (uint32_t)(c & 1), l1_da, l1_db[c][1], idesc_l1, 1u);
+                    if (ld) tc::mma_commit(&zfull[c & 1]);
                 };
-                tc::bulk_load(b_stage(0u), w2g1, (uint32_t)kStashChunkBytes, &wfull[0]);
-                tc::bulk_load(b_stage(1u), w2g1 + kStashChunkBytes, (uint32_t)kStashChunkBytes, &wfull[1]);
-                while (!tc::mbar_try_wait(&x0full, lt & 1u)) __nanosleep(PLUME_TC_POLL_NS);
-                tc::mbar_wait(&l1full, lt & 1u);
+                if (ld) tc::bulk_load(b_stage(0u), w2g1, (uint32_t)kStashChunkBytes, &wfull[0]);
+                if (ld) tc::bulk_load(b_stage(1u), w2g1 + kStashChunkBytes, (uint32_t)kStashChunkBytes, &wfull[1]);
+                tc::mbar_wait_warp(&x0full, lt & 1u, PLUME_TC_POLL_NS);
+                tc::mbar_wait_warp(&l1full, lt & 1u, PLUME_TC_POLL_NS);
                 tc::tc_fence_after();
                 issue_l1(0);
                 issue_l1(1);
+#pragma unroll 1
                 for (int c = 0; c < 4; ++c, ++st) {                                                      // G1
-                    while (!tc::mbar_try_wait(&full[st & 1u], (st >> 1) & 1u)) __nanosleep(PLUME_TC_POLL_NS);
-                    tc::mbar_wait(&wfull[c & 1], (uint32_t)(c >> 1));
+                    const uint32_t g1a = tc::smem_u32(a_stage(st)), g1b = tc::smem_u32(b_stage(st));
+                    const tc::MmaOperands g1 = tc::make_operands(g1a, g1a + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO, g1b,
+                                                                 g1b + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO);
+                    tc::mbar_wait_warp(&full[st & 1u], (st >> 1) & 1u, PLUME_TC_POLL_NS);
+                    tc::mbar_wait_warp(&wfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_POLL_NS);
                     tc::tc_fence_after();
                     if (c >= 1) {
                         // Nothing in a turn waits for work issued in the same turn (issuing the 12 MMAs blocks this thread while
                         // the tensor pipe's queue is full): the previous chunk's store has had a whole turn to read its source ...
                         const uint32_t pst = st - 1u;
-                        tc::bulk_wait_group_read_all();
-                        mbar_arrive(&sdone[pst & 1u]);
+                        if (ld) tc::bulk_wait_group_read_all();
+                        if (ld) mbar_arrive(&sdone[pst & 1u]);
                         if (c + 1 < 4) {                    // ... and its MMAs to complete: W2 chunk c + 1 into their stage
-                            tc::mbar_wait(&bar[pst & 1u], (pst >> 1) & 1u);
-                            tc::bulk_load(b_stage(pst), w2g1 + (size_t)(c + 1) * kStashChunkBytes, (uint32_t)kStashChunkBytes,
+                            tc::mbar_wait_warp(&bar[pst & 1u], (pst >> 1) & 1u, PLUME_TC_POLL_NS);
+                            if (ld) tc::bulk_load(b_stage(pst), w2g1 + (size_t)(c + 1) * kStashChunkBytes, (uint32_t)kStashChunkBytes,
                                           &wfull[(c + 1) & 1]);
                         }
                     }
                     if (c + 2 < 4) issue_l1(c + 2);         // every compute thread has read buffer c & 1 (it arrived on `full`)
                     // stash the chunk (one tensor copy: the stage's 32 KB -> the chunk's interleaved half of pair c >> 1; the
                     // producers' fence.proxy.async + the `full` barrier made their writes visible to the async proxy), then G1
-                    tc::tensor_store_5d(&stash_map, a_stage(st), 0, c & 1, 0, 0, (int)blockIdx.x * 2 + (c >> 1));
-                    tc::bulk_commit_group();
-                    tc::mma_chunk_f16(tmem, a_stage(st), a_stage(st) + kChunkFloats, b_stage(st), b_stage(st) + kChunkFloats, idesc,
-                                      c == 0);
-                    tc::mma_commit(&bar[st & 1u]);
+                    if (ld) tc::tensor_store_5d(&stash_map, a_stage(st), 0, c & 1, 0, 0, (int)blockIdx.x * 2 + (c >> 1));
+                    if (ld) tc::bulk_commit_group();
+                    tc::issue_split_steps(ld, tmem, g1, 4, idesc, c == 0 ? 0u : 1u);
+                    if (ld) tc::mma_commit(&bar[st & 1u]);
                 }
-                tc::bulk_wait_group_read_all();
-                mbar_arrive(&sdone[(st - 1u) & 1u]);
+                if (ld) tc::bulk_wait_group_read_all();
+                if (ld) mbar_arrive(&sdone[(st - 1u) & 1u]);
                 // ---- backward: eight 32 KB bulk copies per tile go through the two halves of stage 1, in this order per half h:
                 // W2^T chunk h (G2, inputs 0..127), W2^T chunk 2 + h (G2, inputs 128..255), stashed activation chunks h and
                 // 2 + h (G3).  bfull / bfree see four phases per tile and half: the parity of phase k is k & 1.
@@ -526,60 +523,65 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #else
 #define PLUME_IS(n)
 #endif
-                tc::mbar_wait(&bar[1], 1u);                 // G1's last step (st - 1 = 4 lt + 3) has completed: stage 1 is free
+                tc::mbar_wait_warp(&bar[1], 1u, PLUME_TC_POLL_NS);                 // G1's last step (st - 1 = 4 lt + 3) has completed: stage 1 is free
                 PLUME_IS(0);
                 const char* const w2t = reinterpret_cast<const char*>(w2s + kW2SplitG2);
-                tc::bulk_load(bstage_buf(0u, 0), w2t, (uint32_t)kStashChunkBytes, &bfull[0]);
-                tc::bulk_load(bstage_buf(1u, 0), w2t + kStashChunkBytes, (uint32_t)kStashChunkBytes, &bfull[1]);
-                while (!tc::mbar_try_wait(&dzfull, lt & 1u)) __nanosleep(PLUME_TC_POLL_NS);     // Ph4 has written dz2
+                if (ld) tc::bulk_load(bstage_buf(0u, 0), w2t, (uint32_t)kStashChunkBytes, &bfull[0]);
+                if (ld) tc::bulk_load(bstage_buf(1u, 0), w2t + kStashChunkBytes, (uint32_t)kStashChunkBytes, &bfull[1]);
+                tc::mbar_wait_warp(&dzfull, lt & 1u, PLUME_TC_POLL_NS);     // Ph4 has written dz2
                 tc::tc_fence_after();
                 PLUME_IS(1);
                 for (int hN = 0; hN < 2; ++hN) {                                                         // G2
                     for (int c = 0; c < 2; ++c) {
-                        tc::mbar_wait(&bfull[c], (uint32_t)hN);
+                        const tc::MmaOperands g2 = step_g2((uint32_t)c, c);
+                        tc::mbar_wait_warp(&bfull[c], (uint32_t)hN, PLUME_TC_POLL_NS);
+                        if (hN == 0) { PLUME_IS(14 + 2 * c); }
                         tc::tc_fence_after();
-                        issue_g2((uint32_t)c, (uint32_t)(128 * hN), c, c == 0);
-                        tc::mma_commit(&bfree[c]);
+                        tc::issue_split_steps(ld, tmem + (uint32_t)(128 * hN), g2, 4, idesc_amn, c == 0 ? 0u : 1u);
+                        if (ld) tc::mma_commit(&bfree[c]);
+                        if (hN == 0) { PLUME_IS(15 + 2 * c); }
                     }
-                    tc::mma_commit(&g2half[hN]);
+                    if (ld) tc::mma_commit(&g2half[hN]);
                     PLUME_IS(2 + 3 * hN);
                     if (hN == 0) {
                         for (int c = 0; c < 2; ++c) {
-                            tc::mbar_wait(&bfree[c], 0u);
+                            tc::mbar_wait_warp(&bfree[c], 0u, PLUME_TC_POLL_NS);
                             PLUME_IS(3 + c);
-                            tc::bulk_load(bstage_buf((uint32_t)c, 0), w2t + (size_t)(2 + c) * kStashChunkBytes,
+                            if (ld) tc::bulk_load(bstage_buf((uint32_t)c, 0), w2t + (size_t)(2 + c) * kStashChunkBytes,
                                           (uint32_t)kStashChunkBytes, &bfull[c]);
                         }
                     }
                 }
                 // G3: the four stashed chunks; nothing for the compute warps to do
-                tc::bulk_wait_group_all();                  // the stash holds the tile's four chunks
+                if (ld) tc::bulk_wait_group_all();                  // the stash holds the tile's four chunks
                 for (int r = 0; r < 2; ++r) {              // pair r = inputs [128 r, 128 r + 128); c = half of the samples
                     for (int c = 0; c < 2; ++c) {
-                        tc::mbar_wait(&bfree[c], (uint32_t)((1 + r) & 1));
+                        tc::mbar_wait_warp(&bfree[c], (uint32_t)((1 + r) & 1), PLUME_TC_POLL_NS);
                         PLUME_IS(6 + 4 * r + c);
                         const char* const src = stash + (size_t)r * (2 * kStashChunkBytes) + (size_t)c * 16384;
-                        tc::bulk_load2(bstage_buf((uint32_t)c, 0), src, bstage_buf((uint32_t)c, 1), src + kStashChunkBytes, 16384u,
+                        if (ld) tc::bulk_load2(bstage_buf((uint32_t)c, 0), src, bstage_buf((uint32_t)c, 1), src + kStashChunkBytes, 16384u,
                                        &bfull[c]);
                     }
                     for (int c = 0; c < 2; ++c) {
-                        tc::mbar_wait(&bfull[c], (uint32_t)((2 + r) & 1));
+                        const tc::MmaOperands g3 = step_g3((uint32_t)c, c);
+                        tc::mbar_wait_warp(&bfull[c], (uint32_t)((2 + r) & 1), PLUME_TC_POLL_NS);
                         PLUME_IS(8 + 4 * r + c);
                         tc::tc_fence_after();
-                        issue_g3(c, c, (uint32_t)(256 + 128 * r), first_tile && c == 0);
-                        tc::mma_commit(&bfree[c]);
+                        tc::issue_split_steps(ld, tmem + (uint32_t)(256 + 128 * r), g3, 4, idesc_g3, (first_tile && c == 0) ? 0u : 1u);
+                        if (ld) tc::mma_commit(&bfree[c]);
                     }
                 }
-                tc::mma_commit(&g3done);
+                if (ld) tc::mma_commit(&g3done);
 #ifdef PLUME_TC_TIMELINE
                 if (is_on) {
-                    tc::mbar_wait(&g3done, lt & 1u);
+                    tc::mbar_wait_warp(&g3done, lt & 1u, PLUME_TC_POLL_NS);
                     const long long e = clock64();
-                    printf("issuer (cycles after G1 done): dz ready %lld | G2h0 issued %lld | bfree0 %lld | bfree1 %lld | G2h1 issued %lld | "
+                    if (ld) printf("issuer (cycles after G1 done): dz ready %lld | G2h0 issued %lld | bfree0 %lld | bfree1 %lld | G2h1 issued %lld | "
                            "G3: bfree0 %lld bfree1 %lld | H0 landed %lld H1 landed %lld | bfree0 %lld bfree1 %lld | H2 landed %lld H3 landed "
-                           "%lld | all done %lld\n", is_[1] - is_[0], is_[2] - is_[0], is_[3] - is_[0], is_[4] - is_[0], is_[5] - is_[0],
+                           "%lld | all done %lld || G2h0: chunk 0 landed %lld, issued %lld, chunk 1 landed %lld, issued %lld\n", is_[1] - is_[0], is_[2] - is_[0], is_[3] - is_[0], is_[4] - is_[0], is_[5] - is_[0],
                            is_[6] - is_[0], is_[7] - is_[0], is_[8] - is_[0], is_[9] - is_[0], is_[10] - is_[0], is_[11] - is_[0],
-                           is_[12] - is_[0], is_[13] - is_[0], e - is_[0]);
+                           is_[12] - is_[0], is_[13] - is_[0], e - is_[0], is_[14] - is_[0], is_[15] - is_[0], is_[16] - is_[0],
+                           is_[17] - is_[0]);
                 }
 #endif
             }
@@ -593,24 +595,18 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         // 64..127 read whatever follows and land in TMEM lanes that nobody reads), B = X (one 16-byte slot per sample, read
         // MN-major with N = 16: columns 8..15 are the next sample's slot, ignored), K = the tile's 128 samples; the result
         // overwrites the first 16 of the chunk's own dh1 columns, which every thread has consumed by then.
-        if (lane == 0) {
+        {   // all 32 lanes run the control flow (descriptors stay in uniform registers); `ld` issues
             const uint32_t idesc_p = tc::make_idesc_f16(PLUME_TC_PM, PLUME_TC_PN) | (1u << 15) | (1u << 16);
             const uint32_t xph = tc::smem_u32(sm + TcSmem::x), xpl = xph + 2048u;
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+#pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    while (!tc::mbar_try_wait(&dyfull[c & 1], (uint32_t)(c >> 1))) __nanosleep(PLUME_TC_POLL_NS);
-                    tc::tc_fence_after();
                     const uint32_t ah = tc::smem_u32(sm + TcSmem::xh) + (uint32_t)(c & 1) * 32768u, al = ah + 16384u;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t aoff = (uint32_t)(2 * j) * 1024u, boff = (uint32_t)(2 * j) * 128u;
-                        const uint64_t dah = tc::make_smem_desc(ah + aoff, 1024, 128), dal = tc::make_smem_desc(al + aoff, 1024, 128);
-                        const uint64_t dbh = tc::make_smem_desc(xph + boff, 128, 16), dbl = tc::make_smem_desc(xpl + boff, 128, 16);
-                        tc::mma_f16(tmem + (uint32_t)(64 * c), dal, dbh, idesc_p, j == 0 ? 0u : 1u);
-                        tc::mma_f16(tmem + (uint32_t)(64 * c), dah, dbl, idesc_p, 1u);
-                        tc::mma_f16(tmem + (uint32_t)(64 * c), dah, dbh, idesc_p, 1u);
-                    }
-                    tc::mma_commit(&pdone[c & 1]);
+                    const tc::MmaOperands po = tc::make_operands(ah, al, 2 * 1024u, 1024, 128, xph, xpl, 2 * 128u, 128, 16);
+                    tc::mbar_wait_warp(&dyfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_POLL_NS);
+                    tc::tc_fence_after();
+                    tc::issue_split_steps(ld, tmem + (uint32_t)(64 * c), po, 8, idesc_p, 0u);
+                    if (ld) tc::mma_commit(&pdone[c & 1]);
                 }
             }
         }
@@ -726,7 +722,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         // ---- Ph2: G1 forward, K = 256 inputs in 4 chunks of 64; thread = (sample r128, 8/G of the 8 slots) ----
         // (the previous tile's G3 reads dz2 in stage 0 and the stashed chunks in stage 1 until here: its tail overlaps that
         // tile's scalar sums and this tile's Ph0)
-        if (lt > 0) tc::mbar_wait(&g3done, (lt - 1u) & 1u);
+        if (lt > 0) tc::mbar_wait_sleep(&g3done, (lt - 1u) & 1u, PLUME_TC_WAIT_NS);
         for (int c = 0; c < 4; ++c) {
             const uint32_t st = step;
             acquire(st);
@@ -735,7 +731,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             uint4* al = ah + 1024;
             // the centred pre-activations of this thread's sample and 16 inputs (64 c + 16 ug ..) from the chunk's TMEM buffer
             float z[16];
-            tc::mbar_wait(&zfull[c & 1], (uint32_t)(c >> 1));
+            tc::mbar_wait_sleep(&zfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_WAIT_NS);
             tc::tc_fence_after();
             tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + 64 * (c & 1) + 16 * ug), z);
             tc::tmem_ld_wait();
@@ -1010,7 +1006,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if ((c & 1) == 0) {
-                    tc::mbar_wait(&g2half[c >> 1], lt & 1u);   // dh1 of this half is complete (the other half's MMAs may still run)
+                    tc::mbar_wait_sleep(&g2half[c >> 1], lt & 1u, PLUME_TC_WAIT_NS);   // dh1 of this half is complete (the other half's MMAs may still run)
                     tc::tc_fence_after();
                 }
                 float dv[16];

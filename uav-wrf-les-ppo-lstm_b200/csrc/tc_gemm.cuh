@@ -58,6 +58,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// the same with a back-off between polls: sixteen warps spinning on try_wait take the issue slots of the one thread that
+// issues the MMAs they are waiting for
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
+// Wait of a WHOLE warp whose control flow has to stay warp-uniform (the MMA-issuing warps: only then does the compiler keep
+// descriptors and addresses in uniform registers): every lane polls, the vote makes the loop condition uniform.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) __nanosleep(ns);
+}
+
 // ---- proxy / tcgen05 fences -----------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -287,6 +299,46 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// ONE rolled issue loop for every hi/lo GEMM step of the update kernel: n K-steps of (lo.hi, hi.lo, hi.hi) into one
+// accumulator, the four descriptors advancing by a fixed number of bytes per K-step (profiles/debug/mma/umma_rate.cu measures
+// what an instruction costs back to back: 64 cycles for M128 x N128 x K16 with this hi / lo pattern).
+struct MmaOperands {
+    uint64_t ah, al, bh, bl;          // descriptors of the first K-step
+    uint32_t a_adv, b_adv;            // advance per K-step in 16-byte units (added to the descriptors' start-address field)
+};
+__device__ __forceinline__ MmaOperands make_operands(uint32_t a_hi, uint32_t a_lo, uint32_t a_adv_bytes, uint32_t a_lbo,
+                                                     uint32_t a_sbo, uint32_t b_hi, uint32_t b_lo, uint32_t b_adv_bytes,
+                                                     uint32_t b_lbo, uint32_t b_sbo) {
+    MmaOperands o;
+    o.ah = make_smem_desc(a_hi, a_lbo, a_sbo);
+    o.al = make_smem_desc(a_lo, a_lbo, a_sbo);
+    o.bh = make_smem_desc(b_hi, b_lbo, b_sbo);
+    o.bl = make_smem_desc(b_lo, b_lbo, b_sbo);
+    o.a_adv = a_adv_bytes >> 4;
+    o.b_adv = b_adv_bytes >> 4;
+    return o;
+}
+// Called by ALL lanes of the issuing warp with warp-uniform arguments; lane `leader` issues.  (Inside a one-lane branch the
+// compiler keeps the descriptors in vector registers and wraps every tcgen05.mma in an ELECT + 7 x R2UR + BRA.U.ANY loop:
+// ~100 cycles of issue latency per instruction -- measured 105-140 cycles per MMA in the kernel against 64 back to back.)
+__device__ __forceinline__ void issue_split_steps(bool leader, uint32_t tmem_d, MmaOperands o, int n, uint32_t idesc,
+                                                      uint32_t first_acc) {
+    uint32_t acc = first_acc;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        if (leader) {
+            mma_f16(tmem_d, o.al, o.bh, idesc, acc);
+            mma_f16(tmem_d, o.ah, o.bl, idesc, 1u);
+            mma_f16(tmem_d, o.ah, o.bh, idesc, 1u);
+        }
+        acc = 1u;
+        o.ah += o.a_adv;              // (shared-memory addresses >> 4 stay inside the 14-bit field: no carry into the LBO bits)
+        o.al += o.a_adv;
+        o.bh += o.b_adv;
+        o.bl += o.b_adv;
+    }
 }
 
 // two values -> packed fp16 hi and fp16 lo (scaled by s)

@@ -384,7 +384,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     // s & 7) at sg * 2048 + q * 1024 + u * 128 + (s & 7) * 16 bytes, hi in the pair's first 32 KB, lo in the second -- so that
     // a pair comes back as ONE MN-major B operand with N = 128 for G3 (next 8 inputs 128 bytes on, next 8 samples 2048 bytes
     // on).  Second 64 KB = the B stages: stage q holds a W2 chunk as [B_hi 16 KB][B_lo 16 KB].
-    auto a_stage = [&](uint32_t st) -> float* { return sm + TcSmem::ring + (st & 1u) * 2 * kChunkFloats; };
+    // THREE A stages: chunks 0, 1, 3 use the ring's two, chunk 2 a third one in the staging region (idle during the G1 pass;
+    // bytes [18 KB, 50 KB): behind the scalar transposition rows of the previous tile, in front of the layer-1 B operands) --
+    // a stage is only reused (chunk 3 after chunk 0) long after its tensor store has read it.  With two stages chunks 2 and 3
+    // each started 1.7-2 k cycles late, waiting for the store of their stage's previous chunk.
+    auto a_stage = [&](int c) -> float* {
+        return c == 2 ? sm + TcSmem::xh + 4608 : sm + TcSmem::ring + (c == 1 ? 2 * kChunkFloats : 0);   // chunk 3 -> chunk 0's
+    };
     auto b_stage = [&](uint32_t st) -> float* { return sm + TcSmem::ring + (4 + (st & 1u) * 2) * kChunkFloats; };
     // Backward GEMMs (G2, G3): stage 0 of the ring (64 KB) holds the RESIDENT dz2 operand of the tile -- 16-byte slot
     // (og, sg, o & 7) at og * 2048 + sg * 128 + (o & 7) * 16 bytes = dz_scale dz2[8 sg .. 8 sg + 7][o], og = o >> 3,
@@ -396,11 +402,6 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     float* const dz_lo = dz_hi + 2 * kChunkFloats;
     auto bstage_buf = [&](uint32_t st, int which) -> float* {     // which = 0 B_hi, 1 B_lo
         return sm + TcSmem::ring + (4 + (st & 1u) * 2 + which) * kChunkFloats;
-    };
-    // wait until the MMAs that last read this step's stage have completed
-    auto acquire = [&](uint32_t st) {
-        const uint32_t use = st >> 1;
-        if (use >= 1) tc::mbar_wait_sleep(&bar[st & 1u], (use - 1) & 1u, PLUME_TC_WAIT_NS);
     };
     // producers: the operands of step st are complete in shared memory -> visible to the async proxy, arrive
     auto publish = [&](uint32_t st) {
@@ -458,10 +459,10 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     tc::mbar_wait_warp(&pdone[0], 1u, PLUME_TC_POLL_NS);
                     tc::mbar_wait_warp(&pdone[1], 1u, PLUME_TC_POLL_NS);
                 }
-                // (the B operands go behind the first 20 KB of the region: the compute threads transpose the previous tile's
+                // (the B operands go to the last 16 KB of the region: the compute threads transpose the previous tile's
                 // per-sample scalars through its first 18 KB while this copy is in flight)
-                const uint32_t l1a = tc::smem_u32(sm + TcSmem::xh), l1b = l1a + 20480u;
-                if (ld) tc::bulk_load(sm + TcSmem::xh + 5120, w2s + kWsL1Ops, (uint32_t)(kL1OpsFloats * 4), &l1full);
+                const uint32_t l1a = tc::smem_u32(sm + TcSmem::xh), l1b = l1a + 51200u;
+                if (ld) tc::bulk_load(sm + TcSmem::xh + 12800, w2s + kWsL1Ops, (uint32_t)(kL1OpsFloats * 4), &l1full);
                 const char* const w2g1 = reinterpret_cast<const char*>(w2s + kW2SplitG1);
                 const uint32_t idesc_l1 = tc::make_idesc_f16(128, 64);
                 const uint64_t l1_da = tc::make_smem_desc(l1a, 128, 256);
@@ -485,34 +486,47 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 issue_l1(1);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c, ++st) {                                                      // G1
-                    const uint32_t g1a = tc::smem_u32(a_stage(st)), g1b = tc::smem_u32(b_stage(st));
+                    const uint32_t g1a = tc::smem_u32(a_stage(c)), g1b = tc::smem_u32(b_stage(st));
                     const tc::MmaOperands g1 = tc::make_operands(g1a, g1a + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO, g1b,
                                                                  g1b + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO);
                     tc::mbar_wait_warp(&full[st & 1u], (st >> 1) & 1u, PLUME_TC_POLL_NS);
                     tc::mbar_wait_warp(&wfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_POLL_NS);
                     tc::tc_fence_after();
-                    if (c >= 1) {
-                        // Nothing in a turn waits for work issued in the same turn (issuing the 12 MMAs blocks this thread while
-                        // the tensor pipe's queue is full): the previous chunk's store has had a whole turn to read its source ...
-                        const uint32_t pst = st - 1u;
-                        if (ld) tc::bulk_wait_group_read_all();
-                        if (ld) mbar_arrive(&sdone[pst & 1u]);
-                        if (c + 1 < 4) {                    // ... and its MMAs to complete: W2 chunk c + 1 into their stage
-                            tc::mbar_wait_warp(&bar[pst & 1u], (pst >> 1) & 1u, PLUME_TC_POLL_NS);
-                            if (ld) tc::bulk_load(b_stage(pst), w2g1 + (size_t)(c + 1) * kStashChunkBytes, (uint32_t)kStashChunkBytes,
-                                          &wfull[(c + 1) & 1]);
-                        }
+                    if (c == 2) {                           // chunk 3 will reuse chunk 0's stage: its store (two turns ago) has read it
+                        if (ld) tc::bulk_wait_group_read_1();
+                        if (ld) mbar_arrive(&sdone[0]);
                     }
                     if (c + 2 < 4) issue_l1(c + 2);         // every compute thread has read buffer c & 1 (it arrived on `full`)
                     // stash the chunk (one tensor copy: the stage's 32 KB -> the chunk's interleaved half of pair c >> 1; the
                     // producers' fence.proxy.async + the `full` barrier made their writes visible to the async proxy), then G1
-                    if (ld) tc::tensor_store_5d(&stash_map, a_stage(st), 0, c & 1, 0, 0, (int)blockIdx.x * 2 + (c >> 1));
+                    if (ld) tc::tensor_store_5d(&stash_map, a_stage(c), 0, c & 1, 0, 0, (int)blockIdx.x * 2 + (c >> 1));
                     if (ld) tc::bulk_commit_group();
                     tc::issue_split_steps(ld, tmem, g1, 4, idesc, c == 0 ? 0u : 1u);
                     if (ld) tc::mma_commit(&bar[st & 1u]);
+#ifdef PLUME_TC_STORE_PROBE
+                    if (blockIdx.x == 0 && lt == 3 && c == 0) {     // how long does the tensor store read its 32 KB source?
+                        const long long p0 = clock64();
+                        if (ld) tc::bulk_wait_group_read_all();
+                        const long long p1 = clock64();
+                        if (ld) tc::bulk_wait_group_all();
+                        if (ld) printf("tensor store of chunk 0: source read %lld cycles after the MMAs were issued, complete %lld\n",
+                                       p1 - p0, clock64() - p0);
+                    }
+#endif
+                    // The rest of the turn: the chunk's MMAs complete (~0.9 k cycles, while the compute warps produce chunk
+                    // c + 1) -> the stage's B buffers take W2 chunk c + 2, a whole production ahead of its use
+                    tc::mbar_wait_warp(&bar[st & 1u], (st >> 1) & 1u, PLUME_TC_POLL_NS);
+                    if (c + 2 < 4) {
+                        if (ld) tc::bulk_load(b_stage(st), w2g1 + (size_t)(c + 2) * kStashChunkBytes, (uint32_t)kStashChunkBytes,
+                                              &wfull[c & 1]);
+                    }
                 }
-                if (ld) tc::bulk_wait_group_read_all();
-                if (ld) mbar_arrive(&sdone[(st - 1u) & 1u]);
+                if (ld) {                                   // every store has read its stage: chunks 1, 2, 3
+                    tc::bulk_wait_group_read_all();
+                    mbar_arrive(&sdone[1]);
+                    mbar_arrive(&sdone[0]);
+                    mbar_arrive(&sdone[1]);
+                }
                 // ---- backward: eight 32 KB bulk copies per tile go through the two halves of stage 1, in this order per half h:
                 // W2^T chunk h (G2, inputs 0..127), W2^T chunk 2 + h (G2, inputs 128..255), stashed activation chunks h and
                 // 2 + h (G3).  bfull / bfree see four phases per tile and half: the parity of phase k is k & 1.
@@ -523,7 +537,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
 #else
 #define PLUME_IS(n)
 #endif
-                tc::mbar_wait_warp(&bar[1], 1u, PLUME_TC_POLL_NS);                 // G1's last step (st - 1 = 4 lt + 3) has completed: stage 1 is free
+                // (G1's last step has completed -- waited for at the end of its turn: stage 1 is free)
                 PLUME_IS(0);
                 const char* const w2t = reinterpret_cast<const char*>(w2s + kW2SplitG2);
                 if (ld) tc::bulk_load(bstage_buf(0u, 0), w2t, (uint32_t)kStashChunkBytes, &bfull[0]);
@@ -725,14 +739,20 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
         if (lt > 0) tc::mbar_wait_sleep(&g3done, (lt - 1u) & 1u, PLUME_TC_WAIT_NS);
         for (int c = 0; c < 4; ++c) {
             const uint32_t st = step;
-            acquire(st);
-            if (c >= 2) tc::mbar_wait(&sdone[st & 1u], 0u);     // chunk c - 2 of this stage has been read by its bulk store
-            uint4* ah = reinterpret_cast<uint4*>(a_stage(st));
+            // The only reused stage is chunk 3's (= chunk 0's): chunk 0's store signals `sdone` at the MMA warp's turn 2 (the
+            // barrier's next phase needs this thread's own chunk-3 arrival: the parity wait cannot fall a phase behind);
+            // chunk 0's MMAs are waited for before chunk 2 is published, below, for the same reason.
+            if (c == 3) {
+                tc::mbar_wait_sleep(&sdone[0], 0u, PLUME_TC_WAIT_NS);
+                PLUME_TL(23);
+            }
+            uint4* ah = reinterpret_cast<uint4*>(a_stage(c));
             uint4* al = ah + 1024;
             // the centred pre-activations of this thread's sample and 16 inputs (64 c + 16 ug ..) from the chunk's TMEM buffer
             float z[16];
             tc::mbar_wait_sleep(&zfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_WAIT_NS);
             tc::tc_fence_after();
+            PLUME_TL(18 + c);
             tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + 64 * (c & 1) + 16 * ug), z);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
@@ -756,7 +776,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 ah[f] = hi;
                 al[f] = lo;
             }
+            // (chunk 0's MMAs have long completed; waiting here -- before this thread's arrival lets the MMA warp issue chunk 2's,
+            // the next phase of the same barrier -- keeps the parity wait safe)
+            if (c == 2) tc::mbar_wait_sleep(&bar[0], 0u, PLUME_TC_WAIT_NS);
             publish(st);          // issuer: G1 -> columns [0,128), then the chunk's bulk store to the stash
+            if (c == 2) { PLUME_TL(22); }
             ++step;
         }
         PLUME_TL(2);
@@ -1147,11 +1171,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             printf("ppo_tc timeline (cycles): Ph0 gather+rstd %lld | G1 production %lld | G1 mma drain %lld | Ph3 LN2/loss %lld | "
                    "Ph4 %lld | G2 production %lld | G3 production %lld | Ph6 columns %lld | drain %lld | Ph6 scalars %lld | tail %lld | total %lld"
                    " || Ph3: stats %lld | heads %lld | loss %lld | loss barrier %lld | LN2-bwd means %lld"
-                   " || Ph6: A0 %lld | B0 %lld | A1 %lld | B1 %lld\n",
+                   " || Ph6: A0 %lld | B0 %lld | A1 %lld | B1 %lld || G1 (after Ph0): start c0 %lld, start c1 %lld, start c2 %lld, published c2 "
+                   "%lld, c3: stage free %lld, start %lld\n",
                    tl_[1] - tl_[0], tl_[2] - tl_[1], tl_[3] - tl_[2], tl_[4] - tl_[3], tl_[5] - tl_[4], tl_[6] - tl_[5],
                    tl_[7] - tl_[6], tl_[8] - tl_[7], 0LL, tl_[9] - tl_[8], end - tl_[9], end - tl_[0],
                    tl_[10] - tl_[3], tl_[11] - tl_[10], tl_[12] - tl_[11], tl_[13] - tl_[12], tl_[4] - tl_[13],
-                   tl_[14] - tl_[7], tl_[15] - tl_[14], tl_[16] - tl_[15], tl_[17] - tl_[16]);
+                   tl_[14] - tl_[7], tl_[15] - tl_[14], tl_[16] - tl_[15], tl_[17] - tl_[16], tl_[18] - tl_[1], tl_[19] - tl_[1], tl_[20] - tl_[1],
+                   tl_[22] - tl_[1], tl_[23] - tl_[1], tl_[21] - tl_[1]);
         }
 #endif
     }

@@ -89,8 +89,11 @@ __global__ void __launch_bounds__(kLtGroupThreads * kTPC, kCtas) stop_head_segme
     extern __shared__ __align__(128) float sm[];
     __shared__ uint64_t bar[kTPC];
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, grp = tid / kLtGroupThreads, gt = tid - grp * kLtGroupThreads;
+    // (grp, gwarp and the TMEM base go through a shuffle: the compiler then knows them to be warp-uniform and keeps the MMA
+    // descriptors derived from them in uniform registers)
+    const int tid = threadIdx.x, grp = __shfl_sync(0xffffffffu, tid / kLtGroupThreads, 0), gt = tid - grp * kLtGroupThreads;
     const int warp = gt >> 5, lane = gt & 31;
+    const int gwarp = __shfl_sync(0xffffffffu, warp, 0);     // the same value, known to the compiler as warp-uniform
     const int wq = warp & 3, part = warp >> 2;        // TMEM lane quarter / half of the hidden units
     const int row = wq * 32 + lane;                   // TMEM lane = window of the tile
     const int N = a.n_envs, W = a.W;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kLtGroupThreads * kTPC, kCtas) stop_head_segme
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem = tmem_slot + (uint32_t)(grp * S::N);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0) + (uint32_t)(grp * S::N);
     const uint32_t idesc = tc::make_idesc_f16(128, S::N);
     float* const xs = sm + L::xs + grp * kLstmMaxSteps * 128;
     float* const exch = sm + L::exch + grp * 2 * 128 * 2;
@@ -184,7 +187,11 @@ __global__ void __launch_bounds__(kLtGroupThreads * kTPC, kCtas) stop_head_segme
                 tc::fence_proxy_async();
                 tc::tc_fence_before();
                 group_sync(bid);
-                if (gt == 0) {
+                // The group's first warp issues, with WARP-UNIFORM control flow: inside a one-thread branch the compiler keeps
+                // the descriptors in vector registers and wraps every tcgen05.mma in ELECT + 7 x R2UR + BRA.U.ANY (~100 cycles
+                // of issue latency per instruction, on the critical path of every cell step); here they live in uniform
+                // registers and only the instructions themselves are predicated on lane 0.
+                if (gwarp == 0) {
                     tc::tc_fence_after();
                     const uint32_t sah = tc::smem_u32(ah), sal = tc::smem_u32(al);
                     const uint32_t sbh = tc::smem_u32(op + L::b_hi), sbl = tc::smem_u32(op + L::b_lo);
@@ -195,11 +202,13 @@ __global__ void __launch_bounds__(kLtGroupThreads * kTPC, kCtas) stop_head_segme
                         const uint64_t dal = tc::make_smem_desc(sal + off, tc::kLBO, S::sbo);
                         const uint64_t dbh = tc::make_smem_desc(sbh + off, tc::kLBO, S::sbo);
                         const uint64_t dbl = tc::make_smem_desc(sbl + off, tc::kLBO, S::sbo);
-                        tc::mma_f16(tmem, dal, dbh, idesc, j == 0 ? 0u : 1u);
-                        tc::mma_f16(tmem, dah, dbl, idesc, 1u);
-                        tc::mma_f16(tmem, dah, dbh, idesc, 1u);
+                        if (lane == 0) {
+                            tc::mma_f16(tmem, dal, dbh, idesc, j == 0 ? 0u : 1u);
+                            tc::mma_f16(tmem, dah, dbl, idesc, 1u);
+                            tc::mma_f16(tmem, dah, dbh, idesc, 1u);
+                        }
                     }
-                    tc::mma_commit(&bar[grp]);
+                    if (lane == 0) tc::mma_commit(&bar[grp]);
                 }
                 tc::mbar_wait(&bar[grp], phase & 1u);
                 ++phase;

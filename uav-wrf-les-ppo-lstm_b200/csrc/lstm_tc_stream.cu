@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
     extern __shared__ __align__(128) float sm[];
     __shared__ uint64_t full[kLsStages], empty[kLsStages], acc_full[2], acc_free[2], a_ready;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (the warp index and the TMEM base go through a shuffle: the compiler then knows them to be warp-uniform, and the MMA
+    // warp -- whose control flow is run by all 32 lanes -- keeps its descriptors in uniform registers)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int wq = warp & 3, cg = (warp >> 2) & 3;    // TMEM lane quarter / column group (8 of a chunk's 32 units)
     const int row = wq * 32 + lane;
     const int N = a.n_envs, W = a.W;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const uint32_t idesc = tc::make_idesc_f16(128, 128);
     float* const xs = sm + L::xs;
     float* const exch = sm + L::exch;
@@ -235,11 +237,12 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
                 }
             }
         } else if (any && warp == kLsComputeThreads / 32) {
-            // ---- MMA issuer (one thread) --------------------------------------------------------------------------------
-            if (lane == 0) {
+            // ---- MMA issuer: one warp with warp-uniform control flow, lane 0 issues ------------------------------------------
+            // (inside a one-lane branch every tcgen05.mma was wrapped in ELECT + 7 x R2UR + BRA.U.ANY: ~100 cycles each)
+            {
                 constexpr uint32_t per_step = (uint32_t)(S::NC * (S::KB + 1));
                 for (int step = 0; step < W; ++step) {
-                    tc::mbar_wait(&a_ready, steps_done & 1u);      // A of this step is in shared memory
+                    tc::mbar_wait_warp(&a_ready, steps_done & 1u, 20);      // A of this step is in shared memory
                     ++steps_done;
                     tc::tc_fence_after();
                     for (uint32_t w = 0; w < per_step; ++w, ++item) {
@@ -249,10 +252,10 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
                         const bool tail = kc == (uint32_t)S::KB;
                         const uint32_t b = chunk_q & 1u, use = chunk_q >> 1;
                         if (kc == 0 && use >= 1) {                 // the accumulator's previous contents have been read
-                            tc::mbar_wait(&acc_free[b], (use - 1) & 1u);
+                            tc::mbar_wait_warp(&acc_free[b], (use - 1) & 1u, 20);
                             tc::tc_fence_after();
                         }
-                        tc::mbar_wait(&full[st], (item / kLsStages) & 1u);
+                        tc::mbar_wait_warp(&full[st], (item / kLsStages) & 1u, 20);
                         tc::tc_fence_after();
                         // A: the K chunk of 64 that holds column kc * kLsBK, plus 256 bytes per K step of 16 inside it
                         const uint32_t a_sbo = tail ? 256u : 1024u, b_sbo = tail ? 256u : (uint32_t)(kLsBK / 8) * 128u;
@@ -270,13 +273,15 @@ __global__ void __launch_bounds__(kLsThreads, 1) stop_head_stream_kernel(LtArgs 
                             const uint64_t dbh = tc::make_smem_desc(bh + off, tc::kLBO, b_sbo);
                             const uint64_t dbl = tc::make_smem_desc(bl + off, tc::kLBO, b_sbo);
                             const uint32_t d = tmem + 128u * b;
-                            tc::mma_f16(d, dal, dbh, idesc, (kc == 0 && j == 0) ? 0u : 1u);
-                            tc::mma_f16(d, dah, dbl, idesc, 1u);
-                            tc::mma_f16(d, dah, dbh, idesc, 1u);
+                            if (lane == 0) {
+                                tc::mma_f16(d, dal, dbh, idesc, (kc == 0 && j == 0) ? 0u : 1u);
+                                tc::mma_f16(d, dah, dbl, idesc, 1u);
+                                tc::mma_f16(d, dah, dbh, idesc, 1u);
+                            }
                         }
-                        tc::mma_commit(&empty[st]);
+                        if (lane == 0) tc::mma_commit(&empty[st]);
                         if (tail) {
-                            tc::mma_commit(&acc_full[b]);
+                            if (lane == 0) tc::mma_commit(&acc_full[b]);
                             ++chunk_q;
                         }
                     }

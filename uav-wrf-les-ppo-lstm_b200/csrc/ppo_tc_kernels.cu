@@ -480,6 +480,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 if (ld) tc::bulk_load(b_stage(0u), w2g1, (uint32_t)kStashChunkBytes, &wfull[0]);
                 if (ld) tc::bulk_load(b_stage(1u), w2g1 + kStashChunkBytes, (uint32_t)kStashChunkBytes, &wfull[1]);
                 tc::mbar_wait_warp(&x0full, lt & 1u, PLUME_TC_POLL_NS);
+#ifdef PLUME_TC_TIMELINE
+                long long g1_[12];
+                const bool g1_on = blockIdx.x == 0 && lt == 3;
+                if (g1_on) g1_[0] = clock64();
+#endif
                 tc::mbar_wait_warp(&l1full, lt & 1u, PLUME_TC_POLL_NS);
                 tc::tc_fence_after();
                 issue_l1(0);
@@ -490,7 +495,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     const tc::MmaOperands g1 = tc::make_operands(g1a, g1a + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO, g1b,
                                                                  g1b + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO);
                     tc::mbar_wait_warp(&full[st & 1u], (st >> 1) & 1u, PLUME_TC_POLL_NS);
+#ifdef PLUME_TC_TIMELINE
+                    if (g1_on) g1_[1 + 2 * c] = clock64();
+#endif
                     tc::mbar_wait_warp(&wfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_POLL_NS);
+#ifdef PLUME_TC_TIMELINE
+                    if (g1_on) g1_[2 + 2 * c] = clock64();
+#endif
                     tc::tc_fence_after();
                     if (c == 2) {                           // chunk 3 will reuse chunk 0's stage: its store (two turns ago) has read it
                         if (ld) tc::bulk_wait_group_read_1();
@@ -521,6 +532,12 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                                               &wfull[c & 1]);
                     }
                 }
+#ifdef PLUME_TC_TIMELINE
+                if (g1_on && ld)
+                    printf("MMA warp, G1 pass (cycles after x0full): chunk full / its W2 landed: %lld/%lld %lld/%lld %lld/%lld %lld/%lld | last "
+                           "MMAs complete %lld\n", g1_[1] - g1_[0], g1_[2] - g1_[0], g1_[3] - g1_[0], g1_[4] - g1_[0], g1_[5] - g1_[0],
+                           g1_[6] - g1_[0], g1_[7] - g1_[0], g1_[8] - g1_[0], clock64() - g1_[0]);
+#endif
                 if (ld) {                                   // every store has read its stage: chunks 1, 2, 3
                     tc::bulk_wait_group_read_all();
                     mbar_arrive(&sdone[1]);
@@ -749,6 +766,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             uint4* ah = reinterpret_cast<uint4*>(a_stage(c));
             uint4* al = ah + 1024;
             // the centred pre-activations of this thread's sample and 16 inputs (64 c + 16 ug ..) from the chunk's TMEM buffer
+            // (loading them one chunk ahead, before the previous chunk is published, was tried: no gain)
             float z[16];
             tc::mbar_wait_sleep(&zfull[c & 1], (uint32_t)(c >> 1), PLUME_TC_WAIT_NS);
             tc::tc_fence_after();

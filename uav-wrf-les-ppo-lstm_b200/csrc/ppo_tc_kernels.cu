@@ -1100,20 +1100,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                 PLUME_TL(14 + c);
             }
         PLUME_TL(8);
-            tc::mbar_wait(&pdone[0], 1u);      // the column-sum GEMMs of chunks 2 and 3 (and with them 0 and 1) are complete
-            tc::mbar_wait(&pdone[1], 1u);
-            tc::tc_fence_after();
-            {                                  // an M = 64 accumulator keeps row r in TMEM lane 32 (r / 16) + r % 16: lanes 0..15
-                float pv[8];                   // of warp (wq, cg) hold inputs 64 cg + 16 wq .. of chunk cg
-                tc::tmem_ld8(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * cg), pv);
-                tc::tmem_ld_wait();
-                tc::tc_fence_before();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) Pacc[k] += pv[k];      // (lanes 16..31 accumulate columns nobody reads)
-            }
-            // (G3 may still be running: this exchange has its own area behind the scalar transposition rows and the next
-            // tile's layer-1 operands, in what was the second dy1 buffer)
-            float* const ex6 = xh + 9216;
+            // The per-sample scalars first: they need neither G3 nor the last column-sum GEMM (queued behind G3's MMAs in the
+            // tensor pipe), only the first dy1 buffer back -- chunk 2's GEMM has read it.  Their exchange area (bytes [20 KB,
+            // 24 KB)) and transposition rows ([0, 18 KB)) lie inside that buffer.
+            tc::mbar_wait(&pdone[0], 1u);
+            float* const ex6 = xh + 5120;
             ex6[(0 * G + cg) * kTcTile + srow] = m1p2.x + m1p2.y;
             ex6[(1 * G + cg) * kTcTile + srow] = m2p2.x + m2p2.y;
             quarter_sync(wq);
@@ -1179,6 +1170,17 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                         else if (k < 44) cta_loss[k - 40] += (double)sred[r];
                     }
                 }
+            }
+            // the column sums last: chunk 3's GEMM (and with it every earlier one) is complete
+            tc::mbar_wait(&pdone[1], 1u);
+            tc::tc_fence_after();
+            {                                  // an M = 64 accumulator keeps row r in TMEM lane 32 (r / 16) + r % 16: lanes 0..15
+                float pv[8];                   // of warp (wq, cg) hold inputs 64 cg + 16 wq .. of chunk cg
+                tc::tmem_ld8(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * cg), pv);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) Pacc[k] += pv[k];      // (lanes 16..31 accumulate columns nobody reads)
             }
         PLUME_TL(9);
             compute_sync();       // exch / x tile / staging are rewritten by the next tile

@@ -503,8 +503,8 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     if (g1_on) g1_[2 + 2 * c] = clock64();
 #endif
                     tc::tc_fence_after();
-                    if (c == 2) {                           // chunk 3 will reuse chunk 0's stage: its store (two turns ago) has read it
-                        if (ld) tc::bulk_wait_group_read_1();
+                    if (c == 1) {                           // chunk 3 will reuse chunk 0's stage: its store (a turn ago, the only one
+                        if (ld) tc::bulk_wait_group_read_all();      // pending) has read it -- told a turn before chunk 3 needs it
                         if (ld) mbar_arrive(&sdone[0]);
                     }
                     if (c + 2 < 4) issue_l1(c + 2);         // every compute thread has read buffer c & 1 (it arrived on `full`)

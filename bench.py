@@ -39,8 +39,8 @@ WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture; counters are not
 # readable from inside an unprofiled run, so the line cites the committed capture it copies the number from)
-PPO_TC_TRAFFIC = {"bytes": 35.2e6,
-                  "source": "profiles/r2b_ppo_tc_ncu_summary.txt (prof_r2b_ppo_tc: 34.10 MB read + 1.13 MB written)"}
+PPO_TC_TRAFFIC = {"bytes": 34.5e6,
+                  "source": "profiles/r2c_ppo_tc_ncu_summary.txt (prof_r2c_ppo_tc: 33.52 MB read + 0.98 MB written)"}
 K2_TRAFFIC = {"bytes": 316.7e6, "source": "profiles/r1h_k2_ncu_summary.txt (prof_r1h_k2, 2^20 envs)"}
 
 
@@ -526,7 +526,7 @@ def run_cuda_arm(args) -> None:
                         "profiles/ (algorithmic gather: a 48-byte record + an 8-byte permutation index x 262144 samples "
                         "= 14.7 MB; a record straddles two 32-byte sectors; the operand chunks and the activation stash, 2 KB per "
                         "sample, stay in L2); the kernel is bound by the dependencies between its CUDA-core phases and the "
-                        "tensor / copy work (issue slots 37 % busy, tensor pipe 20 %, 30 % of the samples waiting on MMAs or "
+                        "tensor / copy work (issue slots 40 % busy, tensor pipe 23 %, a quarter of the samples waiting on MMAs or "
                         "bulk copies: DESIGN.md section 5)"}
 
     # ---- end to end through the host-buffer API -------------------------------------------------------

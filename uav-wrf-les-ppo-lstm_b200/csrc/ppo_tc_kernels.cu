@@ -1,39 +1,51 @@
-// ppo_tc_kernels.cu -- K6 on the sm_100a tensor cores: the PPO minibatch gradient
-// (train_ppo2.0.py:42-85) with the three GEMM-shaped parts of the actor-critic's 256->128 layer
-// (model.py:23) on tcgen05.mma (kind::f16 with the two-term fp16 split x = hi + lo/s of tc_gemm.cuh = fp32-grade
-// accuracy at twice the TF32 rate and half the operand bytes, accumulators in TMEM) and everything else (6->256 layer,
-// both LayerNorms, heads, loss, all the reductions) on the CUDA cores of the same persistent CTA -- with packed fp32
-// pairs (FFMA2 / FMUL2 / FADD2) wherever register pairs form naturally, because the kernel is bound by instruction
-// issue.  One CTA per SM, 128-sample tiles, 16 compute warps + 1 issuer warp.  Per-launch invariants (pre-split W2, the
-// centred layer-1 weights, the LayerNorm-1 quadratic form) come from ppo_tc_prep_kernel.
+// ppo_tc_kernels.cu -- K6 on the sm_100a tensor cores: the PPO minibatch gradient (train_ppo2.0.py:42-85).  Every
+// GEMM-shaped part of the actor-critic (model.py:16-46) runs on tcgen05.mma (kind::f16 with the two-term fp16 split
+// x = hi + lo of tc_gemm.cuh: three MMAs per K-step, fp32-grade products; accumulators in TMEM); LayerNorms, ReLUs, heads,
+// loss and the per-parameter reductions run on the CUDA cores of the same persistent CTA (packed fp32 pairs FFMA2 / FMUL2 /
+// FADD2 wherever register pairs form).  One CTA per SM, 128-sample tiles, 16 compute warps + 2 MMA warps.  Per-launch
+// operands (16 W2 pre-split for G1 and for G2, the layer-1 operands, the LayerNorm-1 quadratic form) come from
+// ppo_tc_prep_kernel.  DESIGN.md section 5 has the measurements behind every choice below.
 //
-//   G1  z2[s][o]   = sum_i  h1[s][i] W2[o][i]        A = h1 (produced chunk by chunk from the 6 inputs),
-//                                                     B = W2, pre-split, streamed from L2 with cp.async
-//   G2  dh1[s][i]  = sum_o  dz2[s][o] W2[o][i]       A = dz2 (from shared memory), B = W2^T pre-split
-//   G3  dW2[o][i] += sum_s  dz2[s][o] h1[s][i]       A = dz2^T, B = h1^T (recomputed, K-major along s);
-//                                                     accumulates in TMEM across ALL tiles of the CTA
+//   L1  z1c[s][i]  = sum_k  x[s][k] W1c[i][k] + b1c[i]   K = 16 packed as [x_hi | x_lo] . [w_hi | w_hi] + [x_hi | x_lo] . [w_lo | 0];
+//                                                         per chunk of 64 inputs into one of two TMEM buffers
+//   G1  z2[s][o]   = sum_i  h1[s][i] W2[o][i]             A = h1 chunk = TMEM load of L1 -> LayerNorm scale -> ReLU -> split,
+//                                                         B = 16 W2 chunk, bulk copy from L2
+//   G2  dh1[s][i]  = sum_o  dz2[s][o] W2[o][i]            A = the resident dz2 operand read MN-major, B = 16 W2^T chunks (bulk)
+//   G3  dW2[o][i] += sum_s  dz2[s][o] h1[s][i]            A = the same dz2 bytes read K-major, B = the STASHED h1: every G1 chunk
+//                                                         is copied by one TMA tensor store into an L2 scratch where a pair of
+//                                                         chunks is interleaved, and comes back as one MN-major operand, N = 128;
+//                                                         accumulates in TMEM across ALL tiles of the CTA
+//   P   P[i][c]    = sum_s  dy1[s][i] X[s][c]             the LayerNorm-1 backward column sums, M = 64 inputs x N = 8 per chunk,
+//                                                         A = dy1 written MN-major by Ph6, X = {rstd x_0..x_5, rstd, 1}
 //
-// TMEM map (512 columns): [0,128) G1 result, then G2 result for inputs 0..127; [128,256) G1's scaled cross terms
-// (lo * 2^11, folded in with 2^-11 in the epilogue), then G2 result for inputs 128..255; [256,512) the persistent
-// dW2 accumulator (row = output o, column = input i).  G2 and G3 have no spare accumulator for their cross terms:
-// their lo parts are unscaled and the operands are pre-scaled to O(1) instead (dz_scale dz2, 16 W2^T), undone where
-// dh1 and dW2 are read.  K chunks are 64 fp16 values = the same 128 bytes per row as the former 32-value tf32 chunk.
+// Nothing is computed twice on the CUDA cores except layer 1 in the LayerNorm-1 backward (ReLU mask and xhat1; TMEM is full
+// by then), and every operand that already exists as bytes is moved by the copy engines.  MMA warp 1 (lane 0 issues) owns
+// all copies and L1 / G1 / G2 / G3, MMA warp 2 the column-sum GEMMs; both run WARP-UNIFORM control flow (all 32 lanes wait
+// and compute descriptors, which therefore live in uniform registers): inside a one-lane branch the compiler wrapped every
+// tcgen05.mma in ELECT + 7 x R2UR + BRA.U.ANY, 105-140 cycles per instruction against 64 back to back.  mbarriers carry
+// every hand-over; the compute warps meet at CTA barriers only inside Ph3 / Ph4 and at the end of a tile.
+//
+// TMEM map (512 columns): [0,128) G1 accumulator, then dh1 of inputs 0..127; [128,256) the two layer-1 buffers during the
+// G1 pass, then dh1 of inputs 128..255; the column-sum results overwrite the first 8 (consumed) dh1 columns of their chunk;
+// [256,512) the persistent dW2 accumulator (row = output o, column = input i).  Main and cross terms share one accumulator
+// everywhere: operands are brought to O(1) (16 W2, dz_scale dz2) instead of scaling lo, undone where results are read.
 //
 // Layer 1 never materialises dz1: with dy1 = relu'(y1) o dh1 and the per-sample LayerNorm scalars
-// m1 = mean_i(g1 dy1), m2 = mean_i(g1 dy1 xhat1), every layer-1 gradient is a linear function of
-//   P[i][c] = sum_s dy1[s][i] * {rstd x_0..x_5, rstd, 1}[s][c]     (column sums, accumulated per thread)
+// m1 = mean_i(g1 dy1), m2 = mean_i(g1 dy1 xhat1), every layer-1 gradient is a linear function of the column sums P
 // and of 35 per-sample scalar sums (S0, S[6], R[7], Q[6][6] symmetric); see the epilogue at the end
 // of the kernel.  z1 - mean(z1) is evaluated directly from centred weights (W1 - column mean), so
 // no mean pass is needed.  The algebra was checked against autograd in float64 and its float32
-// error matches autograd's own (DESIGN.md section 5).
+// error matches autograd's own.
 //
 // Algorithmic bytes per sample: one 48-byte record (obs 24, adv 4, ret 4, old value 4, old logp 4, action 4, pad 4;
-// plume_ppo_pack) + an 8-byte permutation index; without the records 44 B from six arrays.  Nothing else leaves the
-// SM.  FLOP per sample: 3 x 65 536 on the tensor cores (x3 MMAs for the split), ~14 000 on the CUDA cores.
+// plume_ppo_pack) + an 8-byte permutation index; without the records 44 B from six arrays.  The operand chunks and the
+// activation stash (2 KB per sample) stay in L2.  FLOP per sample: 3 x 65 536 + layer 1 on the tensor cores (x3 MMAs for
+// the split), ~10 000 on the CUDA cores.
 //
-// Build-time knobs (measured defaults, profiles/r1_notes.md): PLUME_U4 / PLUME_U6 unroll factors of the two
-// column-oriented loops, PLUME_TC_MAXNREG (register-sensitivity experiment), PLUME_TC_TMA_B (TMA bulk copies for the
-// B operand), PLUME_TC_TIMELINE (clock64 stamps per phase, printed by CTA 0).
+// Build-time knobs: PLUME_U4 unroll factor of Ph4's column loop, PLUME_TC_MAXNREG (register-sensitivity experiment),
+// PLUME_TC_POLL_NS / PLUME_TC_WAIT_NS (back-off of the MMA warps / compute warps between barrier polls: no effect between
+// 20 and 200 ns), PLUME_TC_PM / PLUME_TC_PN (shape of the column-sum MMA), PLUME_TC_TIMELINE (clock64 stamps per phase, per
+// G1 chunk and per MMA-warp turn, printed by CTA 0), PLUME_TC_STORE_PROBE (duration of a stash store).
 #include <cuda.h>            // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 
 #include "ppo_loss.cuh"
@@ -43,9 +55,6 @@
 #define PLUME_UNROLL(n) _Pragma(PLUME_STR(unroll n))
 #ifndef PLUME_U4
 #define PLUME_U4 16
-#endif
-#ifndef PLUME_U6
-#define PLUME_U6 4
 #endif
 // shape of the column-sum GEMM's instruction: M = 64 / N = 8 reads only the 64 real rows of its A operand; M = 128 / N = 16
 // (rows 64..127 and columns 8..15 garbage that nobody reads) is the form whose accumulator layout needs no explanation

@@ -286,6 +286,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __shared__ uint64_t x0full;           // "Ph0 has written the tile's x operand of the layer-1 GEMM": one arrival per compute thread
     __shared__ uint64_t l1full;           // "the layer-1 B operands have landed" (bulk-copy bytes)
     __shared__ uint64_t zfull[2];         // "the layer-1 pre-activations of a chunk are complete in this TMEM buffer"
+    __shared__ uint64_t zread[2];         // "every compute thread has loaded this TMEM buffer": it may take the chunk after next
     __shared__ uint64_t wfull[2];         // "the W2 chunk of a G1 step has landed in the stage's B buffers" (bulk-copy bytes)
     __shared__ uint64_t dyfull[2];        // "the dy1 operand chunk in this buffer is written": one arrival per compute thread
     __shared__ uint64_t pdone[2];         // "the column-sum MMAs reading this buffer have completed"
@@ -327,6 +328,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::mbar_init(&g2half[i], 1);
             tc::mbar_init(&dyfull[i], kTcThreads);
             tc::mbar_init(&zfull[i], 1);
+            tc::mbar_init(&zread[i], kTcThreads);
             tc::mbar_init(&wfull[i], 1);
             tc::mbar_init(&pdone[i], 1);
         }
@@ -503,6 +505,11 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                     const uint32_t g1a = tc::smem_u32(a_stage(c)), g1b = tc::smem_u32(b_stage(st));
                     const tc::MmaOperands g1 = tc::make_operands(g1a, g1a + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO, g1b,
                                                                  g1b + 16384u, 2 * tc::kLBO, tc::kLBO, tc::kSBO);
+                    if (c < 2) {                            // the chunk's TMEM buffer has been loaded by everyone (long before the
+                        tc::mbar_wait_warp(&zread[c], lt & 1u, PLUME_TC_POLL_NS);     // chunk is published): refill it with chunk c + 2
+                        tc::tc_fence_after();
+                        issue_l1(c + 2);
+                    }
                     tc::mbar_wait_warp(&full[st & 1u], (st >> 1) & 1u, PLUME_TC_POLL_NS);
 #ifdef PLUME_TC_TIMELINE
                     if (g1_on) g1_[1 + 2 * c] = clock64();
@@ -516,7 +523,6 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
                         if (ld) tc::bulk_wait_group_read_all();      // pending) has read it -- told a turn before chunk 3 needs it
                         if (ld) mbar_arrive(&sdone[0]);
                     }
-                    if (c + 2 < 4) issue_l1(c + 2);         // every compute thread has read buffer c & 1 (it arrived on `full`)
                     // stash the chunk (one tensor copy: the stage's 32 KB -> the chunk's interleaved half of pair c >> 1; the
                     // producers' fence.proxy.async + the `full` barrier made their writes visible to the async proxy), then G1
                     if (ld) tc::tensor_store_5d(&stash_map, a_stage(c), 0, c & 1, 0, 0, (int)blockIdx.x * 2 + (c >> 1));
@@ -783,6 +789,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + 64 * (c & 1) + 16 * ug), z);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
+            if (c < 2) mbar_arrive(&zread[c]);      // (chunks 0 and 1: their buffers take chunks 2 and 3)
 #pragma unroll
             for (int uu = 0; uu < UPT; ++uu) {
                 const int u = UPT * ug + uu;

@@ -729,18 +729,25 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
             // LayerNorm-1 rstd of this sample from the quadratic form (float64: 48 operations instead of the
             // 1800 FMAs of evaluating all 256 pre-activations once more just for their sum of squares)
             const double xd[6] = {(double)q0.x, (double)q0.y, (double)q0.z, (double)q0.w, (double)q1.x, (double)q1.y};
-            double ssq = ln1q[0];
+            // (six independent chains -- one per row of the quadratic form -- instead of one of 27 dependent DFMAs: only four
+            // of the sixteen warps are here and the others wait for them)
+            double part[6];
             int qi = 7;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                ssq = fma(ln1q[1 + k], xd[k], ssq);
+                double row = ln1q[1 + k];
 #pragma unroll
                 for (int l = k; l < 6; ++l) {
-                    ssq = fma(ln1q[qi] * xd[k], xd[l], ssq);
+                    row = fma(ln1q[qi], xd[l], row);
                     ++qi;
                 }
+                part[k] = row * xd[k];
             }
-            const float rstd1_s = (float)(1.0 / sqrt(ssq * (1.0 / 256.0) + (double)kLnEps));
+            const double ssq = ln1q[0] + ((part[0] + part[1]) + (part[2] + part[3])) + (part[4] + part[5]);
+            // float32 from here: rsqrt of a float64-accurate mean square (one Newton step brings it to <= 1 ulp)
+            const float msq = (float)(ssq * (1.0 / 256.0) + (double)kLnEps);
+            float rstd1_s = rsqrtf(msq);
+            rstd1_s = rstd1_s * fmaf(-0.5f * msq * rstd1_s, rstd1_s, 1.5f);
             *reinterpret_cast<float4*>(xt + tid * 8) = q0;
             *reinterpret_cast<float4*>(xt + tid * 8 + 4) = make_float4(q1.x, q1.y, rstd1_s, 0.0f);
             // A operand of the layer-1 GEMM (in the xhat2 / staging region, idle until Ph3): row = sample, K slot 0 = fp16 hi of

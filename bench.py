@@ -42,6 +42,7 @@ WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(
 PPO_TC_TRAFFIC = {"bytes": 34.5e6,
                   "source": "profiles/r2c_ppo_tc_ncu_summary.txt (prof_r2c_ppo_tc: 33.52 MB read + 0.98 MB written)"}
 K2_TRAFFIC = {"bytes": 316.7e6, "source": "profiles/r1h_k2_ncu_summary.txt (prof_r1h_k2, 2^20 envs)"}
+K1_TRAFFIC = {"bytes": 2.009e9, "source": "profiles/r2_ncu_summary.txt (prof_r2_k1, 1024 envs: 1.993 GB written + 0.016 GB read)"}
 
 
 def measured_peaks():
@@ -215,8 +216,8 @@ def plume_kernel_rooflines(pb, torch, peaks, dev) -> dict:
     ms = min(timed(gen, sync) for _ in range(5))
     bytes_k1 = n1 * 2 * 500 * 500 * 4
     out["plume_generate_f32"] = {"bound": "hbm", "achieved": bytes_k1 / ms / 1e6, "peak": peaks["hbm_gbs"],
-                                 "unit": "GB/s", "frac": bytes_k1 / ms / 1e6 / peaks["hbm_gbs"], "traffic": None,
-                                 "ms": ms, "envs": n1, "algorithmic_bytes": bytes_k1, "peak_source": peaks["source"]}
+                                 "unit": "GB/s", "frac": bytes_k1 / ms / 1e6 / peaks["hbm_gbs"], "traffic": K1_TRAFFIC["bytes"],
+                                 "traffic_source": K1_TRAFFIC["source"], "ms": ms, "envs": n1, "algorithmic_bytes": bytes_k1, "peak_source": peaks["source"]}
     del env
     torch.cuda.empty_cache()
     # K2: procedural field.  Algorithmic bytes per env-step in the kernel's own layout (csrc/env_kernels.cu):

@@ -40,7 +40,7 @@ WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture; counters are not
 # readable from inside an unprofiled run, so the line cites the committed capture it copies the number from)
 PPO_TC_TRAFFIC = {"bytes": 34.5e6,
-                  "source": "profiles/r2c_ppo_tc_ncu_summary.txt (prof_r2c_ppo_tc: 33.52 MB read + 0.98 MB written)"}
+                  "source": "profiles/r2d_ppo_tc_ncu_summary.txt (prof_r2d_ppo_tc: 33.5 MB read + 1.0 MB written)"}
 K2_TRAFFIC = {"bytes": 316.7e6, "source": "profiles/r1h_k2_ncu_summary.txt (prof_r1h_k2, 2^20 envs)"}
 K1_TRAFFIC = {"bytes": 2.009e9, "source": "profiles/r2_ncu_summary.txt (prof_r2_k1, 1024 envs: 1.993 GB written + 0.016 GB read)"}
 

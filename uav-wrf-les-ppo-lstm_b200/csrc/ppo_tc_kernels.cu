@@ -307,7 +307,7 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a value the compiler knows to be warp-uniform)
 #ifdef PLUME_TC_TIMELINE
-    long long kt_[4] = {0, 0, 0, 0};
+    long long kt_[4] = {0, 0, 0, 0}, kp_[3] = {0, 0, 0};
     const bool kt_on = (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && tid == 0;
     if (kt_on) kt_[0] = clock64();
 #endif
@@ -340,7 +340,13 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     }
     if (tid < 48) cta_acc[tid] = 0.0f;
     if (tid < 4) cta_loss[tid] = 0.0;
+#ifdef PLUME_TC_TIMELINE
+    if (kt_on) kp_[0] = clock64();
+#endif
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+#ifdef PLUME_TC_TIMELINE
+    if (kt_on) kp_[1] = clock64();
+#endif
     float* const exch = sm + TcSmem::exch;
     // exchange slot k of column group g, row r: slot-major, so that the 32 rows of a warp hit 32 banks
     auto EX = [&](int k, int g, int r) -> float& { return exch[(k * G + g) * kTcTile + r]; };
@@ -348,31 +354,54 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+#ifdef PLUME_TC_TIMELINE
+    if (kt_on) kp_[2] = clock64();
+#endif
     if (tid < kTcThreads) {
-        // centred layer-1 weights / bias and the quadratic form come from the prep kernel's layer-1 block
-        for (int i = tid; i < 6 * 256; i += kTcThreads) sm[TcSmem::W1c + i] = w2s[kWsW1c + i];
-        for (int i = tid; i < 256; i += kTcThreads) {
-            sm[TcSmem::P1 + i] = w2s[kWsB1c + i];
-            sm[TcSmem::P1 + 256 + i] = params[PLUME_OFF_G1 + i];
-            sm[TcSmem::P1 + 512 + i] = params[PLUME_OFF_BE1 + i];
+        // centred layer-1 weights / bias and the quadratic form come from the prep kernel's layer-1 block.  All global loads
+        // are issued before the first shared-memory store: loop by loop (load, store, next loop) the staging was six
+        // dependent round trips to L2, 4-6 k cycles per launch.
+        float t_w1[3], t_p1[3] = {0.0f, 0.0f, 0.0f}, t_p2[3] = {0.0f, 0.0f, 0.0f}, t_wh[2], t_bh = 0.0f;
+        double t_q = 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) t_w1[r] = w2s[kWsW1c + tid + r * kTcThreads];
+        if (tid < 256) {
+            t_p1[0] = w2s[kWsB1c + tid];
+            t_p1[1] = params[PLUME_OFF_G1 + tid];
+            t_p1[2] = params[PLUME_OFF_BE1 + tid];
         }
-        for (int i = tid; i < 128; i += kTcThreads) {
-            sm[TcSmem::P2 + i] = params[PLUME_OFF_B2 + i];
-            sm[TcSmem::P2 + 128 + i] = params[PLUME_OFF_G2 + i];
-            sm[TcSmem::P2 + 256 + i] = params[PLUME_OFF_BE2 + i];
+        if (tid < 128) {
+            t_p2[0] = params[PLUME_OFF_B2 + tid];
+            t_p2[1] = params[PLUME_OFF_G2 + tid];
+            t_p2[2] = params[PLUME_OFF_BE2 + tid];
         }
-        for (int i = tid; i < 128 * 8; i += kTcThreads) {
-            const int k = i >> 3, o = i & 7;
-            float w = 0.0f;
-            if (o < 5) w = params[PLUME_OFF_WA + o * 128 + k];
-            else if (o == 5) w = params[PLUME_OFF_WC + k];
-            else if (o == 6) w = params[PLUME_OFF_G2 + k];          // LayerNorm-2 gamma / beta ride in the two spare
-            else w = params[PLUME_OFF_BE2 + k];                     // slots of the row: one LDS.128 pair per column
-            sm[TcSmem::Wh + i] = w;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * kTcThreads, k = i >> 3, o = i & 7;
+            const int off = o < 5 ? PLUME_OFF_WA + o * 128 + k
+                                  : (o == 5 ? PLUME_OFF_WC + k
+                                            : (o == 6 ? PLUME_OFF_G2 + k          // LayerNorm-2 gamma / beta ride in the two spare
+                                                      : PLUME_OFF_BE2 + k));      // slots of the row: one LDS.128 pair per column
+            t_wh[r] = params[off];
         }
-        if (tid < 8)
-            sm[TcSmem::bh + tid] = tid < 5 ? params[PLUME_OFF_BA + tid] : (tid == 5 ? params[PLUME_OFF_BC] : 0.0f);
-        if (tid < 28) ln1q[tid] = reinterpret_cast<const double*>(w2s + kWsLn1q)[tid];
+        if (tid < 6) t_bh = tid < 5 ? params[PLUME_OFF_BA + tid] : params[PLUME_OFF_BC];
+        if (tid < 28) t_q = reinterpret_cast<const double*>(w2s + kWsLn1q)[tid];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) sm[TcSmem::W1c + tid + r * kTcThreads] = t_w1[r];
+        if (tid < 256) {
+            sm[TcSmem::P1 + tid] = t_p1[0];
+            sm[TcSmem::P1 + 256 + tid] = t_p1[1];
+            sm[TcSmem::P1 + 512 + tid] = t_p1[2];
+        }
+        if (tid < 128) {
+            sm[TcSmem::P2 + tid] = t_p2[0];
+            sm[TcSmem::P2 + 128 + tid] = t_p2[1];
+            sm[TcSmem::P2 + 256 + tid] = t_p2[2];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) sm[TcSmem::Wh + tid + r * kTcThreads] = t_wh[r];
+        if (tid < 8) sm[TcSmem::bh + tid] = t_bh;
+        if (tid < 28) ln1q[tid] = t_q;
     }
     __syncthreads();
 
@@ -1323,8 +1352,9 @@ ppo_tc_kernel(const float* __restrict__ params, PpoArgs a, const float* __restri
     }
 #ifdef PLUME_TC_TIMELINE
     if (kt_on)
-        printf("ppo_tc kernel timeline CTA %d (cycles): prologue %lld | tiles %lld | flush %lld\n", (int)blockIdx.x,
-               kt_[1] - kt_[0], kt_[2] - kt_[1], clock64() - kt_[2]);
+        printf("ppo_tc kernel timeline CTA %d (cycles): prologue %lld (barrier init %lld, TMEM alloc %lld, first barrier %lld, "
+               "parameter staging %lld) | tiles %lld | flush %lld\n", (int)blockIdx.x, kt_[1] - kt_[0], kp_[0] - kt_[0],
+               kp_[1] - kp_[0], kp_[2] - kp_[1], kt_[1] - kp_[2], kt_[2] - kt_[1], clock64() - kt_[2]);
 #endif
     }   // compute warps
     tc::tc_fence_before();

@@ -387,6 +387,47 @@ def test_deferred_stop_head_other_hidden_sizes(hidden, path):
     assert torch.equal(sf[full][clear].bool(), (rs > 0.8)[clear])
 
 
+@pytest.mark.parametrize("chunks", [(16, 48), (8, 8, 48), (5, 59)])
+def test_overlapped_collection_changes_nothing(chunks):
+    """RolloutEngine.overlap_chunks: the segment launched as shorter lockstep segments on one stream with the stop head of
+    each on another (the head of the first rows under the lockstep kernel of the next) writes the same buffer and
+    carries the same state as the single launch -- every array bit for bit, over two consecutive segments."""
+    N, T = 80, 64
+    m, env_a, model_a, head_a, eng_a = _setup(N, T, seed=23, radius=25.0)
+    m, env_b, model_b, head_b, eng_b = _setup(N, T, seed=23, radius=25.0)
+    eng_b.overlap_chunks = chunks
+    for it in range(2):
+        a, b = eng_a.collect(), eng_b.collect()
+        torch.cuda.synchronize()
+        assert eng_b.launches == (it + 1) * 2 * len(chunks) and eng_a.launches == (it + 1) * 2
+        for name in ("obs", "actions", "rewards", "values", "log_probs", "dones", "reached", "flag_code", "stop_prob",
+                     "stop_flag", "peak_pred", "trend", "info", "episode_idx", "conc_sample", "fill_t", "src_dist"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), (it, name)
+        assert torch.equal(eng_a.window_fill, eng_b.window_fill) and torch.equal(eng_a.last_obs, eng_b.last_obs)
+        assert torch.equal(eng_a.conc_window, eng_b.conc_window)
+    assert (a.stop_prob > 0).any() and a.stop_flag.any()
+    # a horizon the chunks do not sum to falls back to the single launch
+    eng_b.collect(horizon=40)
+    assert eng_b.launches == 4 * len(chunks) + 2
+
+
+def test_trainer_overlaps_the_first_rows_of_the_stop_head():
+    """PlumeTrainer enables the two-launch split where the lockstep kernel leaves SMs idle (rollout.overlap_split); the
+    rollout of its first iteration equals the single-launch trainer's."""
+    import uav_wrf_les_ppo_lstm_b200 as m
+    ta = m.PlumeTrainer(num_envs=1024, horizon=256, seed=5, overlap_stop_head=False)
+    tb = m.PlumeTrainer(num_envs=1024, horizon=256, seed=5)
+    assert ta.engine.overlap_chunks is None and tb.engine.overlap_chunks is not None
+    assert sum(tb.engine.overlap_chunks) == 256 and len(tb.engine.overlap_chunks) == 2
+    ta.train_iteration(); tb.train_iteration()
+    torch.cuda.synchronize()
+    a, b = ta.engine.buffer, tb.engine.buffer
+    for name in ("obs", "actions", "rewards", "values", "log_probs", "dones", "stop_prob", "stop_flag", "peak_pred", "trend"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert tb.launches_per_iteration == ta.launches_per_iteration + 2
+    assert torch.allclose(ta.model.flat, tb.model.flat, atol=1e-5)
+
+
 def test_deferred_stop_head_rejects_terminating_stop():
     N, T = 32, 8
     m, env, model, head, eng = _setup(N, T, seed=1)

@@ -107,12 +107,14 @@ class PPOBuffer:
 
     # -- C view -----------------------------------------------------------------------------
     def c_rollout_buffers(self, conc_window, window_fill, last_obs, forced_actions=None, step_noise=None,
-                          noise_out=None, eval_ring=None, stop_threshold=None) -> _lib.RolloutBuffers:
-        p = _lib.ptr
+                          noise_out=None, eval_ring=None, stop_threshold=None, t0: int = 0) -> _lib.RolloutBuffers:
+        """``t0``: the segment starts at row ``t0`` of every ``[T][N]`` array (a rollout collected in several launches)."""
+        p = _lib.ptr if t0 == 0 else (lambda x: _lib.ptr(None if x is None else x[t0:]))
+        q = _lib.ptr
         return _lib.RolloutBuffers(p(self.obs), p(self.actions), p(self.rewards), p(self.values), p(self.log_probs),
                                    p(self.dones), p(self.reached), p(self.stop_prob), p(self.stop_flag),
                                    p(self.peak_pred), p(self.trend), p(self.info), p(self.episode_idx),
-                                   p(forced_actions), p(step_noise), p(noise_out), p(conc_window), p(window_fill),
-                                   p(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist),
-                                   p(self.pos_out), p(self.src_out), p(self.conc_out), p(eval_ring), p(stop_threshold),
+                                   p(forced_actions), p(step_noise), p(noise_out), q(conc_window), q(window_fill),
+                                   q(last_obs), p(self.conc_sample), p(self.fill_t), p(self.src_dist),
+                                   p(self.pos_out), p(self.src_out), p(self.conc_out), q(eval_ring), q(stop_threshold),
                                    p(self.flag_code))

@@ -17,6 +17,27 @@ from .buffer import PPOBuffer
 from .config import FIELD_PROCEDURAL
 
 
+def overlap_split(horizon: int, num_envs: int, sm_count: int) -> tuple | None:
+    """Row counts ``(h0, horizon - h0)`` of a rollout collected in two launches, or None where that does not pay.
+
+    The lockstep kernel occupies one SM per 32-env tile and is latency-bound; the deferred stop head is a throughput
+    kernel whose CTAs cannot share an SM with it (registers, shared memory).  With the head of the first ``h0`` rows on a
+    second stream, its CTAs run on the ``idle = sm_count - tiles`` SMs while the lockstep kernel produces the other rows.
+    ``h0`` is the largest multiple of 8 whose head finishes under them: per row the head costs 0.82 x the lockstep
+    iteration at 4096 envs on all 148 SMs (5.9 us against 7.2 us, bench shape) and scales with the env count.  More
+    launches do not help: a head waiting for SMs takes the ones a finished segment frees before the next segment starts,
+    and every extra lockstep launch costs ~50 us of prologue (measured: ``profiles/r2_notes.md``)."""
+    tiles = (num_envs + 31) // 32
+    idle = sm_count - tiles
+    if idle <= 0 or horizon < 32:
+        return None
+    h0 = int(horizon * idle / (idle + sm_count * 0.82 * num_envs / 4096.0)) // 8 * 8
+    h0 = min(h0, horizon // 2)
+    if h0 < 8 or h0 * 5.9 * num_envs / 4096.0 < 100.0:        # the head time hidden (us) against ~50 us for the second launch
+        return None
+    return (h0, horizon - h0)
+
+
 class RolloutEngine:
     def __init__(self, env, model, stop_head=None, horizon: int = 256, with_info: bool = False,
                  with_trend: bool = False, with_trajectory: bool = False, stop_head_path: str = "auto"):
@@ -39,6 +60,12 @@ class RolloutEngine:
         self.last_obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.launches = 0
+        # ``overlap_chunks`` (row counts summing to the horizon, or None): the deferred-head rollout is launched as that
+        # many shorter segments on a high-priority stream and the stop head of each follows on a second stream, so the
+        # (MUFU-bound) head of the rows already written runs on the SMs the (latency-bound, <= 128-CTA) lockstep kernel
+        # leaves idle.  Same kernels on the same rows: results are identical to the single launch.
+        self.overlap_chunks = None
+        self._streams = None
 
     def reset_windows(self) -> None:
         self.window_fill.zero_()
@@ -85,7 +112,16 @@ class RolloutEngine:
         else:
             lp = _lib.LstmParams()
             lp.window = self.window
+        chunks = self.overlap_chunks if (defer and forced_actions is None and step_noise is None
+                                         and noise_out is None) else None
+        if chunks is not None and (len(chunks) < 2 or sum(chunks) != T or min(chunks) < 1):
+            chunks = None
         with torch.cuda.device(env.device):
+            if chunks is not None:
+                self._collect_overlapped(bufs, lp, chunks, flags)
+                self.buffer.filled = T
+                self.buffer.flag_code_valid = True
+                return self.buffer
             rc = self.lib.plume_rollout(C.byref(env.c_config), C.byref(env.c_state), self.model.flat.data_ptr(),
                                         C.byref(lp), C.byref(bufs), T, flags, self.nan_flag.data_ptr(),
                                         torch.cuda.current_stream(env.device).cuda_stream)
@@ -94,20 +130,54 @@ class RolloutEngine:
             if self.after_loop is not None:
                 self.after_loop(self.buffer, T)
             if defer:
-                b = self.buffer
-                rc = self.lib.plume_stop_head_segment(C.byref(lp), b.conc_sample.data_ptr(), b.fill_t.data_ptr(),
-                                                      _lib.ptr(b.src_dist), T, env.num_envs,
-                                                      self.conc_window.data_ptr(), self._window_next.data_ptr(),
-                                                      env.cfg.conc_peak, b.stop_prob.data_ptr(),
-                                                      b.stop_flag.data_ptr(), b.peak_pred.data_ptr(),
-                                                      _lib.ptr(b.trend), self.stop_head_path,
-                                                      torch.cuda.current_stream(env.device).cuda_stream)
-                _lib.check(rc, "plume_stop_head_segment")
-                self.conc_window, self._window_next = self._window_next, self.conc_window
-                self.launches += 1
+                self._stop_head(lp, 0, T, torch.cuda.current_stream(env.device).cuda_stream)
         self.buffer.filled = T
         self.buffer.flag_code_valid = True
         return self.buffer
+
+    def _stop_head(self, lp, t0: int, h: int, stream: int) -> None:
+        """Deferred head of rows [t0, t0 + h): continues the window ring of the rows before it."""
+        b, env = self.buffer, self.env
+        o = (lambda x: _lib.ptr(None if x is None else x[t0:]))
+        rc = self.lib.plume_stop_head_segment(C.byref(lp), o(b.conc_sample), o(b.fill_t), o(b.src_dist), h, env.num_envs,
+                                              self.conc_window.data_ptr(), self._window_next.data_ptr(),
+                                              env.cfg.conc_peak, o(b.stop_prob), o(b.stop_flag), o(b.peak_pred),
+                                              o(b.trend), self.stop_head_path, stream)
+        _lib.check(rc, "plume_stop_head_segment")
+        self.conc_window, self._window_next = self._window_next, self.conc_window
+        self.launches += 1
+
+    def _collect_overlapped(self, bufs0, lp, chunks, flags) -> None:
+        env, dev = self.env, self.env.device
+        if self._streams is None:
+            lo, hi = torch.cuda.Stream.priority_range()
+            self._streams = (torch.cuda.Stream(device=dev, priority=hi), torch.cuda.Stream(device=dev),
+                             torch.cuda.Event(), [torch.cuda.Event() for _ in range(64)], torch.cuda.Event(),
+                             torch.cuda.Event())
+        loop_s, head_s, start, rows, loop_done, head_done = self._streams
+        main = torch.cuda.current_stream(dev)
+        start.record(main)
+        loop_s.wait_event(start)
+        head_s.wait_event(start)
+        t0 = 0
+        for k, h in enumerate(chunks):
+            bufs = bufs0 if t0 == 0 else self.buffer.c_rollout_buffers(self.conc_window, self.window_fill,
+                                                                       self.last_obs, t0=t0)
+            rc = self.lib.plume_rollout(C.byref(env.c_config), C.byref(env.c_state), self.model.flat.data_ptr(),
+                                        C.byref(lp), C.byref(bufs), h, flags, self.nan_flag.data_ptr(),
+                                        loop_s.cuda_stream)
+            _lib.check(rc, "plume_rollout")
+            self.launches += 1
+            rows[k % 64].record(loop_s)
+            head_s.wait_event(rows[k % 64])
+            self._stop_head(lp, t0, h, head_s.cuda_stream)
+            t0 += h
+        loop_done.record(loop_s)
+        main.wait_event(loop_done)
+        if self.after_loop is not None:
+            self.after_loop(self.buffer, t0)
+        head_done.record(head_s)
+        main.wait_event(head_done)
 
     def check_nan(self) -> None:
         """model.py:41-43: raise if any logit was NaN during the last rollout(s)."""

@@ -14,7 +14,7 @@ from .env import VecMethaneEnv
 from .learner import (MATERIALISE_PERM_MIN, FusedAdam, PPOTrainer, UpdateWorkspace, materialise_permutations,
                       update_model)
 from .model import PeakAndStopPredictor, PPOActorCritic
-from .rollout import RolloutEngine
+from .rollout import RolloutEngine, overlap_split
 
 
 class PlumeTrainer:
@@ -22,7 +22,7 @@ class PlumeTrainer:
                  seed: int = 0, minibatch_size: int | None = None, stop_head: bool = True,
                  rank: int = 0, world_size: int = 1, process_group=None, with_info: bool = False,
                  with_trend: bool = True, cfg: PlumeConfig | None = None, gradient_exchange: str = "peer",
-                 with_trajectory: bool = False, lstm_hidden: int = 32):
+                 with_trajectory: bool = False, lstm_hidden: int = 32, overlap_stop_head: bool = True):
         self.cfg = cfg or config_for(version)
         self.device = torch.device(device)
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
@@ -35,6 +35,10 @@ class PlumeTrainer:
         self.head = PeakAndStopPredictor(hidden_dim=lstm_hidden, device=self.device) if stop_head else None
         self.engine = RolloutEngine(self.env, self.model, self.head, horizon=horizon, with_info=with_info,
                                     with_trend=with_trend and stop_head, with_trajectory=with_trajectory)
+        # the stop head of the first rows runs on the SMs the lockstep kernel leaves idle (rollout.overlap_split)
+        if overlap_stop_head and stop_head and self.device.type == "cuda":
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self.engine.overlap_chunks = overlap_split(self.horizon, self.num_envs, sms)
         self.optimizer = FusedAdam(self.model, lr=self.cfg.learning_rate, max_grad_norm=self.cfg.max_grad_norm)
         # multi-GPU, gradient_exchange="peer" (default): every exchange step of the iteration -- gradient all-reduce
         # fused with clip + Adam, the advantage statistics, the curriculum's flag codes -- goes over NVLink peer
@@ -61,6 +65,8 @@ class PlumeTrainer:
         # normalise, (weight prep, gradient, clip + Adam) per optimiser step; + sample records and the epoch
         # permutations when they are materialised (below)
         self.launches_per_iteration = 1 + (1 if stop_head else 0) + 4 + 2 + 3 * self.cfg.epochs * n_mb
+        if self.engine.overlap_chunks is not None:
+            self.launches_per_iteration += 2 * (len(self.engine.overlap_chunks) - 1)
         # the epoch permutations do not depend on the rollout: they are written out on a side stream while the
         # (latency-bound) rollout kernel runs
         self._perm_stream = None

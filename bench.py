@@ -40,7 +40,7 @@ WORKLOAD = ("PPOV2.1 4096 envs/GPU: fused rollout (MLP policy + env step + LSTM(
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture; counters are not
 # readable from inside an unprofiled run, so the line cites the committed capture it copies the number from)
 PPO_TC_TRAFFIC = {"bytes": 34.5e6,
-                  "source": "profiles/r2d_ppo_tc_ncu_summary.txt (prof_r2d_ppo_tc: 33.5 MB read + 1.0 MB written)"}
+                  "source": "profiles/r2e_ppo_tc_ncu_summary.txt (prof_r2e_ppo_tc: 33.5 MB read + 1.0 MB written)"}
 K2_TRAFFIC = {"bytes": 316.7e6, "source": "profiles/r1h_k2_ncu_summary.txt (prof_r1h_k2, 2^20 envs)"}
 K1_TRAFFIC = {"bytes": 2.009e9, "source": "profiles/r2_ncu_summary.txt (prof_r2_k1, 1024 envs: 1.993 GB written + 0.016 GB read)"}
 
@@ -493,19 +493,27 @@ def run_cuda_arm(args) -> None:
                                                       pb._lib.KERNEL_AUTO,
                                                       torch.cuda.current_stream().cuda_stream), "stop_head_segment")
         seg_ms = min(timed(seg_call, sync) for _ in range(3))
+    # the trainer collects the rollout in two launches with the stop head of the first rows under the second one
+    # (rollout.overlap_split); the lockstep kernel alone = a single-launch collection minus the stop-head kernel
+    chunks, hook = eng.overlap_chunks, eng.after_loop
+    eng.overlap_chunks, eng.after_loop = None, None           # no flag-code exchange outside an iteration
+    single_ms = min(timed(lambda: eng.collect(), sync) for _ in range(3))
+    eng.overlap_chunks, eng.after_loop = chunks, hook
     n_opt = cfg.epochs * ((M + mb - 1) // mb)
     flops_grad = 3 * 70144 * min(mb, M)
     flops_roll = N * T * (70144 + 20 * 2 * 4 * 32 * 33)
     kernels = {
         "ppo_grad(tcgen05 f16 split)": {"ms": grad_ms, "launches_per_step": 2 * n_opt, "tflops": flops_grad / grad_ms / 1e9,
                                       "share_of_step": grad_ms * n_opt / (total_ms / args.steps)},
-        "rollout": {"ms": roll_ms / args.steps, "launches_per_step": 2 if seg_ms else 1,
+        "rollout": {"ms": roll_ms / args.steps,
+                    "launches_per_step": (2 if seg_ms else 1) * (len(chunks) if chunks else 1),
+                    "overlapped_rows": list(chunks) if chunks else None, "single_launch_ms": single_ms,
                     "tflops": flops_roll / (roll_ms / args.steps) / 1e9,
                     "share_of_step": roll_ms / total_ms,
                     "us_per_lockstep_iteration": 1e3 * roll_ms / args.steps / T,
                     "stop_head_segment_ms": seg_ms,
                     "stop_head_segment_tflops": (N * T * 20 * 2 * 4 * 32 * 33 / seg_ms / 1e9) if seg_ms else None,
-                    "lockstep_loop_ms": (roll_ms / args.steps - seg_ms) if seg_ms else roll_ms / args.steps},
+                    "lockstep_loop_ms": (single_ms - seg_ms) if seg_ms else single_ms},
         "gae(scan+normalise)": {"ms": gae_ms, "launches_per_step": 2, "gbs": 32 * M / gae_ms / 1e6,
                                 "hbm_frac": 32 * M / gae_ms / 1e6 / peaks["hbm_gbs"],
                                 "share_of_step": gae_ms / (total_ms / args.steps)},

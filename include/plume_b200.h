@@ -369,7 +369,8 @@ int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int6
                    float entropy_beta, float* grads, double* loss_out, int32_t* nan_flag, void* workspace,
                    int64_t workspace_bytes, int32_t kernel_path, void* stream);
 /* The whole optimiser loop of _update_model (train_ppo2.0.py:42-87) in one call: `epochs` passes over the
- * batch->total transitions in minibatches of mb_size; per step: zero grads, plume_ppo_grad (divisor mb * world),
+ * batch->total transitions in minibatches of mb_size; per step: zero grads (folded into the gradient launch's operand
+ * preparation on the tensor-core path), plume_ppo_grad (divisor mb * world),
  * plume_clip_adam -- or plume_allreduce_clip_adam when comm != NULL.  perms: int64 [epochs][M] (NULL = the stateless
  * bijection keyed by (perm_seed, epoch)); first_step = the optimiser's step number of the first step (1-based);
  * losses double[epochs * ceil(M / mb_size)][4] (zeroed by the caller); grad_norm_out (may be NULL) receives the last

@@ -21,7 +21,7 @@ e1.record()
 torch.cuda.synchronize()
 r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 rr = []
-for _ in range(5):
+for _ in range(12):
     tr.train_iteration(rollout_events=(r0, r1))
     torch.cuda.synchronize()
     rr.append(r0.elapsed_time(r1))

@@ -423,11 +423,11 @@ extern "C" int plume_ppo_pack(const plume_ppo_batch* batch, float* packed, void*
     return launch_ppo_pack(*batch, packed, as_stream(stream));
 }
 
-extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int64_t* perm,
-                              uint64_t perm_seed, int32_t epoch, int64_t mb_start, int64_t mb_size,
-                              int64_t mb_size_global, float clip_eps, float entropy_beta, float* grads,
-                              double* loss_out, int32_t* nan_flag, void* workspace, int64_t workspace_bytes,
-                              int32_t kernel_path, void* stream) {
+// zero_grads: the launch clears `grads` itself before accumulating (the optimiser loop; plume_ppo_grad accumulates)
+static int ppo_grad_impl(const float* params, const plume_ppo_batch* batch, const int64_t* perm, uint64_t perm_seed,
+                         int32_t epoch, int64_t mb_start, int64_t mb_size, int64_t mb_size_global, float clip_eps,
+                         float entropy_beta, float* grads, double* loss_out, int32_t* nan_flag, void* workspace,
+                         int64_t workspace_bytes, int32_t kernel_path, void* stream, bool zero_grads) {
     PLUME_CHECK_ARG(params && batch && grads && loss_out && nan_flag && workspace, "null pointer");
     PLUME_CHECK_ARG(kernel_path >= PLUME_KERNEL_AUTO && kernel_path <= PLUME_KERNEL_SIMT, "unknown kernel_path");
     PLUME_CHECK_ARG(batch->obs && batch->actions && batch->old_log_probs && batch->advantages && batch->returns &&
@@ -436,7 +436,10 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
     PLUME_CHECK_ARG(mb_size_global >= mb_size && mb_size_global > 0, "mb_size_global must be >= mb_size");
     PLUME_CHECK_ARG(workspace_bytes >= plume_ppo_workspace_bytes(mb_size), "workspace too small");
     PLUME_CHECK_ARG((reinterpret_cast<uintptr_t>(batch->packed) & 15) == 0, "packed records must be 16-byte aligned");
-    if (mb_size == 0) return 0;
+    if (mb_size == 0) {
+        if (zero_grads) PLUME_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * PLUME_MLP_PARAMS, as_stream(stream)));
+        return 0;
+    }
     static bool configured = false;
     const int smem_a = (MlpSmem::total + 7 * 32 + 64) * (int)sizeof(float);
     const int smem_b = (6 * 256 + 3 * 256 + 32 * 128 + 32 * kH1Stride) * (int)sizeof(float);
@@ -460,7 +463,8 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
     a.loss_out = loss_out;
     a.nan_flag = nan_flag;
     a.ws_dz2 = a.ws_x = a.ws_stat = nullptr;
-    if (use_tc_path(mb_size, kernel_path)) return launch_ppo_tc(params, a, workspace, as_stream(stream));
+    if (use_tc_path(mb_size, kernel_path)) return launch_ppo_tc(params, a, workspace, as_stream(stream), zero_grads);
+    if (zero_grads) PLUME_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * PLUME_MLP_PARAMS, as_stream(stream)));
     const int64_t padded = ((mb_size + kTileM - 1) / kTileM) * kTileM;
     uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
     a.ws_dz2 = reinterpret_cast<float*>(wsp);
@@ -478,8 +482,17 @@ extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch,
     return 0;
 }
 
+extern "C" int plume_ppo_grad(const float* params, const plume_ppo_batch* batch, const int64_t* perm,
+                              uint64_t perm_seed, int32_t epoch, int64_t mb_start, int64_t mb_size,
+                              int64_t mb_size_global, float clip_eps, float entropy_beta, float* grads,
+                              double* loss_out, int32_t* nan_flag, void* workspace, int64_t workspace_bytes,
+                              int32_t kernel_path, void* stream) {
+    return ppo_grad_impl(params, batch, perm, perm_seed, epoch, mb_start, mb_size, mb_size_global, clip_eps, entropy_beta,
+                         grads, loss_out, nan_flag, workspace, workspace_bytes, kernel_path, stream, false);
+}
+
 // The whole optimiser loop of _update_model (train_ppo2.0.py:42-87) behind one call: `epochs` passes over the M
-// transitions in minibatches of mb_size, each step = zero the gradient, plume_ppo_grad, clip + Adam (fused with the
+// transitions in minibatches of mb_size, each step = zero the gradient (inside the gradient launch), plume_ppo_grad, clip + Adam (fused with the
 // all-reduce over peer memory when `comm` is given).  The launches are the same as when the host drives the steps one
 // by one; the loop only lives on this side of the ABI, because at the reference's BATCH_SIZE = 256 an iteration is
 // 20 480 steps of ~15 us and a Python call per launch costs more than the kernels.
@@ -506,10 +519,9 @@ extern "C" int plume_ppo_update(float* params, float* grads, float* exp_avg, flo
         const int64_t* perm = perms ? perms + (int64_t)epoch * M : nullptr;
         for (int64_t start = 0; start < M; start += mb_size, ++step, ++row) {
             const int64_t size = (M - start) < mb_size ? (M - start) : mb_size;
-            PLUME_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * PLUME_MLP_PARAMS, as_stream(stream)));
-            int rc = plume_ppo_grad(params, batch, perm, perm_seed, epoch, start, size, size * world, clip_eps,
-                                    entropy_beta, grads, losses + 4 * row, nan_flag, workspace, workspace_bytes,
-                                    kernel_path, stream);
+            int rc = ppo_grad_impl(params, batch, perm, perm_seed, epoch, start, size, size * world, clip_eps,
+                                   entropy_beta, grads, losses + 4 * row, nan_flag, workspace, workspace_bytes,
+                                   kernel_path, stream, true);
             if (rc) return rc;
             rc = comm ? plume_allreduce_clip_adam(comm, params, grads, exp_avg, exp_avg_sq, PLUME_MLP_PARAMS, max_norm,
                                                   lr, beta1, beta2, eps, step, grad_norm_out, stream)

@@ -24,7 +24,8 @@ struct PpoArgs {
 
 // tensor-core path (ppo_tc_kernels.cu)
 int64_t ppo_tc_workspace_bytes();
-int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s);
+// zero_grads: the operand-preparation kernel also clears a.grads (the optimiser loop's memset folded into it)
+int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s, bool zero_grads = false);
 int launch_ppo_pack(const plume_ppo_batch& b, float* packed, cudaStream_t s);
 
 struct SampleLoss {

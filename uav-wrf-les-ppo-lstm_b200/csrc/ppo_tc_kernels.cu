@@ -160,7 +160,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // ---- W2 -> fp16 hi/lo operand chunks in the canonical K-major layout (once per minibatch) -------------
 // One thread per 16-byte operand slot (8 consecutive K values of one row).
 constexpr int kPrepSplitBlocks = 32;                  // 32 x 256 threads = 8192 operand slots; block 32 = layer-1 block
-__global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restrict__ params, float* __restrict__ w2s) {
+__global__ void __launch_bounds__(256) ppo_tc_prep_kernel(const float* __restrict__ params, float* __restrict__ w2s,
+                                                          float* __restrict__ zero) {
+    // the gradient accumulator of the launch that follows (plume_ppo_update: no separate memset on the stream)
+    if (zero != nullptr && blockIdx.x < kPrepSplitBlocks)
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < PLUME_MLP_PARAMS; i += kPrepSplitBlocks * 256) zero[i] = 0.0f;
     if (blockIdx.x == kPrepSplitBlocks) {
         // ---- layer-1 invariants: thread = output o --------------------------------------------------------------
         // z_o - mean_o(z) = (b_o - mean b) + sum_k x_k (w_ok - mean_o w_ok): centred weights make the LayerNorm-1 mean
@@ -1412,7 +1416,7 @@ static int make_stash_map(CUtensorMap* map, void* stash, int pairs) {
     return 0;
 }
 
-int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s) {
+int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaStream_t s, bool zero_grads) {
     static bool configured = false;
     const int smem = TcSmem::total * (int)sizeof(float);
     if (!configured) {
@@ -1421,7 +1425,7 @@ int launch_ppo_tc(const float* params, const PpoArgs& a, void* workspace, cudaSt
         configured = true;
     }
     float* w2s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-    ppo_tc_prep_kernel<<<kPrepSplitBlocks + 1, 256, 0, s>>>(params, w2s);
+    ppo_tc_prep_kernel<<<kPrepSplitBlocks + 1, 256, 0, s>>>(params, w2s, zero_grads ? a.grads : nullptr);
     if (cudaGetLastError() != cudaSuccess) return fail("ppo_tc_prep_kernel launch failed");
     const long long tiles = (a.mb_size + kTcTile - 1) / kTcTile;
     int grid = sm_count();

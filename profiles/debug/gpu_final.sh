@@ -1,7 +1,5 @@
-set -x
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-python bench.py > gpurun_out/bench_r1q.log 2> gpurun_out/bench_r1q.err; tail -c 300 gpurun_out/bench_r1q.err
-python bench.py --steps 2 --warmup 3 --skip-cpu --skip-aux > gpurun_out/plain_r1q.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1q.csv python bench.py --steps 2 --warmup 3 --skip-cpu --skip-aux > gpurun_out/ncu_launch_r1q.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ppo_tc_kernel -s 60 -c 1 -o gpurun_out/prof_r1q_ppo_tc -f python bench.py --steps 2 --warmup 3 --skip-cpu --skip-aux > gpurun_out/ncu_full_r1q.log 2>&1
-tail -2 gpurun_out/ncu_full_r1q.log
+# final check of the committed state: whole GPU suite, smoke(), the default bench line
+timeout 600 python -m pytest tests -m gpu -q --timeout=200 2>&1 | tail -3
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err
+tail -c 300 gpurun_out/r2f_bench_n1.json; echo

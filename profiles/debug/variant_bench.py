@@ -9,6 +9,8 @@ if len(sys.argv) > 1 and sys.argv[1] != "-":
 tr = pb.PlumeTrainer(num_envs=4096, horizon=256, minibatch_size=4096 * 256 // 4)
 if len(sys.argv) > 2:                       # rollout collected in overlapped chunks: e.g. 32,32,32,160; "0" = single launch
     tr.engine.overlap_chunks = tuple(int(v) for v in sys.argv[2].split(",")) if sys.argv[2] != "0" else None
+if len(sys.argv) > 3:                       # "0": the stream waits for the stop head right after the rollout
+    tr.defer_head_join = sys.argv[3] != "0"
 for _ in range(3):
     tr.train_iteration()
 torch.cuda.synchronize()

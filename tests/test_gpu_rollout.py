@@ -425,6 +425,14 @@ def test_trainer_overlaps_the_first_rows_of_the_stop_head():
     for name in ("obs", "actions", "rewards", "values", "log_probs", "dones", "stop_prob", "stop_flag", "peak_pred", "trend"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert tb.launches_per_iteration == ta.launches_per_iteration + 2
+    # a collection may be left pending behind the lockstep kernels and joined later (off in the trainer: no gain)
+    assert not tb.defer_head_join and not tb.engine._head_pending
+    seg = tb.engine.collect(join=False)
+    assert tb.engine._head_pending
+    tb.engine.join_stop_head()
+    assert not tb.engine._head_pending
+    ref = ta.engine.collect()
+    torch.cuda.synchronize()
     assert torch.allclose(ta.model.flat, tb.model.flat, atol=1e-5)
 
 

@@ -66,6 +66,7 @@ class RolloutEngine:
         # leaves idle.  Same kernels on the same rows: results are identical to the single launch.
         self.overlap_chunks = None
         self._streams = None
+        self._head_pending = False
 
     def reset_windows(self) -> None:
         self.window_fill.zero_()
@@ -74,14 +75,18 @@ class RolloutEngine:
     def collect(self, greedy: bool = False, stop_terminates: bool = False, forced_actions=None,
                 step_noise=None, noise_out=None, horizon: int | None = None,
                 defer_stop_head: bool | None = None, stop_mode: str | None = None, step_guard: int = 0,
-                eval_ring=None, stop_threshold=None) -> PPOBuffer:
+                eval_ring=None, stop_threshold=None, join: bool = True, end_event=None) -> PPOBuffer:
         """Runs ``horizon`` lockstep iterations and returns the filled buffer (asynchronous).
         ``defer_stop_head`` (default: whenever the stop decision does not terminate episodes)
         evaluates the LSTM head and the trend features after the loop in one batched kernel.
         ``stop_mode`` ("fixed" / "threshold"; engines without a stop head): the V1.1 / V2.0 evaluator stop test runs
         inside the kernel and ends the episode; ``eval_ring`` [N,10] float64 carries the last 10 samples across
         segments, ``stop_threshold`` [N] float64 holds the V2.0 controller's current thresholds, ``step_guard`` ends
-        an episode at that step count (evaluate_model.py:52)."""
+        an episode at that step count (evaluate_model.py:52).
+        ``join=False`` (overlapped collection only): the caller's stream continues after the LOCKSTEP kernels -- rewards,
+        values, flags are complete, the stop head's outputs are not until ``join_stop_head()``; work that does not read
+        them (curriculum, GAE) then runs under the last stop-head launch.  ``end_event``: recorded behind the last launch
+        of the collection, on whichever stream that is."""
         env, T = self.env, int(horizon or self.horizon)
         assert T <= self.horizon
         defer = (self.stop_head is not None and not stop_terminates) if defer_stop_head is None else bool(defer_stop_head)
@@ -117,8 +122,9 @@ class RolloutEngine:
         if chunks is not None and (len(chunks) < 2 or sum(chunks) != T or min(chunks) < 1):
             chunks = None
         with torch.cuda.device(env.device):
+            self.join_stop_head()                 # a collection the caller left pending
             if chunks is not None:
-                self._collect_overlapped(bufs, lp, chunks, flags)
+                self._collect_overlapped(bufs, lp, chunks, flags, join, end_event)
                 self.buffer.filled = T
                 self.buffer.flag_code_valid = True
                 return self.buffer
@@ -131,6 +137,8 @@ class RolloutEngine:
                 self.after_loop(self.buffer, T)
             if defer:
                 self._stop_head(lp, 0, T, torch.cuda.current_stream(env.device).cuda_stream)
+            if end_event is not None:
+                end_event.record(torch.cuda.current_stream(env.device))
         self.buffer.filled = T
         self.buffer.flag_code_valid = True
         return self.buffer
@@ -147,7 +155,13 @@ class RolloutEngine:
         self.conc_window, self._window_next = self._window_next, self.conc_window
         self.launches += 1
 
-    def _collect_overlapped(self, bufs0, lp, chunks, flags) -> None:
+    def join_stop_head(self) -> None:
+        """Makes the current stream wait for the stop head of a collection started with ``join=False``."""
+        if self._head_pending:
+            torch.cuda.current_stream(self.env.device).wait_event(self._streams[5])
+            self._head_pending = False
+
+    def _collect_overlapped(self, bufs0, lp, chunks, flags, join=True, end_event=None) -> None:
         env, dev = self.env, self.env.device
         if self._streams is None:
             lo, hi = torch.cuda.Stream.priority_range()
@@ -177,7 +191,11 @@ class RolloutEngine:
         if self.after_loop is not None:
             self.after_loop(self.buffer, t0)
         head_done.record(head_s)
-        main.wait_event(head_done)
+        if end_event is not None:
+            end_event.record(head_s)
+        self._head_pending = True
+        if join:
+            self.join_stop_head()
 
     def check_nan(self) -> None:
         """model.py:41-43: raise if any logit was NaN during the last rollout(s)."""

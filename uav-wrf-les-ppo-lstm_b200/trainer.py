@@ -60,6 +60,10 @@ class PlumeTrainer:
         self.workspace = UpdateWorkspace(self.device, min(self.minibatch_size, num_envs * horizon))
         self.iteration = 0
         self.last_losses = None
+        # True: the stream goes on behind the lockstep kernels, so that curriculum, flag exchange and GAE (which do not
+        # read the stop head's outputs) run under its last launch, joined before the update.  Measured: 10.12 against
+        # 10.09 ms on one GPU, no difference on two (profiles/r2_notes.md) -- the head's CTAs hold every SM -- so off.
+        self.defer_head_join = False
         n_mb = (num_envs * horizon + self.minibatch_size - 1) // self.minibatch_size
         # my kernels per iteration: rollout (+ deferred stop head), curriculum (count, scan, bin, apply), gae scan +
         # normalise, (weight prep, gradient, clip + Adam) per optimiser step; + sample records and the epoch
@@ -105,9 +109,8 @@ class PlumeTrainer:
         self.check()                               # waits for the previous iteration's error word, not for this one
         if rollout_events is not None:
             rollout_events[0].record(torch.cuda.current_stream(self.device))
-        buf = self.engine.collect()
-        if rollout_events is not None:
-            rollout_events[1].record(torch.cuda.current_stream(self.device))
+        buf = self.engine.collect(join=not self.defer_head_join,
+                                  end_event=rollout_events[1] if rollout_events is not None else None)
         perms = None
         if self._perm_stream is not None:          # launched after the rollout, so its CTAs are placed first
             with torch.cuda.device(self.device):
@@ -119,6 +122,7 @@ class PlumeTrainer:
             self.curriculum.update_from_rollout(buf, self.process_group)
         if perms is not None:
             torch.cuda.current_stream(self.device).wait_event(self._perm_done)
+        self.engine.join_stop_head()
         self.last_losses = update_model(buf, self.model, self.optimizer, cfg=self.cfg,
                                         minibatch_size=self.minibatch_size, workspace=self.workspace,
                                         process_group=self.process_group, perm_seed=self.iteration, perms=perms,
